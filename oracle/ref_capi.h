@@ -1,0 +1,67 @@
+/* oracle/ref_capi.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat C wrapper around the UNMODIFIED reference library (microsoft/SEAL 4.4.3 built from /root/reference by
+ * oracle/Makefile into oracle/_ref/libsealref.so).  It exists so that tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs can drive the reference's own Evaluator on raw uint64 slabs
+ * laid out exactly like seal::Ciphertext::data() ([poly][rns prime][coeff], ciphertext.h:24-37).
+ * The product (seal_b200/, include/) never includes, links or loads this.
+ */
+#ifndef SEALREF_CAPI_H
+#define SEALREF_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sealref_ctx sealref_ctx;
+
+/* scheme: 1 = BFV, 2 = CKKS (seal::scheme_type values, encryptionparams.h).  SEALContext(parms, true, sec none).
+ * Keys come from the reference KeyGenerator with a Blake2xb PRNG seeded with {seed,0,..} => deterministic. */
+sealref_ctx *sealref_create(int scheme, size_t n, const uint64_t *moduli, size_t k, uint64_t plain_modulus, uint64_t seed);
+void sealref_destroy(sealref_ctx *c);
+const char *sealref_last_error(void);
+
+/* default parameter helpers (CoeffModulus::Create / BFVDefault / PlainModulus::Batching) */
+int sealref_coeff_modulus_create(size_t n, const int *bits, size_t k, uint64_t *out);
+int sealref_coeff_modulus_bfv_default(size_t n, uint64_t *out, size_t cap, size_t *k_out);
+uint64_t sealref_plain_modulus_batching(size_t n, int bits);
+
+/* tables, for pinning the oracle/product precomputation */
+size_t sealref_key_prime_count(const sealref_ctx *c);
+int sealref_ntt_root(const sealref_ctx *c, size_t prime_idx, uint64_t *root);
+int sealref_ntt_tables(const sealref_ctx *c, size_t prime_idx, uint64_t *root_powers_operand, uint64_t *root_powers_quotient,
+                       uint64_t *inv_root_powers_operand, uint64_t *inv_degree);
+/* BEHZ auxiliary base at level L: out = [B primes..., m_sk]; returns |Bsk| (0 on error) */
+size_t sealref_base_bsk(const sealref_ctx *c, size_t L, uint64_t *out, size_t cap);
+
+/* keys (flattened [digit j][component 2][key prime K][coeff N]) */
+int sealref_relin_key(sealref_ctx *c, uint64_t *out);                    /* K-1 digits */
+int sealref_galois_key(sealref_ctx *c, uint32_t galois_elt, uint64_t *out); /* generated lazily, cached */
+uint32_t sealref_galois_elt_from_step(const sealref_ctx *c, int step);
+
+/* reference Evaluator ops on raw slabs.  L = number of RNS primes the ciphertext carries (selects the level).
+ * All return 0 on success, <0 on exception (message via sealref_last_error). */
+int sealref_ntt_forward(sealref_ctx *c, size_t L, size_t size, uint64_t *data);   /* Evaluator::transform_to_ntt_inplace */
+int sealref_ntt_inverse(sealref_ctx *c, size_t L, size_t size, uint64_t *data);   /* Evaluator::transform_from_ntt_inplace */
+int sealref_multiply(sealref_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3); /* size2 x size2 -> size3 */
+int sealref_relinearize(sealref_ctx *c, size_t L, const uint64_t *in3, uint64_t *out2);
+int sealref_multiply_relin(sealref_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out2);
+int sealref_rescale(sealref_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2);   /* out has L-1 primes (CKKS) */
+int sealref_mod_switch(sealref_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2); /* BFV: divide-round; CKKS: drop */
+int sealref_apply_galois(sealref_ctx *c, size_t L, const uint64_t *in2, uint32_t galois_elt, uint64_t *out2);
+int sealref_rotate(sealref_ctx *c, size_t L, const uint64_t *in2, int step, uint64_t *out2); /* rotate_rows / rotate_vector */
+
+/* semantic round trip helpers (BFV batching): encrypt a vector of n slots, decrypt; for drop-in demos */
+int sealref_bfv_encrypt(sealref_ctx *c, const uint64_t *slots, uint64_t *out2);
+int sealref_bfv_decrypt(sealref_ctx *c, size_t L, size_t size, const uint64_t *ct, uint64_t *slots, int *noise_budget);
+
+/* CPU baseline: run `op` (0 = multiply+relinearize, 1 = ntt fwd+inv of a size-2 ct, 2 = rotate one step,
+ * 3 = rescale, 4 = bfv multiply) on `threads` host threads, each on its own uniform-random ciphertexts with a thread-local
+ * memory pool, until every thread has done `reps` ops; returns wall seconds (<0 on error). */
+double sealref_time_op(sealref_ctx *c, int op, size_t L, int threads, int reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,718 @@
+/* oracle/seal_oracle.c -- TEST INFRASTRUCTURE ONLY (see seal_oracle.h for the contract and how it is pinned).
+ *
+ * Plain restatement of the reference hot path with `unsigned __int128 %` arithmetic.  Paths in comments are relative
+ * to /root/reference/native/src/seal/.  Nothing here is tuned; clarity over speed.
+ */
+#include "seal_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+
+/* ------------------------------------------------------------------ scalar helpers (util/uintarithsmallmod.h) -- */
+static u64 mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+static u64 addmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a + b) % q); }
+static u64 submod(u64 a, u64 b, u64 q) { return (u64)(((u128)(a % q) + q - (b % q)) % q); }
+static u64 powmod(u64 a, u64 e, u64 q)
+{
+    u64 r = 1 % q;
+    a %= q;
+    while (e)
+    {
+        if (e & 1)
+            r = mulmod(r, a, q);
+        a = mulmod(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+/* modular inverse for any modulus coprime to a (extended Euclid; needed for m_tilde = 2^32 and 2n) */
+static int invmod(u64 a, u64 m, u64 *out)
+{
+    __int128 t = 0, nt = 1, r = m, nr = a % m;
+    while (nr)
+    {
+        __int128 qq = r / nr, tmp = t - qq * nt;
+        t = nt, nt = tmp;
+        tmp = r - qq * nr;
+        r = nr, nr = tmp;
+    }
+    if (r != 1)
+        return 0;
+    if (t < 0)
+        t += m;
+    *out = (u64)t;
+    return 1;
+}
+static u64 reverse_bits(u64 x, int bits)
+{
+    u64 r = 0;
+    for (int i = 0; i < bits; i++)
+        r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+static int ilog2(size_t n)
+{
+    int l = 0;
+    while (((size_t)1 << l) < n)
+        l++;
+    return l;
+}
+
+/* ------------------------------------------------------------------------------- number theory (util/numth.cpp) -- */
+/* numth.cpp:180-277 is a probabilistic Miller-Rabin; primality is a fact, so we use the deterministic base set that
+ * is exact for all 64-bit integers. */
+int orc_is_prime(u64 v)
+{
+    static const u64 small[] = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37 };
+    if (v < 2)
+        return 0;
+    for (size_t i = 0; i < 12; i++)
+    {
+        if (v == small[i])
+            return 1;
+        if (v % small[i] == 0)
+            return 0;
+    }
+    u64 d = v - 1;
+    int r = 0;
+    while (!(d & 1))
+        d >>= 1, r++;
+    for (size_t i = 0; i < 12; i++)
+    {
+        u64 x = powmod(small[i], d, v);
+        if (x == 1 || x == v - 1)
+            continue;
+        int ok = 0;
+        for (int j = 1; j < r; j++)
+        {
+            x = mulmod(x, x, v);
+            if (x == v - 1)
+            {
+                ok = 1;
+                break;
+            }
+        }
+        if (!ok)
+            return 0;
+    }
+    return 1;
+}
+
+/* numth.cpp:278-311: primes = 1 mod factor, scanning down from 2^bit_size */
+int orc_get_primes(u64 factor, int bit_size, size_t count, u64 *out)
+{
+    u64 value = (((u64)1 << bit_size) - 1) / factor * factor + 1;
+    u64 lower = (u64)1 << (bit_size - 1);
+    size_t found = 0;
+    while (found < count && value > lower)
+    {
+        if (orc_is_prime(value))
+            out[found++] = value;
+        value -= factor;
+    }
+    return found == count ? 0 : -1;
+}
+
+/* modulus.cpp:144-184: per distinct bit size take the `count` largest primes; hand them out smallest-first */
+int orc_coeff_modulus_create(size_t n, const int *bits, size_t k, u64 *out)
+{
+    int used[ORC_MAX_PRIMES] = { 0 };
+    if (k > ORC_MAX_PRIMES)
+        return -1;
+    for (size_t i = 0; i < k; i++)
+    {
+        if (used[i])
+            continue;
+        size_t cnt = 0, idx[ORC_MAX_PRIMES];
+        for (size_t j = i; j < k; j++)
+            if (bits[j] == bits[i])
+                idx[cnt++] = j, used[j] = 1;
+        u64 primes[ORC_MAX_PRIMES];
+        if (orc_get_primes(2 * (u64)n, bits[i], cnt, primes))
+            return -1;
+        for (size_t j = 0; j < cnt; j++)
+            out[idx[j]] = primes[cnt - 1 - j];
+    }
+    return 0;
+}
+
+/* numth.cpp:340-412: the reference draws a random primitive root and then walks all odd powers keeping the minimum;
+ * the minimum over the full set of primitive degree-th roots does not depend on the starting point, so we start from
+ * the first small generator candidate that works. */
+int orc_minimal_primitive_root(u64 degree, u64 q, u64 *root)
+{
+    if ((q - 1) % degree)
+        return -1;
+    u64 quot = (q - 1) / degree, r = 0;
+    for (u64 g = 2; g < 1000; g++)
+    {
+        r = powmod(g, quot, q);
+        if (powmod(r, degree >> 1, q) == q - 1)
+            break;
+        r = 0;
+    }
+    if (!r)
+        return -1;
+    u64 gsq = mulmod(r, r, q), cur = r, best = r;
+    for (u64 i = 0; i < degree; i += 2)
+    {
+        if (cur < best)
+            best = cur;
+        cur = mulmod(cur, gsq, q);
+    }
+    *root = best;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------- NTT tables -- */
+typedef struct
+{
+    u64 q, root, inv_n;
+    u64 *rp;  /* root_powers[bitrev(i)] = psi^i            ntt.cpp:269-278 */
+    u64 *irp; /* inv_root_powers[bitrev(i-1)+1] = psi^-i   ntt.cpp:280-288 */
+} orc_tab;
+
+static int tab_init(orc_tab *t, size_t n, u64 q)
+{
+    int logn = ilog2(n);
+    t->q = q;
+    if (orc_minimal_primitive_root(2 * (u64)n, q, &t->root)) /* ntt.cpp:254 */
+        return -1;
+    u64 inv_root = 0;
+    if (!invmod(t->root, q, &inv_root))
+        return -1;
+    t->rp = (u64 *)malloc(n * sizeof(u64));
+    t->irp = (u64 *)malloc(n * sizeof(u64));
+    u64 p = t->root;
+    for (size_t i = 1; i < n; i++)
+    {
+        t->rp[reverse_bits(i, logn)] = p;
+        p = mulmod(p, t->root, q);
+    }
+    t->rp[0] = 1;
+    p = inv_root;
+    for (size_t i = 1; i < n; i++)
+    {
+        t->irp[reverse_bits(i - 1, logn) + 1] = p;
+        p = mulmod(p, inv_root, q);
+    }
+    t->irp[0] = 1;
+    if (!invmod((u64)n % q, q, &t->inv_n)) /* ntt.cpp:290-296 */
+        return -1;
+    return 0;
+}
+static void tab_free(orc_tab *t)
+{
+    free(t->rp);
+    free(t->irp);
+    t->rp = t->irp = NULL;
+}
+
+/* dwthandler.h:94-191 (Cooley-Tukey, natural in -> bit-reversed out, roots consumed sequentially from index 1) */
+static void ntt_fwd(const orc_tab *t, size_t n, u64 *x)
+{
+    u64 q = t->q;
+    size_t gap = n >> 1, m = 1, ridx = 0;
+    for (; m < n; m <<= 1, gap >>= 1)
+    {
+        size_t off = 0;
+        for (size_t i = 0; i < m; i++, off += 2 * gap)
+        {
+            u64 r = t->rp[++ridx];
+            for (size_t j = 0; j < gap; j++)
+            {
+                u64 u = x[off + j] % q, v = mulmod(x[off + j + gap], r, q);
+                x[off + j] = addmod(u, v, q);
+                x[off + j + gap] = submod(u, v, q);
+            }
+        }
+    }
+}
+/* dwthandler.h:202-356 (Gentleman-Sande, bit-reversed in -> natural out, 1/n folded into the last stage) */
+static void ntt_inv(const orc_tab *t, size_t n, u64 *x)
+{
+    u64 q = t->q;
+    size_t gap = 1, m = n >> 1, ridx = 0;
+    for (; m >= 1; m >>= 1, gap <<= 1)
+    {
+        size_t off = 0;
+        for (size_t i = 0; i < m; i++, off += 2 * gap)
+        {
+            u64 r = t->irp[++ridx];
+            for (size_t j = 0; j < gap; j++)
+            {
+                u64 u = x[off + j] % q, v = x[off + j + gap] % q;
+                x[off + j] = addmod(u, v, q);
+                x[off + j + gap] = mulmod(submod(u, v, q), r, q);
+            }
+        }
+        if (m == 1)
+            break;
+    }
+    for (size_t i = 0; i < n; i++)
+        x[i] = mulmod(x[i], t->inv_n, q);
+}
+
+/* ---------------------------------------------------------------------------------------------------- context -- */
+struct orc_ctx
+{
+    int scheme;
+    size_t n, k;
+    int logn;
+    u64 q[ORC_MAX_PRIMES], t;
+    orc_tab tab[ORC_MAX_PRIMES];
+};
+
+orc_ctx *orc_create(int scheme, size_t n, const u64 *moduli, size_t k, u64 t)
+{
+    if (k == 0 || k > ORC_MAX_PRIMES || n < 2 || (n & (n - 1)))
+        return NULL;
+    orc_ctx *c = (orc_ctx *)calloc(1, sizeof(orc_ctx));
+    c->scheme = scheme, c->n = n, c->k = k, c->t = t, c->logn = ilog2(n);
+    for (size_t i = 0; i < k; i++)
+    {
+        c->q[i] = moduli[i];
+        if (tab_init(&c->tab[i], n, moduli[i]))
+        {
+            orc_destroy(c);
+            return NULL;
+        }
+    }
+    return c;
+}
+void orc_destroy(orc_ctx *c)
+{
+    if (!c)
+        return;
+    for (size_t i = 0; i < c->k; i++)
+        tab_free(&c->tab[i]);
+    free(c);
+}
+int orc_ntt_tables(const orc_ctx *c, size_t i, u64 *root, u64 *rp, u64 *irp, u64 *inv_n)
+{
+    if (i >= c->k)
+        return -1;
+    *root = c->tab[i].root;
+    *inv_n = c->tab[i].inv_n;
+    memcpy(rp, c->tab[i].rp, c->n * sizeof(u64));
+    memcpy(irp, c->tab[i].irp, c->n * sizeof(u64));
+    return 0;
+}
+
+void orc_ntt_row(const orc_ctx *c, size_t i, u64 *row) { ntt_fwd(&c->tab[i], c->n, row); }
+void orc_intt_row(const orc_ctx *c, size_t i, u64 *row) { ntt_inv(&c->tab[i], c->n, row); }
+
+void orc_ntt_forward(const orc_ctx *c, size_t L, size_t size, u64 *d)
+{
+    for (size_t p = 0; p < size; p++)
+        for (size_t i = 0; i < L; i++)
+            ntt_fwd(&c->tab[i], c->n, d + (p * L + i) * c->n);
+}
+void orc_ntt_inverse(const orc_ctx *c, size_t L, size_t size, u64 *d)
+{
+    for (size_t p = 0; p < size; p++)
+        for (size_t i = 0; i < L; i++)
+            ntt_inv(&c->tab[i], c->n, d + (p * L + i) * c->n);
+}
+
+/* ---------------------------------------------------------------------- CKKS multiply (evaluator.cpp:634-662) -- */
+void orc_ckks_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64 *o)
+{
+    size_t n = c->n, P = L * n;
+    for (size_t i = 0; i < L; i++)
+    {
+        u64 q = c->q[i];
+        for (size_t j = 0; j < n; j++)
+        {
+            size_t e = i * n + j;
+            u64 x0 = a[e], x1 = a[P + e], y0 = b[e], y1 = b[P + e];
+            o[e] = mulmod(x0, y0, q);
+            o[P + e] = addmod(mulmod(x0, y1, q), mulmod(x1, y0, q), q);
+            o[2 * P + e] = mulmod(x1, y1, q);
+        }
+    }
+}
+
+/* -------------------------------------------------------------------- key switching (evaluator.cpp:2561-2867) -- */
+void orc_switch_key(const orc_ctx *c, size_t L, u64 *ct, const u64 *target, const u64 *key)
+{
+    size_t n = c->n, K = c->k, sp = K - 1;
+    int ntt_in = (c->scheme != ORC_BFV);
+    /* :2651-2658  d_J = coefficients of the J-th RNS component */
+    u64 *d = (u64 *)malloc(L * n * sizeof(u64));
+    memcpy(d, target, L * n * sizeof(u64));
+    if (ntt_in)
+        for (size_t J = 0; J < L; J++)
+            ntt_inv(&c->tab[J], n, d + J * n);
+    u64 *prod = (u64 *)calloc(2 * (L + 1) * n, sizeof(u64)); /* t_poly_prod [2][L+1][n] */
+    u64 *tmp = (u64 *)malloc(n * sizeof(u64));
+    for (size_t I = 0; I <= L; I++)
+    {
+        size_t ki = (I == L) ? sp : I; /* :2664 */
+        u64 q = c->q[ki];
+        for (size_t J = 0; J < L; J++)
+        {
+            /* :2682-2702  digit J seen modulo q_I, in NTT form */
+            if (ntt_in && I == J)
+                memcpy(tmp, target + J * n, n * sizeof(u64));
+            else
+            {
+                for (size_t j = 0; j < n; j++)
+                    tmp[j] = d[J * n + j] % q;
+                ntt_fwd(&c->tab[ki], n, tmp);
+            }
+            /* :2705-2729  multiply-accumulate with key[J][comp][ki] */
+            for (size_t comp = 0; comp < 2; comp++)
+            {
+                const u64 *kr = key + ((J * 2 + comp) * K + ki) * n;
+                u64 *acc = prod + (comp * (L + 1) + I) * n;
+                for (size_t j = 0; j < n; j++)
+                    acc[j] = addmod(acc[j], mulmod(tmp[j] % q, kr[j], q), q);
+            }
+        }
+    }
+    /* :2806-2864 mod-down by the special prime, added into ct */
+    u64 qk = c->q[sp], half = qk >> 1;
+    for (size_t comp = 0; comp < 2; comp++)
+    {
+        u64 *last = prod + (comp * (L + 1) + L) * n;
+        ntt_inv(&c->tab[sp], n, last);
+        for (size_t j = 0; j < n; j++)
+            last[j] = addmod(last[j], half, qk); /* :2813-2817 */
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 q = c->q[i];
+            u64 *acc = prod + (comp * (L + 1) + i) * n;
+            for (size_t j = 0; j < n; j++)
+                tmp[j] = submod(last[j] % q, half % q, q); /* :2824-2836 */
+            if (c->scheme == ORC_CKKS)
+                ntt_fwd(&c->tab[i], n, tmp); /* :2842 */
+            else
+                ntt_inv(&c->tab[i], n, acc); /* :2854 (BFV: accumulated poly back to coefficients) */
+            u64 inv = 0;
+            invmod(qk % q, q, &inv); /* inv_q_last_mod_q of the key level, rns.cpp:767-776 */
+            u64 *dst = ct + (comp * L + i) * n;
+            for (size_t j = 0; j < n; j++)
+                dst[j] = addmod(dst[j], mulmod(submod(acc[j], tmp[j], q), inv, q), q); /* :2858-2863 */
+        }
+    }
+    free(d), free(prod), free(tmp);
+}
+
+/* evaluator.cpp:1144-1199 (size 3 -> 2) */
+void orc_relinearize(const orc_ctx *c, size_t L, const u64 *in3, const u64 *key, u64 *out2)
+{
+    size_t P = L * c->n;
+    memcpy(out2, in3, 2 * P * sizeof(u64));
+    orc_switch_key(c, L, out2, in3 + 2 * P, key);
+}
+
+/* CKKS rescale: rns.cpp:830-901 + evaluator.cpp:1276-1279 (drop last component) */
+void orc_rescale(const orc_ctx *c, size_t L, const u64 *in2, u64 *out2)
+{
+    size_t n = c->n;
+    u64 ql = c->q[L - 1], half = ql >> 1;
+    u64 *last = (u64 *)malloc(n * sizeof(u64)), *tmp = (u64 *)malloc(n * sizeof(u64));
+    for (size_t p = 0; p < 2; p++)
+    {
+        memcpy(last, in2 + (p * L + L - 1) * n, n * sizeof(u64));
+        ntt_inv(&c->tab[L - 1], n, last);
+        for (size_t j = 0; j < n; j++)
+            last[j] = addmod(last[j], half, ql);
+        for (size_t i = 0; i + 1 < L; i++)
+        {
+            u64 q = c->q[i], inv = 0;
+            invmod(ql % q, q, &inv);
+            for (size_t j = 0; j < n; j++)
+                tmp[j] = submod(last[j] % q, half % q, q);
+            ntt_fwd(&c->tab[i], n, tmp);
+            const u64 *src = in2 + (p * L + i) * n;
+            u64 *dst = out2 + (p * (L - 1) + i) * n;
+            for (size_t j = 0; j < n; j++)
+                dst[j] = mulmod(submod(src[j], tmp[j], q), inv, q);
+        }
+    }
+    free(last), free(tmp);
+}
+
+/* BFV mod_switch_to_next: rns.cpp:789-828 (coefficient form) */
+void orc_bfv_mod_switch(const orc_ctx *c, size_t L, const u64 *in2, u64 *out2)
+{
+    size_t n = c->n;
+    u64 ql = c->q[L - 1], half = ql >> 1;
+    for (size_t p = 0; p < 2; p++)
+        for (size_t i = 0; i + 1 < L; i++)
+        {
+            u64 q = c->q[i], inv = 0;
+            invmod(ql % q, q, &inv);
+            const u64 *last = in2 + (p * L + L - 1) * n, *src = in2 + (p * L + i) * n;
+            u64 *dst = out2 + (p * (L - 1) + i) * n;
+            for (size_t j = 0; j < n; j++)
+            {
+                u64 l = addmod(last[j], half, ql);
+                dst[j] = mulmod(submod(src[j], submod(l % q, half % q, q), q), inv, q);
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------- Galois (util/galois.cpp) -- */
+uint32_t orc_galois_elt_from_step(size_t n, int step) /* galois.cpp:53-95 */
+{
+    uint64_t m = 2 * (uint64_t)n;
+    if (step == 0)
+        return (uint32_t)(m - 1);
+    int sign = step < 0;
+    uint32_t pos = (uint32_t)(sign ? -step : step);
+    if (pos >= (n >> 1))
+        return 0;
+    int s = sign ? (int)(n >> 1) - (int)pos : (int)pos;
+    uint64_t e = 1;
+    while (s--)
+        e = (e * 3) & (m - 1);
+    return (uint32_t)e;
+}
+void orc_galois_coeff_row(size_t n, u64 q, uint32_t g, const u64 *in, u64 *out) /* galois.cpp:148-190 */
+{
+    int logn = ilog2(n);
+    for (u64 i = 0; i < n; i++)
+    {
+        u64 raw = i * g, idx = raw & (n - 1), v = in[i];
+        if ((raw >> logn) & 1)
+            v = v ? q - v : 0;
+        out[idx] = v;
+    }
+}
+void orc_galois_ntt_row(size_t n, uint32_t g, const u64 *in, u64 *out) /* galois.cpp:18-51, 192-218 */
+{
+    int logn = ilog2(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        u64 rev = reverse_bits(i + n, logn + 1);
+        u64 raw = ((u64)g * rev) >> 1;
+        raw &= (n - 1);
+        out[i] = in[reverse_bits(raw, logn)];
+    }
+}
+/* evaluator.cpp:2384-2502 */
+void orc_apply_galois(const orc_ctx *c, size_t L, const u64 *in2, uint32_t g, const u64 *key, u64 *out2)
+{
+    size_t n = c->n, P = L * n;
+    u64 *temp = (u64 *)malloc(P * sizeof(u64));
+    for (size_t i = 0; i < L; i++)
+    {
+        if (c->scheme == ORC_BFV)
+        {
+            orc_galois_coeff_row(n, c->q[i], g, in2 + i * n, out2 + i * n);
+            orc_galois_coeff_row(n, c->q[i], g, in2 + P + i * n, temp + i * n);
+        }
+        else
+        {
+            orc_galois_ntt_row(n, g, in2 + i * n, out2 + i * n);
+            orc_galois_ntt_row(n, g, in2 + P + i * n, temp + i * n);
+        }
+    }
+    memset(out2 + P, 0, P * sizeof(u64));
+    orc_switch_key(c, L, out2, temp, key);
+    free(temp);
+}
+
+/* ------------------------------------------------------------------------------ BEHZ (util/rns.cpp, BFV only) -- */
+/* bit length of prod(q[0..L)) via a tiny big-integer (rns.cpp:605) */
+static int prod_bit_count(const u64 *q, size_t L)
+{
+    u64 limbs[ORC_MAX_PRIMES + 1] = { 1 };
+    size_t len = 1;
+    for (size_t i = 0; i < L; i++)
+    {
+        u64 carry = 0;
+        for (size_t j = 0; j < len; j++)
+        {
+            u128 v = (u128)limbs[j] * q[i] + carry;
+            limbs[j] = (u64)v;
+            carry = (u64)(v >> 64);
+        }
+        if (carry)
+            limbs[len++] = carry;
+    }
+    int bits = 0;
+    u64 top = limbs[len - 1];
+    while (top)
+        bits++, top >>= 1;
+    return (int)(len - 1) * 64 + bits;
+}
+static int bit_count(u64 v)
+{
+    int b = 0;
+    while (v)
+        b++, v >>= 1;
+    return b;
+}
+typedef struct
+{
+    size_t nB, nBsk;
+    u64 B[ORC_MAX_PRIMES + 1], msk, Bsk[ORC_MAX_PRIMES + 2];
+} behz_base;
+static int behz_base_init(const orc_ctx *c, size_t L, behz_base *b)
+{
+    /* rns.cpp:598-641 */
+    b->nB = L;
+    if (32 + bit_count(c->t) + prod_bit_count(c->q, L) >= 61 * (int)L + 61)
+        b->nB++;
+    b->nBsk = b->nB + 1;
+    u64 primes[ORC_MAX_PRIMES + 4];
+    if (orc_get_primes(2 * (u64)c->n, 61, b->nBsk + 1, primes))
+        return -1;
+    b->msk = primes[0]; /* primes[1] = gamma (decryption only) */
+    for (size_t i = 0; i < b->nB; i++)
+        b->B[i] = b->Bsk[i] = primes[2 + i];
+    b->Bsk[b->nB] = b->msk;
+    return 0;
+}
+size_t orc_base_bsk(const orc_ctx *c, size_t L, u64 *out)
+{
+    behz_base b;
+    if (behz_base_init(c, L, &b))
+        return 0;
+    memcpy(out, b.Bsk, b.nBsk * sizeof(u64));
+    return b.nBsk;
+}
+/* prod_{j != skip} base[j] mod p  (skip = (size_t)-1 for the full product) */
+static u64 prod_mod(const u64 *base, size_t nb, size_t skip, u64 p)
+{
+    u64 r = 1 % p;
+    for (size_t j = 0; j < nb; j++)
+        if (j != skip)
+            r = mulmod(r, base[j] % p, p);
+    return r;
+}
+/* FastBConv, rns.cpp:418-463: y = sum_i [x_i * (b/b_i)^-1 mod b_i] * ((b/b_i) mod p) mod p   (no correction term) */
+static void fastbconv(const u64 *ibase, size_t ni, const u64 *x, size_t xstride, size_t n, u64 p, u64 *out)
+{
+    u64 inv[ORC_MAX_PRIMES + 2], mat[ORC_MAX_PRIMES + 2];
+    for (size_t i = 0; i < ni; i++)
+    {
+        invmod(prod_mod(ibase, ni, i, ibase[i]), ibase[i], &inv[i]);
+        mat[i] = prod_mod(ibase, ni, i, p);
+    }
+    for (size_t j = 0; j < n; j++)
+    {
+        u128 s = 0;
+        for (size_t i = 0; i < ni; i++)
+        {
+            u64 ti = mulmod(x[i * xstride + j] % ibase[i], inv[i], ibase[i]);
+            s = (s + (u128)ti * mat[i]) % p;
+        }
+        out[j] = (u64)s;
+    }
+}
+
+int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64 *out3)
+{
+    size_t n = c->n;
+    behz_base bb;
+    if (c->scheme != ORC_BFV || behz_base_init(c, L, &bb))
+        return -1;
+    size_t nB = bb.nB, nS = bb.nBsk;
+    const u64 mt = (u64)1 << 32; /* m_tilde, rns.cpp:635 */
+    orc_tab *stab = (orc_tab *)calloc(nS, sizeof(orc_tab));
+    for (size_t i = 0; i < nS; i++)
+        if (tab_init(&stab[i], n, bb.Bsk[i]))
+            return -1;
+    /* steps (1)-(3), evaluator.cpp:456-474, for the 4 input polys: [0,1] of a then [0,1] of b */
+    u64 *xq = (u64 *)malloc(4 * L * n * sizeof(u64)), *xs = (u64 *)malloc(4 * nS * n * sizeof(u64));
+    u64 *tmp = (u64 *)malloc(L * n * sizeof(u64)), *ymt = (u64 *)malloc(n * sizeof(u64));
+    u64 qinv_mt = 0;
+    invmod(prod_mod(c->q, L, (size_t)-1, mt), mt, &qinv_mt);
+    u64 neg_inv_q_mt = (mt - qinv_mt) % mt; /* rns.cpp:724-730 */
+    for (size_t p = 0; p < 4; p++)
+    {
+        const u64 *src = (p < 2 ? a : b) + (p & 1) * L * n;
+        for (size_t i = 0; i < L; i++)
+        {
+            memcpy(xq + (p * L + i) * n, src + i * n, n * sizeof(u64));
+            ntt_fwd(&c->tab[i], n, xq + (p * L + i) * n);
+            for (size_t j = 0; j < n; j++)
+                tmp[i * n + j] = mulmod(src[i * n + j], mt % c->q[i], c->q[i]); /* rns.cpp:1123-1124 */
+        }
+        fastbconv(c->q, L, tmp, n, n, mt, ymt); /* rns.cpp:1130 */
+        for (size_t s = 0; s < nS; s++)
+        {
+            u64 P = bb.Bsk[s], inv_mt = 0, qmodP = prod_mod(c->q, L, (size_t)-1, P);
+            invmod(mt % P, P, &inv_mt);
+            u64 *dst = xs + (p * nS + s) * n;
+            fastbconv(c->q, L, tmp, n, n, P, dst); /* rns.cpp:1127 */
+            for (size_t j = 0; j < n; j++)        /* sm_mrq, rns.cpp:1015-1037 */
+            {
+                u64 r = (u64)(((u128)ymt[j] * neg_inv_q_mt) % mt);
+                if (r >= (mt >> 1))
+                    r += P - mt;
+                dst[j] = mulmod(addmod(mulmod(r, qmodP, P), dst[j], P), inv_mt, P);
+            }
+            ntt_fwd(&stab[s], n, dst);
+        }
+    }
+    /* step (4) tensor, :497-541; (5) INTT :545-546; (6) times t :554-556 */
+    u64 *dq = (u64 *)malloc(3 * L * n * sizeof(u64)), *ds = (u64 *)malloc(3 * nS * n * sizeof(u64));
+    for (int base = 0; base < 2; base++)
+    {
+        size_t nb = base ? nS : L;
+        u64 *x = base ? xs : xq, *d = base ? ds : dq;
+        for (size_t i = 0; i < nb; i++)
+        {
+            u64 P = base ? bb.Bsk[i] : c->q[i];
+            const orc_tab *t = base ? &stab[i] : &c->tab[i];
+            u64 *x0 = x + (0 * nb + i) * n, *x1 = x + (1 * nb + i) * n, *y0 = x + (2 * nb + i) * n,
+                *y1 = x + (3 * nb + i) * n;
+            for (size_t j = 0; j < n; j++)
+            {
+                d[(0 * nb + i) * n + j] = mulmod(x0[j], y0[j], P);
+                d[(1 * nb + i) * n + j] = addmod(mulmod(x0[j], y1[j], P), mulmod(x1[j], y0[j], P), P);
+                d[(2 * nb + i) * n + j] = mulmod(x1[j], y1[j], P);
+            }
+            for (size_t p = 0; p < 3; p++)
+            {
+                ntt_inv(t, n, d + (p * nb + i) * n);
+                for (size_t j = 0; j < n; j++)
+                    d[(p * nb + i) * n + j] = mulmod(d[(p * nb + i) * n + j], c->t % P, P);
+            }
+        }
+    }
+    /* steps (7) fast_floor rns.cpp:1041-1084 and (8) fastbconv_sk rns.cpp:903-977 */
+    u64 *f = (u64 *)malloc(nS * n * sizeof(u64)), *conv = (u64 *)malloc(n * sizeof(u64)), *alpha = (u64 *)malloc(n * sizeof(u64));
+    for (size_t p = 0; p < 3; p++)
+    {
+        for (size_t s = 0; s < nS; s++)
+        {
+            u64 P = bb.Bsk[s], invq = 0;
+            invmod(prod_mod(c->q, L, (size_t)-1, P), P, &invq);
+            fastbconv(c->q, L, dq + p * L * n, n, n, P, conv);
+            for (size_t j = 0; j < n; j++)
+                f[s * n + j] = mulmod(submod(ds[(p * nS + s) * n + j], conv[j], P), invq, P);
+        }
+        u64 invB = 0;
+        invmod(prod_mod(bb.B, nB, (size_t)-1, bb.msk), bb.msk, &invB);
+        fastbconv(bb.B, nB, f, n, n, bb.msk, conv);
+        for (size_t j = 0; j < n; j++)
+            alpha[j] = mulmod(submod(conv[j], f[nB * n + j], bb.msk), invB, bb.msk); /* :946-949 */
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 q = c->q[i], prodB = prod_mod(bb.B, nB, (size_t)-1, q);
+            u64 *dst = out3 + (p * L + i) * n;
+            fastbconv(bb.B, nB, f, n, n, q, dst);
+            for (size_t j = 0; j < n; j++)
+            {
+                if (alpha[j] > (bb.msk >> 1)) /* :964 */
+                    dst[j] = addmod(dst[j], mulmod((bb.msk - alpha[j]) % q, prodB, q), q);
+                else
+                    dst[j] = addmod(dst[j], mulmod(alpha[j] % q, q - prodB, q), q);
+            }
+        }
+    }
+    free(f), free(conv), free(alpha), free(dq), free(ds), free(xq), free(xs), free(tmp), free(ymt);
+    for (size_t i = 0; i < nS; i++)
+        tab_free(&stab[i]);
+    free(stab);
+    return 0;
+}

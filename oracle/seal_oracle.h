@@ -1,0 +1,66 @@
+/* oracle/seal_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C CPU restatement of the reference's (microsoft/SEAL 4.4.3) RNS-polynomial hot path, written with fully
+ * reduced `unsigned __int128 %` arithmetic (no Shoup/Barrett/lazy ranges) so that it is an independent statement of
+ * WHAT the reference computes.  Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/native/src/seal/).
+ *
+ * PINNING: tests/test_oracle_*.py check this file against (i) the reference's in-source known-answer tests
+ * (tests/seal/util/ntt.cpp:53-100, tests/seal/util/galois.cpp:86-120), (ii) golden vectors generated from the real
+ * reference in the build container (tests/golden/, generator tests/golden/make_golden.py) and (iii) live outputs of
+ * oracle/_ref/libsealref.so (the reference compiled from its own sources) wherever that library is present.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this; the product never does.
+ */
+#ifndef SEAL_ORACLE_H
+#define SEAL_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_BFV 1
+#define ORC_CKKS 2
+#define ORC_MAX_PRIMES 64
+
+typedef struct orc_ctx orc_ctx;
+
+/* number theory (util/numth.cpp) */
+int orc_is_prime(uint64_t v);
+int orc_get_primes(uint64_t factor, int bit_size, size_t count, uint64_t *out);           /* numth.cpp:278-311 */
+int orc_minimal_primitive_root(uint64_t degree, uint64_t q, uint64_t *root);              /* numth.cpp:340-412 */
+int orc_coeff_modulus_create(size_t n, const int *bits, size_t k, uint64_t *out);         /* modulus.cpp:144-184 */
+
+/* context: moduli = the key-level coeff_modulus (k primes, last = special prime); t = plain modulus (BFV) */
+orc_ctx *orc_create(int scheme, size_t n, const uint64_t *moduli, size_t k, uint64_t t);
+void orc_destroy(orc_ctx *c);
+/* tables of prime i, ntt.cpp:241-300 */
+int orc_ntt_tables(const orc_ctx *c, size_t i, uint64_t *root, uint64_t *root_powers, uint64_t *inv_root_powers, uint64_t *inv_n);
+/* BEHZ auxiliary base at level L: [B..., m_sk]; returns |Bsk| (rns.cpp:598-641) */
+size_t orc_base_bsk(const orc_ctx *c, size_t L, uint64_t *out);
+
+/* single-row transforms with explicit modulus index (ntt.cpp:394-475 / dwthandler.h:94-356); canonical outputs */
+void orc_ntt_row(const orc_ctx *c, size_t prime_idx, uint64_t *row);
+void orc_intt_row(const orc_ctx *c, size_t prime_idx, uint64_t *row);
+
+/* slab ops; slabs are [size][L][n] like seal::Ciphertext::data() */
+void orc_ntt_forward(const orc_ctx *c, size_t L, size_t size, uint64_t *data);            /* evaluator.cpp:2289-2335 */
+void orc_ntt_inverse(const orc_ctx *c, size_t L, size_t size, uint64_t *data);            /* evaluator.cpp:2337-2382 */
+void orc_ckks_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3); /* evaluator.cpp:569-708 */
+int orc_bfv_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3);   /* evaluator.cpp:395-567 */
+/* ct (size 2, updated in place) += key-switch of target ([L][n]); key = [L digits][2][k][n]; evaluator.cpp:2561-2867 */
+void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct2, const uint64_t *target, const uint64_t *key);
+void orc_relinearize(const orc_ctx *c, size_t L, const uint64_t *in3, const uint64_t *key, uint64_t *out2); /* evaluator.cpp:1144-1199 */
+void orc_rescale(const orc_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2);        /* CKKS; rns.cpp:830-901, evaluator.cpp:1201-1294 */
+void orc_bfv_mod_switch(const orc_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2); /* BFV; rns.cpp:789-828 */
+void orc_apply_galois(const orc_ctx *c, size_t L, const uint64_t *in2, uint32_t galois_elt, const uint64_t *key, uint64_t *out2); /* evaluator.cpp:2384-2502 */
+uint32_t orc_galois_elt_from_step(size_t n, int step);                                    /* galois.cpp:53-95 */
+/* bare permutations (galois.cpp:148-218) on one row */
+void orc_galois_coeff_row(size_t n, uint64_t q, uint32_t galois_elt, const uint64_t *in, uint64_t *out);
+void orc_galois_ntt_row(size_t n, uint32_t galois_elt, const uint64_t *in, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

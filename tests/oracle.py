@@ -1,0 +1,172 @@
+"""ctypes driver for oracle/liboracle.so (the plain-C restatement, oracle/seal_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "..", "oracle")
+_LIB_PATH = os.path.join(_DIR, "liboracle.so")
+BFV, CKKS = 1, 2
+_u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_DIR, "seal_oracle.c")
+        if not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(_LIB_PATH)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_size_t, _u64p, C.c_size_t, C.c_uint64]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_is_prime.argtypes = [C.c_uint64]
+        L.orc_get_primes.argtypes = [C.c_uint64, C.c_int, C.c_size_t, _u64p]
+        L.orc_minimal_primitive_root.argtypes = [C.c_uint64, C.c_uint64, _u64p]
+        L.orc_coeff_modulus_create.argtypes = [C.c_size_t, C.POINTER(C.c_int), C.c_size_t, _u64p]
+        L.orc_ntt_tables.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p, _u64p]
+        L.orc_base_bsk.restype = C.c_size_t
+        L.orc_base_bsk.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.orc_ntt_row.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.orc_intt_row.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.orc_ntt_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
+        L.orc_ntt_inverse.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
+        L.orc_ckks_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.orc_bfv_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.orc_switch_key.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.orc_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.orc_rescale.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.orc_bfv_mod_switch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.orc_apply_galois.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_uint32, _u64p, _u64p]
+        L.orc_galois_elt_from_step.restype = C.c_uint32
+        L.orc_galois_elt_from_step.argtypes = [C.c_size_t, C.c_int]
+        L.orc_galois_coeff_row.argtypes = [C.c_size_t, C.c_uint64, C.c_uint32, _u64p, _u64p]
+        L.orc_galois_ntt_row.argtypes = [C.c_size_t, C.c_uint32, _u64p, _u64p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+def get_primes(factor, bits, count):
+    out = np.zeros(count, dtype=np.uint64)
+    if lib().orc_get_primes(factor, bits, count, _p(out)):
+        raise RuntimeError("not enough primes")
+    return [int(x) for x in out]
+
+
+def coeff_modulus_create(n, bits):
+    out = np.zeros(len(bits), dtype=np.uint64)
+    b = (C.c_int * len(bits))(*bits)
+    if lib().orc_coeff_modulus_create(n, b, len(bits), _p(out)):
+        raise RuntimeError("coeff_modulus_create failed")
+    return [int(x) for x in out]
+
+
+def minimal_primitive_root(degree, q):
+    r = C.c_uint64(0)
+    if lib().orc_minimal_primitive_root(degree, q, C.byref(r)):
+        raise RuntimeError("no primitive root")
+    return r.value
+
+
+def galois_elt_from_step(n, step):
+    return int(lib().orc_galois_elt_from_step(n, step))
+
+
+def galois_coeff_row(n, q, elt, row):
+    out = np.zeros(n, dtype=np.uint64)
+    lib().orc_galois_coeff_row(n, q, elt, _p(np.ascontiguousarray(row)), _p(out))
+    return out
+
+
+def galois_ntt_row(n, elt, row):
+    out = np.zeros(n, dtype=np.uint64)
+    lib().orc_galois_ntt_row(n, elt, _p(np.ascontiguousarray(row)), _p(out))
+    return out
+
+
+class Oracle:
+    def __init__(self, scheme, n, moduli, plain_modulus=0):
+        self.scheme, self.n, self.moduli, self.k, self.t = scheme, n, list(moduli), len(moduli), plain_modulus
+        m = np.array(self.moduli, dtype=np.uint64)
+        self.h = lib().orc_create(scheme, n, _p(m), self.k, plain_modulus)
+        if not self.h:
+            raise RuntimeError("orc_create failed")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def ntt_tables(self, i):
+        n = self.n
+        rp, irp = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        root, inv_n = C.c_uint64(0), C.c_uint64(0)
+        assert lib().orc_ntt_tables(self.h, i, C.byref(root), _p(rp), _p(irp), C.byref(inv_n)) == 0
+        return root.value, rp, irp, inv_n.value
+
+    def base_bsk(self, L):
+        out = np.zeros(self.k + 4, dtype=np.uint64)
+        cnt = lib().orc_base_bsk(self.h, L, _p(out))
+        return [int(x) for x in out[:cnt]]
+
+    def ntt_row(self, i, row):
+        r = np.ascontiguousarray(row).copy()
+        lib().orc_ntt_row(self.h, i, _p(r))
+        return r
+
+    def intt_row(self, i, row):
+        r = np.ascontiguousarray(row).copy()
+        lib().orc_intt_row(self.h, i, _p(r))
+        return r
+
+    def ntt_forward(self, L, data):
+        d = np.ascontiguousarray(data).copy()
+        lib().orc_ntt_forward(self.h, L, d.shape[0], _p(d))
+        return d
+
+    def ntt_inverse(self, L, data):
+        d = np.ascontiguousarray(data).copy()
+        lib().orc_ntt_inverse(self.h, L, d.shape[0], _p(d))
+        return d
+
+    def multiply(self, L, a, b):
+        out = np.zeros((3, L, self.n), dtype=np.uint64)
+        if self.scheme == CKKS:
+            lib().orc_ckks_multiply(self.h, L, _p(a), _p(b), _p(out))
+        else:
+            assert lib().orc_bfv_multiply(self.h, L, _p(a), _p(b), _p(out)) == 0
+        return out
+
+    def relinearize(self, L, c3, key):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        lib().orc_relinearize(self.h, L, _p(c3), _p(key), _p(out))
+        return out
+
+    def multiply_relin(self, L, a, b, key):
+        return self.relinearize(L, self.multiply(L, a, b), key)
+
+    def rescale(self, L, c2):
+        out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
+        lib().orc_rescale(self.h, L, _p(c2), _p(out))
+        return out
+
+    def bfv_mod_switch(self, L, c2):
+        out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
+        lib().orc_bfv_mod_switch(self.h, L, _p(c2), _p(out))
+        return out
+
+    def apply_galois(self, L, c2, elt, key):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        lib().orc_apply_galois(self.h, L, _p(c2), elt, _p(key), _p(out))
+        return out

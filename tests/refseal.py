@@ -1,0 +1,206 @@
+"""ctypes driver for oracle/_ref/libsealref.so -- the UNMODIFIED reference (microsoft/SEAL 4.4.3) behind the flat
+C wrapper oracle/ref_capi.{h,cpp}.  TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; the product never loads it.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "..", "oracle", "_ref", "libsealref.so")
+
+BFV, CKKS = 1, 2
+_u64p = C.POINTER(C.c_uint64)
+
+
+def available():
+    return os.path.exists(_LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_LIB_PATH)
+        L.sealref_create.restype = C.c_void_p
+        L.sealref_create.argtypes = [C.c_int, C.c_size_t, _u64p, C.c_size_t, C.c_uint64, C.c_uint64]
+        L.sealref_destroy.argtypes = [C.c_void_p]
+        L.sealref_last_error.restype = C.c_char_p
+        L.sealref_coeff_modulus_create.argtypes = [C.c_size_t, C.POINTER(C.c_int), C.c_size_t, _u64p]
+        L.sealref_coeff_modulus_bfv_default.argtypes = [C.c_size_t, _u64p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.sealref_plain_modulus_batching.restype = C.c_uint64
+        L.sealref_plain_modulus_batching.argtypes = [C.c_size_t, C.c_int]
+        L.sealref_ntt_root.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.sealref_ntt_tables.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p, _u64p]
+        L.sealref_base_bsk.restype = C.c_size_t
+        L.sealref_base_bsk.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_size_t]
+        L.sealref_relin_key.argtypes = [C.c_void_p, _u64p]
+        L.sealref_galois_key.argtypes = [C.c_void_p, C.c_uint32, _u64p]
+        L.sealref_galois_elt_from_step.restype = C.c_uint32
+        L.sealref_galois_elt_from_step.argtypes = [C.c_void_p, C.c_int]
+        L.sealref_ntt_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
+        L.sealref_ntt_inverse.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
+        L.sealref_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.sealref_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_multiply_relin.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.sealref_rescale.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_mod_switch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_apply_galois.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_uint32, _u64p]
+        L.sealref_rotate.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_int, _u64p]
+        L.sealref_bfv_encrypt.argtypes = [C.c_void_p, _u64p, _u64p]
+        L.sealref_bfv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int)]
+        L.sealref_time_op.restype = C.c_double
+        L.sealref_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+def coeff_modulus_create(n, bits):
+    out = np.zeros(len(bits), dtype=np.uint64)
+    b = (C.c_int * len(bits))(*bits)
+    if lib().sealref_coeff_modulus_create(n, b, len(bits), _p(out)):
+        raise RuntimeError(lib().sealref_last_error().decode())
+    return [int(x) for x in out]
+
+
+def coeff_modulus_bfv_default(n):
+    out = np.zeros(64, dtype=np.uint64)
+    k = C.c_size_t(0)
+    if lib().sealref_coeff_modulus_bfv_default(n, _p(out), 64, C.byref(k)):
+        raise RuntimeError(lib().sealref_last_error().decode())
+    return [int(x) for x in out[: k.value]]
+
+
+def plain_modulus_batching(n, bits):
+    return int(lib().sealref_plain_modulus_batching(n, bits))
+
+
+class RefContext:
+    """One reference SEALContext + KeyGenerator + Evaluator (sec_level none, expand_mod_chain=true)."""
+
+    def __init__(self, scheme, n, moduli, plain_modulus=0, seed=0x5EA1):
+        self.scheme, self.n, self.moduli, self.k = scheme, n, list(moduli), len(moduli)
+        self.plain_modulus = plain_modulus
+        m = np.array(self.moduli, dtype=np.uint64)
+        self.h = lib().sealref_create(scheme, n, _p(m), self.k, plain_modulus, seed)
+        if not self.h:
+            raise RuntimeError(lib().sealref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().sealref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+
+    def ntt_root(self, i):
+        r = C.c_uint64(0)
+        self._chk(lib().sealref_ntt_root(self.h, i, C.byref(r)))
+        return r.value
+
+    def ntt_tables(self, i):
+        n = self.n
+        a, b, c = (np.zeros(n, dtype=np.uint64) for _ in range(3))
+        d = C.c_uint64(0)
+        self._chk(lib().sealref_ntt_tables(self.h, i, _p(a), _p(b), _p(c), C.byref(d)))
+        return a, b, c, d.value
+
+    def base_bsk(self, L):
+        out = np.zeros(self.k + 4, dtype=np.uint64)
+        cnt = lib().sealref_base_bsk(self.h, L, _p(out), len(out))
+        if cnt == 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+        return [int(x) for x in out[:cnt]]
+
+    def relin_key(self):
+        out = np.zeros((self.k - 1, 2, self.k, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_relin_key(self.h, _p(out)))
+        return out
+
+    def galois_key(self, elt):
+        out = np.zeros((self.k - 1, 2, self.k, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_galois_key(self.h, elt, _p(out)))
+        return out
+
+    def galois_elt_from_step(self, step):
+        return int(lib().sealref_galois_elt_from_step(self.h, step))
+
+    def ntt_forward(self, L, data):
+        d = np.ascontiguousarray(data).copy()
+        self._chk(lib().sealref_ntt_forward(self.h, L, d.shape[0], _p(d)))
+        return d
+
+    def ntt_inverse(self, L, data):
+        d = np.ascontiguousarray(data).copy()
+        self._chk(lib().sealref_ntt_inverse(self.h, L, d.shape[0], _p(d)))
+        return d
+
+    def multiply(self, L, a, b):
+        out = np.zeros((3, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_multiply(self.h, L, _p(a), _p(b), _p(out)))
+        return out
+
+    def relinearize(self, L, c3):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_relinearize(self.h, L, _p(c3), _p(out)))
+        return out
+
+    def multiply_relin(self, L, a, b):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_multiply_relin(self.h, L, _p(a), _p(b), _p(out)))
+        return out
+
+    def rescale(self, L, c2):
+        out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_rescale(self.h, L, _p(c2), _p(out)))
+        return out
+
+    def mod_switch(self, L, c2):
+        out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_mod_switch(self.h, L, _p(c2), _p(out)))
+        return out
+
+    def apply_galois(self, L, c2, elt):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_apply_galois(self.h, L, _p(c2), elt, _p(out)))
+        return out
+
+    def rotate(self, L, c2, step):
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_rotate(self.h, L, _p(c2), step, _p(out)))
+        return out
+
+    def bfv_encrypt(self, slots):
+        out = np.zeros((2, self.k - 1, self.n), dtype=np.uint64)
+        s = np.ascontiguousarray(slots, dtype=np.uint64)
+        self._chk(lib().sealref_bfv_encrypt(self.h, _p(s), _p(out)))
+        return out
+
+    def bfv_decrypt(self, L, ct):
+        ct = np.ascontiguousarray(ct)
+        out = np.zeros(self.n, dtype=np.uint64)
+        nb = C.c_int(0)
+        self._chk(lib().sealref_bfv_decrypt(self.h, L, ct.shape[0], _p(ct), _p(out), C.byref(nb)))
+        return out, nb.value
+
+    def time_op(self, op, L, threads, reps):
+        t = lib().sealref_time_op(self.h, op, L, threads, reps)
+        if t < 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+        return t

@@ -1,0 +1,134 @@
+"""Pins the oracle (oracle/seal_oracle.c): reference in-source KATs, committed golden vectors generated from the real
+reference, and -- where oracle/_ref/libsealref.so is present -- live comparison with the reference itself."""
+import numpy as np
+import pytest
+
+import oracle as O
+import refseal as R
+from common import golden, rand_ct
+
+Q_KAT = 0xFFFFFFFFFFC0001
+
+
+def test_kat_ntt_root_powers():
+    # native/tests/seal/util/ntt.cpp:53-73
+    oc = O.Oracle(O.CKKS, 2, [Q_KAT])
+    root, rp, irp, _ = oc.ntt_tables(0)
+    assert rp[0] == 1 and rp[1] == 288794978602139552
+    assert (int(rp[1]) * int(irp[1])) % Q_KAT == 1
+    oc = O.Oracle(O.CKKS, 4, [Q_KAT])
+    _, rp, _, _ = oc.ntt_tables(0)
+    assert list(map(int, rp)) == [1, 288794978602139552, 178930308976060547, 748001537669050592]
+
+
+def test_kat_ntt_values():
+    # native/tests/seal/util/ntt.cpp:75-100
+    oc = O.Oracle(O.CKKS, 2, [Q_KAT])
+    assert list(oc.ntt_row(0, np.array([0, 0], dtype=np.uint64))) == [0, 0]
+    assert list(oc.ntt_row(0, np.array([1, 0], dtype=np.uint64))) == [1, 1]
+    assert list(map(int, oc.ntt_row(0, np.array([1, 1], dtype=np.uint64)))) == [288794978602139553, 864126526004445282]
+
+
+def test_kat_ntt_roundtrip():
+    # native/tests/seal/util/ntt.cpp:103-133 (n = 8)
+    oc = O.Oracle(O.CKKS, 8, [Q_KAT])
+    rng = np.random.default_rng(0x5EA1)
+    x = rng.integers(0, Q_KAT, 8, dtype=np.uint64)
+    assert (oc.intt_row(0, oc.ntt_row(0, x)) == x).all()
+    assert (oc.intt_row(0, np.zeros(8, dtype=np.uint64)) == 0).all()
+
+
+def test_kat_galois():
+    # native/tests/seal/util/galois.cpp:86-120 (n=8, q=17, g=3)
+    x = np.arange(8, dtype=np.uint64)
+    assert list(O.galois_coeff_row(8, 17, 3, x)) == [0, 14, 6, 1, 13, 7, 2, 12]
+    assert list(O.galois_ntt_row(8, 3, x)) == [4, 5, 7, 6, 1, 0, 2, 3]
+
+
+def test_kat_galois_elts():
+    # native/tests/seal/util/galois.cpp:28-69 (EltFromStep for n = 8: generator 3 mod 16)
+    assert O.galois_elt_from_step(8, 0) == 15
+    assert O.galois_elt_from_step(8, 1) == 3
+    assert O.galois_elt_from_step(8, -3) == 3
+    assert O.galois_elt_from_step(8, 2) == 9
+    assert O.galois_elt_from_step(8, -2) == 9
+    assert O.galois_elt_from_step(8, 3) == 11
+    assert O.galois_elt_from_step(8, -1) == 11
+
+
+def test_default_moduli_known_values():
+    # util/globals.cpp:43 BFVDefault(4096) = {0xffffee001, 0xffffc4001, 0x1ffffe0001}; CoeffModulus::Create hands equal-size
+    # primes out smallest-first (modulus.cpp:175-181), so Create(4096,{36,36,37}) is the same set in ascending order
+    assert O.coeff_modulus_create(4096, [36, 36, 37]) == [0xFFFFC4001, 0xFFFFEE001, 0x1FFFFE0001]
+    assert all(O.lib().orc_is_prime(p) and p % 8192 == 1 for p in (0xFFFFEE001, 0xFFFFC4001, 0x1FFFFE0001))
+
+
+@pytest.mark.parametrize("name", ["ckks_n128", "bfv_n128", "ckks_n1024"])
+def test_oracle_vs_golden(name):
+    g = golden(name)
+    scheme, n, mods, t = int(g["scheme"]), int(g["n"]), [int(x) for x in g["moduli"]], int(g["t"])
+    k = len(mods)
+    oc = O.Oracle(scheme, n, mods, t)
+    for i in range(k):
+        assert oc.ntt_tables(i)[0] == int(g["roots"][i])
+    key = g["relin_key"]
+    for L in range(k - 1, 0, -1):
+        a, b = g[f"L{L}_a"], g[f"L{L}_b"]
+        assert (oc.ntt_forward(L, a) == g[f"L{L}_ntt_fwd_a"]).all()
+        assert (oc.ntt_inverse(L, a) == g[f"L{L}_ntt_inv_a"]).all()
+        m = oc.multiply(L, a, b)
+        assert (m == g[f"L{L}_mul"]).all()
+        assert (oc.relinearize(L, m, key) == g[f"L{L}_relin"]).all()
+        if L > 1:
+            ms = oc.rescale(L, a) if scheme == O.CKKS else oc.bfv_mod_switch(L, a)
+            assert (ms == g[f"L{L}_modswitch_a"]).all()
+        for e in g["galois_elts"]:
+            e = int(e)
+            assert (oc.apply_galois(L, a, e, g[f"galois_key_{e}"]) == g[f"L{L}_galois_{e}"]).all()
+        if scheme == O.BFV:
+            assert oc.base_bsk(L) == [int(x) for x in g[f"L{L}_bsk"]]
+
+
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not built")
+
+
+@needs_ref
+def test_oracle_vs_live_reference_ckks():
+    # non-descending chain (50/40/45/60 bits) exercises both conditional-reduction branches (evaluator.cpp:2690, :2824)
+    n = 512
+    mods = R.coeff_modulus_create(n, [50, 40, 45, 60])
+    assert mods == O.coeff_modulus_create(n, [50, 40, 45, 60])
+    rc, oc = R.RefContext(R.CKKS, n, mods), O.Oracle(O.CKKS, n, mods)
+    rng = np.random.default_rng(3)
+    key = rc.relin_key()
+    for i in range(len(mods)):
+        a, _, c, d = rc.ntt_tables(i)
+        root, rp, irp, invn = oc.ntt_tables(i)
+        assert root == rc.ntt_root(i) and (a == rp).all() and (c == irp).all() and d == invn
+    for L in (3, 2, 1):
+        x, y = rand_ct(rng, mods, n, 2, L), rand_ct(rng, mods, n, 2, L)
+        assert (rc.multiply_relin(L, x, y) == oc.multiply_relin(L, x, y, key)).all()
+        if L > 1:
+            assert (rc.rescale(L, x) == oc.rescale(L, x)).all()
+        for step in (1, -5):
+            e = rc.galois_elt_from_step(step)
+            assert e == O.galois_elt_from_step(n, step)
+            assert (rc.apply_galois(L, x, e) == oc.apply_galois(L, x, e, rc.galois_key(e))).all()
+
+
+@needs_ref
+def test_oracle_vs_live_reference_bfv_cfg1():
+    # BASELINE.json configs[0]: BFV n=4096, 3x36-bit coeff_modulus, single multiply (bit-exact plumbing check)
+    n = 4096
+    mods = R.coeff_modulus_bfv_default(n)
+    t = R.plain_modulus_batching(n, 20)
+    rb, ob = R.RefContext(R.BFV, n, mods, t), O.Oracle(O.BFV, n, mods, t)
+    rng = np.random.default_rng(4)
+    L = 2
+    assert rb.base_bsk(L) == ob.base_bsk(L)
+    x, y = rand_ct(rng, mods, n, 2, L), rand_ct(rng, mods, n, 2, L)
+    m = rb.multiply(L, x, y)
+    assert (m == ob.multiply(L, x, y)).all()
+    assert (rb.relinearize(L, m) == ob.relinearize(L, m, rb.relin_key())).all()
+    e = rb.galois_elt_from_step(1)
+    assert (rb.apply_galois(L, x, e) == ob.apply_galois(L, x, e, rb.galois_key(e))).all()
