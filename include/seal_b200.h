@@ -1,0 +1,113 @@
+/* include/seal_b200.h -- C-ABI of libseal_b200.so: the B200 (sm_100a) drop-in for the RNS-polynomial hot path of
+ * microsoft/SEAL 4.4.3 (negacyclic NTT/INTT, dyadic products, hybrid key switching, rescale / BEHZ base conversion)
+ * that backs Evaluator::multiply / relinearize_inplace / rotate_rows / rotate_vector / rescale_to_next.
+ *
+ * Style follows the reference's own C layer (native/src/seal/c/defines.h:34-96): extern "C", opaque handles, plain
+ * pointers and sizes, an integer status instead of exceptions, a last-error string.  Unlike the reference's C layer
+ * the data arguments are raw uint64 slabs laid out exactly like seal::Ciphertext::data() (ciphertext.h:24-37):
+ *
+ *      [batch][poly (size)][rns prime (L)][coefficient (n)]       8*n*L*size bytes per ciphertext
+ *
+ * so a binding marshals `ct.data()` with one memcpy.  `L` = number of RNS primes the
+ * ciphertexts carry = parms.coeff_modulus().size() at that level of the modulus-switching chain; the key level has
+ * k primes, ciphertexts have L <= k-1 (context.cpp:513-535).  Device entry points (d_ prefix on arguments) are
+ * stream-ordered and never synchronise; the *_host entry points take host buffers, copy H2D / D2H themselves and
+ * return after the result is in the host buffer.
+ *
+ * There is NO CPU fallback: every entry point fails with SB200_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef SEAL_B200_H
+#define SEAL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; the mapping mirrors the reference's exception -> HRESULT ladder (c/defines.h:72-96) */
+#define SB200_OK 0
+#define SB200_E_INVALID_ARG (-1)  /* std::invalid_argument  -> E_INVALIDARG            */
+#define SB200_E_LOGIC (-2)        /* std::logic_error       -> COR_E_INVALIDOPERATION  */
+#define SB200_E_OUT_OF_RANGE (-3) /* std::out_of_range      -> ERROR_INVALID_INDEX     */
+#define SB200_E_CUDA (-4)         /* std::runtime_error     -> COR_E_IO                */
+#define SB200_E_NOMEM (-5)        /* std::bad_alloc         -> E_OUTOFMEMORY           */
+#define SB200_E_POINTER (-6)      /* null handle / pointer  -> E_POINTER               */
+
+#define SB200_SCHEME_BFV 1  /* seal::scheme_type::bfv  (encryptionparams.h) */
+#define SB200_SCHEME_CKKS 2 /* seal::scheme_type::ckks */
+
+typedef struct sb200_context sb200_context;   /* mirrors SEALContext + Evaluator state (context.h:277-439) */
+typedef struct sb200_kswitch_key sb200_kswitch_key; /* one KSwitchKeys::data()[index] entry on the device (kswitchkeys.h) */
+
+/* last error message of the calling thread (never NULL) */
+const char *sb200_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------
+ * Replaces SEALContext(parms, expand_mod_chain=true, sec_level_type::none) + Evaluator(context) for this path
+ * (context.cpp:495-563, evaluator.cpp:121-128).  coeff_modulus = the k key-level primes (last = special prime),
+ * each < 2^61, prime, = 1 mod 2n.  plain_modulus is used by BFV only.  All NTT / RNS / Galois tables are computed
+ * here from these numbers alone and uploaded to CUDA device `device`. */
+int sb200_context_create(int scheme, size_t poly_modulus_degree, const uint64_t *coeff_modulus, size_t k,
+                         uint64_t plain_modulus, int device, sb200_context **out);
+int sb200_context_destroy(sb200_context *ctx);
+/* helpers that reproduce CoeffModulus::Create (modulus.cpp:144-184) */
+int sb200_coeff_modulus_create(size_t poly_modulus_degree, const int *bit_sizes, size_t k, uint64_t *out);
+/* table introspection for parity tests: NTTTables::get_root / get_from_root_powers / get_from_inv_root_powers /
+ * inv_degree_modulo (ntt.h:95-123) in the reference's own order; any output pointer may be NULL */
+int sb200_get_ntt_tables(const sb200_context *ctx, size_t prime_index, uint64_t *root, uint64_t *root_powers_operand,
+                         uint64_t *root_powers_quotient, uint64_t *inv_root_powers_operand, uint64_t *inv_degree_modulo);
+/* RNSTool::base_Bsk() at the level with L primes (rns.h:246-309); out gets |Bsk| values */
+int sb200_get_base_bsk(const sb200_context *ctx, size_t L, uint64_t *out, size_t capacity, size_t *count);
+/* GaloisTool::get_elt_from_step (galois.cpp:53-95); returns 0 on invalid step */
+uint32_t sb200_galois_elt_from_step(const sb200_context *ctx, int step);
+/* number of CUDA kernels launched through this context so far */
+unsigned long long sb200_launch_count(const sb200_context *ctx);
+/* device bytes currently held by the context (tables + scratch) */
+size_t sb200_device_bytes(const sb200_context *ctx);
+
+/* ---- key-switching keys --------------------------------------------------------------------------------------
+ * h_key = the flattened KSwitchKeys::data()[index]: [digit j < digits][component 2][key prime k][coeff n], i.e. for
+ * each j the PublicKey's ciphertext data (kswitchkeys.h, keygenerator.cpp:327-360).  digits must be >= L of every
+ * ciphertext it is used with (evaluator.cpp:2635). */
+int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out);
+int sb200_kswitch_key_destroy(sb200_kswitch_key *key);
+
+/* ---- device-resident batch operations (stream = cudaStream_t, may be NULL) ---------------------------------- */
+/* Evaluator::transform_to_ntt_inplace / transform_from_ntt_inplace (evaluator.cpp:2289-2382) */
+int sb200_ntt_forward(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d_data, void *stream);
+int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d_data, void *stream);
+/* Evaluator::multiply (evaluator.cpp:352-708), size-2 x size-2 -> size-3; CKKS (NTT form) or BFV (BEHZ) per ctx */
+int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, const uint64_t *d_b,
+                   uint64_t *d_out3, void *stream);
+/* Evaluator::relinearize_inplace, size 3 -> 2 (evaluator.cpp:1144-1199 + 2561-2867) */
+int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in3,
+                      const sb200_kswitch_key *relin_key, uint64_t *d_out2, void *stream);
+/* multiply followed by relinearize_inplace in one call; the size-3 intermediate never reaches the caller */
+int sb200_multiply_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, const uint64_t *d_b,
+                               const sb200_kswitch_key *relin_key, uint64_t *d_out2, void *stream);
+/* Evaluator::rescale_to_next (CKKS; evaluator.cpp:1503-1541, rns.cpp:830-901): [2][L][n] -> [2][L-1][n] */
+int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint64_t *d_out2, void *stream);
+/* Evaluator::mod_switch_to_next: BFV divide-and-round (rns.cpp:789-828); CKKS drops the last prime */
+int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint64_t *d_out2, void *stream);
+/* Evaluator::apply_galois (evaluator.cpp:2384-2502): automorphism x -> x^galois_elt on both polys + key switch.
+ * rotate_rows / rotate_vector(step) = apply_galois(sb200_galois_elt_from_step(step)) with that element's key. */
+int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint32_t galois_elt,
+                       const sb200_kswitch_key *galois_key, uint64_t *d_out2, void *stream);
+
+/* ---- host-buffer variants: H2D copy, operation, D2H copy, synchronise (the plugin-facing end-to-end path) ---- */
+int sb200_ntt_forward_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
+int sb200_ntt_inverse_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
+int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out3);
+int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in3,
+                           const sb200_kswitch_key *relin_key, uint64_t *h_out2);
+int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b,
+                                    const sb200_kswitch_key *relin_key, uint64_t *h_out2);
+int sb200_rescale_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint64_t *h_out2);
+int sb200_mod_switch_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint64_t *h_out2);
+int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint32_t galois_elt,
+                            const sb200_kswitch_key *galois_key, uint64_t *h_out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

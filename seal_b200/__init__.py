@@ -1,0 +1,275 @@
+"""seal_b200 -- Python (ctypes) binding of libseal_b200.so, the B200 (sm_100a) drop-in for the RNS-polynomial hot
+path of microsoft/SEAL (NTT/INTT, CKKS/BFV multiply, relinearize, rotate, rescale).
+
+The product is the C-ABI library (include/seal_b200.h) and, for C++ users, the header-only Evaluator shim
+(include/seal_b200/evaluator.hpp).  This module exists for tests and bench.py: it mirrors the reference's operator
+names (Evaluator.multiply / relinearize / rescale_to_next / rotate_rows / apply_galois / transform_to_ntt ...)
+on raw uint64 slabs laid out like seal::Ciphertext::data().  There is no CPU fallback: importing works anywhere, but
+creating a Context raises unless the CUDA library is built and a B200 is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+BFV, CKKS = 1, 2
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseal_b200.so")
+_u64p = C.POINTER(C.c_uint64)
+_lib = None
+
+_STATUS = {-1: ValueError, -2: RuntimeError, -3: IndexError, -4: RuntimeError, -5: MemoryError, -6: ValueError}
+
+# every symbol include/seal_b200.h declares (checked by tests/test_host_logic.py)
+SYMBOLS = [
+    "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
+    "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
+    "sb200_device_bytes", "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
+    "sb200_multiply_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
+    "sb200_mod_switch_to_next_host", "sb200_apply_galois_host",
+]
+
+
+def lib():
+    """Load libseal_b200.so (fails loudly if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, u64, i32, u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32
+        L.sb200_last_error.restype = C.c_char_p
+        L.sb200_context_create.argtypes = [i32, sz, _u64p, sz, u64, i32, C.POINTER(vp)]
+        L.sb200_context_destroy.argtypes = [vp]
+        L.sb200_coeff_modulus_create.argtypes = [sz, C.POINTER(i32), sz, _u64p]
+        L.sb200_get_ntt_tables.argtypes = [vp, sz, _u64p, _u64p, _u64p, _u64p, _u64p]
+        L.sb200_get_base_bsk.argtypes = [vp, sz, _u64p, sz, C.POINTER(sz)]
+        L.sb200_galois_elt_from_step.restype = u32
+        L.sb200_galois_elt_from_step.argtypes = [vp, i32]
+        L.sb200_launch_count.restype = C.c_ulonglong
+        L.sb200_launch_count.argtypes = [vp]
+        L.sb200_device_bytes.restype = sz
+        L.sb200_device_bytes.argtypes = [vp]
+        L.sb200_kswitch_key_create.argtypes = [vp, _u64p, sz, C.POINTER(vp)]
+        L.sb200_kswitch_key_destroy.argtypes = [vp]
+        L.sb200_ntt_forward.argtypes = [vp, sz, sz, sz, vp, vp]
+        L.sb200_ntt_inverse.argtypes = [vp, sz, sz, sz, vp, vp]
+        L.sb200_multiply.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+        L.sb200_relinearize.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+        L.sb200_multiply_relinearize.argtypes = [vp, sz, sz, vp, vp, vp, vp, vp]
+        L.sb200_rescale_to_next.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.sb200_mod_switch_to_next.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.sb200_apply_galois.argtypes = [vp, sz, sz, vp, u32, vp, vp, vp]
+        L.sb200_ntt_forward_host.argtypes = [vp, sz, sz, sz, _u64p]
+        L.sb200_ntt_inverse_host.argtypes = [vp, sz, sz, sz, _u64p]
+        L.sb200_multiply_host.argtypes = [vp, sz, sz, _u64p, _u64p, _u64p]
+        L.sb200_relinearize_host.argtypes = [vp, sz, sz, _u64p, vp, _u64p]
+        L.sb200_multiply_relinearize_host.argtypes = [vp, sz, sz, _u64p, _u64p, vp, _u64p]
+        L.sb200_rescale_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
+        L.sb200_mod_switch_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
+        L.sb200_apply_galois_host.argtypes = [vp, sz, sz, _u64p, u32, vp, _u64p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise _STATUS.get(rc, RuntimeError)(f"seal_b200 error {rc}: {lib().sb200_last_error().decode()}")
+
+
+def _hp(a):
+    assert isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need C-contiguous uint64"
+    return a.ctypes.data_as(_u64p)
+
+
+def _dp(t):
+    """device pointer of a torch int64/uint64 CUDA tensor (or a raw int)"""
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous() and t.element_size() == 8
+    return C.c_void_p(t.data_ptr())
+
+
+def coeff_modulus_create(n, bits):
+    """CoeffModulus::Create (modulus.cpp:144-184)"""
+    out = np.zeros(len(bits), dtype=np.uint64)
+    b = (C.c_int * len(bits))(*bits)
+    _check(lib().sb200_coeff_modulus_create(n, b, len(bits), _hp(out)))
+    return [int(x) for x in out]
+
+
+class KSwitchKey:
+    """Device copy of one KSwitchKeys::data()[index] entry ([digit][2][k][n])."""
+
+    def __init__(self, ctx, host_key):
+        host_key = np.ascontiguousarray(host_key, dtype=np.uint64)
+        assert host_key.ndim == 4 and host_key.shape[1] == 2 and host_key.shape[2] == ctx.k and host_key.shape[3] == ctx.n
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(lib().sb200_kswitch_key_create(ctx.h, _hp(host_key), host_key.shape[0], C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().sb200_kswitch_key_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Context:
+    """SEALContext(parms, true, sec_level none) + Evaluator for the hot path, on one B200.
+
+    Host-array methods (numpy in / numpy out) go through the *_host C-ABI entry points; the d_* methods take torch
+    CUDA int64 tensors (device-resident slabs) and are stream-ordered on the current torch stream.
+    """
+
+    def __init__(self, scheme, n, moduli, plain_modulus=0, device=0):
+        self.scheme, self.n, self.moduli, self.k, self.t = scheme, n, [int(m) for m in moduli], len(moduli), plain_modulus
+        self.device = device
+        m = np.array(self.moduli, dtype=np.uint64)
+        h = C.c_void_p()
+        _check(lib().sb200_context_create(scheme, n, _hp(m), self.k, plain_modulus, device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sb200_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables ----
+    def ntt_tables(self, i):
+        n = self.n
+        root, inv_n = C.c_uint64(0), C.c_uint64(0)
+        rp, rq, irp = (np.zeros(n, dtype=np.uint64) for _ in range(3))
+        _check(lib().sb200_get_ntt_tables(self.h, i, C.byref(root), _hp(rp), _hp(rq), _hp(irp), C.byref(inv_n)))
+        return root.value, rp, rq, irp, inv_n.value
+
+    def base_bsk(self, L):
+        out = np.zeros(self.k + 4, dtype=np.uint64)
+        cnt = C.c_size_t(0)
+        _check(lib().sb200_get_base_bsk(self.h, L, _hp(out), len(out), C.byref(cnt)))
+        return [int(x) for x in out[: cnt.value]]
+
+    def galois_elt_from_step(self, step):
+        return int(lib().sb200_galois_elt_from_step(self.h, step))
+
+    @property
+    def launch_count(self):
+        return int(lib().sb200_launch_count(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(lib().sb200_device_bytes(self.h))
+
+    def load_key(self, host_key):
+        return KSwitchKey(self, host_key)
+
+    # ---- host-buffer API: a is [batch][size][L][n] (or [size][L][n] for a single ciphertext) ----
+    @staticmethod
+    def _batched(a, ndim_single=3):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        single = a.ndim == ndim_single
+        return (a[None] if single else a), single
+
+    def transform_to_ntt(self, a):
+        a, single = self._batched(a)
+        d = a.copy()
+        _check(lib().sb200_ntt_forward_host(self.h, d.shape[2], d.shape[1], d.shape[0], _hp(d)))
+        return d[0] if single else d
+
+    def transform_from_ntt(self, a):
+        a, single = self._batched(a)
+        d = a.copy()
+        _check(lib().sb200_ntt_inverse_host(self.h, d.shape[2], d.shape[1], d.shape[0], _hp(d)))
+        return d[0] if single else d
+
+    def multiply(self, a, b):
+        a, single = self._batched(a)
+        b, _ = self._batched(b)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 3, L, n), dtype=np.uint64)
+        _check(lib().sb200_multiply_host(self.h, L, B, _hp(a), _hp(b), _hp(out)))
+        return out[0] if single else out
+
+    def relinearize(self, c3, key):
+        c3, single = self._batched(c3)
+        B, _, L, n = c3.shape
+        out = np.zeros((B, 2, L, n), dtype=np.uint64)
+        _check(lib().sb200_relinearize_host(self.h, L, B, _hp(c3), key.h, _hp(out)))
+        return out[0] if single else out
+
+    def multiply_relinearize(self, a, b, key):
+        a, single = self._batched(a)
+        b, _ = self._batched(b)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 2, L, n), dtype=np.uint64)
+        _check(lib().sb200_multiply_relinearize_host(self.h, L, B, _hp(a), _hp(b), key.h, _hp(out)))
+        return out[0] if single else out
+
+    def rescale_to_next(self, a):
+        a, single = self._batched(a)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 2, max(L - 1, 0), n), dtype=np.uint64)
+        _check(lib().sb200_rescale_to_next_host(self.h, L, B, _hp(a), _hp(out)))
+        return out[0] if single else out
+
+    def mod_switch_to_next(self, a):
+        a, single = self._batched(a)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 2, max(L - 1, 0), n), dtype=np.uint64)
+        _check(lib().sb200_mod_switch_to_next_host(self.h, L, B, _hp(a), _hp(out)))
+        return out[0] if single else out
+
+    def apply_galois(self, a, galois_elt, key):
+        a, single = self._batched(a)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 2, L, n), dtype=np.uint64)
+        _check(lib().sb200_apply_galois_host(self.h, L, B, _hp(a), galois_elt, key.h, _hp(out)))
+        return out[0] if single else out
+
+    def rotate(self, a, step, key):
+        """rotate_rows (BFV) / rotate_vector (CKKS) by `step` with the Galois key of that step's element"""
+        return self.apply_galois(a, self.galois_elt_from_step(step), key)
+
+    # ---- device-resident API (torch CUDA tensors, current stream) ----
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def d_ntt_forward(self, t, L, size, batch):
+        _check(lib().sb200_ntt_forward(self.h, L, size, batch, _dp(t), self._stream()))
+
+    def d_ntt_inverse(self, t, L, size, batch):
+        _check(lib().sb200_ntt_inverse(self.h, L, size, batch, _dp(t), self._stream()))
+
+    def d_multiply(self, a, b, out3, L, batch):
+        _check(lib().sb200_multiply(self.h, L, batch, _dp(a), _dp(b), _dp(out3), self._stream()))
+
+    def d_relinearize(self, in3, key, out2, L, batch):
+        _check(lib().sb200_relinearize(self.h, L, batch, _dp(in3), key.h, _dp(out2), self._stream()))
+
+    def d_multiply_relinearize(self, a, b, key, out2, L, batch):
+        _check(lib().sb200_multiply_relinearize(self.h, L, batch, _dp(a), _dp(b), key.h, _dp(out2), self._stream()))
+
+    def d_rescale_to_next(self, in2, out2, L, batch):
+        _check(lib().sb200_rescale_to_next(self.h, L, batch, _dp(in2), _dp(out2), self._stream()))
+
+    def d_mod_switch_to_next(self, in2, out2, L, batch):
+        _check(lib().sb200_mod_switch_to_next(self.h, L, batch, _dp(in2), _dp(out2), self._stream()))
+
+    def d_apply_galois(self, in2, galois_elt, key, out2, L, batch):
+        _check(lib().sb200_apply_galois(self.h, L, batch, _dp(in2), galois_elt, key.h, _dp(out2), self._stream()))

@@ -1,0 +1,472 @@
+// seal_b200/csrc/sb_api.cu -- the extern "C" boundary declared in include/seal_b200.h.
+// Exceptions never cross it: they are mapped to status codes the way the reference's C layer maps them to HRESULTs
+// (native/src/seal/c/defines.h:72-96) and the message is kept in a thread-local string.
+#include "../../include/seal_b200.h"
+#include "sb_engine.cuh"
+#include <new>
+
+using namespace sb;
+
+static thread_local std::string g_last_error;
+
+struct sb200_context
+{
+    std::unique_ptr<Context> c;
+};
+struct sb200_kswitch_key
+{
+    KSwitchKey k;
+};
+
+#define SB_TRY try {
+#define SB_CATCH                                   \
+    }                                              \
+    catch (const std::invalid_argument &e)         \
+    {                                              \
+        g_last_error = e.what();                   \
+        return SB200_E_INVALID_ARG;                \
+    }                                              \
+    catch (const std::out_of_range &e)             \
+    {                                              \
+        g_last_error = e.what();                   \
+        return SB200_E_OUT_OF_RANGE;               \
+    }                                              \
+    catch (const std::logic_error &e)              \
+    {                                              \
+        g_last_error = e.what();                   \
+        return SB200_E_LOGIC;                      \
+    }                                              \
+    catch (const std::bad_alloc &e)                \
+    {                                              \
+        g_last_error = e.what();                   \
+        return SB200_E_NOMEM;                      \
+    }                                              \
+    catch (const std::exception &e)                \
+    {                                              \
+        g_last_error = e.what();                   \
+        return SB200_E_CUDA;                       \
+    }
+
+#define SB_NEED(p)                                      \
+    if (!(p))                                           \
+    {                                                   \
+        g_last_error = "null pointer: " #p;             \
+        return SB200_E_POINTER;                         \
+    }
+
+extern "C" {
+
+const char *sb200_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+int sb200_context_create(int scheme, size_t n, const uint64_t *coeff_modulus, size_t k, uint64_t plain_modulus, int device,
+                         sb200_context **out)
+{
+    SB_NEED(coeff_modulus);
+    SB_NEED(out);
+    SB_TRY
+    auto h = std::make_unique<sb200_context>();
+    h->c = make_context(scheme, n, reinterpret_cast<const u64 *>(coeff_modulus), k, plain_modulus, device);
+    *out = h.release();
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_context_destroy(sb200_context *ctx)
+{
+    SB_NEED(ctx);
+    delete ctx;
+    return SB200_OK;
+}
+
+int sb200_coeff_modulus_create(size_t n, const int *bit_sizes, size_t k, uint64_t *out)
+{
+    SB_NEED(bit_sizes);
+    SB_NEED(out);
+    SB_TRY
+    if (n < 2 || (n & (n - 1)) || n > 131072)
+        throw std::invalid_argument("poly_modulus_degree is invalid");
+    for (size_t i = 0; i < k; i++)
+        if (bit_sizes[i] < 2 || bit_sizes[i] > 60)
+            throw std::invalid_argument("bit_sizes is invalid");
+    auto v = sbh::coeff_modulus_create(n, std::vector<int>(bit_sizes, bit_sizes + k));
+    for (size_t i = 0; i < k; i++)
+        out[i] = v[i];
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_get_ntt_tables(const sb200_context *ctx, size_t i, uint64_t *root, uint64_t *rp_op, uint64_t *rp_quo, uint64_t *irp_op,
+                         uint64_t *inv_n)
+{
+    SB_NEED(ctx);
+    SB_TRY
+    const Context &c = *ctx->c;
+    if (i >= c.k)
+        throw std::out_of_range("prime_index");
+    const auto &t = c.tabs[i];
+    if (root)
+        *root = t.root;
+    if (inv_n)
+        *inv_n = t.inv_n.w;
+    for (size_t j = 0; j < c.n; j++)
+    {
+        if (rp_op)
+            rp_op[j] = t.root_powers[j].w;
+        if (rp_quo)
+            rp_quo[j] = t.root_powers[j].wq;
+        if (irp_op)
+            irp_op[j] = t.inv_root_powers[j].w;
+    }
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_get_base_bsk(const sb200_context *ctx, size_t L, uint64_t *out, size_t capacity, size_t *count)
+{
+    SB_NEED(ctx);
+    SB_NEED(out);
+    SB_NEED(count);
+    SB_TRY
+    Context &c = *ctx->c;
+    if (c.scheme != SB200_SCHEME_BFV)
+        throw std::logic_error("BEHZ base exists for BFV contexts only");
+    const auto &b = behz_host(c, L);
+    if (b.nBsk > capacity)
+        throw std::out_of_range("capacity");
+    for (size_t i = 0; i < b.nBsk; i++)
+        out[i] = b.Bsk[i];
+    *count = b.nBsk;
+    return SB200_OK;
+    SB_CATCH
+}
+
+uint32_t sb200_galois_elt_from_step(const sb200_context *ctx, int step)
+{
+    if (!ctx)
+        return 0;
+    try
+    {
+        return sbh::galois_elt_from_step(ctx->c->n, step);
+    }
+    catch (const std::exception &e)
+    {
+        g_last_error = e.what();
+        return 0;
+    }
+}
+
+unsigned long long sb200_launch_count(const sb200_context *ctx)
+{
+    return ctx ? ctx->c->stats.launches : 0;
+}
+
+size_t sb200_device_bytes(const sb200_context *ctx)
+{
+    return ctx ? ctx->c->table_bytes + ctx->c->scratch_bytes : 0;
+}
+
+int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out)
+{
+    SB_NEED(ctx);
+    SB_NEED(h_key);
+    SB_NEED(out);
+    SB_TRY
+    Context &c = *ctx->c;
+    if (c.k < 2)
+        throw std::logic_error("keyswitching is not supported by the context");
+    if (digits < 1 || digits > c.k - 1)
+        throw std::invalid_argument("kswitch key has an invalid number of digits");
+    auto h = std::make_unique<sb200_kswitch_key>();
+    size_t bytes = digits * 2 * c.k * c.n * sizeof(u64);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    cuda_check(cudaMalloc(reinterpret_cast<void **>(&h->k.d_key), bytes), "cudaMalloc(key)");
+    cuda_check(cudaMemcpy(h->k.d_key, h_key, bytes, cudaMemcpyHostToDevice), "upload key");
+    h->k.ctx = &c;
+    h->k.digits = digits;
+    *out = h.release();
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_kswitch_key_destroy(sb200_kswitch_key *key)
+{
+    SB_NEED(key);
+    cudaFree(key->k.d_key);
+    delete key;
+    return SB200_OK;
+}
+
+#define SB_ENTER(ctx)                                      \
+    SB_NEED(ctx);                                          \
+    Context &c = *ctx->c;                                  \
+    std::lock_guard<std::mutex> lock(c.mu);                \
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+
+static void check_level(const Context &c, size_t L, size_t batch)
+{
+    if (L < 1 || L > c.k)
+        throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    if (batch == 0)
+        throw std::invalid_argument("batch must be positive");
+}
+
+int sb200_ntt_forward(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d, void *stream)
+{
+    SB_NEED(d);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_ntt(c, false, L, size, batch, reinterpret_cast<u64 *>(d), static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d, void *stream)
+{
+    SB_NEED(d);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_ntt(c, true, L, size, batch, reinterpret_cast<u64 *>(d), static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out3, void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(out3);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    auto st = static_cast<cudaStream_t>(stream);
+    if (c.scheme == SB200_SCHEME_CKKS)
+        op_ckks_multiply(c, L, batch, (const u64 *)a, (const u64 *)b, (u64 *)out3, st);
+    else
+        op_bfv_multiply(c, L, batch, (const u64 *)a, (const u64 *)b, (u64 *)out3, st);
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in3, const sb200_kswitch_key *key, uint64_t *out2,
+                      void *stream)
+{
+    SB_NEED(in3);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_relinearize(c, L, batch, (const u64 *)in3, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, const uint64_t *b,
+                               const sb200_kswitch_key *key, uint64_t *out2, void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_multiply_relinearize(c, L, batch, (const u64 *)a, (const u64 *)b, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
+{
+    SB_NEED(in2);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_rescale(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
+{
+    SB_NEED(in2);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_mod_switch(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint32_t elt, const sb200_kswitch_key *key,
+                       uint64_t *out2, void *stream)
+{
+    SB_NEED(in2);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_apply_galois(c, L, batch, (const u64 *)in2, elt, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+// ---- host-buffer variants: staged through device buffers owned by the call ---------------------------------------
+namespace
+{
+    struct DevBuf
+    {
+        u64 *p = nullptr;
+        explicit DevBuf(size_t words) { cuda_check(cudaMalloc(reinterpret_cast<void **>(&p), words * sizeof(u64)), "cudaMalloc(io)"); }
+        ~DevBuf() { cudaFree(p); }
+        DevBuf(const DevBuf &) = delete;
+        DevBuf &operator=(const DevBuf &) = delete;
+    };
+    void h2d(u64 *d, const uint64_t *h, size_t words, cudaStream_t st)
+    {
+        cuda_check(cudaMemcpyAsync(d, h, words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+    }
+    void d2h(uint64_t *h, const u64 *d, size_t words, cudaStream_t st)
+    {
+        cuda_check(cudaMemcpyAsync(h, d, words * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H");
+        cuda_check(cudaStreamSynchronize(st), "synchronize");
+    }
+} // namespace
+
+static int ntt_host(sb200_context *ctx, bool inverse, size_t L, size_t size, size_t batch, uint64_t *h)
+{
+    SB_NEED(h);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    size_t words = batch * size * L * c.n;
+    DevBuf d(words);
+    h2d(d.p, h, words, 0);
+    op_ntt(c, inverse, L, size, batch, d.p, 0);
+    d2h(h, d.p, words, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_ntt_forward_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h)
+{
+    return ntt_host(ctx, false, L, size, batch, h);
+}
+int sb200_ntt_inverse_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h)
+{
+    return ntt_host(ctx, true, L, size, batch, h);
+}
+
+int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out3)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(out3);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    size_t w = batch * L * c.n;
+    DevBuf da(2 * w), db(2 * w), dout(3 * w);
+    h2d(da.p, a, 2 * w, 0);
+    h2d(db.p, b, 2 * w, 0);
+    if (c.scheme == SB200_SCHEME_CKKS)
+        op_ckks_multiply(c, L, batch, da.p, db.p, dout.p, 0);
+    else
+        op_bfv_multiply(c, L, batch, da.p, db.p, dout.p, 0);
+    d2h(out3, dout.p, 3 * w, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in3, const sb200_kswitch_key *key, uint64_t *out2)
+{
+    SB_NEED(in3);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    size_t w = batch * L * c.n;
+    DevBuf din(3 * w), dout(2 * w);
+    h2d(din.p, in3, 3 * w, 0);
+    op_relinearize(c, L, batch, din.p, key->k, dout.p, 0);
+    d2h(out2, dout.p, 2 * w, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, const uint64_t *b,
+                                    const sb200_kswitch_key *key, uint64_t *out2)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    size_t w = batch * L * c.n;
+    DevBuf da(2 * w), db(2 * w), dout(2 * w);
+    h2d(da.p, a, 2 * w, 0);
+    h2d(db.p, b, 2 * w, 0);
+    op_multiply_relinearize(c, L, batch, da.p, db.p, key->k, dout.p, 0);
+    d2h(out2, dout.p, 2 * w, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+
+static int modswitch_host(sb200_context *ctx, bool rescale, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
+{
+    SB_NEED(in2);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    if (L < 2)
+        throw std::invalid_argument("end of modulus switching chain reached");
+    size_t wi = batch * 2 * L * c.n, wo = batch * 2 * (L - 1) * c.n;
+    DevBuf din(wi), dout(wo);
+    h2d(din.p, in2, wi, 0);
+    if (rescale)
+        op_rescale(c, L, batch, din.p, dout.p, 0);
+    else
+        op_mod_switch(c, L, batch, din.p, dout.p, 0);
+    d2h(out2, dout.p, wo, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_rescale_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
+{
+    return modswitch_host(ctx, true, L, batch, in2, out2);
+}
+int sb200_mod_switch_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
+{
+    return modswitch_host(ctx, false, L, batch, in2, out2);
+}
+
+int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint32_t elt, const sb200_kswitch_key *key,
+                            uint64_t *out2)
+{
+    SB_NEED(in2);
+    SB_NEED(key);
+    SB_NEED(out2);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    size_t w = batch * 2 * L * c.n;
+    DevBuf din(w), dout(w);
+    h2d(din.p, in2, w, 0);
+    op_apply_galois(c, L, batch, din.p, elt, key->k, dout.p, 0);
+    d2h(out2, dout.p, w, 0);
+    return SB200_OK;
+    SB_CATCH
+}
+
+} // extern "C"

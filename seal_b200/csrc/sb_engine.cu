@@ -1,0 +1,823 @@
+// seal_b200/csrc/sb_engine.cu -- device context, fused prologue/epilogue functors and the operation drivers for
+// NTT, CKKS multiply, hybrid key switching (relinearize / apply_galois), rescale and modulus switching.
+//
+// Reference behaviour being reproduced (paths under /root/reference/native/src/seal/):
+//   evaluator.cpp:569-708   ckks_multiply            -> ckks_tensor_kernel
+//   evaluator.cpp:2561-2867 switch_key_inplace       -> key_switch(): INTT(target) | digit NTTs | MAC | mod-down
+//   evaluator.cpp:1144-1199 relinearize_internal     -> op_relinearize / op_multiply_relinearize
+//   evaluator.cpp:2384-2502 apply_galois_inplace     -> op_apply_galois (permutation fused into the loads)
+//   evaluator.cpp:1201-1294 + rns.cpp:789-901        -> op_rescale / op_mod_switch
+#include "sb_engine.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace sb
+{
+    void cuda_check(cudaError_t e, const char *what)
+    {
+        if (e != cudaSuccess)
+            throw CudaError(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+
+    // ------------------------------------------------------------------------------------------- context ----
+    Context::~Context()
+    {
+        cudaSetDevice(device);
+        for (auto p : d_fwd)
+            cudaFree(p);
+        for (auto p : d_inv)
+            cudaFree(p);
+        for (auto &kv : galois_tables)
+            cudaFree(kv.second);
+        cudaFree(d_primes);
+        cudaFree(d_invq);
+        cudaFree(scratch);
+    }
+
+    void *Context::ensure_scratch(size_t bytes)
+    {
+        if (bytes > scratch_bytes)
+        {
+            cuda_check(cudaDeviceSynchronize(), "sync before scratch growth");
+            cudaFree(scratch);
+            scratch = nullptr;
+            scratch_bytes = 0;
+            cuda_check(cudaMalloc(&scratch, bytes), "cudaMalloc(scratch)");
+            scratch_bytes = bytes;
+        }
+        return scratch;
+    }
+
+    const uint32_t *Context::galois_table(uint32_t elt)
+    {
+        auto it = galois_tables.find(elt);
+        if (it != galois_tables.end())
+            return it->second;
+        auto h = sbh::galois_table_ntt(n, elt);
+        uint32_t *d = nullptr;
+        cuda_check(cudaMalloc(&d, n * sizeof(uint32_t)), "cudaMalloc(galois table)");
+        cuda_check(cudaMemcpy(d, h.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "upload galois table");
+        table_bytes += n * sizeof(uint32_t);
+        galois_tables[elt] = d;
+        return d;
+    }
+
+    static Tw to_tw(const sbh::TwPair &p)
+    {
+        Tw t;
+        t.w = p.w;
+        t.wq = p.wq;
+        return t;
+    }
+
+    static void upload_prime(Context &c, const sbh::PrimeTables &pt, std::vector<PrimeDev> &hp)
+    {
+        static_assert(sizeof(sbh::TwPair) == sizeof(Tw), "layout");
+        Tw *f = nullptr, *i = nullptr;
+        size_t bytes = c.n * sizeof(Tw);
+        cuda_check(cudaMalloc(&f, bytes), "cudaMalloc(twiddles)");
+        cuda_check(cudaMalloc(&i, bytes), "cudaMalloc(twiddles)");
+        cuda_check(cudaMemcpy(f, pt.fwd.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles");
+        cuda_check(cudaMemcpy(i, pt.inv.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles");
+        c.d_fwd.push_back(f);
+        c.d_inv.push_back(i);
+        c.table_bytes += 2 * bytes;
+        PrimeDev d;
+        d.q = pt.q;
+        d.q2 = 2 * pt.q;
+        d.ratio_lo = pt.ratio_lo;
+        d.ratio_hi = pt.ratio_hi;
+        d.inv_n = to_tw(pt.inv_n);
+        d.inv_n_w = to_tw(pt.inv_n_w);
+        d.fwd = f;
+        d.inv = i;
+        hp.push_back(d);
+    }
+
+    std::unique_ptr<Context> make_context(int scheme, size_t n, const u64 *moduli, size_t k, u64 t, int device)
+    {
+        if (scheme != 1 && scheme != 2)
+            throw std::invalid_argument("unsupported scheme");
+        if (n < 2 || (n & (n - 1)) || n > 131072)
+            throw std::invalid_argument("poly_modulus_degree is invalid");
+        if (k < 1 || k > 256)
+            throw std::invalid_argument("coeff_modulus size is invalid");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError("no CUDA device available (libseal_b200 has no CPU fallback)");
+        if (device < 0 || device >= ndev)
+            throw std::invalid_argument("device index out of range");
+        cuda_check(cudaSetDevice(device), "cudaSetDevice");
+        cudaDeviceProp prop;
+        cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+        if (prop.major != 10)
+            throw CudaError("libseal_b200 is built for sm_100a (B200) only; found compute capability " +
+                            std::to_string(prop.major) + "." + std::to_string(prop.minor));
+
+        auto c = std::make_unique<Context>();
+        c->scheme = scheme, c->n = n, c->k = k, c->t = t, c->device = device, c->logn = sbh::ilog2(n);
+        if (const char *e = std::getenv("SB200_SCRATCH_MB"))
+            c->scratch_budget = static_cast<size_t>(std::max(64L, std::atol(e))) << 20;
+        for (size_t i = 0; i < k; i++)
+        {
+            if (moduli[i] >> 61)
+                throw std::invalid_argument("coeff_modulus primes must be below 2^61");
+            for (size_t j = 0; j < i; j++)
+                if (moduli[j] == moduli[i])
+                    throw std::invalid_argument("coeff_modulus primes must be distinct");
+            c->q.push_back(moduli[i]);
+        }
+        if (scheme == 1)
+        {
+            if (t < 2 || (t >> 60))
+                throw std::invalid_argument("plain_modulus is invalid");
+            // all levels use prefixes of one auxiliary list: [m_sk, gamma, B_0, B_1, ...]  (rns.cpp:626-632)
+            size_t max_nb = (k > 1 ? k - 1 : 1) + 1;
+            c->aux = sbh::get_primes(2 * static_cast<u64>(n), 61, max_nb + 2);
+        }
+        std::vector<PrimeDev> hp;
+        c->tabs.resize(k + c->aux.size());
+        for (size_t i = 0; i < k; i++)
+            c->tabs[i].build(n, c->q[i]);
+        for (size_t i = 0; i < c->aux.size(); i++)
+            if (i != 1) // gamma is only used by decryption
+                c->tabs[k + i].build(n, c->aux[i]);
+        for (size_t i = 0; i < c->tabs.size(); i++)
+        {
+            if (c->tabs[i].q == 0)
+            {
+                c->d_fwd.push_back(nullptr);
+                c->d_inv.push_back(nullptr);
+                hp.push_back(PrimeDev{});
+                continue;
+            }
+            upload_prime(*c, c->tabs[i], hp);
+        }
+        c->nprimes = hp.size();
+        cuda_check(cudaMalloc(&c->d_primes, hp.size() * sizeof(PrimeDev)), "cudaMalloc(primes)");
+        cuda_check(cudaMemcpy(c->d_primes, hp.data(), hp.size() * sizeof(PrimeDev), cudaMemcpyHostToDevice), "upload primes");
+        // q_j^-1 mod q_i (rns.cpp:767-776 for every level at once)
+        std::vector<Tw> invq(k * k);
+        for (size_t j = 0; j < k; j++)
+            for (size_t i = 0; i < k; i++)
+            {
+                Tw tw{ 0, 0 };
+                if (i != j)
+                {
+                    u64 v = 0;
+                    if (!sbh::invmod(c->q[j] % c->q[i], c->q[i], v))
+                        throw std::logic_error("invalid rns bases");
+                    tw.w = v;
+                    tw.wq = sbh::shoup(v, c->q[i]);
+                }
+                invq[j * k + i] = tw;
+            }
+        cuda_check(cudaMalloc(&c->d_invq, invq.size() * sizeof(Tw)), "cudaMalloc(invq)");
+        cuda_check(cudaMemcpy(c->d_invq, invq.data(), invq.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload invq");
+        c->table_bytes += hp.size() * sizeof(PrimeDev) + invq.size() * sizeof(Tw);
+        return c;
+    }
+
+    // --------------------------------------------------------------------------------- source accessors ----
+    // A batch of [L][n] polynomials, optionally seen through a Galois automorphism (galois.cpp:148-218).
+    struct Src
+    {
+        const u64 *p = nullptr;
+        long long bstride = 0; // words between consecutive batch items
+        const uint32_t *perm = nullptr; // NTT-form: out[i] = in[perm[i]]
+        uint32_t ginv = 0;              // coefficient form: inverse Galois element mod 2n (0 = identity)
+        int logn = 0;
+
+        __device__ __forceinline__ u64 get(int b, int J, int idx, u64 qJ) const
+        {
+            const u64 *r = p + b * bstride + (static_cast<long long>(J) << logn);
+            if (perm)
+                return r[perm[idx]];
+            if (ginv)
+            {
+                uint32_t ip = (static_cast<uint32_t>(idx) * ginv) & ((2u << logn) - 1u);
+                u64 v = r[ip & ((1u << logn) - 1u)];
+                if (ip >> logn)
+                    v = v ? qJ - v : 0;
+                return v;
+            }
+            return r[idx];
+        }
+    };
+
+    // -------------------------------------------------------------------------------------- NTT functors ----
+    struct OpBase
+    {
+        int logn;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+    };
+
+    // plain slab transform, in place: Evaluator::transform_to_ntt_inplace / transform_from_ntt_inplace
+    template <bool INVERSE>
+    struct OpSlab
+    {
+        u64 *data;
+        int logn, L;
+        const int *pid_tab; // optional prime-id table (BEHZ bases); null = identity
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const
+        {
+            int i = row % L;
+            return pid_tab ? pid_tab[i] : i;
+        }
+        __device__ __forceinline__ u64 *rowp(int row) const { return data + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
+        {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(rowp(row) + idx0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                ulonglong2 v = p[j];
+                a[2 * j] = v.x, a[2 * j + 1] = v.y;
+            }
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return rowp(row); }
+        __device__ __forceinline__ u64 canon(u64 v, const PrimeDev &P) const
+        {
+            return INVERSE ? csub(v, P.q) : csub(csub(v, P.q2), P.q);
+        }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            rowp(row)[idx] = canon(v, P);
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(rowp(row) + idx0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                p[j] = make_ulonglong2(canon(a[2 * j], P), canon(a[2 * j + 1], P));
+        }
+    };
+
+    void op_ntt_rows(Context &c, bool inverse, u64 *d, size_t rows, size_t L, const int *pid_tab, cudaStream_t st)
+    {
+        if (inverse)
+        {
+            OpSlab<true> op{ d, c.logn, static_cast<int>(L), pid_tab };
+            cuda_check(launch_ntt_inv(op, static_cast<int>(rows), c.logn, c.d_primes, st, c.stats), "ntt_inv");
+        }
+        else
+        {
+            OpSlab<false> op{ d, c.logn, static_cast<int>(L), pid_tab };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(rows), c.logn, c.d_primes, st, c.stats), "ntt_fwd");
+        }
+    }
+
+    void op_ntt(Context &c, bool inverse, size_t L, size_t size, size_t batch, u64 *d, cudaStream_t st)
+    {
+        // keep grid.x below 2^31 and launches reasonably sized
+        const size_t rows = batch * size * L, max_rows = size_t(1) << 20;
+        for (size_t r0 = 0; r0 < rows; r0 += max_rows - (max_rows % L))
+        {
+            size_t cnt = std::min(rows - r0, max_rows - (max_rows % L));
+            op_ntt_rows(c, inverse, d + r0 * c.n, cnt, L, nullptr, st);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------ CKKS multiply ----
+    // (x0 y0, x0 y1 + x1 y0, x1 y1) per prime per coefficient; evaluator.cpp:634-662.
+    // FUSED: poly 0,1 go to out (stride 2 polys) and poly 2 to c2 ([b][L][n]) -- the key-switch target.
+    template <bool FUSED>
+    __global__ void __launch_bounds__(256) ckks_tensor_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *out, u64 *c2,
+                                                               const PrimeDev *__restrict__ primes, int logn, int L, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over batch*L*n
+        if (e >= total)
+            return;
+        const long long poly = static_cast<long long>(L) << logn;
+        const long long bidx = e / poly, r = e % poly;
+        const int i = static_cast<int>(r >> logn);
+        const PrimeDev P = primes[i];
+        const u64 *pa = a + bidx * 2 * poly + r, *pb = b + bidx * 2 * poly + r;
+        u64 x0 = pa[0], x1 = pa[poly], y0 = pb[0], y1 = pb[poly];
+        u64 d0 = mulmod_barrett(x0, y0, P);
+        u64 lo = 0, hi = 0;
+        mac128(lo, hi, x0, y1);
+        mac128(lo, hi, x1, y0);
+        u64 d1 = barrett128(lo, hi, P.q, P.ratio_lo, P.ratio_hi);
+        u64 d2 = mulmod_barrett(x1, y1, P);
+        if (FUSED)
+        {
+            u64 *po = out + bidx * 2 * poly + r;
+            po[0] = d0, po[poly] = d1;
+            c2[bidx * poly + r] = d2;
+        }
+        else
+        {
+            u64 *po = out + bidx * 3 * poly + r;
+            po[0] = d0, po[poly] = d1, po[2 * poly] = d2;
+        }
+    }
+
+    static void launch_tensor(Context &c, bool fused, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out, u64 *c2,
+                              cudaStream_t st)
+    {
+        long long total = static_cast<long long>(batch) * L * c.n;
+        unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        if (fused)
+            ckks_tensor_kernel<true><<<blocks, 256, 0, st>>>(a, b, out, c2, c.d_primes, c.logn, static_cast<int>(L), total);
+        else
+            ckks_tensor_kernel<false><<<blocks, 256, 0, st>>>(a, b, out, c2, c.d_primes, c.logn, static_cast<int>(L), total);
+        c.stats.launches++;
+        cuda_check(cudaGetLastError(), "ckks_tensor_kernel");
+    }
+
+    void op_ckks_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st)
+    {
+        const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (L * c.n));
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            size_t nb = std::min(step, batch - b0);
+            launch_tensor(c, false, L, nb, a + b0 * 2 * L * c.n, b + b0 * 2 * L * c.n, out3 + b0 * 3 * L * c.n, nullptr, st);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------- key switching ----
+    // (1) target -> coefficient form (CKKS only): rows (b, J); evaluator.cpp:2651-2658
+    struct OpKsIntt
+    {
+        Src tgt;
+        u64 *D; // [B][L][n]
+        int logn, L;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const { return row % L; }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
+        {
+            return tgt.get(row / L, row % L, idx, P.q);
+        }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = load1(row, idx0 + j, P);
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return D + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const { mid(row)[idx] = csub(v, P.q); }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+
+    // (2) digit J re-reduced modulo output prime I and transformed: rows (b, I, J); evaluator.cpp:2682-2702
+    struct OpKsDigit
+    {
+        Src dsrc; // coefficient-form digits: D (CKKS) or the target itself (BFV)
+        u64 *E;   // [B][L+1][L][n]
+        const PrimeDev *primes;
+        int logn, L, k, ntt_in;
+        __device__ __forceinline__ bool skip(int row) const { return ntt_in && ((row / L) % (L + 1)) == (row % L); }
+        __device__ __forceinline__ int pid(int row) const
+        {
+            int I = (row / L) % (L + 1);
+            return I == L ? k - 1 : I;
+        }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
+        {
+            int J = row % L, b = row / (L * (L + 1));
+            u64 qJ = primes[J].q;
+            u64 v = dsrc.get(b, J, idx, qJ);
+            return qJ > P.q ? barrett64(v, P.q, P.ratio_hi) : v; // evaluator.cpp:2690-2698
+        }
+        __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
+        __device__ __forceinline__ u64 *mid(int row) const { return E + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            mid(row)[idx] = csub(csub(v, P.q2), P.q);
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(mid(row) + idx0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                p[j] = make_ulonglong2(csub(csub(a[2 * j], P.q2), P.q), csub(csub(a[2 * j + 1], P.q2), P.q));
+        }
+    };
+
+    // (3) multiply-accumulate with the key, 128-bit lazy sums, one Barrett at the end; evaluator.cpp:2705-2755
+    //     grid = (B, n/256, L+1): consecutive CTAs share the key tile of (I, coefficient range) through L2.
+    __global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
+                                                          u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k)
+    {
+        const int n = 1 << logn;
+        const int b = blockIdx.x, I = blockIdx.z;
+        const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+        if (idx >= n)
+            return;
+        const int ki = (I == L) ? k - 1 : I;
+        const PrimeDev P = primes[ki];
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+        const u64 *e = E + ((static_cast<long long>(b) * (L + 1) + I) * L << logn) + idx;
+        for (int J = 0; J < L; J++)
+        {
+            u64 x = (ntt_in && I == J) ? tgt.get(b, J, idx, P.q) : e[static_cast<long long>(J) << logn];
+            const u64 *kr = key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + idx;
+            mac128(lo0, hi0, x, __ldg(kr));
+            mac128(lo1, hi1, x, __ldg(kr + (static_cast<long long>(k) << logn)));
+        }
+        u64 *o = Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + idx;
+        o[0] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
+        o[static_cast<long long>(L + 1) << logn] = barrett128(lo1, hi1, P.q, P.ratio_lo, P.ratio_hi);
+    }
+
+    // (4a) special-prime component back to coefficients, + floor(q_sp/2) for rounding; evaluator.cpp:2809-2817.
+    //      Also used by rescale with the last data prime (rns.cpp:855-860).  rows = (b, c)
+    struct OpTopIntt
+    {
+        const u64 *src;          // row (b,c) at src + b*bstride + c*pstride
+        long long bstride, pstride;
+        u64 *U;                  // [B][2][n]
+        int logn, pid_top;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int) const { return pid_top; }
+        __device__ __forceinline__ const u64 *rowp(int row) const { return src + (row >> 1) * bstride + (row & 1) * pstride; }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
+        {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(rowp(row) + idx0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                ulonglong2 v = p[j];
+                a[2 * j] = v.x, a[2 * j + 1] = v.y;
+            }
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return U + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            mid(row)[idx] = csub(csub(v, P.q) + (P.q >> 1), P.q);
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+
+    // in-place INTT of rows (b, c, i<L) of the accumulated products (BFV branch, evaluator.cpp:2854)
+    struct OpProdIntt
+    {
+        u64 *Pp; // [B][2][L+1][n]
+        int logn, L;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const { return row % L; }
+        __device__ __forceinline__ u64 *rowp(int row) const
+        {
+            return Pp + ((static_cast<long long>(row / L) * (L + 1) + row % L) << logn);
+        }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = rowp(row)[idx0 + j];
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return rowp(row); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const { rowp(row)[idx] = csub(v, P.q); }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+
+    // what the mod-down result is added to (the ciphertext being updated)
+    struct BaseSrc
+    {
+        Src s;            // polys 0,1 of the base ciphertext: poly c of item b at s.p + b*s.bstride + c*pstride
+        long long pstride = 0;
+        int c1_zero = 0;  // apply_galois: component 1 starts from zero (evaluator.cpp:2487)
+        int present = 0;
+        __device__ __forceinline__ u64 get(int b, int c, int i, int idx, u64 q) const
+        {
+            if (!present || (c == 1 && c1_zero))
+                return 0;
+            Src t = s;
+            t.p += c * pstride;
+            return t.get(b, i, idx, q);
+        }
+    };
+
+    // (4b) per data prime: NTT((u mod q_i) - (half mod q_i)), subtract from the accumulated component, scale by
+    //      q_top^-1 and add into the ciphertext; evaluator.cpp:2819-2864 (CKKS branch), rns.cpp:863-900 (rescale).
+    //      rows = (b, c, i), i < Lout
+    struct OpModDownFwd
+    {
+        const u64 *U;            // [B][2][n]: (INTT(top component) + half) mod q_top
+        const u64 *X;            // component being corrected: X + b*x_bs + c*x_ps + i*n
+        long long x_bs, x_ps;
+        u64 *T;                  // intermediate rows [B][2][Lout][n]
+        u64 *out;                // out + b*o_bs + c*o_ps + i*n
+        long long o_bs, o_ps;
+        const Tw *inv_top;       // q_top^-1 mod q_i, i < Lout
+        BaseSrc base;
+        u64 q_top;
+        int logn, Lout;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const { return row % Lout; }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
+        {
+            u64 u = U[(static_cast<long long>(row / Lout) << logn) + idx];
+            if (q_top > P.q)
+                u = barrett64(u, P.q, P.ratio_hi);
+            u64 half_mod = barrett64(q_top >> 1, P.q, P.ratio_hi);
+            return u + (P.q - half_mod); // < 2q (or < q_top + q <= 2q when no reduction was needed)
+        }
+        __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
+        __device__ __forceinline__ u64 *mid(int row) const { return T + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            const int i = row % Lout, bc = row / Lout, b = bc >> 1, c = bc & 1;
+            u64 t = csub(csub(v, P.q2), P.q);
+            u64 x = X[b * x_bs + c * x_ps + (static_cast<long long>(i) << logn) + idx];
+            u64 r = mul_shoup(x + P.q - t, inv_top[i], P.q);
+            r = csub(r + base.get(b, c, i, idx, P.q), P.q);
+            out[b * o_bs + c * o_ps + (static_cast<long long>(i) << logn) + idx] = r;
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+
+    // coefficient-form mod-down (BFV): evaluator.cpp:2819-2864 (bfv branch) and rns.cpp:789-828 (mod_switch).
+    // ADD_HALF: U holds the raw top component (mod_switch); otherwise U already includes + half (key switch).
+    template <bool ADD_HALF>
+    __global__ void __launch_bounds__(256) moddown_coeff_kernel(const u64 *__restrict__ U, long long u_bs, long long u_ps, const u64 *X,
+                                                                 long long x_bs, long long x_ps, u64 *out, long long o_bs, long long o_ps,
+                                                                 const Tw *__restrict__ inv_top, BaseSrc base, u64 q_top,
+                                                                 const PrimeDev *__restrict__ primes, int logn, int Lout, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*2*Lout*n
+        if (e >= total)
+            return;
+        const int idx = static_cast<int>(e & ((1 << logn) - 1));
+        const long long row = e >> logn;
+        const int i = static_cast<int>(row % Lout), bc = static_cast<int>(row / Lout), b = bc >> 1, c = bc & 1;
+        const PrimeDev P = primes[i];
+        u64 u = U[b * u_bs + c * u_ps + idx];
+        if (ADD_HALF)
+            u = csub(u + (q_top >> 1), q_top);
+        if (q_top > P.q)
+            u = barrett64(u, P.q, P.ratio_hi);
+        else
+            u = csub(u, P.q);
+        u64 t = u + P.q - barrett64(q_top >> 1, P.q, P.ratio_hi); // in (0, 2q)
+        u64 x = X[b * x_bs + c * x_ps + (static_cast<long long>(i) << logn) + idx];
+        u64 r = mul_shoup(x + P.q2 - t, inv_top[i], P.q);
+        r = csub(r + base.get(b, c, i, idx, P.q), P.q);
+        out[b * o_bs + c * o_ps + (static_cast<long long>(i) << logn) + idx] = r;
+    }
+
+    struct KsScratch
+    {
+        u64 *D, *E, *Pp, *U, *T, *C2;
+    };
+    static size_t ks_words_per_ct(const Context &c, size_t L, bool need_c2)
+    {
+        return c.n * (L + (L + 1) * L + 2 * (L + 1) + 2 + 2 * L + (need_c2 ? L : 0));
+    }
+    static KsScratch ks_carve(Context &c, size_t L, size_t B, bool need_c2)
+    {
+        u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64)));
+        KsScratch s;
+        s.D = p, p += B * L * c.n;
+        s.E = p, p += B * (L + 1) * L * c.n;
+        s.Pp = p, p += B * 2 * (L + 1) * c.n;
+        s.U = p, p += B * 2 * c.n;
+        s.T = p, p += B * 2 * L * c.n;
+        s.C2 = need_c2 ? p : nullptr;
+        return s;
+    }
+    static size_t ks_chunk(const Context &c, size_t L, size_t batch, bool need_c2)
+    {
+        size_t per = ks_words_per_ct(c, L, need_c2) * sizeof(u64);
+        size_t chunk = std::max<size_t>(1, c.scratch_budget / per);
+        // keep row counts of a launch inside int range
+        chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 30) / ((L + 1) * L * c.n)));
+        chunk = std::min<size_t>(chunk, 32768);
+        return std::min(chunk, batch);
+    }
+
+    static void check_ks_args(const Context &c, size_t L, const KSwitchKey &key)
+    {
+        if (c.k < 2)
+            throw std::logic_error("keyswitching is not supported by the context"); // evaluator.cpp:2581-2584
+        if (L < 1 || L > c.k - 1)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        if (key.ctx != &c)
+            throw std::invalid_argument("parameter mismatch"); // evaluator.cpp:2587-2590
+        if (key.digits < L)
+            throw std::invalid_argument("kswitch_keys inner dimension is too small"); // evaluator.cpp:2635-2638
+    }
+
+    // ct[b] (= base) += key-switch(target[b]) for a chunk of B ciphertexts; writes out[b][2][L][n].
+    static void key_switch_chunk(Context &c, size_t L, size_t B, const KsScratch &s, Src target, const KSwitchKey &key, BaseSrc base,
+                                 u64 *out, cudaStream_t st)
+    {
+        const int n = static_cast<int>(c.n), Li = static_cast<int>(L), ki = static_cast<int>(c.k);
+        const bool ntt_in = (c.scheme != 1);
+        Src dsrc = target;
+        if (ntt_in)
+        {
+            OpKsIntt op{ target, s.D, c.logn, Li };
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats), "ks intt");
+            dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
+        }
+        {
+            OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0 };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats), "ks digit ntt");
+        }
+        {
+            int threads = std::min(n, 256);
+            dim3 grid(static_cast<unsigned>(B), (n + threads - 1) / threads, static_cast<unsigned>(L + 1));
+            ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki);
+            c.stats.launches++;
+            cuda_check(cudaGetLastError(), "ks_mac_kernel");
+        }
+        const long long pp_ps = static_cast<long long>(L + 1) * n, pp_bs = 2 * pp_ps;
+        {
+            OpTopIntt op{ s.Pp + static_cast<long long>(L) * n, pp_bs, pp_ps, s.U, c.logn, ki - 1 };
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats), "ks top intt");
+        }
+        const Tw *inv_top = c.d_invq + (c.k - 1) * c.k;
+        const long long o_ps = static_cast<long long>(L) * n, o_bs = 2 * o_ps;
+        if (ntt_in)
+        {
+            OpModDownFwd op{ s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats), "ks moddown ntt");
+        }
+        else
+        {
+            OpProdIntt op{ s.Pp, c.logn, Li };
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats), "ks prod intt");
+            long long total = static_cast<long long>(B) * 2 * L * n;
+            moddown_coeff_kernel<false><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+                s.U, 2LL * n, n, s.Pp, pp_bs, pp_ps, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.d_primes, c.logn, Li, total);
+            c.stats.launches++;
+            cuda_check(cudaGetLastError(), "moddown_coeff_kernel");
+        }
+    }
+
+    void op_relinearize(Context &c, size_t L, size_t batch, const u64 *in3, const KSwitchKey &key, u64 *out2, cudaStream_t st)
+    {
+        check_ks_args(c, L, key);
+        const size_t poly = L * c.n, chunk = ks_chunk(c, L, batch, false);
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            size_t B = std::min(chunk, batch - b0);
+            KsScratch s = ks_carve(c, L, B, false);
+            const u64 *in = in3 + b0 * 3 * poly;
+            Src target{ in + 2 * poly, static_cast<long long>(3 * poly), nullptr, 0, c.logn };
+            BaseSrc base;
+            base.s = Src{ in, static_cast<long long>(3 * poly), nullptr, 0, c.logn };
+            base.pstride = static_cast<long long>(poly);
+            base.present = 1;
+            key_switch_chunk(c, L, B, s, target, key, base, out2 + b0 * 2 * poly, st);
+        }
+    }
+
+    void op_multiply_relinearize(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, const KSwitchKey &key, u64 *out2,
+                                 cudaStream_t st)
+    {
+        check_ks_args(c, L, key);
+        const size_t poly = L * c.n;
+        if (c.scheme == 1)
+        {
+            // BFV: BEHZ multiply into a size-3 scratch, then relinearize (no fusion across the base conversion)
+            const size_t chunk = std::min(batch, std::max<size_t>(1, (size_t(1) << 30) / (3 * poly * sizeof(u64))));
+            u64 *tmp = nullptr;
+            cuda_check(cudaMallocAsync(reinterpret_cast<void **>(&tmp), chunk * 3 * poly * sizeof(u64), st), "cudaMallocAsync");
+            for (size_t b0 = 0; b0 < batch; b0 += chunk)
+            {
+                size_t B = std::min(chunk, batch - b0);
+                op_bfv_multiply(c, L, B, a + b0 * 2 * poly, b + b0 * 2 * poly, tmp, st);
+                op_relinearize(c, L, B, tmp, key, out2 + b0 * 2 * poly, st);
+            }
+            cuda_check(cudaFreeAsync(tmp, st), "cudaFreeAsync");
+            return;
+        }
+        const size_t chunk = ks_chunk(c, L, batch, true);
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            size_t B = std::min(chunk, batch - b0);
+            KsScratch s = ks_carve(c, L, B, true);
+            u64 *o = out2 + b0 * 2 * poly;
+            launch_tensor(c, true, L, B, a + b0 * 2 * poly, b + b0 * 2 * poly, o, s.C2, st);
+            Src target{ s.C2, static_cast<long long>(poly), nullptr, 0, c.logn };
+            BaseSrc base;
+            base.s = Src{ o, static_cast<long long>(2 * poly), nullptr, 0, c.logn }; // read-modify-write of (c0, c1)
+            base.pstride = static_cast<long long>(poly);
+            base.present = 1;
+            key_switch_chunk(c, L, B, s, target, key, base, o, st);
+        }
+    }
+
+    void op_apply_galois(Context &c, size_t L, size_t batch, const u64 *in2, uint32_t elt, const KSwitchKey &key, u64 *out2,
+                         cudaStream_t st)
+    {
+        check_ks_args(c, L, key);
+        if (!(elt & 1) || elt >= 2 * c.n)
+            throw std::invalid_argument("Galois element is not valid"); // evaluator.cpp:2424-2427
+        if (in2 == out2)
+            throw std::invalid_argument("apply_galois: in and out must not alias");
+        const size_t poly = L * c.n, chunk = ks_chunk(c, L, batch, false);
+        const uint32_t *perm = nullptr;
+        uint32_t ginv = 0;
+        if (c.scheme == 1)
+        {
+            u64 gi = 0;
+            sbh::invmod(elt, 2 * c.n, gi);
+            ginv = static_cast<uint32_t>(gi);
+            if (ginv == 1)
+                ginv = 0;
+        }
+        else
+            perm = c.galois_table(elt);
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            size_t B = std::min(chunk, batch - b0);
+            KsScratch s = ks_carve(c, L, B, false);
+            const u64 *in = in2 + b0 * 2 * poly;
+            Src target{ in + poly, static_cast<long long>(2 * poly), perm, ginv, c.logn };
+            BaseSrc base;
+            base.s = Src{ in, static_cast<long long>(2 * poly), perm, ginv, c.logn };
+            base.pstride = static_cast<long long>(poly);
+            base.c1_zero = 1;
+            base.present = 1;
+            key_switch_chunk(c, L, B, s, target, key, base, out2 + b0 * 2 * poly, st);
+        }
+    }
+
+    // ------------------------------------------------------------------------- rescale / modulus switching ----
+    void op_rescale(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st)
+    {
+        if (c.scheme != 2)
+            throw std::invalid_argument("unsupported operation for scheme type"); // evaluator.cpp:1533
+        if (L < 2 || L > c.k)
+            throw std::invalid_argument("end of modulus switching chain reached"); // evaluator.cpp:1521
+        const int n = static_cast<int>(c.n);
+        const size_t Lout = L - 1;
+        const size_t per = (2 + 2 * Lout) * c.n * sizeof(u64);
+        size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (2 * L * c.n)));
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            size_t B = std::min(chunk, batch - b0);
+            u64 *U = static_cast<u64 *>(c.ensure_scratch(per * B));
+            u64 *T = U + B * 2 * c.n;
+            const u64 *in = in2 + b0 * 2 * L * c.n;
+            const long long i_ps = static_cast<long long>(L) * n, i_bs = 2 * i_ps;
+            OpTopIntt top{ in + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
+            cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats), "rescale intt");
+            BaseSrc none;
+            const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
+            OpModDownFwd op{ U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
+                             c.logn, static_cast<int>(Lout) };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats), "rescale ntt");
+        }
+    }
+
+    void op_mod_switch(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st)
+    {
+        if (L < 2 || L > c.k)
+            throw std::invalid_argument("end of modulus switching chain reached");
+        const size_t Lout = L - 1;
+        if (c.scheme == 2)
+        {
+            // CKKS mod_switch_drop_to_next: drop the last RNS component (evaluator.cpp:1296-1358)
+            cuda_check(cudaMemcpy2DAsync(out2, Lout * c.n * sizeof(u64), in2, L * c.n * sizeof(u64), Lout * c.n * sizeof(u64), batch * 2,
+                                         cudaMemcpyDeviceToDevice, st),
+                       "mod_switch copy");
+            return;
+        }
+        const int n = static_cast<int>(c.n);
+        const long long i_ps = static_cast<long long>(L) * n, o_ps = static_cast<long long>(Lout) * n;
+        const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (2 * L * c.n));
+        BaseSrc none;
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            size_t B = std::min(step, batch - b0);
+            const u64 *in = in2 + b0 * 2 * L * c.n;
+            long long total = static_cast<long long>(B) * 2 * Lout * n;
+            moddown_coeff_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+                in + (L - 1) * c.n, 2 * i_ps, i_ps, in, 2 * i_ps, i_ps, out2 + b0 * 2 * Lout * c.n, 2 * o_ps, o_ps,
+                c.d_invq + (L - 1) * c.k, none, c.q[L - 1], c.d_primes, c.logn, static_cast<int>(Lout), total);
+            c.stats.launches++;
+            cuda_check(cudaGetLastError(), "moddown_coeff_kernel");
+        }
+    }
+} // namespace sb

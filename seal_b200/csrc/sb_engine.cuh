@@ -1,0 +1,68 @@
+// seal_b200/csrc/sb_engine.cuh -- device context + operation drivers (declarations).
+#pragma once
+#include "sb_host.hpp"
+#include "sb_ntt.cuh"
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace sb
+{
+    struct CudaError : std::runtime_error
+    {
+        using std::runtime_error::runtime_error;
+    };
+    void cuda_check(cudaError_t e, const char *what);
+
+    // device copy of sbh::BehzLevel (BFV multiply), see sb_bfv.cu
+    struct BehzDev;
+
+    struct KSwitchKey
+    {
+        struct Context *ctx = nullptr;
+        u64 *d_key = nullptr; // [digits][2][k][n]
+        size_t digits = 0;
+    };
+
+    struct Context
+    {
+        int scheme = 0, device = 0, logn = 0;
+        size_t n = 0, k = 0;
+        u64 t = 0;
+        std::vector<u64> q;                  // key-level primes
+        std::vector<sbh::PrimeTables> tabs;  // host tables; ids [0,k) = q primes, [k, ...) = BEHZ auxiliary primes
+        std::vector<u64> aux;                // auxiliary prime list [m_sk, gamma, B_0, B_1, ...] (BFV)
+        std::vector<Tw *> d_fwd, d_inv;      // per prime id
+        PrimeDev *d_primes = nullptr;        // [nprimes]
+        size_t nprimes = 0;
+        Tw *d_invq = nullptr;                // [k][k]: d_invq[j*k+i] = q_j^-1 mod q_i  (i != j)
+        std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
+        std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
+        void *scratch = nullptr;
+        size_t scratch_bytes = 0, table_bytes = 0, scratch_budget = size_t(8) << 30;
+        LaunchStats stats;
+        std::mutex mu;
+
+        ~Context();
+        void *ensure_scratch(size_t bytes);
+        const uint32_t *galois_table(uint32_t elt);
+        size_t prime_id_aux(size_t aux_index) const { return k + aux_index; }
+    };
+
+    std::unique_ptr<Context> make_context(int scheme, size_t n, const u64 *moduli, size_t k, u64 t, int device);
+
+    // drivers (all stream-ordered, no synchronisation); slabs as documented in include/seal_b200.h
+    void op_ntt(Context &c, bool inverse, size_t L, size_t size, size_t batch, u64 *d, cudaStream_t st);
+    void op_ckks_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st);
+    void op_bfv_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st);
+    void op_relinearize(Context &c, size_t L, size_t batch, const u64 *in3, const KSwitchKey &key, u64 *out2, cudaStream_t st);
+    void op_multiply_relinearize(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, const KSwitchKey &key,
+                                 u64 *out2, cudaStream_t st);
+    void op_rescale(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st);
+    void op_mod_switch(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st);
+    void op_apply_galois(Context &c, size_t L, size_t batch, const u64 *in2, uint32_t elt, const KSwitchKey &key, u64 *out2,
+                         cudaStream_t st);
+    const sbh::BehzLevel &behz_host(Context &c, size_t L);
+} // namespace sb

@@ -1,0 +1,503 @@
+// seal_b200/csrc/sb_ntt.cuh -- batched negacyclic NTT / inverse NTT kernels for sm_100a.
+//
+// Replaces the reference's DWTHandler::transform_to_rev / transform_from_rev (util/dwthandler.h:94-356) driven by
+// ntt_negacyclic_harvey(_lazy) / inverse_ntt_negacyclic_harvey(_lazy) (util/ntt.cpp:394-475).  Same mathematical
+// transform (psi = minimal primitive 2n-th root, output of the forward transform in bit-reversed order), different
+// schedule:
+//
+//   n = NA * 256.  The log2(NA) stages whose butterflies span more than 256 coefficients run in a "column pass":
+//   a CTA owns NA rows x C columns (4096 coefficients, C = 4096/NA) in shared memory, every thread keeps 8
+//   coefficients in registers and does radix-8 (3 stages) per register pass; the NA-1 twiddles of those stages are the
+//   same for every column and are staged to shared memory with one TMA bulk copy.  The 8 stages that stay inside a
+//   256-coefficient block run in a "local pass": one warp owns one block, 8 coefficients per lane, exchanges through a
+//   warp-private, XOR-swizzled (bank-conflict-free) 2 KiB shared-memory slice with __syncwarp only.
+//   The two passes meet in an intermediate row that is sized to stay L2-resident.
+//
+// Every kernel is parameterised by an Op functor that supplies the row->prime map, the load (prologue) and the store
+// (epilogue), so digit reduction, rounding corrections, canonicalisation and the key-switch combine are fused into the
+// transforms instead of being separate passes over HBM.
+//
+// Op interface (all __device__):
+//   bool skip(int row)                       row needs no transform (CTA exits)
+//   int  pid(int row)                        prime id of the row
+//   u64  load1(int row, int idx, P)          value of coefficient idx  (forward: < 4q, inverse: < 2q)
+//   void load8(int row, int idx0, u64(&)[8], P)   8 consecutive coefficients
+//   u64 *mid(int row)                        n-word intermediate row between the two passes
+//   void store1(int row, int idx, u64 v, P)  v lazily reduced (forward: < 4q, inverse: < 2q)
+//   void store8(int row, int idx0, u64(&)[8], P)
+#pragma once
+#include "sb_device.cuh"
+
+namespace sb
+{
+    constexpr int kLocalLog = 8;       // 256-coefficient local blocks
+    constexpr int kTile = 4096;        // coefficients per column-pass CTA
+    constexpr int kColThreads = kTile / 8;
+
+    // ------------------------------------------------------------------------------- register radix-8 helpers ----
+    // forward, pair levels in order: (j,j+4), (j,j+2), (j,j+1)
+    template <int NST, class TwF>
+    __device__ __forceinline__ void fwd_regs(u64 (&a)[8], TwF tw, u64 q, u64 q2)
+    {
+        {
+            Tw w = tw(0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                ct_bfly(a[j], a[j + 4], w, q, q2);
+        }
+        if (NST >= 2)
+        {
+            Tw w0 = tw(1, 0), w1 = tw(1, 1);
+            ct_bfly(a[0], a[2], w0, q, q2);
+            ct_bfly(a[1], a[3], w0, q, q2);
+            ct_bfly(a[4], a[6], w1, q, q2);
+            ct_bfly(a[5], a[7], w1, q, q2);
+        }
+        if (NST >= 3)
+        {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                ct_bfly(a[2 * p], a[2 * p + 1], tw(2, p), q, q2);
+        }
+    }
+
+    // inverse, pair levels in order: (j,j+1) [level 0], (j,j+2) [level 1], (j,j+4) [level 2]; FIRST = first level run
+    // FINAL: the (j,j+4) level is the last stage of the whole transform -> fold n^-1 (dwthandler.h:273-313)
+    template <int FIRST, bool FINAL, class TwF>
+    __device__ __forceinline__ void inv_regs(u64 (&a)[8], TwF tw, const PrimeDev &P)
+    {
+        const u64 q = P.q, q2 = P.q2;
+        if (FIRST <= 0)
+        {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                gs_bfly(a[2 * p], a[2 * p + 1], tw(0, p), q, q2);
+        }
+        if (FIRST <= 1)
+        {
+            Tw w0 = tw(1, 0), w1 = tw(1, 1);
+            gs_bfly(a[0], a[2], w0, q, q2);
+            gs_bfly(a[1], a[3], w0, q, q2);
+            gs_bfly(a[4], a[6], w1, q, q2);
+            gs_bfly(a[5], a[7], w1, q, q2);
+        }
+        if (!FINAL)
+        {
+            Tw w = tw(2, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                gs_bfly(a[j], a[j + 4], w, q, q2);
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                u64 u = a[j], v = a[j + 4];
+                a[j] = mul_shoup_lazy(u + v, P.inv_n, q);
+                a[j + 4] = mul_shoup_lazy(u - v + q2, P.inv_n_w, q);
+            }
+        }
+    }
+
+    // warp-private swizzle of a 256-word slice: every access pattern used below hits 16 distinct 8-byte banks per
+    // half-warp (checked exhaustively in tests/test_host_logic.py::test_swizzle_conflict_free)
+    __device__ __forceinline__ int swz(int e)
+    {
+        int b4 = (e >> 4) & 1, b5 = (e >> 5) & 1, b6 = (e >> 6) & 1;
+        return e ^ (b4 | (b5 << 1) | (b6 << 2) | ((b5 ^ b6) << 3));
+    }
+
+    // ---------------------------------------------------------------------------------- forward: column pass ----
+    template <int LOGNA, class Op>
+    __global__ void __launch_bounds__(kColThreads) ntt_fwd_col(Op op, const PrimeDev *__restrict__ primes)
+    {
+        constexpr int NA = 1 << LOGNA;
+        constexpr int C = kTile / NA;
+        constexpr int NST0 = LOGNA % 3;
+        __shared__ __align__(16) u64 tile[kTile];
+        __shared__ __align__(16) Tw tw_s[NA];
+        __shared__ __align__(8) u64 bar;
+
+        const int row = blockIdx.x, col0 = blockIdx.y * C;
+        if (op.skip(row))
+            return;
+        const int tid = threadIdx.x, c = tid % C, ridx = tid / C;
+        const PrimeDev P = primes[op.pid(row)];
+        const u64 q = P.q, q2 = P.q2;
+
+        if (tid == 0)
+            mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(&bar, NA * sizeof(Tw));
+            tma_load_1d(tw_s, P.fwd, NA * sizeof(Tw), &bar); // entries [1, NA) are the twiddles of stages 0..LOGNA-1
+        }
+
+        u64 a[8];
+        {
+            constexpr int g = NA >> 3; // first layout: r = ridx + j*g
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = op.load1(row, ((ridx + j * g) << kLocalLog) + col0 + c, P);
+        }
+        mbar_wait(&bar, 0);
+
+        int prev_g = NA >> 3; // layout of the loaded registers: r = rhi*8g + rlo + j*g with g = NA/8 (rhi = 0)
+        if (NST0 != 0)
+        {
+            // partial first pass: stages 0..NST0-1 in the initial layout
+            auto twf = [&](int lvl, int k) { return tw_s[(1 << lvl) + k]; };
+            fwd_regs<NST0>(a, twf, q, q2);
+        }
+        // full 3-stage passes; the layout changes between passes through the shared tile
+#pragma unroll
+        for (int S = NST0; S < LOGNA; S += 3)
+        {
+            const int g = NA >> (S + 3);
+            const int rhi = ridx / g, rlo = ridx % g;
+            if (g != prev_g)
+            {
+                const int prhi = ridx / prev_g, prlo = ridx % prev_g;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    tile[(prhi * 8 * prev_g + prlo + j * prev_g) * C + c] = a[j];
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = tile[(rhi * 8 * g + rlo + j * g) * C + c];
+                __syncthreads();
+            }
+            const int m = 1 << S;
+            auto twf = [&](int lvl, int k) { return tw_s[(m << lvl) + (rhi << lvl) + k]; };
+            fwd_regs<3>(a, twf, q, q2);
+            prev_g = g;
+        }
+        // last layout has g = 1: r = 8*ridx + j
+        u64 *mid = op.mid(row);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            mid[((8 * ridx + j) << kLocalLog) + col0 + c] = a[j];
+    }
+
+    // ----------------------------------------------------------------------------------- forward: local pass ----
+    template <class Op>
+    __global__ void __launch_bounds__(256) ntt_fwd_local(Op op, const PrimeDev *__restrict__ primes, int na)
+    {
+        __shared__ __align__(16) u64 xs[8][256];
+        const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (op.skip(row))
+            return;
+        const int b = blockIdx.y * 8 + warp;
+        const PrimeDev P = primes[op.pid(row)];
+        const u64 q = P.q, q2 = P.q2;
+        const u64 *src = op.mid(row) + (b << kLocalLog);
+        u64 *x = xs[warp];
+        const Tw *__restrict__ tw = P.fwd;
+        const int t0 = na + b;
+
+        u64 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = src[l + 32 * j];
+        {
+            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << lvl) + k); };
+            fwd_regs<3>(a, twf, q, q2);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            x[swz(l + 32 * j)] = a[j];
+        __syncwarp();
+        {
+            const int hi = l >> 2, lo = l & 3;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = x[swz(32 * hi + lo + 4 * j)];
+            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (3 + lvl)) + (hi << lvl) + k); };
+            fwd_regs<3>(a, twf, q, q2);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                x[swz(32 * hi + lo + 4 * j)] = a[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = x[swz(8 * l + j)];
+        {
+            // strides 2 and 1: pairs (j,j+2) then (j,j+1)
+            Tw wa = ldg_tw(tw + (t0 << 6) + 2 * l), wb = ldg_tw(tw + (t0 << 6) + 2 * l + 1);
+            ct_bfly(a[0], a[2], wa, q, q2);
+            ct_bfly(a[1], a[3], wa, q, q2);
+            ct_bfly(a[4], a[6], wb, q, q2);
+            ct_bfly(a[5], a[7], wb, q, q2);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                ct_bfly(a[2 * p], a[2 * p + 1], ldg_tw(tw + (t0 << 7) + 4 * l + p), q, q2);
+        }
+        op.store8(row, (b << kLocalLog) + 8 * l, a, P);
+    }
+
+    // ----------------------------------------------------------------------------------- inverse: local pass ----
+    template <class Op>
+    __global__ void __launch_bounds__(256) ntt_inv_local(Op op, const PrimeDev *__restrict__ primes, int na)
+    {
+        __shared__ __align__(16) u64 xs[8][256];
+        const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (op.skip(row))
+            return;
+        const int b = blockIdx.y * 8 + warp;
+        const PrimeDev P = primes[op.pid(row)];
+        u64 *x = xs[warp];
+        const Tw *__restrict__ tw = P.inv;
+        const int t0 = na + b;
+
+        u64 a[8];
+        op.load8(row, (b << kLocalLog) + 8 * l, a, P);
+        {
+            // strides 1,2,4
+            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (7 - lvl)) + (l << (2 - lvl)) + k); };
+            inv_regs<0, false>(a, twf, P);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            x[swz(8 * l + j)] = a[j];
+        __syncwarp();
+        {
+            const int hi = l >> 3, lo = l & 7;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = x[swz(64 * hi + lo + 8 * j)];
+            // strides 8,16,32
+            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (4 - lvl)) + (hi << (2 - lvl)) + k); };
+            inv_regs<0, false>(a, twf, P);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                x[swz(64 * hi + lo + 8 * j)] = a[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = x[swz(l + 32 * j)];
+        {
+            // strides 64 (pairs j,j+2) and 128 (pairs j,j+4)
+            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (2 - lvl)) + k); };
+            inv_regs<1, false>(a, twf, P);
+        }
+        u64 *mid = op.mid(row) + (b << kLocalLog);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            mid[l + 32 * j] = a[j];
+    }
+
+    // ---------------------------------------------------------------------------------- inverse: column pass ----
+    template <int LOGNA, class Op>
+    __global__ void __launch_bounds__(kColThreads) ntt_inv_col(Op op, const PrimeDev *__restrict__ primes)
+    {
+        constexpr int NA = 1 << LOGNA;
+        constexpr int C = kTile / NA;
+        constexpr int NSTL = LOGNA % 3; // stages in the (partial) last pass
+        constexpr int NFULL = LOGNA / 3;
+        __shared__ __align__(16) u64 tile[kTile];
+        __shared__ __align__(16) Tw tw_s[NA];
+        __shared__ __align__(8) u64 bar;
+
+        const int row = blockIdx.x, col0 = blockIdx.y * C;
+        if (op.skip(row))
+            return;
+        const int tid = threadIdx.x, c = tid % C, ridx = tid / C;
+        const PrimeDev P = primes[op.pid(row)];
+
+        if (tid == 0)
+            mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(&bar, NA * sizeof(Tw));
+            tma_load_1d(tw_s, P.inv, NA * sizeof(Tw), &bar);
+        }
+        u64 a[8];
+        const u64 *mid = op.mid(row);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = mid[((8 * ridx + j) << kLocalLog) + col0 + c];
+        mbar_wait(&bar, 0);
+
+        int prev_g = 1;
+#pragma unroll
+        for (int p = 0; p < NFULL; p++)
+        {
+            const int U = 3 * p, g = 1 << U;
+            const int rhi = ridx / g, rlo = ridx % g;
+            if (p > 0)
+            {
+                const int prhi = ridx / prev_g, prlo = ridx % prev_g;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    tile[(prhi * 8 * prev_g + prlo + j * prev_g) * C + c] = a[j];
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = tile[(rhi * 8 * g + rlo + j * g) * C + c];
+                __syncthreads();
+            }
+            // level lvl has r-stride g<<lvl: m_r = NA >> (U+lvl+1), group = (rhi << (2-lvl)) + k
+            auto twf = [&](int lvl, int k) { return tw_s[(NA >> (U + lvl + 1)) + (rhi << (2 - lvl)) + k]; };
+            if (NSTL == 0 && p == NFULL - 1)
+                inv_regs<0, true>(a, twf, P);
+            else
+                inv_regs<0, false>(a, twf, P);
+            prev_g = g;
+        }
+        if (NSTL != 0)
+        {
+            constexpr int g = NA >> 3; // layout covering r-strides NA/8, NA/4, NA/2; run only the last NSTL of them
+            {
+                const int prhi = ridx / prev_g, prlo = ridx % prev_g;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    tile[(prhi * 8 * prev_g + prlo + j * prev_g) * C + c] = a[j];
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = tile[(ridx + j * g) * C + c];
+            }
+            // level 1: r-stride NA/4 -> m_r = 2 ; level 2: r-stride NA/2 -> m_r = 1 (final)
+            auto twf = [&](int lvl, int k) { return tw_s[(lvl == 1 ? 2 : 1) + k]; };
+            inv_regs<3 - NSTL, true>(a, twf, P);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                op.store1(row, ((ridx + j * g) << kLocalLog) + col0 + c, a[j], P);
+        }
+        else
+        {
+            constexpr int g = NA >> 3;
+            const int rhi = ridx / g, rlo = ridx % g; // rhi == 0
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                op.store1(row, ((rhi * 8 * g + rlo + j * g) << kLocalLog) + col0 + c, a[j], P);
+        }
+    }
+
+    // ------------------------------------------------------------------- small transforms (n < 4096): one CTA/row ----
+    template <class Op>
+    __global__ void __launch_bounds__(256) ntt_fwd_small(Op op, const PrimeDev *__restrict__ primes, int logn)
+    {
+        extern __shared__ __align__(16) u64 s[];
+        const int n = 1 << logn, row = blockIdx.x;
+        if (op.skip(row))
+            return;
+        const PrimeDev P = primes[op.pid(row)];
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            s[i] = op.load1(row, i, P);
+        __syncthreads();
+        for (int m = 1, gap = n >> 1; m < n; m <<= 1, gap >>= 1)
+        {
+            for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x)
+            {
+                int i = k / gap, j = k % gap, pos = 2 * i * gap + j;
+                ct_bfly(s[pos], s[pos + gap], ldg_tw(P.fwd + m + i), P.q, P.q2);
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            op.store1(row, i, s[i], P);
+    }
+
+    template <class Op>
+    __global__ void __launch_bounds__(256) ntt_inv_small(Op op, const PrimeDev *__restrict__ primes, int logn)
+    {
+        extern __shared__ __align__(16) u64 s[];
+        const int n = 1 << logn, row = blockIdx.x;
+        if (op.skip(row))
+            return;
+        const PrimeDev P = primes[op.pid(row)];
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            s[i] = op.load1(row, i, P);
+        __syncthreads();
+        for (int m = n >> 1, gap = 1; m >= 1; m >>= 1, gap <<= 1)
+        {
+            for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x)
+            {
+                int i = k / gap, j = k % gap, pos = 2 * i * gap + j;
+                if (m > 1)
+                    gs_bfly(s[pos], s[pos + gap], ldg_tw(P.inv + m + i), P.q, P.q2);
+                else
+                {
+                    u64 u = s[pos], v = s[pos + gap];
+                    s[pos] = mul_shoup_lazy(u + v, P.inv_n, P.q);
+                    s[pos + gap] = mul_shoup_lazy(u - v + P.q2, P.inv_n_w, P.q);
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            op.store1(row, i, s[i], P);
+    }
+
+    // ------------------------------------------------------------------------------------------- launchers ----
+    struct LaunchStats
+    {
+        unsigned long long launches = 0;
+    };
+
+    template <class Op>
+    inline cudaError_t launch_ntt_fwd(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls)
+    {
+        if (nrows <= 0)
+            return cudaSuccess;
+        if (logn < 12)
+        {
+            int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
+            ntt_fwd_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
+            ls.launches++;
+            return cudaGetLastError();
+        }
+        const int logna = logn - kLocalLog, na = 1 << logna;
+        dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
+        switch (logna)
+        {
+        case 4: ntt_fwd_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 5: ntt_fwd_col<5, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 6: ntt_fwd_col<6, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 7: ntt_fwd_col<7, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 8: ntt_fwd_col<8, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 9: ntt_fwd_col<9, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        default: return cudaErrorInvalidValue;
+        }
+        ntt_fwd_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        ls.launches += 2;
+        return cudaGetLastError();
+    }
+
+    template <class Op>
+    inline cudaError_t launch_ntt_inv(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls)
+    {
+        if (nrows <= 0)
+            return cudaSuccess;
+        if (logn < 12)
+        {
+            int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
+            ntt_inv_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
+            ls.launches++;
+            return cudaGetLastError();
+        }
+        const int logna = logn - kLocalLog, na = 1 << logna;
+        ntt_inv_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
+        switch (logna)
+        {
+        case 4: ntt_inv_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 5: ntt_inv_col<5, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 6: ntt_inv_col<6, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 7: ntt_inv_col<7, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 8: ntt_inv_col<8, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 9: ntt_inv_col<9, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        default: return cudaErrorInvalidValue;
+        }
+        ls.launches += 2;
+        return cudaGetLastError();
+    }
+} // namespace sb

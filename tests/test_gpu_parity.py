@@ -1,0 +1,182 @@
+"""GPU parity tests proper (-m gpu): every call goes through the C-ABI of libseal_b200.so and is compared word for
+word with (i) committed golden vectors from the real reference, (ii) the plain-C oracle, (iii) the reference library
+itself (oracle/_ref/libsealref.so) where it travelled to the box.  Bar: bit-exact."""
+import numpy as np
+import pytest
+
+import oracle as O
+import refseal as R
+from common import golden, rand_ct
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not present")
+
+
+def sb():
+    import seal_b200
+
+    return seal_b200
+
+
+@pytest.mark.parametrize("name", ["ckks_n128", "ckks_n1024", "bfv_n128"])
+def test_golden_vectors(name):
+    g = golden(name)
+    scheme, n, mods, t = int(g["scheme"]), int(g["n"]), [int(x) for x in g["moduli"]], int(g["t"])
+    k = len(mods)
+    ctx = sb().Context(scheme, n, mods, t)
+    for i in range(k):
+        assert ctx.ntt_tables(i)[0] == int(g["roots"][i])
+    rk = ctx.load_key(g["relin_key"])
+    for L in range(k - 1, 0, -1):
+        a, b = g[f"L{L}_a"], g[f"L{L}_b"]
+        assert (ctx.transform_to_ntt(a) == g[f"L{L}_ntt_fwd_a"]).all()
+        assert (ctx.transform_from_ntt(a) == g[f"L{L}_ntt_inv_a"]).all()
+        m = ctx.multiply(a, b)
+        assert (m == g[f"L{L}_mul"]).all()
+        assert (ctx.multiply_relinearize(a, b, rk) == g[f"L{L}_relin"]).all()
+        assert (ctx.relinearize(g[f"L{L}_mul"], rk) == g[f"L{L}_relin"]).all()
+        if L > 1:
+            ms = ctx.rescale_to_next(a) if scheme == sb().CKKS else ctx.mod_switch_to_next(a)
+            assert (ms == g[f"L{L}_modswitch_a"]).all()
+        for e in g["galois_elts"]:
+            e = int(e)
+            gk = ctx.load_key(g[f"galois_key_{e}"])
+            assert (ctx.apply_galois(a, e, gk) == g[f"L{L}_galois_{e}"]).all()
+
+
+def test_kat_ntt_n2():
+    # native/tests/seal/util/ntt.cpp:75-100 through the CUDA path
+    q = 0xFFFFFFFFFFC0001
+    ctx = sb().Context(sb().CKKS, 2, [q])
+    root, rp, _, irp, _ = ctx.ntt_tables(0)
+    assert int(rp[1]) == 288794978602139552 and (int(rp[1]) * int(irp[1])) % q == 1
+    x = np.array([[[1, 1]]], dtype=np.uint64)
+    assert [int(v) for v in ctx.transform_to_ntt(x)[0, 0]] == [288794978602139553, 864126526004445282]
+    z = np.array([[[1, 0]]], dtype=np.uint64)
+    assert [int(v) for v in ctx.transform_to_ntt(z)[0, 0]] == [1, 1]
+
+
+@pytest.mark.parametrize("logn", [3, 8, 11, 12, 13, 14, 15, 16, 17])
+def test_ntt_vs_oracle_and_roundtrip(logn):
+    n = 1 << logn
+    bits = [50, 60, 36] if logn < 17 else [50, 60, 40]
+    mods = O.coeff_modulus_create(n, bits)
+    ctx = sb().Context(sb().CKKS, n, mods)
+    oc = O.Oracle(O.CKKS, n, mods)
+    for i in range(3):
+        root, rp, _, irp, inv_n = ctx.ntt_tables(i)
+        oroot, orp, oirp, oinv = oc.ntt_tables(i)
+        assert root == oroot and (rp == orp).all() and (irp == oirp).all() and inv_n == oinv
+    rng = np.random.default_rng(logn)
+    x = rand_ct(rng, mods, n, 2, 3, batch=3)
+    f = ctx.transform_to_ntt(x)
+    assert (ctx.transform_from_ntt(f) == x).all()
+    assert (f[1] == oc.ntt_forward(3, x[1])).all()
+    assert (ctx.transform_from_ntt(x)[2] == oc.ntt_inverse(3, x[2])).all()
+    # linearity: NTT(a + b) = NTT(a) + NTT(b)
+    y = rand_ct(rng, mods, n, 2, 3, batch=3)
+    qv = np.array(mods, dtype=np.uint64)[None, None, :, None]
+    s = (x + y) % qv  # primes <= 60 bits so the sum cannot wrap
+    assert (ctx.transform_to_ntt(s) == (f + ctx.transform_to_ntt(y)) % qv).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("n,bits,batch", [(4096, [50, 40, 45, 60], 3), (8192, [54, 54, 54, 54], 4), (16384, [40, 50, 50, 45, 50], 2)])
+def test_ckks_ops_vs_reference(n, bits, batch):
+    mods = R.coeff_modulus_create(n, bits)
+    assert mods == sb().coeff_modulus_create(n, bits)
+    k = len(mods)
+    rc = R.RefContext(R.CKKS, n, mods)
+    ctx = sb().Context(sb().CKKS, n, mods)
+    rk = ctx.load_key(rc.relin_key())
+    rng = np.random.default_rng(n)
+    for L in (k - 1, k - 2, 1):
+        a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+        m = ctx.multiply(a, b)
+        r = ctx.relinearize(m, rk)
+        mr = ctx.multiply_relinearize(a, b, rk)
+        for i in range(batch):
+            assert (m[i] == rc.multiply(L, a[i], b[i])).all()
+            assert (r[i] == rc.relinearize(L, m[i])).all()
+        assert (mr == r).all()
+        if L > 1:
+            rs = ctx.rescale_to_next(a)
+            dr = ctx.mod_switch_to_next(a)
+            for i in range(batch):
+                assert (rs[i] == rc.rescale(L, a[i])).all()
+                assert (dr[i] == rc.mod_switch(L, a[i])).all()
+        for step in (1, -2):
+            e = rc.galois_elt_from_step(step)
+            assert e == ctx.galois_elt_from_step(step)
+            gk = ctx.load_key(rc.galois_key(e))
+            g = ctx.rotate(a, step, gk)
+            for i in range(batch):
+                assert (g[i] == rc.rotate(L, a[i], step)).all()
+
+
+@needs_ref
+def test_bfv_keyswitch_vs_reference():
+    # BFV branches of switch_key_inplace / apply_galois / mod_switch (coefficient form)
+    n = 4096
+    mods = R.coeff_modulus_bfv_default(n)
+    t = R.plain_modulus_batching(n, 20)
+    rb = R.RefContext(R.BFV, n, mods, t)
+    ctx = sb().Context(sb().BFV, n, mods, t)
+    rng = np.random.default_rng(5)
+    L, batch = 2, 3
+    a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+    rk = ctx.load_key(rb.relin_key())
+    m = np.stack([rb.multiply(L, a[i], b[i]) for i in range(batch)])
+    r = ctx.relinearize(m, rk)
+    for i in range(batch):
+        assert (r[i] == rb.relinearize(L, m[i])).all()
+    for step in (1, -3, 0):
+        e = rb.galois_elt_from_step(step)
+        gk = ctx.load_key(rb.galois_key(e))
+        g = ctx.apply_galois(a, e, gk)
+        for i in range(batch):
+            assert (g[i] == rb.apply_galois(L, a[i], e)).all()
+    ms = ctx.mod_switch_to_next(a)
+    for i in range(batch):
+        assert (ms[i] == rb.mod_switch(L, a[i])).all()
+
+
+def test_device_api_matches_host_api():
+    import torch
+
+    n, bits = 4096, [50, 50, 50, 50]
+    mods = O.coeff_modulus_create(n, bits)
+    ctx = sb().Context(sb().CKKS, n, mods)
+    rng = np.random.default_rng(9)
+    L, batch = 3, 5
+    a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+    key = rng.integers(0, 1 << 40, (L, 2, 4, n), dtype=np.uint64)  # any residues < q work as a "key" for parity
+    rk = ctx.load_key(key)
+    da = torch.from_numpy(a.view(np.int64)).cuda()
+    db = torch.from_numpy(b.view(np.int64)).cuda()
+    out = torch.empty((batch, 2, L, n), dtype=torch.int64, device="cuda")
+    before = ctx.launch_count
+    ctx.d_multiply_relinearize(da, db, rk, out, L, batch)
+    torch.cuda.synchronize()
+    assert ctx.launch_count > before
+    host = ctx.multiply_relinearize(a, b, rk)
+    assert (out.cpu().numpy().view(np.uint64) == host).all()
+    oc = O.Oracle(O.CKKS, n, mods)
+    assert (host[0] == oc.multiply_relin(L, a[0], b[0], key)).all()
+
+
+def test_error_codes():
+    s = sb()
+    with pytest.raises(ValueError):
+        s.Context(s.CKKS, 1000, [1099511480321])  # not a power of two
+    with pytest.raises(ValueError):
+        s.Context(s.CKKS, 1024, [1099511480321 + 2])  # no primitive 2n-th root
+    n = 1024
+    mods = O.coeff_modulus_create(n, [40, 40, 40])
+    ctx = s.Context(s.CKKS, n, mods)
+    key = ctx.load_key(np.zeros((1, 2, 3, n), dtype=np.uint64))
+    a = np.zeros((1, 3, 2, n), dtype=np.uint64)
+    with pytest.raises(ValueError):  # key with too few digits: evaluator.cpp:2635
+        ctx.relinearize(a, key)
+    with pytest.raises(ValueError):  # rescale at the last level: evaluator.cpp:1521
+        ctx.rescale_to_next(np.zeros((1, 2, 1, n), dtype=np.uint64))
