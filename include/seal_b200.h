@@ -65,6 +65,15 @@ unsigned long long sb200_launch_count(const sb200_context *ctx);
 /* device bytes currently held by the context (tables + scratch) */
 size_t sb200_device_bytes(const sb200_context *ctx);
 
+/* ---- per-kernel timing (CUDA events on the launching stream) -------------------------------------------------
+ * enable, run operations, then read entries 0,1,... until SB200_E_OUT_OF_RANGE.  Each entry aggregates one kernel
+ * (a transform contributes "<name>:col" and "<name>:local"): total device ms, launches, and the algorithmic bytes
+ * those launches had to move (DESIGN.md lists the per-kernel formula).  Used by bench.py for the roofline line. */
+int sb200_profile_enable(sb200_context *ctx, int on);
+int sb200_profile_reset(sb200_context *ctx);
+int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                       unsigned long long *launches, double *algorithmic_bytes);
+
 /* ---- key-switching keys --------------------------------------------------------------------------------------
  * h_key = the flattened KSwitchKeys::data()[index]: [digit j < digits][component 2][key prime k][coeff n], i.e. for
  * each j the PublicKey's ciphertext data (kswitchkeys.h, keygenerator.cpp:327-360).  digits must be >= L of every

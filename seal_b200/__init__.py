@@ -24,7 +24,8 @@ _STATUS = {-1: ValueError, -2: RuntimeError, -3: IndexError, -4: RuntimeError, -
 SYMBOLS = [
     "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
-    "sb200_device_bytes", "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
+    "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
+    "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
     "sb200_ntt_inverse", "sb200_multiply", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
     "sb200_multiply_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
@@ -54,6 +55,10 @@ def lib():
         L.sb200_launch_count.argtypes = [vp]
         L.sb200_device_bytes.restype = sz
         L.sb200_device_bytes.argtypes = [vp]
+        L.sb200_profile_enable.argtypes = [vp, i32]
+        L.sb200_profile_reset.argtypes = [vp]
+        L.sb200_profile_read.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
+                                         C.POINTER(C.c_double)]
         L.sb200_kswitch_key_create.argtypes = [vp, _u64p, sz, C.POINTER(vp)]
         L.sb200_kswitch_key_destroy.argtypes = [vp]
         L.sb200_ntt_forward.argtypes = [vp, sz, sz, sz, vp, vp]
@@ -172,6 +177,20 @@ class Context:
     @property
     def device_bytes(self):
         return int(lib().sb200_device_bytes(self.h))
+
+    def profile(self, on=True):
+        _check(lib().sb200_profile_enable(self.h, 1 if on else 0))
+        _check(lib().sb200_profile_reset(self.h))
+
+    def profile_read(self):
+        """[(kernel name, total device ms, launches, algorithmic bytes)] since the last profile()/reset"""
+        out, i = [], 0
+        name = C.create_string_buffer(128)
+        ms, n, by = C.c_double(0), C.c_ulonglong(0), C.c_double(0)
+        while lib().sb200_profile_read(self.h, i, name, 128, C.byref(ms), C.byref(n), C.byref(by)) == 0:
+            out.append((name.value.decode(), ms.value, n.value, by.value))
+            i += 1
+        return out
 
     def load_key(self, host_key):
         return KSwitchKey(self, host_key)

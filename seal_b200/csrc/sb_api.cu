@@ -3,6 +3,8 @@
 // (native/src/seal/c/defines.h:72-96) and the message is kept in a thread-local string.
 #include "../../include/seal_b200.h"
 #include "sb_engine.cuh"
+#include <algorithm>
+#include <cstdio>
 #include <new>
 
 using namespace sb;
@@ -166,6 +168,69 @@ unsigned long long sb200_launch_count(const sb200_context *ctx)
 size_t sb200_device_bytes(const sb200_context *ctx)
 {
     return ctx ? ctx->c->table_bytes + ctx->c->scratch_bytes : 0;
+}
+
+int sb200_profile_enable(sb200_context *ctx, int on)
+{
+    SB_NEED(ctx);
+    std::lock_guard<std::mutex> lock(ctx->c->mu);
+    ctx->c->stats.profiling = (on != 0);
+    return SB200_OK;
+}
+
+int sb200_profile_reset(sb200_context *ctx)
+{
+    SB_NEED(ctx);
+    std::lock_guard<std::mutex> lock(ctx->c->mu);
+    cudaSetDevice(ctx->c->device);
+    cudaDeviceSynchronize();
+    ctx->c->stats.clear();
+    return SB200_OK;
+}
+
+int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                       unsigned long long *launches, double *algorithmic_bytes)
+{
+    SB_NEED(ctx);
+    SB_NEED(name);
+    SB_NEED(total_ms);
+    SB_NEED(launches);
+    SB_NEED(algorithmic_bytes);
+    SB_TRY
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    cuda_check(cudaDeviceSynchronize(), "synchronize");
+    // aggregate by (name, pass) in first-seen order
+    struct Agg
+    {
+        std::string name;
+        double ms = 0, bytes = 0;
+        unsigned long long n = 0;
+    };
+    std::vector<Agg> aggs;
+    static const char *suffix[] = { "", ":col", ":local" };
+    for (auto &r : c.stats.recs)
+    {
+        std::string nm = std::string(r.name) + suffix[r.pass];
+        float ms = 0;
+        cuda_check(cudaEventElapsedTime(&ms, r.e0, r.e1), "cudaEventElapsedTime");
+        auto it = std::find_if(aggs.begin(), aggs.end(), [&](const Agg &a) { return a.name == nm; });
+        if (it == aggs.end())
+        {
+            aggs.push_back(Agg{ nm });
+            it = aggs.end() - 1;
+        }
+        it->ms += ms, it->bytes += r.bytes, it->n++;
+    }
+    if (index >= aggs.size())
+        throw std::out_of_range("profile index");
+    std::snprintf(name, name_capacity, "%s", aggs[index].name.c_str());
+    *total_ms = aggs[index].ms;
+    *launches = aggs[index].n;
+    *algorithmic_bytes = aggs[index].bytes;
+    return SB200_OK;
+    SB_CATCH
 }
 
 int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out)

@@ -321,11 +321,12 @@ namespace sb
     {
         long long total = static_cast<long long>(batch) * L * c.n;
         unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        c.stats.begin("ckks_tensor", 0, 7.0 * 8.0 * total, st); // 4 reads + 3 writes per coefficient
         if (fused)
             ckks_tensor_kernel<true><<<blocks, 256, 0, st>>>(a, b, out, c2, c.d_primes, c.logn, static_cast<int>(L), total);
         else
             ckks_tensor_kernel<false><<<blocks, 256, 0, st>>>(a, b, out, c2, c.d_primes, c.logn, static_cast<int>(L), total);
-        c.stats.launches++;
+        c.stats.end(st);
         cuda_check(cudaGetLastError(), "ckks_tensor_kernel");
     }
 
@@ -634,40 +635,46 @@ namespace sb
         if (ntt_in)
         {
             OpKsIntt op{ target, s.D, c.logn, Li };
-            cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats), "ks intt");
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats, "ks_target_intt"), "ks intt");
             dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
         }
         {
             OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0 };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats), "ks digit ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats, "ks_digit_ntt",
+                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L))),
+                       "ks digit ntt");
         }
         {
             int threads = std::min(n, 256);
             dim3 grid(static_cast<unsigned>(B), (n + threads - 1) / threads, static_cast<unsigned>(L + 1));
+            // digits in + 2 accumulated components out per (b, I), plus one pass over the key
+            double bytes = 8.0 * n * (static_cast<double>(B) * (L + 1) * (L + 2) + 2.0 * L * (L + 1));
+            c.stats.begin("ks_mac", 0, bytes, st);
             ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki);
-            c.stats.launches++;
+            c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_mac_kernel");
         }
         const long long pp_ps = static_cast<long long>(L + 1) * n, pp_bs = 2 * pp_ps;
         {
             OpTopIntt op{ s.Pp + static_cast<long long>(L) * n, pp_bs, pp_ps, s.U, c.logn, ki - 1 };
-            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats), "ks top intt");
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "ks_top_intt"), "ks top intt");
         }
         const Tw *inv_top = c.d_invq + (c.k - 1) * c.k;
         const long long o_ps = static_cast<long long>(L) * n, o_bs = 2 * o_ps;
         if (ntt_in)
         {
             OpModDownFwd op{ s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats), "ks moddown ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_moddown_ntt"), "ks moddown ntt");
         }
         else
         {
             OpProdIntt op{ s.Pp, c.logn, Li };
-            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats), "ks prod intt");
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_prod_intt"), "ks prod intt");
             long long total = static_cast<long long>(B) * 2 * L * n;
+            c.stats.begin("moddown_coeff", 0, 32.0 * total, st);
             moddown_coeff_kernel<false><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
                 s.U, 2LL * n, n, s.Pp, pp_bs, pp_ps, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.d_primes, c.logn, Li, total);
-            c.stats.launches++;
+            c.stats.end(st);
             cuda_check(cudaGetLastError(), "moddown_coeff_kernel");
         }
     }
@@ -782,12 +789,12 @@ namespace sb
             const u64 *in = in2 + b0 * 2 * L * c.n;
             const long long i_ps = static_cast<long long>(L) * n, i_bs = 2 * i_ps;
             OpTopIntt top{ in + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
-            cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats), "rescale intt");
+            cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "rescale_top_intt"), "rescale intt");
             BaseSrc none;
             const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
             OpModDownFwd op{ U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
                              c.logn, static_cast<int>(Lout) };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats), "rescale ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "rescale_ntt"), "rescale ntt");
         }
     }
 
@@ -813,10 +820,11 @@ namespace sb
             size_t B = std::min(step, batch - b0);
             const u64 *in = in2 + b0 * 2 * L * c.n;
             long long total = static_cast<long long>(B) * 2 * Lout * n;
+            c.stats.begin("moddown_coeff", 0, 24.0 * total, st);
             moddown_coeff_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
                 in + (L - 1) * c.n, 2 * i_ps, i_ps, in, 2 * i_ps, i_ps, out2 + b0 * 2 * Lout * c.n, 2 * o_ps, o_ps,
                 c.d_invq + (L - 1) * c.k, none, c.q[L - 1], c.d_primes, c.logn, static_cast<int>(Lout), total);
-            c.stats.launches++;
+            c.stats.end(st);
             cuda_check(cudaGetLastError(), "moddown_coeff_kernel");
         }
     }

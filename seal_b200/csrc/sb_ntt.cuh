@@ -27,6 +27,7 @@
 //   void store8(int row, int idx0, u64(&)[8], P)
 #pragma once
 #include "sb_device.cuh"
+#include <vector>
 
 namespace sb
 {
@@ -438,25 +439,82 @@ namespace sb
     }
 
     // ------------------------------------------------------------------------------------------- launchers ----
+    // Launch bookkeeping + optional per-kernel CUDA-event timing (sb200_profile_* in the C-ABI).  Timing is recorded on
+    // the launching stream; algorithmic bytes are what the kernel must move once (rows x 2 x n x 8 for a transform pass).
     struct LaunchStats
     {
         unsigned long long launches = 0;
+        bool profiling = false;
+        struct Rec
+        {
+            const char *name;
+            int pass; // 0 = whole kernel, 1 = column pass of a transform, 2 = local pass
+            double bytes;
+            cudaEvent_t e0, e1;
+        };
+        std::vector<Rec> recs;
+        std::vector<cudaEvent_t> pool;
+        cudaEvent_t get_event()
+        {
+            cudaEvent_t e;
+            if (!pool.empty())
+            {
+                e = pool.back();
+                pool.pop_back();
+                return e;
+            }
+            cudaEventCreate(&e);
+            return e;
+        }
+        void begin(const char *name, int pass, double bytes, cudaStream_t st)
+        {
+            launches++;
+            if (!profiling)
+                return;
+            Rec r{ name, pass, bytes, get_event(), get_event() };
+            cudaEventRecord(r.e0, st);
+            recs.push_back(r);
+        }
+        void end(cudaStream_t st)
+        {
+            if (profiling)
+                cudaEventRecord(recs.back().e1, st);
+        }
+        void clear()
+        {
+            for (auto &r : recs)
+            {
+                pool.push_back(r.e0);
+                pool.push_back(r.e1);
+            }
+            recs.clear();
+        }
+        ~LaunchStats()
+        {
+            clear();
+            for (auto e : pool)
+                cudaEventDestroy(e);
+        }
     };
 
     template <class Op>
-    inline cudaError_t launch_ntt_fwd(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls)
+    inline cudaError_t launch_ntt_fwd(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls,
+                                      const char *name = "ntt_fwd", int active_rows = -1)
     {
         if (nrows <= 0)
             return cudaSuccess;
+        const double bytes = 16.0 * (active_rows < 0 ? nrows : active_rows) * (1 << logn);
         if (logn < 12)
         {
             int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
+            ls.begin(name, 0, bytes, st);
             ntt_fwd_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
-            ls.launches++;
+            ls.end(st);
             return cudaGetLastError();
         }
         const int logna = logn - kLocalLog, na = 1 << logna;
         dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
+        ls.begin(name, 1, bytes, st); // column pass
         switch (logna)
         {
         case 4: ntt_fwd_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
@@ -467,26 +525,34 @@ namespace sb
         case 9: ntt_fwd_col<9, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
         default: return cudaErrorInvalidValue;
         }
+        ls.end(st);
+        ls.begin(name, 2, bytes, st); // local pass
         ntt_fwd_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
-        ls.launches += 2;
+        ls.end(st);
         return cudaGetLastError();
     }
 
     template <class Op>
-    inline cudaError_t launch_ntt_inv(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls)
+    inline cudaError_t launch_ntt_inv(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls,
+                                      const char *name = "ntt_inv", int active_rows = -1)
     {
         if (nrows <= 0)
             return cudaSuccess;
+        const double bytes = 16.0 * (active_rows < 0 ? nrows : active_rows) * (1 << logn);
         if (logn < 12)
         {
             int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
+            ls.begin(name, 0, bytes, st);
             ntt_inv_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
-            ls.launches++;
+            ls.end(st);
             return cudaGetLastError();
         }
         const int logna = logn - kLocalLog, na = 1 << logna;
+        ls.begin(name, 2, bytes, st); // local pass
         ntt_inv_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        ls.end(st);
         dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
+        ls.begin(name, 1, bytes, st); // column pass
         switch (logna)
         {
         case 4: ntt_inv_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
@@ -497,7 +563,7 @@ namespace sb
         case 9: ntt_inv_col<9, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
         default: return cudaErrorInvalidValue;
         }
-        ls.launches += 2;
+        ls.end(st);
         return cudaGetLastError();
     }
 } // namespace sb
