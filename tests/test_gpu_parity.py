@@ -180,3 +180,50 @@ def test_error_codes():
         ctx.relinearize(a, key)
     with pytest.raises(ValueError):  # rescale at the last level: evaluator.cpp:1521
         ctx.rescale_to_next(np.zeros((1, 2, 1, n), dtype=np.uint64))
+
+
+@needs_ref
+@pytest.mark.parametrize("n,mods_fn,t_bits,batch", [
+    (4096, lambda: R.coeff_modulus_bfv_default(4096), 20, 3),            # BASELINE.json configs[0]
+    (16384, lambda: R.coeff_modulus_create(16384, [54] * 8), 20, 2),     # configs[3] shape (BFV n=16384, 8 primes)
+    (8192, lambda: R.coeff_modulus_create(8192, [60, 60, 60]), 30, 2),   # 60-bit primes: |B| grows to L+1 (rns.cpp:607-612)
+])
+def test_bfv_multiply_vs_reference(n, mods_fn, t_bits, batch):
+    mods = mods_fn()
+    t = R.plain_modulus_batching(n, t_bits)
+    rb = R.RefContext(R.BFV, n, mods, t)
+    ctx = sb().Context(sb().BFV, n, mods, t)
+    rng = np.random.default_rng(n + 1)
+    rk = ctx.load_key(rb.relin_key())
+    for L in (len(mods) - 1, 1):
+        assert ctx.base_bsk(L) == rb.base_bsk(L)
+        a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+        m = ctx.multiply(a, b)
+        mr = ctx.multiply_relinearize(a, b, rk)
+        for i in range(batch):
+            want = rb.multiply(L, a[i], b[i])
+            assert (m[i] == want).all()
+            assert (mr[i] == rb.relinearize(L, want)).all()
+
+
+@needs_ref
+def test_bfv_semantic_roundtrip():
+    # the reference's own style of integration test (native/tests/seal/evaluator.cpp:1356 BFVEncryptMultiplyDecrypt,
+    # :5670 BFVEncryptRotateMatrixDecrypt): encrypt with the reference, evaluate on the GPU, decrypt with the reference
+    n = 4096
+    mods = R.coeff_modulus_bfv_default(n)
+    t = R.plain_modulus_batching(n, 20)
+    rb = R.RefContext(R.BFV, n, mods, t)
+    ctx = sb().Context(sb().BFV, n, mods, t)
+    L = 2
+    rng = np.random.default_rng(77)
+    x, y = rng.integers(0, 1000, n, dtype=np.uint64), rng.integers(0, 1000, n, dtype=np.uint64)
+    cx, cy = rb.bfv_encrypt(x), rb.bfv_encrypt(y)
+    prod = ctx.multiply_relinearize(cx, cy, ctx.load_key(rb.relin_key()))
+    got, budget = rb.bfv_decrypt(L, prod)
+    assert budget > 0 and (got == (x * y) % np.uint64(t)).all()
+    e = rb.galois_elt_from_step(3)
+    rot = ctx.apply_galois(cx, e, ctx.load_key(rb.galois_key(e)))
+    got, _ = rb.bfv_decrypt(L, rot)
+    rows = x.reshape(2, n // 2)
+    assert (got.reshape(2, n // 2) == np.roll(rows, -3, axis=1)).all()
