@@ -1,0 +1,460 @@
+// include/seal_b200/evaluator.hpp -- header-only C++17 drop-in for the hot-path members of seal::Evaluator.
+//
+// seal::Evaluator has no virtual members and cannot be subclassed (evaluator.h:79, copy/move deleted :1320-1326), so the
+// drop-in is a class with the SAME member signatures (same seal::Ciphertext / RelinKeys / GaloisKeys / SEALContext
+// types, same argument meaning, same exception types from the same prologue checks) that a SEAL user instantiates
+// instead of seal::Evaluator for multiply / relinearize / rescale_to_next / mod_switch_to_next / apply_galois /
+// rotate_rows / rotate_columns / rotate_vector / complex_conjugate / transform_{to,from}_ntt.  It is compiled against the
+// user's own SEAL headers; all arithmetic happens in libseal_b200.so (include/seal_b200.h) on the GPU -- there is
+// no CPU fallback.  Batch overloads (std::vector<Ciphertext>) are the extension the reference does not have.
+//
+// Reference members mirrored (native/src/seal/): evaluator.h:219-345, 510-545, 929-1316; evaluator.cpp:352-393, 569-708,
+// 1144-1199, 1201-1294, 1404-1541, 2289-2559.
+#pragma once
+#include "../seal_b200.h"
+#include "seal/seal.h"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace seal_b200
+{
+    class Evaluator
+    {
+    public:
+        explicit Evaluator(const seal::SEALContext &context, int device = 0) : context_(context)
+        {
+            if (!context_.parameters_set())
+                throw std::invalid_argument("encryption parameters are not set correctly"); // evaluator.cpp:121-128
+            auto &parms = context_.key_context_data()->parms();
+            std::vector<std::uint64_t> q;
+            for (auto &m : parms.coeff_modulus())
+                q.push_back(m.value());
+            scheme_ = parms.scheme();
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::ckks)
+                throw std::invalid_argument("unsupported scheme");
+            check(sb200_context_create(
+                static_cast<int>(scheme_), parms.poly_modulus_degree(), q.data(), q.size(),
+                scheme_ == seal::scheme_type::bfv ? parms.plain_modulus().value() : 0, device, &ctx_));
+        }
+        ~Evaluator()
+        {
+            for (auto &kv : keys_)
+                sb200_kswitch_key_destroy(kv.second);
+            if (ctx_)
+                sb200_context_destroy(ctx_);
+        }
+        Evaluator(const Evaluator &) = delete;
+        Evaluator &operator=(const Evaluator &) = delete;
+
+        // ---- multiply (evaluator.cpp:352-393) ------------------------------------------------------------------
+        void multiply_inplace(seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2,
+                              seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted1, "encrypted1 is not valid for encryption parameters");
+            validate(encrypted2, "encrypted2 is not valid for encryption parameters");
+            if (encrypted1.parms_id() != encrypted2.parms_id())
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            const bool ckks = scheme_ == seal::scheme_type::ckks;
+            if (ckks && !(encrypted1.is_ntt_form() && encrypted2.is_ntt_form()))
+                throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form"); // :571-574
+            if (!ckks && (encrypted1.is_ntt_form() || encrypted2.is_ntt_form()))
+                throw std::invalid_argument("encrypted1 or encrypted2 cannot be in NTT form"); // :397-400
+            if (encrypted1.size() != 2 || encrypted2.size() != 2)
+                throw std::invalid_argument("seal_b200: multiply is implemented for size-2 ciphertexts");
+            auto cd = context_.get_context_data(encrypted1.parms_id());
+            const std::size_t L = encrypted1.coeff_modulus_size(), n = encrypted1.poly_modulus_degree();
+            std::vector<std::uint64_t> a(encrypted1.data(), encrypted1.data() + 2 * L * n);
+            double new_scale = encrypted1.scale() * encrypted2.scale();
+            if (ckks && !scale_within_bounds(new_scale, *cd))
+                throw std::invalid_argument("scale out of bounds"); // :703-707
+            encrypted1.resize(context_, cd->parms_id(), 3);
+            check(sb200_multiply_host(ctx_, L, 1, a.data(), encrypted2.data(), encrypted1.data()));
+            if (ckks)
+                encrypted1.scale() = new_scale;
+            throw_if_transparent(encrypted1);
+        }
+        void multiply(const seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, seal::Ciphertext &destination,
+                      seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (&encrypted2 == &destination)
+            {
+                multiply_inplace(destination, encrypted1, std::move(pool));
+            }
+            else
+            {
+                destination = encrypted1;
+                multiply_inplace(destination, encrypted2, std::move(pool));
+            }
+        }
+
+        // ---- relinearize (evaluator.cpp:1144-1199) ---------------------------------------------------------------
+        void relinearize_inplace(seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys,
+                                 seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            auto cd = context_.get_context_data(encrypted.parms_id());
+            if (!cd)
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (relin_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+            if (encrypted.size() < 2)
+                throw std::invalid_argument("destination_size must be at least 2 and less than or equal to current count");
+            if (relin_keys.size() < encrypted.size() - 2)
+                throw std::invalid_argument("not enough relinearization keys");
+            if (encrypted.size() == 2)
+                return;
+            if (encrypted.size() != 3)
+                throw std::invalid_argument("seal_b200: relinearize is implemented for size-3 ciphertexts");
+            check_keyswitch_operand(encrypted, pool);
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
+            sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), L);
+            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 3 * L * n);
+            encrypted.resize(context_, cd->parms_id(), 2);
+            check(sb200_relinearize_host(ctx_, L, 1, in.data(), key, encrypted.data()));
+            throw_if_transparent(encrypted);
+        }
+        void relinearize(const seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys, seal::Ciphertext &destination,
+                         seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            relinearize_inplace(destination, relin_keys, std::move(pool));
+        }
+
+        // ---- rescale / mod switch (evaluator.cpp:1404-1541, 1201-1358) --------------------------------------------
+        void rescale_to_next(const seal::Ciphertext &encrypted, seal::Ciphertext &destination,
+                             seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (context_.last_parms_id() == encrypted.parms_id())
+                throw std::invalid_argument("end of modulus switching chain reached");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::invalid_argument("unsupported operation for scheme type");
+            mod_switch_impl(encrypted, destination, true);
+        }
+        void rescale_to_next_inplace(seal::Ciphertext &encrypted, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            rescale_to_next(encrypted, encrypted, std::move(pool));
+        }
+        void mod_switch_to_next(const seal::Ciphertext &encrypted, seal::Ciphertext &destination,
+                                seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (context_.last_parms_id() == encrypted.parms_id())
+                throw std::invalid_argument("end of modulus switching chain reached");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            mod_switch_impl(encrypted, destination, false);
+        }
+        void mod_switch_to_next_inplace(seal::Ciphertext &encrypted, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            mod_switch_to_next(encrypted, encrypted, std::move(pool));
+        }
+
+        // ---- Galois automorphisms and rotations (evaluator.cpp:2384-2559, evaluator.h:1006-1316) ---------------------
+        void apply_galois_inplace(seal::Ciphertext &encrypted, std::uint32_t galois_elt, const seal::GaloisKeys &galois_keys,
+                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (galois_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (!galois_keys.has_key(galois_elt))
+                throw std::invalid_argument("Galois key not present");
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
+            if (!(galois_elt & 1) || galois_elt >= 2 * n)
+                throw std::invalid_argument("Galois element is not valid");
+            if (encrypted.size() != 2)
+                throw std::invalid_argument("encrypted size must be 2");
+            check_keyswitch_operand(encrypted, pool);
+            sb200_kswitch_key *key = key_for(galois_keys, seal::GaloisKeys::get_index(galois_elt), L);
+            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 2 * L * n);
+            check(sb200_apply_galois_host(ctx_, L, 1, in.data(), galois_elt, key, encrypted.data()));
+            throw_if_transparent(encrypted);
+        }
+        void apply_galois(const seal::Ciphertext &encrypted, std::uint32_t galois_elt, const seal::GaloisKeys &galois_keys,
+                          seal::Ciphertext &destination, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            apply_galois_inplace(destination, galois_elt, galois_keys, std::move(pool));
+        }
+        void rotate_rows_inplace(seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys,
+                                 seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (scheme_ != seal::scheme_type::bfv)
+                throw std::logic_error("unsupported scheme");
+            rotate_internal(encrypted, steps, galois_keys, std::move(pool));
+        }
+        void rotate_rows(const seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys, seal::Ciphertext &destination,
+                         seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            rotate_rows_inplace(destination, steps, galois_keys, std::move(pool));
+        }
+        void rotate_columns_inplace(seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys,
+                                    seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (scheme_ != seal::scheme_type::bfv)
+                throw std::logic_error("unsupported scheme");
+            conjugate_internal(encrypted, galois_keys, std::move(pool));
+        }
+        void rotate_columns(const seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys, seal::Ciphertext &destination,
+                            seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            rotate_columns_inplace(destination, galois_keys, std::move(pool));
+        }
+        void rotate_vector_inplace(seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys,
+                                   seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::logic_error("unsupported scheme");
+            rotate_internal(encrypted, steps, galois_keys, std::move(pool));
+        }
+        void rotate_vector(const seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys, seal::Ciphertext &destination,
+                           seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            rotate_vector_inplace(destination, steps, galois_keys, std::move(pool));
+        }
+        void complex_conjugate_inplace(seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys,
+                                       seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::logic_error("unsupported scheme");
+            conjugate_internal(encrypted, galois_keys, std::move(pool));
+        }
+        void complex_conjugate(const seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys, seal::Ciphertext &destination,
+                               seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            complex_conjugate_inplace(destination, galois_keys, std::move(pool));
+        }
+
+        // ---- NTT form changes (evaluator.cpp:2289-2382) -------------------------------------------------------------
+        void transform_to_ntt_inplace(seal::Ciphertext &encrypted) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (encrypted.is_ntt_form())
+                throw std::invalid_argument("encrypted is already in NTT form");
+            check(sb200_ntt_forward_host(ctx_, encrypted.coeff_modulus_size(), encrypted.size(), 1, encrypted.data()));
+            encrypted.is_ntt_form() = true;
+            throw_if_transparent(encrypted);
+        }
+        void transform_to_ntt(const seal::Ciphertext &encrypted, seal::Ciphertext &destination_ntt) const
+        {
+            destination_ntt = encrypted;
+            transform_to_ntt_inplace(destination_ntt);
+        }
+        void transform_from_ntt_inplace(seal::Ciphertext &encrypted_ntt) const
+        {
+            validate(encrypted_ntt, "encrypted is not valid for encryption parameters");
+            if (!encrypted_ntt.is_ntt_form())
+                throw std::invalid_argument("encrypted_ntt is not in NTT form");
+            check(sb200_ntt_inverse_host(ctx_, encrypted_ntt.coeff_modulus_size(), encrypted_ntt.size(), 1, encrypted_ntt.data()));
+            encrypted_ntt.is_ntt_form() = false;
+            throw_if_transparent(encrypted_ntt);
+        }
+        void transform_from_ntt(const seal::Ciphertext &encrypted_ntt, seal::Ciphertext &destination) const
+        {
+            destination = encrypted_ntt;
+            transform_from_ntt_inplace(destination);
+        }
+
+        // ---- batch extension: destination[i] = relinearize(multiply(a[i], b[i])), one device pass over the batch ----
+        void multiply_relinearize(const std::vector<seal::Ciphertext> &a, const std::vector<seal::Ciphertext> &b,
+                                  const seal::RelinKeys &relin_keys, std::vector<seal::Ciphertext> &destination) const
+        {
+            if (a.size() != b.size() || a.empty())
+                throw std::invalid_argument("batch size mismatch");
+            if (relin_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+            const std::size_t B = a.size(), L = a[0].coeff_modulus_size(), n = a[0].poly_modulus_degree(), w = 2 * L * n;
+            const bool ckks = scheme_ == seal::scheme_type::ckks;
+            auto cd = context_.get_context_data(a[0].parms_id());
+            std::vector<std::uint64_t> ha(B * w), hb(B * w), ho(B * w);
+            for (std::size_t i = 0; i < B; i++)
+            {
+                validate(a[i], "encrypted1 is not valid for encryption parameters");
+                validate(b[i], "encrypted2 is not valid for encryption parameters");
+                if (a[i].parms_id() != a[0].parms_id() || b[i].parms_id() != a[0].parms_id())
+                    throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+                if (a[i].size() != 2 || b[i].size() != 2 || a[i].is_ntt_form() != ckks || b[i].is_ntt_form() != ckks)
+                    throw std::invalid_argument("batch entries must be fresh size-2 ciphertexts in the scheme's native form");
+                if (ckks && !scale_within_bounds(a[i].scale() * b[i].scale(), *cd))
+                    throw std::invalid_argument("scale out of bounds");
+                std::memcpy(ha.data() + i * w, a[i].data(), w * sizeof(std::uint64_t));
+                std::memcpy(hb.data() + i * w, b[i].data(), w * sizeof(std::uint64_t));
+            }
+            sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), L);
+            check(sb200_multiply_relinearize_host(ctx_, L, B, ha.data(), hb.data(), key, ho.data()));
+            destination.resize(B);
+            for (std::size_t i = 0; i < B; i++)
+            {
+                destination[i] = a[i];
+                std::memcpy(destination[i].data(), ho.data() + i * w, w * sizeof(std::uint64_t));
+                if (ckks)
+                    destination[i].scale() = a[i].scale() * b[i].scale();
+                throw_if_transparent(destination[i]);
+            }
+        }
+
+        sb200_context *native_handle() const noexcept { return ctx_; }
+
+    private:
+        static void check(int status)
+        {
+            if (status == SB200_OK)
+                return;
+            const std::string msg = sb200_last_error();
+            switch (status)
+            {
+            case SB200_E_INVALID_ARG:
+            case SB200_E_POINTER: throw std::invalid_argument(msg);
+            case SB200_E_LOGIC: throw std::logic_error(msg);
+            case SB200_E_OUT_OF_RANGE: throw std::out_of_range(msg);
+            case SB200_E_NOMEM: throw std::bad_alloc();
+            default: throw std::runtime_error(msg);
+            }
+        }
+        void validate(const seal::Ciphertext &ct, const char *msg) const
+        {
+            if (!seal::is_metadata_valid_for(ct, context_) || !seal::is_buffer_valid(ct))
+                throw std::invalid_argument(msg);
+        }
+        static void throw_if_transparent(const seal::Ciphertext &ct)
+        {
+#ifdef SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT
+            if (ct.is_transparent())
+                throw std::logic_error("result ciphertext is transparent");
+#else
+            (void)ct;
+#endif
+        }
+        // evaluator.cpp:29-48
+        static bool scale_within_bounds(double scale, const seal::SEALContext::ContextData &cd) noexcept
+        {
+            int bound = cd.parms().scheme() == seal::scheme_type::ckks ? cd.total_coeff_modulus_bit_count()
+                                                                        : cd.parms().plain_modulus().bit_count();
+            return !(!std::isnormal(scale) || scale <= 0 || (static_cast<int>(std::log2(scale)) >= bound));
+        }
+        // the parts of switch_key_inplace's prologue that concern the operand (evaluator.cpp:2573-2611)
+        void check_keyswitch_operand(const seal::Ciphertext &encrypted, const seal::MemoryPoolHandle &pool) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (!context_.using_keyswitching())
+                throw std::logic_error("keyswitching is not supported by the context");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            if (scheme_ == seal::scheme_type::bfv && encrypted.is_ntt_form())
+                throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+            if (scheme_ == seal::scheme_type::ckks && !encrypted.is_ntt_form())
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        }
+        // uploads KSwitchKeys::data()[index] once (keys are immutable after generation) -- evaluator.cpp:2586-2648
+        sb200_kswitch_key *key_for(const seal::KSwitchKeys &keys, std::size_t index, std::size_t L) const
+        {
+            if (keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("parameter mismatch");
+            if (index >= keys.data().size())
+                throw std::out_of_range("kswitch_keys_index");
+            auto &kv = keys.data(index); // throws on an empty slot, like the reference's checked accessor
+            if (kv.size() < L)
+                throw std::invalid_argument("kswitch_keys inner dimension is too small");
+            for (auto &each : kv)
+                if (!seal::is_metadata_valid_for(each, context_) || !seal::is_buffer_valid(each))
+                    throw std::invalid_argument("kswitch_keys is not valid for encryption parameters");
+            std::lock_guard<std::mutex> lock(mu_);
+            const void *id = kv[0].data().data();
+            auto it = keys_.find(id);
+            if (it != keys_.end())
+                return it->second;
+            const std::size_t K = context_.key_context_data()->parms().coeff_modulus().size();
+            const std::size_t n = context_.key_context_data()->parms().poly_modulus_degree(), row = 2 * K * n;
+            std::vector<std::uint64_t> flat(kv.size() * row);
+            for (std::size_t j = 0; j < kv.size(); j++)
+                std::memcpy(flat.data() + j * row, kv[j].data().data(), row * sizeof(std::uint64_t));
+            sb200_kswitch_key *h = nullptr;
+            check(sb200_kswitch_key_create(ctx_, flat.data(), kv.size(), &h));
+            keys_[id] = h;
+            return h;
+        }
+        void mod_switch_impl(const seal::Ciphertext &encrypted, seal::Ciphertext &destination, bool rescale) const
+        {
+            auto cd = context_.get_context_data(encrypted.parms_id());
+            auto next = cd->next_context_data();
+            const bool ckks = scheme_ == seal::scheme_type::ckks;
+            if (ckks && !encrypted.is_ntt_form())
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (!ckks && encrypted.is_ntt_form())
+                throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+            if (encrypted.size() != 2)
+                throw std::invalid_argument("seal_b200: modulus switching is implemented for size-2 ciphertexts");
+            double scale = encrypted.scale();
+            if (rescale)
+            {
+                if (!scale_within_bounds(encrypted.scale(), *cd))
+                    throw std::invalid_argument("scale out of bounds");
+                scale = encrypted.scale() / static_cast<double>(cd->parms().coeff_modulus().back().value());
+                if (!scale_within_bounds(scale, *next))
+                    throw std::invalid_argument("scale out of bounds");
+            }
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
+            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 2 * L * n);
+            const bool ntt = encrypted.is_ntt_form();
+            destination.resize(context_, next->parms_id(), 2);
+            check(rescale ? sb200_rescale_to_next_host(ctx_, L, 1, in.data(), destination.data())
+                          : sb200_mod_switch_to_next_host(ctx_, L, 1, in.data(), destination.data()));
+            destination.is_ntt_form() = ntt;
+            destination.scale() = scale;
+            throw_if_transparent(destination);
+        }
+        // evaluator.cpp:2504-2559
+        void rotate_internal(seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys, seal::MemoryPoolHandle pool) const
+        {
+            auto cd = context_.get_context_data(encrypted.parms_id());
+            if (!cd)
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (!cd->qualifiers().using_batching)
+                throw std::logic_error("encryption parameters do not support batching");
+            if (galois_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (steps == 0)
+                return;
+            const std::size_t n = cd->parms().poly_modulus_degree();
+            const std::uint32_t elt = cd->galois_tool()->get_elt_from_step(steps);
+            if (galois_keys.has_key(elt))
+            {
+                apply_galois_inplace(encrypted, elt, galois_keys, std::move(pool));
+                return;
+            }
+            std::vector<int> naf_steps = seal::util::naf(steps);
+            if (naf_steps.size() == 1)
+                throw std::invalid_argument("Galois key not present");
+            for (int s : naf_steps)
+                if (static_cast<std::size_t>(std::abs(s)) != (n >> 1))
+                    rotate_internal(encrypted, s, galois_keys, pool);
+        }
+        void conjugate_internal(seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys, seal::MemoryPoolHandle pool) const
+        {
+            auto cd = context_.get_context_data(encrypted.parms_id());
+            if (!cd)
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (!cd->qualifiers().using_batching)
+                throw std::logic_error("encryption parameters do not support batching");
+            apply_galois_inplace(encrypted, cd->galois_tool()->get_elt_from_step(0), galois_keys, std::move(pool));
+        }
+
+        seal::SEALContext context_;
+        seal::scheme_type scheme_;
+        sb200_context *ctx_ = nullptr;
+        mutable std::mutex mu_;
+        mutable std::map<const void *, sb200_kswitch_key *> keys_;
+    };
+} // namespace seal_b200

@@ -1,0 +1,302 @@
+// tests/cpp/shim_test.cpp -- drop-in check of include/seal_b200/evaluator.hpp against the reference's own
+// seal::Evaluator (linked from oracle/_ref/libseal.so): same inputs -> identical ciphertext words and metadata, same
+// exception types; plus the reference's style of semantic tests (encrypt -> evaluate on GPU -> decrypt), cf.
+// native/tests/seal/evaluator.cpp:1356 (BFVEncryptMultiplyDecrypt), :3513 (CKKSEncryptMultiplyRelinRescaleDecrypt),
+// :4326 (CKKSEncryptRotateDecrypt), :5670 (BFVEncryptRotateMatrixDecrypt), :2505/:2532 (negative relinearize tests).
+// TEST INFRASTRUCTURE: links the reference; built only where /root/reference exists; the binary travels to the GPU box.
+#include "seal_b200/evaluator.hpp"
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <random>
+#include <typeinfo>
+
+using namespace seal;
+
+static int g_checks = 0, g_fail = 0;
+#define CHECK(cond)                                                        \
+    do                                                                     \
+    {                                                                      \
+        g_checks++;                                                        \
+        if (!(cond))                                                       \
+        {                                                                  \
+            g_fail++;                                                      \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);    \
+        }                                                                  \
+    } while (0)
+
+static bool same_ct(const Ciphertext &a, const Ciphertext &b)
+{
+    if (a.parms_id() != b.parms_id() || a.size() != b.size() || a.is_ntt_form() != b.is_ntt_form() ||
+        a.coeff_modulus_size() != b.coeff_modulus_size())
+        return false;
+    double sa = a.scale(), sb = b.scale();
+    if (std::memcmp(&sa, &sb, sizeof(double)) != 0)
+        return false;
+    return std::memcmp(a.data(), b.data(), a.size() * a.coeff_modulus_size() * a.poly_modulus_degree() * 8) == 0;
+}
+
+// runs f on both evaluators; returns a tag describing the exception type (or "ok")
+template <class F>
+static std::string outcome(F f)
+{
+    try
+    {
+        f();
+        return "ok";
+    }
+    catch (const std::invalid_argument &)
+    {
+        return "invalid_argument";
+    }
+    catch (const std::out_of_range &)
+    {
+        return "out_of_range";
+    }
+    catch (const std::logic_error &)
+    {
+        return "logic_error";
+    }
+    catch (const std::exception &)
+    {
+        return "exception";
+    }
+}
+
+static void test_ckks()
+{
+    EncryptionParameters parms(scheme_type::ckks);
+    const size_t n = 8192;
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::Create(n, { 54, 40, 40, 54 }));
+    SEALContext context(parms, true, sec_level_type::none);
+    KeyGenerator keygen(context);
+    PublicKey pk;
+    keygen.create_public_key(pk);
+    RelinKeys rlk;
+    keygen.create_relin_keys(rlk);
+    GaloisKeys glk;
+    keygen.create_galois_keys(glk); // power-of-two steps only -> step 5 goes through the NAF fallback
+    Encryptor encryptor(context, pk);
+    Decryptor decryptor(context, keygen.secret_key());
+    CKKSEncoder encoder(context);
+    seal::Evaluator ref(context);
+    seal_b200::Evaluator gpu(context);
+
+    const size_t slots = n / 2;
+    std::mt19937_64 rng(0x5EA1);
+    std::vector<double> x(slots), y(slots);
+    for (size_t i = 0; i < slots; i++)
+        x[i] = double(rng() % 2000) / 100.0 - 10.0, y[i] = double(rng() % 2000) / 100.0 - 10.0;
+    const double scale = std::pow(2.0, 40);
+    Plaintext px, py;
+    encoder.encode(x, scale, px);
+    encoder.encode(y, scale, py);
+    Ciphertext cx, cy;
+    encryptor.encrypt(px, cx);
+    encryptor.encrypt(py, cy);
+
+    Ciphertext r1, g1;
+    ref.multiply(cx, cy, r1);
+    gpu.multiply(cx, cy, g1);
+    CHECK(same_ct(r1, g1));
+    ref.relinearize_inplace(r1, rlk);
+    gpu.relinearize_inplace(g1, rlk);
+    CHECK(same_ct(r1, g1));
+    ref.rescale_to_next_inplace(r1);
+    gpu.rescale_to_next_inplace(g1);
+    CHECK(same_ct(r1, g1));
+    {
+        Plaintext p;
+        decryptor.decrypt(g1, p);
+        std::vector<double> got;
+        encoder.decode(p, got);
+        double err = 0;
+        for (size_t i = 0; i < slots; i++)
+            err = std::max(err, std::abs(got[i] - x[i] * y[i]));
+        CHECK(err < 1e-3);
+    }
+    for (int step : { 1, -4, 5, 1023 })
+    {
+        Ciphertext r2, g2;
+        ref.rotate_vector(r1, step, glk, r2);
+        gpu.rotate_vector(g1, step, glk, g2);
+        CHECK(same_ct(r2, g2));
+    }
+    {
+        Ciphertext r2, g2;
+        ref.complex_conjugate(cx, glk, r2);
+        gpu.complex_conjugate(cx, glk, g2);
+        CHECK(same_ct(r2, g2));
+        ref.mod_switch_to_next_inplace(r2);
+        gpu.mod_switch_to_next_inplace(g2);
+        CHECK(same_ct(r2, g2));
+        ref.transform_from_ntt_inplace(r2);
+        gpu.transform_from_ntt_inplace(g2);
+        CHECK(same_ct(r2, g2));
+        ref.transform_to_ntt_inplace(r2);
+        gpu.transform_to_ntt_inplace(g2);
+        CHECK(same_ct(r2, g2));
+    }
+    // batch extension == singles
+    {
+        std::vector<Ciphertext> a(3, cx), b(3, cy), out;
+        ref.square_inplace(a[1]);
+        ref.relinearize_inplace(a[1], rlk); // a different (size-2) operand; scale 2^80 is still in bounds at level 3? use cx*cx rescaled
+        ref.rescale_to_next_inplace(a[1]);
+        // bring everything to the same level
+        for (auto *v : { &a[0], &a[2], &b[0], &b[1], &b[2] })
+            ref.mod_switch_to_next_inplace(*v);
+        gpu.multiply_relinearize(a, b, rlk, out);
+        for (size_t i = 0; i < 3; i++)
+        {
+            Ciphertext r;
+            ref.multiply(a[i], b[i], r);
+            ref.relinearize_inplace(r, rlk);
+            CHECK(same_ct(r, out[i]));
+        }
+    }
+    // negative tests: identical exception types
+    {
+        Ciphertext bad = cx;
+        bad.is_ntt_form() = false; // CKKS operand not in NTT form -> evaluator.cpp:571-574
+        auto a = outcome([&] { Ciphertext t; ref.multiply(bad, cy, t); });
+        auto b = outcome([&] { Ciphertext t; gpu.multiply(bad, cy, t); });
+        CHECK(a == b && a == "invalid_argument");
+        Ciphertext last = cx;
+        while (last.parms_id() != context.last_parms_id())
+            ref.mod_switch_to_next_inplace(last);
+        a = outcome([&] { Ciphertext t = last; ref.rescale_to_next_inplace(t); });
+        b = outcome([&] { Ciphertext t = last; gpu.rescale_to_next_inplace(t); });
+        CHECK(a == b && a == "invalid_argument");
+        GaloisKeys few;
+        keygen.create_galois_keys(std::vector<int>{ 1 }, few);
+        a = outcome([&] { Ciphertext t = cx; ref.rotate_vector_inplace(t, 2, few); });
+        b = outcome([&] { Ciphertext t = cx; gpu.rotate_vector_inplace(t, 2, few); });
+        CHECK(a == b && a == "invalid_argument"); // "Galois key not present"
+        a = outcome([&] { Ciphertext t = cx; ref.rotate_rows_inplace(t, 1, glk); });
+        b = outcome([&] { Ciphertext t = cx; gpu.rotate_rows_inplace(t, 1, glk); });
+        CHECK(a == b && a == "logic_error"); // wrong scheme
+        // key set from another context (parms mismatch) -> relinearize_internal :1153-1156
+        EncryptionParameters p2(scheme_type::ckks);
+        p2.set_poly_modulus_degree(n);
+        p2.set_coeff_modulus(CoeffModulus::Create(n, { 50, 50, 50 }));
+        SEALContext c2(p2, true, sec_level_type::none);
+        KeyGenerator kg2(c2);
+        RelinKeys rlk2;
+        kg2.create_relin_keys(rlk2);
+        Ciphertext m3;
+        ref.multiply(cx, cy, m3);
+        a = outcome([&] { Ciphertext t = m3; ref.relinearize_inplace(t, rlk2); });
+        b = outcome([&] { Ciphertext t = m3; gpu.relinearize_inplace(t, rlk2); });
+        CHECK(a == b && a == "invalid_argument");
+    }
+}
+
+static void test_bfv()
+{
+    EncryptionParameters parms(scheme_type::bfv);
+    const size_t n = 4096; // BASELINE.json configs[0]: BFV n=4096, 3x36-bit coeff_modulus
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::BFVDefault(n));
+    parms.set_plain_modulus(PlainModulus::Batching(n, 20));
+    SEALContext context(parms, true, sec_level_type::none);
+    KeyGenerator keygen(context);
+    RelinKeys rlk;
+    keygen.create_relin_keys(rlk);
+    GaloisKeys glk;
+    keygen.create_galois_keys(glk);
+    Encryptor encryptor(context, keygen.secret_key());
+    Decryptor decryptor(context, keygen.secret_key());
+    BatchEncoder encoder(context);
+    seal::Evaluator ref(context);
+    seal_b200::Evaluator gpu(context);
+    const uint64_t t = parms.plain_modulus().value();
+
+    std::mt19937_64 rng(7);
+    std::vector<uint64_t> x(n), y(n);
+    for (size_t i = 0; i < n; i++)
+        x[i] = rng() % 500, y[i] = rng() % 500;
+    Plaintext px, py;
+    encoder.encode(x, px);
+    encoder.encode(y, py);
+    Ciphertext cx, cy;
+    encryptor.encrypt_symmetric(px, cx);
+    encryptor.encrypt_symmetric(py, cy);
+
+    Ciphertext r1, g1;
+    ref.multiply(cx, cy, r1);
+    gpu.multiply(cx, cy, g1);
+    CHECK(same_ct(r1, g1));
+    ref.relinearize_inplace(r1, rlk);
+    gpu.relinearize_inplace(g1, rlk);
+    CHECK(same_ct(r1, g1));
+    {
+        Plaintext p;
+        decryptor.decrypt(g1, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == (x[i] * y[i]) % t;
+        CHECK(ok);
+        CHECK(decryptor.invariant_noise_budget(g1) > 0);
+    }
+    for (int step : { 1, -2, 7 })
+    {
+        Ciphertext r2, g2;
+        ref.rotate_rows(cx, step, glk, r2);
+        gpu.rotate_rows(cx, step, glk, g2);
+        CHECK(same_ct(r2, g2));
+    }
+    {
+        Ciphertext r2, g2;
+        ref.rotate_columns(cx, glk, r2);
+        gpu.rotate_columns(cx, glk, g2);
+        CHECK(same_ct(r2, g2));
+        Plaintext p;
+        decryptor.decrypt(g2, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n / 2; i++)
+            ok = ok && got[i] == x[i + n / 2] && got[i + n / 2] == x[i];
+        CHECK(ok);
+        ref.mod_switch_to_next_inplace(r2);
+        gpu.mod_switch_to_next_inplace(g2);
+        CHECK(same_ct(r2, g2));
+        ref.transform_to_ntt_inplace(r2);
+        gpu.transform_to_ntt_inplace(g2);
+        CHECK(same_ct(r2, g2));
+    }
+    {
+        Ciphertext bad = cx;
+        bad.is_ntt_form() = true; // evaluator.cpp:397-400
+        auto a = outcome([&] { Ciphertext tt; ref.multiply(bad, cy, tt); });
+        auto b = outcome([&] { Ciphertext tt; gpu.multiply(bad, cy, tt); });
+        CHECK(a == b && a == "invalid_argument");
+        a = outcome([&] { Ciphertext tt = cx; ref.rescale_to_next_inplace(tt); });
+        b = outcome([&] { Ciphertext tt = cx; gpu.rescale_to_next_inplace(tt); });
+        CHECK(a == b && a == "invalid_argument"); // unsupported operation for scheme type
+        a = outcome([&] { Ciphertext tt = cx; ref.apply_galois_inplace(tt, 4, glk); });
+        b = outcome([&] { Ciphertext tt = cx; gpu.apply_galois_inplace(tt, 4, glk); });
+        CHECK(a == b && a == "invalid_argument"); // even Galois element: no such key
+    }
+}
+
+int main()
+{
+    try
+    {
+        test_ckks();
+        test_bfv();
+    }
+    catch (const std::exception &e)
+    {
+        std::printf("FAIL: unexpected exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf("%s: %d checks, %d failed\n", g_fail ? "FAIL" : "PASS", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}
