@@ -222,11 +222,11 @@ def main():
     ctx.profile(False)
 
     # end-of-run gather (the only collective): one 64-bit digest per ciphertext of this rank's last step
-    digest = out.view(B, -1).sum(dim=1)
-    if world > 1:
-        gathered = [torch.empty_like(digest) for _ in range(world)] if rank == 0 else None
-        dist.gather(digest, gathered, dst=0)
+    from seal_b200.shard import digest as ct_digest, gather_digests
+
+    digests = gather_digests(ct_digest(out), rank, world)  # NCCL over NVLink when world > 1
     torch.cuda.synchronize()
+    assert rank != 0 or digests.numel() == B * world
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
