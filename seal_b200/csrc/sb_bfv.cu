@@ -319,7 +319,7 @@ namespace sb
             const u64 *pa = a + b0 * 2 * L * c.n, *pb = b + b0 * 2 * L * c.n;
             {
                 OpBfvFwdQ op{ pa, pb, XQ, c.logn, Li };
-                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 4 * L), c.logn, c.d_primes, st, c.stats, "bfv_ntt_q"), "bfv ntt q");
+                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 4 * L), c.logn, c.d_primes, st, c.stats, "bfv_ntt_q", -1, c.fast_q), "bfv ntt q");
             }
             {
                 dim3 grid((n + TH - 1) / TH, 4, static_cast<unsigned>(B));

@@ -21,6 +21,8 @@ struct PrimeDev
 {
     u64 q;
     u64 q2;         // 2q
+    u64 q4;         // 4q
+    u64 nq;         // 2^64 - q
     u64 ratio_lo;   // floor(2^128 / q), low word
     u64 ratio_hi;   //                   high word (= floor(2^64 / q))
     Tw inv_n;       // n^-1 mod q
@@ -34,7 +36,38 @@ __device__ __forceinline__ u64 csub(u64 x, u64 q)
     return x >= q ? x - q : x;
 }
 
-// x * w mod q, lazily: result in [0, 2q) for ANY 64-bit x (w < q, wq = floor(w 2^64 / q)).
+// ---- Shoup / Harvey multiplication tuned for the sm_100 integer pipes -------------------------------------------
+// Integer multiplies issue on the FMA-heavy pipe only (ncu: the binding pipe of every transform kernel) and a
+// 32x32->64 multiply-add costs twice a 32-bit one, so the quotient estimate uses three wide products instead of the
+// four (+ carry chain) of an exact 64x64 high half:
+//     T = y1*wq1 + hi32(y1*wq0) + hi32(y0*wq1)      with  t-2 <= T <= t,  t = floor(y*wq / 2^64)
+// and the remainder y*w - T*q is formed as lo64(y*w + T*(2^64-q)) with two wide and four 32-bit multiply-adds.
+// Result: x*w mod q in [0, 4q) for ANY 64-bit x (w < q, wq = floor(w 2^64 / q), q < 2^61).
+__device__ __forceinline__ u64 approx_mulhi(u64 y, u64 wq)
+{
+    const unsigned y0 = static_cast<unsigned>(y), y1 = static_cast<unsigned>(y >> 32);
+    const unsigned wq0 = static_cast<unsigned>(wq), wq1 = static_cast<unsigned>(wq >> 32);
+    // the two cross products have equal weight 2^32: keep their high halves, drop their low halves and y0*wq0
+    u64 a = static_cast<u64>(y1) * wq0, b = static_cast<u64>(y0) * wq1;
+    return static_cast<u64>(y1) * wq1 + ((a >> 32) + (b >> 32));
+}
+// lo64(y*w + T*nq)
+__device__ __forceinline__ u64 mullo_combine(u64 y, u64 w, u64 T, u64 nq)
+{
+    const unsigned y0 = static_cast<unsigned>(y), y1 = static_cast<unsigned>(y >> 32);
+    const unsigned w0 = static_cast<unsigned>(w), w1 = static_cast<unsigned>(w >> 32);
+    const unsigned T0 = static_cast<unsigned>(T), T1 = static_cast<unsigned>(T >> 32);
+    const unsigned n0 = static_cast<unsigned>(nq), n1 = static_cast<unsigned>(nq >> 32);
+    u64 acc = static_cast<u64>(y0) * w0;
+    acc = static_cast<u64>(T0) * n0 + acc;
+    unsigned hi = static_cast<unsigned>(acc >> 32) + y0 * w1 + y1 * w0 + T0 * n1 + T1 * n0;
+    return (static_cast<u64>(hi) << 32) | static_cast<unsigned>(acc);
+}
+__device__ __forceinline__ u64 mul_shoup_lazy4(u64 x, Tw t, u64 nq)
+{
+    return mullo_combine(x, t.w, approx_mulhi(x, t.wq), nq);
+}
+// exact variants (result in [0,2q) / canonical) for the element-wise epilogues
 __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, Tw t, u64 q)
 {
     u64 h = __umul64hi(x, t.wq);
@@ -43,6 +76,16 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, Tw t, u64 q)
 __device__ __forceinline__ u64 mul_shoup(u64 x, Tw t, u64 q)
 {
     return csub(mul_shoup_lazy(x, t, q), q);
+}
+// x mod q, lazily in [0, 4q), for any 64-bit x (three wide products + one wide + two 32-bit multiply-adds)
+__device__ __forceinline__ u64 barrett_lazy4(u64 x, u64 ratio_hi, u64 nq)
+{
+    u64 T = approx_mulhi(x, ratio_hi);
+    const unsigned T0 = static_cast<unsigned>(T), T1 = static_cast<unsigned>(T >> 32);
+    const unsigned n0 = static_cast<unsigned>(nq), n1 = static_cast<unsigned>(nq >> 32);
+    u64 acc = static_cast<u64>(T0) * n0 + x;
+    unsigned hi = static_cast<unsigned>(acc >> 32) + T0 * n1 + T1 * n0;
+    return (static_cast<u64>(hi) << 32) | static_cast<unsigned>(acc);
 }
 
 // x mod q for any 64-bit x (ratio_hi = floor(2^64 / q)); result canonical.
@@ -81,21 +124,30 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b)
     hi += ph + (lo < pl);
 }
 
-// Harvey butterflies on lazily reduced values.
-// forward (Cooley-Tukey): inputs in [0,4q) -> outputs in [0,4q)
-__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, Tw w, u64 q, u64 q2)
+// Harvey-style butterflies on lazily reduced values.
+// forward (Cooley-Tukey).  FAST (all primes of the launch < 2^57): no conditional subtraction at all -- values grow
+//   by at most 4q per stage ((4 + 4*17) q < 2^64), the kernel reduces once before the store.
+//   guarded (any prime < 2^61): inputs in [0,8q) -> outputs in [0,8q).
+template <bool FAST>
+__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, Tw w, const PrimeDev &P)
 {
-    u64 u = csub(x, q2);
-    u64 v = mul_shoup_lazy(y, w, q);
+    u64 v = mul_shoup_lazy4(y, w, P.nq);
+    u64 u = FAST ? x : csub(x, P.q4);
     x = u + v;
-    y = u - v + q2;
+    y = u - v + P.q4;
 }
-// inverse (Gentleman-Sande): inputs in [0,2q) -> outputs in [0,2q)
-__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, Tw w, u64 q, u64 q2)
+// inverse (Gentleman-Sande): inputs in [0,4q) -> outputs in [0,4q)
+__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, Tw w, const PrimeDev &P)
 {
     u64 u = x, v = y;
-    x = csub(u + v, q2);
-    y = mul_shoup_lazy(u - v + q2, w, q);
+    x = csub(u + v, P.q4);
+    y = mul_shoup_lazy4(u - v + P.q4, w, P.nq);
+}
+// forward values before the store: -> [0, 4q)
+template <bool FAST>
+__device__ __forceinline__ u64 fwd_finish(u64 v, const PrimeDev &P)
+{
+    return FAST ? barrett_lazy4(v, P.ratio_hi, P.nq) : csub(v, P.q4);
 }
 
 __device__ __forceinline__ Tw ldg_tw(const Tw *p)

@@ -86,6 +86,8 @@ namespace sb
         PrimeDev d;
         d.q = pt.q;
         d.q2 = 2 * pt.q;
+        d.q4 = 4 * pt.q;
+        d.nq = 0ull - pt.q;
         d.ratio_lo = pt.ratio_lo;
         d.ratio_hi = pt.ratio_hi;
         d.inv_n = to_tw(pt.inv_n);
@@ -127,6 +129,8 @@ namespace sb
                 if (moduli[j] == moduli[i])
                     throw std::invalid_argument("coeff_modulus primes must be distinct");
             c->q.push_back(moduli[i]);
+            if (moduli[i] >> 57)
+                c->fast_q = false; // the guard-free forward butterflies need (4 + 4*17) q < 2^64
         }
         if (scheme == 1)
         {
@@ -266,7 +270,7 @@ namespace sb
         else
         {
             OpSlab<false> op{ d, c.logn, static_cast<int>(L), pid_tab };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(rows), c.logn, c.d_primes, st, c.stats), "ntt_fwd");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(rows), c.logn, c.d_primes, st, c.stats, "ntt_fwd", -1, c.fast_q && !pid_tab), "ntt_fwd");
         }
     }
 
@@ -641,7 +645,7 @@ namespace sb
         {
             OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0 };
             cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats, "ks_digit_ntt",
-                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L))),
+                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L)), c.fast_q),
                        "ks digit ntt");
         }
         {
@@ -664,7 +668,7 @@ namespace sb
         if (ntt_in)
         {
             OpModDownFwd op{ s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_moddown_ntt"), "ks moddown ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_moddown_ntt", -1, c.fast_q), "ks moddown ntt");
         }
         else
         {
@@ -794,7 +798,7 @@ namespace sb
             const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
             OpModDownFwd op{ U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
                              c.logn, static_cast<int>(Lout) };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "rescale_ntt"), "rescale ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "rescale_ntt", -1, c.fast_q), "rescale ntt");
         }
     }
 

@@ -29,6 +29,7 @@ namespace sb
     struct Context
     {
         int scheme = 0, device = 0, logn = 0;
+        bool fast_q = true;                  // every q prime < 2^57: guard-free forward butterflies (sb_device.cuh)
         size_t n = 0, k = 0;
         u64 t = 0;
         std::vector<u64> q;                  // key-level primes

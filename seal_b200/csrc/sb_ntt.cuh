@@ -20,7 +20,7 @@
 // Op interface (all __device__):
 //   bool skip(int row)                       row needs no transform (CTA exits)
 //   int  pid(int row)                        prime id of the row
-//   u64  load1(int row, int idx, P)          value of coefficient idx  (forward: < 4q, inverse: < 2q)
+//   u64  load1(int row, int idx, P)          value of coefficient idx  (forward: < 4q, inverse: < 4q)
 //   void load8(int row, int idx0, u64(&)[8], P)   8 consecutive coefficients
 //   u64 *mid(int row)                        n-word intermediate row between the two passes
 //   void store1(int row, int idx, u64 v, P)  v lazily reduced (forward: < 4q, inverse: < 2q)
@@ -37,28 +37,28 @@ namespace sb
 
     // ------------------------------------------------------------------------------- register radix-8 helpers ----
     // forward, pair levels in order: (j,j+4), (j,j+2), (j,j+1)
-    template <int NST, class TwF>
-    __device__ __forceinline__ void fwd_regs(u64 (&a)[8], TwF tw, u64 q, u64 q2)
+    template <int NST, bool FAST, class TwF>
+    __device__ __forceinline__ void fwd_regs(u64 (&a)[8], TwF tw, const PrimeDev &P)
     {
         {
             Tw w = tw(0, 0);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                ct_bfly(a[j], a[j + 4], w, q, q2);
+                ct_bfly<FAST>(a[j], a[j + 4], w, P);
         }
         if (NST >= 2)
         {
             Tw w0 = tw(1, 0), w1 = tw(1, 1);
-            ct_bfly(a[0], a[2], w0, q, q2);
-            ct_bfly(a[1], a[3], w0, q, q2);
-            ct_bfly(a[4], a[6], w1, q, q2);
-            ct_bfly(a[5], a[7], w1, q, q2);
+            ct_bfly<FAST>(a[0], a[2], w0, P);
+            ct_bfly<FAST>(a[1], a[3], w0, P);
+            ct_bfly<FAST>(a[4], a[6], w1, P);
+            ct_bfly<FAST>(a[5], a[7], w1, P);
         }
         if (NST >= 3)
         {
 #pragma unroll
             for (int p = 0; p < 4; p++)
-                ct_bfly(a[2 * p], a[2 * p + 1], tw(2, p), q, q2);
+                ct_bfly<FAST>(a[2 * p], a[2 * p + 1], tw(2, p), P);
         }
     }
 
@@ -67,36 +67,36 @@ namespace sb
     template <int FIRST, bool FINAL, class TwF>
     __device__ __forceinline__ void inv_regs(u64 (&a)[8], TwF tw, const PrimeDev &P)
     {
-        const u64 q = P.q, q2 = P.q2;
         if (FIRST <= 0)
         {
 #pragma unroll
             for (int p = 0; p < 4; p++)
-                gs_bfly(a[2 * p], a[2 * p + 1], tw(0, p), q, q2);
+                gs_bfly(a[2 * p], a[2 * p + 1], tw(0, p), P);
         }
         if (FIRST <= 1)
         {
             Tw w0 = tw(1, 0), w1 = tw(1, 1);
-            gs_bfly(a[0], a[2], w0, q, q2);
-            gs_bfly(a[1], a[3], w0, q, q2);
-            gs_bfly(a[4], a[6], w1, q, q2);
-            gs_bfly(a[5], a[7], w1, q, q2);
+            gs_bfly(a[0], a[2], w0, P);
+            gs_bfly(a[1], a[3], w0, P);
+            gs_bfly(a[4], a[6], w1, P);
+            gs_bfly(a[5], a[7], w1, P);
         }
         if (!FINAL)
         {
             Tw w = tw(2, 0);
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                gs_bfly(a[j], a[j + 4], w, q, q2);
+                gs_bfly(a[j], a[j + 4], w, P);
         }
         else
         {
+            // last stage: outputs reduced to [0, 2q) for the store
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
                 u64 u = a[j], v = a[j + 4];
-                a[j] = mul_shoup_lazy(u + v, P.inv_n, q);
-                a[j + 4] = mul_shoup_lazy(u - v + q2, P.inv_n_w, q);
+                a[j] = csub(mul_shoup_lazy4(u + v, P.inv_n, P.nq), P.q2);
+                a[j + 4] = csub(mul_shoup_lazy4(u - v + P.q4, P.inv_n_w, P.nq), P.q2);
             }
         }
     }
@@ -110,7 +110,7 @@ namespace sb
     }
 
     // ---------------------------------------------------------------------------------- forward: column pass ----
-    template <int LOGNA, class Op>
+    template <int LOGNA, bool FAST, class Op>
     __global__ void __launch_bounds__(kColThreads) ntt_fwd_col(Op op, const PrimeDev *__restrict__ primes)
     {
         constexpr int NA = 1 << LOGNA;
@@ -125,7 +125,6 @@ namespace sb
             return;
         const int tid = threadIdx.x, c = tid % C, ridx = tid / C;
         const PrimeDev P = primes[op.pid(row)];
-        const u64 q = P.q, q2 = P.q2;
 
         if (tid == 0)
             mbar_init(&bar, 1);
@@ -150,7 +149,7 @@ namespace sb
         {
             // partial first pass: stages 0..NST0-1 in the initial layout
             auto twf = [&](int lvl, int k) { return tw_s[(1 << lvl) + k]; };
-            fwd_regs<NST0>(a, twf, q, q2);
+            fwd_regs<NST0, FAST>(a, twf, P);
         }
         // full 3-stage passes; the layout changes between passes through the shared tile
 #pragma unroll
@@ -172,7 +171,7 @@ namespace sb
             }
             const int m = 1 << S;
             auto twf = [&](int lvl, int k) { return tw_s[(m << lvl) + (rhi << lvl) + k]; };
-            fwd_regs<3>(a, twf, q, q2);
+            fwd_regs<3, FAST>(a, twf, P);
             prev_g = g;
         }
         // last layout has g = 1: r = 8*ridx + j
@@ -183,7 +182,7 @@ namespace sb
     }
 
     // ----------------------------------------------------------------------------------- forward: local pass ----
-    template <class Op>
+    template <bool FAST, class Op>
     __global__ void __launch_bounds__(256) ntt_fwd_local(Op op, const PrimeDev *__restrict__ primes, int na)
     {
         __shared__ __align__(16) u64 xs[8][256];
@@ -192,7 +191,6 @@ namespace sb
             return;
         const int b = blockIdx.y * 8 + warp;
         const PrimeDev P = primes[op.pid(row)];
-        const u64 q = P.q, q2 = P.q2;
         const u64 *src = op.mid(row) + (b << kLocalLog);
         u64 *x = xs[warp];
         const Tw *__restrict__ tw = P.fwd;
@@ -204,7 +202,7 @@ namespace sb
             a[j] = src[l + 32 * j];
         {
             auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << lvl) + k); };
-            fwd_regs<3>(a, twf, q, q2);
+            fwd_regs<3, FAST>(a, twf, P);
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -216,7 +214,7 @@ namespace sb
             for (int j = 0; j < 8; j++)
                 a[j] = x[swz(32 * hi + lo + 4 * j)];
             auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (3 + lvl)) + (hi << lvl) + k); };
-            fwd_regs<3>(a, twf, q, q2);
+            fwd_regs<3, FAST>(a, twf, P);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -229,14 +227,17 @@ namespace sb
         {
             // strides 2 and 1: pairs (j,j+2) then (j,j+1)
             Tw wa = ldg_tw(tw + (t0 << 6) + 2 * l), wb = ldg_tw(tw + (t0 << 6) + 2 * l + 1);
-            ct_bfly(a[0], a[2], wa, q, q2);
-            ct_bfly(a[1], a[3], wa, q, q2);
-            ct_bfly(a[4], a[6], wb, q, q2);
-            ct_bfly(a[5], a[7], wb, q, q2);
+            ct_bfly<FAST>(a[0], a[2], wa, P);
+            ct_bfly<FAST>(a[1], a[3], wa, P);
+            ct_bfly<FAST>(a[4], a[6], wb, P);
+            ct_bfly<FAST>(a[5], a[7], wb, P);
 #pragma unroll
             for (int p = 0; p < 4; p++)
-                ct_bfly(a[2 * p], a[2 * p + 1], ldg_tw(tw + (t0 << 7) + 4 * l + p), q, q2);
+                ct_bfly<FAST>(a[2 * p], a[2 * p + 1], ldg_tw(tw + (t0 << 7) + 4 * l + p), P);
         }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = fwd_finish<FAST>(a[j], P);
         op.store8(row, (b << kLocalLog) + 8 * l, a, P);
     }
 
@@ -399,12 +400,12 @@ namespace sb
             for (int k = threadIdx.x; k < (n >> 1); k += blockDim.x)
             {
                 int i = k / gap, j = k % gap, pos = 2 * i * gap + j;
-                ct_bfly(s[pos], s[pos + gap], ldg_tw(P.fwd + m + i), P.q, P.q2);
+                ct_bfly<false>(s[pos], s[pos + gap], ldg_tw(P.fwd + m + i), P);
             }
             __syncthreads();
         }
         for (int i = threadIdx.x; i < n; i += blockDim.x)
-            op.store1(row, i, s[i], P);
+            op.store1(row, i, csub(s[i], P.q4), P);
     }
 
     template <class Op>
@@ -424,12 +425,12 @@ namespace sb
             {
                 int i = k / gap, j = k % gap, pos = 2 * i * gap + j;
                 if (m > 1)
-                    gs_bfly(s[pos], s[pos + gap], ldg_tw(P.inv + m + i), P.q, P.q2);
+                    gs_bfly(s[pos], s[pos + gap], ldg_tw(P.inv + m + i), P);
                 else
                 {
                     u64 u = s[pos], v = s[pos + gap];
-                    s[pos] = mul_shoup_lazy(u + v, P.inv_n, P.q);
-                    s[pos + gap] = mul_shoup_lazy(u - v + P.q2, P.inv_n_w, P.q);
+                    s[pos] = csub(mul_shoup_lazy4(u + v, P.inv_n, P.nq), P.q2);
+                    s[pos + gap] = csub(mul_shoup_lazy4(u - v + P.q4, P.inv_n_w, P.nq), P.q2);
                 }
             }
             __syncthreads();
@@ -499,7 +500,7 @@ namespace sb
 
     template <class Op>
     inline cudaError_t launch_ntt_fwd(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls,
-                                      const char *name = "ntt_fwd", int active_rows = -1)
+                                      const char *name = "ntt_fwd", int active_rows = -1, bool fast = false)
     {
         if (nrows <= 0)
             return cudaSuccess;
@@ -517,17 +518,20 @@ namespace sb
         ls.begin(name, 1, bytes, st); // column pass
         switch (logna)
         {
-        case 4: ntt_fwd_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
-        case 5: ntt_fwd_col<5, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
-        case 6: ntt_fwd_col<6, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
-        case 7: ntt_fwd_col<7, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
-        case 8: ntt_fwd_col<8, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
-        case 9: ntt_fwd_col<9, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 4: fast ? ntt_fwd_col<4, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<4, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 5: fast ? ntt_fwd_col<5, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<5, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 6: fast ? ntt_fwd_col<6, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<6, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 7: fast ? ntt_fwd_col<7, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<7, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 8: fast ? ntt_fwd_col<8, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<8, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
+        case 9: fast ? ntt_fwd_col<9, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<9, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
         default: return cudaErrorInvalidValue;
         }
         ls.end(st);
         ls.begin(name, 2, bytes, st); // local pass
-        ntt_fwd_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        if (fast)
+            ntt_fwd_local<true, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        else
+            ntt_fwd_local<false, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
         ls.end(st);
         return cudaGetLastError();
     }
