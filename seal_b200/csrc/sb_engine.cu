@@ -379,7 +379,7 @@ namespace sb
         Src dsrc; // coefficient-form digits: D (CKKS) or the target itself (BFV)
         u64 *E;   // [B][L+1][L][n]
         const PrimeDev *primes;
-        int logn, L, k, ntt_in;
+        int logn, L, k, ntt_in, reduce; // reduce == 0: every digit prime < 4 * every output prime, loads are in range as is
         __device__ __forceinline__ bool skip(int row) const { return ntt_in && ((row / L) % (L + 1)) == (row % L); }
         __device__ __forceinline__ int pid(int row) const
         {
@@ -391,7 +391,7 @@ namespace sb
             int J = row % L, b = row / (L * (L + 1));
             u64 qJ = primes[J].q;
             u64 v = dsrc.get(b, J, idx, qJ);
-            return qJ > P.q ? barrett64(v, P.q, P.ratio_hi) : v; // evaluator.cpp:2690-2698
+            return (reduce && qJ > P.q) ? barrett64(v, P.q, P.ratio_hi) : v; // evaluator.cpp:2690-2698
         }
         __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
         __device__ __forceinline__ u64 *mid(int row) const { return E + (static_cast<long long>(row) << logn); }
@@ -432,6 +432,80 @@ namespace sb
         u64 *o = Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + idx;
         o[0] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
         o[static_cast<long long>(L + 1) << logn] = barrett128(lo1, hi1, P.q, P.ratio_lo, P.ratio_hi);
+    }
+
+    // (2b)+(3) fused: the 8 in-block stages of every digit transform + the multiply-accumulate with the key, looping
+    //     over the digits J inside the kernel so the transformed digits never reach memory and the 128-bit sums live in
+    //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
+    //     blocks.  blockIdx.x = b + B * block_group: consecutive CTAs share the key tile of (I, block group) through L2.
+    template <bool FAST>
+    __global__ void __launch_bounds__(256, 2) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
+                                                                   u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
+                                                                   int B)
+    {
+        __shared__ __align__(16) u64 xs[8][256];
+        const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const int b = blockIdx.x % B, bg = blockIdx.x / B, I = blockIdx.y;
+        const int na = 1 << (logn - kLocalLog), blk = bg * 8 + warp;
+        const int ki = (I == L) ? k - 1 : I;
+        const PrimeDev P = primes[ki];
+        const int e0 = (blk << kLocalLog) + 8 * l; // first of this lane's 8 consecutive output coefficients
+        u64 s0l[8], s0h[8], s1l[8], s1h[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            s0l[j] = s0h[j] = s1l[j] = s1h[j] = 0;
+        const u64 *erow = E + ((static_cast<long long>(b) * (L + 1) + I) * L << logn) + (blk << kLocalLog);
+        for (int J = 0; J < L; J++)
+        {
+            u64 a[8];
+            if (ntt_in && J == I)
+            {
+                // the input already is digit J in NTT form modulo q_J (evaluator.cpp:2682-2685)
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = tgt.get(b, J, e0 + j, P.q);
+            }
+            else
+            {
+                const u64 *src = erow + (static_cast<long long>(J) << logn);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = src[l + 32 * j];
+                fwd_local_block<FAST>(a, xs[warp], P.fwd, na + blk, l, P);
+                if (!FAST)
+                {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        a[j] = csub(csub(csub(a[j], P.q4), P.q2), P.q); // keeps 256 summands below 2^128 for 60-bit primes
+                }
+            }
+            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + e0);
+            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + k + ki) << logn) + e0);
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+            {
+                ulonglong2 v = __ldg(k0 + h);
+                mac128(s0l[2 * h], s0h[2 * h], a[2 * h], v.x);
+                mac128(s0l[2 * h + 1], s0h[2 * h + 1], a[2 * h + 1], v.y);
+            }
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+            {
+                ulonglong2 v = __ldg(k1 + h);
+                mac128(s1l[2 * h], s1h[2 * h], a[2 * h], v.x);
+                mac128(s1l[2 * h + 1], s1h[2 * h + 1], a[2 * h + 1], v.y);
+            }
+        }
+        ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + e0);
+        ulonglong2 *o1 = reinterpret_cast<ulonglong2 *>(Pp + (((static_cast<long long>(b) * 2 + 1) * (L + 1) + I) << logn) + e0);
+#pragma unroll
+        for (int h = 0; h < 4; h++)
+        {
+            o0[h] = make_ulonglong2(barrett128(s0l[2 * h], s0h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
+                                    barrett128(s0l[2 * h + 1], s0h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
+            o1[h] = make_ulonglong2(barrett128(s1l[2 * h], s1h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
+                                    barrett128(s1l[2 * h + 1], s1h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
+        }
     }
 
     // (4a) special-prime component back to coefficients, + floor(q_sp/2) for rounding; evaluator.cpp:2809-2817.
@@ -642,18 +716,40 @@ namespace sb
             cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats, "ks_target_intt"), "ks intt");
             dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
         }
+        const bool fused = c.logn >= 12; // two-pass transforms: fuse the in-block stages with the key multiply-accumulate
         {
-            OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0 };
+            // the transforms accept inputs below 4q: skip the digit re-reduction when no digit prime reaches 4x an output prime
+            u64 qmax = 0, qmin = ~0ull;
+            for (size_t i = 0; i < L; i++)
+                qmax = std::max(qmax, c.q[i]), qmin = std::min(qmin, c.q[i]);
+            qmin = std::min(qmin, c.q[c.k - 1]);
+            const int reduce = (qmax >> 2) >= qmin ? 1 : 0;
+            OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0, reduce };
             cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats, "ks_digit_ntt",
-                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L)), c.fast_q),
+                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L)), c.fast_q, fused),
                        "ks digit ntt");
         }
+        // digits in + 2 accumulated components out per (b, I), plus one pass over the key
+        const double mac_bytes = 8.0 * n * (static_cast<double>(B) * (L + 1) * (L + 2) + 2.0 * L * (L + 1));
+        if (fused)
+        {
+            const int na = n >> kLocalLog;
+            dim3 grid(static_cast<unsigned>(B * (na / 8)), static_cast<unsigned>(L + 1));
+            c.stats.begin("ks_local_mac", 0, mac_bytes, st);
+            if (c.fast_q)
+                ks_local_mac_kernel<true><<<grid, 256, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
+                                                                static_cast<int>(B));
+            else
+                ks_local_mac_kernel<false><<<grid, 256, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
+                                                                 static_cast<int>(B));
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "ks_local_mac_kernel");
+        }
+        else
         {
             int threads = std::min(n, 256);
             dim3 grid(static_cast<unsigned>(B), (n + threads - 1) / threads, static_cast<unsigned>(L + 1));
-            // digits in + 2 accumulated components out per (b, I), plus one pass over the key
-            double bytes = 8.0 * n * (static_cast<double>(B) * (L + 1) * (L + 2) + 2.0 * L * (L + 1));
-            c.stats.begin("ks_mac", 0, bytes, st);
+            c.stats.begin("ks_mac", 0, mac_bytes, st);
             ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_mac_kernel");

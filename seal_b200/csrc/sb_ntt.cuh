@@ -182,24 +182,12 @@ namespace sb
     }
 
     // ----------------------------------------------------------------------------------- forward: local pass ----
-    template <bool FAST, class Op>
-    __global__ void __launch_bounds__(256) ntt_fwd_local(Op op, const PrimeDev *__restrict__ primes, int na)
+    // The 8 stages inside one 256-coefficient block, executed by one warp.  In: a[j] = coefficient l + 32 j of the
+    // block (lane l).  Out: a[j] = coefficient 8 l + j, lazily reduced (FAST: unreduced growth, guarded: < 8q).
+    // x = the warp's private 256-word shared slice; t0 = NA + block index (twiddle base of the block).
+    template <bool FAST>
+    __device__ __forceinline__ void fwd_local_block(u64 (&a)[8], u64 *x, const Tw *__restrict__ tw, int t0, int l, const PrimeDev &P)
     {
-        __shared__ __align__(16) u64 xs[8][256];
-        const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (op.skip(row))
-            return;
-        const int b = blockIdx.y * 8 + warp;
-        const PrimeDev P = primes[op.pid(row)];
-        const u64 *src = op.mid(row) + (b << kLocalLog);
-        u64 *x = xs[warp];
-        const Tw *__restrict__ tw = P.fwd;
-        const int t0 = na + b;
-
-        u64 a[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            a[j] = src[l + 32 * j];
         {
             auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << lvl) + k); };
             fwd_regs<3, FAST>(a, twf, P);
@@ -224,6 +212,7 @@ namespace sb
 #pragma unroll
         for (int j = 0; j < 8; j++)
             a[j] = x[swz(8 * l + j)];
+        __syncwarp();
         {
             // strides 2 and 1: pairs (j,j+2) then (j,j+1)
             Tw wa = ldg_tw(tw + (t0 << 6) + 2 * l), wb = ldg_tw(tw + (t0 << 6) + 2 * l + 1);
@@ -235,6 +224,23 @@ namespace sb
             for (int p = 0; p < 4; p++)
                 ct_bfly<FAST>(a[2 * p], a[2 * p + 1], ldg_tw(tw + (t0 << 7) + 4 * l + p), P);
         }
+    }
+
+    template <bool FAST, class Op>
+    __global__ void __launch_bounds__(256) ntt_fwd_local(Op op, const PrimeDev *__restrict__ primes, int na)
+    {
+        __shared__ __align__(16) u64 xs[8][256];
+        const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (op.skip(row))
+            return;
+        const int b = blockIdx.y * 8 + warp;
+        const PrimeDev P = primes[op.pid(row)];
+        const u64 *src = op.mid(row) + (b << kLocalLog);
+        u64 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = src[l + 32 * j];
+        fwd_local_block<FAST>(a, xs[warp], P.fwd, na + b, l, P);
 #pragma unroll
         for (int j = 0; j < 8; j++)
             a[j] = fwd_finish<FAST>(a[j], P);
@@ -500,7 +506,7 @@ namespace sb
 
     template <class Op>
     inline cudaError_t launch_ntt_fwd(const Op &op, int nrows, int logn, const PrimeDev *primes, cudaStream_t st, LaunchStats &ls,
-                                      const char *name = "ntt_fwd", int active_rows = -1, bool fast = false)
+                                      const char *name = "ntt_fwd", int active_rows = -1, bool fast = false, bool col_only = false)
     {
         if (nrows <= 0)
             return cudaSuccess;
@@ -527,6 +533,8 @@ namespace sb
         default: return cudaErrorInvalidValue;
         }
         ls.end(st);
+        if (col_only)
+            return cudaGetLastError(); // the caller runs its own fused local pass on op.mid()
         ls.begin(name, 2, bytes, st); // local pass
         if (fast)
             ntt_fwd_local<true, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
