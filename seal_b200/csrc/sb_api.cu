@@ -384,27 +384,99 @@ int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_
     SB_CATCH
 }
 
-// ---- host-buffer variants: staged through device buffers owned by the call ---------------------------------------
+// ---- host-buffer variants ------------------------------------------------------------------------------------------
+// The batch is cut into chunks that flow through a 3-stage pipeline on three streams: H2D copy of chunk i+1 | kernels
+// of chunk i | D2H copy of chunk i-1, double-buffered device staging owned by the context (PCIe is full duplex, so with
+// pinned host buffers both copy directions overlap each other and the compute).  Pageable host memory works too, the
+// copies then serialise inside the driver.
+} // extern "C"
+
 namespace
 {
-    struct DevBuf
+    struct HostPipe
     {
-        u64 *p = nullptr;
-        explicit DevBuf(size_t words) { cuda_check(cudaMalloc(reinterpret_cast<void **>(&p), words * sizeof(u64)), "cudaMalloc(io)"); }
-        ~DevBuf() { cudaFree(p); }
-        DevBuf(const DevBuf &) = delete;
-        DevBuf &operator=(const DevBuf &) = delete;
+        Context &c;
+        cudaStream_t s_in, s_comp, s_out;
+        cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+        explicit HostPipe(Context &ctx) : c(ctx)
+        {
+            IoArena &io = c.io;
+            if (!io.ready)
+            {
+                for (auto *s : { &io.s_in, &io.s_comp, &io.s_out })
+                    cuda_check(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate");
+                for (int i = 0; i < 2; i++)
+                    for (auto *e : { &io.ev_in[i], &io.ev_comp[i], &io.ev_out[i] })
+                        cuda_check(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+                io.ready = true;
+            }
+            s_in = io.s_in, s_comp = io.s_comp, s_out = io.s_out;
+            for (int i = 0; i < 2; i++)
+                ev_in[i] = io.ev_in[i], ev_comp[i] = io.ev_comp[i], ev_out[i] = io.ev_out[i];
+        }
+        u64 *buffer(int slot, int which, size_t words)
+        {
+            IoArena &io = c.io;
+            size_t &cap = io.cap[slot][which];
+            if (words > cap)
+            {
+                cuda_check(cudaDeviceSynchronize(), "sync before io growth");
+                cudaFree(io.buf[slot][which]);
+                io.buf[slot][which] = nullptr;
+                cap = 0;
+                cuda_check(cudaMalloc(reinterpret_cast<void **>(&io.buf[slot][which]), words * sizeof(u64)), "cudaMalloc(io)");
+                cap = words;
+            }
+            return io.buf[slot][which];
+        }
+        // wa / wb / wo: words per ciphertext of input a, input b (0 = none), output (0 = in place in a)
+        template <class F>
+        void run(size_t batch, size_t wa, size_t wb, size_t wo, const uint64_t *ha, const uint64_t *hb, uint64_t *ho, F &&op)
+        {
+            const size_t per_ct = (wa + wb + wo) * sizeof(u64);
+            size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (size_t(1) << 30) / std::max<size_t>(per_ct, 1)));
+            if (chunk >= batch && batch >= 4)
+                chunk = (batch + 1) / 2; // at least two chunks so the copies overlap the kernels
+            // size all staging (and let the op grow its scratch) before the pipeline starts: growth synchronises the device
+            for (int slot = 0; slot < 2; slot++)
+            {
+                buffer(slot, 0, chunk * wa);
+                if (wb)
+                    buffer(slot, 1, chunk * wb);
+                if (wo)
+                    buffer(slot, 2, chunk * wo);
+            }
+            size_t i = 0;
+            for (size_t b0 = 0; b0 < batch; b0 += chunk, i++)
+            {
+                const size_t B = std::min(chunk, batch - b0);
+                const int slot = static_cast<int>(i & 1);
+                u64 *da = buffer(slot, 0, B * wa), *db = wb ? buffer(slot, 1, B * wb) : nullptr, *dout = wo ? buffer(slot, 2, B * wo) : da;
+                if (i >= 2)
+                {
+                    // inputs of this slot are free once its previous kernels finished (and, in place, once copied out)
+                    cuda_check(cudaStreamWaitEvent(s_in, wo ? ev_comp[slot] : ev_out[slot], 0), "wait");
+                }
+                cuda_check(cudaMemcpyAsync(da, ha + b0 * wa, B * wa * sizeof(u64), cudaMemcpyHostToDevice, s_in), "H2D");
+                if (wb)
+                    cuda_check(cudaMemcpyAsync(db, hb + b0 * wb, B * wb * sizeof(u64), cudaMemcpyHostToDevice, s_in), "H2D");
+                cuda_check(cudaEventRecord(ev_in[slot], s_in), "record");
+                cuda_check(cudaStreamWaitEvent(s_comp, ev_in[slot], 0), "wait");
+                if (i >= 2 && wo)
+                    cuda_check(cudaStreamWaitEvent(s_comp, ev_out[slot], 0), "wait"); // output staging of this slot drained
+                op(B, da, db, dout, s_comp);
+                cuda_check(cudaEventRecord(ev_comp[slot], s_comp), "record");
+                cuda_check(cudaStreamWaitEvent(s_out, ev_comp[slot], 0), "wait");
+                cuda_check(cudaMemcpyAsync(ho + b0 * (wo ? wo : wa), dout, B * (wo ? wo : wa) * sizeof(u64), cudaMemcpyDeviceToHost, s_out), "D2H");
+                cuda_check(cudaEventRecord(ev_out[slot], s_out), "record");
+            }
+            cuda_check(cudaStreamSynchronize(s_out), "synchronize");
+            cuda_check(cudaStreamSynchronize(s_comp), "synchronize");
+        }
     };
-    void h2d(u64 *d, const uint64_t *h, size_t words, cudaStream_t st)
-    {
-        cuda_check(cudaMemcpyAsync(d, h, words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
-    }
-    void d2h(uint64_t *h, const u64 *d, size_t words, cudaStream_t st)
-    {
-        cuda_check(cudaMemcpyAsync(h, d, words * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H");
-        cuda_check(cudaStreamSynchronize(st), "synchronize");
-    }
 } // namespace
+
+extern "C" {
 
 static int ntt_host(sb200_context *ctx, bool inverse, size_t L, size_t size, size_t batch, uint64_t *h)
 {
@@ -412,11 +484,8 @@ static int ntt_host(sb200_context *ctx, bool inverse, size_t L, size_t size, siz
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
-    size_t words = batch * size * L * c.n;
-    DevBuf d(words);
-    h2d(d.p, h, words, 0);
-    op_ntt(c, inverse, L, size, batch, d.p, 0);
-    d2h(h, d.p, words, 0);
+    HostPipe(c).run(batch, size * L * c.n, 0, 0, h, nullptr, h,
+                    [&](size_t B, u64 *da, u64 *, u64 *, cudaStream_t st) { op_ntt(c, inverse, L, size, B, da, st); });
     return SB200_OK;
     SB_CATCH
 }
@@ -437,15 +506,13 @@ int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
-    size_t w = batch * L * c.n;
-    DevBuf da(2 * w), db(2 * w), dout(3 * w);
-    h2d(da.p, a, 2 * w, 0);
-    h2d(db.p, b, 2 * w, 0);
-    if (c.scheme == SB200_SCHEME_CKKS)
-        op_ckks_multiply(c, L, batch, da.p, db.p, dout.p, 0);
-    else
-        op_bfv_multiply(c, L, batch, da.p, db.p, dout.p, 0);
-    d2h(out3, dout.p, 3 * w, 0);
+    const size_t w = L * c.n;
+    HostPipe(c).run(batch, 2 * w, 2 * w, 3 * w, a, b, out3, [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
+        if (c.scheme == SB200_SCHEME_CKKS)
+            op_ckks_multiply(c, L, B, da, db, dout, st);
+        else
+            op_bfv_multiply(c, L, B, da, db, dout, st);
+    });
     return SB200_OK;
     SB_CATCH
 }
@@ -458,11 +525,9 @@ int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uin
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
-    size_t w = batch * L * c.n;
-    DevBuf din(3 * w), dout(2 * w);
-    h2d(din.p, in3, 3 * w, 0);
-    op_relinearize(c, L, batch, din.p, key->k, dout.p, 0);
-    d2h(out2, dout.p, 2 * w, 0);
+    const size_t w = L * c.n;
+    HostPipe(c).run(batch, 3 * w, 0, 2 * w, in3, nullptr, out2,
+                    [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) { op_relinearize(c, L, B, da, key->k, dout, st); });
     return SB200_OK;
     SB_CATCH
 }
@@ -477,12 +542,10 @@ int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, 
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
-    size_t w = batch * L * c.n;
-    DevBuf da(2 * w), db(2 * w), dout(2 * w);
-    h2d(da.p, a, 2 * w, 0);
-    h2d(db.p, b, 2 * w, 0);
-    op_multiply_relinearize(c, L, batch, da.p, db.p, key->k, dout.p, 0);
-    d2h(out2, dout.p, 2 * w, 0);
+    const size_t w = L * c.n;
+    HostPipe(c).run(batch, 2 * w, 2 * w, 2 * w, a, b, out2, [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
+        op_multiply_relinearize(c, L, B, da, db, key->k, dout, st);
+    });
     return SB200_OK;
     SB_CATCH
 }
@@ -496,14 +559,12 @@ static int modswitch_host(sb200_context *ctx, bool rescale, size_t L, size_t bat
     check_level(c, L, batch);
     if (L < 2)
         throw std::invalid_argument("end of modulus switching chain reached");
-    size_t wi = batch * 2 * L * c.n, wo = batch * 2 * (L - 1) * c.n;
-    DevBuf din(wi), dout(wo);
-    h2d(din.p, in2, wi, 0);
-    if (rescale)
-        op_rescale(c, L, batch, din.p, dout.p, 0);
-    else
-        op_mod_switch(c, L, batch, din.p, dout.p, 0);
-    d2h(out2, dout.p, wo, 0);
+    HostPipe(c).run(batch, 2 * L * c.n, 0, 2 * (L - 1) * c.n, in2, nullptr, out2, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
+        if (rescale)
+            op_rescale(c, L, B, da, dout, st);
+        else
+            op_mod_switch(c, L, B, da, dout, st);
+    });
     return SB200_OK;
     SB_CATCH
 }
@@ -525,11 +586,9 @@ int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const ui
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
-    size_t w = batch * 2 * L * c.n;
-    DevBuf din(w), dout(w);
-    h2d(din.p, in2, w, 0);
-    op_apply_galois(c, L, batch, din.p, elt, key->k, dout.p, 0);
-    d2h(out2, dout.p, w, 0);
+    const size_t w = 2 * L * c.n;
+    HostPipe(c).run(batch, w, 0, w, in2, nullptr, out2,
+                    [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) { op_apply_galois(c, L, B, da, elt, key->k, dout, st); });
     return SB200_OK;
     SB_CATCH
 }

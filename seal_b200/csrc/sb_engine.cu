@@ -33,6 +33,17 @@ namespace sb
         cudaFree(d_primes);
         cudaFree(d_invq);
         cudaFree(scratch);
+        for (auto &slot : io.buf)
+            for (auto p : slot)
+                cudaFree(p);
+        if (io.ready)
+        {
+            for (auto s : { io.s_in, io.s_comp, io.s_out })
+                cudaStreamDestroy(s);
+            for (int i = 0; i < 2; i++)
+                for (auto e : { io.ev_in[i], io.ev_comp[i], io.ev_out[i] })
+                    cudaEventDestroy(e);
+        }
     }
 
     void *Context::ensure_scratch(size_t bytes)

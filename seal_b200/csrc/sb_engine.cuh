@@ -26,6 +26,16 @@ namespace sb
         size_t digits = 0;
     };
 
+    // staging for the host-buffer entry points (sb_api.cu: HostPipe)
+    struct IoArena
+    {
+        bool ready = false;
+        cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+        cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+        u64 *buf[2][3] = {};
+        size_t cap[2][3] = {};
+    };
+
     struct Context
     {
         int scheme = 0, device = 0, logn = 0;
@@ -44,6 +54,7 @@ namespace sb
         void *scratch = nullptr;
         size_t scratch_bytes = 0, table_bytes = 0, scratch_budget = size_t(8) << 30;
         LaunchStats stats;
+        IoArena io;
         std::mutex mu;
 
         ~Context();

@@ -13,12 +13,11 @@ __device__ __forceinline__ void bf_exact_guard(u64 &x, u64 &y, Tw w, const Prime
 __device__ __forceinline__ u64 approx_mulhi_w(u64 y, u64 wq)
 {   // all three partial products as mul.wide (no IMAD.HI)
     unsigned y0 = (unsigned)y, y1 = (unsigned)(y >> 32), wq0 = (unsigned)wq, wq1 = (unsigned)(wq >> 32);
-    u64 m, n, T;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(m) : "r"(y0), "r"(wq1));
-    u64 mh = m >> 32;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(n) : "r"(y1), "r"(wq0), "l"(mh));
-    u64 nh = n >> 32;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(T) : "r"(y1), "r"(wq1), "l"(nh));
+    u64 a, b, T;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(a) : "r"(y1), "r"(wq0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(b) : "r"(y0), "r"(wq1));
+    u64 s = (a >> 32) + (b >> 32);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(T) : "r"(y1), "r"(wq1), "l"(s));
     return T;
 }
 __device__ __forceinline__ u64 mullo_combine_a(u64 y, u64 w, u64 T, u64 nq)
@@ -42,6 +41,22 @@ __device__ __forceinline__ void bf_fast_asm(u64 &x, u64 &y, Tw w, const PrimeDev
     x = u + v;
     y = u - v + P.q4;
 }
+__device__ __forceinline__ void bf_fast_exact(u64 &x, u64 &y, Tw w, const PrimeDev &P)
+{   // exact quotient (compiler's mul.hi.u64), remainder via 64-bit mad.lo with 2^64-q: result < 2q, growth 2q/stage
+    u64 T = __umul64hi(y, w.wq);
+    u64 v = y * w.w + T * P.nq;
+    u64 u = x;
+    x = u + v;
+    y = u - v + P.q2;
+}
+__device__ __forceinline__ void bf_fast_asm2(u64 &x, u64 &y, Tw w, const PrimeDev &P)
+{   // approximate quotient, remainder through plain 64-bit C multiplies (compiler picks the expansion)
+    u64 T = approx_mulhi_w(y, w.wq);
+    u64 v = y * w.w + T * P.nq;
+    u64 u = x;
+    x = u + v;
+    y = u - v + P.q4;
+}
 template <int KIND>
 __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *tws)
 {
@@ -57,13 +72,15 @@ __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *t
     else if (KIND == 1) ct_bfly<true>(X, Y, W, P);               \
     else if (KIND == 2) ct_bfly<false>(X, Y, W, P);              \
     else if (KIND == 3) bf_fast_asm(X, Y, W, P);                 \
-    else if (KIND == 4) gs_bfly(X, Y, W, P);
+    else if (KIND == 4) gs_bfly(X, Y, W, P);                     \
+    else if (KIND == 5) bf_fast_exact(X, Y, W, P);               \
+    else if (KIND == 6) bf_fast_asm2(X, Y, W, P);
 #pragma unroll
         for (int j = 0; j < 4; j++) { BF(a[j], a[j + 4], t[0]) }
         BF(a[0], a[2], t[1]) BF(a[1], a[3], t[1]) BF(a[4], a[6], t[2]) BF(a[5], a[7], t[2])
 #pragma unroll
         for (int p = 0; p < 4; p++) { BF(a[2 * p], a[2 * p + 1], t[3 + p]) }
-        if (KIND == 1 || KIND == 3)
+        if (KIND == 1 || KIND == 3 || KIND == 5 || KIND == 6)
         {   // keep FAST-mode values bounded the way a real kernel does once per 17 stages; here once per 12
 #pragma unroll
             for (int j = 0; j < 8; j++) a[j] = (r & 7) ? a[j] : barrett_lazy4(a[j], P.ratio_hi, P.nq);
@@ -119,5 +136,7 @@ int main()
     run<2>("guarded lazy4 (C)", d, dp, dt);
     run<3>("FAST lazy4 (asm wide), + barrett/96", d, dp, dt);
     run<4>("inverse gs lazy4", d, dp, dt);
+    run<5>("FAST exact mulhi + mad.lo nq", d, dp, dt);
+    run<6>("FAST approx(asm) + C 64-bit mads", d, dp, dt);
     return 0;
 }
