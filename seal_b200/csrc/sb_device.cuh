@@ -43,25 +43,50 @@ __device__ __forceinline__ u64 csub(u64 x, u64 q)
 //     T = y1*wq1 + hi32(y1*wq0) + hi32(y0*wq1)      with  t-2 <= T <= t,  t = floor(y*wq / 2^64)
 // and the remainder y*w - T*q is formed as lo64(y*w + T*(2^64-q)) with two wide and four 32-bit multiply-adds.
 // Result: x*w mod q in [0, 4q) for ANY 64-bit x (w < q, wq = floor(w 2^64 / q), q < 2^61).
+__device__ __forceinline__ u64 pack64(unsigned lo, unsigned hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack64(u64 v, unsigned &lo, unsigned &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+// written with explicit 32-bit PTX so that ptxas keeps every 64-bit quantity in the register pair the wide multiply-add
+// produced it in (the C formulation costs ~3 extra moves per butterfly, which also land on the multiply pipe)
 __device__ __forceinline__ u64 approx_mulhi(u64 y, u64 wq)
 {
-    const unsigned y0 = static_cast<unsigned>(y), y1 = static_cast<unsigned>(y >> 32);
-    const unsigned wq0 = static_cast<unsigned>(wq), wq1 = static_cast<unsigned>(wq >> 32);
+    unsigned y0, y1, wq0, wq1, alo, ahi, blo, bhi, slo, shi;
+    unpack64(y, y0, y1);
+    unpack64(wq, wq0, wq1);
+    u64 a, b, T;
     // the two cross products have equal weight 2^32: keep their high halves, drop their low halves and y0*wq0
-    u64 a = static_cast<u64>(y1) * wq0, b = static_cast<u64>(y0) * wq1;
-    return static_cast<u64>(y1) * wq1 + ((a >> 32) + (b >> 32));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(a) : "r"(y1), "r"(wq0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(b) : "r"(y0), "r"(wq1));
+    unpack64(a, alo, ahi);
+    unpack64(b, blo, bhi);
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(slo), "=r"(shi) : "r"(ahi), "r"(bhi));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(T) : "r"(y1), "r"(wq1), "l"(pack64(slo, shi)));
+    return T;
 }
 // lo64(y*w + T*nq)
 __device__ __forceinline__ u64 mullo_combine(u64 y, u64 w, u64 T, u64 nq)
 {
-    const unsigned y0 = static_cast<unsigned>(y), y1 = static_cast<unsigned>(y >> 32);
-    const unsigned w0 = static_cast<unsigned>(w), w1 = static_cast<unsigned>(w >> 32);
-    const unsigned T0 = static_cast<unsigned>(T), T1 = static_cast<unsigned>(T >> 32);
-    const unsigned n0 = static_cast<unsigned>(nq), n1 = static_cast<unsigned>(nq >> 32);
-    u64 acc = static_cast<u64>(y0) * w0;
-    acc = static_cast<u64>(T0) * n0 + acc;
-    unsigned hi = static_cast<unsigned>(acc >> 32) + y0 * w1 + y1 * w0 + T0 * n1 + T1 * n0;
-    return (static_cast<u64>(hi) << 32) | static_cast<unsigned>(acc);
+    unsigned y0, y1, w0, w1, T0, T1, n0, n1, lo, hi;
+    unpack64(y, y0, y1);
+    unpack64(w, w0, w1);
+    unpack64(T, T0, T1);
+    unpack64(nq, n0, n1);
+    u64 acc;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(T0), "r"(n0));
+    unpack64(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(T0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(T1), "r"(n0));
+    return pack64(lo, hi);
 }
 __device__ __forceinline__ u64 mul_shoup_lazy4(u64 x, Tw t, u64 nq)
 {

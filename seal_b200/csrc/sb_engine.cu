@@ -450,21 +450,27 @@ namespace sb
     //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
     //     blocks.  blockIdx.x = b + B * block_group: consecutive CTAs share the key tile of (I, block group) through L2.
     template <bool FAST>
-    __global__ void __launch_bounds__(256, 2) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
+    __global__ void __launch_bounds__(256, 3) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
                                                                    u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
                                                                    int B)
     {
         __shared__ __align__(16) u64 xs[8][256];
+        // 128-bit sums of key component 1 live in shared memory ([j][thread], conflict-free 16-byte accesses) so that the
+        // register file holds three CTAs per SM; component 0 stays in registers
+        __shared__ __align__(16) ulonglong2 acc1[8][256];
         const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         const int b = blockIdx.x % B, bg = blockIdx.x / B, I = blockIdx.y;
         const int na = 1 << (logn - kLocalLog), blk = bg * 8 + warp;
         const int ki = (I == L) ? k - 1 : I;
         const PrimeDev P = primes[ki];
         const int e0 = (blk << kLocalLog) + 8 * l; // first of this lane's 8 consecutive output coefficients
-        u64 s0l[8], s0h[8], s1l[8], s1h[8];
+        u64 s0l[8], s0h[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
-            s0l[j] = s0h[j] = s1l[j] = s1h[j] = 0;
+        {
+            s0l[j] = s0h[j] = 0;
+            acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
+        }
         const u64 *erow = E + ((static_cast<long long>(b) * (L + 1) + I) * L << logn) + (blk << kLocalLog);
         for (int J = 0; J < L; J++)
         {
@@ -503,8 +509,11 @@ namespace sb
             for (int h = 0; h < 4; h++)
             {
                 ulonglong2 v = __ldg(k1 + h);
-                mac128(s1l[2 * h], s1h[2 * h], a[2 * h], v.x);
-                mac128(s1l[2 * h + 1], s1h[2 * h + 1], a[2 * h + 1], v.y);
+                ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
+                mac128(t0.x, t0.y, a[2 * h], v.x);
+                mac128(t1.x, t1.y, a[2 * h + 1], v.y);
+                acc1[2 * h][threadIdx.x] = t0;
+                acc1[2 * h + 1][threadIdx.x] = t1;
             }
         }
         ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + e0);
@@ -514,8 +523,8 @@ namespace sb
         {
             o0[h] = make_ulonglong2(barrett128(s0l[2 * h], s0h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
                                     barrett128(s0l[2 * h + 1], s0h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
-            o1[h] = make_ulonglong2(barrett128(s1l[2 * h], s1h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
-                                    barrett128(s1l[2 * h + 1], s1h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
+            ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
+            o1[h] = make_ulonglong2(barrett128(t0.x, t0.y, P.q, P.ratio_lo, P.ratio_hi), barrett128(t1.x, t1.y, P.q, P.ratio_lo, P.ratio_hi));
         }
     }
 

@@ -29,6 +29,10 @@
 #include "sb_device.cuh"
 #include <vector>
 
+#ifndef SB_COL_MIN_BLOCKS
+#define SB_COL_MIN_BLOCKS 3 // 512-thread column-pass CTAs per SM the register allocation is tuned for
+#endif
+
 namespace sb
 {
     constexpr int kLocalLog = 8;       // 256-coefficient local blocks
@@ -111,7 +115,7 @@ namespace sb
 
     // ---------------------------------------------------------------------------------- forward: column pass ----
     template <int LOGNA, bool FAST, class Op>
-    __global__ void __launch_bounds__(kColThreads) ntt_fwd_col(Op op, const PrimeDev *__restrict__ primes)
+    __global__ void __launch_bounds__(kColThreads, SB_COL_MIN_BLOCKS) ntt_fwd_col(Op op, const PrimeDev *__restrict__ primes)
     {
         constexpr int NA = 1 << LOGNA;
         constexpr int C = kTile / NA;

@@ -57,6 +57,43 @@ __device__ __forceinline__ void bf_fast_asm2(u64 &x, u64 &y, Tw w, const PrimeDe
     x = u + v;
     y = u - v + P.q4;
 }
+__device__ __forceinline__ u64 pack(unsigned lo, unsigned hi){ u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpack(u64 v, unsigned &lo, unsigned &hi){ asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 lazy4_asm(u64 y, Tw w, u64 nq)
+{
+    unsigned y0, y1, wq0, wq1, w0, w1, n0, n1;
+    unpack(y, y0, y1); unpack(w.wq, wq0, wq1); unpack(w.w, w0, w1); unpack(nq, n0, n1);
+    u64 a, b, T, acc;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(a) : "r"(y1), "r"(wq0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(b) : "r"(y0), "r"(wq1));
+    unsigned alo, ahi, blo, bhi; unpack(a, alo, ahi); unpack(b, blo, bhi);
+    unsigned slo, shi;
+    asm("add.cc.u32 %0, %2, %3; addc.u32 %1, 0, 0;" : "=r"(slo), "=r"(shi) : "r"(ahi), "r"(bhi));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(T) : "r"(y1), "r"(wq1), "l"(pack(slo, shi)));
+    unsigned T0, T1; unpack(T, T0, T1);
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(T0), "r"(n0));
+    unsigned lo, hi; unpack(acc, lo, hi);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y0), "r"(w1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(y1), "r"(w0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(T0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(T1), "r"(n0));
+    return pack(lo, hi);
+}
+__device__ __forceinline__ void bf_fast_asm3(u64 &x, u64 &y, Tw w, const PrimeDev &P)
+{
+    u64 v = lazy4_asm(y, w, P.nq);
+    u64 u = x;
+    x = u + v;
+    y = u - v + P.q4;
+}
+__device__ __forceinline__ void bf_guard_asm3(u64 &x, u64 &y, Tw w, const PrimeDev &P)
+{
+    u64 v = lazy4_asm(y, w, P.nq);
+    u64 u = csub(x, P.q4);
+    x = u + v;
+    y = u - v + P.q4;
+}
 template <int KIND>
 __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *tws)
 {
@@ -74,13 +111,15 @@ __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *t
     else if (KIND == 3) bf_fast_asm(X, Y, W, P);                 \
     else if (KIND == 4) gs_bfly(X, Y, W, P);                     \
     else if (KIND == 5) bf_fast_exact(X, Y, W, P);               \
-    else if (KIND == 6) bf_fast_asm2(X, Y, W, P);
+    else if (KIND == 6) bf_fast_asm2(X, Y, W, P);                \
+    else if (KIND == 7) bf_fast_asm3(X, Y, W, P);                \
+    else if (KIND == 8) bf_guard_asm3(X, Y, W, P);
 #pragma unroll
         for (int j = 0; j < 4; j++) { BF(a[j], a[j + 4], t[0]) }
         BF(a[0], a[2], t[1]) BF(a[1], a[3], t[1]) BF(a[4], a[6], t[2]) BF(a[5], a[7], t[2])
 #pragma unroll
         for (int p = 0; p < 4; p++) { BF(a[2 * p], a[2 * p + 1], t[3 + p]) }
-        if (KIND == 1 || KIND == 3 || KIND == 5 || KIND == 6)
+        if (KIND == 1 || KIND == 3 || KIND == 5 || KIND == 6 || KIND == 7)
         {   // keep FAST-mode values bounded the way a real kernel does once per 17 stages; here once per 12
 #pragma unroll
             for (int j = 0; j < 8; j++) a[j] = (r & 7) ? a[j] : barrett_lazy4(a[j], P.ratio_hi, P.nq);
@@ -138,5 +177,7 @@ int main()
     run<4>("inverse gs lazy4", d, dp, dt);
     run<5>("FAST exact mulhi + mad.lo nq", d, dp, dt);
     run<6>("FAST approx(asm) + C 64-bit mads", d, dp, dt);
+    run<7>("FAST hand PTX (pack/unpack)", d, dp, dt);
+    run<8>("guarded hand PTX", d, dp, dt);
     return 0;
 }
