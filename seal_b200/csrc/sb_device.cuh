@@ -144,9 +144,8 @@ __device__ __forceinline__ u64 mulmod_barrett(u64 a, u64 b, const PrimeDev &P)
 // 128-bit accumulate: (hi:lo) += a*b
 __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b)
 {
-    u64 pl = a * b, ph = __umul64hi(a, b);
-    lo += pl;
-    hi += ph + (lo < pl);
+    // one carry chain instead of a compare + select per accumulate
+    asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(a), "l"(b));
 }
 
 // Harvey-style butterflies on lazily reduced values.

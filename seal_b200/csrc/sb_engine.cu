@@ -12,6 +12,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef SB_MAC_MIN_BLOCKS
+#define SB_MAC_MIN_BLOCKS 2 // CTAs per SM the fused key-switch kernel is register-tuned for
+#endif
+
 namespace sb
 {
     void cuda_check(cudaError_t e, const char *what)
@@ -450,7 +454,7 @@ namespace sb
     //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
     //     blocks.  blockIdx.x = b + B * block_group: consecutive CTAs share the key tile of (I, block group) through L2.
     template <bool FAST>
-    __global__ void __launch_bounds__(256, 3) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
+    __global__ void __launch_bounds__(256, SB_MAC_MIN_BLOCKS) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
                                                                    u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
                                                                    int B)
     {
