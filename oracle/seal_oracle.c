@@ -554,15 +554,15 @@ typedef struct
     size_t nB, nBsk;
     u64 B[ORC_MAX_PRIMES + 1], msk, Bsk[ORC_MAX_PRIMES + 2];
 } behz_base;
-static int behz_base_init(const orc_ctx *c, size_t L, behz_base *b)
+/* rns.cpp:598-641; works for ANY pairwise-coprime base q (the reference's RNSTool KATs use q = {3}, {3,5}) */
+static int behz_base_init_raw(size_t n, const u64 *q, size_t L, u64 t, behz_base *b)
 {
-    /* rns.cpp:598-641 */
     b->nB = L;
-    if (32 + bit_count(c->t) + prod_bit_count(c->q, L) >= 61 * (int)L + 61)
+    if (32 + bit_count(t) + prod_bit_count(q, L) >= 61 * (int)L + 61)
         b->nB++;
     b->nBsk = b->nB + 1;
     u64 primes[ORC_MAX_PRIMES + 4];
-    if (orc_get_primes(2 * (u64)c->n, 61, b->nBsk + 1, primes))
+    if (orc_get_primes(2 * (u64)n, 61, b->nBsk + 1, primes))
         return -1;
     b->msk = primes[0]; /* primes[1] = gamma (decryption only) */
     for (size_t i = 0; i < b->nB; i++)
@@ -570,14 +570,16 @@ static int behz_base_init(const orc_ctx *c, size_t L, behz_base *b)
     b->Bsk[b->nB] = b->msk;
     return 0;
 }
-size_t orc_base_bsk(const orc_ctx *c, size_t L, u64 *out)
+static int behz_base_init(const orc_ctx *c, size_t L, behz_base *b) { return behz_base_init_raw(c->n, c->q, L, c->t, b); }
+size_t orc_behz_base(size_t n, const u64 *q, size_t L, u64 t, u64 *out)
 {
     behz_base b;
-    if (behz_base_init(c, L, &b))
+    if (behz_base_init_raw(n, q, L, t, &b))
         return 0;
     memcpy(out, b.Bsk, b.nBsk * sizeof(u64));
     return b.nBsk;
 }
+size_t orc_base_bsk(const orc_ctx *c, size_t L, u64 *out) { return orc_behz_base(c->n, c->q, L, c->t, out); }
 /* prod_{j != skip} base[j] mod p  (skip = (size_t)-1 for the full product) */
 static u64 prod_mod(const u64 *base, size_t nb, size_t skip, u64 p)
 {
@@ -593,6 +595,7 @@ static void fastbconv(const u64 *ibase, size_t ni, const u64 *x, size_t xstride,
     u64 inv[ORC_MAX_PRIMES + 2], mat[ORC_MAX_PRIMES + 2];
     for (size_t i = 0; i < ni; i++)
     {
+        inv[i] = 0;
         invmod(prod_mod(ibase, ni, i, ibase[i]), ibase[i], &inv[i]);
         mat[i] = prod_mod(ibase, ni, i, p);
     }
@@ -607,6 +610,115 @@ static void fastbconv(const u64 *ibase, size_t ni, const u64 *x, size_t xstride,
         out[j] = (u64)s;
     }
 }
+/* BaseConverter::fast_convert_array (rns.cpp:418-463): in [ni][n] -> out [no][n] */
+void orc_fastbconv_array(const u64 *ibase, size_t ni, const u64 *obase, size_t no, const u64 *in, size_t n, u64 *out)
+{
+    for (size_t s = 0; s < no; s++)
+        fastbconv(ibase, ni, in, n, n, obase[s], out + s * n);
+}
+#define ORC_MT ((u64)1 << 32) /* m_tilde, rns.cpp:635 */
+/* RNSTool::fastbconv_m_tilde (rns.cpp:1086-1131): in [L][n] (base q) -> out [nBsk+1][n] (base Bsk U {m_tilde}) */
+int orc_behz_fastbconv_m_tilde(size_t n, const u64 *q, size_t L, u64 t, const u64 *in, u64 *out)
+{
+    behz_base bb;
+    if (behz_base_init_raw(n, q, L, t, &bb))
+        return -1;
+    u64 *tmp = (u64 *)malloc(L * n * sizeof(u64));
+    for (size_t i = 0; i < L; i++)
+        for (size_t j = 0; j < n; j++)
+            tmp[i * n + j] = mulmod(in[i * n + j] % q[i], ORC_MT % q[i], q[i]); /* :1123-1124 */
+    for (size_t s = 0; s < bb.nBsk; s++)
+        fastbconv(q, L, tmp, n, n, bb.Bsk[s], out + s * n); /* :1127 */
+    fastbconv(q, L, tmp, n, n, ORC_MT, out + bb.nBsk * n);  /* :1130 */
+    free(tmp);
+    return 0;
+}
+/* RNSTool::sm_mrq (rns.cpp:979-1039): in [nBsk+1][n] -> out [nBsk][n] */
+int orc_behz_sm_mrq(size_t n, const u64 *q, size_t L, u64 t, const u64 *in, u64 *out)
+{
+    behz_base bb;
+    if (behz_base_init_raw(n, q, L, t, &bb))
+        return -1;
+    u64 qinv_mt = 0;
+    invmod(prod_mod(q, L, (size_t)-1, ORC_MT), ORC_MT, &qinv_mt);
+    u64 neg_inv_q_mt = (ORC_MT - qinv_mt) % ORC_MT; /* rns.cpp:724-730 */
+    const u64 *ymt = in + bb.nBsk * n;
+    for (size_t s = 0; s < bb.nBsk; s++)
+    {
+        u64 P = bb.Bsk[s], inv_mt = 0, qmodP = prod_mod(q, L, (size_t)-1, P);
+        invmod(ORC_MT % P, P, &inv_mt);
+        for (size_t j = 0; j < n; j++)
+        {
+            u64 r = (u64)(((u128)(ymt[j] % ORC_MT) * neg_inv_q_mt) % ORC_MT);
+            if (r >= (ORC_MT >> 1)) /* :1028 */
+                r += P - ORC_MT;
+            out[s * n + j] = mulmod(addmod(mulmod(r, qmodP, P), in[s * n + j] % P, P), inv_mt, P);
+        }
+    }
+    return 0;
+}
+/* RNSTool::fast_floor (rns.cpp:1041-1084): in [L + nBsk][n] (base q then Bsk) -> out [nBsk][n] */
+int orc_behz_fast_floor(size_t n, const u64 *q, size_t L, u64 t, const u64 *in, u64 *out)
+{
+    behz_base bb;
+    if (behz_base_init_raw(n, q, L, t, &bb))
+        return -1;
+    u64 *conv = (u64 *)malloc(n * sizeof(u64));
+    for (size_t s = 0; s < bb.nBsk; s++)
+    {
+        u64 P = bb.Bsk[s], invq = 0;
+        invmod(prod_mod(q, L, (size_t)-1, P), P, &invq);
+        fastbconv(q, L, in, n, n, P, conv);
+        for (size_t j = 0; j < n; j++)
+            out[s * n + j] = mulmod(submod(in[(L + s) * n + j], conv[j], P), invq, P);
+    }
+    free(conv);
+    return 0;
+}
+/* RNSTool::fastbconv_sk (rns.cpp:903-977): in [nBsk][n] -> out [L][n] */
+int orc_behz_fastbconv_sk(size_t n, const u64 *q, size_t L, u64 t, const u64 *in, u64 *out)
+{
+    behz_base bb;
+    if (behz_base_init_raw(n, q, L, t, &bb))
+        return -1;
+    size_t nB = bb.nB;
+    u64 *conv = (u64 *)malloc(n * sizeof(u64)), *alpha = (u64 *)malloc(n * sizeof(u64));
+    u64 invB = 0;
+    invmod(prod_mod(bb.B, nB, (size_t)-1, bb.msk), bb.msk, &invB);
+    fastbconv(bb.B, nB, in, n, n, bb.msk, conv);
+    for (size_t j = 0; j < n; j++)
+        alpha[j] = mulmod(submod(conv[j], in[nB * n + j], bb.msk), invB, bb.msk); /* :946-949 */
+    for (size_t i = 0; i < L; i++)
+    {
+        u64 qi = q[i], prodB = prod_mod(bb.B, nB, (size_t)-1, qi);
+        u64 *dst = out + i * n;
+        fastbconv(bb.B, nB, in, n, n, qi, dst);
+        for (size_t j = 0; j < n; j++)
+        {
+            if (alpha[j] > (bb.msk >> 1)) /* :964 */
+                dst[j] = addmod(dst[j], mulmod((bb.msk - alpha[j]) % qi, prodB, qi), qi);
+            else
+                dst[j] = addmod(dst[j], mulmod(alpha[j] % qi, (qi - prodB) % qi, qi), qi);
+        }
+    }
+    free(conv), free(alpha);
+    return 0;
+}
+/* RNSTool::divide_and_round_q_last_inplace (rns.cpp:789-828): data [L][n]; the first L-1 rows receive the result */
+void orc_divide_and_round_q_last(const u64 *q, size_t L, size_t n, u64 *data)
+{
+    u64 ql = q[L - 1], half = ql >> 1;
+    u64 *last = data + (L - 1) * n;
+    for (size_t j = 0; j < n; j++)
+        last[j] = addmod(last[j], half, ql);
+    for (size_t i = 0; i + 1 < L; i++)
+    {
+        u64 qi = q[i], inv = 0;
+        invmod(ql % qi, qi, &inv);
+        for (size_t j = 0; j < n; j++)
+            data[i * n + j] = mulmod(submod(data[i * n + j], submod(last[j] % qi, half % qi, qi), qi), inv, qi);
+    }
+}
 
 int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64 *out3)
 {
@@ -614,18 +726,14 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
     behz_base bb;
     if (c->scheme != ORC_BFV || behz_base_init(c, L, &bb))
         return -1;
-    size_t nB = bb.nB, nS = bb.nBsk;
-    const u64 mt = (u64)1 << 32; /* m_tilde, rns.cpp:635 */
+    size_t nS = bb.nBsk;
     orc_tab *stab = (orc_tab *)calloc(nS, sizeof(orc_tab));
     for (size_t i = 0; i < nS; i++)
         if (tab_init(&stab[i], n, bb.Bsk[i]))
             return -1;
     /* steps (1)-(3), evaluator.cpp:456-474, for the 4 input polys: [0,1] of a then [0,1] of b */
     u64 *xq = (u64 *)malloc(4 * L * n * sizeof(u64)), *xs = (u64 *)malloc(4 * nS * n * sizeof(u64));
-    u64 *tmp = (u64 *)malloc(L * n * sizeof(u64)), *ymt = (u64 *)malloc(n * sizeof(u64));
-    u64 qinv_mt = 0;
-    invmod(prod_mod(c->q, L, (size_t)-1, mt), mt, &qinv_mt);
-    u64 neg_inv_q_mt = (mt - qinv_mt) % mt; /* rns.cpp:724-730 */
+    u64 *lift = (u64 *)malloc((nS + 1) * n * sizeof(u64));
     for (size_t p = 0; p < 4; p++)
     {
         const u64 *src = (p < 2 ? a : b) + (p & 1) * L * n;
@@ -633,25 +741,11 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
         {
             memcpy(xq + (p * L + i) * n, src + i * n, n * sizeof(u64));
             ntt_fwd(&c->tab[i], n, xq + (p * L + i) * n);
-            for (size_t j = 0; j < n; j++)
-                tmp[i * n + j] = mulmod(src[i * n + j], mt % c->q[i], c->q[i]); /* rns.cpp:1123-1124 */
         }
-        fastbconv(c->q, L, tmp, n, n, mt, ymt); /* rns.cpp:1130 */
+        orc_behz_fastbconv_m_tilde(n, c->q, L, c->t, src, lift);
+        orc_behz_sm_mrq(n, c->q, L, c->t, lift, xs + p * nS * n);
         for (size_t s = 0; s < nS; s++)
-        {
-            u64 P = bb.Bsk[s], inv_mt = 0, qmodP = prod_mod(c->q, L, (size_t)-1, P);
-            invmod(mt % P, P, &inv_mt);
-            u64 *dst = xs + (p * nS + s) * n;
-            fastbconv(c->q, L, tmp, n, n, P, dst); /* rns.cpp:1127 */
-            for (size_t j = 0; j < n; j++)        /* sm_mrq, rns.cpp:1015-1037 */
-            {
-                u64 r = (u64)(((u128)ymt[j] * neg_inv_q_mt) % mt);
-                if (r >= (mt >> 1))
-                    r += P - mt;
-                dst[j] = mulmod(addmod(mulmod(r, qmodP, P), dst[j], P), inv_mt, P);
-            }
-            ntt_fwd(&stab[s], n, dst);
-        }
+            ntt_fwd(&stab[s], n, xs + (p * nS + s) * n);
     }
     /* step (4) tensor, :497-541; (5) INTT :545-546; (6) times t :554-556 */
     u64 *dq = (u64 *)malloc(3 * L * n * sizeof(u64)), *ds = (u64 *)malloc(3 * nS * n * sizeof(u64));
@@ -680,37 +774,15 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
         }
     }
     /* steps (7) fast_floor rns.cpp:1041-1084 and (8) fastbconv_sk rns.cpp:903-977 */
-    u64 *f = (u64 *)malloc(nS * n * sizeof(u64)), *conv = (u64 *)malloc(n * sizeof(u64)), *alpha = (u64 *)malloc(n * sizeof(u64));
+    u64 *qs = (u64 *)malloc((L + nS) * n * sizeof(u64)), *f = (u64 *)malloc(nS * n * sizeof(u64));
     for (size_t p = 0; p < 3; p++)
     {
-        for (size_t s = 0; s < nS; s++)
-        {
-            u64 P = bb.Bsk[s], invq = 0;
-            invmod(prod_mod(c->q, L, (size_t)-1, P), P, &invq);
-            fastbconv(c->q, L, dq + p * L * n, n, n, P, conv);
-            for (size_t j = 0; j < n; j++)
-                f[s * n + j] = mulmod(submod(ds[(p * nS + s) * n + j], conv[j], P), invq, P);
-        }
-        u64 invB = 0;
-        invmod(prod_mod(bb.B, nB, (size_t)-1, bb.msk), bb.msk, &invB);
-        fastbconv(bb.B, nB, f, n, n, bb.msk, conv);
-        for (size_t j = 0; j < n; j++)
-            alpha[j] = mulmod(submod(conv[j], f[nB * n + j], bb.msk), invB, bb.msk); /* :946-949 */
-        for (size_t i = 0; i < L; i++)
-        {
-            u64 q = c->q[i], prodB = prod_mod(bb.B, nB, (size_t)-1, q);
-            u64 *dst = out3 + (p * L + i) * n;
-            fastbconv(bb.B, nB, f, n, n, q, dst);
-            for (size_t j = 0; j < n; j++)
-            {
-                if (alpha[j] > (bb.msk >> 1)) /* :964 */
-                    dst[j] = addmod(dst[j], mulmod((bb.msk - alpha[j]) % q, prodB, q), q);
-                else
-                    dst[j] = addmod(dst[j], mulmod(alpha[j] % q, q - prodB, q), q);
-            }
-        }
+        memcpy(qs, dq + p * L * n, L * n * sizeof(u64));
+        memcpy(qs + L * n, ds + p * nS * n, nS * n * sizeof(u64));
+        orc_behz_fast_floor(n, c->q, L, c->t, qs, f);
+        orc_behz_fastbconv_sk(n, c->q, L, c->t, f, out3 + p * L * n);
     }
-    free(f), free(conv), free(alpha), free(dq), free(ds), free(xq), free(xs), free(tmp), free(ymt);
+    free(qs), free(f), free(dq), free(ds), free(xq), free(xs), free(lift);
     for (size_t i = 0; i < nS; i++)
         tab_free(&stab[i]);
     free(stab);

@@ -5,8 +5,10 @@
  * WHAT the reference computes.  Every function cites the reference file:line it follows (paths relative to
  * /root/reference/native/src/seal/).
  *
- * PINNING: tests/test_oracle_*.py check this file against (i) the reference's in-source known-answer tests
- * (tests/seal/util/ntt.cpp:53-100, tests/seal/util/galois.cpp:86-120), (ii) golden vectors generated from the real
+ * PINNING: tests/test_oracle*.py check this file against (i) the reference's in-source known-answer tests
+ * (tests/seal/util/ntt.cpp:53-133, tests/seal/util/galois.cpp:28-120, tests/seal/util/rns.cpp:347-438 BaseConverter,
+ * :460-853 FastBConvMTilde / MontgomeryReduction / FastFloor / FastBConvSK, :904-1011 DivideAndRoundQLastInplace),
+ * (ii) golden vectors generated from the real
  * reference in the build container (tests/golden/, generator tests/golden/make_golden.py) and (iii) live outputs of
  * oracle/_ref/libsealref.so (the reference compiled from its own sources) wherever that library is present.
  *
@@ -39,6 +41,15 @@ void orc_destroy(orc_ctx *c);
 int orc_ntt_tables(const orc_ctx *c, size_t i, uint64_t *root, uint64_t *root_powers, uint64_t *inv_root_powers, uint64_t *inv_n);
 /* BEHZ auxiliary base at level L: [B..., m_sk]; returns |Bsk| (rns.cpp:598-641) */
 size_t orc_base_bsk(const orc_ctx *c, size_t L, uint64_t *out);
+
+/* RNS base conversion building blocks with explicit bases (so the reference's tiny-base KATs can be replayed) */
+void orc_fastbconv_array(const uint64_t *ibase, size_t ni, const uint64_t *obase, size_t no, const uint64_t *in, size_t n, uint64_t *out); /* rns.cpp:418-463 */
+size_t orc_behz_base(size_t n, const uint64_t *q, size_t L, uint64_t t, uint64_t *bsk_out);                      /* rns.cpp:598-641 */
+int orc_behz_fastbconv_m_tilde(size_t n, const uint64_t *q, size_t L, uint64_t t, const uint64_t *in, uint64_t *out); /* rns.cpp:1086-1131 */
+int orc_behz_sm_mrq(size_t n, const uint64_t *q, size_t L, uint64_t t, const uint64_t *in, uint64_t *out);      /* rns.cpp:979-1039 */
+int orc_behz_fast_floor(size_t n, const uint64_t *q, size_t L, uint64_t t, const uint64_t *in, uint64_t *out);  /* rns.cpp:1041-1084 */
+int orc_behz_fastbconv_sk(size_t n, const uint64_t *q, size_t L, uint64_t t, const uint64_t *in, uint64_t *out); /* rns.cpp:903-977 */
+void orc_divide_and_round_q_last(const uint64_t *q, size_t L, size_t n, uint64_t *data);                        /* rns.cpp:789-828 */
 
 /* single-row transforms with explicit modulus index (ntt.cpp:394-475 / dwthandler.h:94-356); canonical outputs */
 void orc_ntt_row(const orc_ctx *c, size_t prime_idx, uint64_t *row);

@@ -170,3 +170,63 @@ class Oracle:
         out = np.zeros((2, L, self.n), dtype=np.uint64)
         lib().orc_apply_galois(self.h, L, _p(c2), elt, _p(key), _p(out))
         return out
+
+
+# ---- standalone RNS building blocks (explicit bases) ----
+def _setup_rns():
+    L = lib()
+    L.orc_fastbconv_array.argtypes = [_u64p, C.c_size_t, _u64p, C.c_size_t, _u64p, C.c_size_t, _u64p]
+    L.orc_behz_base.restype = C.c_size_t
+    L.orc_behz_base.argtypes = [C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _u64p]
+    for f in (L.orc_behz_fastbconv_m_tilde, L.orc_behz_sm_mrq, L.orc_behz_fast_floor, L.orc_behz_fastbconv_sk):
+        f.argtypes = [C.c_size_t, _u64p, C.c_size_t, C.c_uint64, _u64p, _u64p]
+    L.orc_divide_and_round_q_last.argtypes = [_u64p, C.c_size_t, C.c_size_t, _u64p]
+    return L
+
+
+def fastbconv_array(ibase, obase, x):
+    """BaseConverter::fast_convert_array: x [ni][n] -> [no][n]"""
+    L = _setup_rns()
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    n = x.shape[1]
+    out = np.zeros((len(obase), n), dtype=np.uint64)
+    L.orc_fastbconv_array(_p(np.array(ibase, dtype=np.uint64)), len(ibase), _p(np.array(obase, dtype=np.uint64)), len(obase), _p(x), n, _p(out))
+    return out
+
+
+def behz_base(n, q, t=0):
+    L = _setup_rns()
+    out = np.zeros(len(q) + 4, dtype=np.uint64)
+    cnt = L.orc_behz_base(n, _p(np.array(q, dtype=np.uint64)), len(q), t, _p(out))
+    return [int(v) for v in out[:cnt]]
+
+
+def _behz(fn, n, q, t, x, rows_out):
+    L = _setup_rns()
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.zeros((rows_out, n), dtype=np.uint64)
+    assert getattr(L, fn)(n, _p(np.array(q, dtype=np.uint64)), len(q), t, _p(x), _p(out)) == 0
+    return out
+
+
+def behz_fastbconv_m_tilde(n, q, x, t=0):
+    return _behz("orc_behz_fastbconv_m_tilde", n, q, t, x, len(behz_base(n, q, t)) + 1)
+
+
+def behz_sm_mrq(n, q, x, t=0):
+    return _behz("orc_behz_sm_mrq", n, q, t, x, len(behz_base(n, q, t)))
+
+
+def behz_fast_floor(n, q, x, t=0):
+    return _behz("orc_behz_fast_floor", n, q, t, x, len(behz_base(n, q, t)))
+
+
+def behz_fastbconv_sk(n, q, x, t=0):
+    return _behz("orc_behz_fastbconv_sk", n, q, t, x, len(q))
+
+
+def divide_and_round_q_last(q, x):
+    L = _setup_rns()
+    x = np.ascontiguousarray(x, dtype=np.uint64).copy()
+    L.orc_divide_and_round_q_last(_p(np.array(q, dtype=np.uint64)), len(q), x.shape[1], _p(x))
+    return x[:-1]
