@@ -228,6 +228,24 @@ def main():
     torch.cuda.synchronize()
     assert rank != 0 or digests.numel() == B * world
 
+    # ---- second headline metric: NTT GB/s vs the HBM roofline (Evaluator::transform_from_ntt_inplace + transform_to_ntt_inplace
+    #      over the whole input slab, the reference bench's NTTForward/NTTInverse cases; 2*n*8 algorithmic bytes per row per transform)
+    ntt_rows = B * 2 * L
+    nb = min(B, 64)
+    ntt_rows = nb * 2 * L
+    ctx.d_ntt_inverse(a, L, 2, nb)
+    ctx.d_ntt_forward(a, L, 2, nb)
+    torch.cuda.synchronize()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(args.steps):
+        ctx.d_ntt_inverse(a, L, 2, nb)
+        ctx.d_ntt_forward(a, L, 2, nb)  # restores the slab exactly (checked by the parity tests)
+    n1.record()
+    torch.cuda.synchronize()
+    ntt_ms = n0.elapsed_time(n1) / (2 * args.steps)
+    ntt_gbps = ntt_rows * 2 * n * 8 / (ntt_ms * 1e-3) / 1e9
+
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -301,6 +319,8 @@ def main():
                    "l2": f"inputs {2 * a.numel() * 8 / 2**30:.1f} GiB per GPU >> 126 MB L2 (no flush needed)",
                    "parallelism": f"batch sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "ntt": {"metric": "negacyclic NTT GB/s (2*n*8 B per row per transform)", "rows_per_transform_call": ntt_rows, "n": n,
+                "ms_per_call": ntt_ms, "achieved_GBps": ntt_gbps, "peak_GBps": peak, "frac_of_hbm_peak": ntt_gbps / peak},
         "op_roofline": {"alg_bytes_per_ct": alg_per_ct, "achieved_GBps_per_gpu": op_gbps, "frac_of_hbm_peak": op_gbps / peak},
         "cpu_baseline": cpu,
     }
