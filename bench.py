@@ -54,7 +54,8 @@ def ncu_traffic(kernel):
     """dram bytes per launch of the dominant kernel from the committed ncu capture summary, or None"""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            e = json.load(f).get(kernel)
+            return e["dram_bytes_per_launch"] if e else None
     except Exception:
         return None
 
