@@ -237,12 +237,12 @@ namespace sb
         int logn, L;
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int row) const { return row % L; }
-        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const
         {
             const int i = row % L, bp = row / L, p4 = bp & 3, bb = bp >> 2;
-            const u64 *src = (p4 < 2 ? a : b) + (((static_cast<long long>(bb) * 2 + (p4 & 1)) * L + i) << logn);
-            return src[idx];
+            return (p4 < 2 ? a : b) + (((static_cast<long long>(bb) * 2 + (p4 & 1)) * L + i) << logn);
         }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const { return direct(row, P)[idx]; }
         __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
         __device__ __forceinline__ u64 *mid(int row) const { return XQ + (static_cast<long long>(row) << logn); }
         __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const { mid(row)[idx] = csub(csub(v, P.q2), P.q); }
@@ -269,6 +269,7 @@ namespace sb
             return pid_tab ? pid_tab[i] : i;
         }
         __device__ __forceinline__ u64 *rowp(int row) const { return data + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return rowp(row); }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
         __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
         {

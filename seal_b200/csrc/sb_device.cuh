@@ -23,6 +23,7 @@ struct PrimeDev
     u64 q2;         // 2q
     u64 q4;         // 4q
     u64 nq;         // 2^64 - q
+    u64 zero;       // always 0, but not a compile-time constant: see ct_bfly
     u64 ratio_lo;   // floor(2^128 / q), low word
     u64 ratio_hi;   //                   high word (= floor(2^64 / q))
     Tw inv_n;       // n^-1 mod q
@@ -157,7 +158,9 @@ __device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, Tw w, const PrimeDev &P)
 {
     u64 v = mul_shoup_lazy4(y, w, P.nq);
     u64 u = FAST ? x : csub(x, P.q4);
-    x = u + v;
+    // three-operand form: keeps the 64-bit adds on the integer ALU (IADD3/IADD3.X); the two-operand form is scheduled by
+    // ptxas onto the multiply pipe (IMAD.X), which is the pipe that limits these kernels
+    x = u + v + P.zero;
     y = u - v + P.q4;
 }
 // inverse (Gentleman-Sande): inputs in [0,4q) -> outputs in [0,4q)

@@ -103,6 +103,7 @@ namespace sb
         d.q2 = 2 * pt.q;
         d.q4 = 4 * pt.q;
         d.nq = 0ull - pt.q;
+        d.zero = 0;
         d.ratio_lo = pt.ratio_lo;
         d.ratio_hi = pt.ratio_hi;
         d.inv_n = to_tw(pt.inv_n);
@@ -208,6 +209,8 @@ namespace sb
         uint32_t ginv = 0;              // coefficient form: inverse Galois element mod 2n (0 = identity)
         int logn = 0;
 
+        __device__ __forceinline__ bool plain() const { return perm == nullptr && ginv == 0; }
+        __device__ __forceinline__ const u64 *row(int b, int J) const { return p + b * bstride + (static_cast<long long>(J) << logn); }
         __device__ __forceinline__ u64 get(int b, int J, int idx, u64 qJ) const
         {
             const u64 *r = p + b * bstride + (static_cast<long long>(J) << logn);
@@ -246,6 +249,7 @@ namespace sb
             return pid_tab ? pid_tab[i] : i;
         }
         __device__ __forceinline__ u64 *rowp(int row) const { return data + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return rowp(row); }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
         __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
         {
@@ -368,12 +372,24 @@ namespace sb
         int logn, L;
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int row) const { return row % L; }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return tgt.plain() ? tgt.row(row / L, row % L) : nullptr; }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
         {
             return tgt.get(row / L, row % L, idx, P.q);
         }
         __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
         {
+            if (tgt.plain())
+            {
+                const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(tgt.row(row / L, row % L) + idx0);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    ulonglong2 v = p[j];
+                    a[2 * j] = v.x, a[2 * j + 1] = v.y;
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++)
                 a[j] = load1(row, idx0 + j, P);
@@ -400,6 +416,13 @@ namespace sb
         {
             int I = (row / L) % (L + 1);
             return I == L ? k - 1 : I;
+        }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &P) const
+        {
+            const int J = row % L;
+            if (!dsrc.plain() || (reduce && primes[J].q > P.q))
+                return nullptr;
+            return dsrc.row(row / (L * (L + 1)), J);
         }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
         {
@@ -482,9 +505,22 @@ namespace sb
             if (ntt_in && J == I)
             {
                 // the input already is digit J in NTT form modulo q_J (evaluator.cpp:2682-2685)
+                if (tgt.plain())
+                {
+                    const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tgt.row(b, J) + e0);
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    a[j] = tgt.get(b, J, e0 + j, P.q);
+                    for (int h = 0; h < 4; h++)
+                    {
+                        ulonglong2 v = tp[h];
+                        a[2 * h] = v.x, a[2 * h + 1] = v.y;
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        a[j] = tgt.get(b, J, e0 + j, P.q);
+                }
             }
             else
             {
@@ -543,6 +579,7 @@ namespace sb
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int) const { return pid_top; }
         __device__ __forceinline__ const u64 *rowp(int row) const { return src + (row >> 1) * bstride + (row & 1) * pstride; }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return rowp(row); }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
         __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
         {
@@ -578,6 +615,7 @@ namespace sb
         {
             return Pp + ((static_cast<long long>(row / L) * (L + 1) + row % L) << logn);
         }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return rowp(row); }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
         __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
         {
@@ -629,6 +667,7 @@ namespace sb
         int logn, Lout;
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int row) const { return row % Lout; }
+        __device__ __forceinline__ const u64 *direct(int, const PrimeDev &) const { return nullptr; }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
         {
             u64 u = U[(static_cast<long long>(row / Lout) << logn) + idx];

@@ -21,6 +21,7 @@
 //   bool skip(int row)                       row needs no transform (CTA exits)
 //   int  pid(int row)                        prime id of the row
 //   u64  load1(int row, int idx, P)          value of coefficient idx  (forward: < 4q, inverse: < 4q)
+//   const u64 *direct(int row, P)            non-null when load1(row, idx) == direct(row)[idx] (plain row, no prologue)
 //   void load8(int row, int idx0, u64(&)[8], P)   8 consecutive coefficients
 //   u64 *mid(int row)                        n-word intermediate row between the two passes
 //   void store1(int row, int idx, u64 v, P)  v lazily reduced (forward: < 4q, inverse: < 2q)
@@ -142,9 +143,20 @@ namespace sb
         u64 a[8];
         {
             constexpr int g = NA >> 3; // first layout: r = ridx + j*g
+            const u64 *dp = op.direct(row, P); // non-null: the row is a plain array in range, no prologue needed
+            if (dp)
+            {
+                dp += (ridx << kLocalLog) + col0 + c;
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                a[j] = op.load1(row, ((ridx + j * g) << kLocalLog) + col0 + c, P);
+                for (int j = 0; j < 8; j++)
+                    a[j] = dp[(j * g) << kLocalLog];
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = op.load1(row, ((ridx + j * g) << kLocalLog) + col0 + c, P);
+            }
         }
         mbar_wait(&bar, 0);
 
