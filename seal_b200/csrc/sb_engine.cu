@@ -481,16 +481,32 @@ namespace sb
                                                                    u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
                                                                    int B)
     {
-        __shared__ __align__(16) u64 xs[8][256];
-        // 128-bit sums of key component 1 live in shared memory ([j][thread], conflict-free 16-byte accesses) so that the
-        // register file holds three CTAs per SM; component 0 stays in registers
-        __shared__ __align__(16) ulonglong2 acc1[8][256];
+        // dynamic shared memory: [xs 8x256 u64 | acc1 8x256 x 16 B | twiddles 8*255 x 16 B | mbarrier]
+        extern __shared__ __align__(16) unsigned char ks_smem[];
+        u64(*xs)[256] = reinterpret_cast<u64(*)[256]>(ks_smem);
+        // 128-bit sums of key component 1 live in shared memory ([j][thread], conflict-free 16-byte accesses); component 0
+        // stays in registers
+        ulonglong2(*acc1)[256] = reinterpret_cast<ulonglong2(*)[256]>(ks_smem + 8 * 256 * sizeof(u64));
+        // the twiddles of this CTA's 8 blocks are the same for every digit J: staged once with 8 TMA bulk copies
+        // (stage s of 8 adjacent blocks is one contiguous run of 8*2^s table entries)
+        Tw *tws = reinterpret_cast<Tw *>(ks_smem + 8 * 256 * (sizeof(u64) + sizeof(ulonglong2)));
+        u64 *bar = reinterpret_cast<u64 *>(tws + 8 * 255 + 1);
         const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         const int b = blockIdx.x % B, bg = blockIdx.x / B, I = blockIdx.y;
         const int na = 1 << (logn - kLocalLog), blk = bg * 8 + warp;
         const int ki = (I == L) ? k - 1 : I;
         const PrimeDev P = primes[ki];
         const int e0 = (blk << kLocalLog) + 8 * l; // first of this lane's 8 consecutive output coefficients
+        if (threadIdx.x == 0)
+            mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            mbar_expect_tx(bar, 8 * 255 * sizeof(Tw));
+#pragma unroll
+            for (int st = 0; st < 8; st++)
+                tma_load_1d(tws + 8 * ((1 << st) - 1), P.fwd + ((na + bg * 8) << st), (8u << st) * sizeof(Tw), bar);
+        }
         u64 s0l[8], s0h[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -498,6 +514,8 @@ namespace sb
             s0l[j] = s0h[j] = 0;
             acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
         }
+        mbar_wait(bar, 0);
+        auto twf = [&](int st, int i) { return tws[8 * ((1 << st) - 1) + (warp << st) + i]; };
         const u64 *erow = E + ((static_cast<long long>(b) * (L + 1) + I) * L << logn) + (blk << kLocalLog);
         for (int J = 0; J < L; J++)
         {
@@ -528,7 +546,7 @@ namespace sb
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     a[j] = src[l + 32 * j];
-                fwd_local_block<FAST>(a, xs[warp], P.fwd, na + blk, l, P);
+                fwd_local_block_tw<FAST>(a, xs[warp], twf, l, P);
                 if (!FAST)
                 {
 #pragma unroll
@@ -798,12 +816,16 @@ namespace sb
         {
             const int na = n >> kLocalLog;
             dim3 grid(static_cast<unsigned>(B * (na / 8)), static_cast<unsigned>(L + 1));
+            constexpr size_t smem = 8 * 256 * (sizeof(u64) + sizeof(ulonglong2)) + (8 * 255 + 1) * sizeof(Tw) + 16;
+            cuda_check(cudaFuncSetAttribute(c.fast_q ? ks_local_mac_kernel<true> : ks_local_mac_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                       "smem attr");
             c.stats.begin("ks_local_mac", 0, mac_bytes, st);
             if (c.fast_q)
-                ks_local_mac_kernel<true><<<grid, 256, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
+                ks_local_mac_kernel<true><<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
                                                                 static_cast<int>(B));
             else
-                ks_local_mac_kernel<false><<<grid, 256, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
+                ks_local_mac_kernel<false><<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
                                                                  static_cast<int>(B));
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_local_mac_kernel");

@@ -201,12 +201,13 @@ namespace sb
     // The 8 stages inside one 256-coefficient block, executed by one warp.  In: a[j] = coefficient l + 32 j of the
     // block (lane l).  Out: a[j] = coefficient 8 l + j, lazily reduced (FAST: unreduced growth, guarded: < 8q).
     // x = the warp's private 256-word shared slice; t0 = NA + block index (twiddle base of the block).
-    template <bool FAST>
-    __device__ __forceinline__ void fwd_local_block(u64 (&a)[8], u64 *x, const Tw *__restrict__ tw, int t0, int l, const PrimeDev &P)
+    // twf(s, i): twiddle of in-block stage s (0..7), group i of this block (0 <= i < 2^s)
+    template <bool FAST, class TwF>
+    __device__ __forceinline__ void fwd_local_block_tw(u64 (&a)[8], u64 *x, TwF twf, int l, const PrimeDev &P)
     {
         {
-            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << lvl) + k); };
-            fwd_regs<3, FAST>(a, twf, P);
+            auto t = [&](int lvl, int k) { return twf(lvl, k); };
+            fwd_regs<3, FAST>(a, t, P);
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -217,8 +218,8 @@ namespace sb
 #pragma unroll
             for (int j = 0; j < 8; j++)
                 a[j] = x[swz(32 * hi + lo + 4 * j)];
-            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (3 + lvl)) + (hi << lvl) + k); };
-            fwd_regs<3, FAST>(a, twf, P);
+            auto t = [&](int lvl, int k) { return twf(3 + lvl, (hi << lvl) + k); };
+            fwd_regs<3, FAST>(a, t, P);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -231,15 +232,21 @@ namespace sb
         __syncwarp();
         {
             // strides 2 and 1: pairs (j,j+2) then (j,j+1)
-            Tw wa = ldg_tw(tw + (t0 << 6) + 2 * l), wb = ldg_tw(tw + (t0 << 6) + 2 * l + 1);
+            Tw wa = twf(6, 2 * l), wb = twf(6, 2 * l + 1);
             ct_bfly<FAST>(a[0], a[2], wa, P);
             ct_bfly<FAST>(a[1], a[3], wa, P);
             ct_bfly<FAST>(a[4], a[6], wb, P);
             ct_bfly<FAST>(a[5], a[7], wb, P);
 #pragma unroll
             for (int p = 0; p < 4; p++)
-                ct_bfly<FAST>(a[2 * p], a[2 * p + 1], ldg_tw(tw + (t0 << 7) + 4 * l + p), P);
+                ct_bfly<FAST>(a[2 * p], a[2 * p + 1], twf(7, 4 * l + p), P);
         }
+    }
+    template <bool FAST>
+    __device__ __forceinline__ void fwd_local_block(u64 (&a)[8], u64 *x, const Tw *__restrict__ tw, int t0, int l, const PrimeDev &P)
+    {
+        auto twf = [&](int s, int i) { return ldg_tw(tw + (t0 << s) + i); };
+        fwd_local_block_tw<FAST>(a, x, twf, l, P);
     }
 
     template <bool FAST, class Op>
