@@ -88,6 +88,13 @@ int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, u
 /* Evaluator::multiply (evaluator.cpp:352-708), size-2 x size-2 -> size-3; CKKS (NTT form) or BFV (BEHZ) per ctx */
 int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, const uint64_t *d_b,
                    uint64_t *d_out3, void *stream);
+/* Evaluator::square (evaluator.cpp:843-1142): same residues as multiply(a, a), size 2 -> 3 */
+int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, uint64_t *d_out3, void *stream);
+/* Evaluator::add / sub / negate on equal-size operands (evaluator.cpp:130-350), element-wise over [batch][size][L][n];
+ * these are the "next" row of SURVEY 8(f): the linear ops users interleave with multiply / relinearize / rescale */
+int sb200_add(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, void *stream);
+int sb200_sub(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out, void *stream);
+int sb200_negate(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_a, uint64_t *d_out, void *stream);
 /* Evaluator::relinearize_inplace, size 3 -> 2 (evaluator.cpp:1144-1199 + 2561-2867) */
 int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in3,
                       const sb200_kswitch_key *relin_key, uint64_t *d_out2, void *stream);
@@ -107,6 +114,10 @@ int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_
 int sb200_ntt_forward_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
 int sb200_ntt_inverse_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
 int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out3);
+int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, uint64_t *h_out3);
+int sb200_add_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out);
+int sb200_sub_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out);
+int sb200_negate_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, uint64_t *h_out);
 int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in3,
                            const sb200_kswitch_key *relin_key, uint64_t *h_out2);
 int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b,

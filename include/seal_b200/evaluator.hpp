@@ -94,6 +94,59 @@ namespace seal_b200
             }
         }
 
+        // ---- square (evaluator.cpp:843-1142): same residues as multiply(x, x) -------------------------------------------
+        void square_inplace(seal::Ciphertext &encrypted, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            seal::Ciphertext copy = encrypted;
+            multiply_inplace(encrypted, copy, std::move(pool));
+        }
+        void square(const seal::Ciphertext &encrypted, seal::Ciphertext &destination,
+                    seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            square_inplace(destination, std::move(pool));
+        }
+
+        // ---- negate / add / sub (evaluator.cpp:130-350), equal-size operands ------------------------------------------
+        void negate_inplace(seal::Ciphertext &encrypted) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            check(sb200_negate_host(ctx_, encrypted.coeff_modulus_size(), encrypted.size(), 1, encrypted.data(), encrypted.data()));
+            throw_if_transparent(encrypted);
+        }
+        void negate(const seal::Ciphertext &encrypted, seal::Ciphertext &destination) const
+        {
+            destination = encrypted;
+            negate_inplace(destination);
+        }
+        void add_inplace(seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2) const { linear(encrypted1, encrypted2, false); }
+        void add(const seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, seal::Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+            {
+                add_inplace(destination, encrypted1);
+            }
+            else
+            {
+                destination = encrypted1;
+                add_inplace(destination, encrypted2);
+            }
+        }
+        void sub_inplace(seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2) const { linear(encrypted1, encrypted2, true); }
+        void sub(const seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, seal::Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+            {
+                sub_inplace(destination, encrypted1);
+                negate_inplace(destination);
+            }
+            else
+            {
+                destination = encrypted1;
+                sub_inplace(destination, encrypted2);
+            }
+        }
+
         // ---- relinearize (evaluator.cpp:1144-1199) ---------------------------------------------------------------
         void relinearize_inplace(seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys,
                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
@@ -308,6 +361,24 @@ namespace seal_b200
         sb200_context *native_handle() const noexcept { return ctx_; }
 
     private:
+        // evaluator.cpp:154-262 / 264-350 prologue; sizes must match here (the reference also pads the shorter operand)
+        void linear(seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, bool subtract) const
+        {
+            validate(encrypted1, "encrypted1 is not valid for encryption parameters");
+            validate(encrypted2, "encrypted2 is not valid for encryption parameters");
+            if (encrypted1.parms_id() != encrypted2.parms_id())
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            if (encrypted1.is_ntt_form() != encrypted2.is_ntt_form())
+                throw std::invalid_argument("NTT form mismatch");
+            if (!seal::util::are_close<double>(encrypted1.scale(), encrypted2.scale()))
+                throw std::invalid_argument("scale mismatch");
+            if (encrypted1.size() != encrypted2.size())
+                throw std::invalid_argument("seal_b200: add/sub are implemented for equal-size ciphertexts");
+            const std::size_t L = encrypted1.coeff_modulus_size();
+            check(subtract ? sb200_sub_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data())
+                           : sb200_add_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data()));
+            throw_if_transparent(encrypted1);
+        }
         static void check(int status)
         {
             if (status == SB200_OK)

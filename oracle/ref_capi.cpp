@@ -272,6 +272,35 @@ extern "C" int sealref_multiply(sealref_ctx *c, size_t L, const uint64_t *a, con
     REF_CATCH(-1)
 }
 
+extern "C" int sealref_square(sealref_ctx *c, size_t L, const uint64_t *a, uint64_t *out3)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, 2, a);
+    c->evaluator->square_inplace(x);
+    store_ct(c, x, out3);
+    return 0;
+    REF_CATCH(-1)
+}
+
+extern "C" int sealref_linear(sealref_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, size, a);
+    if (mode == 2)
+        c->evaluator->negate_inplace(x);
+    else
+    {
+        Ciphertext y = make_ct(c, L, size, b);
+        if (mode == 0)
+            c->evaluator->add_inplace(x, y);
+        else
+            c->evaluator->sub_inplace(x, y);
+    }
+    store_ct(c, x, out);
+    return 0;
+    REF_CATCH(-1)
+}
+
 static const RelinKeys &relin_keys(sealref_ctx *c)
 {
     if (!c->relin)

@@ -335,6 +335,20 @@ void orc_ckks_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u
     }
 }
 
+/* add / sub / negate (evaluator.cpp:130-350; polyarithsmallmod.cpp:43-195) */
+void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const u64 *a, const u64 *b, u64 *out)
+{
+    size_t n = c->n;
+    for (size_t p = 0; p < size; p++)
+        for (size_t i = 0; i < L; i++)
+            for (size_t j = 0; j < n; j++)
+            {
+                size_t e = (p * L + i) * n + j;
+                u64 q = c->q[i];
+                out[e] = mode == 0 ? addmod(a[e], b[e], q) : mode == 1 ? submod(a[e], b[e], q) : submod(0, a[e], q);
+            }
+}
+
 /* -------------------------------------------------------------------- key switching (evaluator.cpp:2561-2867) -- */
 void orc_switch_key(const orc_ctx *c, size_t L, u64 *ct, const u64 *target, const u64 *key)
 {

@@ -26,9 +26,9 @@ SYMBOLS = [
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
-    "sb200_ntt_inverse", "sb200_multiply", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
-    "sb200_multiply_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
+    "sb200_multiply_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host",
 ]
 
@@ -64,6 +64,14 @@ def lib():
         L.sb200_ntt_forward.argtypes = [vp, sz, sz, sz, vp, vp]
         L.sb200_ntt_inverse.argtypes = [vp, sz, sz, sz, vp, vp]
         L.sb200_multiply.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+        L.sb200_square.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.sb200_add.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
+        L.sb200_sub.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
+        L.sb200_negate.argtypes = [vp, sz, sz, sz, vp, vp, vp]
+        L.sb200_square_host.argtypes = [vp, sz, sz, _u64p, _u64p]
+        L.sb200_add_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
+        L.sb200_sub_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
+        L.sb200_negate_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p]
         L.sb200_relinearize.argtypes = [vp, sz, sz, vp, vp, vp, vp]
         L.sb200_multiply_relinearize.argtypes = [vp, sz, sz, vp, vp, vp, vp, vp]
         L.sb200_rescale_to_next.argtypes = [vp, sz, sz, vp, vp, vp]
@@ -221,6 +229,34 @@ class Context:
         out = np.zeros((B, 3, L, n), dtype=np.uint64)
         _check(lib().sb200_multiply_host(self.h, L, B, _hp(a), _hp(b), _hp(out)))
         return out[0] if single else out
+
+    def square(self, a):
+        a, single = self._batched(a)
+        B, _, L, n = a.shape
+        out = np.zeros((B, 3, L, n), dtype=np.uint64)
+        _check(lib().sb200_square_host(self.h, L, B, _hp(a), _hp(out)))
+        return out[0] if single else out
+
+    def _linear(self, fn, a, b=None):
+        a, single = self._batched(a)
+        B, size, L, n = a.shape
+        out = np.zeros_like(a)
+        if b is None:
+            _check(fn(self.h, L, size, B, _hp(a), _hp(out)))
+        else:
+            b, _ = self._batched(b)
+            assert b.shape == a.shape
+            _check(fn(self.h, L, size, B, _hp(a), _hp(b), _hp(out)))
+        return out[0] if single else out
+
+    def add(self, a, b):
+        return self._linear(lib().sb200_add_host, a, b)
+
+    def sub(self, a, b):
+        return self._linear(lib().sb200_sub_host, a, b)
+
+    def negate(self, a):
+        return self._linear(lib().sb200_negate_host, a)
 
     def relinearize(self, c3, key):
         c3, single = self._batched(c3)

@@ -317,6 +317,37 @@ int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a
     SB_CATCH
 }
 
+static int linear_dev(sb200_context *ctx, int mode, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out,
+                      void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(out);
+    if (mode != 2)
+        SB_NEED(b);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_linear(c, mode, L, size, batch, (const u64 *)a, (const u64 *)b, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_add(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out, void *stream)
+{
+    return linear_dev(ctx, 0, L, size, batch, a, b, out, stream);
+}
+int sb200_sub(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out, void *stream)
+{
+    return linear_dev(ctx, 1, L, size, batch, a, b, out, stream);
+}
+int sb200_negate(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, uint64_t *out, void *stream)
+{
+    return linear_dev(ctx, 2, L, size, batch, a, nullptr, out, stream);
+}
+int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3, void *stream)
+{
+    return sb200_multiply(ctx, L, batch, a, a, out3, stream);
+}
+
 int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in3, const sb200_kswitch_key *key, uint64_t *out2,
                       void *stream)
 {
@@ -515,6 +546,38 @@ int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64
     });
     return SB200_OK;
     SB_CATCH
+}
+
+static int linear_host(sb200_context *ctx, int mode, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out)
+{
+    SB_NEED(a);
+    SB_NEED(out);
+    if (mode != 2)
+        SB_NEED(b);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t w = size * L * c.n;
+    HostPipe(c).run(batch, w, mode == 2 ? 0 : w, w, a, b, out,
+                    [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) { op_linear(c, mode, L, size, B, da, db, dout, st); });
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_add_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out)
+{
+    return linear_host(ctx, 0, L, size, batch, a, b, out);
+}
+int sb200_sub_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out)
+{
+    return linear_host(ctx, 1, L, size, batch, a, b, out);
+}
+int sb200_negate_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, uint64_t *out)
+{
+    return linear_host(ctx, 2, L, size, batch, a, nullptr, out);
+}
+int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3)
+{
+    return sb200_multiply_host(ctx, L, batch, a, a, out3);
 }
 
 int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in3, const sb200_kswitch_key *key, uint64_t *out2)

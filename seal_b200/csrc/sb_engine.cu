@@ -363,6 +363,51 @@ namespace sb
         }
     }
 
+    // ---- add / sub / negate (evaluator.cpp:130-350: add_poly_coeffmod / sub_poly_coeffmod / negate_poly_coeffmod) ---------
+    // MODE 0: a + b, 1: a - b, 2: -a; rows of n coefficients, prime of a row = row % L
+    template <int MODE>
+    __global__ void __launch_bounds__(256) linear_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b, ulonglong2 *out,
+                                                          const PrimeDev *__restrict__ primes, int logn, int L, long long total2)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over pairs of coefficients
+        if (e >= total2)
+            return;
+        const u64 q = primes[static_cast<int>(((e * 2) >> logn) % L)].q;
+        ulonglong2 x = a[e], y = MODE == 2 ? make_ulonglong2(0, 0) : b[e], r;
+        if (MODE == 0)
+            r = make_ulonglong2(csub(x.x + y.x, q), csub(x.y + y.y, q));
+        else if (MODE == 1)
+            r = make_ulonglong2(csub(x.x + q - y.x, q), csub(x.y + q - y.y, q));
+        else
+            r = make_ulonglong2(x.x ? q - x.x : 0, x.y ? q - x.y : 0);
+        out[e] = r;
+    }
+
+    void op_linear(Context &c, int mode, size_t L, size_t size, size_t batch, const u64 *a, const u64 *b, u64 *out, cudaStream_t st)
+    {
+        if (c.n < 2 || size < 1)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        const size_t per = size * L * c.n, step = std::max<size_t>(1, (size_t(1) << 32) / per);
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t nb = std::min(step, batch - b0);
+            const long long total2 = static_cast<long long>(nb * per / 2);
+            const unsigned blocks = static_cast<unsigned>((total2 + 255) / 256);
+            auto pa = reinterpret_cast<const ulonglong2 *>(a + b0 * per);
+            auto pb = reinterpret_cast<const ulonglong2 *>(b ? b + b0 * per : nullptr);
+            auto po = reinterpret_cast<ulonglong2 *>(out + b0 * per);
+            c.stats.begin(mode == 0 ? "add" : mode == 1 ? "sub" : "negate", 0, (mode == 2 ? 16.0 : 24.0) * total2 * 2, st);
+            if (mode == 0)
+                linear_kernel<0><<<blocks, 256, 0, st>>>(pa, pb, po, c.d_primes, c.logn, static_cast<int>(L), total2);
+            else if (mode == 1)
+                linear_kernel<1><<<blocks, 256, 0, st>>>(pa, pb, po, c.d_primes, c.logn, static_cast<int>(L), total2);
+            else
+                linear_kernel<2><<<blocks, 256, 0, st>>>(pa, pb, po, c.d_primes, c.logn, static_cast<int>(L), total2);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "linear_kernel");
+        }
+    }
+
     // ------------------------------------------------------------------------------------- key switching ----
     // (1) target -> coefficient form (CKKS only): rows (b, J); evaluator.cpp:2651-2658
     struct OpKsIntt

@@ -117,6 +117,25 @@ static void test_ckks()
             err = std::max(err, std::abs(got[i] - x[i] * y[i]));
         CHECK(err < 1e-3);
     }
+    {
+        // square / add / sub / negate
+        Ciphertext r2, g2, r3, g3;
+        ref.square(cx, r2);
+        gpu.square(cx, g2);
+        CHECK(same_ct(r2, g2));
+        ref.add(cx, cy, r3);
+        gpu.add(cx, cy, g3);
+        CHECK(same_ct(r3, g3));
+        ref.sub_inplace(r3, cx);
+        gpu.sub_inplace(g3, cx);
+        CHECK(same_ct(r3, g3));
+        ref.negate_inplace(r3);
+        gpu.negate_inplace(g3);
+        CHECK(same_ct(r3, g3));
+        auto a = outcome([&] { Ciphertext t = cx; t.scale() *= 2; ref.add_inplace(t, cy); });
+        auto b = outcome([&] { Ciphertext t = cx; t.scale() *= 2; gpu.add_inplace(t, cy); });
+        CHECK(a == b && a == "invalid_argument"); // scale mismatch
+    }
     for (int step : { 1, -4, 5, 1023 })
     {
         Ciphertext r2, g2;

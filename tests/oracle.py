@@ -148,6 +148,14 @@ class Oracle:
             assert lib().orc_bfv_multiply(self.h, L, _p(a), _p(b), _p(out)) == 0
         return out
 
+    def linear(self, mode, L, a, b=None):
+        lib().orc_linear.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
+        a = np.ascontiguousarray(a)
+        out = np.zeros_like(a)
+        bb = np.ascontiguousarray(b) if b is not None else a
+        lib().orc_linear(self.h, mode, L, a.shape[0], _p(a), _p(bb), _p(out))
+        return out
+
     def relinearize(self, L, c3, key):
         out = np.zeros((2, L, self.n), dtype=np.uint64)
         lib().orc_relinearize(self.h, L, _p(c3), _p(key), _p(out))

@@ -44,6 +44,8 @@ def lib():
         L.sealref_ntt_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
         L.sealref_ntt_inverse.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
         L.sealref_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.sealref_square.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_linear.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.sealref_multiply_relin.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_rescale.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
@@ -154,6 +156,18 @@ class RefContext:
     def multiply(self, L, a, b):
         out = np.zeros((3, L, self.n), dtype=np.uint64)
         self._chk(lib().sealref_multiply(self.h, L, _p(a), _p(b), _p(out)))
+        return out
+
+    def square(self, L, a):
+        out = np.zeros((3, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_square(self.h, L, _p(a), _p(out)))
+        return out
+
+    def linear(self, mode, L, a, b=None):
+        a = np.ascontiguousarray(a)
+        out = np.zeros_like(a)
+        bb = np.ascontiguousarray(b) if b is not None else a
+        self._chk(lib().sealref_linear(self.h, mode, L, a.shape[0], _p(a), _p(bb), _p(out)))
         return out
 
     def relinearize(self, L, c3):

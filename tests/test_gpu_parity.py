@@ -227,3 +227,27 @@ def test_bfv_semantic_roundtrip():
     got, _ = rb.bfv_decrypt(L, rot)
     rows = x.reshape(2, n // 2)
     assert (got.reshape(2, n // 2) == np.roll(rows, -3, axis=1)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv"])
+def test_linear_ops_and_square_vs_reference(scheme):
+    # add / sub / negate / square
+    n, batch = 4096, 3
+    mods = R.coeff_modulus_create(n, [50, 45, 60])
+    t = R.plain_modulus_batching(n, 20) if scheme == "bfv" else 0
+    sid = sb().BFV if scheme == "bfv" else sb().CKKS
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    rng = np.random.default_rng(31)
+    L = 2
+    a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+    add, sub, neg, sq = ctx.add(a, b), ctx.sub(a, b), ctx.negate(a), ctx.square(a)
+    for i in range(batch):
+        assert (add[i] == rc.linear(0, L, a[i], b[i])).all()
+        assert (sub[i] == rc.linear(1, L, a[i], b[i])).all()
+        assert (neg[i] == rc.linear(2, L, a[i])).all()
+        assert (sq[i] == rc.square(L, a[i])).all()
+    # size-3 operands
+    a3 = rand_ct(rng, mods, n, 3, L, batch)
+    assert (ctx.add(a3, a3)[1] == rc.linear(0, L, a3[1], a3[1])).all()

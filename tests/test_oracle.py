@@ -132,3 +132,19 @@ def test_oracle_vs_live_reference_bfv_cfg1():
     assert (rb.relinearize(L, m) == ob.relinearize(L, m, rb.relin_key())).all()
     e = rb.galois_elt_from_step(1)
     assert (rb.apply_galois(L, x, e) == ob.apply_galois(L, x, e, rb.galois_key(e))).all()
+
+
+@needs_ref
+def test_oracle_linear_and_square_vs_live_reference():
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42])
+    rc, oc = R.RefContext(R.CKKS, n, mods), O.Oracle(O.CKKS, n, mods)
+    rng = np.random.default_rng(21)
+    L = 2
+    a, b = rand_ct(rng, mods, n, 2, L), rand_ct(rng, mods, n, 2, L)
+    for mode in (0, 1, 2):
+        assert (rc.linear(mode, L, a, b) == oc.linear(mode, L, a, b)).all()
+    assert (rc.square(L, a) == oc.multiply(L, a, a)).all()  # square computes the same residues as multiply(a, a)
+    t = R.plain_modulus_batching(n, 17)
+    rb, ob = R.RefContext(R.BFV, n, mods, t), O.Oracle(O.BFV, n, mods, t)
+    assert (rb.square(L, a) == ob.multiply(L, a, a)).all()
