@@ -80,6 +80,35 @@ __device__ __forceinline__ u64 lazy4_asm(u64 y, Tw w, u64 nq)
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(T1), "r"(n0));
     return pack(lo, hi);
 }
+__device__ __forceinline__ u64 lazy4_asm_b(u64 y, Tw w, u64 nq)
+{   // variant: the four 32-bit cross products as two independent chains (shorter dependency chain)
+    unsigned y0, y1, wq0, wq1, w0, w1, n0, n1;
+    unpack(y, y0, y1); unpack(w.wq, wq0, wq1); unpack(w.w, w0, w1); unpack(nq, n0, n1);
+    u64 a, b, T, acc;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(a) : "r"(y1), "r"(wq0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(b) : "r"(y0), "r"(wq1));
+    unsigned c1 = y0 * w1;                       // independent of T: can issue while T is being formed
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(y1), "r"(w0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(acc) : "r"(y0), "r"(w0));
+    unsigned alo, ahi, blo, bhi; unpack(a, alo, ahi); unpack(b, blo, bhi);
+    unsigned slo, shi;
+    asm("add.cc.u32 %0, %2, %3; addc.u32 %1, 0, 0;" : "=r"(slo), "=r"(shi) : "r"(ahi), "r"(bhi));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(T) : "r"(y1), "r"(wq1), "l"(pack(slo, shi)));
+    unsigned T0, T1; unpack(T, T0, T1);
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(T0), "r"(n0));
+    unsigned c2 = T0 * n1;
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(T1), "r"(n0));
+    unsigned lo, hi; unpack(acc, lo, hi);
+    hi = hi + c1 + c2;
+    return pack(lo, hi);
+}
+__device__ __forceinline__ void bf_fast_asm4(u64 &x, u64 &y, Tw w, const PrimeDev &P)
+{
+    u64 v = lazy4_asm_b(y, w, P.nq);
+    u64 u = x;
+    x = u + v;
+    y = u - v + P.q4;
+}
 __device__ __forceinline__ void bf_fast_asm3(u64 &x, u64 &y, Tw w, const PrimeDev &P)
 {
     u64 v = lazy4_asm(y, w, P.nq);
@@ -113,13 +142,14 @@ __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *t
     else if (KIND == 5) bf_fast_exact(X, Y, W, P);               \
     else if (KIND == 6) bf_fast_asm2(X, Y, W, P);                \
     else if (KIND == 7) bf_fast_asm3(X, Y, W, P);                \
-    else if (KIND == 8) bf_guard_asm3(X, Y, W, P);
+    else if (KIND == 8) bf_guard_asm3(X, Y, W, P);               \
+    else if (KIND == 9) bf_fast_asm4(X, Y, W, P);
 #pragma unroll
         for (int j = 0; j < 4; j++) { BF(a[j], a[j + 4], t[0]) }
         BF(a[0], a[2], t[1]) BF(a[1], a[3], t[1]) BF(a[4], a[6], t[2]) BF(a[5], a[7], t[2])
 #pragma unroll
         for (int p = 0; p < 4; p++) { BF(a[2 * p], a[2 * p + 1], t[3 + p]) }
-        if (KIND == 1 || KIND == 3 || KIND == 5 || KIND == 6 || KIND == 7)
+        if (KIND == 1 || KIND == 3 || KIND == 5 || KIND == 6 || KIND == 7 || KIND == 9)
         {   // keep FAST-mode values bounded the way a real kernel does once per 17 stages; here once per 12
 #pragma unroll
             for (int j = 0; j < 8; j++) a[j] = (r & 7) ? a[j] : barrett_lazy4(a[j], P.ratio_hi, P.nq);
@@ -129,12 +159,13 @@ __global__ void __launch_bounds__(256) k(u64 *d, const PrimeDev *pp, const Tw *t
     for (int j = 0; j < 8; j++) s ^= a[j];
     d[blockIdx.x * 256 + threadIdx.x] = s;
 }
+static int g_blocks_per_sm = 4;
 template <int KIND>
 void run(const char *name, u64 *d, PrimeDev *dp, Tw *dt)
 {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
-    const int blocks = 148 * 4;
+    const int blocks = 148 * g_blocks_per_sm;
     k<KIND><<<blocks, 256>>>(d, dp, dt);
     cudaEventRecord(e0);
     k<KIND><<<blocks, 256>>>(d, dp, dt);
@@ -164,8 +195,8 @@ int main()
     u64 *d;
     PrimeDev *dp;
     Tw *dt;
-    cudaMalloc(&d, 148 * 4 * 256 * 8 * 8);
-    cudaMemset(d, 7, 148 * 4 * 256 * 8 * 8);
+    cudaMalloc(&d, 148 * 8 * 256 * 8 * 8);
+    cudaMemset(d, 7, 148 * 8 * 256 * 8 * 8);
     cudaMalloc(&dp, sizeof(P));
     cudaMalloc(&dt, sizeof(t));
     cudaMemcpy(dp, &P, sizeof(P), cudaMemcpyHostToDevice);
@@ -179,5 +210,10 @@ int main()
     run<6>("FAST approx(asm) + C 64-bit mads", d, dp, dt);
     run<7>("FAST hand PTX (pack/unpack)", d, dp, dt);
     run<8>("guarded hand PTX", d, dp, dt);
+    run<9>("FAST hand PTX, split IMAD chains", d, dp, dt);
+    g_blocks_per_sm = 2;
+    run<7>("FAST hand PTX @2 CTAs/SM (16 warps)", d, dp, dt);
+    g_blocks_per_sm = 8;
+    run<7>("FAST hand PTX @8 CTAs/SM (64 warps)", d, dp, dt);
     return 0;
 }

@@ -29,6 +29,9 @@ __global__ void k(u32 *out, u32 a0, u32 b0)
             if (KIND == 8) { asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b)); asm volatile("addc.u32 %0, %0, %1;" : "+r"(((u32*)w)[2*i]) : "r"(a)); }
             if (KIND == 9) { asm volatile("{.reg .pred p; setp.ge.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(r[i]) : "r"(b), "r"(a)); }
             if (KIND == 10) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a), "r"(b)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(a)); }
+            if (KIND == 11) { asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(r[i]), "r"(b)); asm volatile("xor.b32 %0, %0, %1;" : "+r"(r[i]) : "r"(((u32*)w)[2*i+1])); }
+            if (KIND == 12) { asm volatile("mul.lo.u32 %0, %0, %1;" : "+r"(r[i]) : "r"(b)); }
+            if (KIND == 13) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a), "r"(b)); asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[(i+1)&7]) : "r"(b), "r"(a)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(b), "r"(a)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[(i+3)&7]) : "r"(a), "r"(b)); asm volatile("add.u32 %0, %0, %1;" : "+r"(((u32*)w)[2*((i+2)&7)]) : "r"(b)); }
         }
     }
     u32 s = 0;
@@ -70,5 +73,8 @@ int main()
     run<8>("IADD.CC + IADDC", 2);
     run<9>("ISETP + SEL", 2);
     run<10>("IMAD.WIDE + IMAD", 2);
+    run<11>("MUL.WIDE (no addend) + XOR", 2);
+    run<12>("IMUL lo (no addend)", 1);
+    run<13>("2 WIDE + 2 IMAD + 1 IADD", 5);
     return 0;
 }
