@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     # BASELINE.json configs[4] (the config the metric is quoted on): CKKS n=65536, 32 primes, multiply+relinearize;
     # 8192 ciphertexts over 8 GPUs = 1024 per GPU.  Fits one GPU: 2 x 33.3 GB in + 33.3 GB out + scratch.
-    "ckks_n65536_k32": dict(scheme=2, n=65536, bits=[55] * 32, batch=1024, e2e_batch=48, cpu_reps=1),
+    "ckks_n65536_k32": dict(scheme=2, n=65536, bits=[55] * 32, batch=1024, e2e_batch=64, cpu_reps=1),
     # BASELINE.json configs[1]
     "ckks_n8192_k4": dict(scheme=2, n=8192, bits=[54] * 4, batch=1024, e2e_batch=256, cpu_reps=200),
     # metric text "n=2^16, L=16 primes"

@@ -251,3 +251,28 @@ def test_linear_ops_and_square_vs_reference(scheme):
     # size-3 operands
     a3 = rand_ct(rng, mods, n, 3, L, batch)
     assert (ctx.add(a3, a3)[1] == rc.linear(0, L, a3[1], a3[1])).all()
+
+
+def test_c_abi_pointer_and_argument_errors():
+    # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
+    import ctypes as C
+
+    s = sb()
+    lib = s.lib()
+    null = C.c_void_p(None)
+    buf = np.zeros(8, dtype=np.uint64)
+    assert lib.sb200_ntt_forward_host(null, 1, 1, 1, s._hp(buf)) == -6
+    h = C.c_void_p()
+    assert lib.sb200_context_create(2, 1024, None, 1, 0, 0, C.byref(h)) == -6
+    n = 1024
+    mods = O.coeff_modulus_create(n, [40, 40])
+    ctx = s.Context(s.CKKS, n, mods)
+    assert lib.sb200_multiply_host(ctx.h, 1, 1, None, s._hp(buf), s._hp(buf)) == -6
+    assert lib.sb200_ntt_forward_host(ctx.h, 5, 1, 1, s._hp(buf)) == -1       # no such level
+    assert b"not valid" in lib.sb200_last_error()
+    assert lib.sb200_ntt_forward_host(ctx.h, 1, 1, 0, s._hp(buf)) == -1       # empty batch
+    with pytest.raises(ValueError):
+        s.Context(s.CKKS, n, mods, device=99)
+    # BEHZ queries on a CKKS context are a logic error, like RNSTool without a plain modulus
+    cnt = C.c_size_t(0)
+    assert lib.sb200_get_base_bsk(ctx.h, 1, s._hp(buf), 8, C.byref(cnt)) == -2
