@@ -103,3 +103,77 @@ def test_multi_rank_gather_gloo(tmp_path):
     outs = [p.communicate(timeout=240) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0][0]
+
+
+# ---- the product's host-side precomputation (sb_host.cpp) against the oracle, on the CPU ---------------------------
+def _probe():
+    import ctypes as C
+
+    d = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-C", d, "probe"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(d, "_bin", "libhostprobe.so"))
+    u64p = C.POINTER(C.c_uint64)
+    L.probe_tables.argtypes = [C.c_size_t, C.c_uint64] + [u64p] * 8
+    L.probe_bsk.restype = C.c_size_t
+    L.probe_bsk.argtypes = [C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
+    L.probe_galois_table.argtypes = [C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.probe_elt_from_step.restype = C.c_uint32
+    L.probe_elt_from_step.argtypes = [C.c_size_t, C.c_int]
+    L.probe_is_prime.argtypes = [C.c_uint64]
+    return L
+
+
+def _pp(a):
+    import ctypes as C
+
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+@pytest.mark.parametrize("n,bits", [(2, None), (8, [20]), (1024, [40, 50]), (4096, [36, 60]), (32768, [55])])
+def test_host_tables_match_oracle(n, bits):
+    import ctypes as C
+
+    P = _probe()
+    mods = [0xFFFFFFFFFFC0001] if bits is None else O.coeff_modulus_create(n, bits)
+    oc = O.Oracle(O.CKKS, n, mods)
+    for i, q in enumerate(mods):
+        root, inv_n = C.c_uint64(0), C.c_uint64(0)
+        rp, rpq, irp, fw, iw = (np.zeros(n, dtype=np.uint64) for _ in range(5))
+        ratio = np.zeros(2, dtype=np.uint64)
+        assert P.probe_tables(n, q, C.byref(root), _pp(rp), _pp(rpq), _pp(irp), C.byref(inv_n), _pp(fw), _pp(iw), _pp(ratio)) == 0
+        oroot, orp, oirp, oinv = oc.ntt_tables(i)
+        assert root.value == oroot and (rp == orp).all() and (irp == oirp).all() and inv_n.value == oinv
+        # Shoup quotients and the Barrett ratio are exact floors
+        for j in (0, 1, n // 2, n - 1):
+            assert int(rpq[j]) == (int(rp[j]) << 64) // q
+        assert (int(ratio[1]) << 64) + int(ratio[0]) == (1 << 128) // q
+        # device order: fwd[m+i] = root_powers[m+i]; inv[m+i] = inv_root_powers[n-2m+1+i]
+        assert (fw == rp).all()
+        m = 1
+        while m < n:
+            assert (iw[m:2 * m] == irp[n - 2 * m + 1:n - m + 1]).all()
+            m *= 2
+    if n == 2:  # native/tests/seal/util/ntt.cpp:53-63
+        assert int(rp[1]) == 288794978602139552
+
+
+def test_host_galois_and_behz_match_oracle():
+    import ctypes as C
+
+    P = _probe()
+    # native/tests/seal/util/galois.cpp:104-120: n=8, g=3 -> NTT-form permutation {4,5,7,6,1,0,2,3}
+    t = np.zeros(8, dtype=np.uint32)
+    P.probe_galois_table(8, 3, t.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert list(t) == [4, 5, 7, 6, 1, 0, 2, 3]
+    x = np.arange(8, dtype=np.uint64)
+    assert list(x[t]) == list(O.galois_ntt_row(8, 3, x))
+    for n in (8, 4096, 65536):
+        for step in (0, 1, -1, 3, -(n // 2 - 1), n // 2 - 1):
+            assert P.probe_elt_from_step(n, step) == O.galois_elt_from_step(n, step)
+        assert P.probe_elt_from_step(n, n // 2) == 0  # "step count too large" (galois.cpp:72-75)
+    n = 4096
+    for q, tt in (([0xFFFFEE001, 0xFFFFC4001], 1032193), (O.coeff_modulus_create(n, [60, 60, 60])[:2], 1 << 30)):
+        out = np.zeros(8, dtype=np.uint64)
+        cnt = P.probe_bsk(n, _pp(np.array(q, dtype=np.uint64)), len(q), tt, _pp(out))
+        assert [int(v) for v in out[:cnt]] == O.behz_base(n, q, tt)
+    assert P.probe_is_prime(0xFFFFEE001) == 1 and P.probe_is_prime(0xFFFFEE003) == O.lib().orc_is_prime(0xFFFFEE003)
