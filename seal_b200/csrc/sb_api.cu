@@ -167,7 +167,7 @@ unsigned long long sb200_launch_count(const sb200_context *ctx)
 
 size_t sb200_device_bytes(const sb200_context *ctx)
 {
-    return ctx ? ctx->c->table_bytes + ctx->c->scratch_bytes : 0;
+    return ctx ? ctx->c->table_bytes + ctx->c->scratch_bytes + ctx->c->aux_bytes : 0;
 }
 
 int sb200_profile_enable(sb200_context *ctx, int on)

@@ -37,6 +37,7 @@ namespace sb
         cudaFree(d_primes);
         cudaFree(d_invq);
         cudaFree(scratch);
+        cudaFree(aux_buf);
         for (auto &slot : io.buf)
             for (auto p : slot)
                 cudaFree(p);
@@ -62,6 +63,20 @@ namespace sb
             scratch_bytes = bytes;
         }
         return scratch;
+    }
+
+    void *Context::ensure_aux(size_t bytes)
+    {
+        if (bytes > aux_bytes)
+        {
+            cuda_check(cudaDeviceSynchronize(), "sync before aux growth");
+            cudaFree(aux_buf);
+            aux_buf = nullptr;
+            aux_bytes = 0;
+            cuda_check(cudaMalloc(&aux_buf, bytes), "cudaMalloc(aux)");
+            aux_bytes = bytes;
+        }
+        return aux_buf;
     }
 
     const uint32_t *Context::galois_table(uint32_t elt)
@@ -936,15 +951,13 @@ namespace sb
         {
             // BFV: BEHZ multiply into a size-3 scratch, then relinearize (no fusion across the base conversion)
             const size_t chunk = std::min(batch, std::max<size_t>(1, (size_t(1) << 30) / (3 * poly * sizeof(u64))));
-            u64 *tmp = nullptr;
-            cuda_check(cudaMallocAsync(reinterpret_cast<void **>(&tmp), chunk * 3 * poly * sizeof(u64), st), "cudaMallocAsync");
+            u64 *tmp = static_cast<u64 *>(c.ensure_aux(chunk * 3 * poly * sizeof(u64)));
             for (size_t b0 = 0; b0 < batch; b0 += chunk)
             {
                 size_t B = std::min(chunk, batch - b0);
                 op_bfv_multiply(c, L, B, a + b0 * 2 * poly, b + b0 * 2 * poly, tmp, st);
                 op_relinearize(c, L, B, tmp, key, out2 + b0 * 2 * poly, st);
             }
-            cuda_check(cudaFreeAsync(tmp, st), "cudaFreeAsync");
             return;
         }
         const size_t chunk = ks_chunk(c, L, batch, true);

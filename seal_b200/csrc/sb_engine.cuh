@@ -52,6 +52,8 @@ namespace sb
         std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
         std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
         void *scratch = nullptr;
+        void *aux_buf = nullptr;             // second grow-only arena (size-3 intermediate of BFV multiply+relinearize)
+        size_t aux_bytes = 0;
         size_t scratch_bytes = 0, table_bytes = 0, scratch_budget = size_t(8) << 30;
         LaunchStats stats;
         IoArena io;
@@ -59,6 +61,7 @@ namespace sb
 
         ~Context();
         void *ensure_scratch(size_t bytes);
+        void *ensure_aux(size_t bytes);
         const uint32_t *galois_table(uint32_t elt);
         size_t prime_id_aux(size_t aux_index) const { return k + aux_index; }
     };
