@@ -276,3 +276,30 @@ def test_c_abi_pointer_and_argument_errors():
     # BEHZ queries on a CKKS context are a logic error, like RNSTool without a plain modulus
     cnt = C.c_size_t(0)
     assert lib.sb200_get_base_bsk(ctx.h, 1, s._hp(buf), 8, C.byref(cnt)) == -2
+
+
+@pytest.mark.parametrize("logn,scheme", [(17, "ckks"), (15, "bfv"), (11, "ckks")])
+def test_keyswitch_extreme_sizes_vs_oracle(logn, scheme):
+    # n = 131072 is SEAL_POLY_MOD_DEGREE_MAX (util/defines.h:52); n = 2048 is the largest size on the one-CTA-per-row path
+    n = 1 << logn
+    bits = [50, 45, 55] if scheme == "ckks" else [48, 48, 49]
+    mods = O.coeff_modulus_create(n, bits)
+    t = 0
+    if scheme == "bfv":
+        t = next(p for p in range((1 << 20) + 1, 1 << 21, 2 * n) if O.lib().orc_is_prime(p))  # prime = 1 mod 2n
+    sid = sb().BFV if scheme == "bfv" else sb().CKKS
+    ctx = sb().Context(sid, n, mods, t)
+    oc = O.Oracle(sid, n, mods, t)
+    rng = np.random.default_rng(logn)
+    L, k = 2, 3
+    key = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k)]) for _ in range(2)]) for _ in range(L)])
+    rk = ctx.load_key(key)
+    a, b = rand_ct(rng, mods, n, 2, L, 2), rand_ct(rng, mods, n, 2, L, 2)
+    got = ctx.multiply_relinearize(a, b, rk)
+    assert (got[1] == oc.multiply_relin(L, a[1], b[1], key)).all()
+    e = O.galois_elt_from_step(n, 1)
+    assert (ctx.apply_galois(a, e, rk)[0] == oc.apply_galois(L, a[0], e, key)).all()
+    if scheme == "ckks":
+        assert (ctx.rescale_to_next(a)[1] == oc.rescale(L, a[1])).all()
+    else:
+        assert (ctx.mod_switch_to_next(a)[1] == oc.bfv_mod_switch(L, a[1])).all()
