@@ -36,6 +36,8 @@ WORKLOADS = {
     # metric text "n=2^16, L=16 primes"
     "ckks_n65536_k16": dict(scheme=2, n=65536, bits=[55] * 16, batch=1024, e2e_batch=32, cpu_reps=2),
     "ckks_n32768_k16": dict(scheme=2, n=32768, bits=[55] * 15 + [56], batch=256, e2e_batch=64, cpu_reps=4),
+    # tiny shape for the CPU contract test of the reference arm (tests/test_bench_contract.py); not a bench line
+    "smoke": dict(scheme=2, n=4096, bits=[40, 40, 40], batch=8, e2e_batch=4, cpu_reps=4),
 }
 METRIC = "CKKS multiply+relinearize ciphertexts/s"
 UNIT = "ciphertexts/s"
