@@ -613,6 +613,13 @@ namespace sb
                     for (int j = 0; j < 8; j++)
                         a[j] = csub(csub(csub(a[j], P.q4), P.q2), P.q); // keeps 256 summands below 2^128 for 60-bit primes
                 }
+                else if (L > 200)
+                {
+                    // guard-free values reach 72q < 2^63.2: more than 227 products with a 57-bit key word would overflow 128 bits
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        a[j] = barrett_lazy4(a[j], P.ratio_hi, P.nq);
+                }
             }
             const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + e0);
             const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + k + ki) << logn) + e0);
