@@ -81,7 +81,9 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
 int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out);
 int sb200_kswitch_key_destroy(sb200_kswitch_key *key);
 
-/* ---- device-resident batch operations (stream = cudaStream_t, may be NULL) ---------------------------------- */
+/* ---- device-resident batch operations (stream = cudaStream_t, may be NULL) ----------------------------------
+ * Output slabs must not alias input slabs unless noted: multiply_relinearize may write over d_a or d_b, add/sub/negate
+ * may run in place; relinearize / rescale / mod_switch / apply_galois change the layout and reject aliasing. */
 /* Evaluator::transform_to_ntt_inplace / transform_from_ntt_inplace (evaluator.cpp:2289-2382) */
 int sb200_ntt_forward(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d_data, void *stream);
 int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *d_data, void *stream);

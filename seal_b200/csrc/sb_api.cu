@@ -357,6 +357,8 @@ int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
+    if (static_cast<const void *>(in3) == static_cast<const void *>(out2))
+        throw std::invalid_argument("relinearize: input and output slabs must not alias (different layouts)");
     op_relinearize(c, L, batch, (const u64 *)in3, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
     return SB200_OK;
     SB_CATCH
@@ -384,6 +386,8 @@ int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
+    if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
+        throw std::invalid_argument("rescale_to_next: input and output slabs must not alias (different layouts)");
     op_rescale(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
     return SB200_OK;
     SB_CATCH
@@ -396,6 +400,8 @@ int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const u
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
+    if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
+        throw std::invalid_argument("mod_switch_to_next: input and output slabs must not alias (different layouts)");
     op_mod_switch(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
     return SB200_OK;
     SB_CATCH
