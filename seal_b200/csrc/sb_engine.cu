@@ -532,6 +532,68 @@ namespace sb
         o[static_cast<long long>(L + 1) << logn] = barrett128(lo1, hi1, P.q, P.ratio_lo, P.ratio_hi);
     }
 
+    // (2a) column pass of ALL digits of one (ciphertext b, output prime I) in one CTA: the twiddles of prime I are staged once
+    //      by TMA and reused for the L digit rows (the generic ntt_fwd_col pays the staging + row decoding per row).
+    //      grid = (column tiles, B*(L+1)); same arithmetic as ntt_fwd_col<LOGNA, FAST, OpKsDigit>.
+    template <int LOGNA, bool FAST>
+    __global__ void __launch_bounds__(kColThreads, SB_COL_MIN_BLOCKS) ks_digit_col_kernel(OpKsDigit op, const PrimeDev *__restrict__ primes)
+    {
+        constexpr int NA = 1 << LOGNA;
+        constexpr int C = kTile / NA;
+        __shared__ __align__(16) u64 tile[kTile];
+        __shared__ __align__(16) Tw tw_s[NA];
+        __shared__ __align__(8) u64 bar;
+        const int L = op.L, bi = blockIdx.y, I = bi % (L + 1), col0 = blockIdx.x * C;
+        const int tid = threadIdx.x, c = tid % C, ridx = tid / C;
+        const PrimeDev P = primes[I == L ? op.k - 1 : I];
+        if (tid == 0)
+            mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(&bar, NA * sizeof(Tw));
+            tma_load_1d(tw_s, P.fwd, NA * sizeof(Tw), &bar);
+        }
+        mbar_wait(&bar, 0);
+        constexpr int g = NA >> 3;
+        const int off = (ridx << kLocalLog) + col0 + c;
+        for (int J = 0; J < L; J++)
+        {
+            if (op.ntt_in && J == I)
+                continue;
+            const int row = bi * L + J;
+            u64 a[8];
+            const u64 *dp = op.direct(row, P);
+            if (dp)
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = dp[off + ((j * g) << kLocalLog)];
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = op.load1(row, off + ((j * g) << kLocalLog), P);
+            }
+            fwd_col_passes<LOGNA, FAST>(a, tile, tw_s, ridx, c, P);
+            u64 *mid = op.mid(row);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                mid[((8 * ridx + j) << kLocalLog) + col0 + c] = a[j];
+        }
+    }
+
+    template <int LOGNA>
+    static void launch_ks_digit_col(const OpKsDigit &op, int B, bool fast, const PrimeDev *primes, cudaStream_t st)
+    {
+        dim3 grid((1 << kLocalLog) / (kTile >> LOGNA), static_cast<unsigned>(B * (op.L + 1)));
+        if (fast)
+            ks_digit_col_kernel<LOGNA, true><<<grid, kColThreads, 0, st>>>(op, primes);
+        else
+            ks_digit_col_kernel<LOGNA, false><<<grid, kColThreads, 0, st>>>(op, primes);
+    }
+
     // (2b)+(3) fused: the 8 in-block stages of every digit transform + the multiply-accumulate with the key, looping
     //     over the digits J inside the kernel so the transformed digits never reach memory and the 128-bit sums live in
     //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
@@ -836,6 +898,7 @@ namespace sb
         // keep row counts of a launch inside int range
         chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 30) / ((L + 1) * L * c.n)));
         chunk = std::min<size_t>(chunk, 32768);
+        chunk = std::min<size_t>(chunk, 65535 / (L + 1)); // (b, I) pairs ride in gridDim.y of the key-switch kernels
         return std::min(chunk, batch);
     }
 
@@ -873,9 +936,26 @@ namespace sb
             qmin = std::min(qmin, c.q[c.k - 1]);
             const int reduce = (qmax >> 2) >= qmin ? 1 : 0;
             OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0, reduce };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats, "ks_digit_ntt",
-                                      static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L)), c.fast_q, fused),
-                       "ks digit ntt");
+            const int active = static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L));
+            if (fused)
+            {
+                c.stats.begin("ks_digit_ntt", 1, 16.0 * active * n, st);
+                switch (c.logn - kLocalLog)
+                {
+                case 4: launch_ks_digit_col<4>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 5: launch_ks_digit_col<5>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 6: launch_ks_digit_col<6>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 7: launch_ks_digit_col<7>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 8: launch_ks_digit_col<8>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 9: launch_ks_digit_col<9>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                default: throw std::logic_error("unsupported transform size");
+                }
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "ks_digit_col_kernel");
+            }
+            else
+                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * (L + 1) * L), c.logn, c.d_primes, st, c.stats, "ks_digit_ntt", active, c.fast_q),
+                           "ks digit ntt");
         }
         // digits in + 2 accumulated components out per (b, I), plus one pass over the key
         const double mac_bytes = 8.0 * n * (static_cast<double>(B) * (L + 1) * (L + 2) + 2.0 * L * (L + 1));

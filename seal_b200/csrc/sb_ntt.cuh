@@ -115,6 +115,46 @@ namespace sb
     }
 
     // ---------------------------------------------------------------------------------- forward: column pass ----
+    // The log2(NA) column stages on one thread's 8 coefficients: in = layout r = ridx + j*(NA/8), out = layout r = 8*ridx + j.
+    // Layout changes go through the CTA's shared tile (two barriers each); tw_s = the NA-1 twiddles of these stages.
+    template <int LOGNA, bool FAST>
+    __device__ __forceinline__ void fwd_col_passes(u64 (&a)[8], u64 *tile, const Tw *tw_s, int ridx, int c, const PrimeDev &P)
+    {
+        constexpr int NA = 1 << LOGNA;
+        constexpr int C = kTile / NA;
+        constexpr int NST0 = LOGNA % 3;
+        int prev_g = NA >> 3; // layout of the loaded registers: r = rhi*8g + rlo + j*g with g = NA/8 (rhi = 0)
+        if (NST0 != 0)
+        {
+            // partial first pass: stages 0..NST0-1 in the initial layout
+            auto twf = [&](int lvl, int k) { return tw_s[(1 << lvl) + k]; };
+            fwd_regs<NST0, FAST>(a, twf, P);
+        }
+        // full 3-stage passes; the layout changes between passes through the shared tile
+#pragma unroll
+        for (int S = NST0; S < LOGNA; S += 3)
+        {
+            const int g = NA >> (S + 3);
+            const int rhi = ridx / g, rlo = ridx % g;
+            if (g != prev_g)
+            {
+                const int prhi = ridx / prev_g, prlo = ridx % prev_g;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    tile[(prhi * 8 * prev_g + prlo + j * prev_g) * C + c] = a[j];
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = tile[(rhi * 8 * g + rlo + j * g) * C + c];
+                __syncthreads();
+            }
+            const int m = 1 << S;
+            auto twf = [&](int lvl, int k) { return tw_s[(m << lvl) + (rhi << lvl) + k]; };
+            fwd_regs<3, FAST>(a, twf, P);
+            prev_g = g;
+        }
+    }
+
     template <int LOGNA, bool FAST, class Op>
     __global__ void __launch_bounds__(kColThreads, SB_COL_MIN_BLOCKS) ntt_fwd_col(Op op, const PrimeDev *__restrict__ primes)
     {
@@ -160,36 +200,7 @@ namespace sb
         }
         mbar_wait(&bar, 0);
 
-        int prev_g = NA >> 3; // layout of the loaded registers: r = rhi*8g + rlo + j*g with g = NA/8 (rhi = 0)
-        if (NST0 != 0)
-        {
-            // partial first pass: stages 0..NST0-1 in the initial layout
-            auto twf = [&](int lvl, int k) { return tw_s[(1 << lvl) + k]; };
-            fwd_regs<NST0, FAST>(a, twf, P);
-        }
-        // full 3-stage passes; the layout changes between passes through the shared tile
-#pragma unroll
-        for (int S = NST0; S < LOGNA; S += 3)
-        {
-            const int g = NA >> (S + 3);
-            const int rhi = ridx / g, rlo = ridx % g;
-            if (g != prev_g)
-            {
-                const int prhi = ridx / prev_g, prlo = ridx % prev_g;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    tile[(prhi * 8 * prev_g + prlo + j * prev_g) * C + c] = a[j];
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    a[j] = tile[(rhi * 8 * g + rlo + j * g) * C + c];
-                __syncthreads();
-            }
-            const int m = 1 << S;
-            auto twf = [&](int lvl, int k) { return tw_s[(m << lvl) + (rhi << lvl) + k]; };
-            fwd_regs<3, FAST>(a, twf, P);
-            prev_g = g;
-        }
+        fwd_col_passes<LOGNA, FAST>(a, tile, tw_s, ridx, c, P);
         // last layout has g = 1: r = 8*ridx + j
         u64 *mid = op.mid(row);
 #pragma unroll
