@@ -543,7 +543,7 @@ namespace sb
         __shared__ __align__(16) u64 tile[kTile];
         __shared__ __align__(16) Tw tw_s[NA];
         __shared__ __align__(8) u64 bar;
-        const int L = op.L, bi = blockIdx.y, I = bi % (L + 1), col0 = blockIdx.x * C;
+        const int L = op.L, bi = blockIdx.y, I = bi % (L + 1), b = bi / (L + 1), col0 = blockIdx.x * C;
         const int tid = threadIdx.x, c = tid % C, ridx = tid / C;
         const PrimeDev P = primes[I == L ? op.k - 1 : I];
         if (tid == 0)
@@ -563,7 +563,8 @@ namespace sb
                 continue;
             const int row = bi * L + J;
             u64 a[8];
-            const u64 *dp = op.direct(row, P);
+            // same decision as OpKsDigit::direct(), without its per-row index divisions
+            const u64 *dp = (op.dsrc.plain() && !(op.reduce && primes[J].q > P.q)) ? op.dsrc.row(b, J) : nullptr;
             if (dp)
             {
 #pragma unroll
@@ -836,9 +837,32 @@ namespace sb
         }
         __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
         {
+            // 8 consecutive coefficients: 16-byte loads of the accumulated component and of the base ciphertext, 16-byte stores
+            const int i = row % Lout, bc = row / Lout, b = bc >> 1, c = bc & 1;
+            const ulonglong2 *xp = reinterpret_cast<const ulonglong2 *>(X + b * x_bs + c * x_ps + (static_cast<long long>(i) << logn) + idx0);
+            ulonglong2 *op_ = reinterpret_cast<ulonglong2 *>(out + b * o_bs + c * o_ps + (static_cast<long long>(i) << logn) + idx0);
+            const bool has_base = base.present && !(c == 1 && base.c1_zero);
+            const bool base_plain = has_base && base.s.plain();
+            const ulonglong2 *bp = base_plain ? reinterpret_cast<const ulonglong2 *>(base.s.row(b, i) + c * base.pstride + idx0) : nullptr;
+            const Tw inv = inv_top[i];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                store1(row, idx0 + j, a[j], P);
+            for (int h = 0; h < 4; h++)
+            {
+                ulonglong2 x = xp[h];
+                u64 t0 = csub(csub(a[2 * h], P.q2), P.q), t1 = csub(csub(a[2 * h + 1], P.q2), P.q);
+                u64 r0 = mul_shoup(x.x + P.q - t0, inv, P.q), r1 = mul_shoup(x.y + P.q - t1, inv, P.q);
+                if (base_plain)
+                {
+                    ulonglong2 bv = bp[h];
+                    r0 = csub(r0 + bv.x, P.q), r1 = csub(r1 + bv.y, P.q);
+                }
+                else if (has_base)
+                {
+                    r0 = csub(r0 + base.get(b, c, i, idx0 + 2 * h, P.q), P.q);
+                    r1 = csub(r1 + base.get(b, c, i, idx0 + 2 * h + 1, P.q), P.q);
+                }
+                op_[h] = make_ulonglong2(r0, r1);
+            }
         }
     };
 
