@@ -471,7 +471,7 @@ namespace
         void run(size_t batch, size_t wa, size_t wb, size_t wo, const uint64_t *ha, const uint64_t *hb, uint64_t *ho, F &&op)
         {
             const size_t per_ct = (wa + wb + wo) * sizeof(u64);
-            size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (size_t(1) << 30) / std::max<size_t>(per_ct, 1)));
+            size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (size_t(640) << 20) / std::max<size_t>(per_ct, 1)));
             if (chunk >= batch && batch >= 4)
                 chunk = (batch + 1) / 2; // at least two chunks so the copies overlap the kernels
             // size all staging (and let the op grow its scratch) before the pipeline starts: growth synchronises the device
