@@ -147,6 +147,40 @@ namespace seal_b200
             }
         }
 
+        // ---- multiply_plain with an NTT-form plaintext (evaluator.cpp:1975-2019 dispatcher, :2157-2195 multiply_plain_ntt) ----
+        // Coefficient-form plaintexts (BFV multiply_plain_normal, :2021-2155) are outside the path: transform them with
+        // seal::Evaluator::transform_to_ntt_inplace(plain, parms_id) first.
+        void multiply_plain_inplace(seal::Ciphertext &encrypted, const seal::Plaintext &plain,
+                                    seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (!seal::is_metadata_valid_for(plain, context_) || !seal::is_buffer_valid(plain))
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            if (!plain.is_ntt_form())
+                throw std::invalid_argument("seal_b200: multiply_plain is implemented for NTT-form plaintexts");
+            const bool back = !encrypted.is_ntt_form(); // :2006-2011: to NTT form, multiply, back
+            if (back)
+                transform_to_ntt_inplace(encrypted);
+            if (encrypted.parms_id() != plain.parms_id())
+                throw std::invalid_argument("encrypted_ntt and plain_ntt parameter mismatch"); // :2164-2167
+            check(sb200_multiply_plain_host(ctx_, encrypted.coeff_modulus_size(), encrypted.size(), 1, encrypted.data(), plain.data(),
+                                            encrypted.data()));
+            encrypted.scale() *= plain.scale();
+            if (!scale_within_bounds(encrypted.scale(), *context_.get_context_data(encrypted.parms_id())))
+                throw std::invalid_argument("scale out of bounds"); // :2189-2193
+            if (back)
+                transform_from_ntt_inplace(encrypted);
+            throw_if_transparent(encrypted);
+        }
+        void multiply_plain(const seal::Ciphertext &encrypted, const seal::Plaintext &plain, seal::Ciphertext &destination,
+                            seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            multiply_plain_inplace(destination, plain, std::move(pool));
+        }
+
         // ---- relinearize (evaluator.cpp:1144-1199) ---------------------------------------------------------------
         void relinearize_inplace(seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys,
                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const

@@ -301,6 +301,23 @@ extern "C" int sealref_linear(sealref_ctx *c, int mode, size_t L, size_t size, c
     REF_CATCH(-1)
 }
 
+extern "C" int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, size, a);
+    x.is_ntt_form() = true; // BFV callers pass an already transformed ciphertext (evaluator.cpp:1991-1994)
+    auto cd = level(c, L);
+    Plaintext p;
+    p.resize(L * c->n);
+    std::memcpy(p.data(), plain, L * c->n * sizeof(uint64_t));
+    p.parms_id() = cd->parms_id(); // NTT-form plaintext at the ciphertext's level
+    p.scale() = c->scheme == scheme_type::ckks ? default_scale(*cd) : 1.0;
+    c->evaluator->multiply_plain_inplace(x, p);
+    store_ct(c, x, out);
+    return 0;
+    REF_CATCH(-1)
+}
+
 static const RelinKeys &relin_keys(sealref_ctx *c)
 {
     if (!c->relin)

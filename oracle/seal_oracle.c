@@ -349,6 +349,16 @@ void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const u64 *a,
             }
 }
 
+/* multiply_plain with both operands in NTT form (evaluator.cpp:2157-2195: dyadic_product_coeffmod per polynomial) */
+void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const u64 *a, const u64 *plain, u64 *out)
+{
+    size_t n = c->n;
+    for (size_t p = 0; p < size; p++)
+        for (size_t i = 0; i < L; i++)
+            for (size_t j = 0; j < n; j++)
+                out[(p * L + i) * n + j] = mulmod(a[(p * L + i) * n + j], plain[i * n + j], c->q[i]);
+}
+
 /* -------------------------------------------------------------------- key switching (evaluator.cpp:2561-2867) -- */
 void orc_switch_key(const orc_ctx *c, size_t L, u64 *ct, const u64 *target, const u64 *key)
 {

@@ -61,6 +61,8 @@ void orc_ntt_inverse(const orc_ctx *c, size_t L, size_t size, uint64_t *data);  
 void orc_ckks_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3); /* evaluator.cpp:569-708 */
 /* add (mode 0), sub (1), negate (2) on [size][L][n]; evaluator.cpp:130-350 */
 void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out);
+/* Evaluator::multiply_plain, ciphertext and plaintext in NTT form (evaluator.cpp:2157-2195) */
+void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out);
 int orc_bfv_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3);   /* evaluator.cpp:395-567 */
 /* ct (size 2, updated in place) += key-switch of target ([L][n]); key = [L digits][2][k][n]; evaluator.cpp:2561-2867 */
 void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct2, const uint64_t *target, const uint64_t *key);

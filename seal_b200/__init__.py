@@ -26,9 +26,9 @@ SYMBOLS = [
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
-    "sb200_ntt_inverse", "sb200_multiply", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
-    "sb200_multiply_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
+    "sb200_multiply_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host",
 ]
 
@@ -68,6 +68,8 @@ def lib():
         L.sb200_add.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_sub.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_negate.argtypes = [vp, sz, sz, sz, vp, vp, vp]
+        L.sb200_multiply_plain.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
+        L.sb200_multiply_plain_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
         L.sb200_square_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_add_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
         L.sb200_sub_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
@@ -258,6 +260,15 @@ class Context:
     def negate(self, a):
         return self._linear(lib().sb200_negate_host, a)
 
+    def multiply_plain(self, a, plain):
+        """Evaluator.multiply_plain, NTT-form ciphertext [B][size][L][n] x NTT-form plaintexts [B][L][n]"""
+        a, single = self._batched(a)
+        B, size, L, n = a.shape
+        plain = np.ascontiguousarray(plain).reshape(B, L, n)
+        out = np.zeros_like(a)
+        _check(lib().sb200_multiply_plain_host(self.h, L, size, B, _hp(a), _hp(plain), _hp(out)))
+        return out[0] if single else out
+
     def relinearize(self, c3, key):
         c3, single = self._batched(c3)
         B, _, L, n = c3.shape
@@ -313,6 +324,9 @@ class Context:
 
     def d_multiply(self, a, b, out3, L, batch):
         _check(lib().sb200_multiply(self.h, L, batch, _dp(a), _dp(b), _dp(out3), self._stream()))
+
+    def d_multiply_plain(self, a, plain, out, L, size, batch):
+        _check(lib().sb200_multiply_plain(self.h, L, size, batch, _dp(a), _dp(plain), _dp(out), self._stream()))
 
     def d_relinearize(self, in3, key, out2, L, batch):
         _check(lib().sb200_relinearize(self.h, L, batch, _dp(in3), key.h, _dp(out2), self._stream()))

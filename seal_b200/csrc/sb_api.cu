@@ -343,6 +343,19 @@ int sb200_negate(sb200_context *ctx, size_t L, size_t size, size_t batch, const 
 {
     return linear_dev(ctx, 2, L, size, batch, a, nullptr, out, stream);
 }
+int sb200_multiply_plain(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *plain, uint64_t *out,
+                         void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    op_multiply_plain(c, L, size, batch, (const u64 *)a, (const u64 *)plain, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
 int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3, void *stream)
 {
     return sb200_multiply(ctx, L, batch, a, a, out3, stream);
@@ -580,6 +593,20 @@ int sb200_sub_host(sb200_context *ctx, size_t L, size_t size, size_t batch, cons
 int sb200_negate_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, uint64_t *out)
 {
     return linear_host(ctx, 2, L, size, batch, a, nullptr, out);
+}
+int sb200_multiply_plain_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *plain, uint64_t *out)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t w = L * c.n;
+    HostPipe(c).run(batch, size * w, w, size * w, a, plain, out,
+                    [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) { op_multiply_plain(c, L, size, B, da, db, dout, st); });
+    return SB200_OK;
+    SB_CATCH
 }
 int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3)
 {

@@ -423,6 +423,44 @@ namespace sb
         }
     }
 
+    // ---- multiply_plain, NTT x NTT (evaluator.cpp:2157-2195: dyadic_product_coeffmod of every polynomial with the plaintext) ----
+    // ct [B][size][L][n], plain [B][L][n] (one NTT-form plaintext per ciphertext, at the ciphertext's level)
+    __global__ void __launch_bounds__(256) plain_mul_kernel(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ plain,
+                                                             ulonglong2 *out, const PrimeDev *__restrict__ primes, int logn, int L, int size,
+                                                             long long total2)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over pairs of coefficients
+        if (e >= total2)
+            return;
+        const long long row = (e * 2) >> logn;
+        const int i = static_cast<int>(row % L);
+        const long long b = row / (static_cast<long long>(size) * L);
+        const long long pe = (((b * L + i) << logn) >> 1) + (e & ((1ll << (logn - 1)) - 1));
+        const PrimeDev &P = primes[i];
+        const ulonglong2 x = a[e], y = plain[pe];
+        out[e] = make_ulonglong2(mulmod_barrett(x.x, y.x, P), mulmod_barrett(x.y, y.y, P));
+    }
+
+    void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st)
+    {
+        if (c.n < 2 || size < 1)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        const size_t per = size * L * c.n, step = std::max<size_t>(1, (size_t(1) << 32) / per);
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t nb = std::min(step, batch - b0);
+            const long long total2 = static_cast<long long>(nb * per / 2);
+            const unsigned blocks = static_cast<unsigned>((total2 + 255) / 256);
+            c.stats.begin("multiply_plain", 0, 8.0 * (2.0 * nb * per + nb * L * c.n), st);
+            plain_mul_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const ulonglong2 *>(a + b0 * per),
+                                                     reinterpret_cast<const ulonglong2 *>(plain + b0 * L * c.n),
+                                                     reinterpret_cast<ulonglong2 *>(out + b0 * per), c.d_primes, c.logn, static_cast<int>(L),
+                                                     static_cast<int>(size), total2);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "plain_mul_kernel");
+        }
+    }
+
     // ------------------------------------------------------------------------------------- key switching ----
     // (1) target -> coefficient form (CKKS only): rows (b, J); evaluator.cpp:2651-2658
     struct OpKsIntt

@@ -136,6 +136,30 @@ static void test_ckks()
         auto b = outcome([&] { Ciphertext t = cx; t.scale() *= 2; gpu.add_inplace(t, cy); });
         CHECK(a == b && a == "invalid_argument"); // scale mismatch
     }
+    {
+        // multiply_plain, NTT path (CKKS plaintexts are always in NTT form)
+        Ciphertext r2, g2;
+        ref.multiply_plain(cx, py, r2);
+        gpu.multiply_plain(cx, py, g2);
+        CHECK(same_ct(r2, g2));
+        ref.multiply(cx, cy, r2);
+        g2 = r2; // size 3
+        Plaintext pz;
+        encoder.encode(y, r2.parms_id(), std::pow(2.0, 20), pz);
+        ref.multiply_plain_inplace(r2, pz);
+        gpu.multiply_plain_inplace(g2, pz);
+        CHECK(same_ct(r2, g2));
+        Plaintext low;
+        encoder.encode(y, r1.parms_id(), scale, low); // one level down: parameter mismatch with cx
+        auto a = outcome([&] { Ciphertext t = cx; ref.multiply_plain_inplace(t, low); });
+        auto b = outcome([&] { Ciphertext t = cx; gpu.multiply_plain_inplace(t, low); });
+        CHECK(a == b && a == "invalid_argument");
+        Plaintext big;
+        encoder.encode(y, std::pow(2.0, 120), big);
+        a = outcome([&] { Ciphertext t = cx; ref.multiply_plain_inplace(t, big); });
+        b = outcome([&] { Ciphertext t = cx; gpu.multiply_plain_inplace(t, big); });
+        CHECK(a == b && a == "invalid_argument"); // scale out of bounds
+    }
     for (int step : { 1, -4, 5, 1023 })
     {
         Ciphertext r2, g2;
@@ -288,6 +312,29 @@ static void test_bfv()
         ref.transform_to_ntt_inplace(r2);
         gpu.transform_to_ntt_inplace(g2);
         CHECK(same_ct(r2, g2));
+    }
+    {
+        // multiply_plain with an NTT-form plaintext: ciphertext in NTT form (:1991-1994) and in coefficient form (:2006-2011)
+        Plaintext pn = py;
+        ref.transform_to_ntt_inplace(pn, cx.parms_id());
+        Ciphertext r2, g2;
+        ref.multiply_plain(cx, pn, r2);
+        gpu.multiply_plain(cx, pn, g2);
+        CHECK(same_ct(r2, g2));
+        Plaintext p;
+        decryptor.decrypt(g2, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == (x[i] * y[i]) % t;
+        CHECK(ok);
+        Ciphertext rn, gn;
+        ref.transform_to_ntt(cx, rn);
+        gn = rn;
+        ref.multiply_plain_inplace(rn, pn);
+        gpu.multiply_plain_inplace(gn, pn);
+        CHECK(same_ct(rn, gn));
     }
     {
         Ciphertext bad = cx;

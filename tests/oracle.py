@@ -156,6 +156,13 @@ class Oracle:
         lib().orc_linear(self.h, mode, L, a.shape[0], _p(a), _p(bb), _p(out))
         return out
 
+    def multiply_plain(self, L, a, plain):
+        lib().orc_multiply_plain_ntt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
+        a, plain = np.ascontiguousarray(a), np.ascontiguousarray(plain)
+        out = np.zeros_like(a)
+        lib().orc_multiply_plain_ntt(self.h, L, a.shape[0], _p(a), _p(plain), _p(out))
+        return out
+
     def relinearize(self, L, c3, key):
         out = np.zeros((2, L, self.n), dtype=np.uint64)
         lib().orc_relinearize(self.h, L, _p(c3), _p(key), _p(out))

@@ -46,6 +46,7 @@ def lib():
         L.sealref_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_square.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.sealref_linear.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
+        L.sealref_multiply_plain_ntt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.sealref_multiply_relin.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_rescale.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
@@ -168,6 +169,12 @@ class RefContext:
         out = np.zeros_like(a)
         bb = np.ascontiguousarray(b) if b is not None else a
         self._chk(lib().sealref_linear(self.h, mode, L, a.shape[0], _p(a), _p(bb), _p(out)))
+        return out
+
+    def multiply_plain(self, L, a, plain):
+        a, plain = np.ascontiguousarray(a), np.ascontiguousarray(plain)
+        out = np.zeros_like(a)
+        self._chk(lib().sealref_multiply_plain_ntt(self.h, L, a.shape[0], _p(a), _p(plain), _p(out)))
         return out
 
     def relinearize(self, L, c3):

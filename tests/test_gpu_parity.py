@@ -253,6 +253,33 @@ def test_linear_ops_and_square_vs_reference(scheme):
     assert (ctx.add(a3, a3)[1] == rc.linear(0, L, a3[1], a3[1])).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv"])
+def test_multiply_plain_vs_reference(scheme):
+    # multiply_plain, NTT path (evaluator.cpp:2157-2195); one plaintext per ciphertext
+    n, batch = 4096, 5
+    mods = R.coeff_modulus_create(n, [50, 45, 60])
+    t = R.plain_modulus_batching(n, 20) if scheme == "bfv" else 0
+    sid = sb().BFV if scheme == "bfv" else sb().CKKS
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    rng = np.random.default_rng(37)
+    for L, size in ((2, 2), (2, 3), (1, 2)):
+        a = rand_ct(rng, mods, n, size, L, batch)
+        plain = rand_ct(rng, mods, n, 1, L, batch)[:, 0]
+        got = ctx.multiply_plain(a, plain)
+        for i in range(batch):
+            assert (got[i] == rc.multiply_plain(L, a[i], plain[i])).all()
+    # device entry point, in place
+    import torch
+
+    da = torch.from_numpy(a.view(np.int64)).cuda()
+    dp = torch.from_numpy(np.ascontiguousarray(plain).view(np.int64)).cuda()
+    ctx.d_multiply_plain(da, dp, da, L, size, batch)
+    torch.cuda.synchronize()
+    assert (da.cpu().numpy().view(np.uint64) == got).all()
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

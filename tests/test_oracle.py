@@ -148,3 +148,20 @@ def test_oracle_linear_and_square_vs_live_reference():
     t = R.plain_modulus_batching(n, 17)
     rb, ob = R.RefContext(R.BFV, n, mods, t), O.Oracle(O.BFV, n, mods, t)
     assert (rb.square(L, a) == ob.multiply(L, a, a)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv"])
+def test_oracle_multiply_plain_vs_live_reference(scheme):
+    # Evaluator::multiply_plain with ciphertext and plaintext both in NTT form (evaluator.cpp:2157-2195)
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42, 43])
+    t = R.plain_modulus_batching(n, 17) if scheme == "bfv" else 0
+    sid = R.BFV if scheme == "bfv" else R.CKKS
+    rc, oc = R.RefContext(sid, n, mods, t), O.Oracle(sid, n, mods, t)
+    rng = np.random.default_rng(23)
+    for L in (3, 1):
+        for size in (2, 3):
+            a = rand_ct(rng, mods, n, size, L)
+            plain = rand_ct(rng, mods, n, 1, L)[0]
+            assert (rc.multiply_plain(L, a, plain) == oc.multiply_plain(L, a, plain)).all()

@@ -59,6 +59,9 @@ def main():
         res["multiply"] = batch / timeit(lambda: ctx.d_multiply(a, b, o3, L, batch)) * 1e3
         res["relinearize"] = batch / timeit(lambda: ctx.d_relinearize(o3, key, o2, L, batch)) * 1e3
         res["multiply+relinearize"] = batch / timeit(lambda: ctx.d_multiply_relinearize(a, b, key, o2, L, batch)) * 1e3
+        ms = timeit(lambda: ctx.d_multiply_plain(a, b, o2, L, 2, batch))  # b's first [batch][L][n] words serve as the plaintexts
+        res["multiply_plain"] = batch / ms * 1e3
+        res["multiply_plain_GBps"] = batch * 5 * L * n * 8 / (ms * 1e-3) / 1e9
         elt = ctx.galois_elt_from_step(1)
         res["rotate (1 step)"] = batch / timeit(lambda: ctx.d_apply_galois(a, elt, key, o2, L, batch)) * 1e3
         if L > 1:
@@ -74,5 +77,45 @@ def main():
     return rows
 
 
+# the reference on ONE core (survey container), ops/s, for scale only
+CPU_1CORE = {
+    "cfg1": {"multiply": 277.8, "relinearize": 1041.7, "multiply+relinearize": 219.3, "rotate (1 step)": 1408.5, "ct NTT+INTT": 3225.8},
+    "cfg2": {"multiply": 2083.3, "relinearize": 416.7, "multiply+relinearize": 347.2, "rotate (1 step)": 434.8,
+             "rescale/mod_switch": 1041.7, "ct NTT+INTT": 833.3},
+    "cfg3": {"multiply": 82.6, "relinearize": 5.8, "multiply+relinearize": 5.5, "rotate (1 step)": 4.4, "rescale/mod_switch": 37.7,
+             "ct NTT+INTT": 21.8},
+    "cfg4": {"multiply": 19.3, "relinearize": 46.9, "multiply+relinearize": 13.7, "rotate (1 step)": 48.3, "ct NTT+INTT": 163.9},
+    "cfg5": {"multiply": 21.0, "relinearize": 0.7, "multiply+relinearize": 0.7, "rotate (1 step)": 0.8, "rescale/mod_switch": 8.1,
+             "ct NTT+INTT": 7.4},
+}
+HBM_PEAK_GBPS = 6571.6  # MEASURED_PEAKS.json
+
+
+def table(rows):
+    """markdown for profiles/r01_ops_table.md from the JSON lines main() prints"""
+    out = ["# Round 1: device-resident throughput of every hot-path op at the BASELINE.json config shapes", "",
+           "`python tools/bench_ops.py` on one B200 (CUDA events, 3 repetitions after a warm-up, uniform-random ciphertexts and "
+           "synthetic keys resident in HBM); table written by `python tools/bench_ops.py --table <json lines>`.",
+           "`cpu x1` = the reference on ONE core as measured in BASELINE.md section 2 (survey container), for scale only; "
+           "the contract benchmark is bench.py.", "",
+           "| config | batch | op | B200 ops/s | reference 1-core ops/s | ratio |", "|---|---|---|---|---|---|"]
+    for r in rows:
+        cpu = CPU_1CORE.get(r["config"][:4], {})
+        for op, v in r.items():
+            if op in ("config", "batch"):
+                continue
+            if op.endswith("_GBps"):
+                what = "NTT algorithmic GB/s (2*n*8 B per row per transform)" if op == "ntt_GBps" else \
+                    "multiply_plain algorithmic GB/s (5*L*n*8 B per size-2 ciphertext)"
+                out.append(f"| {r['config']} | {r['batch']} | {what} | {v:.0f} | | {v / HBM_PEAK_GBPS:.2f} of HBM peak |")
+            else:
+                c = cpu.get(op)
+                out.append(f"| {r['config']} | {r['batch']} | {op} | {v:.0f} | {c if c else '-'} | {f'{v / c:.0f}x' if c else '-'} |")
+    return "\n".join(out) + "\n"
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 3 and sys.argv[1] == "--table":
+        sys.stdout.write(table([json.loads(ln) for ln in open(sys.argv[2]) if ln.startswith("{")]))
+    else:
+        main()
