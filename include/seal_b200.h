@@ -35,6 +35,7 @@ extern "C" {
 
 #define SB200_SCHEME_BFV 1  /* seal::scheme_type::bfv  (encryptionparams.h) */
 #define SB200_SCHEME_CKKS 2 /* seal::scheme_type::ckks */
+#define SB200_SCHEME_BGV 3  /* seal::scheme_type::bgv: NTT-form ciphertexts like CKKS, plain-modulus-aware mod-down */
 
 typedef struct sb200_context sb200_context;   /* mirrors SEALContext + Evaluator state (context.h:277-439) */
 typedef struct sb200_kswitch_key sb200_kswitch_key; /* one KSwitchKeys::data()[index] entry on the device (kswitchkeys.h) */
@@ -45,7 +46,7 @@ const char *sb200_last_error(void);
 /* ---- context ------------------------------------------------------------------------------------------------
  * Replaces SEALContext(parms, expand_mod_chain=true, sec_level_type::none) + Evaluator(context) for this path
  * (context.cpp:495-563, evaluator.cpp:121-128).  coeff_modulus = the k key-level primes (last = special prime),
- * each < 2^61, prime, = 1 mod 2n.  plain_modulus is used by BFV only.  All NTT / RNS / Galois tables are computed
+ * each < 2^61, prime, = 1 mod 2n.  plain_modulus is used by BFV and BGV (BGV: coprime to every prime, rns.cpp:778-787).  All NTT / RNS / Galois tables are computed
  * here from these numbers alone and uploaded to CUDA device `device`. */
 int sb200_context_create(int scheme, size_t poly_modulus_degree, const uint64_t *coeff_modulus, size_t k,
                          uint64_t plain_modulus, int device, sb200_context **out);

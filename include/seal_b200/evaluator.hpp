@@ -35,11 +35,11 @@ namespace seal_b200
             for (auto &m : parms.coeff_modulus())
                 q.push_back(m.value());
             scheme_ = parms.scheme();
-            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::ckks)
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::ckks && scheme_ != seal::scheme_type::bgv)
                 throw std::invalid_argument("unsupported scheme");
             check(sb200_context_create(
                 static_cast<int>(scheme_), parms.poly_modulus_degree(), q.data(), q.size(),
-                scheme_ == seal::scheme_type::bfv ? parms.plain_modulus().value() : 0, device, &ctx_));
+                scheme_ != seal::scheme_type::ckks ? parms.plain_modulus().value() : 0, device, &ctx_));
         }
         ~Evaluator()
         {
@@ -61,10 +61,10 @@ namespace seal_b200
                 throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
             if (!pool)
                 throw std::invalid_argument("pool is uninitialized");
-            const bool ckks = scheme_ == seal::scheme_type::ckks;
-            if (ckks && !(encrypted1.is_ntt_form() && encrypted2.is_ntt_form()))
-                throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form"); // :571-574
-            if (!ckks && (encrypted1.is_ntt_form() || encrypted2.is_ntt_form()))
+            const bool ckks = scheme_ == seal::scheme_type::ckks, bgv = scheme_ == seal::scheme_type::bgv;
+            if ((ckks || bgv) && !(encrypted1.is_ntt_form() && encrypted2.is_ntt_form()))
+                throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form"); // :571-574, :712-715
+            if (!(ckks || bgv) && (encrypted1.is_ntt_form() || encrypted2.is_ntt_form()))
                 throw std::invalid_argument("encrypted1 or encrypted2 cannot be in NTT form"); // :397-400
             if (encrypted1.size() != 2 || encrypted2.size() != 2)
                 throw std::invalid_argument("seal_b200: multiply is implemented for size-2 ciphertexts");
@@ -78,6 +78,9 @@ namespace seal_b200
             check(sb200_multiply_host(ctx_, L, 1, a.data(), encrypted2.data(), encrypted1.data()));
             if (ckks)
                 encrypted1.scale() = new_scale;
+            if (bgv) // :838-840
+                encrypted1.correction_factor() = seal::util::multiply_uint_mod(
+                    encrypted1.correction_factor(), encrypted2.correction_factor(), cd->parms().plain_modulus());
             throw_if_transparent(encrypted1);
         }
         void multiply(const seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, seal::Ciphertext &destination,
@@ -274,7 +277,7 @@ namespace seal_b200
         void rotate_rows_inplace(seal::Ciphertext &encrypted, int steps, const seal::GaloisKeys &galois_keys,
                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
         {
-            if (scheme_ != seal::scheme_type::bfv)
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::bgv) // evaluator.h:1076-1080, 1145-1149
                 throw std::logic_error("unsupported scheme");
             rotate_internal(encrypted, steps, galois_keys, std::move(pool));
         }
@@ -287,7 +290,7 @@ namespace seal_b200
         void rotate_columns_inplace(seal::Ciphertext &encrypted, const seal::GaloisKeys &galois_keys,
                                     seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
         {
-            if (scheme_ != seal::scheme_type::bfv)
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::bgv) // evaluator.h:1076-1080, 1145-1149
                 throw std::logic_error("unsupported scheme");
             conjugate_internal(encrypted, galois_keys, std::move(pool));
         }
@@ -363,7 +366,7 @@ namespace seal_b200
             if (relin_keys.parms_id() != context_.key_parms_id())
                 throw std::invalid_argument("relin_keys is not valid for encryption parameters");
             const std::size_t B = a.size(), L = a[0].coeff_modulus_size(), n = a[0].poly_modulus_degree(), w = 2 * L * n;
-            const bool ckks = scheme_ == seal::scheme_type::ckks;
+            const bool ckks = scheme_ == seal::scheme_type::ckks, ntt = scheme_ != seal::scheme_type::bfv;
             auto cd = context_.get_context_data(a[0].parms_id());
             std::vector<std::uint64_t> ha(B * w), hb(B * w), ho(B * w);
             for (std::size_t i = 0; i < B; i++)
@@ -372,7 +375,7 @@ namespace seal_b200
                 validate(b[i], "encrypted2 is not valid for encryption parameters");
                 if (a[i].parms_id() != a[0].parms_id() || b[i].parms_id() != a[0].parms_id())
                     throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
-                if (a[i].size() != 2 || b[i].size() != 2 || a[i].is_ntt_form() != ckks || b[i].is_ntt_form() != ckks)
+                if (a[i].size() != 2 || b[i].size() != 2 || a[i].is_ntt_form() != ntt || b[i].is_ntt_form() != ntt)
                     throw std::invalid_argument("batch entries must be fresh size-2 ciphertexts in the scheme's native form");
                 if (ckks && !scale_within_bounds(a[i].scale() * b[i].scale(), *cd))
                     throw std::invalid_argument("scale out of bounds");
@@ -388,6 +391,9 @@ namespace seal_b200
                 std::memcpy(destination[i].data(), ho.data() + i * w, w * sizeof(std::uint64_t));
                 if (ckks)
                     destination[i].scale() = a[i].scale() * b[i].scale();
+                if (scheme_ == seal::scheme_type::bgv)
+                    destination[i].correction_factor() = seal::util::multiply_uint_mod(
+                        a[i].correction_factor(), b[i].correction_factor(), cd->parms().plain_modulus());
                 throw_if_transparent(destination[i]);
             }
         }
@@ -408,6 +414,8 @@ namespace seal_b200
                 throw std::invalid_argument("scale mismatch");
             if (encrypted1.size() != encrypted2.size())
                 throw std::invalid_argument("seal_b200: add/sub are implemented for equal-size ciphertexts");
+            if (encrypted1.correction_factor() != encrypted2.correction_factor()) // BGV rebalancing, evaluator.cpp:188-209
+                throw std::invalid_argument("seal_b200: add/sub are implemented for equal correction factors");
             const std::size_t L = encrypted1.coeff_modulus_size();
             check(subtract ? sb200_sub_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data())
                            : sb200_add_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data()));
@@ -461,6 +469,8 @@ namespace seal_b200
                 throw std::invalid_argument("BFV encrypted cannot be in NTT form");
             if (scheme_ == seal::scheme_type::ckks && !encrypted.is_ntt_form())
                 throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (scheme_ == seal::scheme_type::bgv && !encrypted.is_ntt_form())
+                throw std::invalid_argument("BGV encrypted must be in NTT form");
         }
         // uploads KSwitchKeys::data()[index] once (keys are immutable after generation) -- evaluator.cpp:2586-2648
         sb200_kswitch_key *key_for(const seal::KSwitchKeys &keys, std::size_t index, std::size_t L) const
@@ -494,10 +504,12 @@ namespace seal_b200
         {
             auto cd = context_.get_context_data(encrypted.parms_id());
             auto next = cd->next_context_data();
-            const bool ckks = scheme_ == seal::scheme_type::ckks;
+            const bool ckks = scheme_ == seal::scheme_type::ckks, bgv = scheme_ == seal::scheme_type::bgv;
             if (ckks && !encrypted.is_ntt_form())
                 throw std::invalid_argument("CKKS encrypted must be in NTT form");
-            if (!ckks && encrypted.is_ntt_form())
+            if (bgv && !encrypted.is_ntt_form())
+                throw std::invalid_argument("BGV encrypted must be in NTT form"); // :1214-1217
+            if (!ckks && !bgv && encrypted.is_ntt_form())
                 throw std::invalid_argument("BFV encrypted cannot be in NTT form");
             if (encrypted.size() != 2)
                 throw std::invalid_argument("seal_b200: modulus switching is implemented for size-2 ciphertexts");
@@ -513,11 +525,15 @@ namespace seal_b200
             const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
             std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 2 * L * n);
             const bool ntt = encrypted.is_ntt_form();
+            const std::uint64_t correction = encrypted.correction_factor();
             destination.resize(context_, next->parms_id(), 2);
             check(rescale ? sb200_rescale_to_next_host(ctx_, L, 1, in.data(), destination.data())
                           : sb200_mod_switch_to_next_host(ctx_, L, 1, in.data(), destination.data()));
             destination.is_ntt_form() = ntt;
             destination.scale() = scale;
+            if (bgv) // :1288-1293
+                destination.correction_factor() =
+                    seal::util::multiply_uint_mod(correction, cd->rns_tool()->inv_q_last_mod_t(), next->parms().plain_modulus());
             throw_if_transparent(destination);
         }
         // evaluator.cpp:2504-2559

@@ -399,7 +399,29 @@ void orc_switch_key(const orc_ctx *c, size_t L, u64 *ct, const u64 *target, cons
     }
     /* :2806-2864 mod-down by the special prime, added into ct */
     u64 qk = c->q[sp], half = qk >> 1;
-    for (size_t comp = 0; comp < 2; comp++)
+    for (size_t comp = 0; comp < 2 && c->scheme == ORC_BGV; comp++)
+    {
+        /* :2762-2805 BGV: subtract c + k*qk with k = -c * qk^-1 mod t, so the quotient stays = 0 mod t */
+        u64 *last = prod + (comp * (L + 1) + L) * n, t = c->t, inv_t = 0;
+        ntt_inv(&c->tab[sp], n, last);
+        invmod(qk % t, t, &inv_t); /* RNSTool::inv_q_last_mod_t of the key level, rns.cpp:778-787 */
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 q = c->q[i], inv = 0;
+            u64 *acc = prod + (comp * (L + 1) + i) * n;
+            for (size_t j = 0; j < n; j++)
+            {
+                u64 k = mulmod(submod(0, last[j] % t, t), inv_t, t);                /* :2773-2779 */
+                tmp[j] = addmod(mulmod(k % q, qk % q, q), last[j] % q, q);          /* :2785-2794 */
+            }
+            ntt_fwd(&c->tab[i], n, tmp); /* :2795 */
+            invmod(qk % q, q, &inv);
+            u64 *dst = ct + (comp * L + i) * n;
+            for (size_t j = 0; j < n; j++)
+                dst[j] = addmod(dst[j], mulmod(submod(acc[j], tmp[j], q), inv, q), q); /* :2796-2802 */
+        }
+    }
+    for (size_t comp = 0; comp < 2 && c->scheme != ORC_BGV; comp++)
     {
         u64 *last = prod + (comp * (L + 1) + L) * n;
         ntt_inv(&c->tab[sp], n, last);
@@ -456,6 +478,36 @@ void orc_rescale(const orc_ctx *c, size_t L, const u64 *in2, u64 *out2)
             u64 *dst = out2 + (p * (L - 1) + i) * n;
             for (size_t j = 0; j < n; j++)
                 dst[j] = mulmod(submod(src[j], tmp[j], q), inv, q);
+        }
+    }
+    free(last), free(tmp);
+}
+
+/* BGV mod_switch_to_next: mod_t_and_divide_q_last_ntt_inplace, rns.cpp:1193-1236 + evaluator.cpp:1263-1279 */
+void orc_bgv_mod_switch(const orc_ctx *c, size_t L, const u64 *in2, u64 *out2)
+{
+    size_t n = c->n;
+    u64 ql = c->q[L - 1], t = c->t, inv_t = 0;
+    invmod(ql % t, t, &inv_t); /* inv_q_last_mod_t of this level, rns.cpp:778-787 */
+    u64 *last = (u64 *)malloc(n * sizeof(u64)), *tmp = (u64 *)malloc(n * sizeof(u64));
+    for (size_t p = 0; p < 2; p++)
+    {
+        memcpy(last, in2 + (p * L + L - 1) * n, n * sizeof(u64));
+        ntt_inv(&c->tab[L - 1], n, last);
+        for (size_t i = 0; i + 1 < L; i++)
+        {
+            u64 q = c->q[i], inv = 0;
+            invmod(ql % q, q, &inv);
+            for (size_t j = 0; j < n; j++)
+            {
+                u64 k = mulmod(submod(0, last[j] % t, t), inv_t, t);       /* :1205-1213 */
+                tmp[j] = addmod(mulmod(k % q, ql % q, q), last[j] % q, q); /* :1219-1228 */
+            }
+            ntt_fwd(&c->tab[i], n, tmp);
+            const u64 *src = in2 + (p * L + i) * n;
+            u64 *dst = out2 + (p * (L - 1) + i) * n;
+            for (size_t j = 0; j < n; j++)
+                dst[j] = mulmod(submod(src[j], tmp[j], q), inv, q); /* :1229-1234 */
         }
     }
     free(last), free(tmp);

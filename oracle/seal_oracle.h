@@ -24,6 +24,7 @@ extern "C" {
 
 #define ORC_BFV 1
 #define ORC_CKKS 2
+#define ORC_BGV 3 /* NTT-form ciphertexts like CKKS (orc_ckks_multiply is bgv_multiply's tensor, evaluator.cpp:710-841) */
 #define ORC_MAX_PRIMES 64
 
 typedef struct orc_ctx orc_ctx;
@@ -34,7 +35,7 @@ int orc_get_primes(uint64_t factor, int bit_size, size_t count, uint64_t *out); 
 int orc_minimal_primitive_root(uint64_t degree, uint64_t q, uint64_t *root);              /* numth.cpp:340-412 */
 int orc_coeff_modulus_create(size_t n, const int *bits, size_t k, uint64_t *out);         /* modulus.cpp:144-184 */
 
-/* context: moduli = the key-level coeff_modulus (k primes, last = special prime); t = plain modulus (BFV) */
+/* context: moduli = the key-level coeff_modulus (k primes, last = special prime); t = plain modulus (BFV, BGV) */
 orc_ctx *orc_create(int scheme, size_t n, const uint64_t *moduli, size_t k, uint64_t t);
 void orc_destroy(orc_ctx *c);
 /* tables of prime i, ntt.cpp:241-300 */
@@ -69,6 +70,7 @@ void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct2, const uint64_t *t
 void orc_relinearize(const orc_ctx *c, size_t L, const uint64_t *in3, const uint64_t *key, uint64_t *out2); /* evaluator.cpp:1144-1199 */
 void orc_rescale(const orc_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2);        /* CKKS; rns.cpp:830-901, evaluator.cpp:1201-1294 */
 void orc_bfv_mod_switch(const orc_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2); /* BFV; rns.cpp:789-828 */
+void orc_bgv_mod_switch(const orc_ctx *c, size_t L, const uint64_t *in2, uint64_t *out2); /* BGV; rns.cpp:1193-1236 */
 void orc_apply_galois(const orc_ctx *c, size_t L, const uint64_t *in2, uint32_t galois_elt, const uint64_t *key, uint64_t *out2); /* evaluator.cpp:2384-2502 */
 uint32_t orc_galois_elt_from_step(size_t n, int step);                                    /* galois.cpp:53-95 */
 /* bare permutations (galois.cpp:148-218) on one row */

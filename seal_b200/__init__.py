@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-BFV, CKKS = 1, 2
+BFV, CKKS, BGV = 1, 2, 3
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseal_b200.so")
 _u64p = C.POINTER(C.c_uint64)

@@ -309,7 +309,7 @@ int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a
     SB_ENTER(ctx)
     check_level(c, L, batch);
     auto st = static_cast<cudaStream_t>(stream);
-    if (c.scheme == SB200_SCHEME_CKKS)
+    if (c.scheme != SB200_SCHEME_BFV) // CKKS and BGV share the NTT-form tensor (evaluator.cpp:569-708, :710-841)
         op_ckks_multiply(c, L, batch, (const u64 *)a, (const u64 *)b, (u64 *)out3, st);
     else
         op_bfv_multiply(c, L, batch, (const u64 *)a, (const u64 *)b, (u64 *)out3, st);
@@ -558,7 +558,7 @@ int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64
     check_level(c, L, batch);
     const size_t w = L * c.n;
     HostPipe(c).run(batch, 2 * w, 2 * w, 3 * w, a, b, out3, [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
-        if (c.scheme == SB200_SCHEME_CKKS)
+        if (c.scheme != SB200_SCHEME_BFV)
             op_ckks_multiply(c, L, B, da, db, dout, st);
         else
             op_bfv_multiply(c, L, B, da, db, dout, st);

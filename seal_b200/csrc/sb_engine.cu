@@ -36,6 +36,7 @@ namespace sb
             cudaFree(kv.second);
         cudaFree(d_primes);
         cudaFree(d_invq);
+        cudaFree(d_qmod);
         cudaFree(scratch);
         cudaFree(aux_buf);
         for (auto &slot : io.buf)
@@ -130,7 +131,7 @@ namespace sb
 
     std::unique_ptr<Context> make_context(int scheme, size_t n, const u64 *moduli, size_t k, u64 t, int device)
     {
-        if (scheme != 1 && scheme != 2)
+        if (scheme != 1 && scheme != 2 && scheme != 3)
             throw std::invalid_argument("unsupported scheme");
         if (n < 2 || (n & (n - 1)) || n > 131072)
             throw std::invalid_argument("poly_modulus_degree is invalid");
@@ -170,6 +171,20 @@ namespace sb
             // all levels use prefixes of one auxiliary list: [m_sk, gamma, B_0, B_1, ...]  (rns.cpp:626-632)
             size_t max_nb = (k > 1 ? k - 1 : 1) + 1;
             c->aux = sbh::get_primes(2 * static_cast<u64>(n), 61, max_nb + 2);
+        }
+        if (scheme == 3)
+        {
+            // BGV: q_j^-1 mod t for every prime (RNSTool::inv_q_last_mod_t of each level, rns.cpp:778-787)
+            if (t < 2 || (t >> 60))
+                throw std::invalid_argument("plain_modulus is invalid");
+            c->t_ratio = static_cast<u64>((static_cast<unsigned __int128>(1) << 64) / t);
+            for (size_t j = 0; j < k; j++)
+            {
+                u64 v = 0;
+                if (!sbh::invmod(c->q[j] % t, t, v))
+                    throw std::logic_error("invalid rns bases");
+                c->inv_q_mod_t.push_back(v);
+            }
         }
         std::vector<PrimeDev> hp;
         c->tabs.resize(k + c->aux.size());
@@ -211,6 +226,20 @@ namespace sb
         cuda_check(cudaMalloc(&c->d_invq, invq.size() * sizeof(Tw)), "cudaMalloc(invq)");
         cuda_check(cudaMemcpy(c->d_invq, invq.data(), invq.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload invq");
         c->table_bytes += hp.size() * sizeof(PrimeDev) + invq.size() * sizeof(Tw);
+        if (scheme == 3)
+        {
+            // q_j mod q_i with its Shoup quotient (the "k * q_last" term of the BGV mod-down, rns.cpp:1222-1224)
+            std::vector<Tw> qmod(k * k);
+            for (size_t j = 0; j < k; j++)
+                for (size_t i = 0; i < k; i++)
+                {
+                    const u64 v = c->q[j] % c->q[i];
+                    qmod[j * k + i] = Tw{ v, sbh::shoup(v, c->q[i]) };
+                }
+            cuda_check(cudaMalloc(&c->d_qmod, qmod.size() * sizeof(Tw)), "cudaMalloc(qmod)");
+            cuda_check(cudaMemcpy(c->d_qmod, qmod.data(), qmod.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload qmod");
+            c->table_bytes += qmod.size() * sizeof(Tw);
+        }
         return c;
     }
 
@@ -762,6 +791,10 @@ namespace sb
         long long bstride, pstride;
         u64 *U;                  // [B][2][n]
         int logn, pid_top;
+        // BGV (evaluator.cpp:2770-2779, rns.cpp:1202-1213): U = the canonical top component, K = -U * q_top^-1 mod t
+        u64 *K = nullptr;
+        u64 t = 0, t_ratio = 0;
+        Tw inv_top_mod_t = { 0, 0 };
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int) const { return pid_top; }
         __device__ __forceinline__ const u64 *rowp(int row) const { return src + (row >> 1) * bstride + (row & 1) * pstride; }
@@ -780,6 +813,13 @@ namespace sb
         __device__ __forceinline__ u64 *mid(int row) const { return U + (static_cast<long long>(row) << logn); }
         __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
         {
+            if (K)
+            {
+                const u64 u = csub(v, P.q), r = barrett64(u, t, t_ratio);
+                mid(row)[idx] = u;
+                K[(static_cast<long long>(row) << logn) + idx] = mul_shoup(r ? t - r : 0, inv_top_mod_t, t);
+                return;
+            }
             mid(row)[idx] = csub(csub(v, P.q) + (P.q >> 1), P.q);
         }
         __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
@@ -904,6 +944,25 @@ namespace sb
         }
     };
 
+    // BGV: the correction polynomial is delta = (U mod q_i) + (K mod q_i) * (q_top mod q_i) instead of (u mod q_i) - half
+    // (evaluator.cpp:2762-2805, rns.cpp:1216-1235); the transform and the epilogue are the ones above.
+    struct OpModDownFwdBgv : OpModDownFwd
+    {
+        const u64 *K;            // [B][2][n]: -U * q_top^-1 mod t
+        const Tw *qtop_mod;      // q_top mod q_i, i < Lout
+        u64 t;
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
+        {
+            const long long e = (static_cast<long long>(row / Lout) << logn) + idx;
+            u64 u = U[e], kk = K[e];
+            if (q_top > P.q)
+                u = barrett64(u, P.q, P.ratio_hi);
+            if (t > P.q)
+                kk = barrett64(kk, P.q, P.ratio_hi);
+            return u + mul_shoup(kk, qtop_mod[row % Lout], P.q); // < 2q
+        }
+    };
+
     // coefficient-form mod-down (BFV): evaluator.cpp:2819-2864 (bfv branch) and rns.cpp:789-828 (mod_switch).
     // ADD_HALF: U holds the raw top component (mod_switch); otherwise U already includes + half (key switch).
     template <bool ADD_HALF>
@@ -935,11 +994,11 @@ namespace sb
 
     struct KsScratch
     {
-        u64 *D, *E, *Pp, *U, *T, *C2;
+        u64 *D, *E, *Pp, *U, *K, *T, *C2;
     };
     static size_t ks_words_per_ct(const Context &c, size_t L, bool need_c2)
     {
-        return c.n * (L + (L + 1) * L + 2 * (L + 1) + 2 + 2 * L + (need_c2 ? L : 0));
+        return c.n * (L + (L + 1) * L + 2 * (L + 1) + 4 + 2 * L + (need_c2 ? L : 0));
     }
     static KsScratch ks_carve(Context &c, size_t L, size_t B, bool need_c2)
     {
@@ -949,6 +1008,7 @@ namespace sb
         s.E = p, p += B * (L + 1) * L * c.n;
         s.Pp = p, p += B * 2 * (L + 1) * c.n;
         s.U = p, p += B * 2 * c.n;
+        s.K = p, p += B * 2 * c.n;
         s.T = p, p += B * 2 * L * c.n;
         s.C2 = need_c2 ? p : nullptr;
         return s;
@@ -976,12 +1036,19 @@ namespace sb
             throw std::invalid_argument("kswitch_keys inner dimension is too small"); // evaluator.cpp:2635-2638
     }
 
+    // BGV: make the top-component INTT also emit K = -U * q_top^-1 mod t
+    static void bgv_top(const Context &c, OpTopIntt &op, u64 *K, size_t top)
+    {
+        op.K = K, op.t = c.t, op.t_ratio = c.t_ratio;
+        op.inv_top_mod_t = Tw{ c.inv_q_mod_t[top], sbh::shoup(c.inv_q_mod_t[top], c.t) };
+    }
+
     // ct[b] (= base) += key-switch(target[b]) for a chunk of B ciphertexts; writes out[b][2][L][n].
     static void key_switch_chunk(Context &c, size_t L, size_t B, const KsScratch &s, Src target, const KSwitchKey &key, BaseSrc base,
                                  u64 *out, cudaStream_t st)
     {
         const int n = static_cast<int>(c.n), Li = static_cast<int>(L), ki = static_cast<int>(c.k);
-        const bool ntt_in = (c.scheme != 1);
+        const bool ntt_in = (c.scheme != 1), bgv = (c.scheme == 3);
         Src dsrc = target;
         if (ntt_in)
         {
@@ -1051,11 +1118,19 @@ namespace sb
         const long long pp_ps = static_cast<long long>(L + 1) * n, pp_bs = 2 * pp_ps;
         {
             OpTopIntt op{ s.Pp + static_cast<long long>(L) * n, pp_bs, pp_ps, s.U, c.logn, ki - 1 };
+            if (bgv)
+                bgv_top(c, op, s.K, c.k - 1);
             cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "ks_top_intt"), "ks top intt");
         }
         const Tw *inv_top = c.d_invq + (c.k - 1) * c.k;
         const long long o_ps = static_cast<long long>(L) * n, o_bs = 2 * o_ps;
-        if (ntt_in)
+        if (bgv)
+        {
+            OpModDownFwdBgv op{ { s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li },
+                                s.K, c.d_qmod + (c.k - 1) * c.k, c.t };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_moddown_ntt", -1, c.fast_q), "ks moddown ntt");
+        }
+        else if (ntt_in)
         {
             OpModDownFwd op{ s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li };
             cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_moddown_ntt", -1, c.fast_q), "ks moddown ntt");
@@ -1204,6 +1279,32 @@ namespace sb
             return;
         }
         const int n = static_cast<int>(c.n);
+        if (c.scheme == 3)
+        {
+            // BGV: mod_t_and_divide_q_last_ntt_inplace on both polynomials (evaluator.cpp:1263-1267, rns.cpp:1193-1236)
+            const size_t per = (4 + 2 * Lout) * c.n * sizeof(u64);
+            size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
+            chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (2 * L * c.n)));
+            for (size_t b0 = 0; b0 < batch; b0 += chunk)
+            {
+                size_t B = std::min(chunk, batch - b0);
+                u64 *U = static_cast<u64 *>(c.ensure_scratch(per * B));
+                u64 *K = U + B * 2 * c.n, *T = K + B * 2 * c.n;
+                const u64 *in = in2 + b0 * 2 * L * c.n;
+                const long long i_ps = static_cast<long long>(L) * n, i_bs = 2 * i_ps;
+                OpTopIntt top{ in + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
+                bgv_top(c, top, K, L - 1);
+                cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "modswitch_top_intt"), "mod switch intt");
+                BaseSrc none;
+                const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
+                OpModDownFwdBgv op{ { U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
+                                      c.logn, static_cast<int>(Lout) },
+                                    K, c.d_qmod + (L - 1) * c.k, c.t };
+                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "modswitch_ntt", -1, c.fast_q),
+                           "mod switch ntt");
+            }
+            return;
+        }
         const long long i_ps = static_cast<long long>(L) * n, o_ps = static_cast<long long>(Lout) * n;
         const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (2 * L * c.n));
         BaseSrc none;

@@ -49,6 +49,9 @@ namespace sb
         PrimeDev *d_primes = nullptr;        // [nprimes]
         size_t nprimes = 0;
         Tw *d_invq = nullptr;                // [k][k]: d_invq[j*k+i] = q_j^-1 mod q_i  (i != j)
+        Tw *d_qmod = nullptr;                // BGV, [k][k]: d_qmod[j*k+i] = q_j mod q_i
+        u64 t_ratio = 0;                     // BGV: floor(2^64 / t)
+        std::vector<u64> inv_q_mod_t;        // BGV: q_j^-1 mod t
         std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
         std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
         void *scratch = nullptr;

@@ -32,7 +32,7 @@ static bool same_ct(const Ciphertext &a, const Ciphertext &b)
         a.coeff_modulus_size() != b.coeff_modulus_size())
         return false;
     double sa = a.scale(), sb = b.scale();
-    if (std::memcmp(&sa, &sb, sizeof(double)) != 0)
+    if (std::memcmp(&sa, &sb, sizeof(double)) != 0 || a.correction_factor() != b.correction_factor())
         return false;
     return std::memcmp(a.data(), b.data(), a.size() * a.coeff_modulus_size() * a.poly_modulus_degree() * 8) == 0;
 }
@@ -351,12 +351,126 @@ static void test_bfv()
     }
 }
 
+// BGV -- NTT-form ciphertexts, correction factors, plain-modulus-aware mod-down
+static void test_bgv()
+{
+    EncryptionParameters parms(scheme_type::bgv);
+    const size_t n = 8192;
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::BFVDefault(n));
+    parms.set_plain_modulus(PlainModulus::Batching(n, 20));
+    SEALContext context(parms, true, sec_level_type::none);
+    KeyGenerator keygen(context);
+    RelinKeys rlk;
+    keygen.create_relin_keys(rlk);
+    GaloisKeys glk;
+    keygen.create_galois_keys(glk);
+    Encryptor encryptor(context, keygen.secret_key());
+    Decryptor decryptor(context, keygen.secret_key());
+    BatchEncoder encoder(context);
+    seal::Evaluator ref(context);
+    seal_b200::Evaluator gpu(context);
+    const uint64_t t = parms.plain_modulus().value();
+
+    std::mt19937_64 rng(11);
+    std::vector<uint64_t> x(n), y(n);
+    for (size_t i = 0; i < n; i++)
+        x[i] = rng() % 500, y[i] = rng() % 500;
+    Plaintext px, py;
+    encoder.encode(x, px);
+    encoder.encode(y, py);
+    Ciphertext cx, cy;
+    encryptor.encrypt_symmetric(px, cx);
+    encryptor.encrypt_symmetric(py, cy);
+    CHECK(cx.is_ntt_form());
+
+    Ciphertext r1, g1;
+    ref.multiply(cx, cy, r1);
+    gpu.multiply(cx, cy, g1);
+    CHECK(same_ct(r1, g1));
+    ref.relinearize_inplace(r1, rlk);
+    gpu.relinearize_inplace(g1, rlk);
+    CHECK(same_ct(r1, g1));
+    ref.mod_switch_to_next_inplace(r1);
+    gpu.mod_switch_to_next_inplace(g1);
+    CHECK(same_ct(r1, g1));
+    CHECK(g1.correction_factor() != 1); // q_last^-1 mod t entered the metadata (evaluator.cpp:1288-1293)
+    {
+        Plaintext p;
+        decryptor.decrypt(g1, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == (x[i] * y[i]) % t;
+        CHECK(ok);
+        CHECK(decryptor.invariant_noise_budget(g1) > 0);
+    }
+    {
+        // a second level: square of the switched product, relinearize, switch again
+        Ciphertext r2, g2;
+        ref.square(r1, r2);
+        gpu.square(g1, g2);
+        CHECK(same_ct(r2, g2));
+        ref.relinearize_inplace(r2, rlk);
+        gpu.relinearize_inplace(g2, rlk);
+        ref.mod_switch_to_next_inplace(r2);
+        gpu.mod_switch_to_next_inplace(g2);
+        CHECK(same_ct(r2, g2));
+        Plaintext p;
+        decryptor.decrypt(g2, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == ((x[i] * y[i]) % t) * ((x[i] * y[i]) % t) % t;
+        CHECK(ok);
+    }
+    for (int step : { 1, -3 })
+    {
+        Ciphertext r2, g2;
+        ref.rotate_rows(r1, step, glk, r2);
+        gpu.rotate_rows(g1, step, glk, g2);
+        CHECK(same_ct(r2, g2));
+    }
+    {
+        Ciphertext r2, g2;
+        ref.rotate_columns(cx, glk, r2);
+        gpu.rotate_columns(cx, glk, g2);
+        CHECK(same_ct(r2, g2));
+        std::vector<std::vector<Ciphertext>> out(1);
+        std::vector<Ciphertext> a(2, cx), b(2, cy);
+        gpu.multiply_relinearize(a, b, rlk, out[0]);
+        Ciphertext r;
+        ref.multiply(cx, cy, r);
+        ref.relinearize_inplace(r, rlk);
+        CHECK(same_ct(r, out[0][0]) && same_ct(r, out[0][1]));
+    }
+    {
+        auto a = outcome([&] { Ciphertext tt = cx; ref.rescale_to_next_inplace(tt); });
+        auto b = outcome([&] { Ciphertext tt = cx; gpu.rescale_to_next_inplace(tt); });
+        CHECK(a == b && a == "invalid_argument"); // unsupported operation for scheme type
+        Ciphertext bad = cx;
+        bad.is_ntt_form() = false;
+        a = outcome([&] { Ciphertext tt; ref.multiply(bad, cy, tt); });
+        b = outcome([&] { Ciphertext tt; gpu.multiply(bad, cy, tt); });
+        CHECK(a == b && a == "invalid_argument"); // :712-715
+        a = outcome([&] { Ciphertext tt = bad; ref.mod_switch_to_next_inplace(tt); });
+        b = outcome([&] { Ciphertext tt = bad; gpu.mod_switch_to_next_inplace(tt); });
+        CHECK(a == b && a == "invalid_argument"); // BGV encrypted must be in NTT form
+        a = outcome([&] { Ciphertext tt = cx; ref.rotate_vector_inplace(tt, 1, glk); });
+        b = outcome([&] { Ciphertext tt = cx; gpu.rotate_vector_inplace(tt, 1, glk); });
+        CHECK(a == b && a == "logic_error");
+    }
+}
+
 int main()
 {
     try
     {
         test_ckks();
         test_bfv();
+        test_bgv();
     }
     catch (const std::exception &e)
     {

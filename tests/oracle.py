@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _DIR = os.path.join(_HERE, "..", "oracle")
 _LIB_PATH = os.path.join(_DIR, "liboracle.so")
-BFV, CKKS = 1, 2
+BFV, CKKS, BGV = 1, 2, 3
 _u64p = C.POINTER(C.c_uint64)
 _lib = None
 
@@ -40,6 +40,7 @@ def lib():
         L.orc_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
         L.orc_rescale.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.orc_bfv_mod_switch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.orc_bgv_mod_switch.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.orc_apply_galois.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_uint32, _u64p, _u64p]
         L.orc_galois_elt_from_step.restype = C.c_uint32
         L.orc_galois_elt_from_step.argtypes = [C.c_size_t, C.c_int]
@@ -142,7 +143,7 @@ class Oracle:
 
     def multiply(self, L, a, b):
         out = np.zeros((3, L, self.n), dtype=np.uint64)
-        if self.scheme == CKKS:
+        if self.scheme != BFV:  # CKKS and BGV: the NTT-form tensor
             lib().orc_ckks_multiply(self.h, L, _p(a), _p(b), _p(out))
         else:
             assert lib().orc_bfv_multiply(self.h, L, _p(a), _p(b), _p(out)) == 0
@@ -179,6 +180,11 @@ class Oracle:
     def bfv_mod_switch(self, L, c2):
         out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
         lib().orc_bfv_mod_switch(self.h, L, _p(c2), _p(out))
+        return out
+
+    def bgv_mod_switch(self, L, c2):
+        out = np.zeros((2, L - 1, self.n), dtype=np.uint64)
+        lib().orc_bgv_mod_switch(self.h, L, _p(c2), _p(out))
         return out
 
     def apply_galois(self, L, c2, elt, key):

@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "..", "oracle", "_ref", "libsealref.so")
 
-BFV, CKKS = 1, 2
+BFV, CKKS, BGV = 1, 2, 3
 _u64p = C.POINTER(C.c_uint64)
 
 

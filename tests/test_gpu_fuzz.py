@@ -1,5 +1,5 @@
 """Randomised parity sweep (-m gpu): random ring sizes, prime counts / bit sizes (crossing the 57-bit guard-free boundary
-and the 4x digit-reduction boundary), levels and batch sizes, both schemes, against the plain-C oracle."""
+and the 4x digit-reduction boundary), levels and batch sizes, all three schemes, against the plain-C oracle."""
 import numpy as np
 import pytest
 
@@ -29,6 +29,14 @@ def _cases():
             bits[0], bits[-1] = 60, lo  # large spread: digit re-reduction must stay on
         scheme = "bfv" if i % 3 == 0 else "ckks"
         out.append((logn, tuple(bits), scheme, int(rng.integers(1, 5)), i))
+    for i in range(28, 38):  # BGV; odd seeds use a plain modulus above the small primes
+        logn = int(rng.choice([4, 8, 11, 12, 13, 14]))
+        k = int(rng.integers(2, 6))
+        lo = max(logn + 4, 20)
+        bits = [int(rng.integers(lo, 61)) for _ in range(k)]
+        if i % 5 == 0:
+            bits[0], bits[-1] = 60, lo
+        out.append((logn, tuple(bits), "bgv", int(rng.integers(1, 5)), i))
     return out
 
 
@@ -44,6 +52,8 @@ def test_random_config_vs_oracle(logn, bits, scheme, batch, seed):
     k = len(mods)
     t = 65537 if scheme == "bfv" else 0
     sid = sb().BFV if scheme == "bfv" else sb().CKKS
+    if scheme == "bgv":
+        t, sid = (2147483647 if seed % 2 else 65537), sb().BGV
     ctx = sb().Context(sid, n, mods, t)
     oc = O.Oracle(sid, n, mods, t)
     rng = np.random.default_rng(seed)
@@ -63,5 +73,7 @@ def test_random_config_vs_oracle(logn, bits, scheme, batch, seed):
     if L > 1:
         if scheme == "ckks":
             assert (ctx.rescale_to_next(a)[i] == oc.rescale(L, a[i])).all()
+        elif scheme == "bgv":
+            assert (ctx.mod_switch_to_next(a)[i] == oc.bgv_mod_switch(L, a[i])).all()
         else:
             assert (ctx.mod_switch_to_next(a)[i] == oc.bfv_mod_switch(L, a[i])).all()

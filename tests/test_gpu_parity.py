@@ -280,6 +280,42 @@ def test_multiply_plain_vs_reference(scheme):
     assert (da.cpu().numpy().view(np.uint64) == got).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("n,bits,t_bits,batch", [(4096, [50, 36, 45, 60], 20, 3), (4096, [50, 36, 45, 60], 38, 2),
+                                                  (256, [40, 36, 42, 43], 17, 3), (16384, [54, 54, 54, 54, 54], 20, 2)])
+def test_bgv_ops_vs_reference(n, bits, t_bits, batch):
+    # BGV -- bgv_multiply (evaluator.cpp:710-841), BGV mod-down of switch_key_inplace (:2762-2805),
+    # mod_t_and_divide_q_last_ntt_inplace (rns.cpp:1193-1236); plain modulus below and above the smallest coefficient prime
+    mods = R.coeff_modulus_create(n, bits)
+    k = len(mods)
+    t = R.plain_modulus_batching(n, t_bits)
+    rc = R.RefContext(R.BGV, n, mods, t)
+    ctx = sb().Context(sb().BGV, n, mods, t)
+    rk = ctx.load_key(rc.relin_key())
+    rng = np.random.default_rng(n + t_bits)
+    for L in (k - 1, 2, 1):
+        a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+        m = ctx.multiply(a, b)
+        r = ctx.relinearize(m, rk)
+        mr = ctx.multiply_relinearize(a, b, rk)
+        for i in range(batch):
+            assert (m[i] == rc.multiply(L, a[i], b[i])).all()
+            assert (r[i] == rc.relinearize(L, m[i])).all()
+        assert (mr == r).all()
+        if L > 1:
+            ms = ctx.mod_switch_to_next(a)
+            for i in range(batch):
+                assert (ms[i] == rc.mod_switch(L, a[i])).all()
+            with pytest.raises(ValueError):
+                ctx.rescale_to_next(a)  # evaluator.cpp:1533: unsupported operation for scheme type
+        for step in (1, -2):
+            e = rc.galois_elt_from_step(step)
+            gk = ctx.load_key(rc.galois_key(e))
+            g = ctx.rotate(a, step, gk)
+            for i in range(batch):
+                assert (g[i] == rc.rotate(L, a[i], step)).all()
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

@@ -165,3 +165,25 @@ def test_oracle_multiply_plain_vs_live_reference(scheme):
             a = rand_ct(rng, mods, n, size, L)
             plain = rand_ct(rng, mods, n, 1, L)[0]
             assert (rc.multiply_plain(L, a, plain) == oc.multiply_plain(L, a, plain)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("t_bits", [17, 38])
+def test_oracle_vs_live_reference_bgv(t_bits):
+    # BGV branches -- bgv_multiply (evaluator.cpp:710-841), the BGV mod-down of switch_key_inplace
+    # (:2762-2805) and mod_t_and_divide_q_last_ntt_inplace (rns.cpp:1193-1236); t above and below the coefficient primes
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 36, 42, 43])
+    t = R.plain_modulus_batching(n, t_bits)
+    rb, ob = R.RefContext(R.BGV, n, mods, t), O.Oracle(O.BGV, n, mods, t)
+    rng = np.random.default_rng(29)
+    key = rb.relin_key()
+    for L in (3, 2, 1):
+        a, b = rand_ct(rng, mods, n, 2, L), rand_ct(rng, mods, n, 2, L)
+        m = rb.multiply(L, a, b)
+        assert (m == ob.multiply(L, a, b)).all()
+        assert (rb.relinearize(L, m) == ob.relinearize(L, m, key)).all()
+        if L > 1:
+            assert (rb.mod_switch(L, a) == ob.bgv_mod_switch(L, a)).all()
+        e = rb.galois_elt_from_step(1)
+        assert (rb.apply_galois(L, a, e) == ob.apply_galois(L, a, e, rb.galois_key(e))).all()
