@@ -91,6 +91,10 @@ int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, u
 /* Evaluator::multiply (evaluator.cpp:352-708), size-2 x size-2 -> size-3; CKKS (NTT form) or BFV (BEHZ) per ctx */
 int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, const uint64_t *d_b,
                    uint64_t *d_out3, void *stream);
+/* the general-size branches of the same function (evaluator.cpp:524-560, :664-700, :796-833): size_a x size_b ->
+ * size_a + size_b - 1, out[k] = sum_{i+j=k} a_i * b_j; 2 <= size <= 16 (SEAL_CIPHERTEXT_SIZE_MAX).  No aliasing. */
+int sb200_multiply_sized(sb200_context *ctx, size_t L, size_t size_a, size_t size_b, size_t batch, const uint64_t *d_a,
+                         const uint64_t *d_b, uint64_t *d_out, void *stream);
 /* Evaluator::square (evaluator.cpp:843-1142): same residues as multiply(a, a), size 2 -> 3 */
 int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_a, uint64_t *d_out3, void *stream);
 /* Evaluator::add / sub / negate on equal-size operands (evaluator.cpp:130-350), element-wise over [batch][size][L][n];
@@ -122,6 +126,8 @@ int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_
 int sb200_ntt_forward_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
 int sb200_ntt_inverse_host(sb200_context *ctx, size_t L, size_t size, size_t batch, uint64_t *h_data);
 int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out3);
+int sb200_multiply_sized_host(sb200_context *ctx, size_t L, size_t size_a, size_t size_b, size_t batch, const uint64_t *h_a,
+                              const uint64_t *h_b, uint64_t *h_out);
 int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, uint64_t *h_out3);
 int sb200_add_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out);
 int sb200_sub_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out);

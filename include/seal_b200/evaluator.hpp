@@ -13,6 +13,9 @@
 #pragma once
 #include "../seal_b200.h"
 #include "seal/seal.h"
+#include "seal/util/numth.h"
+#include "seal/util/uintarithsmallmod.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -66,16 +69,15 @@ namespace seal_b200
                 throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form"); // :571-574, :712-715
             if (!(ckks || bgv) && (encrypted1.is_ntt_form() || encrypted2.is_ntt_form()))
                 throw std::invalid_argument("encrypted1 or encrypted2 cannot be in NTT form"); // :397-400
-            if (encrypted1.size() != 2 || encrypted2.size() != 2)
-                throw std::invalid_argument("seal_b200: multiply is implemented for size-2 ciphertexts");
             auto cd = context_.get_context_data(encrypted1.parms_id());
             const std::size_t L = encrypted1.coeff_modulus_size(), n = encrypted1.poly_modulus_degree();
-            std::vector<std::uint64_t> a(encrypted1.data(), encrypted1.data() + 2 * L * n);
+            const std::size_t s1 = encrypted1.size(), s2 = encrypted2.size(); // any sizes: :524-560, :664-700, :796-833
+            std::vector<std::uint64_t> a(encrypted1.data(), encrypted1.data() + s1 * L * n);
             double new_scale = encrypted1.scale() * encrypted2.scale();
             if (ckks && !scale_within_bounds(new_scale, *cd))
                 throw std::invalid_argument("scale out of bounds"); // :703-707
-            encrypted1.resize(context_, cd->parms_id(), 3);
-            check(sb200_multiply_host(ctx_, L, 1, a.data(), encrypted2.data(), encrypted1.data()));
+            encrypted1.resize(context_, cd->parms_id(), s1 + s2 - 1); // throws on > SEAL_CIPHERTEXT_SIZE_MAX like the reference
+            check(sb200_multiply_sized_host(ctx_, L, s1, s2, 1, a.data(), encrypted2.data(), encrypted1.data()));
             if (ckks)
                 encrypted1.scale() = new_scale;
             if (bgv) // :838-840
@@ -110,7 +112,7 @@ namespace seal_b200
             square_inplace(destination, std::move(pool));
         }
 
-        // ---- negate / add / sub (evaluator.cpp:130-350), equal-size operands ------------------------------------------
+        // ---- negate / add / sub (evaluator.cpp:130-350) ------------------------------------------------------------------
         void negate_inplace(seal::Ciphertext &encrypted) const
         {
             validate(encrypted, "encrypted is not valid for encryption parameters");
@@ -401,7 +403,7 @@ namespace seal_b200
         sb200_context *native_handle() const noexcept { return ctx_; }
 
     private:
-        // evaluator.cpp:154-262 / 264-350 prologue; sizes must match here (the reference also pads the shorter operand)
+        // evaluator.cpp:154-262 / 264-350
         void linear(seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, bool subtract) const
         {
             validate(encrypted1, "encrypted1 is not valid for encryption parameters");
@@ -412,14 +414,80 @@ namespace seal_b200
                 throw std::invalid_argument("NTT form mismatch");
             if (!seal::util::are_close<double>(encrypted1.scale(), encrypted2.scale()))
                 throw std::invalid_argument("scale mismatch");
-            if (encrypted1.size() != encrypted2.size())
-                throw std::invalid_argument("seal_b200: add/sub are implemented for equal-size ciphertexts");
-            if (encrypted1.correction_factor() != encrypted2.correction_factor()) // BGV rebalancing, evaluator.cpp:188-209
-                throw std::invalid_argument("seal_b200: add/sub are implemented for equal correction factors");
-            const std::size_t L = encrypted1.coeff_modulus_size();
-            check(subtract ? sb200_sub_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data())
-                           : sb200_add_host(ctx_, L, encrypted1.size(), 1, encrypted1.data(), encrypted2.data(), encrypted1.data()));
+            auto cd = context_.get_context_data(encrypted1.parms_id());
+            const std::size_t L = encrypted1.coeff_modulus_size(), n = encrypted1.poly_modulus_degree();
+            if (encrypted1.correction_factor() != encrypted2.correction_factor())
+            {
+                // BGV: bring both operands to a common correction factor first (evaluator.cpp:188-209, :305-326)
+                std::uint64_t f, e1, e2;
+                balance_factors(encrypted1.correction_factor(), encrypted2.correction_factor(), cd->parms().plain_modulus(), f, e1, e2);
+                seal::Ciphertext copy = encrypted2;
+                scale_by(encrypted1, e1, *cd);
+                scale_by(copy, e2, *cd);
+                encrypted1.correction_factor() = f;
+                copy.correction_factor() = f;
+                linear(encrypted1, copy, subtract);
+                return;
+            }
+            const std::size_t s1 = encrypted1.size(), s2 = encrypted2.size(), lo = std::min(s1, s2);
+            encrypted1.resize(context_, cd->parms_id(), std::max(s1, s2));
+            check(subtract ? sb200_sub_host(ctx_, L, lo, 1, encrypted1.data(), encrypted2.data(), encrypted1.data())
+                           : sb200_add_host(ctx_, L, lo, 1, encrypted1.data(), encrypted2.data(), encrypted1.data()));
+            if (s1 < s2)
+            {
+                // the longer operand's tail is copied (add, :228-233) or negated (sub, :336-341)
+                if (subtract)
+                    check(sb200_negate_host(ctx_, L, s2 - lo, 1, encrypted2.data(lo), encrypted1.data(lo)));
+                else
+                    std::memcpy(encrypted1.data(lo), encrypted2.data(lo), (s2 - lo) * L * n * sizeof(std::uint64_t));
+            }
             throw_if_transparent(encrypted1);
+        }
+        // every polynomial times the scalar e (multiply_poly_scalar_coeffmod, evaluator.cpp:192-200): a dyadic product with the
+        // constant vector e mod q_i, valid in either form
+        void scale_by(seal::Ciphertext &ct, std::uint64_t e, const seal::SEALContext::ContextData &cd) const
+        {
+            const std::size_t L = ct.coeff_modulus_size(), n = ct.poly_modulus_degree();
+            std::vector<std::uint64_t> v(L * n);
+            for (std::size_t i = 0; i < L; i++)
+                std::fill(v.begin() + i * n, v.begin() + (i + 1) * n, seal::util::barrett_reduce_64(e, cd.parms().coeff_modulus()[i]));
+            check(sb200_multiply_plain_host(ctx_, L, ct.size(), 1, ct.data(), v.data(), ct.data()));
+        }
+        // (f, e1, e2) with e1*factor1 = e2*factor2 = f mod t, both e invertible mod t, and |e1| + |e2| (balanced
+        // representatives) minimal over the remainder sequence of (t, factor2/factor1) -- evaluator.cpp:50-118
+        static void balance_factors(std::uint64_t factor1, std::uint64_t factor2, const seal::Modulus &plain, std::uint64_t &f,
+                                    std::uint64_t &e1, std::uint64_t &e2)
+        {
+            using namespace seal::util;
+            const std::uint64_t t = plain.value();
+            auto weight = [t](std::uint64_t x, std::uint64_t y) {
+                auto mag = [t](std::uint64_t v) { return static_cast<std::int64_t>(v > t / 2 ? t - v : v); };
+                return mag(x) + mag(y);
+            };
+            auto residue = [&plain](std::int64_t v) {
+                std::uint64_t r = barrett_reduce_64(static_cast<std::uint64_t>(v < 0 ? -v : v), plain);
+                return v < 0 ? negate_uint_mod(r, plain) : r;
+            };
+            std::uint64_t ratio = 1;
+            if (!try_invert_uint_mod(factor1, plain, ratio))
+                throw std::logic_error("invalid correction factor1");
+            ratio = multiply_uint_mod(ratio, factor2, plain);
+            e1 = ratio, e2 = 1;
+            std::int64_t best = weight(e1, e2);
+            std::int64_t r0 = static_cast<std::int64_t>(t), r1 = static_cast<std::int64_t>(ratio), c0 = 0, c1 = 1;
+            while (r1 != 0)
+            {
+                const std::int64_t quo = r0 / r1, r2 = r0 % r1, c2 = sub_safe(c0, mul_safe(c1, quo));
+                r0 = r1, r1 = r2, c0 = c1, c1 = c2;
+                const std::uint64_t a = residue(r1), b = residue(c1);
+                if (a != 0 && gcd(a, t) == 1)
+                {
+                    const std::int64_t w = weight(a, b);
+                    if (w < best)
+                        best = w, e1 = a, e2 = b;
+                }
+            }
+            f = multiply_uint_mod(e1, factor1, plain);
         }
         static void check(int status)
         {

@@ -272,6 +272,17 @@ extern "C" int sealref_multiply(sealref_ctx *c, size_t L, const uint64_t *a, con
     REF_CATCH(-1)
 }
 
+extern "C" int sealref_multiply_sized(
+    sealref_ctx *c, size_t L, size_t size_a, size_t size_b, const uint64_t *a, const uint64_t *b, uint64_t *out)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, size_a, a), y = make_ct(c, L, size_b, b);
+    c->evaluator->multiply_inplace(x, y);
+    store_ct(c, x, out);
+    return 0;
+    REF_CATCH(-1)
+}
+
 extern "C" int sealref_square(sealref_ctx *c, size_t L, const uint64_t *a, uint64_t *out3)
 {
     REF_TRY

@@ -45,6 +45,7 @@ uint32_t sealref_galois_elt_from_step(const sealref_ctx *c, int step);
 int sealref_ntt_forward(sealref_ctx *c, size_t L, size_t size, uint64_t *data);   /* Evaluator::transform_to_ntt_inplace */
 int sealref_ntt_inverse(sealref_ctx *c, size_t L, size_t size, uint64_t *data);   /* Evaluator::transform_from_ntt_inplace */
 int sealref_multiply(sealref_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3); /* size2 x size2 -> size3 */
+int sealref_multiply_sized(sealref_ctx *c, size_t L, size_t size_a, size_t size_b, const uint64_t *a, const uint64_t *b, uint64_t *out); /* general sizes */
 int sealref_square(sealref_ctx *c, size_t L, const uint64_t *a, uint64_t *out3);                 /* Evaluator::square_inplace */
 int sealref_linear(sealref_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out); /* 0 add, 1 sub, 2 negate */
 int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out); /* Evaluator::multiply_plain, both NTT form */

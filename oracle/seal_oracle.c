@@ -320,19 +320,28 @@ void orc_ntt_inverse(const orc_ctx *c, size_t L, size_t size, u64 *d)
 /* ---------------------------------------------------------------------- CKKS multiply (evaluator.cpp:634-662) -- */
 void orc_ckks_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64 *o)
 {
-    size_t n = c->n, P = L * n;
-    for (size_t i = 0; i < L; i++)
-    {
-        u64 q = c->q[i];
-        for (size_t j = 0; j < n; j++)
-        {
-            size_t e = i * n + j;
-            u64 x0 = a[e], x1 = a[P + e], y0 = b[e], y1 = b[P + e];
-            o[e] = mulmod(x0, y0, q);
-            o[P + e] = addmod(mulmod(x0, y1, q), mulmod(x1, y0, q), q);
-            o[2 * P + e] = mulmod(x1, y1, q);
-        }
-    }
+    orc_ckks_multiply_sized(c, L, 2, 2, a, b, o);
+}
+
+/* out[k] = sum_{i+j=k} x_i * y_j over rows of nb primes (the general-size loop, evaluator.cpp:664-700; 2x2 is :600-662) */
+static void tensor_rows(const u64 *x, size_t s1, const u64 *y, size_t s2, size_t nb, size_t n, const u64 *mods, u64 *o)
+{
+    size_t P = nb * n;
+    for (size_t k = 0; k < s1 + s2 - 1; k++)
+        for (size_t i = 0; i < nb; i++)
+            for (size_t j = 0; j < n; j++)
+            {
+                size_t e = i * n + j;
+                u64 acc = 0;
+                for (size_t p = 0; p < s1; p++)
+                    if (k >= p && k - p < s2)
+                        acc = addmod(acc, mulmod(x[p * P + e], y[(k - p) * P + e], mods[i]), mods[i]);
+                o[k * P + e] = acc;
+            }
+}
+void orc_ckks_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, const u64 *a, const u64 *b, u64 *o)
+{
+    tensor_rows(a, s1, b, s2, L, c->n, c->q, o);
 }
 
 /* add / sub / negate (evaluator.cpp:130-350; polyarithsmallmod.cpp:43-195) */
@@ -798,7 +807,11 @@ void orc_divide_and_round_q_last(const u64 *q, size_t L, size_t n, u64 *data)
 
 int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64 *out3)
 {
-    size_t n = c->n;
+    return orc_bfv_multiply_sized(c, L, 2, 2, a, b, out3);
+}
+int orc_bfv_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, const u64 *a, const u64 *b, u64 *out3)
+{
+    size_t n = c->n, nin = s1 + s2, nout = s1 + s2 - 1;
     behz_base bb;
     if (c->scheme != ORC_BFV || behz_base_init(c, L, &bb))
         return -1;
@@ -807,12 +820,12 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
     for (size_t i = 0; i < nS; i++)
         if (tab_init(&stab[i], n, bb.Bsk[i]))
             return -1;
-    /* steps (1)-(3), evaluator.cpp:456-474, for the 4 input polys: [0,1] of a then [0,1] of b */
-    u64 *xq = (u64 *)malloc(4 * L * n * sizeof(u64)), *xs = (u64 *)malloc(4 * nS * n * sizeof(u64));
+    /* steps (1)-(3), evaluator.cpp:456-474, for every input poly: those of a, then those of b */
+    u64 *xq = (u64 *)malloc(nin * L * n * sizeof(u64)), *xs = (u64 *)malloc(nin * nS * n * sizeof(u64));
     u64 *lift = (u64 *)malloc((nS + 1) * n * sizeof(u64));
-    for (size_t p = 0; p < 4; p++)
+    for (size_t p = 0; p < nin; p++)
     {
-        const u64 *src = (p < 2 ? a : b) + (p & 1) * L * n;
+        const u64 *src = p < s1 ? a + p * L * n : b + (p - s1) * L * n;
         for (size_t i = 0; i < L; i++)
         {
             memcpy(xq + (p * L + i) * n, src + i * n, n * sizeof(u64));
@@ -824,24 +837,17 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
             ntt_fwd(&stab[s], n, xs + (p * nS + s) * n);
     }
     /* step (4) tensor, :497-541; (5) INTT :545-546; (6) times t :554-556 */
-    u64 *dq = (u64 *)malloc(3 * L * n * sizeof(u64)), *ds = (u64 *)malloc(3 * nS * n * sizeof(u64));
+    u64 *dq = (u64 *)malloc(nout * L * n * sizeof(u64)), *ds = (u64 *)malloc(nout * nS * n * sizeof(u64));
     for (int base = 0; base < 2; base++)
     {
         size_t nb = base ? nS : L;
         u64 *x = base ? xs : xq, *d = base ? ds : dq;
+        tensor_rows(x, s1, x + s1 * nb * n, s2, nb, n, base ? bb.Bsk : c->q, d);
         for (size_t i = 0; i < nb; i++)
         {
             u64 P = base ? bb.Bsk[i] : c->q[i];
             const orc_tab *t = base ? &stab[i] : &c->tab[i];
-            u64 *x0 = x + (0 * nb + i) * n, *x1 = x + (1 * nb + i) * n, *y0 = x + (2 * nb + i) * n,
-                *y1 = x + (3 * nb + i) * n;
-            for (size_t j = 0; j < n; j++)
-            {
-                d[(0 * nb + i) * n + j] = mulmod(x0[j], y0[j], P);
-                d[(1 * nb + i) * n + j] = addmod(mulmod(x0[j], y1[j], P), mulmod(x1[j], y0[j], P), P);
-                d[(2 * nb + i) * n + j] = mulmod(x1[j], y1[j], P);
-            }
-            for (size_t p = 0; p < 3; p++)
+            for (size_t p = 0; p < nout; p++)
             {
                 ntt_inv(t, n, d + (p * nb + i) * n);
                 for (size_t j = 0; j < n; j++)
@@ -851,7 +857,7 @@ int orc_bfv_multiply(const orc_ctx *c, size_t L, const u64 *a, const u64 *b, u64
     }
     /* steps (7) fast_floor rns.cpp:1041-1084 and (8) fastbconv_sk rns.cpp:903-977 */
     u64 *qs = (u64 *)malloc((L + nS) * n * sizeof(u64)), *f = (u64 *)malloc(nS * n * sizeof(u64));
-    for (size_t p = 0; p < 3; p++)
+    for (size_t p = 0; p < nout; p++)
     {
         memcpy(qs, dq + p * L * n, L * n * sizeof(u64));
         memcpy(qs + L * n, ds + p * nS * n, nS * n * sizeof(u64));

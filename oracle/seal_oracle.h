@@ -65,6 +65,9 @@ void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const uint64_
 /* Evaluator::multiply_plain, ciphertext and plaintext in NTT form (evaluator.cpp:2157-2195) */
 void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out);
 int orc_bfv_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3);   /* evaluator.cpp:395-567 */
+/* general ciphertext sizes s1 x s2 -> s1+s2-1 (evaluator.cpp:664-700, :796-833; BFV :453-560) */
+void orc_ckks_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, const uint64_t *a, const uint64_t *b, uint64_t *out);
+int orc_bfv_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, const uint64_t *a, const uint64_t *b, uint64_t *out);
 /* ct (size 2, updated in place) += key-switch of target ([L][n]); key = [L digits][2][k][n]; evaluator.cpp:2561-2867 */
 void orc_switch_key(const orc_ctx *c, size_t L, uint64_t *ct2, const uint64_t *target, const uint64_t *key);
 void orc_relinearize(const orc_ctx *c, size_t L, const uint64_t *in3, const uint64_t *key, uint64_t *out2); /* evaluator.cpp:1144-1199 */

@@ -26,9 +26,9 @@ SYMBOLS = [
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
-    "sb200_ntt_inverse", "sb200_multiply", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
-    "sb200_multiply_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
+    "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host",
 ]
 
@@ -65,6 +65,8 @@ def lib():
         L.sb200_ntt_inverse.argtypes = [vp, sz, sz, sz, vp, vp]
         L.sb200_multiply.argtypes = [vp, sz, sz, vp, vp, vp, vp]
         L.sb200_square.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.sb200_multiply_sized.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp, vp]
+        L.sb200_multiply_sized_host.argtypes = [vp, sz, sz, sz, sz, _u64p, _u64p, _u64p]
         L.sb200_add.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_sub.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_negate.argtypes = [vp, sz, sz, sz, vp, vp, vp]
@@ -227,7 +229,12 @@ class Context:
     def multiply(self, a, b):
         a, single = self._batched(a)
         b, _ = self._batched(b)
-        B, _, L, n = a.shape
+        B, sa, L, n = a.shape
+        sb_ = b.shape[1]
+        if (sa, sb_) != (2, 2):  # general-size branch of Evaluator::multiply
+            out = np.zeros((B, sa + sb_ - 1, L, n), dtype=np.uint64)
+            _check(lib().sb200_multiply_sized_host(self.h, L, sa, sb_, B, _hp(a), _hp(b), _hp(out)))
+            return out[0] if single else out
         out = np.zeros((B, 3, L, n), dtype=np.uint64)
         _check(lib().sb200_multiply_host(self.h, L, B, _hp(a), _hp(b), _hp(out)))
         return out[0] if single else out
@@ -327,6 +334,9 @@ class Context:
 
     def d_multiply_plain(self, a, plain, out, L, size, batch):
         _check(lib().sb200_multiply_plain(self.h, L, size, batch, _dp(a), _dp(plain), _dp(out), self._stream()))
+
+    def d_multiply_sized(self, a, b, out, L, size_a, size_b, batch):
+        _check(lib().sb200_multiply_sized(self.h, L, size_a, size_b, batch, _dp(a), _dp(b), _dp(out), self._stream()))
 
     def d_relinearize(self, in3, key, out2, L, batch):
         _check(lib().sb200_relinearize(self.h, L, batch, _dp(in3), key.h, _dp(out2), self._stream()))

@@ -317,6 +317,26 @@ int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a
     SB_CATCH
 }
 
+int sb200_multiply_sized(sb200_context *ctx, size_t L, size_t size_a, size_t size_b, size_t batch, const uint64_t *a, const uint64_t *b,
+                         uint64_t *out, void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    if (out == a || out == b)
+        throw std::invalid_argument("multiply: the output slab must not alias an input slab");
+    auto st = static_cast<cudaStream_t>(stream);
+    if (c.scheme != SB200_SCHEME_BFV)
+        op_ckks_multiply(c, L, size_a, size_b, batch, (const u64 *)a, (const u64 *)b, (u64 *)out, st);
+    else
+        op_bfv_multiply(c, L, size_a, size_b, batch, (const u64 *)a, (const u64 *)b, (u64 *)out, st);
+    return SB200_OK;
+    SB_CATCH
+}
+
 static int linear_dev(sb200_context *ctx, int mode, size_t L, size_t size, size_t batch, const uint64_t *a, const uint64_t *b, uint64_t *out,
                       void *stream)
 {
@@ -563,6 +583,28 @@ int sb200_multiply_host(sb200_context *ctx, size_t L, size_t batch, const uint64
         else
             op_bfv_multiply(c, L, B, da, db, dout, st);
     });
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply_sized_host(sb200_context *ctx, size_t L, size_t size_a, size_t size_b, size_t batch, const uint64_t *a, const uint64_t *b,
+                              uint64_t *out)
+{
+    SB_NEED(a);
+    SB_NEED(b);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    check_sizes(size_a, size_b);
+    const size_t w = L * c.n;
+    HostPipe(c).run(batch, size_a * w, size_b * w, (size_a + size_b - 1) * w, a, b, out,
+                    [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
+                        if (c.scheme != SB200_SCHEME_BFV)
+                            op_ckks_multiply(c, L, size_a, size_b, B, da, db, dout, st);
+                        else
+                            op_bfv_multiply(c, L, size_a, size_b, B, da, db, dout, st);
+                    });
     return SB200_OK;
     SB_CATCH
 }

@@ -110,21 +110,22 @@ namespace sb
         return behz_dev(c, L).host;
     }
 
-    // ---- (1)+(2): lift the 4 input polynomials from base q to base Bsk, removing the q-overflow --------------------
-    // grid = (n/TH, 4, B); dynamic smem = L*TH words
+    // ---- (1)+(2): lift the s1+s2 input polynomials from base q to base Bsk, removing the q-overflow ----------------
+    // grid = (n/TH, s1+s2, B); dynamic smem = L*TH words
     constexpr int kBehzThreads = 128;
     __global__ void __launch_bounds__(kBehzThreads) behz_lift_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ XS,
                                                                       const PrimeDev *__restrict__ primes, const int *__restrict__ pids_bsk,
                                                                       const Tw *__restrict__ lift_c, const u64 *__restrict__ q_to_bsk,
                                                                       const uint32_t *__restrict__ q_to_mt, const Tw *__restrict__ prod_q_mod_bsk,
                                                                       const Tw *__restrict__ inv_mt_mod_bsk, uint32_t neg_inv_q_mod_mt, int logn,
-                                                                      int L, int nS)
+                                                                      int L, int nS, int s1, int s2)
     {
         extern __shared__ u64 sm[];
         const int n = 1 << logn, idx = blockIdx.x * blockDim.x + threadIdx.x, p4 = blockIdx.y, bb = blockIdx.z;
         if (idx >= n)
             return;
-        const u64 *src = (p4 < 2 ? a : b) + ((static_cast<long long>(bb) * 2 + (p4 & 1)) * L << logn) + idx;
+        const u64 *src = (p4 < s1 ? a + ((static_cast<long long>(bb) * s1 + p4) * L << logn)
+                                  : b + ((static_cast<long long>(bb) * s2 + (p4 - s1)) * L << logn)) + idx;
         u64 *t = sm + threadIdx.x;
         uint32_t ymt = 0;
         for (int i = 0; i < L; i++)
@@ -135,7 +136,7 @@ namespace sb
             ymt += static_cast<uint32_t>(ti) * q_to_mt[i]; // FastBConv to {m~ = 2^32}: only the low 32 bits matter
         }
         const uint32_t r = ymt * neg_inv_q_mod_mt; // rns.cpp:1016-1017 (mod 2^32)
-        u64 *dst = XS + ((static_cast<long long>(bb) * 4 + p4) * nS << logn) + idx;
+        u64 *dst = XS + ((static_cast<long long>(bb) * (s1 + s2) + p4) * nS << logn) + idx;
         for (int s = 0; s < nS; s++)
         {
             const PrimeDev P = primes[pids_bsk[s]];
@@ -174,7 +175,7 @@ namespace sb
     }
 
     // ---- (7)+(8): divide by q and floor into Bsk, then Shenoy-Kumaresan back to base q -----------------------------
-    // grid = (n/TH, 3, B); dynamic smem = (max(L, nS) + nS) * TH words
+    // grid = (n/TH, s1+s2-1, B); dynamic smem = (max(L, nS) + nS) * TH words
     __global__ void __launch_bounds__(kBehzThreads) behz_floor_sk_kernel(
         const u64 *__restrict__ DQ, const u64 *__restrict__ DS, u64 *__restrict__ out, const PrimeDev *__restrict__ primes,
         const int *__restrict__ pids_bsk, const Tw *__restrict__ inv_punc_q, const u64 *__restrict__ q_to_bsk, const Tw *__restrict__ inv_q_mod_bsk,
@@ -188,8 +189,9 @@ namespace sb
         const int TH = blockDim.x, W = L > nS ? L : nS;
         u64 *t = sm + threadIdx.x;          // [W]  t_i, later u_i
         u64 *f = sm + W * TH + threadIdx.x; // [nS] f_s
-        const u64 *dq = DQ + ((static_cast<long long>(bb) * 3 + p) * L << logn) + idx;
-        const u64 *ds = DS + ((static_cast<long long>(bb) * 3 + p) * nS << logn) + idx;
+        const int nout = gridDim.y;
+        const u64 *dq = DQ + ((static_cast<long long>(bb) * nout + p) * L << logn) + idx;
+        const u64 *ds = DS + ((static_cast<long long>(bb) * nout + p) * nS << logn) + idx;
         for (int i = 0; i < L; i++)
             t[i * TH] = mul_shoup(dq[static_cast<long long>(i) << logn], inv_punc_q[i], primes[i].q);
         // fast_floor: f_s = (d_s - FastBConv_{q->s}(d)) q^-1 mod Bsk_s   (rns.cpp:1074-1083)
@@ -215,7 +217,7 @@ namespace sb
             alpha = mul_shoup(conv + M.q - f[nB * TH], inv_b_mod_msk, M.q);
         }
         const bool neg = alpha > (M.q >> 1); // rns.cpp:964
-        u64 *o = out + ((static_cast<long long>(bb) * 3 + p) * L << logn) + idx;
+        u64 *o = out + ((static_cast<long long>(bb) * nout + p) * L << logn) + idx;
         for (int j = 0; j < L; j++)
         {
             const PrimeDev P = primes[j];
@@ -229,18 +231,19 @@ namespace sb
     }
 
     // ---- NTT functors ------------------------------------------------------------------------------------------------
-    // forward transform of the 4 input polys in base q: rows (b, p4, i) -> XQ[b][p4][i]
+    // forward transform of the s1+s2 input polys in base q: rows (b, p4, i) -> XQ[b][p4][i]
     struct OpBfvFwdQ
     {
         const u64 *a, *b;
         u64 *XQ;
-        int logn, L;
+        int logn, L, s1, s2;
         __device__ __forceinline__ bool skip(int) const { return false; }
         __device__ __forceinline__ int pid(int row) const { return row % L; }
         __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const
         {
-            const int i = row % L, bp = row / L, p4 = bp & 3, bb = bp >> 2;
-            return (p4 < 2 ? a : b) + (((static_cast<long long>(bb) * 2 + (p4 & 1)) * L + i) << logn);
+            const int i = row % L, bp = row / L, p4 = bp % (s1 + s2), bb = bp / (s1 + s2);
+            return p4 < s1 ? a + (((static_cast<long long>(bb) * s1 + p4) * L + i) << logn)
+                           : b + (((static_cast<long long>(bb) * s2 + (p4 - s1)) * L + i) << logn);
         }
         __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const { return direct(row, P)[idx]; }
         __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
@@ -298,13 +301,21 @@ namespace sb
 
     void op_bfv_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st)
     {
+        op_bfv_multiply(c, L, 2, 2, batch, a, b, out3, st);
+    }
+
+    // evaluator.cpp:395-567 for ciphertext sizes s1 x s2 -> s1+s2-1 (the BEHZ steps run per polynomial, :453-522, :524-560)
+    void op_bfv_multiply(Context &c, size_t L, size_t s1, size_t s2, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st)
+    {
+        check_sizes(s1, s2);
         BehzDev &d = behz_dev(c, L);
         const int n = static_cast<int>(c.n), Li = d.L, nS = d.nS, nB = d.nB;
-        // scratch per ciphertext: XQ 4L, XS 4nS, DQ 3L, DS 3nS rows
-        const size_t rows_per_ct = 7 * (L + nS);
+        const size_t nin = s1 + s2, nout = s1 + s2 - 1;
+        // scratch per ciphertext: XQ nin*L, XS nin*nS, DQ nout*L, DS nout*nS rows
+        const size_t rows_per_ct = (nin + nout) * (L + nS);
         const size_t per = rows_per_ct * c.n * sizeof(u64);
         size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
-        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (4 * (L + nS) * c.n)));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (nin * (L + nS) * c.n)));
         chunk = std::min<size_t>(chunk, 65535);
         const int TH = std::min(n, kBehzThreads);
         const size_t smem_lift = static_cast<size_t>(Li) * TH * sizeof(u64);
@@ -316,21 +327,30 @@ namespace sb
         {
             const size_t B = std::min(chunk, batch - b0);
             u64 *XQ = static_cast<u64 *>(c.ensure_scratch(per * B));
-            u64 *XS = XQ + B * 4 * L * c.n, *DQ = XS + B * 4 * nS * c.n, *DS = DQ + B * 3 * L * c.n;
-            const u64 *pa = a + b0 * 2 * L * c.n, *pb = b + b0 * 2 * L * c.n;
+            u64 *XS = XQ + B * nin * L * c.n, *DQ = XS + B * nin * nS * c.n, *DS = DQ + B * nout * L * c.n;
+            const u64 *pa = a + b0 * s1 * L * c.n, *pb = b + b0 * s2 * L * c.n;
             {
-                OpBfvFwdQ op{ pa, pb, XQ, c.logn, Li };
-                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 4 * L), c.logn, c.d_primes, st, c.stats, "bfv_ntt_q", -1, c.fast_q), "bfv ntt q");
+                OpBfvFwdQ op{ pa, pb, XQ, c.logn, Li, static_cast<int>(s1), static_cast<int>(s2) };
+                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * nin * L), c.logn, c.d_primes, st, c.stats, "bfv_ntt_q", -1, c.fast_q), "bfv ntt q");
             }
             {
-                dim3 grid((n + TH - 1) / TH, 4, static_cast<unsigned>(B));
-                c.stats.begin("behz_lift", 0, 8.0 * n * B * 4 * (L + nS), st);
+                dim3 grid((n + TH - 1) / TH, static_cast<unsigned>(nin), static_cast<unsigned>(B));
+                c.stats.begin("behz_lift", 0, 8.0 * n * B * nin * (L + nS), st);
                 behz_lift_kernel<<<grid, TH, smem_lift, st>>>(pa, pb, XS, c.d_primes, d.pids_bsk, d.lift_c, d.q_to_bsk, d.q_to_mt, d.prod_q_mod_bsk,
-                                                              d.inv_mt_mod_bsk, d.neg_inv_q_mod_mt, c.logn, Li, nS);
+                                                              d.inv_mt_mod_bsk, d.neg_inv_q_mod_mt, c.logn, Li, nS, static_cast<int>(s1),
+                                                              static_cast<int>(s2));
                 c.stats.end(st);
                 cuda_check(cudaGetLastError(), "behz_lift_kernel");
             }
-            op_ntt_rows(c, false, XS, B * 4 * nS, nS, d.pids_bsk, st);
+            op_ntt_rows(c, false, XS, B * nin * nS, nS, d.pids_bsk, st);
+            if (s1 != 2 || s2 != 2)
+            {
+                launch_tensor_general(c, XQ, static_cast<long long>(nin * L) * n, XQ + s1 * L * c.n, static_cast<long long>(nin * L) * n, DQ,
+                                      nullptr, L, s1, s2, B, st);
+                launch_tensor_general(c, XS, static_cast<long long>(nin) * nS * n, XS + s1 * nS * c.n, static_cast<long long>(nin) * nS * n, DS,
+                                      d.pids_bsk, nS, s1, s2, B, st);
+            }
+            else
             {
                 long long tq = static_cast<long long>(B) * L * n, ts = static_cast<long long>(B) * nS * n;
                 c.stats.begin("behz_tensor", 0, 56.0 * tq, st);
@@ -343,14 +363,14 @@ namespace sb
             }
             {
                 OpBfvInvMulT oq{ DQ, d.t_mod_q, nullptr, c.logn, Li };
-                cuda_check(launch_ntt_inv(oq, static_cast<int>(B * 3 * L), c.logn, c.d_primes, st, c.stats, "bfv_intt_q"), "bfv intt q");
+                cuda_check(launch_ntt_inv(oq, static_cast<int>(B * nout * L), c.logn, c.d_primes, st, c.stats, "bfv_intt_q"), "bfv intt q");
                 OpBfvInvMulT os{ DS, d.t_mod_bsk, d.pids_bsk, c.logn, nS };
-                cuda_check(launch_ntt_inv(os, static_cast<int>(B * 3 * nS), c.logn, c.d_primes, st, c.stats, "bfv_intt_bsk"), "bfv intt bsk");
+                cuda_check(launch_ntt_inv(os, static_cast<int>(B * nout * nS), c.logn, c.d_primes, st, c.stats, "bfv_intt_bsk"), "bfv intt bsk");
             }
             {
-                dim3 grid((n + TH - 1) / TH, 3, static_cast<unsigned>(B));
-                c.stats.begin("behz_floor_sk", 0, 8.0 * n * B * 3 * (2 * L + nS), st);
-                behz_floor_sk_kernel<<<grid, TH, smem_floor, st>>>(DQ, DS, out3 + b0 * 3 * L * c.n, c.d_primes, d.pids_bsk, d.inv_punc_q, d.q_to_bsk,
+                dim3 grid((n + TH - 1) / TH, static_cast<unsigned>(nout), static_cast<unsigned>(B));
+                c.stats.begin("behz_floor_sk", 0, 8.0 * n * B * nout * (2 * L + nS), st);
+                behz_floor_sk_kernel<<<grid, TH, smem_floor, st>>>(DQ, DS, out3 + b0 * nout * L * c.n, c.d_primes, d.pids_bsk, d.inv_punc_q, d.q_to_bsk,
                                                                   d.inv_q_mod_bsk, d.inv_punc_b, d.b_to_q, d.b_to_msk, d.inv_b_mod_msk,
                                                                   d.prod_b_mod_q, d.neg_prod_b_mod_q, c.logn, Li, nB, nS);
                 c.stats.end(st);

@@ -397,6 +397,65 @@ namespace sb
         cuda_check(cudaGetLastError(), "ckks_tensor_kernel");
     }
 
+    // general-size tensor in an arbitrary base (evaluator.cpp:664-700 / :796-833 NTT-form schemes, :524-560 BFV):
+    // out[k] = sum_{i+j=k} x_i * y_j for 0 <= k < s1+s2-1.  x = [B][s1][nb][n] at xa (+ b*xa_bs), y likewise; the prime of
+    // row i is pid_tab[i] (or i).  At most min(s1,s2) <= 16 products of canonical residues meet in one 128-bit sum.
+    __global__ void __launch_bounds__(256) tensor_general_kernel(const u64 *__restrict__ xa, long long xa_bs, const u64 *__restrict__ xb,
+                                                                  long long xb_bs, u64 *__restrict__ out, const PrimeDev *__restrict__ primes,
+                                                                  const int *__restrict__ pid_tab, int logn, int nb, int s1, int s2,
+                                                                  long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*nb*n
+        if (e >= total)
+            return;
+        const long long poly = static_cast<long long>(nb) << logn;
+        const long long bidx = e / poly, r = e % poly;
+        const int i = static_cast<int>(r >> logn);
+        const PrimeDev P = primes[pid_tab ? pid_tab[i] : i];
+        const u64 *px = xa + bidx * xa_bs + r, *py = xb + bidx * xb_bs + r;
+        u64 *po = out + bidx * (s1 + s2 - 1) * poly + r;
+        for (int k = 0; k < s1 + s2 - 1; k++)
+        {
+            const int i0 = k - (s2 - 1) > 0 ? k - (s2 - 1) : 0, i1 = k < s1 - 1 ? k : s1 - 1;
+            u64 lo = 0, hi = 0;
+            for (int a = i0; a <= i1; a++)
+                mac128(lo, hi, px[a * poly], py[(k - a) * poly]);
+            po[k * poly] = barrett128(lo, hi, P.q, P.ratio_lo, P.ratio_hi);
+        }
+    }
+
+    void launch_tensor_general(Context &c, const u64 *xa, long long xa_bs, const u64 *xb, long long xb_bs, u64 *out, const int *pid_tab,
+                               size_t nb, size_t s1, size_t s2, size_t B, cudaStream_t st)
+    {
+        const long long total = static_cast<long long>(B) * nb * c.n;
+        c.stats.begin("tensor_general", 0, 8.0 * total * (2.0 * (s1 + s2) - 1.0), st);
+        tensor_general_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+            xa, xa_bs, xb, xb_bs, out, c.d_primes, pid_tab, c.logn, static_cast<int>(nb), static_cast<int>(s1), static_cast<int>(s2), total);
+        c.stats.end(st);
+        cuda_check(cudaGetLastError(), "tensor_general_kernel");
+    }
+
+    void check_sizes(size_t s1, size_t s2)
+    {
+        // Ciphertext sizes are bounded by SEAL_CIPHERTEXT_SIZE_MAX = 16 (defines.h), the product by the same bound (evaluator.cpp:588-596)
+        if (s1 < 2 || s2 < 2 || s1 > 16 || s2 > 16 || s1 + s2 - 1 > 16)
+            throw std::invalid_argument("invalid ciphertext sizes");
+    }
+
+    void op_ckks_multiply(Context &c, size_t L, size_t s1, size_t s2, size_t batch, const u64 *a, const u64 *b, u64 *out, cudaStream_t st)
+    {
+        if (s1 == 2 && s2 == 2)
+            return op_ckks_multiply(c, L, batch, a, b, out, st);
+        check_sizes(s1, s2);
+        const size_t poly = L * c.n, step = std::max<size_t>(1, (size_t(1) << 31) / poly);
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t nb = std::min(step, batch - b0);
+            launch_tensor_general(c, a + b0 * s1 * poly, static_cast<long long>(s1 * poly), b + b0 * s2 * poly, static_cast<long long>(s2 * poly),
+                                  out + b0 * (s1 + s2 - 1) * poly, nullptr, L, s1, s2, nb, st);
+        }
+    }
+
     void op_ckks_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st)
     {
         const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (L * c.n));

@@ -132,6 +132,19 @@ static void test_ckks()
         ref.negate_inplace(r3);
         gpu.negate_inplace(g3);
         CHECK(same_ct(r3, g3));
+        // operands of different sizes: the longer tail is copied (add) or negated (sub), evaluator.cpp:228-233, :336-341
+        Ciphertext c3, r4, g4;
+        ref.multiply(cx, cy, c3);
+        c3.scale() = cx.scale();
+        ref.add(cx, c3, r4);
+        gpu.add(cx, c3, g4);
+        CHECK(r4.size() == 3 && same_ct(r4, g4));
+        ref.sub(cx, c3, r4);
+        gpu.sub(cx, c3, g4);
+        CHECK(same_ct(r4, g4));
+        ref.sub(c3, cx, r4);
+        gpu.sub(c3, cx, g4);
+        CHECK(same_ct(r4, g4));
         auto a = outcome([&] { Ciphertext t = cx; t.scale() *= 2; ref.add_inplace(t, cy); });
         auto b = outcome([&] { Ciphertext t = cx; t.scale() *= 2; gpu.add_inplace(t, cy); });
         CHECK(a == b && a == "invalid_argument"); // scale mismatch
@@ -159,6 +172,20 @@ static void test_ckks()
         a = outcome([&] { Ciphertext t = cx; ref.multiply_plain_inplace(t, big); });
         b = outcome([&] { Ciphertext t = cx; gpu.multiply_plain_inplace(t, big); });
         CHECK(a == b && a == "invalid_argument"); // scale out of bounds
+    }
+    {
+        // general-size multiply (evaluator.cpp:664-700): size 3 x size 2 -> 4, and a size-3 square
+        Ciphertext r2, g2, c3;
+        ref.multiply(cx, cy, c3);
+        Ciphertext lo = cx;
+        lo.scale() = 4.0; // keep the product scale inside the level's bounds
+        c3.scale() = 4.0;
+        ref.multiply(c3, lo, r2);
+        gpu.multiply(c3, lo, g2);
+        CHECK(r2.size() == 4 && same_ct(r2, g2));
+        ref.square(c3, r2);
+        gpu.square(c3, g2);
+        CHECK(r2.size() == 5 && same_ct(r2, g2));
     }
     for (int step : { 1, -4, 5, 1023 })
     {
@@ -314,6 +341,25 @@ static void test_bfv()
         CHECK(same_ct(r2, g2));
     }
     {
+        // general-size BFV multiply (:524-560): size 3 x size 2 -> 4; decrypts to x*y*y
+        Ciphertext c3, r2, g2;
+        ref.multiply(cx, cy, c3);
+        ref.multiply(c3, cy, r2);
+        gpu.multiply(c3, cy, g2);
+        CHECK(r2.size() == 4 && same_ct(r2, g2));
+        if (decryptor.invariant_noise_budget(g2) > 0)
+        {
+            Plaintext p;
+            decryptor.decrypt(g2, p);
+            std::vector<uint64_t> got;
+            encoder.decode(p, got);
+            bool ok = true;
+            for (size_t i = 0; i < n; i++)
+                ok = ok && got[i] == (x[i] * y[i] % t) * y[i] % t;
+            CHECK(ok);
+        }
+    }
+    {
         // multiply_plain with an NTT-form plaintext: ciphertext in NTT form (:1991-1994) and in coefficient form (:2006-2011)
         Plaintext pn = py;
         ref.transform_to_ntt_inplace(pn, cx.parms_id());
@@ -445,6 +491,38 @@ static void test_bgv()
         ref.multiply(cx, cy, r);
         ref.relinearize_inplace(r, rlk);
         CHECK(same_ct(r, out[0][0]) && same_ct(r, out[0][1]));
+    }
+    {
+        // add / sub across different correction factors (evaluator.cpp:50-118, :188-209): u = x two levels down,
+        // w = x*y one level down, multiplied and switched once more
+        Ciphertext u = cx, v = cy, w;
+        ref.mod_switch_to_next_inplace(u);
+        ref.mod_switch_to_next_inplace(v);
+        ref.multiply(u, v, w);
+        ref.relinearize_inplace(w, rlk);
+        ref.mod_switch_to_next_inplace(w);
+        ref.mod_switch_to_next_inplace(u);
+        CHECK(u.correction_factor() != w.correction_factor());
+        Ciphertext r2, g2;
+        ref.add(u, w, r2);
+        gpu.add(u, w, g2);
+        CHECK(same_ct(r2, g2));
+        Plaintext p;
+        decryptor.decrypt(g2, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == (x[i] + x[i] * y[i]) % t;
+        CHECK(ok);
+        ref.sub(w, u, r2);
+        gpu.sub(w, u, g2);
+        CHECK(same_ct(r2, g2));
+        Ciphertext odd = u;
+        odd.correction_factor() = 12345; // arbitrary factors take the same path
+        ref.add(odd, w, r2);
+        gpu.add(odd, w, g2);
+        CHECK(same_ct(r2, g2));
     }
     {
         auto a = outcome([&] { Ciphertext tt = cx; ref.rescale_to_next_inplace(tt); });

@@ -142,11 +142,15 @@ class Oracle:
         return d
 
     def multiply(self, L, a, b):
-        out = np.zeros((3, L, self.n), dtype=np.uint64)
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        sa, sb = a.shape[0], b.shape[0]
+        out = np.zeros((sa + sb - 1, L, self.n), dtype=np.uint64)
+        sized = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
+        lib().orc_ckks_multiply_sized.argtypes = lib().orc_bfv_multiply_sized.argtypes = sized
         if self.scheme != BFV:  # CKKS and BGV: the NTT-form tensor
-            lib().orc_ckks_multiply(self.h, L, _p(a), _p(b), _p(out))
+            lib().orc_ckks_multiply_sized(self.h, L, sa, sb, _p(a), _p(b), _p(out))
         else:
-            assert lib().orc_bfv_multiply(self.h, L, _p(a), _p(b), _p(out)) == 0
+            assert lib().orc_bfv_multiply_sized(self.h, L, sa, sb, _p(a), _p(b), _p(out)) == 0
         return out
 
     def linear(self, mode, L, a, b=None):

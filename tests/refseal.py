@@ -45,6 +45,7 @@ def lib():
         L.sealref_ntt_inverse.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]
         L.sealref_multiply.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_square.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_multiply_sized.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_linear.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_multiply_plain_ntt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
         L.sealref_relinearize.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
@@ -155,8 +156,13 @@ class RefContext:
         return d
 
     def multiply(self, L, a, b):
-        out = np.zeros((3, L, self.n), dtype=np.uint64)
-        self._chk(lib().sealref_multiply(self.h, L, _p(a), _p(b), _p(out)))
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        sa, sb = a.shape[0], b.shape[0]
+        out = np.zeros((sa + sb - 1, L, self.n), dtype=np.uint64)
+        if (sa, sb) == (2, 2):
+            self._chk(lib().sealref_multiply(self.h, L, _p(a), _p(b), _p(out)))
+        else:
+            self._chk(lib().sealref_multiply_sized(self.h, L, sa, sb, _p(a), _p(b), _p(out)))
         return out
 
     def square(self, L, a):

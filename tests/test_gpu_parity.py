@@ -316,6 +316,27 @@ def test_bgv_ops_vs_reference(n, bits, t_bits, batch):
                 assert (g[i] == rc.rotate(L, a[i], step)).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv", "bgv"])
+def test_general_size_multiply_vs_reference(scheme):
+    # the general-size branches of multiply (evaluator.cpp:524-560, :664-700, :796-833)
+    n, batch = 4096, 3
+    mods = R.coeff_modulus_create(n, [50, 45, 60, 55])
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 20)
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    rng = np.random.default_rng(43)
+    for L, sa, sb_ in ((3, 3, 2), (2, 2, 3), (1, 3, 3), (2, 4, 2)):
+        a, b = rand_ct(rng, mods, n, sa, L, batch), rand_ct(rng, mods, n, sb_, L, batch)
+        got = ctx.multiply(a, b)
+        assert got.shape == (batch, sa + sb_ - 1, L, n)
+        for i in range(batch):
+            assert (got[i] == rc.multiply(L, a[i], b[i])).all()
+    with pytest.raises(ValueError):
+        ctx.multiply(rand_ct(rng, mods, n, 9, 1, 1), rand_ct(rng, mods, n, 9, 1, 1))  # 17 polynomials > SEAL_CIPHERTEXT_SIZE_MAX
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

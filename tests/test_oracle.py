@@ -187,3 +187,18 @@ def test_oracle_vs_live_reference_bgv(t_bits):
             assert (rb.mod_switch(L, a) == ob.bgv_mod_switch(L, a)).all()
         e = rb.galois_elt_from_step(1)
         assert (rb.apply_galois(L, a, e) == ob.apply_galois(L, a, e, rb.galois_key(e))).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv", "bgv"])
+def test_oracle_general_size_multiply_vs_live_reference(scheme):
+    # the general-size branches of Evaluator::multiply (evaluator.cpp:524-560, :664-700, :796-833)
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42, 43])
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 17)
+    rc, oc = R.RefContext(sid, n, mods, t), O.Oracle(sid, n, mods, t)
+    rng = np.random.default_rng(41)
+    for L, sa, sb in ((3, 3, 2), (2, 2, 3), (1, 3, 3), (2, 4, 2)):
+        a, b = rand_ct(rng, mods, n, sa, L), rand_ct(rng, mods, n, sb, L)
+        assert (rc.multiply(L, a, b) == oc.multiply(L, a, b)).all()
