@@ -104,6 +104,26 @@ class ClockSampler:
         return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def gpu_numa_cpus(dev):
+    """(node, cpus) of the NUMA node the GPU's PCIe root port hangs off, or (None, None) when the box does not say"""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(dev)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else (None, None)
+    except Exception:
+        return None, None
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the reference's own CPU implementation (oracle/_ref) on the host cores."""
     if rank != 0:
@@ -253,6 +273,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         Be = wl["e2e_batch"]
+        # staging buffers on the GPU's own NUMA node (first touch by a thread bound there): every rank's H2D / D2H traffic then
+        # stays on its socket instead of crossing the inter-socket link; the affinity is restored before the CPU baseline runs
+        all_cpus = os.sched_getaffinity(0)
+        numa_node, numa_cpus = gpu_numa_cpus(local)
+        if numa_cpus:
+            os.sched_setaffinity(0, numa_cpus)
         ha = torch.empty((Be, 2, L, n), dtype=torch.int64).pin_memory()
         hb = torch.empty((Be, 2, L, n), dtype=torch.int64).pin_memory()
         ho = torch.empty((Be, 2, L, n), dtype=torch.int64).pin_memory()
@@ -274,8 +300,9 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert (ho.cuda() == out[:Be]).all(), "e2e result differs from the device-resident result"
+        os.sched_setaffinity(0, all_cpus)
         e2e = {"value": world * Be * args.steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(ha.nbytes + hb.nbytes),
-               "d2h_bytes_per_step": int(ho.nbytes), "batch_per_step": Be}
+               "d2h_bytes_per_step": int(ho.nbytes), "batch_per_step": Be, "host_numa_node": numa_node}
 
     if rank != 0:
         if world > 1:

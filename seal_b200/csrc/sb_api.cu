@@ -270,6 +270,32 @@ int sb200_kswitch_key_destroy(sb200_kswitch_key *key)
     std::lock_guard<std::mutex> lock(c.mu);                \
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
 
+// The scratch arenas of a context are shared by all of its calls.  Calls on one stream are ordered by the stream; a call on a
+// different stream than the previous one first waits for that one's work (one event record per call, no host synchronisation).
+namespace
+{
+    struct StreamOrder
+    {
+        Context &c;
+        cudaStream_t st;
+        StreamOrder(Context &ctx, cudaStream_t stream) : c(ctx), st(stream)
+        {
+            if (c.order_valid && c.order_stream != st)
+                cuda_check(cudaStreamWaitEvent(st, c.order_event, 0), "cudaStreamWaitEvent(order)");
+        }
+        ~StreamOrder()
+        {
+            if (!c.order_event && cudaEventCreateWithFlags(&c.order_event, cudaEventDisableTiming) != cudaSuccess)
+                return;
+            if (cudaEventRecord(c.order_event, st) == cudaSuccess)
+                c.order_stream = st, c.order_valid = true;
+        }
+    };
+} // namespace
+#define SB_ENTER_STREAM(ctx, stream) \
+    SB_ENTER(ctx)                    \
+    StreamOrder order_(c, static_cast<cudaStream_t>(stream));
+
 static void check_level(const Context &c, size_t L, size_t batch)
 {
     if (L < 1 || L > c.k)
@@ -282,7 +308,7 @@ int sb200_ntt_forward(sb200_context *ctx, size_t L, size_t size, size_t batch, u
 {
     SB_NEED(d);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_ntt(c, false, L, size, batch, reinterpret_cast<u64 *>(d), static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -293,7 +319,7 @@ int sb200_ntt_inverse(sb200_context *ctx, size_t L, size_t size, size_t batch, u
 {
     SB_NEED(d);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_ntt(c, true, L, size, batch, reinterpret_cast<u64 *>(d), static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -306,7 +332,7 @@ int sb200_multiply(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a
     SB_NEED(b);
     SB_NEED(out3);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     auto st = static_cast<cudaStream_t>(stream);
     if (c.scheme != SB200_SCHEME_BFV) // CKKS and BGV share the NTT-form tensor (evaluator.cpp:569-708, :710-841)
@@ -324,7 +350,7 @@ int sb200_multiply_sized(sb200_context *ctx, size_t L, size_t size_a, size_t siz
     SB_NEED(b);
     SB_NEED(out);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     if (out == a || out == b)
         throw std::invalid_argument("multiply: the output slab must not alias an input slab");
@@ -345,7 +371,7 @@ static int linear_dev(sb200_context *ctx, int mode, size_t L, size_t size, size_
     if (mode != 2)
         SB_NEED(b);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_linear(c, mode, L, size, batch, (const u64 *)a, (const u64 *)b, (u64 *)out, static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -370,7 +396,7 @@ int sb200_multiply_plain(sb200_context *ctx, size_t L, size_t size, size_t batch
     SB_NEED(plain);
     SB_NEED(out);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_multiply_plain(c, L, size, batch, (const u64 *)a, (const u64 *)plain, (u64 *)out, static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -388,7 +414,7 @@ int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t
     SB_NEED(key);
     SB_NEED(out2);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     if (static_cast<const void *>(in3) == static_cast<const void *>(out2))
         throw std::invalid_argument("relinearize: input and output slabs must not alias (different layouts)");
@@ -405,7 +431,7 @@ int sb200_multiply_relinearize(sb200_context *ctx, size_t L, size_t batch, const
     SB_NEED(key);
     SB_NEED(out2);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_multiply_relinearize(c, L, batch, (const u64 *)a, (const u64 *)b, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -417,7 +443,7 @@ int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint
     SB_NEED(in2);
     SB_NEED(out2);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
         throw std::invalid_argument("rescale_to_next: input and output slabs must not alias (different layouts)");
@@ -431,7 +457,7 @@ int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const u
     SB_NEED(in2);
     SB_NEED(out2);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
         throw std::invalid_argument("mod_switch_to_next: input and output slabs must not alias (different layouts)");
@@ -447,7 +473,7 @@ int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_
     SB_NEED(key);
     SB_NEED(out2);
     SB_TRY
-    SB_ENTER(ctx)
+    SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_apply_galois(c, L, batch, (const u64 *)in2, elt, key->k, (u64 *)out2, static_cast<cudaStream_t>(stream));
     return SB200_OK;
@@ -503,6 +529,7 @@ namespace
         template <class F>
         void run(size_t batch, size_t wa, size_t wb, size_t wo, const uint64_t *ha, const uint64_t *hb, uint64_t *ho, F &&op)
         {
+            StreamOrder order(c, s_comp); // the operation's kernels (and the scratch arenas they use) run on s_comp
             const size_t per_ct = (wa + wb + wo) * sizeof(u64);
             size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (size_t(640) << 20) / std::max<size_t>(per_ct, 1)));
             if (chunk >= batch && batch >= 4)

@@ -39,6 +39,8 @@ namespace sb
         cudaFree(d_qmod);
         cudaFree(scratch);
         cudaFree(aux_buf);
+        if (order_event)
+            cudaEventDestroy(order_event);
         for (auto &slot : io.buf)
             for (auto p : slot)
                 cudaFree(p);

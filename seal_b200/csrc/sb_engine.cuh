@@ -61,6 +61,10 @@ namespace sb
         LaunchStats stats;
         IoArena io;
         std::mutex mu;
+        // cross-stream ordering of calls that share the scratch arenas (sb_api.cu: StreamOrder)
+        cudaEvent_t order_event = nullptr;
+        cudaStream_t order_stream = nullptr;
+        bool order_valid = false;
 
         ~Context();
         void *ensure_scratch(size_t bytes);

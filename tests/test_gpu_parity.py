@@ -165,6 +165,32 @@ def test_device_api_matches_host_api():
     assert (host[0] == oc.multiply_relin(L, a[0], b[0], key)).all()
 
 
+def test_one_context_on_two_streams():
+    # calls of one context share its scratch arenas: a call on another stream must wait for the previous call's kernels
+    import torch
+
+    n, bits = 8192, [50, 50, 50, 50, 50]
+    mods = O.coeff_modulus_create(n, bits)
+    ctx = sb().Context(sb().CKKS, n, mods)
+    rng = np.random.default_rng(10)
+    L, batch = 4, 24
+    key = rng.integers(0, 1 << 40, (L, 2, 5, n), dtype=np.uint64)
+    rk = ctx.load_key(key)
+    ins = [(rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)) for _ in range(2)]
+    want = [ctx.multiply_relinearize(a, b, rk) for a, b in ins]
+    dev = [(torch.from_numpy(a.view(np.int64)).cuda(), torch.from_numpy(b.view(np.int64)).cuda()) for a, b in ins]
+    outs = [torch.empty((batch, 2, L, n), dtype=torch.int64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                ctx.d_multiply_relinearize(dev[i][0], dev[i][1], rk, outs[i], L, batch)
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert (outs[i].cpu().numpy().view(np.uint64) == want[i]).all()
+
+
 def test_error_codes():
     s = sb()
     with pytest.raises(ValueError):
