@@ -143,6 +143,42 @@ int sb200_mod_switch_to_next_host(sb200_context *ctx, size_t L, size_t batch, co
 int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint32_t galois_elt,
                             const sb200_kswitch_key *galois_key, uint64_t *h_out2);
 
+/* ---- wire format: Ciphertext::save / load with compr_mode_type::none, straight between a byte
+ * stream and a device slab (ciphertext.cpp:190-359, serialization.h:76-91, dynarray.h:662-690).  Compressed streams
+ * (zlib / zstd) and seed-compressed ciphertexts (Ciphertext::save of a symmetric encryption) stay with the reference:
+ * inspect reports them, load rejects them. */
+typedef struct sb200_ct_info
+{
+    uint64_t parms_id[4];         /* Ciphertext::parms_id() */
+    uint64_t size;                /* polynomials */
+    uint64_t poly_modulus_degree;
+    uint64_t coeff_modulus_size;  /* L */
+    uint64_t correction_factor;   /* BGV */
+    double scale;                 /* CKKS */
+    int32_t is_ntt_form;
+    int32_t seeded;               /* 1: only c_0 is stored, c_1 is a PRNG seed */
+    uint64_t data_offset;         /* byte offset of the first coefficient word in the stream */
+    uint64_t data_words;          /* 64-bit words stored */
+    uint64_t stream_bytes;        /* length of the serialized object (SEALHeader::size) */
+} sb200_ct_info;
+
+/* EncryptionParameters::parms_id() of the level with L primes (L = k: the key level); encryptionparams.cpp:124-158 */
+int sb200_get_parms_id(const sb200_context *ctx, size_t L, uint64_t out[4]);
+/* Serialization::LoadHeader + the metadata half of Ciphertext::load_members; pure host, needs no context */
+int sb200_ciphertext_inspect(const uint8_t *stream, size_t len, sb200_ct_info *info);
+/* bytes Ciphertext::save(compr_mode_type::none) produces for size polynomials at the level with L primes */
+size_t sb200_ciphertext_save_size(const sb200_context *ctx, size_t L, size_t size);
+/* Ciphertext::load (validate != 0; also checks every residue < q_i like is_data_valid_for, valcheck.cpp) or unsafe_load
+ * (validate == 0) of `batch` serialized ciphertexts of one shape into d_out [batch][size][L][n]; infos may be NULL.
+ * The coefficient words are copied from the streams to the device directly. */
+int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const *streams, const size_t *lens, size_t L, size_t size,
+                          int validate, uint64_t *d_out, sb200_ct_info *infos, void *stream);
+/* Ciphertext::save(compr_mode_type::none) of d_in [batch][size][L][n] into outs[b] (capacity >= sb200_ciphertext_save_size);
+ * meta[b] supplies is_ntt_form / scale / correction_factor (parms_id, sizes and offsets are filled in here).  Returns after
+ * the bytes are in place. */
+int sb200_ciphertext_save(sb200_context *ctx, size_t batch, size_t L, size_t size, const uint64_t *d_in, const sb200_ct_info *meta,
+                          uint8_t *const *outs, size_t capacity, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

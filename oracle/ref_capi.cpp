@@ -407,6 +407,57 @@ extern "C" int sealref_rotate(sealref_ctx *c, size_t L, const uint64_t *in2, int
     REF_CATCH(-1)
 }
 
+// ---- wire format (Ciphertext::save / load, compr_mode_type::none) and parms_id, for the rank-3 parity tests ----
+extern "C" int sealref_parms_id(sealref_ctx *c, size_t L, uint64_t *out4)
+{
+    REF_TRY
+    auto id = L == c->k ? c->context->key_parms_id() : level(c, L)->parms_id();
+    for (int i = 0; i < 4; i++)
+        out4[i] = id[i];
+    return 0;
+    REF_CATCH(-1)
+}
+
+extern "C" long sealref_ct_save(
+    sealref_ctx *c, size_t L, size_t size, const uint64_t *data, int is_ntt_form, double scale, uint64_t correction_factor,
+    uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    Ciphertext ct = make_ct(c, L, size, data);
+    ct.is_ntt_form() = is_ntt_form != 0;
+    ct.scale() = scale;
+    ct.correction_factor() = correction_factor;
+    return static_cast<long>(ct.save(reinterpret_cast<seal_byte *>(out), capacity, compr_mode_type::none));
+    REF_CATCH(-1)
+}
+
+extern "C" int sealref_ct_load(
+    sealref_ctx *c, const uint8_t *in, size_t len, uint64_t *data, size_t capacity_words, uint64_t *size, uint64_t *L,
+    int *is_ntt_form, double *scale, uint64_t *correction_factor)
+{
+    REF_TRY
+    Ciphertext ct;
+    ct.load(*c->context, reinterpret_cast<const seal_byte *>(in), len);
+    size_t words = ct.size() * ct.coeff_modulus_size() * ct.poly_modulus_degree();
+    if (words > capacity_words)
+        throw std::invalid_argument("capacity");
+    std::memcpy(data, ct.data(), words * sizeof(uint64_t));
+    *size = ct.size(), *L = ct.coeff_modulus_size(), *is_ntt_form = ct.is_ntt_form(), *scale = ct.scale();
+    *correction_factor = ct.correction_factor();
+    return 0;
+    REF_CATCH(-1)
+}
+
+// a seed-compressed ciphertext as Encryptor::encrypt_zero_symmetric(...).save() writes it (c_1 replaced by its PRNG seed)
+extern "C" long sealref_seeded_ct_stream(sealref_ctx *c, uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    Encryptor encryptor(*c->context, c->keygen->secret_key());
+    auto ser = encryptor.encrypt_zero_symmetric();
+    return static_cast<long>(ser.save(reinterpret_cast<seal_byte *>(out), capacity, compr_mode_type::none));
+    REF_CATCH(-1)
+}
+
 extern "C" int sealref_bfv_encrypt(sealref_ctx *c, const uint64_t *slots, uint64_t *out2)
 {
     REF_TRY

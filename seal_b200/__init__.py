@@ -29,8 +29,17 @@ SYMBOLS = [
     "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
     "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
-    "sb200_mod_switch_to_next_host", "sb200_apply_galois_host",
+    "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
+    "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save",
 ]
+
+
+class CtInfo(C.Structure):
+    """sb200_ct_info: the metadata of one serialized seal::Ciphertext (include/seal_b200.h)"""
+    _fields_ = [("parms_id", C.c_uint64 * 4), ("size", C.c_uint64), ("poly_modulus_degree", C.c_uint64),
+                ("coeff_modulus_size", C.c_uint64), ("correction_factor", C.c_uint64), ("scale", C.c_double),
+                ("is_ntt_form", C.c_int32), ("seeded", C.c_int32), ("data_offset", C.c_uint64), ("data_words", C.c_uint64),
+                ("stream_bytes", C.c_uint64)]
 
 
 def lib():
@@ -89,6 +98,12 @@ def lib():
         L.sb200_rescale_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_mod_switch_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_apply_galois_host.argtypes = [vp, sz, sz, _u64p, u32, vp, _u64p]
+        L.sb200_get_parms_id.argtypes = [vp, sz, _u64p]
+        L.sb200_ciphertext_inspect.argtypes = [C.c_char_p, sz, C.POINTER(CtInfo)]
+        L.sb200_ciphertext_save_size.restype = sz
+        L.sb200_ciphertext_save_size.argtypes = [vp, sz, sz]
+        L.sb200_ciphertext_load.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.POINTER(sz), sz, sz, i32, vp, C.POINTER(CtInfo), vp]
+        L.sb200_ciphertext_save.argtypes = [vp, sz, sz, sz, vp, C.POINTER(CtInfo), C.POINTER(vp), sz, vp]
         _lib = L
     return _lib
 
@@ -96,6 +111,13 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise _STATUS.get(rc, RuntimeError)(f"seal_b200 error {rc}: {lib().sb200_last_error().decode()}")
+
+
+def ciphertext_inspect(stream):
+    """metadata of one Ciphertext::save(compr_mode_type::none) stream (pure host, no context needed)"""
+    info = CtInfo()
+    _check(lib().sb200_ciphertext_inspect(stream, len(stream), C.byref(info)))
+    return info
 
 
 def _hp(a):
@@ -337,6 +359,32 @@ class Context:
 
     def d_multiply_sized(self, a, b, out, L, size_a, size_b, batch):
         _check(lib().sb200_multiply_sized(self.h, L, size_a, size_b, batch, _dp(a), _dp(b), _dp(out), self._stream()))
+
+    def parms_id(self, L):
+        """EncryptionParameters::parms_id() of the level with L primes (L = k: the key level)"""
+        out = (C.c_uint64 * 4)()
+        _check(lib().sb200_get_parms_id(self.h, L, out))
+        return tuple(out)
+
+    def d_load_ciphertexts(self, streams, out, L, size, validate=True):
+        """Ciphertext::load (or unsafe_load) of serialized ciphertexts straight into the device slab `out`"""
+        B = len(streams)
+        arr = (C.c_char_p * B)(*streams)
+        lens = (C.c_size_t * B)(*[len(s) for s in streams])
+        infos = (CtInfo * B)()
+        _check(lib().sb200_ciphertext_load(self.h, B, arr, lens, L, size, 1 if validate else 0, _dp(out), infos, self._stream()))
+        return list(infos)
+
+    def d_save_ciphertexts(self, t, L, size, batch, is_ntt_form, scale=1.0, correction_factor=1):
+        """Ciphertext::save(compr_mode_type::none) of a device slab [batch][size][L][n] -> list of bytes"""
+        cap = lib().sb200_ciphertext_save_size(self.h, L, size)
+        bufs = [C.create_string_buffer(cap) for _ in range(batch)]
+        outs = (C.c_void_p * batch)(*[C.addressof(b) for b in bufs])
+        meta = (CtInfo * batch)()
+        for m in meta:
+            m.is_ntt_form, m.scale, m.correction_factor = int(is_ntt_form), scale, correction_factor
+        _check(lib().sb200_ciphertext_save(self.h, batch, L, size, _dp(t), meta, outs, cap, self._stream()))
+        return [b.raw for b in bufs]
 
     def d_relinearize(self, in3, key, out2, L, batch):
         _check(lib().sb200_relinearize(self.h, L, batch, _dp(in3), key.h, _dp(out2), self._stream()))

@@ -5,6 +5,7 @@
 #include "sb_engine.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <new>
 
 using namespace sb;
@@ -754,6 +755,96 @@ int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const ui
     const size_t w = 2 * L * c.n;
     HostPipe(c).run(batch, w, 0, w, in2, nullptr, out2,
                     [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) { op_apply_galois(c, L, B, da, elt, key->k, dout, st); });
+    return SB200_OK;
+    SB_CATCH
+}
+
+// ---- wire format: Ciphertext::save / load, compr_mode none, between byte streams and device slabs ----
+int sb200_get_parms_id(const sb200_context *ctx, size_t L, uint64_t out[4])
+{
+    SB_NEED(ctx);
+    SB_NEED(out);
+    SB_TRY
+    const Context &c = *ctx->c;
+    if (L < 1 || L > c.k)
+        throw std::out_of_range("L");
+    for (int i = 0; i < 4; i++)
+        out[i] = c.parms_ids[L - 1][i];
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_ciphertext_inspect(const uint8_t *stream, size_t len, sb200_ct_info *info)
+{
+    SB_NEED(info);
+    SB_TRY
+    sbw::inspect(stream, len, *info);
+    return SB200_OK;
+    SB_CATCH
+}
+
+size_t sb200_ciphertext_save_size(const sb200_context *ctx, size_t L, size_t size)
+{
+    return ctx ? sbw::save_size(size * L * ctx->c->n) : 0;
+}
+
+int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const *streams, const size_t *lens, size_t L, size_t size,
+                          int validate, uint64_t *d_out, sb200_ct_info *infos, void *stream)
+{
+    SB_NEED(streams);
+    SB_NEED(lens);
+    SB_NEED(d_out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    auto st = static_cast<cudaStream_t>(stream);
+    const size_t words = size * L * c.n;
+    for (size_t b = 0; b < batch; b++)
+    {
+        sb200_ct_info info;
+        sbw::inspect(streams[b], lens[b], info);
+        if (info.seeded)
+            throw std::logic_error("seeded ciphertexts must be expanded by the reference (Ciphertext::load) first");
+        // is_metadata_valid_for (ciphertext.cpp:299-302): the stream must belong to this context at the level asked for
+        if (info.poly_modulus_degree != c.n || info.coeff_modulus_size != L || info.size != size ||
+            std::memcmp(info.parms_id, c.parms_ids[L - 1].data(), sizeof(info.parms_id)) != 0)
+            throw std::logic_error("ciphertext data is invalid");
+        if (infos)
+            infos[b] = info;
+        cuda_check(cudaMemcpyAsync(d_out + b * words, streams[b] + info.data_offset, words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+    }
+    if (validate && !op_residues_in_range(c, L, batch * size * L, reinterpret_cast<const u64 *>(d_out), st))
+        throw std::logic_error("ciphertext data is invalid"); // Ciphertext::load -> is_valid_for (ciphertext.h:640-655)
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_ciphertext_save(sb200_context *ctx, size_t batch, size_t L, size_t size, const uint64_t *d_in, const sb200_ct_info *meta,
+                          uint8_t *const *outs, size_t capacity, void *stream)
+{
+    SB_NEED(d_in);
+    SB_NEED(meta);
+    SB_NEED(outs);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    auto st = static_cast<cudaStream_t>(stream);
+    const size_t words = size * L * c.n;
+    if (size < 2 || size > 16)
+        throw std::invalid_argument("invalid size");
+    if (capacity < sbw::save_size(words))
+        throw std::invalid_argument("insufficient size"); // Serialization::Save into a too small buffer
+    for (size_t b = 0; b < batch; b++)
+    {
+        if (!outs[b])
+            throw std::invalid_argument("out cannot be null");
+        sb200_ct_info info = meta[b];
+        std::memcpy(info.parms_id, c.parms_ids[L - 1].data(), sizeof(info.parms_id));
+        info.size = size, info.poly_modulus_degree = c.n, info.coeff_modulus_size = L, info.data_words = words;
+        sbw::write_prefix(info, outs[b]);
+        cuda_check(cudaMemcpyAsync(outs[b] + sbw::kDataOffset, d_in + b * words, words * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H");
+    }
+    cuda_check(cudaStreamSynchronize(st), "synchronize");
     return SB200_OK;
     SB_CATCH
 }

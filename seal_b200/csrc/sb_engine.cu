@@ -228,6 +228,12 @@ namespace sb
         cuda_check(cudaMalloc(&c->d_invq, invq.size() * sizeof(Tw)), "cudaMalloc(invq)");
         cuda_check(cudaMemcpy(c->d_invq, invq.data(), invq.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload invq");
         c->table_bytes += hp.size() * sizeof(PrimeDev) + invq.size() * sizeof(Tw);
+        for (size_t L = 1; L <= k; L++)
+        {
+            std::array<u64, 4> id;
+            sbw::parms_id(scheme, n, c->q.data(), L, scheme == 2 ? 0 : t, id.data());
+            c->parms_ids.push_back(id);
+        }
         if (scheme == 3)
         {
             // q_j mod q_i with its Shoup quotient (the "k * q_last" term of the BGV mod-down, rns.cpp:1222-1224)
@@ -1295,6 +1301,33 @@ namespace sb
             base.present = 1;
             key_switch_chunk(c, L, B, s, target, key, base, out2 + b0 * 2 * poly, st);
         }
+    }
+
+    // ---- is_data_valid_for (valcheck.cpp: every coefficient below its modulus), for the checked wire-format load ----
+    __global__ void __launch_bounds__(256) range_check_kernel(const u64 *__restrict__ d, const PrimeDev *__restrict__ primes, int logn, int L,
+                                                               long long total, int *flag)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (e < total && d[e] >= primes[static_cast<int>((e >> logn) % L)].q)
+            atomicOr(flag, 1);
+    }
+    bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st)
+    {
+        int *flag = static_cast<int *>(c.ensure_aux(sizeof(int)));
+        cuda_check(cudaMemsetAsync(flag, 0, sizeof(int), st), "memset");
+        const size_t step = std::max<size_t>(1, (size_t(1) << 31) / c.n);
+        for (size_t r0 = 0; r0 < rows; r0 += step * L)
+        {
+            const long long total = static_cast<long long>(std::min(step * L, rows - r0) * c.n);
+            range_check_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d + r0 * c.n, c.d_primes, c.logn, static_cast<int>(L),
+                                                                                            total, flag);
+            cuda_check(cudaGetLastError(), "range_check_kernel");
+            c.stats.launches++;
+        }
+        int h = 0;
+        cuda_check(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st), "flag D2H");
+        cuda_check(cudaStreamSynchronize(st), "synchronize");
+        return h == 0;
     }
 
     // ------------------------------------------------------------------------- rescale / modulus switching ----

@@ -2,6 +2,8 @@
 #pragma once
 #include "sb_host.hpp"
 #include "sb_ntt.cuh"
+#include "sb_wire.hpp"
+#include <array>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -52,6 +54,7 @@ namespace sb
         Tw *d_qmod = nullptr;                // BGV, [k][k]: d_qmod[j*k+i] = q_j mod q_i
         u64 t_ratio = 0;                     // BGV: floor(2^64 / t)
         std::vector<u64> inv_q_mod_t;        // BGV: q_j^-1 mod t
+        std::vector<std::array<u64, 4>> parms_ids; // parms_ids[L-1] = parms_id of the level with L primes (sb_wire.hpp)
         std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
         std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
         void *scratch = nullptr;
@@ -95,4 +98,6 @@ namespace sb
     void op_apply_galois(Context &c, size_t L, size_t batch, const u64 *in2, uint32_t elt, const KSwitchKey &key, u64 *out2,
                          cudaStream_t st);
     const sbh::BehzLevel &behz_host(Context &c, size_t L);
+    // wire format support (sb_api.cu): 1 if any residue of data [rows][n] (prime of a row = row % L) is >= its modulus
+    bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st);
 } // namespace sb

@@ -1,6 +1,7 @@
 // tests/cpp/host_probe.cpp -- exposes the product's host-side precomputation (seal_b200/csrc/sb_host.cpp, no CUDA) to
 // the CPU test-suite so tables can be compared with the oracle / reference without a GPU.
 #include "../../seal_b200/csrc/sb_host.hpp"
+#include "../../seal_b200/csrc/sb_wire.hpp"
 #include <cstring>
 
 extern "C" {
@@ -57,5 +58,10 @@ unsigned probe_elt_from_step(size_t n, int step)
         return 0;
     }
 }
+void probe_parms_id(int scheme, size_t n, const unsigned long long *q, size_t L, unsigned long long t, unsigned long long *out4)
+{
+    sbw::parms_id(scheme, n, q, L, t, out4);
+}
+void probe_blake2b_256(const void *in, size_t len, unsigned long long *out4) { sbw::blake2b_256(in, len, out4); }
 int probe_is_prime(unsigned long long v) { return sbh::is_prime(v) ? 1 : 0; }
 }

@@ -58,6 +58,13 @@ def lib():
         L.sealref_bfv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int)]
         L.sealref_time_op.restype = C.c_double
         L.sealref_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]
+        L.sealref_parms_id.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.sealref_ct_save.restype = C.c_long
+        L.sealref_ct_save.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, C.c_int, C.c_double, C.c_uint64, C.c_char_p, C.c_size_t]
+        L.sealref_ct_load.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, _u64p, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_double), _u64p]
+        L.sealref_seeded_ct_stream.restype = C.c_long
+        L.sealref_seeded_ct_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -225,6 +232,36 @@ class RefContext:
         nb = C.c_int(0)
         self._chk(lib().sealref_bfv_decrypt(self.h, L, ct.shape[0], _p(ct), _p(out), C.byref(nb)))
         return out, nb.value
+
+    def parms_id(self, L):
+        out = np.zeros(4, dtype=np.uint64)
+        self._chk(lib().sealref_parms_id(self.h, L, _p(out)))
+        return tuple(int(x) for x in out)
+
+    def ct_save(self, L, data, is_ntt_form, scale=1.0, correction_factor=1):
+        """Ciphertext::save(compr_mode_type::none) of [size][L][n] words"""
+        data = np.ascontiguousarray(data)
+        buf = C.create_string_buffer(data.nbytes + 4096)
+        ln = lib().sealref_ct_save(self.h, L, data.shape[0], _p(data), int(is_ntt_form), scale, correction_factor, buf, len(buf))
+        if ln < 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+        return buf.raw[:ln]
+
+    def ct_load(self, stream, max_size=16):
+        """Ciphertext::load -> (data [size][L][n], is_ntt_form, scale, correction_factor)"""
+        out = np.zeros(max_size * self.k * self.n, dtype=np.uint64)
+        size, L, cf = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        ntt, scale = C.c_int(0), C.c_double(0)
+        self._chk(lib().sealref_ct_load(self.h, stream, len(stream), _p(out), out.size, C.byref(size), C.byref(L), C.byref(ntt),
+                                        C.byref(scale), C.byref(cf)))
+        return out[: size.value * L.value * self.n].reshape(size.value, L.value, self.n).copy(), bool(ntt.value), scale.value, cf.value
+
+    def seeded_ct_stream(self):
+        buf = C.create_string_buffer(2 * self.k * self.n * 8 + 4096)
+        ln = lib().sealref_seeded_ct_stream(self.h, buf, len(buf))
+        if ln < 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+        return buf.raw[:ln]
 
     def time_op(self, op, L, threads, reps):
         t = lib().sealref_time_op(self.h, op, L, threads, reps)

@@ -363,6 +363,56 @@ def test_general_size_multiply_vs_reference(scheme):
         ctx.multiply(rand_ct(rng, mods, n, 9, 1, 1), rand_ct(rng, mods, n, 9, 1, 1))  # 17 polynomials > SEAL_CIPHERTEXT_SIZE_MAX
 
 
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv"])
+def test_wire_format_vs_reference(scheme):
+    # Ciphertext::save / load (compr_mode none) between byte streams and device slabs
+    import torch
+
+    n, batch, L, size = 4096, 3, 2, 2
+    mods = R.coeff_modulus_create(n, [50, 45, 60])
+    sid = R.CKKS if scheme == "ckks" else R.BFV
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 20)
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    for lv in (3, 2, 1):
+        assert ctx.parms_id(lv) == rc.parms_id(lv)
+    rng = np.random.default_rng(47)
+    data = rand_ct(rng, mods, n, size, L, batch)
+    ntt, scale = scheme == "ckks", (2.0 ** 40 if scheme == "ckks" else 1.0)
+    streams = [rc.ct_save(L, data[i], ntt, scale) for i in range(batch)]
+    dev = torch.zeros((batch, size, L, n), dtype=torch.int64, device="cuda")
+    infos = ctx.d_load_ciphertexts(streams, dev, L, size)
+    torch.cuda.synchronize()
+    assert (dev.cpu().numpy().view(np.uint64) == data).all()
+    assert all(i.is_ntt_form == int(ntt) and i.scale == scale for i in infos)
+    # save: byte-identical to the reference's own stream, and the reference loads it back
+    saved = ctx.d_save_ciphertexts(dev, L, size, batch, ntt, scale)
+    assert saved == streams
+    back, b_ntt, b_scale, b_cf = rc.ct_load(saved[1])
+    assert (back == data[1]).all() and b_ntt == ntt and b_scale == scale and b_cf == 1
+    # a pipeline that never leaves the device between load and save
+    if scheme == "ckks":
+        rk = ctx.load_key(rc.relin_key())
+        out = torch.empty_like(dev)
+        ctx.d_multiply_relinearize(dev, dev, rk, out, L, batch)
+        res = ctx.d_save_ciphertexts(out, L, size, batch, True, scale * scale)
+        got, _, g_scale, _ = rc.ct_load(res[0])
+        assert (got == rc.multiply_relin(L, data[0], data[0])).all() and g_scale == scale * scale
+    # Ciphertext::load rejects residues >= q_i (is_data_valid_for); unsafe_load does not look
+    bad = bytearray(streams[0])
+    off = infos[0].data_offset
+    bad[off:off + 8] = int(mods[0]).to_bytes(8, "little")
+    with pytest.raises(RuntimeError):
+        ctx.d_load_ciphertexts([bytes(bad)], dev, L, size)
+    ctx.d_load_ciphertexts([bytes(bad)], dev, L, size, validate=False)
+    # a stream of another level / another context
+    with pytest.raises(RuntimeError):
+        ctx.d_load_ciphertexts([rc.ct_save(1, data[0][:, :1], ntt, scale)], dev, L, size)
+    with pytest.raises(RuntimeError):
+        ctx.d_load_ciphertexts([rc.seeded_ct_stream()], dev, 2, 2)
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

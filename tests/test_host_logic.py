@@ -120,6 +120,8 @@ def _probe():
     L.probe_elt_from_step.restype = C.c_uint32
     L.probe_elt_from_step.argtypes = [C.c_size_t, C.c_int]
     L.probe_is_prime.argtypes = [C.c_uint64]
+    L.probe_parms_id.argtypes = [C.c_int, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
+    L.probe_blake2b_256.argtypes = [C.c_char_p, C.c_size_t, u64p]
     return L
 
 
@@ -177,3 +179,69 @@ def test_host_galois_and_behz_match_oracle():
         cnt = P.probe_bsk(n, _pp(np.array(q, dtype=np.uint64)), len(q), tt, _pp(out))
         assert [int(v) for v in out[:cnt]] == O.behz_base(n, q, tt)
     assert P.probe_is_prime(0xFFFFEE001) == 1 and P.probe_is_prime(0xFFFFEE003) == O.lib().orc_is_prime(0xFFFFEE003)
+
+
+# ---- wire format: parms_id hashing and stream parsing are pure host code ---------------------------
+def test_blake2b_matches_hashlib():
+    import hashlib
+
+    P = _probe()
+    rng = np.random.default_rng(5)
+    for ln in (0, 1, 24, 127, 128, 129, 256, 1000):
+        msg = rng.integers(0, 256, ln, dtype=np.uint8).tobytes()
+        out = np.zeros(4, dtype=np.uint64)
+        P.probe_blake2b_256(msg, ln, _pp(out))
+        assert out.tobytes() == hashlib.blake2b(msg, digest_size=32).digest()
+
+
+@pytest.mark.skipif(not __import__("refseal").available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scheme", ["bfv", "ckks", "bgv"])
+def test_parms_id_matches_reference(scheme):
+    import refseal as R
+
+    P = _probe()
+    n = 1024
+    mods = R.coeff_modulus_create(n, [40, 41, 42, 43])
+    sid = {"bfv": R.BFV, "ckks": R.CKKS, "bgv": R.BGV}[scheme]
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 17)
+    rc = R.RefContext(sid, n, mods, t)
+    q = np.array(mods, dtype=np.uint64)
+    for L in (4, 3, 2, 1):  # 4 = the key level
+        out = np.zeros(4, dtype=np.uint64)
+        P.probe_parms_id(sid, n, _pp(q), L, t, _pp(out))
+        assert tuple(int(x) for x in out) == rc.parms_id(L)
+
+
+@pytest.mark.skipif(not __import__("refseal").available(), reason="oracle/_ref not built")
+def test_ciphertext_inspect_vs_reference_stream():
+    import refseal as R
+    import seal_b200 as S
+    from common import rand_ct
+
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42])
+    rc = R.RefContext(R.CKKS, n, mods)
+    rng = np.random.default_rng(6)
+    for L, size in ((2, 2), (1, 3)):
+        data = rand_ct(rng, mods, n, size, L)
+        stream = rc.ct_save(L, data, True, scale=2.0 ** 30, correction_factor=1)
+        info = S.ciphertext_inspect(stream)
+        assert tuple(info.parms_id) == rc.parms_id(L)
+        assert (info.size, info.poly_modulus_degree, info.coeff_modulus_size) == (size, n, L)
+        assert info.is_ntt_form == 1 and info.seeded == 0 and info.scale == 2.0 ** 30 and info.correction_factor == 1
+        assert info.stream_bytes == len(stream) and info.data_words == data.size
+        words = np.frombuffer(stream, dtype=np.uint64, count=data.size, offset=info.data_offset)
+        assert (words == data.reshape(-1)).all()
+    # seed-compressed ciphertexts are recognised (and left to the reference)
+    assert S.ciphertext_inspect(rc.seeded_ct_stream()).seeded == 1
+    # malformed streams: Serialization::Load's error ladder
+    with pytest.raises(ValueError):
+        S.ciphertext_inspect(stream[:8])                       # insufficient size
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(b"\x00\x00" + stream[2:])         # bad magic
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(stream[:3] + b"\x05" + stream[4:])  # newer major version
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(stream[:5] + b"\x02" + stream[6:])  # compressed
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(stream[:-8])                      # truncated
