@@ -81,6 +81,11 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
  * ciphertext it is used with (evaluator.cpp:2635). */
 int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out);
 int sb200_kswitch_key_destroy(sb200_kswitch_key *key);
+/* KSwitchKeys::load of the single entry data()[index] out of a RelinKeys / GaloisKeys stream saved with
+ * compr_mode_type::none (kswitchkeys.cpp:42-160): the key polynomials go from the stream to the device directly.
+ * index = RelinKeys::get_index(2) = 0 for relinearization, GaloisKeys::get_index(galois_elt) = (galois_elt - 1) / 2 for a
+ * rotation (relinkeys.h:58-65, galoiskeys.h:48-51).  SB200_E_OUT_OF_RANGE: no such slot; SB200_E_INVALID_ARG: empty slot. */
+int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len, size_t index, sb200_kswitch_key **out);
 
 /* ---- device-resident batch operations (stream = cudaStream_t, may be NULL) ----------------------------------
  * Output slabs must not alias input slabs unless noted: multiply_relinearize may write over d_a or d_b, add/sub/negate/multiply_plain

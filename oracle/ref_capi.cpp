@@ -448,6 +448,16 @@ extern "C" int sealref_ct_load(
     REF_CATCH(-1)
 }
 
+// RelinKeys / GaloisKeys::save(compr_mode_type::none); galois_elt == 0 selects the relinearization keys
+extern "C" long sealref_kswitch_keys_stream(sealref_ctx *c, uint32_t galois_elt, uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    if (galois_elt == 0)
+        return static_cast<long>(relin_keys(c).save(reinterpret_cast<seal_byte *>(out), capacity, compr_mode_type::none));
+    return static_cast<long>(galois_for(c, galois_elt).save(reinterpret_cast<seal_byte *>(out), capacity, compr_mode_type::none));
+    REF_CATCH(-1)
+}
+
 // a seed-compressed ciphertext as Encryptor::encrypt_zero_symmetric(...).save() writes it (c_1 replaced by its PRNG seed)
 extern "C" long sealref_seeded_ct_stream(sealref_ctx *c, uint8_t *out, size_t capacity)
 {

@@ -25,7 +25,7 @@ SYMBOLS = [
     "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
-    "sb200_kswitch_key_create", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
+    "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
     "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
     "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
@@ -70,6 +70,7 @@ def lib():
                                          C.POINTER(C.c_double)]
         L.sb200_kswitch_key_create.argtypes = [vp, _u64p, sz, C.POINTER(vp)]
         L.sb200_kswitch_key_destroy.argtypes = [vp]
+        L.sb200_kswitch_key_load.argtypes = [vp, C.c_char_p, sz, sz, C.POINTER(vp)]
         L.sb200_ntt_forward.argtypes = [vp, sz, sz, sz, vp, vp]
         L.sb200_ntt_inverse.argtypes = [vp, sz, sz, sz, vp, vp]
         L.sb200_multiply.argtypes = [vp, sz, sz, vp, vp, vp, vp]
@@ -144,7 +145,14 @@ def coeff_modulus_create(n, bits):
 class KSwitchKey:
     """Device copy of one KSwitchKeys::data()[index] entry ([digit][2][k][n])."""
 
-    def __init__(self, ctx, host_key):
+    def __init__(self, ctx, host_key, stream_index=None):
+        self.ctx = ctx
+        if stream_index is not None:
+            # host_key is a serialized RelinKeys / GaloisKeys object (KSwitchKeys::save, compr_mode none)
+            h = C.c_void_p()
+            _check(lib().sb200_kswitch_key_load(ctx.h, host_key, len(host_key), stream_index, C.byref(h)))
+            self.h = h
+            return
         host_key = np.ascontiguousarray(host_key, dtype=np.uint64)
         assert host_key.ndim == 4 and host_key.shape[1] == 2 and host_key.shape[2] == ctx.k and host_key.shape[3] == ctx.n
         self.ctx = ctx
@@ -228,6 +236,10 @@ class Context:
 
     def load_key(self, host_key):
         return KSwitchKey(self, host_key)
+
+    def load_key_stream(self, stream, index=0):
+        """KSwitchKeys::load of data()[index] from a serialized RelinKeys (index 0) / GaloisKeys ((elt - 1) // 2) object"""
+        return KSwitchKey(self, stream, stream_index=index)
 
     # ---- host-buffer API: a is [batch][size][L][n] (or [size][L][n] for a single ciphertext) ----
     @staticmethod

@@ -19,6 +19,7 @@ struct sb200_context
 struct sb200_kswitch_key
 {
     KSwitchKey k;
+    ~sb200_kswitch_key() { cudaFree(k.d_key); }
 };
 
 #define SB_TRY try {
@@ -257,10 +258,39 @@ int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t d
     SB_CATCH
 }
 
+int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len, size_t index, sb200_kswitch_key **out)
+{
+    SB_NEED(ctx);
+    SB_NEED(stream);
+    SB_NEED(out);
+    SB_TRY
+    Context &c = *ctx->c;
+    if (c.k < 2)
+        throw std::logic_error("keyswitching is not supported by the context");
+    sbw::KSwitchEntry e;
+    sbw::inspect_kswitch(stream, len, index, e);
+    // is_valid_for(KSwitchKeys): keys live at the key level of this context (valcheck.cpp, kswitchkeys.cpp:149-153)
+    if (e.n != c.n || e.L != c.k || std::memcmp(e.parms_id, c.parms_ids[c.k - 1].data(), sizeof(e.parms_id)) != 0)
+        throw std::logic_error("KSwitchKeys data is invalid");
+    const size_t digits = e.offsets.size();
+    if (digits > c.k - 1)
+        throw std::logic_error("KSwitchKeys data is invalid");
+    auto h = std::make_unique<sb200_kswitch_key>();
+    const size_t row = 2 * c.k * c.n * sizeof(u64);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    cuda_check(cudaMalloc(reinterpret_cast<void **>(&h->k.d_key), digits * row), "cudaMalloc(key)");
+    for (size_t j = 0; j < digits; j++)
+        cuda_check(cudaMemcpy(reinterpret_cast<uint8_t *>(h->k.d_key) + j * row, stream + e.offsets[j], row, cudaMemcpyHostToDevice), "upload key");
+    h->k.ctx = &c;
+    h->k.digits = digits;
+    *out = h.release();
+    return SB200_OK;
+    SB_CATCH
+}
+
 int sb200_kswitch_key_destroy(sb200_kswitch_key *key)
 {
     SB_NEED(key);
-    cudaFree(key->k.d_key);
     delete key;
     return SB200_OK;
 }

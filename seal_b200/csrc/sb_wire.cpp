@@ -193,4 +193,52 @@ namespace sbw
         put(w, h);
         put<uint64_t>(w, info.data_words);
     }
+    void inspect_kswitch(const uint8_t *p, size_t len, size_t index, KSwitchEntry &entry)
+    {
+        if (!p)
+            throw std::invalid_argument("in cannot be null");
+        if (len < kHeaderBytes)
+            throw std::invalid_argument("insufficient size");
+        const Header outer = read_header(p);
+        if (outer.size > len || outer.size < kHeaderBytes + 32 + 8)
+            throw std::logic_error("loaded SEALHeader is invalid");
+        const uint8_t *r = p + kHeaderBytes, *end = p + outer.size;
+        for (int i = 0; i < 4; i++)
+            entry.parms_id[i] = take<uint64_t>(r);
+        const uint64_t dim1 = take<uint64_t>(r);
+        if (dim1 > 131072)
+            throw std::logic_error("KSwitchKeys outer dimension is invalid"); // kswitchkeys.cpp:121-125
+        entry.slots = static_cast<size_t>(dim1);
+        entry.offsets.clear();
+        if (index >= dim1)
+            throw std::out_of_range("kswitch_keys_index");
+        for (uint64_t slot = 0; slot < dim1; slot++)
+        {
+            if (static_cast<size_t>(end - r) < 8)
+                throw std::logic_error("loaded data is invalid");
+            const uint64_t dim2 = take<uint64_t>(r);
+            if (dim2 > 256)
+                throw std::logic_error("KSwitchKeys inner dimension is invalid");
+            for (uint64_t j = 0; j < dim2; j++)
+            {
+                sb200_ct_info info;
+                inspect(r, static_cast<size_t>(end - r), info);
+                if (slot == index)
+                {
+                    if (info.seeded)
+                        throw std::logic_error("seeded keys must be expanded by the reference (KSwitchKeys::load) first");
+                    if (info.size != 2 || !info.is_ntt_form || std::memcmp(info.parms_id, entry.parms_id, sizeof(info.parms_id)) != 0 ||
+                        (j > 0 && (info.coeff_modulus_size != entry.L || info.poly_modulus_degree != entry.n)))
+                        throw std::logic_error("key data is invalid");
+                    entry.L = static_cast<size_t>(info.coeff_modulus_size), entry.n = static_cast<size_t>(info.poly_modulus_degree);
+                    entry.offsets.push_back(static_cast<size_t>(r - p) + static_cast<size_t>(info.data_offset));
+                }
+                r += info.stream_bytes;
+            }
+            if (slot == index)
+                break; // later slots are not needed
+        }
+        if (entry.offsets.empty())
+            throw std::invalid_argument("key not present"); // an empty slot (relinkeys.h:84-95, galoiskeys.h:75-86)
+    }
 } // namespace sbw

@@ -8,6 +8,7 @@
 #include "../../include/seal_b200.h"
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace sbw
 {
@@ -27,4 +28,15 @@ namespace sbw
     inline size_t save_size(size_t words) { return kDataOffset + 8 * words; }
     // writes everything in front of the coefficient words (kDataOffset bytes) for a ciphertext of info.data_words words
     void write_prefix(const sb200_ct_info &info, uint8_t *out);
+    // One entry of a serialized KSwitchKeys object (RelinKeys / GaloisKeys saved with compr_mode_type::none,
+    // kswitchkeys.cpp:42-86: SEALHeader, parms_id, dim1, then per slot dim2 and dim2 PublicKey = Ciphertext streams).
+    // Returns the byte offsets (from p) of the coefficient words of data()[index][j], j < digits, each 2*L*n words.
+    struct KSwitchEntry
+    {
+        u64 parms_id[4];
+        size_t slots = 0;               // data().size()
+        size_t L = 0, n = 0;            // shape of every key polynomial pair
+        std::vector<size_t> offsets;    // one per decomposition digit
+    };
+    void inspect_kswitch(const uint8_t *p, size_t len, size_t index, KSwitchEntry &entry);
 } // namespace sbw

@@ -3,6 +3,7 @@
 #include "../../seal_b200/csrc/sb_host.hpp"
 #include "../../seal_b200/csrc/sb_wire.hpp"
 #include <cstring>
+#include <stdexcept>
 
 extern "C" {
 int probe_tables(size_t n, unsigned long long q, unsigned long long *root, unsigned long long *rp, unsigned long long *rpq,
@@ -63,5 +64,31 @@ void probe_parms_id(int scheme, size_t n, const unsigned long long *q, size_t L,
     sbw::parms_id(scheme, n, q, L, t, out4);
 }
 void probe_blake2b_256(const void *in, size_t len, unsigned long long *out4) { sbw::blake2b_256(in, len, out4); }
+// offsets of data()[index][j] inside a serialized KSwitchKeys object; returns the digit count or a negative status
+long probe_kswitch_offsets(const unsigned char *stream, size_t len, size_t index, size_t *offsets, size_t capacity, size_t *L, size_t *n)
+{
+    try
+    {
+        sbw::KSwitchEntry e;
+        sbw::inspect_kswitch(stream, len, index, e);
+        if (e.offsets.size() > capacity)
+            return -4;
+        std::memcpy(offsets, e.offsets.data(), e.offsets.size() * sizeof(size_t));
+        *L = e.L, *n = e.n;
+        return static_cast<long>(e.offsets.size());
+    }
+    catch (const std::out_of_range &)
+    {
+        return -3;
+    }
+    catch (const std::invalid_argument &)
+    {
+        return -1;
+    }
+    catch (...)
+    {
+        return -2;
+    }
+}
 int probe_is_prime(unsigned long long v) { return sbh::is_prime(v) ? 1 : 0; }
 }

@@ -63,6 +63,8 @@ def lib():
         L.sealref_ct_save.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, C.c_int, C.c_double, C.c_uint64, C.c_char_p, C.c_size_t]
         L.sealref_ct_load.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, _u64p, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int),
                                       C.POINTER(C.c_double), _u64p]
+        L.sealref_kswitch_keys_stream.restype = C.c_long
+        L.sealref_kswitch_keys_stream.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]
         L.sealref_seeded_ct_stream.restype = C.c_long
         L.sealref_seeded_ct_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         _lib = L
@@ -255,6 +257,14 @@ class RefContext:
         self._chk(lib().sealref_ct_load(self.h, stream, len(stream), _p(out), out.size, C.byref(size), C.byref(L), C.byref(ntt),
                                         C.byref(scale), C.byref(cf)))
         return out[: size.value * L.value * self.n].reshape(size.value, L.value, self.n).copy(), bool(ntt.value), scale.value, cf.value
+
+    def kswitch_keys_stream(self, galois_elt=0):
+        """RelinKeys::save (galois_elt == 0) or GaloisKeys::save of the keys holding that element, compr_mode none"""
+        buf = C.create_string_buffer((self.k - 1) * 2 * self.k * self.n * 8 + 8 * self.n + (1 << 16))
+        ln = lib().sealref_kswitch_keys_stream(self.h, galois_elt, buf, len(buf))
+        if ln < 0:
+            raise RuntimeError(lib().sealref_last_error().decode())
+        return buf.raw[:ln]
 
     def seeded_ct_stream(self):
         buf = C.create_string_buffer(2 * self.k * self.n * 8 + 4096)

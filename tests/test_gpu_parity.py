@@ -399,6 +399,17 @@ def test_wire_format_vs_reference(scheme):
         res = ctx.d_save_ciphertexts(out, L, size, batch, True, scale * scale)
         got, _, g_scale, _ = rc.ct_load(res[0])
         assert (got == rc.multiply_relin(L, data[0], data[0])).all() and g_scale == scale * scale
+    # keys from a serialized RelinKeys / GaloisKeys object (KSwitchKeys::load of one entry)
+    m = ctx.multiply(data, data)
+    rk_s = ctx.load_key_stream(rc.kswitch_keys_stream(0), 0)
+    assert (ctx.relinearize(m, rk_s) == ctx.relinearize(m, ctx.load_key(rc.relin_key()))).all()
+    e = rc.galois_elt_from_step(1)
+    gk_s = ctx.load_key_stream(rc.kswitch_keys_stream(e), (e - 1) // 2)
+    assert (ctx.apply_galois(data, e, gk_s)[0] == rc.apply_galois(L, data[0], e)).all()
+    with pytest.raises(ValueError):
+        ctx.load_key_stream(rc.kswitch_keys_stream(e), 0)  # empty slot
+    with pytest.raises(IndexError):
+        ctx.load_key_stream(rc.kswitch_keys_stream(0), 5)
     # Ciphertext::load rejects residues >= q_i (is_data_valid_for); unsafe_load does not look
     bad = bytearray(streams[0])
     off = infos[0].data_offset

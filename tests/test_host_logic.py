@@ -122,6 +122,9 @@ def _probe():
     L.probe_is_prime.argtypes = [C.c_uint64]
     L.probe_parms_id.argtypes = [C.c_int, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
     L.probe_blake2b_256.argtypes = [C.c_char_p, C.c_size_t, u64p]
+    L.probe_kswitch_offsets.restype = C.c_long
+    L.probe_kswitch_offsets.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_size_t)]
     return L
 
 
@@ -245,3 +248,35 @@ def test_ciphertext_inspect_vs_reference_stream():
         S.ciphertext_inspect(stream[:5] + b"\x02" + stream[6:])  # compressed
     with pytest.raises(RuntimeError):
         S.ciphertext_inspect(stream[:-8])                      # truncated
+
+
+@pytest.mark.skipif(not __import__("refseal").available(), reason="oracle/_ref not built")
+def test_kswitch_keys_stream_parsing_vs_reference():
+    # KSwitchKeys::save layout (kswitchkeys.cpp:42-86): the product locates data()[index][j] inside the stream
+    import ctypes as C
+
+    import refseal as R
+
+    P = _probe()
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42, 43])
+    k = len(mods)
+    rc = R.RefContext(R.CKKS, n, mods)
+
+    def entry(stream, index):
+        offs = (C.c_size_t * 16)()
+        L, nn = C.c_size_t(0), C.c_size_t(0)
+        d = P.probe_kswitch_offsets(stream, len(stream), index, offs, 16, C.byref(L), C.byref(nn))
+        if d < 0:
+            return d
+        assert (L.value, nn.value) == (k, n)
+        return np.stack([np.frombuffer(stream, dtype=np.uint64, count=2 * k * n, offset=offs[j]).reshape(2, k, n) for j in range(d)])
+
+    rs = rc.kswitch_keys_stream(0)
+    assert (entry(rs, 0) == rc.relin_key()).all()
+    assert entry(rs, 1) == -3  # out of range: RelinKeys made for size-3 ciphertexts hold one entry
+    e = rc.galois_elt_from_step(1)
+    gs = rc.kswitch_keys_stream(e)
+    assert (entry(gs, (e - 1) // 2) == rc.galois_key(e)).all()
+    assert entry(gs, 0) == -1  # an empty slot: "key not present"
+    assert entry(gs[:200], (e - 1) // 2) == -2  # truncated
