@@ -186,6 +186,148 @@ namespace seal_b200
             multiply_plain_inplace(destination, plain, std::move(pool));
         }
 
+        // ---- add_plain / sub_plain for CKKS (evaluator.cpp:1759-1868, :1870-1975): the NTT-form plaintext joins c_0 ---------
+        // BFV / BGV plaintexts need the scaling-variant lift (util/scalingvariant.cpp) and stay with the reference.
+        void add_plain_inplace(seal::Ciphertext &encrypted, const seal::Plaintext &plain,
+                               seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            plain_linear(encrypted, plain, false);
+            (void)pool;
+        }
+        void add_plain(const seal::Ciphertext &encrypted, const seal::Plaintext &plain, seal::Ciphertext &destination,
+                       seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            add_plain_inplace(destination, plain, std::move(pool));
+        }
+        void sub_plain_inplace(seal::Ciphertext &encrypted, const seal::Plaintext &plain,
+                               seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            plain_linear(encrypted, plain, true);
+            (void)pool;
+        }
+        void sub_plain(const seal::Ciphertext &encrypted, const seal::Plaintext &plain, seal::Ciphertext &destination,
+                       seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            sub_plain_inplace(destination, plain, std::move(pool));
+        }
+
+        // ---- compositions the reference builds from the operations above ---------------------------------------------
+        // add_many (evaluator.cpp:236-262)
+        void add_many(const std::vector<seal::Ciphertext> &encrypteds, seal::Ciphertext &destination) const
+        {
+            if (encrypteds.empty())
+                throw std::invalid_argument("encrypteds cannot be empty");
+            for (auto &e : encrypteds)
+                if (&e == &destination)
+                    throw std::invalid_argument("encrypteds must be different from destination");
+            destination = encrypteds[0];
+            for (std::size_t i = 1; i < encrypteds.size(); i++)
+                add_inplace(destination, encrypteds[i]);
+        }
+        // multiply_many (evaluator.cpp:1649-1724): pairwise products, each relinearized, appended until one is left
+        void multiply_many(const std::vector<seal::Ciphertext> &encrypteds, const seal::RelinKeys &relin_keys, seal::Ciphertext &destination,
+                           seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (encrypteds.empty())
+                throw std::invalid_argument("encrypteds vector must not be empty");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            for (auto &e : encrypteds)
+                if (&e == &destination)
+                    throw std::invalid_argument("encrypteds must be different from destination");
+            if (!context_.get_context_data(encrypteds[0].parms_id()))
+                throw std::invalid_argument("encrypteds is not valid for encryption parameters");
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::bgv)
+                throw std::logic_error("unsupported scheme");
+            if (encrypteds.size() == 1)
+            {
+                destination = encrypteds[0];
+                return;
+            }
+            std::vector<seal::Ciphertext> products;
+            for (std::size_t i = 0; i + 1 < encrypteds.size(); i += 2)
+            {
+                seal::Ciphertext temp;
+                if (encrypteds[i].data() == encrypteds[i + 1].data())
+                    square(encrypteds[i], temp);
+                else
+                    multiply(encrypteds[i], encrypteds[i + 1], temp);
+                relinearize_inplace(temp, relin_keys, pool);
+                products.emplace_back(std::move(temp));
+            }
+            if (encrypteds.size() & 1)
+                products.emplace_back(encrypteds.back());
+            for (std::size_t i = 0; i + 1 < products.size(); i += 2)
+            {
+                seal::Ciphertext temp;
+                multiply(products[i], products[i + 1], temp);
+                relinearize_inplace(temp, relin_keys, pool);
+                products.emplace_back(std::move(temp));
+            }
+            destination = products.back();
+        }
+        // exponentiate (evaluator.cpp:1726-1757)
+        void exponentiate_inplace(seal::Ciphertext &encrypted, std::uint64_t exponent, const seal::RelinKeys &relin_keys,
+                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (!context_.get_context_data(encrypted.parms_id()))
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (!context_.get_context_data(relin_keys.parms_id()))
+                throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            if (exponent == 0)
+                throw std::invalid_argument("exponent cannot be 0");
+            if (exponent == 1)
+                return;
+            std::vector<seal::Ciphertext> copies(static_cast<std::size_t>(exponent), encrypted);
+            multiply_many(copies, relin_keys, encrypted, std::move(pool));
+        }
+        void exponentiate(const seal::Ciphertext &encrypted, std::uint64_t exponent, const seal::RelinKeys &relin_keys,
+                          seal::Ciphertext &destination, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            exponentiate_inplace(destination, exponent, relin_keys, std::move(pool));
+        }
+        // mod_switch_to / rescale_to (evaluator.cpp:1451-1473, :1543-1590): repeat the single step down to parms_id
+        void mod_switch_to_inplace(seal::Ciphertext &encrypted, seal::parms_id_type parms_id,
+                                   seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            check_target_level(encrypted, parms_id);
+            while (encrypted.parms_id() != parms_id)
+                mod_switch_to_next_inplace(encrypted, pool);
+        }
+        void mod_switch_to(const seal::Ciphertext &encrypted, seal::parms_id_type parms_id, seal::Ciphertext &destination,
+                           seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            mod_switch_to_inplace(destination, parms_id, std::move(pool));
+        }
+        void rescale_to_inplace(seal::Ciphertext &encrypted, seal::parms_id_type parms_id,
+                                seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            check_target_level(encrypted, parms_id);
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::invalid_argument("unsupported operation for scheme type");
+            while (encrypted.parms_id() != parms_id)
+            {
+                seal::Ciphertext next;
+                mod_switch_impl(encrypted, next, true);
+                encrypted = std::move(next);
+            }
+        }
+        void rescale_to(const seal::Ciphertext &encrypted, seal::parms_id_type parms_id, seal::Ciphertext &destination,
+                        seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            rescale_to_inplace(destination, parms_id, std::move(pool));
+        }
+
         // ---- relinearize (evaluator.cpp:1144-1199) ---------------------------------------------------------------
         void relinearize_inplace(seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys,
                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
@@ -488,6 +630,38 @@ namespace seal_b200
                 }
             }
             f = multiply_uint_mod(e1, factor1, plain);
+        }
+        void check_target_level(const seal::Ciphertext &encrypted, const seal::parms_id_type &parms_id) const
+        {
+            auto cur = context_.get_context_data(encrypted.parms_id());
+            auto target = context_.get_context_data(parms_id);
+            if (!cur)
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (!target)
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            if (cur->chain_index() < target->chain_index())
+                throw std::invalid_argument("cannot switch to higher level modulus");
+        }
+        void plain_linear(seal::Ciphertext &encrypted, const seal::Plaintext &plain, bool subtract) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (!seal::is_metadata_valid_for(plain, context_) || !seal::is_buffer_valid(plain))
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::invalid_argument("seal_b200: add_plain / sub_plain are implemented for CKKS");
+            if (!encrypted.is_ntt_form())
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (!plain.is_ntt_form())
+                throw std::invalid_argument("CKKS plain must be in NTT form");
+            if (encrypted.parms_id() != plain.parms_id())
+                throw std::invalid_argument("encrypted and plain parameter mismatch");
+            if (!seal::util::are_close<double>(encrypted.scale(), plain.scale()))
+                throw std::invalid_argument("scale mismatch");
+            const std::size_t L = encrypted.coeff_modulus_size();
+            // c_0 +/- plain: a one-polynomial slab (add_poly_coeffmod / sub_poly_coeffmod on encrypted[0], :1831-1836)
+            check(subtract ? sb200_sub_host(ctx_, L, 1, 1, encrypted.data(), plain.data(), encrypted.data())
+                           : sb200_add_host(ctx_, L, 1, 1, encrypted.data(), plain.data(), encrypted.data()));
+            throw_if_transparent(encrypted);
         }
         static void check(int status)
         {

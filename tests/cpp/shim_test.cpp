@@ -187,6 +187,35 @@ static void test_ckks()
         gpu.square(c3, g2);
         CHECK(r2.size() == 5 && same_ct(r2, g2));
     }
+    {
+        // add_plain / sub_plain (CKKS), add_many, mod_switch_to / rescale_to
+        Ciphertext r2, g2;
+        ref.add_plain(cx, py, r2);
+        gpu.add_plain(cx, py, g2);
+        CHECK(same_ct(r2, g2));
+        ref.sub_plain_inplace(r2, px);
+        gpu.sub_plain_inplace(g2, px);
+        CHECK(same_ct(r2, g2));
+        std::vector<Ciphertext> many{ cx, cy, r2 };
+        ref.add_many(many, r2);
+        gpu.add_many(many, g2);
+        CHECK(same_ct(r2, g2));
+        auto last = context.last_parms_id();
+        ref.mod_switch_to(cx, last, r2);
+        gpu.mod_switch_to(cx, last, g2);
+        CHECK(same_ct(r2, g2));
+        Ciphertext hi = cx;
+        hi.scale() = std::pow(2.0, 100);
+        ref.rescale_to(hi, last, r2);
+        gpu.rescale_to(hi, last, g2);
+        CHECK(same_ct(r2, g2));
+        auto a = outcome([&] { Ciphertext t = r2; ref.mod_switch_to_inplace(t, cx.parms_id()); });
+        auto b = outcome([&] { Ciphertext t = g2; gpu.mod_switch_to_inplace(t, cx.parms_id()); });
+        CHECK(a == b && a == "invalid_argument"); // cannot switch to higher level modulus
+        a = outcome([&] { Ciphertext t; ref.multiply_many(many, rlk, t); });
+        b = outcome([&] { Ciphertext t; gpu.multiply_many(many, rlk, t); });
+        CHECK(a == b && a == "logic_error"); // BFV / BGV only
+    }
     for (int step : { 1, -4, 5, 1023 })
     {
         Ciphertext r2, g2;
@@ -358,6 +387,23 @@ static void test_bfv()
                 ok = ok && got[i] == (x[i] * y[i] % t) * y[i] % t;
             CHECK(ok);
         }
+    }
+    {
+        // multiply_many / exponentiate (evaluator.cpp:1649-1757)
+        std::vector<Ciphertext> many{ cx, cy, cx };
+        Ciphertext r2, g2;
+        ref.multiply_many(many, rlk, r2);
+        gpu.multiply_many(many, rlk, g2);
+        CHECK(same_ct(r2, g2));
+        ref.exponentiate(cx, 3, rlk, r2);
+        gpu.exponentiate(cx, 3, rlk, g2);
+        CHECK(same_ct(r2, g2));
+        auto a = outcome([&] { Ciphertext t = cx; ref.exponentiate_inplace(t, 0, rlk); });
+        auto b = outcome([&] { Ciphertext t = cx; gpu.exponentiate_inplace(t, 0, rlk); });
+        CHECK(a == b && a == "invalid_argument");
+        ref.mod_switch_to(cx, context.last_parms_id(), r2);
+        gpu.mod_switch_to(cx, context.last_parms_id(), g2);
+        CHECK(same_ct(r2, g2));
     }
     {
         // multiply_plain with an NTT-form plaintext: ciphertext in NTT form (:1991-1994) and in coefficient form (:2006-2011)
