@@ -112,6 +112,19 @@ int sb200_negate(sb200_context *ctx, size_t L, size_t size, size_t batch, const 
  * plaintext per ciphertext, at the ciphertext's level (Plaintext::data() with parms_id == the ciphertext's).  May run in place. */
 int sb200_multiply_plain(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_a, const uint64_t *d_plain,
                          uint64_t *d_out, void *stream);
+/* ---- coefficient-form plaintexts (BFV / BGV): d_plain is [batch][n] words < plain_modulus, zero above coeff_count ----
+ * Evaluator::transform_to_ntt_inplace(Plaintext&, parms_id) (evaluator.cpp:2197-2287): lift to the level with L primes
+ * (words >= (t+1)/2 are negative, :2240-2272) and transform; d_out is [batch][L][n] */
+int sb200_plain_to_ntt(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_plain, uint64_t *d_out, void *stream);
+/* Evaluator::multiply_plain with such a plaintext: multiply_plain_normal (:2021-2155) for coefficient-form ciphertexts
+ * (ct_is_ntt = 0, BFV), transform + multiply_plain_ntt (:1999-2004) for NTT-form ciphertexts (BGV).  May run in place. */
+int sb200_multiply_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batch, int ct_is_ntt, const uint64_t *d_a,
+                               const uint64_t *d_plain, uint64_t *d_out, void *stream);
+/* Evaluator::add_plain / sub_plain with such a plaintext: BFV adds round(q m / t) to c_0 (util/scalingvariant.cpp:70-160);
+ * BGV adds NTT(lift(m * correction_factor mod t)) (:1838-1849), h_correction_factors = [batch] host words or NULL (= 1).
+ * May run in place. */
+int sb200_add_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *d_a,
+                          const uint64_t *d_plain, const uint64_t *h_correction_factors, uint64_t *d_out, void *stream);
 /* Evaluator::relinearize_inplace, size 3 -> 2 (evaluator.cpp:1144-1199 + 2561-2867) */
 int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in3,
                       const sb200_kswitch_key *relin_key, uint64_t *d_out2, void *stream);
@@ -139,6 +152,11 @@ int sb200_sub_host(sb200_context *ctx, size_t L, size_t size, size_t batch, cons
 int sb200_negate_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, uint64_t *h_out);
 int sb200_multiply_plain_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_a, const uint64_t *h_plain,
                               uint64_t *h_out);
+int sb200_plain_to_ntt_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_plain, uint64_t *h_out);
+int sb200_multiply_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t batch, int ct_is_ntt, const uint64_t *h_a,
+                                    const uint64_t *h_plain, uint64_t *h_out);
+int sb200_add_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *h_a,
+                               const uint64_t *h_plain, const uint64_t *h_correction_factors, uint64_t *h_out);
 int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in3,
                            const sb200_kswitch_key *relin_key, uint64_t *h_out2);
 int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b,

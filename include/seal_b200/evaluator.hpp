@@ -152,9 +152,7 @@ namespace seal_b200
             }
         }
 
-        // ---- multiply_plain with an NTT-form plaintext (evaluator.cpp:1975-2019 dispatcher, :2157-2195 multiply_plain_ntt) ----
-        // Coefficient-form plaintexts (BFV multiply_plain_normal, :2021-2155) are outside the path: transform them with
-        // seal::Evaluator::transform_to_ntt_inplace(plain, parms_id) first.
+        // ---- multiply_plain (evaluator.cpp:1975-2019 dispatcher, :2157-2195 multiply_plain_ntt, :2021-2155 multiply_plain_normal) ----
         void multiply_plain_inplace(seal::Ciphertext &encrypted, const seal::Plaintext &plain,
                                     seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
         {
@@ -164,7 +162,16 @@ namespace seal_b200
             if (!pool)
                 throw std::invalid_argument("pool is uninitialized");
             if (!plain.is_ntt_form())
-                throw std::invalid_argument("seal_b200: multiply_plain is implemented for NTT-form plaintexts");
+            {
+                // multiply_plain_normal (:2021-2155) / transform + multiply_plain_ntt (:1999-2004)
+                if (scheme_ == seal::scheme_type::ckks)
+                    throw std::invalid_argument("plain is not valid for encryption parameters"); // CKKS plaintexts are always in NTT form
+                const std::vector<std::uint64_t> words = padded(plain);
+                check(sb200_multiply_plain_coeff_host(ctx_, encrypted.coeff_modulus_size(), encrypted.size(), 1, encrypted.is_ntt_form() ? 1 : 0,
+                                                      encrypted.data(), words.data(), encrypted.data()));
+                throw_if_transparent(encrypted);
+                return;
+            }
             const bool back = !encrypted.is_ntt_form(); // :2006-2011: to NTT form, multiply, back
             if (back)
                 transform_to_ntt_inplace(encrypted);
@@ -186,8 +193,7 @@ namespace seal_b200
             multiply_plain_inplace(destination, plain, std::move(pool));
         }
 
-        // ---- add_plain / sub_plain for CKKS (evaluator.cpp:1759-1868, :1870-1975): the NTT-form plaintext joins c_0 ---------
-        // BFV / BGV plaintexts need the scaling-variant lift (util/scalingvariant.cpp) and stay with the reference.
+        // ---- add_plain / sub_plain (evaluator.cpp:1759-1868, :1870-1975) ---------------------------------------------------
         void add_plain_inplace(seal::Ciphertext &encrypted, const seal::Plaintext &plain,
                                seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
         {
@@ -501,6 +507,32 @@ namespace seal_b200
             transform_from_ntt_inplace(destination);
         }
 
+        // transform_to_ntt_inplace(Plaintext&, parms_id) (evaluator.cpp:2197-2287)
+        void transform_to_ntt_inplace(seal::Plaintext &plain, seal::parms_id_type parms_id,
+                                      seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            if (!seal::is_valid_for(plain, context_))
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            auto cd = context_.get_context_data(parms_id);
+            if (!cd)
+                throw std::invalid_argument("parms_id is not valid for the current context");
+            if (plain.is_ntt_form())
+                throw std::invalid_argument("plain is already in NTT form");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            const std::vector<std::uint64_t> words = padded(plain);
+            const std::size_t L = cd->parms().coeff_modulus().size(), n = cd->parms().poly_modulus_degree();
+            plain.resize(n * L);
+            check(sb200_plain_to_ntt_host(ctx_, L, 1, words.data(), plain.data()));
+            plain.parms_id() = parms_id;
+        }
+        void transform_to_ntt(const seal::Plaintext &plain, seal::parms_id_type parms_id, seal::Plaintext &destination_ntt,
+                              seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination_ntt = plain;
+            transform_to_ntt_inplace(destination_ntt, parms_id, std::move(pool));
+        }
+
         // ---- batch extension: destination[i] = relinearize(multiply(a[i], b[i])), one device pass over the batch ----
         void multiply_relinearize(const std::vector<seal::Ciphertext> &a, const std::vector<seal::Ciphertext> &b,
                                   const seal::RelinKeys &relin_keys, std::vector<seal::Ciphertext> &destination) const
@@ -631,6 +663,14 @@ namespace seal_b200
             }
             f = multiply_uint_mod(e1, factor1, plain);
         }
+        // a coefficient-form plaintext as n words (Plaintext::coeff_count() may be smaller; the rest is zero)
+        std::vector<std::uint64_t> padded(const seal::Plaintext &plain) const
+        {
+            const std::size_t n = context_.key_context_data()->parms().poly_modulus_degree();
+            std::vector<std::uint64_t> w(n, 0);
+            std::copy(plain.data(), plain.data() + std::min(n, plain.coeff_count()), w.begin());
+            return w;
+        }
         void check_target_level(const seal::Ciphertext &encrypted, const seal::parms_id_type &parms_id) const
         {
             auto cur = context_.get_context_data(encrypted.parms_id());
@@ -648,7 +688,22 @@ namespace seal_b200
             if (!seal::is_metadata_valid_for(plain, context_) || !seal::is_buffer_valid(plain))
                 throw std::invalid_argument("plain is not valid for encryption parameters");
             if (scheme_ != seal::scheme_type::ckks)
-                throw std::invalid_argument("seal_b200: add_plain / sub_plain are implemented for CKKS");
+            {
+                // BFV: scaling variant on c_0 (util/scalingvariant.cpp:70-160); BGV: correction factor, lift, NTT (:1838-1849)
+                const bool bfv = scheme_ == seal::scheme_type::bfv;
+                if (bfv && encrypted.is_ntt_form())
+                    throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+                if (!bfv && !encrypted.is_ntt_form())
+                    throw std::invalid_argument("BGV encrypted must be in NTT form");
+                if (plain.is_ntt_form())
+                    throw std::invalid_argument(bfv ? "BFV plain cannot be in NTT form" : "BGV plain cannot be in NTT form");
+                const std::vector<std::uint64_t> words = padded(plain);
+                const std::uint64_t cf = encrypted.correction_factor();
+                check(sb200_add_plain_coeff_host(ctx_, encrypted.coeff_modulus_size(), encrypted.size(), 1, subtract ? 1 : 0, encrypted.data(),
+                                                 words.data(), bfv ? nullptr : &cf, encrypted.data()));
+                throw_if_transparent(encrypted);
+                return;
+            }
             if (!encrypted.is_ntt_form())
                 throw std::invalid_argument("CKKS encrypted must be in NTT form");
             if (!plain.is_ntt_form())

@@ -329,6 +329,45 @@ extern "C" int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size,
     REF_CATCH(-1)
 }
 
+// coefficient-form plaintext of n words (< plain_modulus)
+static Plaintext make_plain(const sealref_ctx *c, const uint64_t *words)
+{
+    Plaintext p(c->n);
+    std::memcpy(p.data(), words, c->n * sizeof(uint64_t));
+    return p;
+}
+
+extern "C" int sealref_plain_to_ntt(sealref_ctx *c, size_t L, const uint64_t *plain, uint64_t *out)
+{
+    REF_TRY
+    Plaintext p = make_plain(c, plain);
+    c->evaluator->transform_to_ntt_inplace(p, level(c, L)->parms_id());
+    std::memcpy(out, p.data(), L * c->n * sizeof(uint64_t));
+    return 0;
+    REF_CATCH(-1)
+}
+
+// Evaluator::multiply_plain / add_plain / sub_plain (mode 0 / 1 / 2) with a coefficient-form plaintext
+extern "C" int sealref_plain_op_coeff(
+    sealref_ctx *c, int mode, size_t L, size_t size, int ct_is_ntt, uint64_t correction_factor, const uint64_t *a,
+    const uint64_t *plain, uint64_t *out)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, size, a);
+    x.is_ntt_form() = ct_is_ntt != 0;
+    x.correction_factor() = correction_factor;
+    Plaintext p = make_plain(c, plain);
+    if (mode == 0)
+        c->evaluator->multiply_plain_inplace(x, p);
+    else if (mode == 1)
+        c->evaluator->add_plain_inplace(x, p);
+    else
+        c->evaluator->sub_plain_inplace(x, p);
+    store_ct(c, x, out);
+    return 0;
+    REF_CATCH(-1)
+}
+
 static const RelinKeys &relin_keys(sealref_ctx *c)
 {
     if (!c->relin)

@@ -368,6 +368,75 @@ void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const u64 *
                 out[(p * L + i) * n + j] = mulmod(a[(p * L + i) * n + j], plain[i * n + j], c->q[i]);
 }
 
+/* ---- coefficient-form plaintexts (BFV / BGV) -------------------------------------------------------------------------- */
+/* the lift of evaluator.cpp:2240-2272 / :2101-2127: words >= (t+1)/2 stand for negative numbers */
+static u64 plain_lift(u64 v, u64 t, u64 q)
+{
+    return v >= ((t + 1) >> 1) ? submod(v % q, t % q, q) : v % q;
+}
+/* Evaluator::transform_to_ntt_inplace(Plaintext, parms_id) (evaluator.cpp:2197-2287): plain [n] -> out [L][n] */
+void orc_plain_to_ntt(const orc_ctx *c, size_t L, const u64 *plain, u64 *out)
+{
+    size_t n = c->n;
+    for (size_t i = 0; i < L; i++)
+    {
+        for (size_t j = 0; j < n; j++)
+            out[i * n + j] = plain_lift(plain[j], c->t, c->q[i]);
+        ntt_fwd(&c->tab[i], n, out + i * n);
+    }
+}
+/* Evaluator::multiply_plain with a coefficient-form plaintext: multiply_plain_normal (:2021-2155) when the ciphertext is in
+ * coefficient form, transform + multiply_plain_ntt (:1999-2004) when it is in NTT form */
+void orc_multiply_plain_coeff(const orc_ctx *c, size_t L, size_t size, int ct_is_ntt, const u64 *a, const u64 *plain, u64 *out)
+{
+    size_t n = c->n;
+    u64 *p = (u64 *)malloc(L * n * sizeof(u64));
+    orc_plain_to_ntt(c, L, plain, p);
+    memcpy(out, a, size * L * n * sizeof(u64));
+    if (!ct_is_ntt)
+        orc_ntt_forward(c, L, size, out);
+    orc_multiply_plain_ntt(c, L, size, out, p, out);
+    if (!ct_is_ntt)
+        orc_ntt_inverse(c, L, size, out);
+    free(p);
+}
+/* Evaluator::add_plain / sub_plain with a coefficient-form plaintext; BFV: util/scalingvariant.cpp:70-160 (c_0 +/-
+ * floor((q m + (t+1)/2) / t), evaluated as m * floor(q/t) + floor((m (q mod t) + (t+1)/2) / t)); BGV: evaluator.cpp:1838-1849 */
+void orc_add_plain_coeff(const orc_ctx *c, size_t L, size_t size, int subtract, u64 correction_factor, const u64 *a, const u64 *plain, u64 *out)
+{
+    size_t n = c->n;
+    u64 t = c->t;
+    memcpy(out, a, size * L * n * sizeof(u64));
+    if (c->scheme == ORC_BFV)
+    {
+        u64 q_mod_t = 1;
+        for (size_t i = 0; i < L; i++)
+            q_mod_t = mulmod(q_mod_t, c->q[i] % t, t);
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 q = c->q[i], inv_t = 0;
+            invmod(t % q, q, &inv_t);
+            u64 delta = mulmod(submod(0, q_mod_t % q, q), inv_t, q); /* floor(Q / t) mod q_i, Q = 0 mod q_i */
+            for (size_t j = 0; j < n; j++)
+            {
+                u64 m = plain[j];
+                u64 fix = (u64)(((u128)m * q_mod_t + ((t + 1) >> 1)) / t);
+                u64 scaled = addmod(mulmod(m % q, delta, q), fix % q, q);
+                out[i * n + j] = subtract ? submod(out[i * n + j], scaled, q) : addmod(out[i * n + j], scaled, q);
+            }
+        }
+        return;
+    }
+    u64 *m = (u64 *)malloc(n * sizeof(u64)), *p = (u64 *)malloc(L * n * sizeof(u64));
+    for (size_t j = 0; j < n; j++)
+        m[j] = mulmod(plain[j], correction_factor, t);
+    orc_plain_to_ntt(c, L, m, p);
+    for (size_t i = 0; i < L; i++)
+        for (size_t j = 0; j < n; j++)
+            out[i * n + j] = subtract ? submod(out[i * n + j], p[i * n + j], c->q[i]) : addmod(out[i * n + j], p[i * n + j], c->q[i]);
+    free(m), free(p);
+}
+
 /* -------------------------------------------------------------------- key switching (evaluator.cpp:2561-2867) -- */
 void orc_switch_key(const orc_ctx *c, size_t L, u64 *ct, const u64 *target, const u64 *key)
 {

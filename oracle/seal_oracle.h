@@ -64,6 +64,11 @@ void orc_ckks_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint
 void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out);
 /* Evaluator::multiply_plain, ciphertext and plaintext in NTT form (evaluator.cpp:2157-2195) */
 void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out);
+/* coefficient-form plaintexts (n words < t): transform_to_ntt(Plaintext) :2197-2287, multiply_plain :2021-2155 / :1999-2004,
+ * add_plain / sub_plain util/scalingvariant.cpp:70-160 (BFV) and evaluator.cpp:1838-1849 (BGV) */
+void orc_plain_to_ntt(const orc_ctx *c, size_t L, const uint64_t *plain, uint64_t *out);
+void orc_multiply_plain_coeff(const orc_ctx *c, size_t L, size_t size, int ct_is_ntt, const uint64_t *a, const uint64_t *plain, uint64_t *out);
+void orc_add_plain_coeff(const orc_ctx *c, size_t L, size_t size, int subtract, uint64_t correction_factor, const uint64_t *a, const uint64_t *plain, uint64_t *out);
 int orc_bfv_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint64_t *b, uint64_t *out3);   /* evaluator.cpp:395-567 */
 /* general ciphertext sizes s1 x s2 -> s1+s2-1 (evaluator.cpp:664-700, :796-833; BFV :453-560) */
 void orc_ckks_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, const uint64_t *a, const uint64_t *b, uint64_t *out);

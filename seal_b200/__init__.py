@@ -26,9 +26,10 @@ SYMBOLS = [
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
-    "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
-    "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
+    "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_plain_to_ntt_host", "sb200_multiply_plain_coeff_host", "sb200_add_plain_coeff_host",
+    "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
     "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save",
 ]
@@ -82,6 +83,12 @@ def lib():
         L.sb200_negate.argtypes = [vp, sz, sz, sz, vp, vp, vp]
         L.sb200_multiply_plain.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_multiply_plain_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
+        L.sb200_plain_to_ntt.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.sb200_multiply_plain_coeff.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp, vp]
+        L.sb200_add_plain_coeff.argtypes = [vp, sz, sz, sz, i32, vp, vp, _u64p, vp, vp]
+        L.sb200_plain_to_ntt_host.argtypes = [vp, sz, sz, _u64p, _u64p]
+        L.sb200_multiply_plain_coeff_host.argtypes = [vp, sz, sz, sz, i32, _u64p, _u64p, _u64p]
+        L.sb200_add_plain_coeff_host.argtypes = [vp, sz, sz, sz, i32, _u64p, _u64p, _u64p, _u64p]
         L.sb200_square_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_add_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
         L.sb200_sub_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
@@ -308,6 +315,34 @@ class Context:
         plain = np.ascontiguousarray(plain).reshape(B, L, n)
         out = np.zeros_like(a)
         _check(lib().sb200_multiply_plain_host(self.h, L, size, B, _hp(a), _hp(plain), _hp(out)))
+        return out[0] if single else out
+
+    def plain_to_ntt(self, plain, L):
+        """Evaluator.transform_to_ntt(Plaintext, parms_id of the level with L primes): [B][n] words < t -> [B][L][n]"""
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        single = plain.ndim == 1
+        p = plain[None] if single else plain
+        out = np.zeros((p.shape[0], L, self.n), dtype=np.uint64)
+        _check(lib().sb200_plain_to_ntt_host(self.h, L, p.shape[0], _hp(p), _hp(out)))
+        return out[0] if single else out
+
+    def multiply_plain_coeff(self, a, plain, ct_is_ntt):
+        """Evaluator.multiply_plain with coefficient-form plaintexts [B][n]"""
+        a, single = self._batched(a)
+        B, size, L, n = a.shape
+        plain = np.ascontiguousarray(plain, dtype=np.uint64).reshape(B, n)
+        out = np.zeros_like(a)
+        _check(lib().sb200_multiply_plain_coeff_host(self.h, L, size, B, int(ct_is_ntt), _hp(a), _hp(plain), _hp(out)))
+        return out[0] if single else out
+
+    def add_plain_coeff(self, a, plain, subtract=False, correction_factors=None):
+        """Evaluator.add_plain / sub_plain with coefficient-form plaintexts [B][n] (BFV, BGV)"""
+        a, single = self._batched(a)
+        B, size, L, n = a.shape
+        plain = np.ascontiguousarray(plain, dtype=np.uint64).reshape(B, n)
+        out = np.zeros_like(a)
+        cf = None if correction_factors is None else _hp(np.ascontiguousarray(correction_factors, dtype=np.uint64).reshape(B))
+        _check(lib().sb200_add_plain_coeff_host(self.h, L, size, B, int(subtract), _hp(a), _hp(plain), cf, _hp(out)))
         return out[0] if single else out
 
     def relinearize(self, c3, key):

@@ -433,6 +433,47 @@ int sb200_multiply_plain(sb200_context *ctx, size_t L, size_t size, size_t batch
     return SB200_OK;
     SB_CATCH
 }
+int sb200_plain_to_ntt(sb200_context *ctx, size_t L, size_t batch, const uint64_t *plain, uint64_t *out, void *stream)
+{
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_plain_to_ntt(c, L, batch, (const u64 *)plain, nullptr, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batch, int ct_is_ntt, const uint64_t *a, const uint64_t *plain,
+                               uint64_t *out, void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_multiply_plain_coeff(c, L, size, batch, ct_is_ntt != 0, (const u64 *)a, (const u64 *)plain, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_add_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *a, const uint64_t *plain,
+                          const uint64_t *h_correction_factors, uint64_t *out, void *stream)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_add_plain_coeff(c, L, size, batch, subtract != 0, (const u64 *)a, (const u64 *)plain, (const u64 *)h_correction_factors, (u64 *)out,
+                       static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
 int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3, void *stream)
 {
     return sb200_multiply(ctx, L, batch, a, a, out3, stream);
@@ -708,6 +749,56 @@ int sb200_multiply_plain_host(sb200_context *ctx, size_t L, size_t size, size_t 
     return SB200_OK;
     SB_CATCH
 }
+int sb200_plain_to_ntt_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *plain, uint64_t *out)
+{
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    HostPipe(c).run(batch, c.n, 0, L * c.n, plain, nullptr, out,
+                    [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) { op_plain_to_ntt(c, L, B, da, nullptr, dout, st); });
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_multiply_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t batch, int ct_is_ntt, const uint64_t *a,
+                                    const uint64_t *plain, uint64_t *out)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t w = size * L * c.n;
+    HostPipe(c).run(batch, w, c.n, w, a, plain, out, [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
+        op_multiply_plain_coeff(c, L, size, B, ct_is_ntt != 0, da, db, dout, st);
+    });
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_add_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *a, const uint64_t *plain,
+                               const uint64_t *h_correction_factors, uint64_t *out)
+{
+    SB_NEED(a);
+    SB_NEED(plain);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t w = size * L * c.n;
+    size_t done = 0; // chunks arrive in order: the correction factors advance with them
+    HostPipe(c).run(batch, w, c.n, w, a, plain, out, [&](size_t B, u64 *da, u64 *db, u64 *dout, cudaStream_t st) {
+        op_add_plain_coeff(c, L, size, B, subtract != 0, da, db, h_correction_factors ? (const u64 *)h_correction_factors + done : nullptr, dout,
+                           st);
+        done += B;
+    });
+    return SB200_OK;
+    SB_CATCH
+}
+
 int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3)
 {
     return sb200_multiply_host(ctx, L, batch, a, a, out3);

@@ -37,6 +37,9 @@ namespace sb
         cudaFree(d_primes);
         cudaFree(d_invq);
         cudaFree(d_qmod);
+        cudaFree(d_t_mod_q);
+        for (auto &kv : plain_levels)
+            cudaFree(kv.second.d_delta);
         cudaFree(scratch);
         cudaFree(aux_buf);
         if (order_event)
@@ -554,6 +557,238 @@ namespace sb
                                                      static_cast<int>(size), total2);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "plain_mul_kernel");
+        }
+    }
+
+    // ---- coefficient-form plaintexts (BFV / BGV): lift, transform, multiply_plain, add_plain / sub_plain ----------------
+    static const Context::PlainLevel &plain_level(Context &c, size_t L)
+    {
+        if (c.scheme == 2 || c.t < 2)
+            throw std::invalid_argument("unsupported operation for scheme type");
+        if (!c.d_t_mod_q)
+        {
+            std::vector<u64> tm(c.k);
+            for (size_t i = 0; i < c.k; i++)
+                tm[i] = c.t % c.q[i];
+            cuda_check(cudaMalloc(&c.d_t_mod_q, c.k * sizeof(u64)), "cudaMalloc(t_mod_q)");
+            cuda_check(cudaMemcpy(c.d_t_mod_q, tm.data(), c.k * sizeof(u64), cudaMemcpyHostToDevice), "upload t_mod_q");
+            const unsigned __int128 ratio = ~static_cast<unsigned __int128>(0) / c.t; // floor((2^128 - 1) / t): at most 1 below floor(2^128 / t)
+            c.t_ratio_lo = static_cast<u64>(ratio), c.t_ratio_hi = static_cast<u64>(ratio >> 64);
+        }
+        auto it = c.plain_levels.find(L);
+        if (it != c.plain_levels.end())
+            return it->second;
+        Context::PlainLevel pl;
+        unsigned __int128 acc = 1;
+        for (size_t i = 0; i < L; i++)
+            acc = acc * (c.q[i] % c.t) % c.t;
+        pl.q_mod_t = static_cast<u64>(acc);
+        // floor(q / t) = (q - (q mod t)) / t, and q = 0 mod q_i: floor(q / t) mod q_i = -(q mod t) * t^-1 mod q_i
+        std::vector<Tw> delta(L);
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 inv = 0;
+            if (!sbh::invmod(c.t % c.q[i], c.q[i], inv))
+                throw std::logic_error("plain_modulus and coeff_modulus are not coprime");
+            const u64 r = pl.q_mod_t % c.q[i];
+            const u64 v = static_cast<u64>(static_cast<unsigned __int128>(r ? c.q[i] - r : 0) * inv % c.q[i]);
+            delta[i] = Tw{ v, sbh::shoup(v, c.q[i]) };
+        }
+        cuda_check(cudaMalloc(&pl.d_delta, L * sizeof(Tw)), "cudaMalloc(delta)");
+        cuda_check(cudaMemcpy(pl.d_delta, delta.data(), L * sizeof(Tw), cudaMemcpyHostToDevice), "upload delta");
+        return c.plain_levels.emplace(L, pl).first->second;
+    }
+
+    // per-ciphertext BGV correction factors -> device (behind the scratch words of this call); nullptr stays nullptr
+    static const u64 *upload_cf(Context &c, const u64 *h_cf, size_t B, u64 *slot, cudaStream_t st)
+    {
+        if (!h_cf)
+            return nullptr;
+        cuda_check(cudaMemcpyAsync(slot, h_cf, B * sizeof(u64), cudaMemcpyHostToDevice, st), "upload correction factors");
+        (void)c;
+        return slot;
+    }
+
+    // lift of one coefficient-form plaintext word v < t to the prime q: the representative in (-t/2, t/2] modulo q
+    // (plain_upper_half_threshold / plain_upper_half_increment, evaluator.cpp:2240-2272, :2101-2127)
+    __device__ __forceinline__ u64 plain_lift(u64 v, u64 t, u64 t_mod_q, const PrimeDev &P)
+    {
+        u64 r = t > P.q ? barrett64(v, P.q, P.ratio_hi) : v;
+        if (v >= ((t + 1) >> 1))
+            r = csub(r + P.q - t_mod_q, P.q);
+        return r;
+    }
+
+    // forward transform of lifted plaintexts: rows (b, i) -> out[b][i][:]; cf (optional): plaintext times cf[b] mod t first
+    struct OpPlainLift
+    {
+        const u64 *plain; // [B][n]
+        const u64 *cf;    // [B] or nullptr
+        const u64 *t_mod_q;
+        u64 *out;         // [B][L][n]
+        u64 t, t_ratio_lo, t_ratio_hi;
+        int logn, L;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const { return row % L; }
+        __device__ __forceinline__ const u64 *direct(int, const PrimeDev &) const { return nullptr; }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const
+        {
+            const int b = row / L;
+            u64 v = plain[(static_cast<long long>(b) << logn) + idx];
+            if (cf)
+            {
+                const u64 f = cf[b];
+                v = barrett128(v * f, __umul64hi(v, f), t, t_ratio_lo, t_ratio_hi);
+                v = csub(v, t); // the ratio may sit one below floor(2^128 / t)
+            }
+            return plain_lift(v, t, t_mod_q[row % L], P);
+        }
+        __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
+        __device__ __forceinline__ u64 *mid(int row) const { return out + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const { mid(row)[idx] = csub(csub(v, P.q2), P.q); }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&v)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, v[j], P);
+        }
+    };
+
+    static void plain_to_ntt_dev(Context &c, size_t L, size_t B, const u64 *plain, const u64 *d_cf, u64 *out, cudaStream_t st)
+    {
+        plain_level(c, L);
+        OpPlainLift op{ plain, d_cf, c.d_t_mod_q, out, c.t, c.t_ratio_lo, c.t_ratio_hi, c.logn, static_cast<int>(L) };
+        cuda_check(launch_ntt_fwd(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats, "plain_lift_ntt", -1, c.fast_q), "plain lift ntt");
+    }
+
+    void op_plain_to_ntt(Context &c, size_t L, size_t batch, const u64 *plain, const u64 *h_cf, u64 *out, cudaStream_t st)
+    {
+        const size_t step = std::max<size_t>(1, (size_t(1) << 30) / (L * c.n));
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t B = std::min(step, batch - b0);
+            const u64 *d_cf = nullptr;
+            if (h_cf)
+                d_cf = upload_cf(c, h_cf + b0, B, static_cast<u64 *>(c.ensure_scratch(B * sizeof(u64))), st);
+            plain_to_ntt_dev(c, L, B, plain + b0 * c.n, d_cf, out + b0 * L * c.n, st);
+        }
+    }
+
+    void op_multiply_plain_coeff(Context &c, size_t L, size_t size, size_t batch, bool ct_ntt, const u64 *ct, const u64 *plain, u64 *out,
+                                 cudaStream_t st)
+    {
+        if (size < 1)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        const size_t per = size * L * c.n;
+        size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / (L * c.n * sizeof(u64))));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / per));
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const size_t B = std::min(chunk, batch - b0);
+            u64 *T = static_cast<u64 *>(c.ensure_scratch(B * L * c.n * sizeof(u64)));
+            plain_to_ntt_dev(c, L, B, plain + b0 * c.n, nullptr, T, st);
+            const u64 *in = ct + b0 * per;
+            u64 *o = out + b0 * per;
+            if (ct_ntt)
+            {
+                op_multiply_plain(c, L, size, B, in, T, o, st); // evaluator.cpp:1999-2004
+                continue;
+            }
+            // multiply_plain_normal (evaluator.cpp:2130-2143): ciphertext to NTT form, dyadic product, back
+            if (o != in)
+                cuda_check(cudaMemcpyAsync(o, in, B * per * sizeof(u64), cudaMemcpyDeviceToDevice, st), "copy");
+            op_ntt(c, false, L, size, B, o, st);
+            op_multiply_plain(c, L, size, B, o, T, o, st);
+            op_ntt(c, true, L, size, B, o, st);
+        }
+    }
+
+    // BFV: c_0 +/- round(q * m / t) (multiply_add / multiply_sub_plain_with_scaling_variant, util/scalingvariant.cpp:70-160)
+    __global__ void __launch_bounds__(256) bfv_add_plain_kernel(const u64 *__restrict__ plain, u64 *ct, long long ct_bs, const Tw *__restrict__ delta,
+                                                                 const PrimeDev *__restrict__ primes, u64 t, u64 t_ratio_lo, u64 t_ratio_hi,
+                                                                 u64 q_mod_t, int logn, int L, int subtract, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*n
+        if (e >= total)
+            return;
+        const long long b = e >> logn;
+        const int idx = static_cast<int>(e & ((1 << logn) - 1));
+        const u64 m = plain[e];
+        // fix = floor((m * (q mod t) + (t + 1) / 2) / t): quotient estimate from the Barrett ratio, corrected by the remainder
+        u64 lo = m * q_mod_t, hi = __umul64hi(m, q_mod_t);
+        const u64 half = (t + 1) >> 1;
+        lo += half, hi += (lo < half);
+        const u64 c0 = __umul64hi(lo, t_ratio_lo);
+        const u64 a_lo = lo * t_ratio_hi, a_hi = __umul64hi(lo, t_ratio_hi), b_lo = hi * t_ratio_lo, b_hi = __umul64hi(hi, t_ratio_lo);
+        u64 s1 = a_lo + c0, carry = (s1 < a_lo);
+        const u64 s2 = s1 + b_lo;
+        carry += (s2 < s1);
+        u64 fix = hi * t_ratio_hi + a_hi + b_hi + carry;
+        u64 rem = lo - fix * t;
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (rem >= t)
+                rem -= t, fix++;
+        u64 *dst = ct + b * ct_bs + idx;
+        for (int i = 0; i < L; i++)
+        {
+            const PrimeDev P = primes[i];
+            const u64 mm = t > P.q ? barrett64(m, P.q, P.ratio_hi) : m;
+            const u64 scaled = csub(mul_shoup(mm, delta[i], P.q) + barrett64(fix, P.q, P.ratio_hi), P.q);
+            const u64 x = dst[static_cast<long long>(i) << logn];
+            dst[static_cast<long long>(i) << logn] = subtract ? csub(x + P.q - scaled, P.q) : csub(x + scaled, P.q);
+        }
+    }
+
+    // BGV: c_0 +/- T, T = [B][L][n] transformed plaintexts (evaluator.cpp:1838-1849)
+    __global__ void __launch_bounds__(256) add_c0_kernel(const u64 *__restrict__ T, u64 *ct, long long ct_bs, const PrimeDev *__restrict__ primes,
+                                                          int logn, int L, int subtract, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*L*n
+        if (e >= total)
+            return;
+        const long long poly = static_cast<long long>(L) << logn, b = e / poly, r = e % poly;
+        const u64 q = primes[static_cast<int>(r >> logn)].q;
+        u64 *p = ct + b * ct_bs + r;
+        const u64 x = *p, y = T[e];
+        *p = subtract ? csub(x + q - y, q) : csub(x + y, q);
+    }
+
+    void op_add_plain_coeff(Context &c, size_t L, size_t size, size_t batch, bool subtract, const u64 *ct, const u64 *plain, const u64 *h_cf,
+                            u64 *out, cudaStream_t st)
+    {
+        if (size < 1)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        const Context::PlainLevel &pl = plain_level(c, L);
+        const size_t per = size * L * c.n;
+        if (out != ct)
+            cuda_check(cudaMemcpyAsync(out, ct, batch * per * sizeof(u64), cudaMemcpyDeviceToDevice, st), "copy");
+        size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / ((L * c.n + 1) * sizeof(u64))));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (L * c.n)));
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const size_t B = std::min(chunk, batch - b0);
+            u64 *o = out + b0 * per;
+            if (c.scheme == 1)
+            {
+                const long long total = static_cast<long long>(B * c.n);
+                c.stats.begin("bfv_add_plain", 0, 8.0 * total * (1 + 2 * L), st);
+                bfv_add_plain_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+                    plain + b0 * c.n, o, static_cast<long long>(per), pl.d_delta, c.d_primes, c.t, c.t_ratio_lo, c.t_ratio_hi, pl.q_mod_t, c.logn,
+                    static_cast<int>(L), subtract ? 1 : 0, total);
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "bfv_add_plain_kernel");
+                continue;
+            }
+            u64 *T = static_cast<u64 *>(c.ensure_scratch((B * L * c.n + B) * sizeof(u64)));
+            const u64 *d_cf = upload_cf(c, h_cf ? h_cf + b0 : nullptr, B, T + B * L * c.n, st);
+            plain_to_ntt_dev(c, L, B, plain + b0 * c.n, d_cf, T, st);
+            const long long total = static_cast<long long>(B * L * c.n);
+            c.stats.begin("bgv_add_plain", 0, 24.0 * total, st);
+            add_c0_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(T, o, static_cast<long long>(per), c.d_primes, c.logn,
+                                                                                      static_cast<int>(L), subtract ? 1 : 0, total);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "add_c0_kernel");
         }
     }
 

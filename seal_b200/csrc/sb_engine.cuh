@@ -54,6 +54,15 @@ namespace sb
         Tw *d_qmod = nullptr;                // BGV, [k][k]: d_qmod[j*k+i] = q_j mod q_i
         u64 t_ratio = 0;                     // BGV: floor(2^64 / t)
         std::vector<u64> inv_q_mod_t;        // BGV: q_j^-1 mod t
+        // coefficient-form plaintext operations (BFV / BGV): per-level constants, built on first use (sb_engine.cu: plain_level)
+        struct PlainLevel
+        {
+            Tw *d_delta = nullptr;  // [L]: floor(q / t) mod q_i (ContextData::coeff_div_plain_modulus, context.cpp:300-318)
+            u64 q_mod_t = 0;        // ContextData::coeff_modulus_mod_plain_modulus
+        };
+        std::map<size_t, PlainLevel> plain_levels;
+        u64 *d_t_mod_q = nullptr;   // [k]: t mod q_i
+        u64 t_ratio_lo = 0, t_ratio_hi = 0; // floor(2^128 / t)
         std::vector<std::array<u64, 4>> parms_ids; // parms_ids[L-1] = parms_id of the level with L primes (sb_wire.hpp)
         std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
         std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
@@ -82,6 +91,13 @@ namespace sb
     void op_ntt(Context &c, bool inverse, size_t L, size_t size, size_t batch, u64 *d, cudaStream_t st);
     void op_linear(Context &c, int mode, size_t L, size_t size, size_t batch, const u64 *a, const u64 *b, u64 *out, cudaStream_t st);
     void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st);
+    // coefficient-form plaintexts [B][n] (words < t): lift + NTT, multiply_plain, add_plain / sub_plain (BFV, BGV);
+    // h_cf: per-ciphertext BGV correction factors on the host (nullptr = 1)
+    void op_plain_to_ntt(Context &c, size_t L, size_t batch, const u64 *plain, const u64 *h_cf, u64 *out, cudaStream_t st);
+    void op_multiply_plain_coeff(Context &c, size_t L, size_t size, size_t batch, bool ct_ntt, const u64 *ct, const u64 *plain, u64 *out,
+                                 cudaStream_t st);
+    void op_add_plain_coeff(Context &c, size_t L, size_t size, size_t batch, bool subtract, const u64 *ct, const u64 *plain, const u64 *h_cf,
+                            u64 *out, cudaStream_t st);
     void op_ckks_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st);
     void op_bfv_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st);
     // general ciphertext sizes s1 x s2 -> s1+s2-1 (2 x 2 forwards to the specialised kernels above)

@@ -389,6 +389,39 @@ static void test_bfv()
         }
     }
     {
+        // coefficient-form plaintexts: multiply_plain_normal, add_plain / sub_plain (scaling variant), transform_to_ntt(Plaintext)
+        Ciphertext r2, g2;
+        ref.multiply_plain(cx, py, r2);
+        gpu.multiply_plain(cx, py, g2);
+        CHECK(same_ct(r2, g2));
+        ref.add_plain_inplace(r2, px);
+        gpu.add_plain_inplace(g2, px);
+        CHECK(same_ct(r2, g2));
+        ref.sub_plain_inplace(r2, py);
+        gpu.sub_plain_inplace(g2, py);
+        CHECK(same_ct(r2, g2));
+        Plaintext p;
+        decryptor.decrypt(g2, p);
+        std::vector<uint64_t> got;
+        encoder.decode(p, got);
+        bool ok = true;
+        for (size_t i = 0; i < n; i++)
+            ok = ok && got[i] == (x[i] * y[i] + x[i] + t - y[i]) % t;
+        CHECK(ok);
+        Plaintext rp, gp;
+        ref.transform_to_ntt(py, cx.parms_id(), rp);
+        gpu.transform_to_ntt(py, cx.parms_id(), gp);
+        CHECK(rp.parms_id() == gp.parms_id() && rp.coeff_count() == gp.coeff_count() &&
+              std::memcmp(rp.data(), gp.data(), rp.coeff_count() * 8) == 0);
+        Plaintext mono("3x^5"); // a short plaintext: the monomial branch of multiply_plain_normal (:2047-2092)
+        ref.multiply_plain(cx, mono, r2);
+        gpu.multiply_plain(cx, mono, g2);
+        CHECK(same_ct(r2, g2));
+        auto a = outcome([&] { Ciphertext tt = cx; ref.add_plain_inplace(tt, rp); });
+        auto b = outcome([&] { Ciphertext tt = cx; gpu.add_plain_inplace(tt, gp); });
+        CHECK(a == b && a == "invalid_argument"); // BFV plain cannot be in NTT form
+    }
+    {
         // multiply_many / exponentiate (evaluator.cpp:1649-1757)
         std::vector<Ciphertext> many{ cx, cy, cx };
         Ciphertext r2, g2;
@@ -564,6 +597,27 @@ static void test_bgv()
         ref.sub(w, u, r2);
         gpu.sub(w, u, g2);
         CHECK(same_ct(r2, g2));
+        // add_plain / sub_plain / multiply_plain with a coefficient-form plaintext on a ciphertext whose correction factor is not 1
+        {
+            Ciphertext r3 = w, g3 = w;
+            ref.add_plain_inplace(r3, py);
+            gpu.add_plain_inplace(g3, py);
+            CHECK(same_ct(r3, g3));
+            ref.multiply_plain_inplace(r3, px);
+            gpu.multiply_plain_inplace(g3, px);
+            CHECK(same_ct(r3, g3));
+            ref.sub_plain_inplace(r3, px);
+            gpu.sub_plain_inplace(g3, px);
+            CHECK(same_ct(r3, g3));
+            Plaintext pp;
+            decryptor.decrypt(g3, pp);
+            std::vector<uint64_t> gg;
+            encoder.decode(pp, gg);
+            bool fine = true;
+            for (size_t i = 0; i < n; i++)
+                fine = fine && gg[i] == ((x[i] * y[i] + y[i]) % t * x[i] + t - x[i]) % t;
+            CHECK(fine);
+        }
         Ciphertext odd = u;
         odd.correction_factor() = 12345; // arbitrary factors take the same path
         ref.add(odd, w, r2);

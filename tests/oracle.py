@@ -168,6 +168,27 @@ class Oracle:
         lib().orc_multiply_plain_ntt(self.h, L, a.shape[0], _p(a), _p(plain), _p(out))
         return out
 
+    def plain_to_ntt(self, L, plain):
+        lib().orc_plain_to_ntt.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        lib().orc_plain_to_ntt(self.h, L, _p(plain), _p(out))
+        return out
+
+    def multiply_plain_coeff(self, L, a, plain, ct_is_ntt):
+        lib().orc_multiply_plain_coeff.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, _u64p, _u64p, _u64p]
+        a, plain = np.ascontiguousarray(a), np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros_like(a)
+        lib().orc_multiply_plain_coeff(self.h, L, a.shape[0], int(ct_is_ntt), _p(a), _p(plain), _p(out))
+        return out
+
+    def add_plain_coeff(self, L, a, plain, subtract=False, correction_factor=1):
+        lib().orc_add_plain_coeff.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, _u64p, _u64p, _u64p]
+        a, plain = np.ascontiguousarray(a), np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros_like(a)
+        lib().orc_add_plain_coeff(self.h, L, a.shape[0], int(subtract), correction_factor, _p(a), _p(plain), _p(out))
+        return out
+
     def relinearize(self, L, c3, key):
         out = np.zeros((2, L, self.n), dtype=np.uint64)
         lib().orc_relinearize(self.h, L, _p(c3), _p(key), _p(out))

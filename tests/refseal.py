@@ -58,6 +58,8 @@ def lib():
         L.sealref_bfv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int)]
         L.sealref_time_op.restype = C.c_double
         L.sealref_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]
+        L.sealref_plain_to_ntt.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.sealref_plain_op_coeff.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, _u64p, _u64p, _u64p]
         L.sealref_parms_id.argtypes = [C.c_void_p, C.c_size_t, _u64p]
         L.sealref_ct_save.restype = C.c_long
         L.sealref_ct_save.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, C.c_int, C.c_double, C.c_uint64, C.c_char_p, C.c_size_t]
@@ -234,6 +236,19 @@ class RefContext:
         nb = C.c_int(0)
         self._chk(lib().sealref_bfv_decrypt(self.h, L, ct.shape[0], _p(ct), _p(out), C.byref(nb)))
         return out, nb.value
+
+    def plain_to_ntt(self, L, plain):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_plain_to_ntt(self.h, L, _p(plain), _p(out)))
+        return out
+
+    def plain_op_coeff(self, mode, L, a, plain, ct_is_ntt, correction_factor=1):
+        """Evaluator.multiply_plain (0) / add_plain (1) / sub_plain (2) with a coefficient-form plaintext [n]"""
+        a, plain = np.ascontiguousarray(a), np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros_like(a)
+        self._chk(lib().sealref_plain_op_coeff(self.h, mode, L, a.shape[0], int(ct_is_ntt), correction_factor, _p(a), _p(plain), _p(out)))
+        return out
 
     def parms_id(self, L):
         out = np.zeros(4, dtype=np.uint64)

@@ -424,6 +424,38 @@ def test_wire_format_vs_reference(scheme):
         ctx.d_load_ciphertexts([rc.seeded_ct_stream()], dev, 2, 2)
 
 
+@needs_ref
+@pytest.mark.parametrize("scheme,t_bits,n", [("bfv", 20, 4096), ("bfv", 38, 4096), ("bgv", 20, 4096), ("bgv", 38, 256)])
+def test_coeff_plain_ops_vs_reference(scheme, t_bits, n):
+    # coefficient-form plaintexts (BFV / BGV): transform_to_ntt(Plaintext), multiply_plain, add_plain, sub_plain
+    batch = 3
+    mods = R.coeff_modulus_create(n, [50, 36, 45, 60])
+    t = R.plain_modulus_batching(n, t_bits)
+    sid = R.BFV if scheme == "bfv" else R.BGV
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    rng = np.random.default_rng(59)
+    ntt = scheme == "bgv"
+    for L, size in ((3, 2), (1, 3)):
+        plain = rng.integers(0, t, (batch, n), dtype=np.uint64)
+        plain[:, :4] = [0, t - 1, (t + 1) // 2, (t + 1) // 2 - 1]
+        a = rand_ct(rng, mods, n, size, L, batch)
+        pn = ctx.plain_to_ntt(plain, L)
+        mp = ctx.multiply_plain_coeff(a, plain, ntt)
+        cf = None if scheme == "bfv" else np.array([1, 12345 % t, t - 1], dtype=np.uint64)
+        ap = ctx.add_plain_coeff(a, plain, False, cf)
+        sp = ctx.add_plain_coeff(a, plain, True, cf)
+        for i in range(batch):
+            f = 1 if cf is None else int(cf[i])
+            assert (pn[i] == rc.plain_to_ntt(L, plain[i])).all()
+            assert (mp[i] == rc.plain_op_coeff(0, L, a[i], plain[i], ntt)).all()
+            assert (ap[i] == rc.plain_op_coeff(1, L, a[i], plain[i], ntt, f)).all()
+            assert (sp[i] == rc.plain_op_coeff(2, L, a[i], plain[i], ntt, f)).all()
+        if scheme == "bfv":  # transformed BFV ciphertext: the NTT branch of multiply_plain
+            mn = ctx.multiply_plain_coeff(a, plain, True)
+            assert (mn[0] == rc.plain_op_coeff(0, L, a[0], plain[0], True)).all()
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

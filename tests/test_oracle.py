@@ -202,3 +202,29 @@ def test_oracle_general_size_multiply_vs_live_reference(scheme):
     for L, sa, sb in ((3, 3, 2), (2, 2, 3), (1, 3, 3), (2, 4, 2)):
         a, b = rand_ct(rng, mods, n, sa, L), rand_ct(rng, mods, n, sb, L)
         assert (rc.multiply(L, a, b) == oc.multiply(L, a, b)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme,t_bits", [("bfv", 17), ("bfv", 38), ("bgv", 17), ("bgv", 38)])
+def test_oracle_coeff_plain_ops_vs_live_reference(scheme, t_bits):
+    # coefficient-form plaintexts: transform_to_ntt(Plaintext), multiply_plain (normal / NTT ciphertext), add_plain, sub_plain;
+    # plain modulus below and above the smallest coefficient prime (fast and general plain lift, context.cpp:320-372)
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 36, 42, 43])
+    t = R.plain_modulus_batching(n, t_bits)
+    sid = R.BFV if scheme == "bfv" else R.BGV
+    rc, oc = R.RefContext(sid, n, mods, t), O.Oracle(sid, n, mods, t)
+    rng = np.random.default_rng(53)
+    ntt = scheme == "bgv"
+    for L in (3, 1):
+        plain = rng.integers(0, t, n, dtype=np.uint64)
+        plain[:4] = [0, t - 1, (t + 1) // 2, (t + 1) // 2 - 1]  # both sides of the upper-half threshold
+        assert (rc.plain_to_ntt(L, plain) == oc.plain_to_ntt(L, plain)).all()
+        for size in (2, 3):
+            a = rand_ct(rng, mods, n, size, L)
+            assert (rc.plain_op_coeff(0, L, a, plain, ntt) == oc.multiply_plain_coeff(L, a, plain, ntt)).all()
+            if scheme == "bfv":  # a transformed BFV ciphertext takes the NTT branch (evaluator.cpp:1999-2004)
+                assert (rc.plain_op_coeff(0, L, a, plain, True) == oc.multiply_plain_coeff(L, a, plain, True)).all()
+            cf = 1 if scheme == "bfv" else 12345 % t
+            assert (rc.plain_op_coeff(1, L, a, plain, ntt, cf) == oc.add_plain_coeff(L, a, plain, False, cf)).all()
+            assert (rc.plain_op_coeff(2, L, a, plain, ntt, cf) == oc.add_plain_coeff(L, a, plain, True, cf)).all()
