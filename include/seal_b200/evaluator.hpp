@@ -334,6 +334,81 @@ namespace seal_b200
             rescale_to_inplace(destination, parms_id, std::move(pool));
         }
 
+        // ---- dropping RNS components without scaling: layout only, no arithmetic ----------------------------------------
+        // mod_reduce_to_next / mod_reduce_to (evaluator.cpp:1598-1647 -> mod_switch_drop_to_next :1296-1366)
+        void mod_reduce_to_next_inplace(seal::Ciphertext &encrypted, seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            validate(encrypted, "encrypted is not valid for encryption parameters");
+            if (context_.last_parms_id() == encrypted.parms_id())
+                throw std::invalid_argument("end of modulus switching chain reached");
+            if (!pool)
+                throw std::invalid_argument("pool is uninitialized");
+            drop_last_component(encrypted);
+            throw_if_transparent(encrypted);
+        }
+        void mod_reduce_to_next(const seal::Ciphertext &encrypted, seal::Ciphertext &destination,
+                                seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            mod_reduce_to_next_inplace(destination, std::move(pool));
+        }
+        void mod_reduce_to_inplace(seal::Ciphertext &encrypted, seal::parms_id_type parms_id,
+                                   seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            check_target_level(encrypted, parms_id);
+            while (encrypted.parms_id() != parms_id)
+                mod_reduce_to_next_inplace(encrypted, pool);
+        }
+        void mod_reduce_to(const seal::Ciphertext &encrypted, seal::parms_id_type parms_id, seal::Ciphertext &destination,
+                           seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
+        {
+            destination = encrypted;
+            mod_reduce_to_inplace(destination, parms_id, std::move(pool));
+        }
+        // NTT-form plaintexts one level down (evaluator.h:431-458, evaluator.cpp:1368-1402): the last component is cut off
+        void mod_switch_to_next_inplace(seal::Plaintext &plain) const
+        {
+            if (!seal::is_valid_for(plain, context_))
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            auto cd = context_.get_context_data(plain.parms_id());
+            if (!plain.is_ntt_form())
+                throw std::invalid_argument("plain is not in NTT form");
+            if (!cd->next_context_data())
+                throw std::invalid_argument("end of modulus switching chain reached");
+            auto &next = *cd->next_context_data();
+            if (!scale_within_bounds(plain.scale(), next))
+                throw std::invalid_argument("scale out of bounds");
+            const std::size_t words = next.parms().coeff_modulus().size() * next.parms().poly_modulus_degree();
+            plain.parms_id() = seal::parms_id_zero;
+            plain.resize(words);
+            plain.parms_id() = next.parms_id();
+        }
+        void mod_switch_to_next(const seal::Plaintext &plain, seal::Plaintext &destination) const
+        {
+            destination = plain;
+            mod_switch_to_next_inplace(destination);
+        }
+        void mod_switch_to_inplace(seal::Plaintext &plain, seal::parms_id_type parms_id) const
+        {
+            auto cur = context_.get_context_data(plain.parms_id());
+            auto target = context_.get_context_data(parms_id);
+            if (!cur)
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            if (!target)
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            if (!plain.is_ntt_form())
+                throw std::invalid_argument("plain is not in NTT form");
+            if (cur->chain_index() < target->chain_index())
+                throw std::invalid_argument("cannot switch to higher level modulus");
+            while (plain.parms_id() != parms_id)
+                mod_switch_to_next_inplace(plain);
+        }
+        void mod_switch_to(const seal::Plaintext &plain, seal::parms_id_type parms_id, seal::Plaintext &destination) const
+        {
+            destination = plain;
+            mod_switch_to_inplace(destination, parms_id);
+        }
+
         // ---- relinearize (evaluator.cpp:1144-1199) ---------------------------------------------------------------
         void relinearize_inplace(seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys,
                                  seal::MemoryPoolHandle pool = seal::MemoryManager::GetPool()) const
@@ -670,6 +745,31 @@ namespace seal_b200
             std::vector<std::uint64_t> w(n, 0);
             std::copy(plain.data(), plain.data() + std::min(n, plain.coeff_count()), w.begin());
             return w;
+        }
+        // mod_switch_drop_to_next (evaluator.cpp:1296-1366): every polynomial keeps its first L-1 components
+        void drop_last_component(seal::Ciphertext &encrypted) const
+        {
+            auto cd = context_.get_context_data(encrypted.parms_id());
+            const auto scheme = cd->parms().scheme();
+            if (scheme == seal::scheme_type::bfv && encrypted.is_ntt_form())
+                throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+            if (scheme == seal::scheme_type::ckks && !encrypted.is_ntt_form())
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (scheme == seal::scheme_type::bgv && !encrypted.is_ntt_form())
+                throw std::invalid_argument("BGV encrypted must be in NTT form");
+            auto &next = *cd->next_context_data();
+            if (!scale_within_bounds(encrypted.scale(), next))
+                throw std::invalid_argument("scale out of bounds");
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree(), size = encrypted.size();
+            std::vector<std::uint64_t> kept(size * (L - 1) * n);
+            for (std::size_t p = 0; p < size; p++)
+                std::memcpy(kept.data() + p * (L - 1) * n, encrypted.data(p), (L - 1) * n * sizeof(std::uint64_t));
+            const bool ntt = encrypted.is_ntt_form();
+            const double scale = encrypted.scale();
+            const std::uint64_t correction = encrypted.correction_factor();
+            encrypted.resize(context_, next.parms_id(), size);
+            std::memcpy(encrypted.data(), kept.data(), kept.size() * sizeof(std::uint64_t));
+            encrypted.is_ntt_form() = ntt, encrypted.scale() = scale, encrypted.correction_factor() = correction;
         }
         void check_target_level(const seal::Ciphertext &encrypted, const seal::parms_id_type &parms_id) const
         {

@@ -200,6 +200,29 @@ static void test_ckks()
         ref.add_many(many, r2);
         gpu.add_many(many, g2);
         CHECK(same_ct(r2, g2));
+        {
+            // layout-only level changes: mod_reduce_to_next (ciphertext), mod_switch_to_next / mod_switch_to (NTT-form plaintext)
+            Ciphertext c3, r5, g5;
+            ref.multiply(cx, cy, c3); // size 3
+            ref.mod_reduce_to_next(c3, r5);
+            gpu.mod_reduce_to_next(c3, g5);
+            CHECK(same_ct(r5, g5));
+            ref.mod_reduce_to(cx, context.last_parms_id(), r5);
+            gpu.mod_reduce_to(cx, context.last_parms_id(), g5);
+            CHECK(same_ct(r5, g5));
+            Plaintext rp, gp;
+            ref.mod_switch_to_next(px, rp);
+            gpu.mod_switch_to_next(px, gp);
+            CHECK(rp.parms_id() == gp.parms_id() && rp.coeff_count() == gp.coeff_count() && rp.scale() == gp.scale() &&
+                  std::memcmp(rp.data(), gp.data(), rp.coeff_count() * 8) == 0);
+            ref.mod_switch_to(px, context.last_parms_id(), rp);
+            gpu.mod_switch_to(px, context.last_parms_id(), gp);
+            CHECK(rp.parms_id() == gp.parms_id() && rp.coeff_count() == gp.coeff_count() &&
+                  std::memcmp(rp.data(), gp.data(), rp.coeff_count() * 8) == 0);
+            auto a = outcome([&] { Plaintext t = rp; ref.mod_switch_to_next_inplace(t); });
+            auto b = outcome([&] { Plaintext t = gp; gpu.mod_switch_to_next_inplace(t); });
+            CHECK(a == b && a == "invalid_argument"); // end of modulus switching chain reached
+        }
         auto last = context.last_parms_id();
         ref.mod_switch_to(cx, last, r2);
         gpu.mod_switch_to(cx, last, g2);
