@@ -125,6 +125,11 @@ int sb200_multiply_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t
  * May run in place. */
 int sb200_add_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *d_a,
                           const uint64_t *d_plain, const uint64_t *h_correction_factors, uint64_t *d_out, void *stream);
+/* BatchEncoder::encode / decode (batchencoder.cpp:84-330): d_values [batch][n] matrix slots (< t,
+ * row-major 2 x n/2) <-> coefficient-form plaintexts d_plain [batch][n].  Needs an NTT-friendly plain modulus
+ * (t prime, t = 1 mod 2n: "encryption parameters are not valid for batching" otherwise).  No aliasing. */
+int sb200_batch_encode(sb200_context *ctx, size_t batch, const uint64_t *d_values, uint64_t *d_plain, void *stream);
+int sb200_batch_decode(sb200_context *ctx, size_t batch, const uint64_t *d_plain, uint64_t *d_values, void *stream);
 /* Evaluator::relinearize_inplace, size 3 -> 2 (evaluator.cpp:1144-1199 + 2561-2867) */
 int sb200_relinearize(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in3,
                       const sb200_kswitch_key *relin_key, uint64_t *d_out2, void *stream);
@@ -157,6 +162,8 @@ int sb200_multiply_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, s
                                     const uint64_t *h_plain, uint64_t *h_out);
 int sb200_add_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t batch, int subtract, const uint64_t *h_a,
                                const uint64_t *h_plain, const uint64_t *h_correction_factors, uint64_t *h_out);
+int sb200_batch_encode_host(sb200_context *ctx, size_t batch, const uint64_t *h_values, uint64_t *h_plain);
+int sb200_batch_decode_host(sb200_context *ctx, size_t batch, const uint64_t *h_plain, uint64_t *h_values);
 int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in3,
                            const sb200_kswitch_key *relin_key, uint64_t *h_out2);
 int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b,

@@ -329,6 +329,30 @@ extern "C" int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size,
     REF_CATCH(-1)
 }
 
+// BatchEncoder::encode / decode on n matrix slots
+extern "C" int sealref_batch_codec(sealref_ctx *c, int decode, const uint64_t *in, uint64_t *out)
+{
+    REF_TRY
+    BatchEncoder enc(*c->context);
+    if (decode)
+    {
+        Plaintext p(c->n);
+        std::memcpy(p.data(), in, c->n * sizeof(uint64_t));
+        std::vector<uint64_t> v;
+        enc.decode(p, v);
+        std::memcpy(out, v.data(), c->n * sizeof(uint64_t));
+    }
+    else
+    {
+        Plaintext p;
+        enc.encode(std::vector<uint64_t>(in, in + c->n), p);
+        std::memset(out, 0, c->n * sizeof(uint64_t));
+        std::memcpy(out, p.data(), p.coeff_count() * sizeof(uint64_t));
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
 // coefficient-form plaintext of n words (< plain_modulus)
 static Plaintext make_plain(const sealref_ctx *c, const uint64_t *words)
 {

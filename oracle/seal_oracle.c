@@ -368,6 +368,42 @@ void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const u64 *
                 out[(p * L + i) * n + j] = mulmod(a[(p * L + i) * n + j], plain[i * n + j], c->q[i]);
 }
 
+/* ---- BatchEncoder (batchencoder.cpp:54-76 index map, :84-130 encode, :229-275 decode) ------------------------------------ */
+int orc_batch_codec(const orc_ctx *c, int decode, const u64 *in, u64 *out)
+{
+    size_t n = c->n, row = n >> 1;
+    int logn = ilog2(n);
+    orc_tab tt; /* plain_ntt_tables: transform tables modulo t (context.cpp:374-394) */
+    if (tab_init(&tt, n, c->t))
+        return -1;
+    size_t *map = (size_t *)malloc(n * sizeof(size_t));
+    u64 m = (u64)n << 1, pos = 1;
+    for (size_t i = 0; i < row; i++)
+    {
+        map[i] = (size_t)reverse_bits((pos - 1) >> 1, logn);
+        map[row | i] = (size_t)reverse_bits((m - pos - 1) >> 1, logn);
+        pos = (pos * 3) & (m - 1);
+    }
+    if (!decode)
+    {
+        for (size_t i = 0; i < n; i++)
+            out[map[i]] = in[i];
+        ntt_inv(&tt, n, out);
+    }
+    else
+    {
+        u64 *tmp = (u64 *)malloc(n * sizeof(u64));
+        memcpy(tmp, in, n * sizeof(u64));
+        ntt_fwd(&tt, n, tmp);
+        for (size_t i = 0; i < n; i++)
+            out[i] = tmp[map[i]];
+        free(tmp);
+    }
+    free(map);
+    tab_free(&tt);
+    return 0;
+}
+
 /* ---- coefficient-form plaintexts (BFV / BGV) -------------------------------------------------------------------------- */
 /* the lift of evaluator.cpp:2240-2272 / :2101-2127: words >= (t+1)/2 stand for negative numbers */
 static u64 plain_lift(u64 v, u64 t, u64 q)

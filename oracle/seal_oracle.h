@@ -64,6 +64,8 @@ void orc_ckks_multiply(const orc_ctx *c, size_t L, const uint64_t *a, const uint
 void orc_linear(const orc_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out);
 /* Evaluator::multiply_plain, ciphertext and plaintext in NTT form (evaluator.cpp:2157-2195) */
 void orc_multiply_plain_ntt(const orc_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out);
+/* BatchEncoder::encode (decode = 0) / decode (1) on n matrix slots (batchencoder.cpp:54-130, :229-275); -1: t does not support batching */
+int orc_batch_codec(const orc_ctx *c, int decode, const uint64_t *in, uint64_t *out);
 /* coefficient-form plaintexts (n words < t): transform_to_ntt(Plaintext) :2197-2287, multiply_plain :2021-2155 / :1999-2004,
  * add_plain / sub_plain util/scalingvariant.cpp:70-160 (BFV) and evaluator.cpp:1838-1849 (BGV) */
 void orc_plain_to_ntt(const orc_ctx *c, size_t L, const uint64_t *plain, uint64_t *out);

@@ -26,9 +26,9 @@ SYMBOLS = [
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
     "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
-    "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
+    "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_batch_encode", "sb200_batch_decode", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
-    "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_plain_to_ntt_host", "sb200_multiply_plain_coeff_host", "sb200_add_plain_coeff_host",
+    "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_batch_encode_host", "sb200_batch_decode_host", "sb200_plain_to_ntt_host", "sb200_multiply_plain_coeff_host", "sb200_add_plain_coeff_host",
     "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
     "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save",
@@ -83,6 +83,10 @@ def lib():
         L.sb200_negate.argtypes = [vp, sz, sz, sz, vp, vp, vp]
         L.sb200_multiply_plain.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
         L.sb200_multiply_plain_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p, _u64p]
+        L.sb200_batch_encode.argtypes = [vp, sz, vp, vp, vp]
+        L.sb200_batch_decode.argtypes = [vp, sz, vp, vp, vp]
+        L.sb200_batch_encode_host.argtypes = [vp, sz, _u64p, _u64p]
+        L.sb200_batch_decode_host.argtypes = [vp, sz, _u64p, _u64p]
         L.sb200_plain_to_ntt.argtypes = [vp, sz, sz, vp, vp, vp]
         L.sb200_multiply_plain_coeff.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp, vp]
         L.sb200_add_plain_coeff.argtypes = [vp, sz, sz, sz, i32, vp, vp, _u64p, vp, vp]
@@ -315,6 +319,24 @@ class Context:
         plain = np.ascontiguousarray(plain).reshape(B, L, n)
         out = np.zeros_like(a)
         _check(lib().sb200_multiply_plain_host(self.h, L, size, B, _hp(a), _hp(plain), _hp(out)))
+        return out[0] if single else out
+
+    def batch_encode(self, values):
+        """BatchEncoder.encode: [B][n] matrix slots (< t) -> coefficient-form plaintexts [B][n]"""
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        single = v.ndim == 1
+        v = v[None] if single else v
+        out = np.zeros_like(v)
+        _check(lib().sb200_batch_encode_host(self.h, v.shape[0], _hp(v), _hp(out)))
+        return out[0] if single else out
+
+    def batch_decode(self, plain):
+        """BatchEncoder.decode: coefficient-form plaintexts [B][n] -> matrix slots [B][n]"""
+        p = np.ascontiguousarray(plain, dtype=np.uint64)
+        single = p.ndim == 1
+        p = p[None] if single else p
+        out = np.zeros_like(p)
+        _check(lib().sb200_batch_decode_host(self.h, p.shape[0], _hp(p), _hp(out)))
         return out[0] if single else out
 
     def plain_to_ntt(self, plain, L):

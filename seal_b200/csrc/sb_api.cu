@@ -474,6 +474,30 @@ int sb200_add_plain_coeff(sb200_context *ctx, size_t L, size_t size, size_t batc
     SB_CATCH
 }
 
+static int batch_codec_dev(sb200_context *ctx, bool decode, size_t batch, const uint64_t *in, uint64_t *out, void *stream)
+{
+    SB_NEED(in);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    if (batch == 0)
+        throw std::invalid_argument("batch must be positive");
+    if (decode)
+        op_batch_decode(c, batch, (const u64 *)in, (u64 *)out, static_cast<cudaStream_t>(stream));
+    else
+        op_batch_encode(c, batch, (const u64 *)in, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_batch_encode(sb200_context *ctx, size_t batch, const uint64_t *values, uint64_t *plain, void *stream)
+{
+    return batch_codec_dev(ctx, false, batch, values, plain, stream);
+}
+int sb200_batch_decode(sb200_context *ctx, size_t batch, const uint64_t *plain, uint64_t *values, void *stream)
+{
+    return batch_codec_dev(ctx, true, batch, plain, values, stream);
+}
+
 int sb200_square(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3, void *stream)
 {
     return sb200_multiply(ctx, L, batch, a, a, out3, stream);
@@ -797,6 +821,32 @@ int sb200_add_plain_coeff_host(sb200_context *ctx, size_t L, size_t size, size_t
     });
     return SB200_OK;
     SB_CATCH
+}
+
+static int batch_codec_host(sb200_context *ctx, bool decode, size_t batch, const uint64_t *in, uint64_t *out)
+{
+    SB_NEED(in);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    if (batch == 0)
+        throw std::invalid_argument("batch must be positive");
+    HostPipe(c).run(batch, c.n, 0, c.n, in, nullptr, out, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
+        if (decode)
+            op_batch_decode(c, B, da, dout, st);
+        else
+            op_batch_encode(c, B, da, dout, st);
+    });
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_batch_encode_host(sb200_context *ctx, size_t batch, const uint64_t *values, uint64_t *plain)
+{
+    return batch_codec_host(ctx, false, batch, values, plain);
+}
+int sb200_batch_decode_host(sb200_context *ctx, size_t batch, const uint64_t *plain, uint64_t *values)
+{
+    return batch_codec_host(ctx, true, batch, plain, values);
 }
 
 int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3)

@@ -38,6 +38,7 @@ namespace sb
         cudaFree(d_invq);
         cudaFree(d_qmod);
         cudaFree(d_t_mod_q);
+        cudaFree(d_batch_inv_map);
         for (auto &kv : plain_levels)
             cudaFree(kv.second.d_delta);
         cudaFree(scratch);
@@ -198,6 +199,13 @@ namespace sb
         for (size_t i = 0; i < c->aux.size(); i++)
             if (i != 1) // gamma is only used by decryption
                 c->tabs[k + i].build(n, c->aux[i]);
+        if (scheme != 2 && t > 2 && (t - 1) % (2 * n) == 0 && sbh::is_prime(t))
+        {
+            // plain_ntt_tables (context.cpp:374-394): batching is available, t gets transform tables of its own
+            c->t_pid = static_cast<int>(c->tabs.size());
+            c->tabs.emplace_back();
+            c->tabs.back().build(n, t);
+        }
         for (size_t i = 0; i < c->tabs.size(); i++)
         {
             if (c->tabs[i].q == 0)
@@ -231,6 +239,16 @@ namespace sb
         cuda_check(cudaMalloc(&c->d_invq, invq.size() * sizeof(Tw)), "cudaMalloc(invq)");
         cuda_check(cudaMemcpy(c->d_invq, invq.data(), invq.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload invq");
         c->table_bytes += hp.size() * sizeof(PrimeDev) + invq.size() * sizeof(Tw);
+        if (c->t_pid >= 0)
+        {
+            const auto map = sbh::batch_index_map(n);
+            std::vector<uint32_t> inv(n);
+            for (size_t i = 0; i < n; i++)
+                inv[map[i]] = static_cast<uint32_t>(i);
+            cuda_check(cudaMalloc(&c->d_batch_inv_map, n * sizeof(uint32_t)), "cudaMalloc(batch map)");
+            cuda_check(cudaMemcpy(c->d_batch_inv_map, inv.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice), "upload batch map");
+            c->table_bytes += n * sizeof(uint32_t);
+        }
         for (size_t L = 1; L <= k; L++)
         {
             std::array<u64, 4> id;
@@ -789,6 +807,95 @@ namespace sb
                                                                                       static_cast<int>(L), subtract ? 1 : 0, total);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "add_c0_kernel");
+        }
+    }
+
+    // ---- BatchEncoder (batchencoder.cpp:84-330): the slot permutation rides in the load (encode) or the store (decode) of a
+    //      transform modulo t; rows = plaintexts
+    struct OpBatchEncode
+    {
+        const u64 *values;        // [B][n] matrix slots
+        const uint32_t *inv_map;  // coefficient index -> slot
+        u64 *plain;               // [B][n]
+        int logn, pid_t;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int) const { return pid_t; }
+        __device__ __forceinline__ const u64 *direct(int, const PrimeDev &) const { return nullptr; }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const
+        {
+            return values[(static_cast<long long>(row) << logn) + inv_map[idx]];
+        }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = load1(row, idx0 + j, P);
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return plain + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const { mid(row)[idx] = csub(v, P.q); }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+    struct OpBatchDecode
+    {
+        const u64 *plain;         // [B][n] coefficients
+        const uint32_t *inv_map;
+        u64 *tmp;                 // [B][n] intermediate rows of the two-pass transform
+        u64 *values;              // [B][n]
+        int logn, pid_t;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int) const { return pid_t; }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return plain + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &P) const { return direct(row, P)[idx]; }
+        __device__ __forceinline__ void load8(int, int, u64 (&)[8], const PrimeDev &) const {}
+        __device__ __forceinline__ u64 *mid(int row) const { return tmp + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            values[(static_cast<long long>(row) << logn) + inv_map[idx]] = csub(csub(v, P.q2), P.q);
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                store1(row, idx0 + j, a[j], P);
+        }
+    };
+
+    static void check_batching(const Context &c)
+    {
+        if (c.t_pid < 0)
+            throw std::invalid_argument("encryption parameters are not valid for batching"); // batchencoder.cpp:27-30
+    }
+    void op_batch_encode(Context &c, size_t batch, const u64 *values, u64 *plain, cudaStream_t st)
+    {
+        check_batching(c);
+        if (values == plain)
+            throw std::invalid_argument("batch_encode: input and output must not alias");
+        const size_t step = std::max<size_t>(1, (size_t(1) << 30) / c.n);
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t B = std::min(step, batch - b0);
+            OpBatchEncode op{ values + b0 * c.n, c.d_batch_inv_map, plain + b0 * c.n, c.logn, c.t_pid };
+            cuda_check(launch_ntt_inv(op, static_cast<int>(B), c.logn, c.d_primes, st, c.stats, "batch_encode_intt"), "batch encode");
+        }
+    }
+    void op_batch_decode(Context &c, size_t batch, const u64 *plain, u64 *values, cudaStream_t st)
+    {
+        check_batching(c);
+        if (values == plain)
+            throw std::invalid_argument("batch_decode: input and output must not alias");
+        const size_t step = std::max<size_t>(1, std::min<size_t>((size_t(1) << 30) / c.n, c.scratch_budget / (c.n * sizeof(u64))));
+        for (size_t b0 = 0; b0 < batch; b0 += step)
+        {
+            const size_t B = std::min(step, batch - b0);
+            u64 *tmp = static_cast<u64 *>(c.ensure_scratch(B * c.n * sizeof(u64)));
+            OpBatchDecode op{ plain + b0 * c.n, c.d_batch_inv_map, tmp, values + b0 * c.n, c.logn, c.t_pid };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B), c.logn, c.d_primes, st, c.stats, "batch_decode_ntt", -1, (c.t >> 57) == 0),
+                       "batch decode");
         }
     }
 

@@ -54,6 +54,9 @@ namespace sb
         Tw *d_qmod = nullptr;                // BGV, [k][k]: d_qmod[j*k+i] = q_j mod q_i
         u64 t_ratio = 0;                     // BGV: floor(2^64 / t)
         std::vector<u64> inv_q_mod_t;        // BGV: q_j^-1 mod t
+        // BatchEncoder on the device (BFV / BGV with an NTT-friendly plain modulus): prime id of t and the inverse slot map
+        int t_pid = -1;
+        uint32_t *d_batch_inv_map = nullptr; // coefficient index -> matrix slot
         // coefficient-form plaintext operations (BFV / BGV): per-level constants, built on first use (sb_engine.cu: plain_level)
         struct PlainLevel
         {
@@ -93,6 +96,9 @@ namespace sb
     void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st);
     // coefficient-form plaintexts [B][n] (words < t): lift + NTT, multiply_plain, add_plain / sub_plain (BFV, BGV);
     // h_cf: per-ciphertext BGV correction factors on the host (nullptr = 1)
+    // BatchEncoder::encode / decode (batchencoder.cpp:84-330): values [B][n] (< t) <-> coefficient-form plaintexts [B][n]
+    void op_batch_encode(Context &c, size_t batch, const u64 *values, u64 *plain, cudaStream_t st);
+    void op_batch_decode(Context &c, size_t batch, const u64 *plain, u64 *values, cudaStream_t st);
     void op_plain_to_ntt(Context &c, size_t L, size_t batch, const u64 *plain, const u64 *h_cf, u64 *out, cudaStream_t st);
     void op_multiply_plain_coeff(Context &c, size_t L, size_t size, size_t batch, bool ct_ntt, const u64 *ct, const u64 *plain, u64 *out,
                                  cudaStream_t st);

@@ -291,6 +291,24 @@ namespace sbh
         return static_cast<std::uint32_t>(e);
     }
 
+    std::vector<std::uint32_t> batch_index_map(std::size_t n)
+    {
+        // slots of row 0 sit at the powers 3^i of the generator, row 1 at their negatives; positions are taken in the
+        // bit-reversed order the transform produces
+        const int logn = ilog2(n);
+        const std::size_t row = n >> 1;
+        const u64 m = static_cast<u64>(n) << 1;
+        std::vector<std::uint32_t> map(n);
+        u64 pos = 1;
+        for (std::size_t i = 0; i < row; i++)
+        {
+            map[i] = static_cast<std::uint32_t>(reverse_bits((pos - 1) >> 1, logn));
+            map[row | i] = static_cast<std::uint32_t>(reverse_bits((m - pos - 1) >> 1, logn));
+            pos = (pos * 3) & (m - 1);
+        }
+        return map;
+    }
+
     std::vector<std::uint32_t> galois_table_ntt(std::size_t n, std::uint32_t elt)
     {
         const int logn = ilog2(n);

@@ -84,4 +84,6 @@ namespace sbh
 
     std::uint32_t galois_elt_from_step(std::size_t n, int step);                 // galois.cpp:53-95
     std::vector<std::uint32_t> galois_table_ntt(std::size_t n, std::uint32_t elt); // galois.cpp:18-51
+    // BatchEncoder::populate_matrix_reps_index_map (batchencoder.cpp:54-76): slot i of the 2 x n/2 matrix -> coefficient index
+    std::vector<std::uint32_t> batch_index_map(std::size_t n);
 } // namespace sbh

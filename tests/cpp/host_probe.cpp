@@ -90,5 +90,11 @@ long probe_kswitch_offsets(const unsigned char *stream, size_t len, size_t index
         return -2;
     }
 }
+int probe_batch_index_map(size_t n, unsigned *out)
+{
+    auto m = sbh::batch_index_map(n);
+    std::memcpy(out, m.data(), n * sizeof(unsigned));
+    return 0;
+}
 int probe_is_prime(unsigned long long v) { return sbh::is_prime(v) ? 1 : 0; }
 }

@@ -4,6 +4,7 @@
 // native/tests/seal/evaluator.cpp:1356 (BFVEncryptMultiplyDecrypt), :3513 (CKKSEncryptMultiplyRelinRescaleDecrypt),
 // :4326 (CKKSEncryptRotateDecrypt), :5670 (BFVEncryptRotateMatrixDecrypt), :2505/:2532 (negative relinearize tests).
 // TEST INFRASTRUCTURE: links the reference; built only where /root/reference exists; the binary travels to the GPU box.
+#include "seal_b200/batchencoder.hpp"
 #include "seal_b200/evaluator.hpp"
 #include <complex>
 #include <cstdio>
@@ -443,6 +444,44 @@ static void test_bfv()
         auto a = outcome([&] { Ciphertext tt = cx; ref.add_plain_inplace(tt, rp); });
         auto b = outcome([&] { Ciphertext tt = cx; gpu.add_plain_inplace(tt, gp); });
         CHECK(a == b && a == "invalid_argument"); // BFV plain cannot be in NTT form
+    }
+    {
+        // BatchEncoder on the device: encode / decode, unsigned and signed, short inputs
+        seal_b200::BatchEncoder genc(context, gpu);
+        CHECK(genc.slot_count() == encoder.slot_count());
+        Plaintext rp, gp;
+        encoder.encode(x, rp);
+        genc.encode(x, gp);
+        CHECK(rp.coeff_count() == gp.coeff_count() && rp.parms_id() == gp.parms_id() &&
+              std::memcmp(rp.data(), gp.data(), rp.coeff_count() * 8) == 0);
+        std::vector<uint64_t> rv, gv;
+        encoder.decode(px, rv);
+        genc.decode(px, gv);
+        CHECK(rv == gv && gv == x);
+        std::vector<int64_t> sx{ -5, 7, 0, -123456, 99 }, rs, gs;
+        encoder.encode(sx, rp);
+        genc.encode(sx, gp);
+        CHECK(rp.coeff_count() == gp.coeff_count() && std::memcmp(rp.data(), gp.data(), rp.coeff_count() * 8) == 0);
+        encoder.decode(rp, rs);
+        genc.decode(gp, gs);
+        CHECK(rs == gs && gs[0] == -5 && gs[3] == -123456 && gs[5] == 0);
+        Plaintext small("7x^2 + 1"); // fewer than n coefficients
+        encoder.decode(small, rv);
+        genc.decode(small, gv);
+        CHECK(rv == gv);
+        auto a = outcome([&] { Plaintext tt; encoder.encode(std::vector<uint64_t>(n + 1, 1), tt); });
+        auto b = outcome([&] { Plaintext tt; genc.encode(std::vector<uint64_t>(n + 1, 1), tt); });
+        CHECK(a == b && a == "invalid_argument");
+        a = outcome([&] { Plaintext tt; encoder.encode(std::vector<uint64_t>{ t }, tt); });
+        b = outcome([&] { Plaintext tt; genc.encode(std::vector<uint64_t>{ t }, tt); });
+        CHECK(a == b && a == "invalid_argument");
+        // whole pipeline on the device side of the boundary: encode -> multiply_plain -> decrypt (reference) -> decode
+        Ciphertext g2;
+        gpu.multiply_plain(cx, gp, g2); // gp = encode(sx)
+        Plaintext dp;
+        decryptor.decrypt(g2, dp);
+        genc.decode(dp, gs);
+        CHECK(gs[0] == static_cast<int64_t>((t - 5 * x[0] % t) % t > t / 2 ? (t - 5 * x[0] % t) % t - t : (t - 5 * x[0] % t) % t));
     }
     {
         // multiply_many / exponentiate (evaluator.cpp:1649-1757)

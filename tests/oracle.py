@@ -168,6 +168,13 @@ class Oracle:
         lib().orc_multiply_plain_ntt(self.h, L, a.shape[0], _p(a), _p(plain), _p(out))
         return out
 
+    def batch_codec(self, data, decode):
+        lib().orc_batch_codec.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        out = np.zeros(self.n, dtype=np.uint64)
+        assert lib().orc_batch_codec(self.h, int(decode), _p(data), _p(out)) == 0
+        return out
+
     def plain_to_ntt(self, L, plain):
         lib().orc_plain_to_ntt.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         plain = np.ascontiguousarray(plain, dtype=np.uint64)

@@ -58,6 +58,7 @@ def lib():
         L.sealref_bfv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_int)]
         L.sealref_time_op.restype = C.c_double
         L.sealref_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]
+        L.sealref_batch_codec.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
         L.sealref_plain_to_ntt.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.sealref_plain_op_coeff.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, _u64p, _u64p, _u64p]
         L.sealref_parms_id.argtypes = [C.c_void_p, C.c_size_t, _u64p]
@@ -236,6 +237,12 @@ class RefContext:
         nb = C.c_int(0)
         self._chk(lib().sealref_bfv_decrypt(self.h, L, ct.shape[0], _p(ct), _p(out), C.byref(nb)))
         return out, nb.value
+
+    def batch_codec(self, data, decode):
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        out = np.zeros(self.n, dtype=np.uint64)
+        self._chk(lib().sealref_batch_codec(self.h, int(decode), _p(data), _p(out)))
+        return out
 
     def plain_to_ntt(self, L, plain):
         plain = np.ascontiguousarray(plain, dtype=np.uint64)

@@ -456,6 +456,30 @@ def test_coeff_plain_ops_vs_reference(scheme, t_bits, n):
             assert (mn[0] == rc.plain_op_coeff(0, L, a[0], plain[0], True)).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("n,t_bits", [(256, 20), (4096, 20), (8192, 44)])
+def test_batch_codec_vs_reference(n, t_bits):
+    # BatchEncoder::encode / decode (batchencoder.cpp:84-330) as a transform modulo t
+    batch = 3
+    mods = R.coeff_modulus_create(n, [50, 45, 60])
+    t = R.plain_modulus_batching(n, t_bits)
+    rc = R.RefContext(R.BFV, n, mods, t)
+    ctx = sb().Context(sb().BFV, n, mods, t)
+    rng = np.random.default_rng(67)
+    v = rng.integers(0, t, (batch, n), dtype=np.uint64)
+    p = ctx.batch_encode(v)
+    w = rng.integers(0, t, (batch, n), dtype=np.uint64)
+    d = ctx.batch_decode(w)
+    for i in range(batch):
+        assert (p[i] == rc.batch_codec(v[i], False)).all()
+        assert (d[i] == rc.batch_codec(w[i], True)).all()
+    assert (ctx.batch_decode(p) == v).all()
+    # a plain modulus that does not support batching
+    ctx2 = sb().Context(sb().BFV, n, mods, 1 << 20)
+    with pytest.raises(ValueError):
+        ctx2.batch_encode(v % (1 << 20))
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

@@ -122,6 +122,7 @@ def _probe():
     L.probe_is_prime.argtypes = [C.c_uint64]
     L.probe_parms_id.argtypes = [C.c_int, C.c_size_t, u64p, C.c_size_t, C.c_uint64, u64p]
     L.probe_blake2b_256.argtypes = [C.c_char_p, C.c_size_t, u64p]
+    L.probe_batch_index_map.argtypes = [C.c_size_t, C.POINTER(C.c_uint32)]
     L.probe_kswitch_offsets.restype = C.c_long
     L.probe_kswitch_offsets.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_size_t)]
@@ -280,3 +281,23 @@ def test_kswitch_keys_stream_parsing_vs_reference():
     assert (entry(gs, (e - 1) // 2) == rc.galois_key(e)).all()
     assert entry(gs, 0) == -1  # an empty slot: "key not present"
     assert entry(gs[:200], (e - 1) // 2) == -2  # truncated
+
+
+def test_batch_index_map_matches_oracle():
+    # BatchEncoder::populate_matrix_reps_index_map (batchencoder.cpp:54-76): encode = scatter by the map + INTT modulo t
+    import ctypes as C
+
+    P = _probe()
+    for n, t in ((8, 17), (256, 12289), (4096, 1032193)):
+        m = np.zeros(n, dtype=np.uint32)
+        P.probe_batch_index_map(n, m.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert sorted(m) == list(range(n))
+        oc = O.Oracle(O.BFV, n, O.coeff_modulus_create(n, [30, 31]), t)
+        rng = np.random.default_rng(n)
+        v = rng.integers(0, t, n, dtype=np.uint64)
+        scattered = np.zeros(n, dtype=np.uint64)
+        scattered[m] = v
+        # decode(plain)[i] = NTT_t(plain)[map[i]]: the scattered vector is the transform of encode(v)
+        assert (oc.batch_codec(oc.batch_codec(v, False), True) == v).all()
+        tt = O.Oracle(O.CKKS, n, [t])  # a context whose only prime is t gives the plain transform
+        assert (tt.ntt_row(0, oc.batch_codec(v, False)) == scattered).all()

@@ -228,3 +228,21 @@ def test_oracle_coeff_plain_ops_vs_live_reference(scheme, t_bits):
             cf = 1 if scheme == "bfv" else 12345 % t
             assert (rc.plain_op_coeff(1, L, a, plain, ntt, cf) == oc.add_plain_coeff(L, a, plain, False, cf)).all()
             assert (rc.plain_op_coeff(2, L, a, plain, ntt, cf) == oc.add_plain_coeff(L, a, plain, True, cf)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ["bfv", "bgv"])
+def test_oracle_batch_codec_vs_live_reference(scheme):
+    # BatchEncoder::encode / decode (batchencoder.cpp:84-330)
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42])
+    t = R.plain_modulus_batching(n, 20)
+    sid = R.BFV if scheme == "bfv" else R.BGV
+    rc, oc = R.RefContext(sid, n, mods, t), O.Oracle(sid, n, mods, t)
+    rng = np.random.default_rng(61)
+    v = rng.integers(0, t, n, dtype=np.uint64)
+    p = rc.batch_codec(v, False)
+    assert (p == oc.batch_codec(v, False)).all()
+    assert (rc.batch_codec(p, True) == v).all() and (oc.batch_codec(p, True) == v).all()
+    w = rng.integers(0, t, n, dtype=np.uint64)  # any coefficient vector decodes
+    assert (rc.batch_codec(w, True) == oc.batch_codec(w, True)).all()
