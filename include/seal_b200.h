@@ -38,6 +38,7 @@ extern "C" {
 #define SB200_SCHEME_BGV 3  /* seal::scheme_type::bgv: NTT-form ciphertexts like CKKS, plain-modulus-aware mod-down */
 
 typedef struct sb200_context sb200_context;   /* mirrors SEALContext + Evaluator state (context.h:277-439) */
+typedef struct sb200_secret_key sb200_secret_key;   /* Decryptor state: the secret key and its powers on the device (decryptor.h) */
 typedef struct sb200_kswitch_key sb200_kswitch_key; /* one KSwitchKeys::data()[index] entry on the device (kswitchkeys.h) */
 
 /* last error message of the calling thread (never NULL) */
@@ -208,6 +209,20 @@ int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const
  * the bytes are in place. */
 int sb200_ciphertext_save(sb200_context *ctx, size_t batch, size_t L, size_t size, const uint64_t *d_in, const sb200_ct_info *meta,
                           uint8_t *const *outs, size_t capacity, void *stream);
+
+/* ---- decryption: Decryptor(context, secret_key) and Decryptor::decrypt (decryptor.cpp:62-197) ------
+ * h_secret_key = SecretKey::data().data(): [k][n] words, NTT form at the key level.  Powers of the key for ciphertexts
+ * of size > 2 are built on the device on first use (compute_secret_key_array, :199-310). */
+int sb200_secret_key_create(sb200_context *ctx, const uint64_t *h_secret_key, sb200_secret_key **out);
+int sb200_secret_key_destroy(sb200_secret_key *key);
+/* d_ct [batch][size][L][n] in the scheme's own form -> d_plain: CKKS [batch][L][n] (NTT form, same level; the caller keeps
+ * scale and parms_id); BFV [batch][n] coefficients mod t (dot product + decrypt_scale_and_round, rns.cpp:1133-1191);
+ * BGV [batch][n] (dot product, INTT, exact base conversion rns.cpp:466-539, times the inverse of the ciphertext's
+ * correction factor: h_correction_factors = [batch] host words or NULL for 1). */
+int sb200_decrypt(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *d_ct,
+                  const uint64_t *h_correction_factors, uint64_t *d_plain, void *stream);
+int sb200_decrypt_host(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *h_ct,
+                       const uint64_t *h_correction_factors, uint64_t *h_plain);
 
 #ifdef __cplusplus
 }

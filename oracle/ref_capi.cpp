@@ -329,6 +329,33 @@ extern "C" int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size,
     REF_CATCH(-1)
 }
 
+// the secret key (NTT form, key level) and Decryptor::decrypt of an arbitrary ciphertext; plain gets n words (BFV / BGV,
+// zero-padded) or L*n words (CKKS, NTT form)
+extern "C" int sealref_secret_key(sealref_ctx *c, uint64_t *out)
+{
+    REF_TRY
+    std::memcpy(out, c->keygen->secret_key().data().data(), c->k * c->n * sizeof(uint64_t));
+    return 0;
+    REF_CATCH(-1)
+}
+
+extern "C" int sealref_decrypt(
+    sealref_ctx *c, size_t L, size_t size, int is_ntt_form, uint64_t correction_factor, const uint64_t *ct, uint64_t *plain)
+{
+    REF_TRY
+    Ciphertext x = make_ct(c, L, size, ct);
+    x.is_ntt_form() = is_ntt_form != 0;
+    x.correction_factor() = correction_factor;
+    Decryptor dec(*c->context, c->keygen->secret_key());
+    Plaintext p;
+    dec.decrypt(x, p);
+    size_t words = c->scheme == scheme_type::ckks ? L * c->n : c->n;
+    std::memset(plain, 0, words * sizeof(uint64_t));
+    std::memcpy(plain, p.data(), std::min(words, p.coeff_count()) * sizeof(uint64_t));
+    return 0;
+    REF_CATCH(-1)
+}
+
 // BatchEncoder::encode / decode on n matrix slots
 extern "C" int sealref_batch_codec(sealref_ctx *c, int decode, const uint64_t *in, uint64_t *out)
 {

@@ -49,6 +49,8 @@ int sealref_multiply_sized(sealref_ctx *c, size_t L, size_t size_a, size_t size_
 int sealref_square(sealref_ctx *c, size_t L, const uint64_t *a, uint64_t *out3);                 /* Evaluator::square_inplace */
 int sealref_linear(sealref_ctx *c, int mode, size_t L, size_t size, const uint64_t *a, const uint64_t *b, uint64_t *out); /* 0 add, 1 sub, 2 negate */
 int sealref_multiply_plain_ntt(sealref_ctx *c, size_t L, size_t size, const uint64_t *a, const uint64_t *plain, uint64_t *out); /* Evaluator::multiply_plain, both NTT form */
+int sealref_secret_key(sealref_ctx *c, uint64_t *out); /* [k][n], NTT form at the key level */
+int sealref_decrypt(sealref_ctx *c, size_t L, size_t size, int is_ntt_form, uint64_t correction_factor, const uint64_t *ct, uint64_t *plain); /* Decryptor::decrypt */
 int sealref_batch_codec(sealref_ctx *c, int decode, const uint64_t *in, uint64_t *out); /* BatchEncoder::encode (0) / decode (1), n slots */
 int sealref_plain_to_ntt(sealref_ctx *c, size_t L, const uint64_t *plain, uint64_t *out); /* transform_to_ntt_inplace(Plaintext, parms_id) */
 int sealref_plain_op_coeff(sealref_ctx *c, int mode, size_t L, size_t size, int ct_is_ntt, uint64_t correction_factor, const uint64_t *a, const uint64_t *plain, uint64_t *out); /* 0 multiply_plain, 1 add_plain, 2 sub_plain; coefficient-form plaintext */

@@ -975,3 +975,111 @@ int orc_bfv_multiply_sized(const orc_ctx *c, size_t L, size_t s1, size_t s2, con
     free(stab);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------ decryption (decryptor.cpp) -- */
+/* dot_product_ct_sk_array (decryptor.cpp:312-384): phase = c_0 + sum_{p>=1} c_p * s^p, in the ciphertext's own form.
+ * sk = the secret key in NTT form at the key level, [k][n]. */
+void orc_decrypt_phase(const orc_ctx *c, size_t L, size_t size, int ct_is_ntt, const u64 *ct, const u64 *sk, u64 *out)
+{
+    size_t n = c->n;
+    u64 *pw = (u64 *)malloc(n * sizeof(u64)), *tmp = (u64 *)malloc(n * sizeof(u64)), *acc = (u64 *)malloc(n * sizeof(u64));
+    for (size_t i = 0; i < L; i++)
+    {
+        u64 q = c->q[i];
+        memset(acc, 0, n * sizeof(u64));
+        for (size_t j = 0; j < n; j++)
+            pw[j] = 1;
+        for (size_t p = 1; p < size; p++)
+        {
+            for (size_t j = 0; j < n; j++)
+                pw[j] = mulmod(pw[j], sk[i * n + j], q); /* s^p, compute_secret_key_array :245-310 */
+            memcpy(tmp, ct + (p * L + i) * n, n * sizeof(u64));
+            if (!ct_is_ntt)
+                ntt_fwd(&c->tab[i], n, tmp);
+            for (size_t j = 0; j < n; j++)
+                acc[j] = addmod(acc[j], mulmod(tmp[j], pw[j], q), q);
+        }
+        if (!ct_is_ntt)
+            ntt_inv(&c->tab[i], n, acc);
+        for (size_t j = 0; j < n; j++)
+            out[i * n + j] = addmod(acc[j], ct[i * n + j], q);
+    }
+    free(pw), free(tmp), free(acc);
+}
+
+/* Decryptor::bfv_decrypt (decryptor.cpp:111-135) = phase + RNSTool::decrypt_scale_and_round (rns.cpp:1133-1191) */
+int orc_bfv_decrypt(const orc_ctx *c, size_t L, size_t size, const u64 *ct, const u64 *sk, u64 *plain)
+{
+    size_t n = c->n;
+    u64 t = c->t, primes[2];
+    if (orc_get_primes(2 * (u64)n, 61, 2, primes))
+        return -1;
+    u64 gamma = primes[1], base[2] = { t, gamma };
+    u64 *phase = (u64 *)malloc(L * n * sizeof(u64)), *conv = (u64 *)malloc(2 * n * sizeof(u64));
+    orc_decrypt_phase(c, L, size, 0, ct, sk, phase);
+    for (size_t i = 0; i < L; i++) /* :1155-1158  |gamma * t|_{q_i} * ct(s) */
+    {
+        u64 f = mulmod(t % c->q[i], gamma % c->q[i], c->q[i]);
+        for (size_t j = 0; j < n; j++)
+            phase[i * n + j] = mulmod(phase[i * n + j], f, c->q[i]);
+    }
+    for (int b = 0; b < 2; b++) /* :1164 FastBConv q -> {t, gamma}; :1167-1171 times -q^-1 */
+    {
+        u64 p = base[b], inv = 0;
+        fastbconv(c->q, L, phase, n, n, p, conv + b * n);
+        invmod(prod_mod(c->q, L, (size_t)-1, p), p, &inv);
+        for (size_t j = 0; j < n; j++)
+            conv[b * n + j] = mulmod(conv[b * n + j], submod(0, inv, p), p);
+    }
+    u64 inv_gamma = 0;
+    invmod(gamma % t, t, &inv_gamma);
+    for (size_t j = 0; j < n; j++) /* :1175-1190 */
+    {
+        u64 g = conv[n + j], r;
+        if (g > (gamma >> 1))
+            r = addmod(conv[j], (gamma - g) % t, t);
+        else
+            r = submod(conv[j], g % t, t);
+        plain[j] = mulmod(r, inv_gamma, t);
+    }
+    free(phase), free(conv);
+    return 0;
+}
+
+/* Decryptor::bgv_decrypt (decryptor.cpp:159-197): phase, INTT, BaseConverter::exact_convert_array (rns.cpp:466-539, in
+ * IEEE doubles, summed in index order), times the inverse correction factor */
+int orc_bgv_decrypt(const orc_ctx *c, size_t L, size_t size, u64 correction_factor, const u64 *ct, const u64 *sk, u64 *plain)
+{
+    size_t n = c->n;
+    u64 t = c->t;
+    u64 *phase = (u64 *)malloc(L * n * sizeof(u64));
+    orc_decrypt_phase(c, L, size, 1, ct, sk, phase);
+    for (size_t i = 0; i < L; i++)
+        ntt_inv(&c->tab[i], n, phase + i * n);
+    u64 inv[ORC_MAX_PRIMES + 2], mat[ORC_MAX_PRIMES + 2], q_mod_t = prod_mod(c->q, L, (size_t)-1, t), fix = 1;
+    for (size_t i = 0; i < L; i++)
+    {
+        inv[i] = 0;
+        invmod(prod_mod(c->q, L, i, c->q[i]), c->q[i], &inv[i]);
+        mat[i] = prod_mod(c->q, L, i, t);
+    }
+    if (correction_factor != 1 && !invmod(correction_factor % t, t, &fix))
+        return -1; /* "invalid correction factor", decryptor.cpp:186-189 */
+    for (size_t j = 0; j < n; j++)
+    {
+        volatile double v = 0.0; /* sequential double additions, :519-523 */
+        u128 sum = 0;
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 x = mulmod(phase[i * n + j], inv[i], c->q[i]); /* :494-513 (operand 1: the same value) */
+            v = v + (double)x / (double)c->q[i];
+            sum = (sum + (u128)x * mat[i]) % t;
+        }
+        v = v + 0.5;
+        u64 rounded = (u64)v; /* :524-525 */
+        u64 r = submod((u64)sum, mulmod(rounded % t, q_mod_t, t), t); /* :532-537 */
+        plain[j] = mulmod(r, fix, t);
+    }
+    free(phase);
+    return 0;
+}

@@ -87,6 +87,11 @@ uint32_t orc_galois_elt_from_step(size_t n, int step);                          
 void orc_galois_coeff_row(size_t n, uint64_t q, uint32_t galois_elt, const uint64_t *in, uint64_t *out);
 void orc_galois_ntt_row(size_t n, uint32_t galois_elt, const uint64_t *in, uint64_t *out);
 
+/* decryption (decryptor.cpp); sk = the secret key in NTT form at the key level, [k][n] */
+void orc_decrypt_phase(const orc_ctx *c, size_t L, size_t size, int ct_is_ntt, const uint64_t *ct, const uint64_t *sk, uint64_t *out); /* :312-384; CKKS decrypt = this */
+int orc_bfv_decrypt(const orc_ctx *c, size_t L, size_t size, const uint64_t *ct, const uint64_t *sk, uint64_t *plain);                 /* :111-135, rns.cpp:1133-1191 */
+int orc_bgv_decrypt(const orc_ctx *c, size_t L, size_t size, uint64_t correction_factor, const uint64_t *ct, const uint64_t *sk, uint64_t *plain); /* :159-197, rns.cpp:466-539 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,8 @@ SYMBOLS = [
     "sb200_multiply_host", "sb200_multiply_sized_host", "sb200_square_host", "sb200_add_host", "sb200_sub_host", "sb200_negate_host", "sb200_multiply_plain_host", "sb200_batch_encode_host", "sb200_batch_decode_host", "sb200_plain_to_ntt_host", "sb200_multiply_plain_coeff_host", "sb200_add_plain_coeff_host",
     "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
-    "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save",
+    "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save", "sb200_secret_key_create",
+    "sb200_secret_key_destroy", "sb200_decrypt", "sb200_decrypt_host",
 ]
 
 
@@ -116,6 +117,10 @@ def lib():
         L.sb200_ciphertext_save_size.argtypes = [vp, sz, sz]
         L.sb200_ciphertext_load.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.POINTER(sz), sz, sz, i32, vp, C.POINTER(CtInfo), vp]
         L.sb200_ciphertext_save.argtypes = [vp, sz, sz, sz, vp, C.POINTER(CtInfo), C.POINTER(vp), sz, vp]
+        L.sb200_secret_key_create.argtypes = [vp, _u64p, C.POINTER(vp)]
+        L.sb200_secret_key_destroy.argtypes = [vp]
+        L.sb200_decrypt.argtypes = [vp, vp, sz, sz, sz, vp, _u64p, vp, vp]
+        L.sb200_decrypt_host.argtypes = [vp, vp, sz, sz, sz, _u64p, _u64p, _u64p]
         _lib = L
     return _lib
 
@@ -175,6 +180,26 @@ class KSwitchKey:
         try:
             if getattr(self, "h", None):
                 lib().sb200_kswitch_key_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class SecretKey:
+    """Decryptor state: the secret key ([k][n], NTT form at the key level) and its powers on the device."""
+
+    def __init__(self, ctx, host_key):
+        host_key = np.ascontiguousarray(host_key, dtype=np.uint64)
+        assert host_key.shape == (ctx.k, ctx.n)
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(lib().sb200_secret_key_create(ctx.h, _hp(host_key), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().sb200_secret_key_destroy(self.h)
                 self.h = None
         except Exception:
             pass
@@ -337,6 +362,18 @@ class Context:
         p = p[None] if single else p
         out = np.zeros_like(p)
         _check(lib().sb200_batch_decode_host(self.h, p.shape[0], _hp(p), _hp(out)))
+        return out[0] if single else out
+
+    def load_secret_key(self, host_key):
+        return SecretKey(self, host_key)
+
+    def decrypt(self, a, sk, correction_factors=None):
+        """Decryptor.decrypt: [B][size][L][n] -> CKKS [B][L][n] (NTT-form plaintexts), BFV / BGV [B][n] (coefficients mod t)"""
+        a, single = self._batched(a)
+        B, size, L, n = a.shape
+        out = np.zeros((B, L, n) if self.scheme == CKKS else (B, n), dtype=np.uint64)
+        cf = None if correction_factors is None else _hp(np.ascontiguousarray(correction_factors, dtype=np.uint64).reshape(B))
+        _check(lib().sb200_decrypt_host(self.h, sk.h, L, size, B, _hp(a), cf, _hp(out)))
         return out[0] if single else out
 
     def plain_to_ntt(self, plain, L):

@@ -16,6 +16,11 @@ struct sb200_context
 {
     std::unique_ptr<Context> c;
 };
+struct sb200_secret_key
+{
+    SecretKey k;
+    ~sb200_secret_key() { cudaFree(k.d_pow); }
+};
 struct sb200_kswitch_key
 {
     KSwitchKey k;
@@ -1016,6 +1021,60 @@ int sb200_ciphertext_save(sb200_context *ctx, size_t batch, size_t L, size_t siz
         cuda_check(cudaMemcpyAsync(outs[b] + sbw::kDataOffset, d_in + b * words, words * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H");
     }
     cuda_check(cudaStreamSynchronize(st), "synchronize");
+    return SB200_OK;
+    SB_CATCH
+}
+
+// ---- decryption: Decryptor(context, secret_key) + Decryptor::decrypt ----
+int sb200_secret_key_create(sb200_context *ctx, const uint64_t *h_secret_key, sb200_secret_key **out)
+{
+    SB_NEED(h_secret_key);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    auto h = std::make_unique<sb200_secret_key>();
+    secret_key_create(c, (const u64 *)h_secret_key, h->k);
+    *out = h.release();
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_secret_key_destroy(sb200_secret_key *key)
+{
+    SB_NEED(key);
+    delete key;
+    return SB200_OK;
+}
+
+int sb200_decrypt(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *ct,
+                  const uint64_t *h_correction_factors, uint64_t *plain, void *stream)
+{
+    SB_NEED(key);
+    SB_NEED(ct);
+    SB_NEED(plain);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_decrypt(c, key->k, L, size, batch, (const u64 *)ct, (const u64 *)h_correction_factors, (u64 *)plain, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_decrypt_host(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *ct,
+                       const uint64_t *h_correction_factors, uint64_t *plain)
+{
+    SB_NEED(key);
+    SB_NEED(ct);
+    SB_NEED(plain);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t wo = c.scheme == SB200_SCHEME_CKKS ? L * c.n : c.n;
+    size_t done = 0;
+    HostPipe(c).run(batch, size * L * c.n, 0, wo, ct, nullptr, plain, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
+        op_decrypt(c, key->k, L, size, B, da, h_correction_factors ? (const u64 *)h_correction_factors + done : nullptr, dout, st);
+        done += B;
+    });
     return SB200_OK;
     SB_CATCH
 }

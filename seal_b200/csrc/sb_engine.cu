@@ -39,6 +39,8 @@ namespace sb
         cudaFree(d_qmod);
         cudaFree(d_t_mod_q);
         cudaFree(d_batch_inv_map);
+        for (auto &kv : decrypt_levels)
+            cudaFree(kv.second.d_consts);
         for (auto &kv : plain_levels)
             cudaFree(kv.second.d_delta);
         cudaFree(scratch);
@@ -896,6 +898,279 @@ namespace sb
             OpBatchDecode op{ plain + b0 * c.n, c.d_batch_inv_map, tmp, values + b0 * c.n, c.logn, c.t_pid };
             cuda_check(launch_ntt_fwd(op, static_cast<int>(B), c.logn, c.d_primes, st, c.stats, "batch_decode_ntt", -1, (c.t >> 57) == 0),
                        "batch decode");
+        }
+    }
+
+    // ---- decryption (decryptor.cpp): phase = c_0 + sum c_p s^p, then per scheme ---------------------------------------
+    void secret_key_create(Context &c, const u64 *h_sk, SecretKey &out)
+    {
+        const size_t bytes = c.k * c.n * sizeof(u64);
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&out.d_pow), bytes), "cudaMalloc(secret key)");
+        cuda_check(cudaMemcpy(out.d_pow, h_sk, bytes, cudaMemcpyHostToDevice), "upload secret key");
+        out.ctx = &c, out.powers = 1;
+    }
+    // Decryptor::compute_secret_key_array (decryptor.cpp:199-310): s^p = s^(p-1) * s, dyadic at the key level
+    static void ensure_key_powers(Context &c, SecretKey &sk, size_t powers, cudaStream_t st)
+    {
+        if (powers <= sk.powers)
+            return;
+        const size_t row = c.k * c.n;
+        u64 *grown = nullptr;
+        cuda_check(cudaDeviceSynchronize(), "sync before key array growth");
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&grown), powers * row * sizeof(u64)), "cudaMalloc(secret key array)");
+        cuda_check(cudaMemcpy(grown, sk.d_pow, sk.powers * row * sizeof(u64), cudaMemcpyDeviceToDevice), "copy");
+        cudaFree(sk.d_pow);
+        sk.d_pow = grown;
+        for (size_t p = sk.powers; p < powers; p++)
+            op_multiply_plain(c, c.k, 1, 1, sk.d_pow + (p - 1) * row, sk.d_pow, sk.d_pow + p * row, st);
+        sk.powers = powers;
+    }
+
+    // sum_{p>=1} src_p * s^p (+ c_0) per coefficient; rows of src: item b, poly p-1 at src + b*src_bs + (p-1)*L*n
+    template <bool ADD_C0>
+    __global__ void __launch_bounds__(256) phase_kernel(const u64 *__restrict__ src, long long src_bs, const u64 *__restrict__ c0, long long c0_bs,
+                                                         const u64 *__restrict__ skpow, long long sk_ps, u64 *__restrict__ out,
+                                                         const PrimeDev *__restrict__ primes, int logn, int L, int npow, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*L*n
+        if (e >= total)
+            return;
+        const long long poly = static_cast<long long>(L) << logn, b = e / poly, r = e % poly;
+        const PrimeDev P = primes[static_cast<int>(r >> logn)];
+        u64 lo = 0, hi = 0;
+        for (int p = 0; p < npow; p++)
+            mac128(lo, hi, src[b * src_bs + p * poly + r], skpow[p * sk_ps + r]);
+        u64 v = barrett128(lo, hi, P.q, P.ratio_lo, P.ratio_hi);
+        if (ADD_C0)
+            v = csub(v + c0[b * c0_bs + r], P.q);
+        out[e] = v;
+    }
+
+    struct DecConst
+    {
+        Tw c;      // BFV: (t * gamma mod q_i) * (q/q_i)^-1 mod q_i;  BGV: (q/q_i)^-1 mod q_i
+        u64 m_t;   // (q/q_i) mod t
+        u64 m_g;   // (q/q_i) mod gamma (BFV)
+        u64 pad;
+    };
+    static_assert(sizeof(DecConst) == 40 || sizeof(DecConst) == 48, "layout");
+
+    __device__ __forceinline__ u64 mulmod_any(u64 a, u64 b, u64 m, u64 ratio_lo, u64 ratio_hi)
+    {
+        // the ratio may sit one below floor(2^128 / m): one more conditional subtraction
+        return csub(barrett128(a * b, __umul64hi(a, b), m, ratio_lo, ratio_hi), m);
+    }
+
+    // BFV: RNSTool::decrypt_scale_and_round (rns.cpp:1133-1191) on phase = T (INTT of the key part) + c_0
+    __global__ void __launch_bounds__(128) bfv_scale_round_kernel(const u64 *__restrict__ T, const u64 *__restrict__ c0, long long c0_bs,
+                                                                   u64 *__restrict__ plain, const DecConst *__restrict__ dc,
+                                                                   const PrimeDev *__restrict__ primes, u64 t, u64 t_rlo, u64 t_rhi, u64 gamma,
+                                                                   u64 g_rlo, u64 g_rhi, u64 neg_inv_q_t, u64 neg_inv_q_g, u64 inv_gamma_t,
+                                                                   int logn, int L, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*n
+        if (e >= total)
+            return;
+        const long long b = e >> logn;
+        const int idx = static_cast<int>(e & ((1 << logn) - 1));
+        u64 tl = 0, th = 0, gl = 0, gh = 0;
+        for (int i = 0; i < L; i++)
+        {
+            const PrimeDev P = primes[i];
+            const long long off = (static_cast<long long>(i) << logn) + idx;
+            const u64 x = csub(T[((b * L) << logn) + off] + c0[b * c0_bs + off], P.q);
+            const u64 u = mul_shoup(x, dc[i].c, P.q);
+            mac128(tl, th, u, dc[i].m_t);
+            mac128(gl, gh, u, dc[i].m_g);
+        }
+        u64 yt = csub(barrett128(tl, th, t, t_rlo, t_rhi), t), yg = csub(barrett128(gl, gh, gamma, g_rlo, g_rhi), gamma);
+        yt = mulmod_any(yt, neg_inv_q_t, t, t_rlo, t_rhi);
+        yg = mulmod_any(yg, neg_inv_q_g, gamma, g_rlo, g_rhi);
+        u64 r;
+        if (yg > (gamma >> 1))
+            r = csub(yt + csub(barrett128(gamma - yg, 0, t, t_rlo, t_rhi), t), t);
+        else
+        {
+            const u64 s = csub(barrett128(yg, 0, t, t_rlo, t_rhi), t);
+            r = csub(yt + t - s, t);
+        }
+        plain[e] = mulmod_any(r, inv_gamma_t, t, t_rlo, t_rhi);
+    }
+
+    // BGV: BaseConverter::exact_convert_array (rns.cpp:466-539) on phase = T (already INTT'd), then the inverse correction factor
+    __global__ void __launch_bounds__(128) bgv_modt_kernel(const u64 *__restrict__ T, u64 *__restrict__ plain, const DecConst *__restrict__ dc,
+                                                            const PrimeDev *__restrict__ primes, const u64 *__restrict__ fix, u64 t, u64 t_rlo,
+                                                            u64 t_rhi, u64 q_mod_t, int logn, int L, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over B*n
+        if (e >= total)
+            return;
+        const long long b = e >> logn;
+        const int idx = static_cast<int>(e & ((1 << logn) - 1));
+        double v = 0.0;
+        u64 lo = 0, hi = 0;
+        for (int i = 0; i < L; i++)
+        {
+            const PrimeDev P = primes[i];
+            const u64 x = mul_shoup(T[(((b * L) + i) << logn) + idx], dc[i].c, P.q);
+            v = __dadd_rn(v, __ddiv_rn(__ull2double_rn(x), __ull2double_rn(P.q))); // IEEE doubles in index order, as the reference sums them
+            mac128(lo, hi, x, dc[i].m_t);
+        }
+        const u64 rounded = __double2ull_rz(__dadd_rn(v, 0.5));
+        const u64 sum = csub(barrett128(lo, hi, t, t_rlo, t_rhi), t);
+        const u64 vq = mulmod_any(csub(barrett128(rounded, 0, t, t_rlo, t_rhi), t), q_mod_t, t, t_rlo, t_rhi);
+        u64 r = csub(sum + t - vq, t);
+        if (fix)
+            r = mulmod_any(r, fix[b], t, t_rlo, t_rhi);
+        plain[e] = r;
+    }
+
+    static u64 mulmod_host(u64 a, u64 b, u64 m) { return static_cast<u64>(static_cast<unsigned __int128>(a) * b % m); }
+    static const Context::DecryptLevel &decrypt_level(Context &c, size_t L)
+    {
+        plain_level(c, L); // t Barrett ratio, scheme check
+        auto it = c.decrypt_levels.find(L);
+        if (it != c.decrypt_levels.end())
+            return it->second;
+        if (L > 60)
+            throw std::invalid_argument("decryption supports at most 60 primes per level");
+        const bool bfv = c.scheme == 1;
+        const u64 t = c.t, gamma = bfv ? c.aux[1] : 1;
+        Context::DecryptLevel dl;
+        std::vector<DecConst> h(L);
+        u64 q_t = 1 % t, q_g = 1 % gamma;
+        for (size_t i = 0; i < L; i++)
+            q_t = mulmod_host(q_t, c.q[i] % t, t), q_g = mulmod_host(q_g, c.q[i] % gamma, gamma);
+        for (size_t i = 0; i < L; i++)
+        {
+            u64 punc_q = 1, punc_t = 1 % t, punc_g = 1 % gamma, inv = 0;
+            for (size_t j = 0; j < L; j++)
+                if (j != i)
+                {
+                    punc_q = mulmod_host(punc_q, c.q[j] % c.q[i], c.q[i]);
+                    punc_t = mulmod_host(punc_t, c.q[j] % t, t);
+                    punc_g = mulmod_host(punc_g, c.q[j] % gamma, gamma);
+                }
+            if (!sbh::invmod(punc_q, c.q[i], inv))
+                throw std::logic_error("invalid rns bases");
+            u64 cst = inv;
+            if (bfv)
+                cst = mulmod_host(mulmod_host(t % c.q[i], gamma % c.q[i], c.q[i]), inv, c.q[i]);
+            h[i] = DecConst{ Tw{ cst, sbh::shoup(cst, c.q[i]) }, punc_t, punc_g, 0 };
+        }
+        u64 inv_t = 0, inv_g = 0;
+        if (bfv)
+        {
+            if (!sbh::invmod(q_t, t, inv_t) || !sbh::invmod(q_g, gamma, inv_g))
+                throw std::logic_error("invalid rns bases");
+            dl.neg_inv_q_mod_t = inv_t ? t - inv_t : 0, dl.neg_inv_q_mod_g = inv_g ? gamma - inv_g : 0;
+        }
+        dl.q_mod_t = q_t;
+        cuda_check(cudaMalloc(&dl.d_consts, L * sizeof(DecConst)), "cudaMalloc(decrypt consts)");
+        cuda_check(cudaMemcpy(dl.d_consts, h.data(), L * sizeof(DecConst), cudaMemcpyHostToDevice), "upload decrypt consts");
+        return c.decrypt_levels.emplace(L, dl).first->second;
+    }
+
+    void op_decrypt(Context &c, SecretKey &sk, size_t L, size_t size, size_t batch, const u64 *ct, const u64 *h_cf, u64 *plain, cudaStream_t st)
+    {
+        if (sk.ctx != &c)
+            throw std::invalid_argument("secret key is not valid for encryption parameters");
+        if (size < 2 || size > 16)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        ensure_key_powers(c, sk, size - 1, st);
+        const int n = static_cast<int>(c.n), npow = static_cast<int>(size - 1);
+        const long long poly = static_cast<long long>(L) * n, ct_bs = static_cast<long long>(size) * poly, sk_ps = static_cast<long long>(c.k) * n;
+        if (c.scheme == 2)
+        {
+            // ckks_decrypt (decryptor.cpp:137-157): the phase in NTT form is the plaintext
+            const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (L * c.n));
+            for (size_t b0 = 0; b0 < batch; b0 += step)
+            {
+                const size_t B = std::min(step, batch - b0);
+                const long long total = static_cast<long long>(B) * poly;
+                const u64 *in = ct + b0 * ct_bs;
+                c.stats.begin("decrypt_phase", 0, 8.0 * total * (size + 1), st);
+                phase_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in + poly, ct_bs, in, ct_bs, sk.d_pow, sk_ps,
+                                                                                               plain + b0 * poly, c.d_primes, c.logn,
+                                                                                               static_cast<int>(L), npow, total);
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "phase_kernel");
+            }
+            return;
+        }
+        const Context::DecryptLevel &dl = decrypt_level(c, L);
+        const bool bfv = c.scheme == 1;
+        // scratch per ciphertext: T [L][n] (+ the transformed copy of c_1.. for BFV) (+ 1 word for the BGV factor)
+        const size_t per = (L * c.n * (bfv ? size : 1) + 1) * sizeof(u64);
+        size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (size * L * c.n)));
+        u64 gamma = 1, g_rlo = 0, g_rhi = 0, inv_gamma_t = 0;
+        if (bfv)
+        {
+            gamma = c.aux[1];
+            const unsigned __int128 ratio = ~static_cast<unsigned __int128>(0) / gamma;
+            g_rlo = static_cast<u64>(ratio), g_rhi = static_cast<u64>(ratio >> 64);
+            if (!sbh::invmod(gamma % c.t, c.t, inv_gamma_t))
+                throw std::logic_error("invalid rns bases");
+        }
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            const size_t B = std::min(chunk, batch - b0);
+            u64 *T = static_cast<u64 *>(c.ensure_scratch(per * B));
+            u64 *extra = T + B * L * c.n;
+            const u64 *in = ct + b0 * ct_bs;
+            const long long total = static_cast<long long>(B) * poly, tn = static_cast<long long>(B) * n;
+            if (bfv)
+            {
+                // coefficient-form ciphertext (decryptor.cpp:348-379): transform c_1.., accumulate, transform back, add c_0
+                u64 *X = extra; // [B][size-1][L][n]
+                cuda_check(cudaMemcpy2DAsync(X, (size - 1) * poly * sizeof(u64), in + poly, ct_bs * sizeof(u64), (size - 1) * poly * sizeof(u64), B,
+                                             cudaMemcpyDeviceToDevice, st),
+                           "copy");
+                op_ntt(c, false, L, size - 1, B, X, st);
+                c.stats.begin("decrypt_phase", 0, 8.0 * total * size, st);
+                phase_kernel<false><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(X, static_cast<long long>(size - 1) * poly, nullptr, 0,
+                                                                                                sk.d_pow, sk_ps, T, c.d_primes, c.logn,
+                                                                                                static_cast<int>(L), npow, total);
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "phase_kernel");
+                op_ntt(c, true, L, 1, B, T, st);
+                c.stats.begin("bfv_scale_round", 0, 8.0 * tn * (2 * L + 1), st);
+                bfv_scale_round_kernel<<<static_cast<unsigned>((tn + 127) / 128), 128, 0, st>>>(
+                    T, in, ct_bs, plain + b0 * c.n, static_cast<const DecConst *>(dl.d_consts), c.d_primes, c.t, c.t_ratio_lo, c.t_ratio_hi, gamma,
+                    g_rlo, g_rhi, dl.neg_inv_q_mod_t, dl.neg_inv_q_mod_g, inv_gamma_t, c.logn, static_cast<int>(L), tn);
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "bfv_scale_round_kernel");
+                continue;
+            }
+            // bgv_decrypt (decryptor.cpp:159-197)
+            const u64 *d_fix = nullptr;
+            std::vector<u64> fix;
+            if (h_cf)
+            {
+                fix.resize(B);
+                for (size_t i = 0; i < B; i++)
+                {
+                    fix[i] = 1;
+                    if (h_cf[b0 + i] != 1 && !sbh::invmod(h_cf[b0 + i] % c.t, c.t, fix[i]))
+                        throw std::logic_error("invalid correction factor");
+                }
+                cuda_check(cudaMemcpyAsync(extra, fix.data(), B * sizeof(u64), cudaMemcpyHostToDevice, st), "upload factors");
+                cuda_check(cudaStreamSynchronize(st), "synchronize"); // fix lives on this stack frame
+                d_fix = extra;
+            }
+            c.stats.begin("decrypt_phase", 0, 8.0 * total * (size + 1), st);
+            phase_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in + poly, ct_bs, in, ct_bs, sk.d_pow, sk_ps, T, c.d_primes,
+                                                                                           c.logn, static_cast<int>(L), npow, total);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "phase_kernel");
+            op_ntt(c, true, L, 1, B, T, st);
+            c.stats.begin("bgv_modt", 0, 8.0 * tn * (L + 1), st);
+            bgv_modt_kernel<<<static_cast<unsigned>((tn + 127) / 128), 128, 0, st>>>(T, plain + b0 * c.n, static_cast<const DecConst *>(dl.d_consts),
+                                                                                     c.d_primes, d_fix, c.t, c.t_ratio_lo, c.t_ratio_hi, dl.q_mod_t,
+                                                                                     c.logn, static_cast<int>(L), tn);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "bgv_modt_kernel");
         }
     }
 

@@ -21,6 +21,14 @@ namespace sb
     // device copy of sbh::BehzLevel (BFV multiply), see sb_bfv.cu
     struct BehzDev;
 
+    // the secret key on the device for decryption: powers s^1 .. s^powers in NTT form at the key level, [powers][k][n]
+    struct SecretKey
+    {
+        struct Context *ctx = nullptr;
+        u64 *d_pow = nullptr;
+        size_t powers = 0;
+    };
+
     struct KSwitchKey
     {
         struct Context *ctx = nullptr;
@@ -54,6 +62,13 @@ namespace sb
         Tw *d_qmod = nullptr;                // BGV, [k][k]: d_qmod[j*k+i] = q_j mod q_i
         u64 t_ratio = 0;                     // BGV: floor(2^64 / t)
         std::vector<u64> inv_q_mod_t;        // BGV: q_j^-1 mod t
+        // decryption constants per level (sb_engine.cu: decrypt_level): [L] x {Tw c, u64 m_t, u64 m_g}
+        struct DecryptLevel
+        {
+            void *d_consts = nullptr;
+            u64 neg_inv_q_mod_t = 0, neg_inv_q_mod_g = 0, q_mod_t = 0;
+        };
+        std::map<size_t, DecryptLevel> decrypt_levels;
         // BatchEncoder on the device (BFV / BGV with an NTT-friendly plain modulus): prime id of t and the inverse slot map
         int t_pid = -1;
         uint32_t *d_batch_inv_map = nullptr; // coefficient index -> matrix slot
@@ -96,6 +111,10 @@ namespace sb
     void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st);
     // coefficient-form plaintexts [B][n] (words < t): lift + NTT, multiply_plain, add_plain / sub_plain (BFV, BGV);
     // h_cf: per-ciphertext BGV correction factors on the host (nullptr = 1)
+    // Decryptor::decrypt (decryptor.cpp:62-197): ct [B][size][L][n] -> CKKS: NTT-form plaintexts [B][L][n]; BFV / BGV:
+    // coefficient-form plaintexts [B][n].  h_cf: BGV correction factors per ciphertext (nullptr = 1).
+    void secret_key_create(Context &c, const u64 *h_sk, SecretKey &out);
+    void op_decrypt(Context &c, SecretKey &sk, size_t L, size_t size, size_t batch, const u64 *ct, const u64 *h_cf, u64 *plain, cudaStream_t st);
     // BatchEncoder::encode / decode (batchencoder.cpp:84-330): values [B][n] (< t) <-> coefficient-form plaintexts [B][n]
     void op_batch_encode(Context &c, size_t batch, const u64 *values, u64 *plain, cudaStream_t st);
     void op_batch_decode(Context &c, size_t batch, const u64 *plain, u64 *values, cudaStream_t st);

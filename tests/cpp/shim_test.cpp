@@ -5,6 +5,7 @@
 // :4326 (CKKSEncryptRotateDecrypt), :5670 (BFVEncryptRotateMatrixDecrypt), :2505/:2532 (negative relinearize tests).
 // TEST INFRASTRUCTURE: links the reference; built only where /root/reference exists; the binary travels to the GPU box.
 #include "seal_b200/batchencoder.hpp"
+#include "seal_b200/decryptor.hpp"
 #include "seal_b200/evaluator.hpp"
 #include <complex>
 #include <cstdio>
@@ -36,6 +37,13 @@ static bool same_ct(const Ciphertext &a, const Ciphertext &b)
     if (std::memcmp(&sa, &sb, sizeof(double)) != 0 || a.correction_factor() != b.correction_factor())
         return false;
     return std::memcmp(a.data(), b.data(), a.size() * a.coeff_modulus_size() * a.poly_modulus_degree() * 8) == 0;
+}
+
+static bool same_plain(const Plaintext &a, const Plaintext &b)
+{
+    double sa = a.scale(), sb = b.scale();
+    return a.parms_id() == b.parms_id() && a.coeff_count() == b.coeff_count() && std::memcmp(&sa, &sb, sizeof(double)) == 0 &&
+           std::memcmp(a.data(), b.data(), a.coeff_count() * 8) == 0;
 }
 
 // runs f on both evaluators; returns a tag describing the exception type (or "ok")
@@ -117,6 +125,19 @@ static void test_ckks()
         for (size_t i = 0; i < slots; i++)
             err = std::max(err, std::abs(got[i] - x[i] * y[i]));
         CHECK(err < 1e-3);
+    }
+    {
+        // Decryptor::decrypt on the device (CKKS: the NTT-form phase is the plaintext), sizes 2 and 3
+        seal_b200::Decryptor gdec(context, keygen.secret_key(), gpu);
+        Plaintext rp, gp;
+        decryptor.decrypt(g1, rp);
+        gdec.decrypt(g1, gp);
+        CHECK(same_plain(rp, gp));
+        Ciphertext c3;
+        ref.multiply(cx, cy, c3);
+        decryptor.decrypt(c3, rp);
+        gdec.decrypt(c3, gp);
+        CHECK(same_plain(rp, gp));
     }
     {
         // square / add / sub / negate
@@ -446,6 +467,22 @@ static void test_bfv()
         CHECK(a == b && a == "invalid_argument"); // BFV plain cannot be in NTT form
     }
     {
+        // Decryptor::decrypt on the device (BFV: phase + decrypt_scale_and_round), sizes 2 and 3
+        seal_b200::Decryptor gdec(context, keygen.secret_key(), gpu);
+        Plaintext rp, gp;
+        decryptor.decrypt(cx, rp);
+        gdec.decrypt(cx, gp);
+        CHECK(same_plain(rp, gp));
+        Ciphertext c3;
+        ref.multiply(cx, cy, c3);
+        decryptor.decrypt(c3, rp);
+        gdec.decrypt(c3, gp);
+        CHECK(same_plain(rp, gp));
+        auto a = outcome([&] { Ciphertext tt = cx; tt.is_ntt_form() = true; Plaintext p; decryptor.decrypt(tt, p); });
+        auto b = outcome([&] { Ciphertext tt = cx; tt.is_ntt_form() = true; Plaintext p; gdec.decrypt(tt, p); });
+        CHECK(a == b && a == "invalid_argument");
+    }
+    {
         // BatchEncoder on the device: encode / decode, unsigned and signed, short inputs
         seal_b200::BatchEncoder genc(context, gpu);
         CHECK(genc.slot_count() == encoder.slot_count());
@@ -582,6 +619,17 @@ static void test_bgv()
     gpu.mod_switch_to_next_inplace(g1);
     CHECK(same_ct(r1, g1));
     CHECK(g1.correction_factor() != 1); // q_last^-1 mod t entered the metadata (evaluator.cpp:1288-1293)
+    {
+        // Decryptor::decrypt on the device (BGV: phase, INTT, exact base conversion, inverse correction factor)
+        seal_b200::Decryptor gdec(context, keygen.secret_key(), gpu);
+        Plaintext rp, gp;
+        decryptor.decrypt(g1, rp);
+        gdec.decrypt(g1, gp);
+        CHECK(same_plain(rp, gp));
+        decryptor.decrypt(cx, rp);
+        gdec.decrypt(cx, gp);
+        CHECK(same_plain(rp, gp));
+    }
     {
         Plaintext p;
         decryptor.decrypt(g1, p);

@@ -168,6 +168,24 @@ class Oracle:
         lib().orc_multiply_plain_ntt(self.h, L, a.shape[0], _p(a), _p(plain), _p(out))
         return out
 
+    def decrypt(self, L, ct, sk, correction_factor=1):
+        """Decryptor::decrypt with the secret key sk [k][n] (NTT form): n words (BFV / BGV) or [L][n] (CKKS)"""
+        ct, sk = np.ascontiguousarray(ct), np.ascontiguousarray(sk)
+        size = ct.shape[0]
+        if self.scheme == CKKS:
+            lib().orc_decrypt_phase.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, _u64p, _u64p, _u64p]
+            out = np.zeros((L, self.n), dtype=np.uint64)
+            lib().orc_decrypt_phase(self.h, L, size, 1, _p(ct), _p(sk), _p(out))
+            return out
+        out = np.zeros(self.n, dtype=np.uint64)
+        if self.scheme == BFV:
+            lib().orc_bfv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]
+            assert lib().orc_bfv_decrypt(self.h, L, size, _p(ct), _p(sk), _p(out)) == 0
+        else:
+            lib().orc_bgv_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint64, _u64p, _u64p, _u64p]
+            assert lib().orc_bgv_decrypt(self.h, L, size, correction_factor, _p(ct), _p(sk), _p(out)) == 0
+        return out
+
     def batch_codec(self, data, decode):
         lib().orc_batch_codec.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
         data = np.ascontiguousarray(data, dtype=np.uint64)

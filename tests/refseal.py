@@ -59,6 +59,8 @@ def lib():
         L.sealref_time_op.restype = C.c_double
         L.sealref_time_op.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int]
         L.sealref_batch_codec.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p]
+        L.sealref_secret_key.argtypes = [C.c_void_p, _u64p]
+        L.sealref_decrypt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, _u64p, _u64p]
         L.sealref_plain_to_ntt.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.sealref_plain_op_coeff.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, _u64p, _u64p, _u64p]
         L.sealref_parms_id.argtypes = [C.c_void_p, C.c_size_t, _u64p]
@@ -237,6 +239,18 @@ class RefContext:
         nb = C.c_int(0)
         self._chk(lib().sealref_bfv_decrypt(self.h, L, ct.shape[0], _p(ct), _p(out), C.byref(nb)))
         return out, nb.value
+
+    def secret_key(self):
+        out = np.zeros((self.k, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_secret_key(self.h, _p(out)))
+        return out
+
+    def decrypt(self, L, ct, is_ntt_form, correction_factor=1):
+        """Decryptor::decrypt -> n words (BFV / BGV) or [L][n] (CKKS)"""
+        ct = np.ascontiguousarray(ct)
+        out = np.zeros((L, self.n) if self.scheme == CKKS else self.n, dtype=np.uint64)
+        self._chk(lib().sealref_decrypt(self.h, L, ct.shape[0], int(is_ntt_form), correction_factor, _p(ct), _p(out)))
+        return out
 
     def batch_codec(self, data, decode):
         data = np.ascontiguousarray(data, dtype=np.uint64)

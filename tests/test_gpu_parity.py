@@ -480,6 +480,33 @@ def test_batch_codec_vs_reference(n, t_bits):
         ctx2.batch_encode(v % (1 << 20))
 
 
+@needs_ref
+@pytest.mark.parametrize("scheme,n", [("ckks", 4096), ("bfv", 4096), ("bgv", 4096), ("bfv", 256), ("bgv", 256)])
+def test_decrypt_vs_reference(scheme, n):
+    # Decryptor::decrypt (decryptor.cpp:62-197) -- phase, then scale-and-round (BFV), exact base
+    # conversion in IEEE doubles (BGV) or nothing (CKKS); uniform-random ciphertexts reach every branch
+    batch = 3
+    mods = R.coeff_modulus_create(n, [50, 45, 60, 55])
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 20)
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    sk = ctx.load_secret_key(rc.secret_key())
+    rng = np.random.default_rng(73)
+    ntt = scheme != "bfv"
+    for L, size in ((3, 2), (2, 3), (1, 2), (3, 4)):
+        ct = rand_ct(rng, mods, n, size, L, batch)
+        cf = np.array([1, 12345, t - 1], dtype=np.uint64) if scheme == "bgv" else None
+        got = ctx.decrypt(ct, sk, cf)
+        for i in range(batch):
+            f = 1 if cf is None else int(cf[i])
+            assert (got[i] == rc.decrypt(L, ct[i], ntt, f)).all()
+    if scheme == "bfv":  # a real encryption comes back: decrypt + decode on the device
+        slots = rng.integers(0, t, n, dtype=np.uint64)
+        p = ctx.decrypt(rc.bfv_encrypt(slots), sk)
+        assert (ctx.batch_decode(p) == slots).all()
+
+
 def test_c_abi_pointer_and_argument_errors():
     # the reference's C layer rejects null handles with E_POINTER (native/tests/seal/cabi.cpp:339-425); same here
     import ctypes as C

@@ -246,3 +246,28 @@ def test_oracle_batch_codec_vs_live_reference(scheme):
     assert (rc.batch_codec(p, True) == v).all() and (oc.batch_codec(p, True) == v).all()
     w = rng.integers(0, t, n, dtype=np.uint64)  # any coefficient vector decodes
     assert (rc.batch_codec(w, True) == oc.batch_codec(w, True)).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme", ["ckks", "bfv", "bgv"])
+def test_oracle_decrypt_vs_live_reference(scheme):
+    # Decryptor::decrypt (decryptor.cpp): phase, then scale-and-round (BFV), exact base conversion (BGV) or nothing (CKKS);
+    # uniform-random "ciphertexts" exercise every branch of the arithmetic
+    n = 256
+    mods = R.coeff_modulus_create(n, [40, 41, 42, 43])
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    t = 0 if scheme == "ckks" else R.plain_modulus_batching(n, 17)
+    rc, oc = R.RefContext(sid, n, mods, t), O.Oracle(sid, n, mods, t)
+    sk = rc.secret_key()
+    rng = np.random.default_rng(71)
+    ntt = scheme != "bfv"
+    for L, size in ((3, 2), (3, 3), (1, 2), (2, 4)):
+        ct = rand_ct(rng, mods, n, size, L)
+        cf = 1 if scheme != "bgv" else (12345 if size == 3 else 1)
+        assert (rc.decrypt(L, ct, ntt, cf) == oc.decrypt(L, ct, sk, cf)).all()
+    if scheme == "bfv":  # and a real encryption: decrypt(encrypt(m)) = m through both
+        slots = rng.integers(0, t, n, dtype=np.uint64)
+        ct = rc.bfv_encrypt(slots)
+        p = oc.decrypt(3, ct, sk)
+        assert (p == rc.decrypt(3, ct, False)).all()
+        assert (oc.batch_codec(p, True) == slots).all()
