@@ -1,8 +1,9 @@
 """seal_b200 -- Python (ctypes) binding of libseal_b200.so, the B200 (sm_100a) drop-in for the RNS-polynomial hot
-path of microsoft/SEAL (NTT/INTT, CKKS/BFV multiply, relinearize, rotate, rescale).
+path of microsoft/SEAL (NTT/INTT, CKKS/BFV/BGV multiply, relinearize, rotate, rescale) and the operations around it
+(plaintext operations, wire format, BatchEncoder, Decryptor -- SURVEY 8f).
 
-The product is the C-ABI library (include/seal_b200.h) and, for C++ users, the header-only Evaluator shim
-(include/seal_b200/evaluator.hpp).  This module exists for tests and bench.py: it mirrors the reference's operator
+The product is the C-ABI library (include/seal_b200.h) and, for C++ users, the header-only shims
+(include/seal_b200/{evaluator,batchencoder,decryptor}.hpp).  This module exists for tests and bench.py: it mirrors the reference's operator
 names (Evaluator.multiply / relinearize / rescale_to_next / rotate_rows / apply_galois / transform_to_ntt ...)
 on raw uint64 slabs laid out like seal::Ciphertext::data().  There is no CPU fallback: importing works anywhere, but
 creating a Context raises unless the CUDA library is built and a B200 is present.
