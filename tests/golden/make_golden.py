@@ -20,7 +20,7 @@ def rnd(rng, mods, n, size, L):
 def make(name, scheme, n, bits, t_bits, seed):
     rng = np.random.default_rng(seed)
     mods = R.coeff_modulus_create(n, bits)
-    t = R.plain_modulus_batching(n, t_bits) if scheme == R.BFV else 0
+    t = R.plain_modulus_batching(n, t_bits) if scheme != R.CKKS else 0
     rc = R.RefContext(scheme, n, mods, t, seed=0x5EA1)
     k = len(mods)
     out = dict(scheme=scheme, n=n, moduli=np.array(mods, dtype=np.uint64), t=np.uint64(t))
@@ -52,3 +52,4 @@ if __name__ == "__main__":
     make("ckks_n128", R.CKKS, 128, [40, 30, 35, 41], 0, 11)
     make("bfv_n128", R.BFV, 128, [36, 36, 37], 17, 12)
     make("ckks_n1024", R.CKKS, 1024, [50, 50, 50], 0, 13)
+    make("bgv_n128", R.BGV, 128, [36, 36, 37, 38], 17, 14)

@@ -63,7 +63,7 @@ def test_default_moduli_known_values():
     assert all(O.lib().orc_is_prime(p) and p % 8192 == 1 for p in (0xFFFFEE001, 0xFFFFC4001, 0x1FFFFE0001))
 
 
-@pytest.mark.parametrize("name", ["ckks_n128", "bfv_n128", "ckks_n1024"])
+@pytest.mark.parametrize("name", ["ckks_n128", "bfv_n128", "ckks_n1024", "bgv_n128"])
 def test_oracle_vs_golden(name):
     g = golden(name)
     scheme, n, mods, t = int(g["scheme"]), int(g["n"]), [int(x) for x in g["moduli"]], int(g["t"])
@@ -80,7 +80,7 @@ def test_oracle_vs_golden(name):
         assert (m == g[f"L{L}_mul"]).all()
         assert (oc.relinearize(L, m, key) == g[f"L{L}_relin"]).all()
         if L > 1:
-            ms = oc.rescale(L, a) if scheme == O.CKKS else oc.bfv_mod_switch(L, a)
+            ms = oc.rescale(L, a) if scheme == O.CKKS else (oc.bfv_mod_switch(L, a) if scheme == O.BFV else oc.bgv_mod_switch(L, a))
             assert (ms == g[f"L{L}_modswitch_a"]).all()
         for e in g["galois_elts"]:
             e = int(e)
