@@ -66,6 +66,41 @@ uint32_t sb200_galois_elt_from_step(const sb200_context *ctx, int step);
 unsigned long long sb200_launch_count(const sb200_context *ctx);
 /* device bytes currently held by the context (tables + scratch) */
 size_t sb200_device_bytes(const sb200_context *ctx);
+/* resource limits of a context (the reference's counterpart is the MemoryPoolHandle a caller passes to Evaluator members,
+ * evaluator.h:219-252): how a batch is cut into device chunks.  Results never depend on them; the parity tests use them
+ * to force the multi-chunk paths (ragged last chunk) at small batch sizes.
+ *   SB200_LIMIT_SCRATCH_BYTES     budget of the per-context scratch arena (default 8 GiB, env SB200_SCRATCH_MB)
+ *   SB200_LIMIT_KS_CHUNK          max ciphertexts per key-switching chunk (0 = derived from the scratch budget)
+ *   SB200_LIMIT_HOST_STAGE_BYTES  device staging per pipeline slot of the *_host entry points (default 640 MiB) */
+#define SB200_LIMIT_SCRATCH_BYTES 0
+#define SB200_LIMIT_KS_CHUNK 1
+#define SB200_LIMIT_HOST_STAGE_BYTES 2
+int sb200_context_set_limit(sb200_context *ctx, int which, size_t value);
+
+/* ---- device-resident slabs (the storage behind seal_b200::CiphertextBatch, include/seal_b200/batch.hpp) ------------
+ * The reference hands out ciphertext storage from a MemoryPoolHandle (memorymanager.h:36-54, ciphertext.h:100-140); a
+ * caller that keeps ciphertexts on the device between Evaluator calls allocates their slabs here.  Slabs belong to the
+ * context's device; sb200_host_malloc returns page-locked host memory (first-touched by the calling thread, so bind the
+ * thread to the device's NUMA node first) for staging that the *_host entry points and the copies below can stream
+ * from at full PCIe rate.  Copies are stream-ordered; sb200_stream_synchronize(ctx, stream) waits for them. */
+int sb200_device_malloc(sb200_context *ctx, size_t bytes, uint64_t **d_out);
+int sb200_device_free(sb200_context *ctx, uint64_t *d_ptr);
+int sb200_host_malloc(sb200_context *ctx, size_t bytes, void **h_out);
+int sb200_host_free(sb200_context *ctx, void *h_ptr);
+int sb200_memcpy_h2d(sb200_context *ctx, uint64_t *d_dst, const void *h_src, size_t bytes, void *stream);
+int sb200_memcpy_d2h(sb200_context *ctx, void *h_dst, const uint64_t *d_src, size_t bytes, void *stream);
+int sb200_memcpy_d2d(sb200_context *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t bytes, void *stream);
+/* strided copies between ciphertext objects and slabs: `rows` runs of row_bytes, source / destination pitch in bytes
+ * (drops or keeps RNS components without touching the rest: mod_switch_drop_to_next, evaluator.cpp:1296-1358) */
+int sb200_memcpy_d2d_2d(sb200_context *ctx, uint64_t *d_dst, size_t dst_pitch, const uint64_t *d_src, size_t src_pitch, size_t row_bytes,
+                        size_t rows, void *stream);
+int sb200_stream_synchronize(sb200_context *ctx, void *stream);
+/* NUMA node of the context's device (-1 when the platform does not say) and the CUDA device index */
+int sb200_device_numa_node(const sb200_context *ctx);
+int sb200_device_index(const sb200_context *ctx);
+/* ciphertexts per key-switching chunk the context would use for `batch` ciphertexts at level L (fused != 0: the
+ * multiply_relinearize entry point).  bench.py samples its verification indices on both sides of a chunk boundary. */
+size_t sb200_keyswitch_chunk(const sb200_context *ctx, size_t L, size_t batch, int fused);
 
 /* ---- per-kernel timing (CUDA events on the launching stream) -------------------------------------------------
  * enable, run operations, then read entries 0,1,... until SB200_E_OUT_OF_RANGE.  Each entry aggregates one kernel

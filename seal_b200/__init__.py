@@ -25,7 +25,7 @@ _STATUS = {-1: ValueError, -2: RuntimeError, -3: IndexError, -4: RuntimeError, -
 SYMBOLS = [
     "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
-    "sb200_device_bytes", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
+    "sb200_device_bytes", "sb200_context_set_limit", "sb200_device_malloc", "sb200_device_free", "sb200_host_malloc", "sb200_host_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d", "sb200_memcpy_d2d_2d", "sb200_stream_synchronize", "sb200_device_numa_node", "sb200_device_index", "sb200_keyswitch_chunk", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
     "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
     "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_batch_encode", "sb200_batch_decode", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
@@ -67,6 +67,11 @@ def lib():
         L.sb200_launch_count.argtypes = [vp]
         L.sb200_device_bytes.restype = sz
         L.sb200_device_bytes.argtypes = [vp]
+        L.sb200_context_set_limit.argtypes = [vp, i32, sz]
+        L.sb200_keyswitch_chunk.restype = sz
+        L.sb200_keyswitch_chunk.argtypes = [vp, sz, sz, i32]
+        L.sb200_device_numa_node.argtypes = [vp]
+        L.sb200_device_index.argtypes = [vp]
         L.sb200_profile_enable.argtypes = [vp, i32]
         L.sb200_profile_reset.argtypes = [vp]
         L.sb200_profile_read.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
@@ -256,6 +261,15 @@ class Context:
     @property
     def device_bytes(self):
         return int(lib().sb200_device_bytes(self.h))
+
+    LIMIT_SCRATCH_BYTES, LIMIT_KS_CHUNK, LIMIT_HOST_STAGE_BYTES = 0, 1, 2
+
+    def set_limit(self, which, value):
+        """sb200_context_set_limit: how a batch is cut into device chunks (results never depend on it)"""
+        _check(lib().sb200_context_set_limit(self.h, which, value))
+
+    def keyswitch_chunk(self, L, batch, fused=True):
+        return int(lib().sb200_keyswitch_chunk(self.h, L, batch, 1 if fused else 0))
 
     def profile(self, on=True):
         _check(lib().sb200_profile_enable(self.h, 1 if on else 0))

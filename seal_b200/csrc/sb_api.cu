@@ -4,6 +4,7 @@
 #include "../../include/seal_b200.h"
 #include "sb_engine.cuh"
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -19,7 +20,18 @@ struct sb200_context
 struct sb200_secret_key
 {
     SecretKey k;
-    ~sb200_secret_key() { cudaFree(k.d_pow); }
+    // the reference keeps SecretKey data in a clear-on-destruction pool (secretkey.h:51-60): wipe before the memory goes back
+    // to the allocator
+    ~sb200_secret_key()
+    {
+        if (k.d_pow && k.ctx)
+        {
+            cudaSetDevice(k.ctx->device);
+            cudaMemset(k.d_pow, 0, k.powers * k.ctx->k * k.ctx->n * sizeof(u64));
+            cudaDeviceSynchronize();
+        }
+        cudaFree(k.d_pow);
+    }
 };
 struct sb200_kswitch_key
 {
@@ -177,6 +189,151 @@ size_t sb200_device_bytes(const sb200_context *ctx)
     return ctx ? ctx->c->table_bytes + ctx->c->scratch_bytes + ctx->c->aux_bytes : 0;
 }
 
+int sb200_context_set_limit(sb200_context *ctx, int which, size_t value)
+{
+    SB_NEED(ctx);
+    SB_TRY
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    switch (which)
+    {
+    case SB200_LIMIT_SCRATCH_BYTES: c.scratch_budget = std::max<size_t>(value, size_t(1) << 20); break;
+    case SB200_LIMIT_KS_CHUNK: c.ks_chunk_max = value; break;
+    case SB200_LIMIT_HOST_STAGE_BYTES: c.host_stage_bytes = std::max<size_t>(value, size_t(1) << 16); break;
+    default: throw std::invalid_argument("unknown limit");
+    }
+    return SB200_OK;
+    SB_CATCH
+}
+
+// ---- device-resident slabs / staging memory ----
+int sb200_device_malloc(sb200_context *ctx, size_t bytes, uint64_t **d_out)
+{
+    SB_NEED(ctx);
+    SB_NEED(d_out);
+    SB_TRY
+    Context &c = *ctx->c;
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 8));
+    if (e == cudaErrorMemoryAllocation)
+    {
+        cudaGetLastError();
+        throw std::bad_alloc();
+    }
+    cuda_check(e, "cudaMalloc(slab)");
+    *d_out = static_cast<uint64_t *>(p);
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_device_free(sb200_context *ctx, uint64_t *d_ptr)
+{
+    SB_NEED(ctx);
+    SB_TRY
+    cuda_check(cudaSetDevice(ctx->c->device), "cudaSetDevice");
+    cuda_check(cudaFree(d_ptr), "cudaFree(slab)");
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_host_malloc(sb200_context *ctx, size_t bytes, void **h_out)
+{
+    SB_NEED(ctx);
+    SB_NEED(h_out);
+    SB_TRY
+    cuda_check(cudaSetDevice(ctx->c->device), "cudaSetDevice");
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, std::max<size_t>(bytes, 8), cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation)
+    {
+        cudaGetLastError();
+        throw std::bad_alloc();
+    }
+    cuda_check(e, "cudaHostAlloc");
+    *h_out = p;
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_host_free(sb200_context *ctx, void *h_ptr)
+{
+    SB_NEED(ctx);
+    SB_TRY
+    cuda_check(cudaFreeHost(h_ptr), "cudaFreeHost");
+    return SB200_OK;
+    SB_CATCH
+}
+static int copy_(sb200_context *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, void *stream)
+{
+    SB_NEED(ctx);
+    SB_NEED(dst);
+    SB_NEED(src);
+    SB_TRY
+    cuda_check(cudaSetDevice(ctx->c->device), "cudaSetDevice");
+    cuda_check(cudaMemcpyAsync(dst, src, bytes, kind, static_cast<cudaStream_t>(stream)), "cudaMemcpyAsync");
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_memcpy_h2d(sb200_context *ctx, uint64_t *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    return copy_(ctx, d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
+}
+int sb200_memcpy_d2h(sb200_context *ctx, void *h_dst, const uint64_t *d_src, size_t bytes, void *stream)
+{
+    return copy_(ctx, h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
+}
+int sb200_memcpy_d2d(sb200_context *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t bytes, void *stream)
+{
+    return copy_(ctx, d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, stream);
+}
+int sb200_memcpy_d2d_2d(sb200_context *ctx, uint64_t *d_dst, size_t dst_pitch, const uint64_t *d_src, size_t src_pitch, size_t row_bytes,
+                        size_t rows, void *stream)
+{
+    SB_NEED(ctx);
+    SB_NEED(d_dst);
+    SB_NEED(d_src);
+    SB_TRY
+    cuda_check(cudaSetDevice(ctx->c->device), "cudaSetDevice");
+    cuda_check(cudaMemcpy2DAsync(d_dst, dst_pitch, d_src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)),
+               "cudaMemcpy2DAsync");
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_stream_synchronize(sb200_context *ctx, void *stream)
+{
+    SB_NEED(ctx);
+    SB_TRY
+    cuda_check(cudaSetDevice(ctx->c->device), "cudaSetDevice");
+    cuda_check(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_device_index(const sb200_context *ctx)
+{
+    return ctx ? ctx->c->device : -1;
+}
+int sb200_device_numa_node(const sb200_context *ctx)
+{
+    if (!ctx)
+        return -1;
+    char bus[32] = { 0 };
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->c->device) != cudaSuccess)
+        return -1;
+    for (char *p = bus; *p; p++)
+        *p = static_cast<char>(std::tolower(*p));
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    int node = -1;
+    if (FILE *f = std::fopen(path.c_str(), "r"))
+    {
+        if (std::fscanf(f, "%d", &node) != 1)
+            node = -1;
+        std::fclose(f);
+    }
+    return node;
+}
+size_t sb200_keyswitch_chunk(const sb200_context *ctx, size_t L, size_t batch, int fused)
+{
+    return ctx ? sb::keyswitch_chunk(*ctx->c, L, batch, fused != 0) : 0;
+}
+
 int sb200_profile_enable(sb200_context *ctx, int on)
 {
     SB_NEED(ctx);
@@ -253,11 +410,16 @@ int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t d
         throw std::invalid_argument("kswitch key has an invalid number of digits");
     auto h = std::make_unique<sb200_kswitch_key>();
     size_t bytes = digits * 2 * c.k * c.n * sizeof(u64);
+    std::lock_guard<std::mutex> lock(c.mu);
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
     cuda_check(cudaMalloc(reinterpret_cast<void **>(&h->k.d_key), bytes), "cudaMalloc(key)");
     cuda_check(cudaMemcpy(h->k.d_key, h_key, bytes, cudaMemcpyHostToDevice), "upload key");
     h->k.ctx = &c;
     h->k.digits = digits;
+    // is_data_valid_for (valcheck.cpp:412-456): every word below its modulus -- the fused key-switch kernel relies on it to
+    // keep its 128-bit sums in range
+    if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr))
+        throw std::invalid_argument("kswitch key data is not valid for encryption parameters");
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -278,16 +440,20 @@ int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len
     if (e.n != c.n || e.L != c.k || std::memcmp(e.parms_id, c.parms_ids[c.k - 1].data(), sizeof(e.parms_id)) != 0)
         throw std::logic_error("KSwitchKeys data is invalid");
     const size_t digits = e.offsets.size();
-    if (digits > c.k - 1)
+    // is_valid_for(KSwitchKeys) (valcheck.cpp:292-323): one public key per decomposition prime, i.e. exactly k-1 digits
+    if (digits != c.k - 1)
         throw std::logic_error("KSwitchKeys data is invalid");
     auto h = std::make_unique<sb200_kswitch_key>();
     const size_t row = 2 * c.k * c.n * sizeof(u64);
+    std::lock_guard<std::mutex> lock(c.mu);
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
     cuda_check(cudaMalloc(reinterpret_cast<void **>(&h->k.d_key), digits * row), "cudaMalloc(key)");
     for (size_t j = 0; j < digits; j++)
         cuda_check(cudaMemcpy(reinterpret_cast<uint8_t *>(h->k.d_key) + j * row, stream + e.offsets[j], row, cudaMemcpyHostToDevice), "upload key");
     h->k.ctx = &c;
     h->k.digits = digits;
+    if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr)) // KSwitchKeys::load ends in is_valid_for (kswitchkeys.cpp:149-153)
+        throw std::logic_error("KSwitchKeys data is invalid");
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -632,7 +798,7 @@ namespace
         {
             StreamOrder order(c, s_comp); // the operation's kernels (and the scratch arenas they use) run on s_comp
             const size_t per_ct = (wa + wb + wo) * sizeof(u64);
-            size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, (size_t(640) << 20) / std::max<size_t>(per_ct, 1)));
+            size_t chunk = std::max<size_t>(1, std::min<size_t>(batch, c.host_stage_bytes / std::max<size_t>(per_ct, 1)));
             if (chunk >= batch && batch >= 4)
                 chunk = (batch + 1) / 2; // at least two chunks so the copies overlap the kernels
             // size all staging (and let the op grow its scratch) before the pipeline starts: growth synchronises the device

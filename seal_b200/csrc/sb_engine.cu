@@ -45,6 +45,7 @@ namespace sb
             cudaFree(kv.second.d_delta);
         cudaFree(scratch);
         cudaFree(aux_buf);
+        cudaFree(d_flag);
         if (order_event)
             cudaEventDestroy(order_event);
         for (auto &slot : io.buf)
@@ -919,6 +920,8 @@ namespace sb
         cuda_check(cudaDeviceSynchronize(), "sync before key array growth");
         cuda_check(cudaMalloc(reinterpret_cast<void **>(&grown), powers * row * sizeof(u64)), "cudaMalloc(secret key array)");
         cuda_check(cudaMemcpy(grown, sk.d_pow, sk.powers * row * sizeof(u64), cudaMemcpyDeviceToDevice), "copy");
+        cuda_check(cudaMemset(sk.d_pow, 0, sk.powers * row * sizeof(u64)), "wipe"); // secret material never goes back to the allocator in clear
+        cuda_check(cudaDeviceSynchronize(), "sync after wipe");
         cudaFree(sk.d_pow);
         sk.d_pow = grown;
         for (size_t p = sk.powers; p < powers; p++)
@@ -1705,7 +1708,16 @@ namespace sb
         chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 30) / ((L + 1) * L * c.n)));
         chunk = std::min<size_t>(chunk, 32768);
         chunk = std::min<size_t>(chunk, 65535 / (L + 1)); // (b, I) pairs ride in gridDim.y of the key-switch kernels
+        if (c.ks_chunk_max)
+            chunk = std::min(chunk, c.ks_chunk_max);
         return std::min(chunk, batch);
+    }
+
+    size_t keyswitch_chunk(const Context &c, size_t L, size_t batch, bool fused)
+    {
+        if (c.scheme == 1)
+            fused = false; // BFV multiply_relinearize = BEHZ multiply + relinearize
+        return ks_chunk(c, L, batch, fused);
     }
 
     static void check_ks_args(const Context &c, size_t L, const KSwitchKey &key)
@@ -1930,7 +1942,9 @@ namespace sb
     }
     bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st)
     {
-        int *flag = static_cast<int *>(c.ensure_aux(sizeof(int)));
+        if (!c.d_flag)
+            cuda_check(cudaMalloc(reinterpret_cast<void **>(&c.d_flag), sizeof(int)), "cudaMalloc(flag)");
+        int *flag = c.d_flag; // a word of its own: the aux arena may be in use by an operation in flight on another stream
         cuda_check(cudaMemsetAsync(flag, 0, sizeof(int), st), "memset");
         const size_t step = std::max<size_t>(1, (size_t(1) << 31) / c.n);
         for (size_t r0 = 0; r0 < rows; r0 += step * L)

@@ -85,9 +85,12 @@ namespace sb
         std::map<uint32_t, uint32_t *> galois_tables; // NTT-form permutation tables (device)
         std::map<size_t, std::shared_ptr<BehzDev>> behz; // per level L
         void *scratch = nullptr;
+        int *d_flag = nullptr;               // result word of the range check (op_residues_in_range)
         void *aux_buf = nullptr;             // second grow-only arena (size-3 intermediate of BFV multiply+relinearize)
         size_t aux_bytes = 0;
         size_t scratch_bytes = 0, table_bytes = 0, scratch_budget = size_t(8) << 30;
+        size_t ks_chunk_max = 0;                       // 0 = derived from scratch_budget (sb200_context_set_limit)
+        size_t host_stage_bytes = size_t(640) << 20;   // per pipeline slot of the *_host entry points
         LaunchStats stats;
         IoArena io;
         std::mutex mu;
@@ -138,6 +141,7 @@ namespace sb
     void op_mod_switch(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st);
     void op_apply_galois(Context &c, size_t L, size_t batch, const u64 *in2, uint32_t elt, const KSwitchKey &key, u64 *out2,
                          cudaStream_t st);
+    size_t keyswitch_chunk(const Context &c, size_t L, size_t batch, bool fused);
     const sbh::BehzLevel &behz_host(Context &c, size_t L);
     // wire format support (sb_api.cu): 1 if any residue of data [rows][n] (prime of a row = row % L) is >= its modulus
     bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st);

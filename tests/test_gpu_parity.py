@@ -206,6 +206,10 @@ def test_error_codes():
         ctx.relinearize(a, key)
     with pytest.raises(ValueError):  # rescale at the last level: evaluator.cpp:1521
         ctx.rescale_to_next(np.zeros((1, 2, 1, n), dtype=np.uint64))
+    bad = np.zeros((2, 2, 3, n), dtype=np.uint64)
+    bad[1, 1, 2, 5] = mods[2]  # one residue == its modulus: is_data_valid_for fails (valcheck.cpp:412-456)
+    with pytest.raises(ValueError):
+        ctx.load_key(bad)
 
 
 @needs_ref
@@ -410,6 +414,16 @@ def test_wire_format_vs_reference(scheme):
         ctx.load_key_stream(rc.kswitch_keys_stream(e), 0)  # empty slot
     with pytest.raises(IndexError):
         ctx.load_key_stream(rc.kswitch_keys_stream(0), 5)
+    # KSwitchKeys::load ends in is_valid_for (kswitchkeys.cpp:149-153): one word >= its modulus makes the stream invalid
+    ks = bytearray(rc.kswitch_keys_stream(0))
+    words = np.frombuffer(bytes(ks), dtype=np.uint8)
+    kdata = rc.relin_key()
+    needle = kdata[0, 1, 0, :4].tobytes()  # the first words of digit 0, component 1, prime 0
+    pos = bytes(ks).find(needle)
+    assert pos > 0
+    ks[pos:pos + 8] = int(mods[0]).to_bytes(8, "little")
+    with pytest.raises(RuntimeError):
+        ctx.load_key_stream(bytes(ks), 0)
     # Ciphertext::load rejects residues >= q_i (is_data_valid_for); unsafe_load does not look
     bad = bytearray(streams[0])
     off = infos[0].data_offset
