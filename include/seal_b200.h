@@ -95,6 +95,11 @@ int sb200_memcpy_d2d(sb200_context *ctx, uint64_t *d_dst, const uint64_t *d_src,
 int sb200_memcpy_d2d_2d(sb200_context *ctx, uint64_t *d_dst, size_t dst_pitch, const uint64_t *d_src, size_t src_pitch, size_t row_bytes,
                         size_t rows, void *stream);
 int sb200_stream_synchronize(sb200_context *ctx, void *stream);
+/* gather / scatter between `count` separate host objects (e.g. seal::Ciphertext::data() of a std::vector<Ciphertext>, pageable
+ * pool memory) and one device slab [count][row_bytes]: staged through page-locked double buffers owned by the context, several
+ * host threads copy, H2D / D2H overlap the host copies.  Both return when the data has arrived. */
+int sb200_upload_rows(sb200_context *ctx, uint64_t *d_dst, const uint64_t *const *h_rows, size_t row_bytes, size_t count);
+int sb200_download_rows(sb200_context *ctx, uint64_t *const *h_rows, const uint64_t *d_src, size_t row_bytes, size_t count);
 /* NUMA node of the context's device (-1 when the platform does not say) and the CUDA device index */
 int sb200_device_numa_node(const sb200_context *ctx);
 int sb200_device_index(const sb200_context *ctx);
@@ -110,6 +115,15 @@ int sb200_profile_enable(sb200_context *ctx, int on);
 int sb200_profile_reset(sb200_context *ctx);
 int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
                        unsigned long long *launches, double *algorithmic_bytes);
+/* the same plus the arithmetic those launches executed: modular butterflies and 64x64-bit key multiply-accumulates (per
+ * coefficient, not per warp) -- the work of the second ceiling of SURVEY 8(d), the integer-multiply issue rate */
+int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                            unsigned long long *launches, double *algorithmic_bytes, double *butterflies, double *macs);
+/* that ceiling, measured in this process on the context's device: the path's own butterfly / multiply-accumulate code on
+ * registers only, at the launch shapes of the dominant kernels.  kind 0: forward butterflies (column-pass shape), 1: forward
+ * butterflies (fused kernel's shape), 2: inverse butterflies, 3: key multiply-accumulates.  Result: warp-level operations per
+ * second of the whole device (one warp-level operation = 32 coefficient-level ones). */
+int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_second);
 
 /* ---- key-switching keys --------------------------------------------------------------------------------------
  * h_key = the flattened KSwitchKeys::data()[index]: [digit j < digits][component 2][key prime k][coeff n], i.e. for
@@ -176,6 +190,15 @@ int sb200_multiply_relinearize(sb200_context *ctx, size_t L, size_t batch, const
 int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint64_t *d_out2, void *stream);
 /* Evaluator::mod_switch_to_next: BFV divide-and-round (rns.cpp:789-828); CKKS drops the last prime */
 int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint64_t *d_out2, void *stream);
+/* the same two functions for ciphertexts of any size (the reference applies the step to every polynomial, evaluator.cpp:1263-1280):
+ * d_in [batch][size][L][n] -> d_out [batch][size][L-1][n] */
+int sb200_rescale_to_next_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_in, uint64_t *d_out, void *stream);
+int sb200_mod_switch_to_next_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_in, uint64_t *d_out, void *stream);
+/* one step of relinearize_internal's loop (evaluator.cpp:1176-1187) on ciphertexts of size >= 3: d_out = d_in with
+ * (c_0, c_1) += switch_key(c_{size-1}, key); every other polynomial is copied, the size is unchanged (the caller drops
+ * polynomials when the loop is done, as the reference's final resize does).  No aliasing. */
+int sb200_relinearize_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *d_in, const sb200_kswitch_key *key,
+                            uint64_t *d_out, void *stream);
 /* Evaluator::apply_galois (evaluator.cpp:2384-2502): automorphism x -> x^galois_elt on both polys + key switch.
  * rotate_rows / rotate_vector(step) = apply_galois(sb200_galois_elt_from_step(step)) with that element's key. */
 int sb200_apply_galois(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_in2, uint32_t galois_elt,
@@ -208,6 +231,10 @@ int sb200_rescale_to_next_host(sb200_context *ctx, size_t L, size_t batch, const
 int sb200_mod_switch_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint64_t *h_out2);
 int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_in2, uint32_t galois_elt,
                             const sb200_kswitch_key *galois_key, uint64_t *h_out2);
+int sb200_rescale_to_next_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_in, uint64_t *h_out);
+int sb200_mod_switch_to_next_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_in, uint64_t *h_out);
+int sb200_relinearize_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *h_in, const sb200_kswitch_key *key,
+                                 uint64_t *h_out);
 
 /* ---- wire format: Ciphertext::save / load with compr_mode_type::none, straight between a byte
  * stream and a device slab (ciphertext.cpp:190-359, serialization.h:76-91, dynarray.h:662-690).  Compressed streams
@@ -258,6 +285,34 @@ int sb200_decrypt(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t si
                   const uint64_t *h_correction_factors, uint64_t *d_plain, void *stream);
 int sb200_decrypt_host(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *h_ct,
                        const uint64_t *h_correction_factors, uint64_t *h_plain);
+
+/* ---- multi-device dispatch: one context per CUDA device of the box, one host thread per device -----------
+ * A batch of independent ciphertexts is cut into contiguous slices, slice i goes to device i through that device's own
+ * context (tables and keys replicated, no data-path collective); every call returns when all slices are back in the host
+ * buffers.  The reference has no counterpart (it is single-threaded per Evaluator call); this is the C++ side of what
+ * bench.py does with one process per GPU.  devices == NULL: every visible device. */
+typedef struct sb200_group sb200_group;
+typedef struct sb200_group_key sb200_group_key; /* one key-switching key replicated on every device of the group */
+int sb200_group_create(int scheme, size_t poly_modulus_degree, const uint64_t *coeff_modulus, size_t k, uint64_t plain_modulus,
+                       const int *devices, size_t device_count, sb200_group **out);
+int sb200_group_destroy(sb200_group *group);
+size_t sb200_group_size(const sb200_group *group);
+sb200_context *sb200_group_context(sb200_group *group, size_t i); /* the context of device slot i (owned by the group) */
+/* first ciphertext and count of slot i's slice of a batch (the same rule for every call; seal_b200/shard.py mirrors it) */
+int sb200_group_slice(const sb200_group *group, size_t batch, size_t i, size_t *first, size_t *count);
+int sb200_group_kswitch_key_create(sb200_group *group, const uint64_t *h_key, size_t digits, sb200_group_key **out);
+int sb200_group_kswitch_key_destroy(sb200_group_key *key);
+int sb200_group_multiply_relinearize_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b,
+                                          const sb200_group_key *relin_key, uint64_t *h_out2);
+int sb200_group_relinearize_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_in3, const sb200_group_key *relin_key,
+                                 uint64_t *h_out2);
+int sb200_group_apply_galois_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_in2, uint32_t galois_elt,
+                                  const sb200_group_key *galois_key, uint64_t *h_out2);
+int sb200_group_multiply_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_a, const uint64_t *h_b, uint64_t *h_out3);
+int sb200_group_rescale_to_next_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_in2, uint64_t *h_out2);
+int sb200_group_mod_switch_to_next_host(sb200_group *group, size_t L, size_t batch, const uint64_t *h_in2, uint64_t *h_out2);
+int sb200_group_ntt_forward_host(sb200_group *group, size_t L, size_t size, size_t batch, uint64_t *h_data);
+int sb200_group_ntt_inverse_host(sb200_group *group, size_t L, size_t size, size_t batch, uint64_t *h_data);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,66 @@
 
 namespace seal_b200
 {
+    class Evaluator;
+
+    // ---- device-resident ciphertexts ---------------------------------------------------------------------------------
+    // A batch of B ciphertexts of one shape that stays on the GPU between Evaluator calls.  It carries exactly the metadata
+    // seal::Ciphertext carries (ciphertext.h:728-742: parms_id, is_ntt_form, size, poly_modulus_degree, coeff_modulus_size,
+    // scale, correction_factor), shared by all members of the batch; Evaluator updates it the way the reference updates the
+    // members of each Ciphertext.  Storage is one slab [B][size][L][n] laid out like Ciphertext::data(), allocated from the
+    // Evaluator's context (sb200_device_malloc) -- the reference's counterpart is the MemoryPoolHandle behind a Ciphertext.
+    // Usage: ev.upload(cts, batch); ev.multiply_relinearize_inplace(batch, other, rk); ev.rescale_to_next_inplace(batch); ...
+    //        ev.download(batch, cts);      -- one H2D and one D2H for a whole chain of operations.
+    class CiphertextBatch
+    {
+    public:
+        CiphertextBatch() = default;
+        ~CiphertextBatch() { release(); }
+        CiphertextBatch(const CiphertextBatch &) = delete;
+        CiphertextBatch &operator=(const CiphertextBatch &) = delete;
+        CiphertextBatch(CiphertextBatch &&o) noexcept { *this = std::move(o); }
+        CiphertextBatch &operator=(CiphertextBatch &&o) noexcept
+        {
+            if (this != &o)
+            {
+                release();
+                ctx_ = o.ctx_, d_ = o.d_, cap_ = o.cap_, batch_ = o.batch_, size_ = o.size_, L_ = o.L_, n_ = o.n_;
+                parms_id_ = o.parms_id_, ntt_ = o.ntt_, scale_ = o.scale_, cf_ = o.cf_;
+                o.ctx_ = nullptr, o.d_ = nullptr, o.cap_ = o.batch_ = o.size_ = o.L_ = o.n_ = 0;
+            }
+            return *this;
+        }
+        std::size_t batch_size() const noexcept { return batch_; }
+        std::size_t size() const noexcept { return size_; }                             // polynomials per ciphertext
+        std::size_t coeff_modulus_size() const noexcept { return L_; }
+        std::size_t poly_modulus_degree() const noexcept { return n_; }
+        const seal::parms_id_type &parms_id() const noexcept { return parms_id_; }
+        bool is_ntt_form() const noexcept { return ntt_; }
+        double &scale() noexcept { return scale_; }
+        double scale() const noexcept { return scale_; }
+        std::uint64_t correction_factor() const noexcept { return cf_; }
+        std::uint64_t *device_data() noexcept { return d_; }
+        const std::uint64_t *device_data() const noexcept { return d_; }
+        std::size_t words_per_ciphertext() const noexcept { return size_ * L_ * n_; }
+        void release() noexcept
+        {
+            if (d_ && ctx_)
+                sb200_device_free(ctx_, d_);
+            d_ = nullptr, cap_ = 0;
+        }
+
+    private:
+        friend class Evaluator;
+        sb200_context *ctx_ = nullptr;
+        std::uint64_t *d_ = nullptr;
+        std::size_t cap_ = 0; // words
+        std::size_t batch_ = 0, size_ = 0, L_ = 0, n_ = 0;
+        seal::parms_id_type parms_id_ = seal::parms_id_zero;
+        bool ntt_ = false;
+        double scale_ = 1.0;
+        std::uint64_t cf_ = 1;
+    };
+
     class Evaluator
     {
     public:
@@ -47,7 +107,8 @@ namespace seal_b200
         ~Evaluator()
         {
             for (auto &kv : keys_)
-                sb200_kswitch_key_destroy(kv.second);
+                sb200_kswitch_key_destroy(kv.second.handle);
+            tmp_.release(); // before the context it was allocated from goes away
             if (ctx_)
                 sb200_context_destroy(ctx_);
         }
@@ -424,14 +485,29 @@ namespace seal_b200
                 throw std::invalid_argument("not enough relinearization keys");
             if (encrypted.size() == 2)
                 return;
-            if (encrypted.size() != 3)
-                throw std::invalid_argument("seal_b200: relinearize is implemented for size-3 ciphertexts");
             check_keyswitch_operand(encrypted, pool);
-            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
-            sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), L);
-            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 3 * L * n);
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree(), size = encrypted.size();
+            std::lock_guard<std::mutex> lock(mu_);
+            if (size == 3)
+            {
+                sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), L);
+                std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 3 * L * n);
+                encrypted.resize(context_, cd->parms_id(), 2);
+                check(sb200_relinearize_host(ctx_, L, 1, in.data(), key, encrypted.data()));
+                throw_if_transparent(encrypted);
+                return;
+            }
+            // size > 3, exactly as the reference's loop is written (evaluator.cpp:1176-1187): every step key-switches the LAST
+            // polynomial (the iterator is not advanced) with the key of index size-1-I, then the ciphertext is cut to 2 polynomials
+            std::vector<std::uint64_t> cur(encrypted.data(), encrypted.data() + size * L * n), next(cur.size());
+            for (std::size_t I = 0; I < size - 2; I++)
+            {
+                sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(size - 1 - I), L);
+                check(sb200_relinearize_sized_host(ctx_, L, size, 1, cur.data(), key, next.data()));
+                cur.swap(next);
+            }
             encrypted.resize(context_, cd->parms_id(), 2);
-            check(sb200_relinearize_host(ctx_, L, 1, in.data(), key, encrypted.data()));
+            std::memcpy(encrypted.data(), cur.data(), 2 * L * n * sizeof(std::uint64_t));
             throw_if_transparent(encrypted);
         }
         void relinearize(const seal::Ciphertext &encrypted, const seal::RelinKeys &relin_keys, seal::Ciphertext &destination,
@@ -488,6 +564,7 @@ namespace seal_b200
             if (encrypted.size() != 2)
                 throw std::invalid_argument("encrypted size must be 2");
             check_keyswitch_operand(encrypted, pool);
+            std::lock_guard<std::mutex> lock(mu_); // the cached key stays valid (not evicted) while the operation uses it
             sb200_kswitch_key *key = key_for(galois_keys, seal::GaloisKeys::get_index(galois_elt), L);
             std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 2 * L * n);
             check(sb200_apply_galois_host(ctx_, L, 1, in.data(), galois_elt, key, encrypted.data()));
@@ -609,6 +686,9 @@ namespace seal_b200
         }
 
         // ---- batch extension: destination[i] = relinearize(multiply(a[i], b[i])), one device pass over the batch ----
+        // (upload through page-locked staging, fused multiply + relinearize on the device, download).  Scales and BGV correction
+        // factors may differ from ciphertext to ciphertext; they are computed before anything is written, so destination may
+        // alias a or b.
         void multiply_relinearize(const std::vector<seal::Ciphertext> &a, const std::vector<seal::Ciphertext> &b,
                                   const seal::RelinKeys &relin_keys, std::vector<seal::Ciphertext> &destination) const
         {
@@ -616,10 +696,11 @@ namespace seal_b200
                 throw std::invalid_argument("batch size mismatch");
             if (relin_keys.parms_id() != context_.key_parms_id())
                 throw std::invalid_argument("relin_keys is not valid for encryption parameters");
-            const std::size_t B = a.size(), L = a[0].coeff_modulus_size(), n = a[0].poly_modulus_degree(), w = 2 * L * n;
+            const std::size_t B = a.size();
             const bool ckks = scheme_ == seal::scheme_type::ckks, ntt = scheme_ != seal::scheme_type::bfv;
             auto cd = context_.get_context_data(a[0].parms_id());
-            std::vector<std::uint64_t> ha(B * w), hb(B * w), ho(B * w);
+            std::vector<double> scales(B);
+            std::vector<std::uint64_t> factors(B);
             for (std::size_t i = 0; i < B; i++)
             {
                 validate(a[i], "encrypted1 is not valid for encryption parameters");
@@ -628,25 +709,279 @@ namespace seal_b200
                     throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
                 if (a[i].size() != 2 || b[i].size() != 2 || a[i].is_ntt_form() != ntt || b[i].is_ntt_form() != ntt)
                     throw std::invalid_argument("batch entries must be fresh size-2 ciphertexts in the scheme's native form");
-                if (ckks && !scale_within_bounds(a[i].scale() * b[i].scale(), *cd))
+                scales[i] = ckks ? a[i].scale() * b[i].scale() : a[i].scale(); // evaluator.cpp:703-707; BFV / BGV leave the scale alone
+                if (ckks && !scale_within_bounds(scales[i], *cd))
                     throw std::invalid_argument("scale out of bounds");
-                std::memcpy(ha.data() + i * w, a[i].data(), w * sizeof(std::uint64_t));
-                std::memcpy(hb.data() + i * w, b[i].data(), w * sizeof(std::uint64_t));
+                factors[i] = scheme_ == seal::scheme_type::bgv
+                                 ? seal::util::multiply_uint_mod(a[i].correction_factor(), b[i].correction_factor(), cd->parms().plain_modulus())
+                                 : a[i].correction_factor();
             }
-            sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), L);
-            check(sb200_multiply_relinearize_host(ctx_, L, B, ha.data(), hb.data(), key, ho.data()));
-            destination.resize(B);
+            CiphertextBatch da, db;
+            upload_rows(a, da);
+            upload_rows(b, db);
+            da.scale_ = db.scale_ = 1.0; // per-ciphertext metadata is applied below
+            multiply_relinearize_inplace(da, db, relin_keys);
+            download(da, destination);
             for (std::size_t i = 0; i < B; i++)
             {
-                destination[i] = a[i];
-                std::memcpy(destination[i].data(), ho.data() + i * w, w * sizeof(std::uint64_t));
-                if (ckks)
-                    destination[i].scale() = a[i].scale() * b[i].scale();
-                if (scheme_ == seal::scheme_type::bgv)
-                    destination[i].correction_factor() = seal::util::multiply_uint_mod(
-                        a[i].correction_factor(), b[i].correction_factor(), cd->parms().plain_modulus());
-                throw_if_transparent(destination[i]);
+                destination[i].scale() = scales[i];
+                destination[i].correction_factor() = factors[i];
             }
+        }
+
+        // =================================== device-resident batches (CiphertextBatch) ===================================
+        // Same members, same checks and metadata updates as the seal::Ciphertext overloads above; the data never leaves the GPU.
+        void upload(const std::vector<seal::Ciphertext> &cts, CiphertextBatch &destination) const
+        {
+            if (cts.empty())
+                throw std::invalid_argument("batch cannot be empty");
+            const seal::Ciphertext &f = cts[0];
+            for (auto &c : cts)
+            {
+                validate(c, "encrypted is not valid for encryption parameters");
+                const double s1 = c.scale(), s2 = f.scale();
+                if (c.parms_id() != f.parms_id() || c.size() != f.size() || c.is_ntt_form() != f.is_ntt_form() ||
+                    c.correction_factor() != f.correction_factor() || std::memcmp(&s1, &s2, sizeof(double)) != 0)
+                    throw std::invalid_argument("batch members must share parms_id, size, NTT form, scale and correction factor");
+            }
+            upload_rows(cts, destination);
+        }
+        void download(const CiphertextBatch &source, std::vector<seal::Ciphertext> &cts) const
+        {
+            owned(source);
+            cts.resize(source.batch_);
+            std::vector<std::uint64_t *> rows(source.batch_);
+            for (std::size_t i = 0; i < source.batch_; i++)
+            {
+                cts[i].resize(context_, source.parms_id_, source.size_);
+                cts[i].is_ntt_form() = source.ntt_;
+                cts[i].scale() = source.scale_;
+                cts[i].correction_factor() = source.cf_;
+                rows[i] = cts[i].data();
+            }
+            std::lock_guard<std::mutex> lock(mu_);
+            check(sb200_download_rows(ctx_, rows.data(), source.d_, source.words_per_ciphertext() * sizeof(std::uint64_t), source.batch_));
+            for (auto &c : cts)
+                throw_if_transparent(c);
+        }
+        void copy(const CiphertextBatch &source, CiphertextBatch &destination) const
+        {
+            owned(source);
+            std::lock_guard<std::mutex> lock(mu_);
+            shape(destination, source.batch_, source.size_, source.L_, source.n_);
+            copy_meta(source, destination);
+            check(sb200_memcpy_d2d(ctx_, destination.d_, source.d_, source.batch_ * source.words_per_ciphertext() * sizeof(std::uint64_t), nullptr));
+        }
+        // Evaluator::multiply_inplace (evaluator.cpp:352-393), any sizes
+        void multiply_inplace(CiphertextBatch &encrypted1, const CiphertextBatch &encrypted2) const
+        {
+            owned(encrypted1), owned(encrypted2);
+            if (encrypted1.parms_id_ != encrypted2.parms_id_ || encrypted1.batch_ != encrypted2.batch_)
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            const bool ckks = scheme_ == seal::scheme_type::ckks, bgv = scheme_ == seal::scheme_type::bgv;
+            if ((ckks || bgv) && !(encrypted1.ntt_ && encrypted2.ntt_))
+                throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form");
+            if (!(ckks || bgv) && (encrypted1.ntt_ || encrypted2.ntt_))
+                throw std::invalid_argument("encrypted1 or encrypted2 cannot be in NTT form");
+            auto cd = context_.get_context_data(encrypted1.parms_id_);
+            const std::size_t s1 = encrypted1.size_, s2 = encrypted2.size_, so = s1 + s2 - 1;
+            if (so > SEAL_CIPHERTEXT_SIZE_MAX)
+                throw std::invalid_argument("invalid size");
+            const double new_scale = encrypted1.scale_ * encrypted2.scale_;
+            if (ckks && !scale_within_bounds(new_scale, *cd))
+                throw std::invalid_argument("scale out of bounds");
+            std::lock_guard<std::mutex> lock(mu_);
+            std::uint64_t *out = out_slab(encrypted1.batch_ * so * encrypted1.L_ * encrypted1.n_);
+            check(sb200_multiply_sized(ctx_, encrypted1.L_, s1, s2, encrypted1.batch_, encrypted1.d_, encrypted2.d_, out, nullptr));
+            adopt(encrypted1);
+            encrypted1.size_ = so;
+            if (ckks)
+                encrypted1.scale_ = new_scale;
+            if (bgv)
+                encrypted1.cf_ = seal::util::multiply_uint_mod(encrypted1.cf_, encrypted2.cf_, cd->parms().plain_modulus());
+        }
+        void square_inplace(CiphertextBatch &encrypted) const { multiply_inplace(encrypted, encrypted); }
+        // Evaluator::relinearize_inplace (evaluator.cpp:1144-1199)
+        void relinearize_inplace(CiphertextBatch &encrypted, const seal::RelinKeys &relin_keys) const
+        {
+            owned(encrypted);
+            if (relin_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+            if (encrypted.size_ < 2)
+                throw std::invalid_argument("destination_size must be at least 2 and less than or equal to current count");
+            if (relin_keys.size() < encrypted.size_ - 2)
+                throw std::invalid_argument("not enough relinearization keys");
+            if (encrypted.size_ == 2)
+                return;
+            check_keyswitch_form(encrypted.ntt_);
+            std::lock_guard<std::mutex> lock(mu_);
+            const std::size_t size = encrypted.size_, poly = encrypted.L_ * encrypted.n_;
+            if (size == 3)
+            {
+                sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), encrypted.L_);
+                std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly);
+                check(sb200_relinearize(ctx_, encrypted.L_, encrypted.batch_, encrypted.d_, key, out, nullptr));
+                adopt(encrypted);
+                encrypted.size_ = 2;
+                return;
+            }
+            // size > 3, as the reference's loop is written (evaluator.cpp:1176-1187): every step key-switches the LAST polynomial
+            // with the key of index size-1-I; afterwards the ciphertexts are cut to 2 polynomials
+            for (std::size_t I = 0; I < size - 2; I++)
+            {
+                sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(size - 1 - I), encrypted.L_);
+                std::uint64_t *out = out_slab(encrypted.batch_ * size * poly);
+                check(sb200_relinearize_sized(ctx_, encrypted.L_, size, encrypted.batch_, encrypted.d_, key, out, nullptr));
+                adopt(encrypted);
+            }
+            std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly);
+            check(sb200_memcpy_d2d_2d(ctx_, out, 2 * poly * sizeof(std::uint64_t), encrypted.d_, size * poly * sizeof(std::uint64_t),
+                                      2 * poly * sizeof(std::uint64_t), encrypted.batch_, nullptr));
+            adopt(encrypted);
+            encrypted.size_ = 2;
+        }
+        // multiply + relinearize in one device pass (both operands size 2); the result replaces encrypted1
+        void multiply_relinearize_inplace(CiphertextBatch &encrypted1, const CiphertextBatch &encrypted2, const seal::RelinKeys &relin_keys) const
+        {
+            owned(encrypted1), owned(encrypted2);
+            if (encrypted1.parms_id_ != encrypted2.parms_id_ || encrypted1.batch_ != encrypted2.batch_)
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            if (relin_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+            if (encrypted1.size_ != 2 || encrypted2.size_ != 2)
+            {
+                multiply_inplace(encrypted1, encrypted2);
+                relinearize_inplace(encrypted1, relin_keys);
+                return;
+            }
+            const bool ckks = scheme_ == seal::scheme_type::ckks, bgv = scheme_ == seal::scheme_type::bgv;
+            if ((ckks || bgv) != encrypted1.ntt_ || (ckks || bgv) != encrypted2.ntt_)
+                throw std::invalid_argument((ckks || bgv) ? "encrypted1 or encrypted2 must be in NTT form" : "encrypted1 or encrypted2 cannot be in NTT form");
+            auto cd = context_.get_context_data(encrypted1.parms_id_);
+            const double new_scale = encrypted1.scale_ * encrypted2.scale_;
+            if (ckks && !scale_within_bounds(new_scale, *cd))
+                throw std::invalid_argument("scale out of bounds");
+            if (!context_.using_keyswitching())
+                throw std::logic_error("keyswitching is not supported by the context");
+            std::lock_guard<std::mutex> lock(mu_);
+            sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), encrypted1.L_);
+            check(sb200_multiply_relinearize(ctx_, encrypted1.L_, encrypted1.batch_, encrypted1.d_, encrypted2.d_, key, encrypted1.d_, nullptr));
+            if (ckks)
+                encrypted1.scale_ = new_scale;
+            if (bgv)
+                encrypted1.cf_ = seal::util::multiply_uint_mod(encrypted1.cf_, encrypted2.cf_, cd->parms().plain_modulus());
+        }
+        // Evaluator::rescale_to_next_inplace / mod_switch_to_next_inplace (evaluator.cpp:1404-1541), any size
+        void rescale_to_next_inplace(CiphertextBatch &encrypted) const
+        {
+            owned(encrypted);
+            if (context_.last_parms_id() == encrypted.parms_id_)
+                throw std::invalid_argument("end of modulus switching chain reached");
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::invalid_argument("unsupported operation for scheme type");
+            mod_switch_batch(encrypted, true);
+        }
+        void mod_switch_to_next_inplace(CiphertextBatch &encrypted) const
+        {
+            owned(encrypted);
+            if (context_.last_parms_id() == encrypted.parms_id_)
+                throw std::invalid_argument("end of modulus switching chain reached");
+            mod_switch_batch(encrypted, false);
+        }
+        // add / sub / negate (evaluator.cpp:130-350) on batches of equal shape
+        void add_inplace(CiphertextBatch &encrypted1, const CiphertextBatch &encrypted2) const { linear_batch(encrypted1, encrypted2, false); }
+        void sub_inplace(CiphertextBatch &encrypted1, const CiphertextBatch &encrypted2) const { linear_batch(encrypted1, encrypted2, true); }
+        void negate_inplace(CiphertextBatch &encrypted) const
+        {
+            owned(encrypted);
+            std::lock_guard<std::mutex> lock(mu_);
+            check(sb200_negate(ctx_, encrypted.L_, encrypted.size_, encrypted.batch_, encrypted.d_, encrypted.d_, nullptr));
+        }
+        // apply_galois / rotations (evaluator.cpp:2384-2559)
+        void apply_galois_inplace(CiphertextBatch &encrypted, std::uint32_t galois_elt, const seal::GaloisKeys &galois_keys) const
+        {
+            owned(encrypted);
+            if (galois_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (!galois_keys.has_key(galois_elt))
+                throw std::invalid_argument("Galois key not present");
+            if (!(galois_elt & 1) || galois_elt >= 2 * encrypted.n_)
+                throw std::invalid_argument("Galois element is not valid");
+            if (encrypted.size_ != 2)
+                throw std::invalid_argument("encrypted size must be 2");
+            check_keyswitch_form(encrypted.ntt_);
+            std::lock_guard<std::mutex> lock(mu_);
+            sb200_kswitch_key *key = key_for(galois_keys, seal::GaloisKeys::get_index(galois_elt), encrypted.L_);
+            std::uint64_t *out = out_slab(encrypted.batch_ * encrypted.words_per_ciphertext());
+            check(sb200_apply_galois(ctx_, encrypted.L_, encrypted.batch_, encrypted.d_, galois_elt, key, out, nullptr));
+            adopt(encrypted);
+        }
+        void rotate_rows_inplace(CiphertextBatch &encrypted, int steps, const seal::GaloisKeys &galois_keys) const
+        {
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::bgv)
+                throw std::logic_error("unsupported scheme");
+            rotate_batch(encrypted, steps, galois_keys);
+        }
+        void rotate_vector_inplace(CiphertextBatch &encrypted, int steps, const seal::GaloisKeys &galois_keys) const
+        {
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::logic_error("unsupported scheme");
+            rotate_batch(encrypted, steps, galois_keys);
+        }
+        void rotate_columns_inplace(CiphertextBatch &encrypted, const seal::GaloisKeys &galois_keys) const
+        {
+            if (scheme_ != seal::scheme_type::bfv && scheme_ != seal::scheme_type::bgv)
+                throw std::logic_error("unsupported scheme");
+            conjugate_batch(encrypted, galois_keys);
+        }
+        void complex_conjugate_inplace(CiphertextBatch &encrypted, const seal::GaloisKeys &galois_keys) const
+        {
+            if (scheme_ != seal::scheme_type::ckks)
+                throw std::logic_error("unsupported scheme");
+            conjugate_batch(encrypted, galois_keys);
+        }
+        // transform_to_ntt_inplace / transform_from_ntt_inplace (evaluator.cpp:2289-2382)
+        void transform_to_ntt_inplace(CiphertextBatch &encrypted) const
+        {
+            owned(encrypted);
+            if (encrypted.ntt_)
+                throw std::invalid_argument("encrypted is already in NTT form");
+            std::lock_guard<std::mutex> lock(mu_);
+            check(sb200_ntt_forward(ctx_, encrypted.L_, encrypted.size_, encrypted.batch_, encrypted.d_, nullptr));
+            encrypted.ntt_ = true;
+        }
+        void transform_from_ntt_inplace(CiphertextBatch &encrypted_ntt) const
+        {
+            owned(encrypted_ntt);
+            if (!encrypted_ntt.ntt_)
+                throw std::invalid_argument("encrypted_ntt is not in NTT form");
+            std::lock_guard<std::mutex> lock(mu_);
+            check(sb200_ntt_inverse(ctx_, encrypted_ntt.L_, encrypted_ntt.size_, encrypted_ntt.batch_, encrypted_ntt.d_, nullptr));
+            encrypted_ntt.ntt_ = false;
+        }
+        // waits for all device work queued by this Evaluator (the batch members above only enqueue)
+        void synchronize() const { check(sb200_stream_synchronize(ctx_, nullptr)); }
+
+        // ---- key cache control: uploaded key-switching keys are cached by CONTENT (a fingerprint of the key words), never by
+        // address; least recently used entries are evicted above the byte budget ----
+        void set_key_cache_limit(std::size_t bytes) const
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            key_cache_limit_ = bytes;
+            evict(nullptr);
+        }
+        void clear_key_cache() const
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            for (auto &kv : keys_)
+                sb200_kswitch_key_destroy(kv.second.handle);
+            keys_.clear();
+            key_cache_bytes_ = 0;
+        }
+        std::size_t key_cache_entries() const
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            return keys_.size();
         }
 
         sb200_context *native_handle() const noexcept { return ctx_; }
@@ -869,7 +1204,49 @@ namespace seal_b200
             if (scheme_ == seal::scheme_type::bgv && !encrypted.is_ntt_form())
                 throw std::invalid_argument("BGV encrypted must be in NTT form");
         }
-        // uploads KSwitchKeys::data()[index] once (keys are immutable after generation) -- evaluator.cpp:2586-2648
+        // uploads KSwitchKeys::data()[index] (evaluator.cpp:2586-2648) and caches the device copy under a fingerprint of the
+        // key's CONTENT (leading / trailing / strided words of every digit + its shape): a regenerated or reloaded key object
+        // that happens to reuse a freed pool address can never be served another key's device copy.  Caller holds mu_.
+        struct KeyEntry
+        {
+            sb200_kswitch_key *handle = nullptr;
+            std::size_t bytes = 0;
+            std::uint64_t last_use = 0;
+        };
+        static std::uint64_t fingerprint(const std::vector<seal::PublicKey> &kv, std::size_t row_words, std::size_t index)
+        {
+            std::uint64_t h = 0x9E3779B97F4A7C15ull ^ (row_words * 0xD6E8FEB86659FD93ull) ^ (kv.size() << 48) ^ (index << 32);
+            auto mix = [&h](std::uint64_t v) {
+                h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+                h *= 0xFF51AFD7ED558CCDull;
+                h ^= h >> 33;
+            };
+            const std::size_t edge = std::min<std::size_t>(64, row_words), stride = std::max<std::size_t>(1, row_words / 96) | 1;
+            for (auto &pk : kv)
+            {
+                const std::uint64_t *p = pk.data().data();
+                for (std::size_t i = 0; i < edge; i++)
+                    mix(p[i]), mix(p[row_words - 1 - i]);
+                for (std::size_t i = 0; i < row_words; i += stride)
+                    mix(p[i]);
+            }
+            return h;
+        }
+        void evict(const sb200_kswitch_key *keep) const
+        {
+            while (key_cache_bytes_ > key_cache_limit_ && keys_.size() > (keep ? 1u : 0u))
+            {
+                auto victim = keys_.end();
+                for (auto it = keys_.begin(); it != keys_.end(); ++it)
+                    if (it->second.handle != keep && (victim == keys_.end() || it->second.last_use < victim->second.last_use))
+                        victim = it;
+                if (victim == keys_.end())
+                    break;
+                sb200_kswitch_key_destroy(victim->second.handle);
+                key_cache_bytes_ -= victim->second.bytes;
+                keys_.erase(victim);
+            }
+        }
         sb200_kswitch_key *key_for(const seal::KSwitchKeys &keys, std::size_t index, std::size_t L) const
         {
             if (keys.parms_id() != context_.key_parms_id())
@@ -882,20 +1259,171 @@ namespace seal_b200
             for (auto &each : kv)
                 if (!seal::is_metadata_valid_for(each, context_) || !seal::is_buffer_valid(each))
                     throw std::invalid_argument("kswitch_keys is not valid for encryption parameters");
-            std::lock_guard<std::mutex> lock(mu_);
-            const void *id = kv[0].data().data();
-            auto it = keys_.find(id);
-            if (it != keys_.end())
-                return it->second;
             const std::size_t K = context_.key_context_data()->parms().coeff_modulus().size();
             const std::size_t n = context_.key_context_data()->parms().poly_modulus_degree(), row = 2 * K * n;
+            const std::uint64_t id = fingerprint(kv, row, index);
+            auto it = keys_.find(id);
+            if (it != keys_.end())
+            {
+                it->second.last_use = ++key_clock_;
+                return it->second.handle;
+            }
             std::vector<std::uint64_t> flat(kv.size() * row);
             for (std::size_t j = 0; j < kv.size(); j++)
                 std::memcpy(flat.data() + j * row, kv[j].data().data(), row * sizeof(std::uint64_t));
             sb200_kswitch_key *h = nullptr;
             check(sb200_kswitch_key_create(ctx_, flat.data(), kv.size(), &h));
-            keys_[id] = h;
+            KeyEntry e;
+            e.handle = h, e.bytes = flat.size() * sizeof(std::uint64_t), e.last_use = ++key_clock_;
+            keys_[id] = e;
+            key_cache_bytes_ += e.bytes;
+            evict(h);
             return h;
+        }
+        // ---- helpers of the CiphertextBatch members ----
+        // data of already validated ciphertexts of one shape -> one device slab; metadata of the first member
+        void upload_rows(const std::vector<seal::Ciphertext> &cts, CiphertextBatch &destination) const
+        {
+            const seal::Ciphertext &f = cts[0];
+            std::lock_guard<std::mutex> lock(mu_);
+            shape(destination, cts.size(), f.size(), f.coeff_modulus_size(), f.poly_modulus_degree());
+            destination.parms_id_ = f.parms_id(), destination.ntt_ = f.is_ntt_form(), destination.scale_ = f.scale();
+            destination.cf_ = f.correction_factor();
+            std::vector<const std::uint64_t *> rows(cts.size());
+            for (std::size_t i = 0; i < cts.size(); i++)
+                rows[i] = cts[i].data();
+            check(sb200_upload_rows(ctx_, destination.d_, rows.data(), destination.words_per_ciphertext() * sizeof(std::uint64_t), cts.size()));
+        }
+        void owned(const CiphertextBatch &b) const
+        {
+            if (b.ctx_ != ctx_ || !b.d_ || !b.batch_)
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            if (!context_.get_context_data(b.parms_id_))
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        }
+        void reserve(CiphertextBatch &b, std::size_t words) const
+        {
+            if (b.ctx_ != ctx_)
+            {
+                b.release();
+                b.ctx_ = ctx_;
+            }
+            if (b.cap_ < words)
+            {
+                b.release();
+                check(sb200_device_malloc(ctx_, words * sizeof(std::uint64_t), &b.d_));
+                b.cap_ = words;
+            }
+        }
+        void shape(CiphertextBatch &b, std::size_t batch, std::size_t size, std::size_t L, std::size_t n) const
+        {
+            reserve(b, batch * size * L * n);
+            b.batch_ = batch, b.size_ = size, b.L_ = L, b.n_ = n;
+        }
+        static void copy_meta(const CiphertextBatch &s, CiphertextBatch &d)
+        {
+            d.parms_id_ = s.parms_id_, d.ntt_ = s.ntt_, d.scale_ = s.scale_, d.cf_ = s.cf_;
+        }
+        // result slab of a layout-changing operation; adopt() swaps it with the operand's storage, so a chain of operations
+        // allocates nothing once the largest shape has been seen.  Caller holds mu_.
+        std::uint64_t *out_slab(std::size_t words) const
+        {
+            reserve(tmp_, words);
+            return tmp_.d_;
+        }
+        void adopt(CiphertextBatch &b) const
+        {
+            std::swap(b.d_, tmp_.d_);
+            std::swap(b.cap_, tmp_.cap_);
+        }
+        void check_keyswitch_form(bool ntt) const
+        {
+            if (!context_.using_keyswitching())
+                throw std::logic_error("keyswitching is not supported by the context");
+            if (scheme_ == seal::scheme_type::bfv && ntt)
+                throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+            if (scheme_ == seal::scheme_type::ckks && !ntt)
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (scheme_ == seal::scheme_type::bgv && !ntt)
+                throw std::invalid_argument("BGV encrypted must be in NTT form");
+        }
+        void mod_switch_batch(CiphertextBatch &e, bool rescale) const
+        {
+            auto cd = context_.get_context_data(e.parms_id_);
+            auto next = cd->next_context_data();
+            const bool ckks = scheme_ == seal::scheme_type::ckks, bgv = scheme_ == seal::scheme_type::bgv;
+            if (ckks && !e.ntt_)
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (bgv && !e.ntt_)
+                throw std::invalid_argument("BGV encrypted must be in NTT form");
+            if (!ckks && !bgv && e.ntt_)
+                throw std::invalid_argument("BFV encrypted cannot be in NTT form");
+            double scale = e.scale_;
+            if (rescale)
+            {
+                if (!scale_within_bounds(e.scale_, *cd))
+                    throw std::invalid_argument("scale out of bounds");
+                scale = e.scale_ / static_cast<double>(cd->parms().coeff_modulus().back().value());
+            }
+            if ((rescale || ckks) && !scale_within_bounds(scale, *next))
+                throw std::invalid_argument("scale out of bounds"); // :1236-1241, mod_switch_drop_to_next :1318-1322
+            std::lock_guard<std::mutex> lock(mu_);
+            std::uint64_t *out = out_slab(e.batch_ * e.size_ * (e.L_ - 1) * e.n_);
+            check(rescale ? sb200_rescale_to_next_sized(ctx_, e.L_, e.size_, e.batch_, e.d_, out, nullptr)
+                          : sb200_mod_switch_to_next_sized(ctx_, e.L_, e.size_, e.batch_, e.d_, out, nullptr));
+            adopt(e);
+            e.L_ -= 1;
+            e.parms_id_ = next->parms_id();
+            e.scale_ = scale;
+            if (bgv)
+                e.cf_ = seal::util::multiply_uint_mod(e.cf_, cd->rns_tool()->inv_q_last_mod_t(), next->parms().plain_modulus());
+        }
+        void linear_batch(CiphertextBatch &a, const CiphertextBatch &b, bool subtract) const
+        {
+            owned(a), owned(b);
+            if (a.parms_id_ != b.parms_id_ || a.batch_ != b.batch_)
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            if (a.ntt_ != b.ntt_)
+                throw std::invalid_argument("NTT form mismatch");
+            if (!seal::util::are_close<double>(a.scale_, b.scale_))
+                throw std::invalid_argument("scale mismatch");
+            if (a.size_ != b.size_ || a.cf_ != b.cf_)
+                throw std::logic_error("seal_b200: batch add / sub needs operands of equal size and correction factor");
+            std::lock_guard<std::mutex> lock(mu_);
+            check(subtract ? sb200_sub(ctx_, a.L_, a.size_, a.batch_, a.d_, b.d_, a.d_, nullptr)
+                           : sb200_add(ctx_, a.L_, a.size_, a.batch_, a.d_, b.d_, a.d_, nullptr));
+        }
+        void rotate_batch(CiphertextBatch &encrypted, int steps, const seal::GaloisKeys &galois_keys) const
+        {
+            owned(encrypted);
+            auto cd = context_.get_context_data(encrypted.parms_id_);
+            if (!cd->qualifiers().using_batching)
+                throw std::logic_error("encryption parameters do not support batching");
+            if (galois_keys.parms_id() != context_.key_parms_id())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (steps == 0)
+                return;
+            const std::size_t n = cd->parms().poly_modulus_degree();
+            const std::uint32_t elt = cd->galois_tool()->get_elt_from_step(steps);
+            if (galois_keys.has_key(elt))
+            {
+                apply_galois_inplace(encrypted, elt, galois_keys);
+                return;
+            }
+            std::vector<int> naf_steps = seal::util::naf(steps);
+            if (naf_steps.size() == 1)
+                throw std::invalid_argument("Galois key not present");
+            for (int st : naf_steps)
+                if (static_cast<std::size_t>(std::abs(st)) != (n >> 1))
+                    rotate_batch(encrypted, st, galois_keys);
+        }
+        void conjugate_batch(CiphertextBatch &encrypted, const seal::GaloisKeys &galois_keys) const
+        {
+            owned(encrypted);
+            auto cd = context_.get_context_data(encrypted.parms_id_);
+            if (!cd->qualifiers().using_batching)
+                throw std::logic_error("encryption parameters do not support batching");
+            apply_galois_inplace(encrypted, cd->galois_tool()->get_elt_from_step(0), galois_keys);
         }
         void mod_switch_impl(const seal::Ciphertext &encrypted, seal::Ciphertext &destination, bool rescale) const
         {
@@ -908,8 +1436,6 @@ namespace seal_b200
                 throw std::invalid_argument("BGV encrypted must be in NTT form"); // :1214-1217
             if (!ckks && !bgv && encrypted.is_ntt_form())
                 throw std::invalid_argument("BFV encrypted cannot be in NTT form");
-            if (encrypted.size() != 2)
-                throw std::invalid_argument("seal_b200: modulus switching is implemented for size-2 ciphertexts");
             double scale = encrypted.scale();
             if (rescale)
             {
@@ -919,13 +1445,15 @@ namespace seal_b200
                 if (!scale_within_bounds(scale, *next))
                     throw std::invalid_argument("scale out of bounds");
             }
-            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree();
-            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + 2 * L * n);
+            else if (ckks && !scale_within_bounds(scale, *next))
+                throw std::invalid_argument("scale out of bounds"); // mod_switch_drop_to_next, evaluator.cpp:1318-1322
+            const std::size_t L = encrypted.coeff_modulus_size(), n = encrypted.poly_modulus_degree(), size = encrypted.size();
+            std::vector<std::uint64_t> in(encrypted.data(), encrypted.data() + size * L * n);
             const bool ntt = encrypted.is_ntt_form();
             const std::uint64_t correction = encrypted.correction_factor();
-            destination.resize(context_, next->parms_id(), 2);
-            check(rescale ? sb200_rescale_to_next_host(ctx_, L, 1, in.data(), destination.data())
-                          : sb200_mod_switch_to_next_host(ctx_, L, 1, in.data(), destination.data()));
+            destination.resize(context_, next->parms_id(), size);
+            check(rescale ? sb200_rescale_to_next_sized_host(ctx_, L, size, 1, in.data(), destination.data())
+                          : sb200_mod_switch_to_next_sized_host(ctx_, L, size, 1, in.data(), destination.data()));
             destination.is_ntt_form() = ntt;
             destination.scale() = scale;
             if (bgv) // :1288-1293
@@ -973,6 +1501,9 @@ namespace seal_b200
         seal::scheme_type scheme_;
         sb200_context *ctx_ = nullptr;
         mutable std::mutex mu_;
-        mutable std::map<const void *, sb200_kswitch_key *> keys_;
+        mutable std::map<std::uint64_t, KeyEntry> keys_;
+        mutable std::size_t key_cache_bytes_ = 0, key_cache_limit_ = std::size_t(24) << 30;
+        mutable std::uint64_t key_clock_ = 0;
+        mutable CiphertextBatch tmp_; // result slab of layout-changing batch operations
     };
 } // namespace seal_b200

@@ -25,7 +25,7 @@ _STATUS = {-1: ValueError, -2: RuntimeError, -3: IndexError, -4: RuntimeError, -
 SYMBOLS = [
     "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
-    "sb200_device_bytes", "sb200_context_set_limit", "sb200_device_malloc", "sb200_device_free", "sb200_host_malloc", "sb200_host_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d", "sb200_memcpy_d2d_2d", "sb200_stream_synchronize", "sb200_device_numa_node", "sb200_device_index", "sb200_keyswitch_chunk", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read",
+    "sb200_device_bytes", "sb200_context_set_limit", "sb200_device_malloc", "sb200_device_free", "sb200_host_malloc", "sb200_host_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d", "sb200_memcpy_d2d_2d", "sb200_stream_synchronize", "sb200_upload_rows", "sb200_download_rows", "sb200_rescale_to_next_sized", "sb200_mod_switch_to_next_sized", "sb200_relinearize_sized", "sb200_rescale_to_next_sized_host", "sb200_mod_switch_to_next_sized_host", "sb200_relinearize_sized_host", "sb200_device_numa_node", "sb200_device_index", "sb200_keyswitch_chunk", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read", "sb200_profile_read_work", "sb200_selftest_rate",
     "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
     "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_batch_encode", "sb200_batch_decode", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
@@ -34,6 +34,10 @@ SYMBOLS = [
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
     "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save", "sb200_secret_key_create",
     "sb200_secret_key_destroy", "sb200_decrypt", "sb200_decrypt_host",
+    "sb200_group_create", "sb200_group_destroy", "sb200_group_size", "sb200_group_context", "sb200_group_slice",
+    "sb200_group_kswitch_key_create", "sb200_group_kswitch_key_destroy", "sb200_group_multiply_relinearize_host",
+    "sb200_group_relinearize_host", "sb200_group_apply_galois_host", "sb200_group_multiply_host", "sb200_group_rescale_to_next_host",
+    "sb200_group_mod_switch_to_next_host", "sb200_group_ntt_forward_host", "sb200_group_ntt_inverse_host",
 ]
 
 
@@ -76,6 +80,9 @@ def lib():
         L.sb200_profile_reset.argtypes = [vp]
         L.sb200_profile_read.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
                                          C.POINTER(C.c_double)]
+        L.sb200_profile_read_work.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
+                                              C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.sb200_selftest_rate.argtypes = [vp, i32, C.POINTER(C.c_double)]
         L.sb200_kswitch_key_create.argtypes = [vp, _u64p, sz, C.POINTER(vp)]
         L.sb200_kswitch_key_destroy.argtypes = [vp]
         L.sb200_kswitch_key_load.argtypes = [vp, C.c_char_p, sz, sz, C.POINTER(vp)]
@@ -117,6 +124,9 @@ def lib():
         L.sb200_rescale_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_mod_switch_to_next_host.argtypes = [vp, sz, sz, _u64p, _u64p]
         L.sb200_apply_galois_host.argtypes = [vp, sz, sz, _u64p, u32, vp, _u64p]
+        L.sb200_rescale_to_next_sized_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p]
+        L.sb200_mod_switch_to_next_sized_host.argtypes = [vp, sz, sz, sz, _u64p, _u64p]
+        L.sb200_relinearize_sized_host.argtypes = [vp, sz, sz, sz, _u64p, vp, _u64p]
         L.sb200_get_parms_id.argtypes = [vp, sz, _u64p]
         L.sb200_ciphertext_inspect.argtypes = [C.c_char_p, sz, C.POINTER(CtInfo)]
         L.sb200_ciphertext_save_size.restype = sz
@@ -285,6 +295,22 @@ class Context:
             i += 1
         return out
 
+    def profile_read_work(self):
+        """[(kernel name, total device ms, launches, algorithmic bytes, butterflies, multiply-accumulates)]"""
+        out, i = [], 0
+        name = C.create_string_buffer(128)
+        ms, n, by, bf, mc = C.c_double(0), C.c_ulonglong(0), C.c_double(0), C.c_double(0), C.c_double(0)
+        while lib().sb200_profile_read_work(self.h, i, name, 128, C.byref(ms), C.byref(n), C.byref(by), C.byref(bf), C.byref(mc)) == 0:
+            out.append((name.value.decode(), ms.value, n.value, by.value, bf.value, mc.value))
+            i += 1
+        return out
+
+    def selftest_rate(self, kind):
+        """warp-level butterflies (kind 0, 1, 2) / key multiply-accumulates (kind 3) per second, registers only"""
+        v = C.c_double(0)
+        _check(lib().sb200_selftest_rate(self.h, kind, C.byref(v)))
+        return v.value
+
     def load_key(self, host_key):
         return KSwitchKey(self, host_key)
 
@@ -436,16 +462,24 @@ class Context:
 
     def rescale_to_next(self, a):
         a, single = self._batched(a)
-        B, _, L, n = a.shape
-        out = np.zeros((B, 2, max(L - 1, 0), n), dtype=np.uint64)
-        _check(lib().sb200_rescale_to_next_host(self.h, L, B, _hp(a), _hp(out)))
+        B, size, L, n = a.shape
+        out = np.zeros((B, size, max(L - 1, 0), n), dtype=np.uint64)
+        _check(lib().sb200_rescale_to_next_sized_host(self.h, L, size, B, _hp(a), _hp(out)))
         return out[0] if single else out
 
     def mod_switch_to_next(self, a):
         a, single = self._batched(a)
-        B, _, L, n = a.shape
-        out = np.zeros((B, 2, max(L - 1, 0), n), dtype=np.uint64)
-        _check(lib().sb200_mod_switch_to_next_host(self.h, L, B, _hp(a), _hp(out)))
+        B, size, L, n = a.shape
+        out = np.zeros((B, size, max(L - 1, 0), n), dtype=np.uint64)
+        _check(lib().sb200_mod_switch_to_next_sized_host(self.h, L, size, B, _hp(a), _hp(out)))
+        return out[0] if single else out
+
+    def relinearize_step(self, c, key):
+        """one step of relinearize_internal's loop on size >= 3 ciphertexts: (c0, c1) += switch_key(c_last); size unchanged"""
+        c, single = self._batched(c)
+        B, size, L, n = c.shape
+        out = np.zeros_like(c)
+        _check(lib().sb200_relinearize_sized_host(self.h, L, size, B, _hp(c), key.h, _hp(out)))
         return out[0] if single else out
 
     def apply_galois(self, a, galois_elt, key):

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <thread>
 
 using namespace sb;
 
@@ -306,6 +307,127 @@ int sb200_stream_synchronize(sb200_context *ctx, void *stream)
     return SB200_OK;
     SB_CATCH
 }
+} // extern "C"
+namespace
+{
+    // copies rows [r0, r1) between the caller's objects and a contiguous page-locked buffer on a few host threads (one thread
+    // moves ~10 GB/s, a Gen5 x16 link 50+ GB/s)
+    void rows_copy(bool gather, uint8_t *stage, const uint64_t *const *rows, size_t row_bytes, size_t r0, size_t r1)
+    {
+        const size_t cnt = r1 - r0;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nt = std::max<size_t>(1, std::min<size_t>({ 8, hw / 2 ? hw / 2 : 1, cnt * row_bytes / (size_t(4) << 20) + 1 }));
+        auto work = [&](size_t t) {
+            // split by bytes so that few large rows still spread over all threads
+            const size_t total = cnt * row_bytes, b0 = total * t / nt, b1 = total * (t + 1) / nt;
+            for (size_t off = b0; off < b1;)
+            {
+                const size_t r = off / row_bytes, in = off % row_bytes, len = std::min(row_bytes - in, b1 - off);
+                uint8_t *user = reinterpret_cast<uint8_t *>(const_cast<uint64_t *>(rows[r0 + r])) + in;
+                if (gather)
+                    std::memcpy(stage + off, user, len);
+                else
+                    std::memcpy(user, stage + off, len);
+                off += len;
+            }
+        };
+        if (nt == 1)
+            return work(0);
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++)
+            th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th)
+            x.join();
+    }
+    void ensure_pin(Context &c, size_t bytes)
+    {
+        IoArena &io = c.io;
+        if (io.pin_cap >= bytes)
+            return;
+        for (int i = 0; i < 2; i++)
+        {
+            cudaFreeHost(io.pin[i]);
+            io.pin[i] = nullptr;
+        }
+        io.pin_cap = 0;
+        for (int i = 0; i < 2; i++)
+        {
+            cuda_check(cudaHostAlloc(&io.pin[i], bytes, cudaHostAllocDefault), "cudaHostAlloc(staging)");
+            if (!io.pin_ev[i])
+                cuda_check(cudaEventCreateWithFlags(&io.pin_ev[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        io.pin_cap = bytes;
+    }
+    void rows_transfer(Context &c, bool upload, uint64_t *dev, const uint64_t *const *rows, size_t row_bytes, size_t count)
+    {
+        if (!count || !row_bytes)
+            return;
+        const size_t per = std::max<size_t>(1, (size_t(128) << 20) / row_bytes), stage_bytes = std::min(per, count) * row_bytes;
+        ensure_pin(c, stage_bytes);
+        IoArena &io = c.io;
+        cudaStream_t st = nullptr; // legacy default stream: ordered with the caller's default-stream work
+        uint8_t *d = reinterpret_cast<uint8_t *>(dev);
+        size_t i = 0, pend[2] = { 0, 0 }, pend_n[2] = { 0, 0 };
+        bool used[2] = { false, false };
+        for (size_t r0 = 0; r0 < count; r0 += per, i++)
+        {
+            const size_t r1 = std::min(count, r0 + per);
+            const int slot = static_cast<int>(i & 1);
+            uint8_t *stage = static_cast<uint8_t *>(io.pin[slot]);
+            if (used[slot])
+            {
+                cuda_check(cudaEventSynchronize(io.pin_ev[slot]), "cudaEventSynchronize");
+                if (!upload)
+                    rows_copy(false, stage, rows, row_bytes, pend[slot], pend[slot] + pend_n[slot]);
+            }
+            if (upload)
+            {
+                rows_copy(true, stage, rows, row_bytes, r0, r1);
+                cuda_check(cudaMemcpyAsync(d + r0 * row_bytes, stage, (r1 - r0) * row_bytes, cudaMemcpyHostToDevice, st), "H2D");
+            }
+            else
+                cuda_check(cudaMemcpyAsync(stage, d + r0 * row_bytes, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, st), "D2H");
+            cuda_check(cudaEventRecord(io.pin_ev[slot], st), "record");
+            used[slot] = true, pend[slot] = r0, pend_n[slot] = r1 - r0;
+        }
+        // drain in submission order
+        for (size_t j = (i >= 2 ? i - 2 : 0); j < i; j++)
+        {
+            const int slot = static_cast<int>(j & 1);
+            cuda_check(cudaEventSynchronize(io.pin_ev[slot]), "cudaEventSynchronize");
+            if (!upload)
+                rows_copy(false, static_cast<uint8_t *>(io.pin[slot]), rows, row_bytes, pend[slot], pend[slot] + pend_n[slot]);
+        }
+    }
+} // namespace
+extern "C" {
+int sb200_upload_rows(sb200_context *ctx, uint64_t *d_dst, const uint64_t *const *h_rows, size_t row_bytes, size_t count)
+{
+    SB_NEED(d_dst);
+    SB_NEED(h_rows);
+    SB_TRY
+    SB_NEED(ctx);
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    rows_transfer(c, true, d_dst, h_rows, row_bytes, count);
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_download_rows(sb200_context *ctx, uint64_t *const *h_rows, const uint64_t *d_src, size_t row_bytes, size_t count)
+{
+    SB_NEED(d_src);
+    SB_NEED(h_rows);
+    SB_TRY
+    SB_NEED(ctx);
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    rows_transfer(c, false, const_cast<uint64_t *>(d_src), h_rows, row_bytes, count);
+    return SB200_OK;
+    SB_CATCH
+}
 int sb200_device_index(const sb200_context *ctx)
 {
     return ctx ? ctx->c->device : -1;
@@ -355,6 +477,25 @@ int sb200_profile_reset(sb200_context *ctx)
 int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
                        unsigned long long *launches, double *algorithmic_bytes)
 {
+    return sb200_profile_read_work(ctx, index, name, name_capacity, total_ms, launches, algorithmic_bytes, nullptr, nullptr);
+}
+
+int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_second)
+{
+    SB_NEED(warp_ops_per_second);
+    SB_NEED(ctx);
+    SB_TRY
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    *warp_ops_per_second = selftest_rate(c, kind, nullptr);
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                            unsigned long long *launches, double *algorithmic_bytes, double *butterflies, double *macs)
+{
     SB_NEED(ctx);
     SB_NEED(name);
     SB_NEED(total_ms);
@@ -369,7 +510,7 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
     struct Agg
     {
         std::string name;
-        double ms = 0, bytes = 0;
+        double ms = 0, bytes = 0, bflys = 0, macs = 0;
         unsigned long long n = 0;
     };
     std::vector<Agg> aggs;
@@ -385,7 +526,7 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
             aggs.push_back(Agg{ nm });
             it = aggs.end() - 1;
         }
-        it->ms += ms, it->bytes += r.bytes, it->n++;
+        it->ms += ms, it->bytes += r.bytes, it->bflys += r.bflys, it->macs += r.macs, it->n++;
     }
     if (index >= aggs.size())
         throw std::out_of_range("profile index");
@@ -393,6 +534,10 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
     *total_ms = aggs[index].ms;
     *launches = aggs[index].n;
     *algorithmic_bytes = aggs[index].bytes;
+    if (butterflies)
+        *butterflies = aggs[index].bflys;
+    if (macs)
+        *macs = aggs[index].macs;
     return SB200_OK;
     SB_CATCH
 }
@@ -420,6 +565,7 @@ int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t d
     // keep its 128-bit sums in range
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr))
         throw std::invalid_argument("kswitch key data is not valid for encryption parameters");
+    key_finalize(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -454,6 +600,7 @@ int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len
     h->k.digits = digits;
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr)) // KSwitchKeys::load ends in is_valid_for (kswitchkeys.cpp:149-153)
         throw std::logic_error("KSwitchKeys data is invalid");
+    key_finalize(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -705,30 +852,62 @@ int sb200_multiply_relinearize(sb200_context *ctx, size_t L, size_t batch, const
     SB_CATCH
 }
 
-int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
+static void check_size(size_t size)
 {
-    SB_NEED(in2);
-    SB_NEED(out2);
+    if (size < 1 || size > 16) // SEAL_CIPHERTEXT_SIZE_MAX (util/defines.h)
+        throw std::invalid_argument("invalid ciphertext size");
+}
+
+int sb200_rescale_to_next_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, uint64_t *out, void *stream)
+{
+    SB_NEED(in);
+    SB_NEED(out);
     SB_TRY
     SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
-    if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
+    check_size(size);
+    if (static_cast<const void *>(in) == static_cast<const void *>(out))
         throw std::invalid_argument("rescale_to_next: input and output slabs must not alias (different layouts)");
-    op_rescale(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    op_rescale(c, L, batch * size, (const u64 *)in, (u64 *)out, static_cast<cudaStream_t>(stream));
     return SB200_OK;
     SB_CATCH
 }
-
-int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
+int sb200_rescale_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
 {
-    SB_NEED(in2);
-    SB_NEED(out2);
+    return sb200_rescale_to_next_sized(ctx, L, 2, batch, in2, out2, stream);
+}
+
+int sb200_mod_switch_to_next_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, uint64_t *out, void *stream)
+{
+    SB_NEED(in);
+    SB_NEED(out);
     SB_TRY
     SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
-    if (static_cast<const void *>(in2) == static_cast<const void *>(out2))
+    check_size(size);
+    if (static_cast<const void *>(in) == static_cast<const void *>(out))
         throw std::invalid_argument("mod_switch_to_next: input and output slabs must not alias (different layouts)");
-    op_mod_switch(c, L, batch, (const u64 *)in2, (u64 *)out2, static_cast<cudaStream_t>(stream));
+    op_mod_switch(c, L, batch * size, (const u64 *)in, (u64 *)out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+int sb200_mod_switch_to_next(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2, void *stream)
+{
+    return sb200_mod_switch_to_next_sized(ctx, L, 2, batch, in2, out2, stream);
+}
+
+int sb200_relinearize_sized(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, const sb200_kswitch_key *key,
+                            uint64_t *out, void *stream)
+{
+    SB_NEED(in);
+    SB_NEED(key);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    if (static_cast<const void *>(in) == static_cast<const void *>(out))
+        throw std::invalid_argument("relinearize: input and output slabs must not alias");
+    op_relinearize_sized(c, L, size, batch, (const u64 *)in, key->k, (u64 *)out, static_cast<cudaStream_t>(stream));
     return SB200_OK;
     SB_CATCH
 }
@@ -1058,31 +1237,56 @@ int sb200_multiply_relinearize_host(sb200_context *ctx, size_t L, size_t batch, 
     SB_CATCH
 }
 
-static int modswitch_host(sb200_context *ctx, bool rescale, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
+static int modswitch_host(sb200_context *ctx, bool rescale, size_t L, size_t size, size_t batch, const uint64_t *in2, uint64_t *out2)
 {
     SB_NEED(in2);
     SB_NEED(out2);
     SB_TRY
     SB_ENTER(ctx)
     check_level(c, L, batch);
+    check_size(size);
     if (L < 2)
         throw std::invalid_argument("end of modulus switching chain reached");
-    HostPipe(c).run(batch, 2 * L * c.n, 0, 2 * (L - 1) * c.n, in2, nullptr, out2, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
+    HostPipe(c).run(batch, size * L * c.n, 0, size * (L - 1) * c.n, in2, nullptr, out2, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
         if (rescale)
-            op_rescale(c, L, B, da, dout, st);
+            op_rescale(c, L, B * size, da, dout, st);
         else
-            op_mod_switch(c, L, B, da, dout, st);
+            op_mod_switch(c, L, B * size, da, dout, st);
     });
     return SB200_OK;
     SB_CATCH
 }
 int sb200_rescale_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
 {
-    return modswitch_host(ctx, true, L, batch, in2, out2);
+    return modswitch_host(ctx, true, L, 2, batch, in2, out2);
 }
 int sb200_mod_switch_to_next_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint64_t *out2)
 {
-    return modswitch_host(ctx, false, L, batch, in2, out2);
+    return modswitch_host(ctx, false, L, 2, batch, in2, out2);
+}
+int sb200_rescale_to_next_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, uint64_t *out)
+{
+    return modswitch_host(ctx, true, L, size, batch, in, out);
+}
+int sb200_mod_switch_to_next_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, uint64_t *out)
+{
+    return modswitch_host(ctx, false, L, size, batch, in, out);
+}
+int sb200_relinearize_sized_host(sb200_context *ctx, size_t L, size_t size, size_t batch, const uint64_t *in, const sb200_kswitch_key *key,
+                                 uint64_t *out)
+{
+    SB_NEED(in);
+    SB_NEED(key);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    check_size(size);
+    const size_t w = size * L * c.n;
+    HostPipe(c).run(batch, w, 0, w, in, nullptr, out,
+                    [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) { op_relinearize_sized(c, L, size, B, da, key->k, dout, st); });
+    return SB200_OK;
+    SB_CATCH
 }
 
 int sb200_apply_galois_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in2, uint32_t elt, const sb200_kswitch_key *key,

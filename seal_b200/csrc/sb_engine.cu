@@ -51,6 +51,12 @@ namespace sb
         for (auto &slot : io.buf)
             for (auto p : slot)
                 cudaFree(p);
+        for (int i = 0; i < 2; i++)
+        {
+            cudaFreeHost(io.pin[i]);
+            if (io.pin_ev[i])
+                cudaEventDestroy(io.pin_ev[i]);
+        }
         if (io.ready)
         {
             for (auto s : { io.s_in, io.s_comp, io.s_out })
@@ -135,6 +141,9 @@ namespace sb
         d.inv_n_w = to_tw(pt.inv_n_w);
         d.fwd = f;
         d.inv = i;
+        d.bits = 64u - static_cast<unsigned>(__builtin_clzll(pt.q));
+        const u64 dsol = (d.bits < 64 ? (1ull << d.bits) : 0ull) - pt.q;
+        d.dsol = dsol < (1ull << 31) ? static_cast<unsigned>(dsol) : 0u;
         hp.push_back(d);
     }
 
@@ -221,6 +230,16 @@ namespace sb
             upload_prime(*c, c->tabs[i], hp);
         }
         c->nprimes = hp.size();
+        // 28-bit-limb key multiply-accumulate (sb_device.cuh): every key-level prime must fold below 2^56 and the three column
+        // sums must hold all digits
+        c->limb_mac = k >= 2 && k - 1 <= 60 && !std::getenv("SB200_NO_LIMB_MAC"); // the env switch exists for A/B runs and the parity test
+        for (size_t i = 0; i < k && c->limb_mac; i++)
+        {
+            const PrimeDev &d = hp[i];
+            const unsigned __int128 folded = (static_cast<unsigned __int128>(1) << d.bits) + ((static_cast<unsigned __int128>(d.dsol) << (64 - d.bits)));
+            if (!d.dsol || d.bits < 32 || d.bits > 56 || folded >= (static_cast<unsigned __int128>(1) << 56))
+                c->limb_mac = false;
+        }
         cuda_check(cudaMalloc(&c->d_primes, hp.size() * sizeof(PrimeDev)), "cudaMalloc(primes)");
         cuda_check(cudaMemcpy(c->d_primes, hp.data(), hp.size() * sizeof(PrimeDev), cudaMemcpyHostToDevice), "upload primes");
         // q_j^-1 mod q_i (rns.cpp:767-776 for every level at once)
@@ -1263,7 +1282,8 @@ namespace sb
     // (3) multiply-accumulate with the key, 128-bit lazy sums, one Barrett at the end; evaluator.cpp:2705-2755
     //     grid = (B, n/256, L+1): consecutive CTAs share the key tile of (I, coefficient range) through L2.
     __global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
-                                                          u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k)
+                                                          u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
+                                                          int limb28)
     {
         const int n = 1 << logn;
         const int b = blockIdx.x, I = blockIdx.z;
@@ -1278,8 +1298,11 @@ namespace sb
         {
             u64 x = (ntt_in && I == J) ? tgt.get(b, J, idx, P.q) : e[static_cast<long long>(J) << logn];
             const u64 *kr = key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + idx;
-            mac128(lo0, hi0, x, __ldg(kr));
-            mac128(lo1, hi1, x, __ldg(kr + (static_cast<long long>(k) << logn)));
+            u64 w0 = __ldg(kr), w1 = __ldg(kr + (static_cast<long long>(k) << logn));
+            if (limb28)
+                w0 = limb28_decode(w0), w1 = limb28_decode(w1);
+            mac128(lo0, hi0, x, w0);
+            mac128(lo1, hi1, x, w1);
         }
         u64 *o = Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + idx;
         o[0] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
@@ -1289,7 +1312,9 @@ namespace sb
     // (2a) column pass of ALL digits of one (ciphertext b, output prime I) in one CTA: the twiddles of prime I are staged once
     //      by TMA and reused for the L digit rows (the generic ntt_fwd_col pays the staging + row decoding per row).
     //      grid = (column tiles, B*(L+1)); same arithmetic as ntt_fwd_col<LOGNA, FAST, OpKsDigit>.
-    template <int LOGNA, bool FAST>
+    //      PLAIN: every digit row is a plain in-range array (no Galois view, no re-reduction) -- the CKKS / BGV case with
+    //      primes of one size; the loop then is loads with immediate offsets + the butterflies + stores.
+    template <int LOGNA, bool FAST, bool PLAIN>
     __global__ void __launch_bounds__(kColThreads, SB_COL_MIN_BLOCKS) ks_digit_col_kernel(OpKsDigit op, const PrimeDev *__restrict__ primes)
     {
         constexpr int NA = 1 << LOGNA;
@@ -1311,6 +1336,27 @@ namespace sb
         mbar_wait(&bar, 0);
         constexpr int g = NA >> 3;
         const int off = (ridx << kLocalLog) + col0 + c;
+        const long long n = 1LL << op.logn;
+        if (PLAIN)
+        {
+            const u64 *src = op.dsrc.p + b * op.dsrc.bstride + off;
+            u64 *dst = op.E + ((static_cast<long long>(bi) * L) << op.logn) + ((8 * ridx) << kLocalLog) + col0 + c;
+            const int skipJ = op.ntt_in ? I : -1;
+            for (int J = 0; J < L; J++, src += n, dst += n)
+            {
+                if (J == skipJ)
+                    continue;
+                u64 a[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = src[(j * g) << kLocalLog];
+                fwd_col_passes<LOGNA, FAST>(a, tile, tw_s, ridx, c, P);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    dst[j << kLocalLog] = a[j];
+            }
+            return;
+        }
         for (int J = 0; J < L; J++)
         {
             if (op.ntt_in && J == I)
@@ -1340,33 +1386,49 @@ namespace sb
     }
 
     template <int LOGNA>
-    static void launch_ks_digit_col(const OpKsDigit &op, int B, bool fast, const PrimeDev *primes, cudaStream_t st)
+    static void launch_ks_digit_col(const OpKsDigit &op, int B, bool fast, bool plain, const PrimeDev *primes, cudaStream_t st)
     {
         dim3 grid((1 << kLocalLog) / (kTile >> LOGNA), static_cast<unsigned>(B * (op.L + 1)));
-        if (fast)
-            ks_digit_col_kernel<LOGNA, true><<<grid, kColThreads, 0, st>>>(op, primes);
+        if (fast && plain)
+            ks_digit_col_kernel<LOGNA, true, true><<<grid, kColThreads, 0, st>>>(op, primes);
+        else if (fast)
+            ks_digit_col_kernel<LOGNA, true, false><<<grid, kColThreads, 0, st>>>(op, primes);
+        else if (plain)
+            ks_digit_col_kernel<LOGNA, false, true><<<grid, kColThreads, 0, st>>>(op, primes);
         else
-            ks_digit_col_kernel<LOGNA, false><<<grid, kColThreads, 0, st>>>(op, primes);
+            ks_digit_col_kernel<LOGNA, false, false><<<grid, kColThreads, 0, st>>>(op, primes);
     }
 
     // (2b)+(3) fused: the 8 in-block stages of every digit transform + the multiply-accumulate with the key, looping
     //     over the digits J inside the kernel so the transformed digits never reach memory and the 128-bit sums live in
     //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
     //     blocks.  blockIdx.x = b + B * block_group: consecutive CTAs share the key tile of (I, block group) through L2.
-    template <bool FAST>
+    // LIMB: the key words are limb-encoded and the sums are the three Karatsuba columns of sb_device.cuh (mac_limb28); otherwise
+    // plain 128-bit carry-chain sums.  Component 0 accumulates in registers, component 1 in shared memory.
+    template <bool FAST, bool LIMB>
+    struct KsMacSmem
+    {
+        static constexpr size_t xs = 8 * 256 * sizeof(u64);
+        static constexpr size_t acc = LIMB ? 8 * 3 * 256 * sizeof(u64) : 8 * 256 * sizeof(ulonglong2);
+        static constexpr size_t tw = (8 * 255 + 1) * sizeof(Tw);
+        static constexpr size_t total = xs + acc + tw + 16;
+    };
+    // PLAIN: the target is a plain slab (relinearize / multiply_relinearize); rotations read it through a Galois view.
+    template <bool FAST, bool LIMB, bool PLAIN>
     __global__ void __launch_bounds__(256, SB_MAC_MIN_BLOCKS) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
                                                                    u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
                                                                    int B)
     {
-        // dynamic shared memory: [xs 8x256 u64 | acc1 8x256 x 16 B | twiddles 8*255 x 16 B | mbarrier]
+        // dynamic shared memory: [xs 8x256 u64 | component-1 sums | twiddles 8*255 x 16 B | mbarrier]
         extern __shared__ __align__(16) unsigned char ks_smem[];
+        using SM = KsMacSmem<FAST, LIMB>;
         u64(*xs)[256] = reinterpret_cast<u64(*)[256]>(ks_smem);
-        // 128-bit sums of key component 1 live in shared memory ([j][thread], conflict-free 16-byte accesses); component 0
-        // stays in registers
-        ulonglong2(*acc1)[256] = reinterpret_cast<ulonglong2(*)[256]>(ks_smem + 8 * 256 * sizeof(u64));
+        // sums of key component 1 live in shared memory ([j][..][thread], conflict-free accesses); component 0 stays in registers
+        ulonglong2(*acc1)[256] = reinterpret_cast<ulonglong2(*)[256]>(ks_smem + SM::xs);
+        u64(*acc3)[3][256] = reinterpret_cast<u64(*)[3][256]>(ks_smem + SM::xs);
         // the twiddles of this CTA's 8 blocks are the same for every digit J: staged once with 8 TMA bulk copies
         // (stage s of 8 adjacent blocks is one contiguous run of 8*2^s table entries)
-        Tw *tws = reinterpret_cast<Tw *>(ks_smem + 8 * 256 * (sizeof(u64) + sizeof(ulonglong2)));
+        Tw *tws = reinterpret_cast<Tw *>(ks_smem + SM::xs + SM::acc);
         u64 *bar = reinterpret_cast<u64 *>(tws + 8 * 255 + 1);
         const int warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         const int b = blockIdx.x % B, bg = blockIdx.x / B, I = blockIdx.y;
@@ -1385,24 +1447,36 @@ namespace sb
                 tma_load_1d(tws + 8 * ((1 << st) - 1), P.fwd + ((na + bg * 8) << st), (8u << st) * sizeof(Tw), bar);
         }
         u64 s0l[8], s0h[8];
+        Acc3 c0[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
         {
-            s0l[j] = s0h[j] = 0;
-            acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
+            if (LIMB)
+            {
+                c0[j] = Acc3{ 0, 0, 0 };
+                acc3[j][0][threadIdx.x] = acc3[j][1][threadIdx.x] = acc3[j][2][threadIdx.x] = 0;
+            }
+            else
+            {
+                s0l[j] = s0h[j] = 0;
+                acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
+            }
         }
         mbar_wait(bar, 0);
         auto twf = [&](int st, int i) { return tws[8 * ((1 << st) - 1) + (warp << st) + i]; };
         const u64 *erow = E + ((static_cast<long long>(b) * (L + 1) + I) * L << logn) + (blk << kLocalLog);
-        for (int J = 0; J < L; J++)
+        // key rows of output prime I: component c of digit J at key + ((J*2 + c)*k + ki) * n
+        const long long kstep = (2LL * k) << logn, kcomp = static_cast<long long>(k) << logn;
+        const u64 *krow = key + (static_cast<long long>(ki) << logn) + e0;
+        for (int J = 0; J < L; J++, krow += kstep)
         {
             u64 a[8];
             if (ntt_in && J == I)
             {
                 // the input already is digit J in NTT form modulo q_J (evaluator.cpp:2682-2685)
-                if (tgt.plain())
+                if (PLAIN || tgt.plain())
                 {
-                    const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tgt.row(b, J) + e0);
+                    const ulonglong2 *tp = reinterpret_cast<const ulonglong2 *>(tgt.p + b * tgt.bstride + (static_cast<long long>(J) << logn) + e0);
 #pragma unroll
                     for (int h = 0; h < 4; h++)
                     {
@@ -1430,7 +1504,7 @@ namespace sb
                     for (int j = 0; j < 8; j++)
                         a[j] = csub(csub(csub(a[j], P.q4), P.q2), P.q); // keeps 256 summands below 2^128 for 60-bit primes
                 }
-                else if (L > 200)
+                else if (!LIMB && L > 200)
                 {
                     // guard-free values reach 72q < 2^63.2: more than 227 products with a 57-bit key word would overflow 128 bits
 #pragma unroll
@@ -1438,24 +1512,59 @@ namespace sb
                         a[j] = barrett_lazy4(a[j], P.ratio_hi, P.nq);
                 }
             }
-            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + e0);
-            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(key + ((static_cast<long long>(J) * 2 * k + k + ki) << logn) + e0);
-#pragma unroll
-            for (int h = 0; h < 4; h++)
+            const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(krow);
+            const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(krow + kcomp);
+            if (LIMB)
             {
-                ulonglong2 v = __ldg(k0 + h);
-                mac128(s0l[2 * h], s0h[2 * h], a[2 * h], v.x);
-                mac128(s0l[2 * h + 1], s0h[2 * h + 1], a[2 * h + 1], v.y);
+                unsigned a0[8], a1[8], as[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    const u64 f = fold_solinas(a[j], P.bits, P.dsol); // < 2^56 whatever the lazy growth was
+                    a0[j] = static_cast<unsigned>(f) & 0x0FFFFFFFu;
+                    a1[j] = static_cast<unsigned>(f >> 28);
+                    as[j] = a0[j] + a1[j];
+                }
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                {
+                    ulonglong2 v = __ldg(k0 + h);
+                    mac_limb28(c0[2 * h], a0[2 * h], a1[2 * h], as[2 * h], v.x);
+                    mac_limb28(c0[2 * h + 1], a0[2 * h + 1], a1[2 * h + 1], as[2 * h + 1], v.y);
+                }
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                {
+                    ulonglong2 v = __ldg(k1 + h);
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                    {
+                        const int j = 2 * h + e;
+                        Acc3 t{ acc3[j][0][threadIdx.x], acc3[j][1][threadIdx.x], acc3[j][2][threadIdx.x] };
+                        mac_limb28(t, a0[j], a1[j], as[j], e ? v.y : v.x);
+                        acc3[j][0][threadIdx.x] = t.s0, acc3[j][1][threadIdx.x] = t.s1, acc3[j][2][threadIdx.x] = t.s2;
+                    }
+                }
             }
-#pragma unroll
-            for (int h = 0; h < 4; h++)
+            else
             {
-                ulonglong2 v = __ldg(k1 + h);
-                ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
-                mac128(t0.x, t0.y, a[2 * h], v.x);
-                mac128(t1.x, t1.y, a[2 * h + 1], v.y);
-                acc1[2 * h][threadIdx.x] = t0;
-                acc1[2 * h + 1][threadIdx.x] = t1;
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                {
+                    ulonglong2 v = __ldg(k0 + h);
+                    mac128(s0l[2 * h], s0h[2 * h], a[2 * h], v.x);
+                    mac128(s0l[2 * h + 1], s0h[2 * h + 1], a[2 * h + 1], v.y);
+                }
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                {
+                    ulonglong2 v = __ldg(k1 + h);
+                    ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
+                    mac128(t0.x, t0.y, a[2 * h], v.x);
+                    mac128(t1.x, t1.y, a[2 * h + 1], v.y);
+                    acc1[2 * h][threadIdx.x] = t0;
+                    acc1[2 * h + 1][threadIdx.x] = t1;
+                }
             }
         }
         ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + e0);
@@ -1463,11 +1572,52 @@ namespace sb
 #pragma unroll
         for (int h = 0; h < 4; h++)
         {
-            o0[h] = make_ulonglong2(barrett128(s0l[2 * h], s0h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
-                                    barrett128(s0l[2 * h + 1], s0h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
-            ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
-            o1[h] = make_ulonglong2(barrett128(t0.x, t0.y, P.q, P.ratio_lo, P.ratio_hi), barrett128(t1.x, t1.y, P.q, P.ratio_lo, P.ratio_hi));
+            u64 r0[2], r1[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+                const int j = 2 * h + e;
+                u64 lo0, hi0, lo1, hi1;
+                if (LIMB)
+                {
+                    acc3_value(c0[j], lo0, hi0);
+                    acc3_value(Acc3{ acc3[j][0][threadIdx.x], acc3[j][1][threadIdx.x], acc3[j][2][threadIdx.x] }, lo1, hi1);
+                }
+                else
+                {
+                    lo0 = s0l[j], hi0 = s0h[j];
+                    const ulonglong2 t = acc1[j][threadIdx.x];
+                    lo1 = t.x, hi1 = t.y;
+                }
+                r0[e] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
+                r1[e] = barrett128(lo1, hi1, P.q, P.ratio_lo, P.ratio_hi);
+            }
+            o0[h] = make_ulonglong2(r0[0], r0[1]);
+            o1[h] = make_ulonglong2(r1[0], r1[1]);
         }
+    }
+
+    // re-encodes uploaded key words as two 28-bit limbs (sb_device.cuh: limb28_encode)
+    __global__ void __launch_bounds__(256) key_limb_encode_kernel(u64 *__restrict__ d, long long total)
+    {
+        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (e < total)
+            d[e] = limb28_encode(d[e]);
+    }
+    void key_finalize(Context &c, KSwitchKey &key, cudaStream_t st)
+    {
+        if (!c.limb_mac || key.limb28)
+            return;
+        const long long total = static_cast<long long>(key.digits) * 2 * c.k * c.n;
+        const long long step = 1LL << 30;
+        for (long long e0 = 0; e0 < total; e0 += step)
+        {
+            const long long cnt = std::min(step, total - e0);
+            key_limb_encode_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(key.d_key + e0, cnt);
+            cuda_check(cudaGetLastError(), "key_limb_encode_kernel");
+        }
+        cuda_check(cudaStreamSynchronize(st), "synchronize");
+        key.limb28 = true;
     }
 
     // (4a) special-prime component back to coefficients, + floor(q_sp/2) for rounding; evaluator.cpp:2809-2817.
@@ -1713,6 +1863,150 @@ namespace sb
         return std::min(chunk, batch);
     }
 
+    // ---- in-process measurement of the arithmetic ceilings ("two ceilings must be reported") -------------------
+    // The path's butterflies and key multiply-accumulates, on registers only (no memory traffic in the loop), at the launch
+    // shapes of the two dominant kernels.  Returns warp-level operations per second of the whole device.
+    template <int KIND, int THREADS, int MINB>
+    __global__ void __launch_bounds__(THREADS, MINB) selftest_bfly_kernel(u64 *d, const PrimeDev *__restrict__ primes, int rounds, int nmask)
+    {
+        __shared__ Tw ts[256];
+        const PrimeDev P = primes[0];
+        for (int i = threadIdx.x; i < 256; i += THREADS)
+            ts[i] = ldg_tw(P.fwd + ((1 + i) & nmask)); // any table entries will do
+        __syncthreads();
+        u64 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            a[j] = d[(static_cast<long long>(blockIdx.x) * 8 + j) * THREADS + threadIdx.x];
+        const int lane = threadIdx.x & 31;
+        for (int r = 0; r < rounds; r++)
+        {
+            const Tw *t = ts + ((r * 7 + lane) & 127); // per-lane twiddles from shared memory, as the transform kernels read them
+            auto tw = [&](int lvl, int kk) { return t[(1 << lvl) - 1 + kk]; };
+            if (KIND == 0)
+                fwd_regs<3, true>(a, tw, P);
+            else if (KIND == 1)
+                fwd_regs<3, false>(a, tw, P);
+            else
+                inv_regs<0, false>(a, tw, P);
+            if (KIND == 0 && (r & 3) == 3)
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    a[j] = barrett_lazy4(a[j], P.ratio_hi, P.nq); // the guard-free mode reduces once per 16 stages; here once per 12
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            d[(static_cast<long long>(blockIdx.x) * 8 + j) * THREADS + threadIdx.x] = a[j];
+    }
+    template <bool LIMB>
+    __global__ void __launch_bounds__(256, 2) selftest_mac_kernel(u64 *d, const PrimeDev *__restrict__ primes, int rounds)
+    {
+        const PrimeDev P = primes[0];
+        u64 a[8], kw[8], lo[8], hi[8];
+        Acc3 s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            a[j] = d[(static_cast<long long>(blockIdx.x) * 8 + j) * 256 + threadIdx.x];
+            kw[j] = LIMB ? limb28_encode(a[j] % P.q) : a[j] % P.q;
+            lo[j] = hi[j] = 0;
+            s[j] = Acc3{ 0, 0, 0 };
+        }
+        for (int r = 0; r < rounds; r++)
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+            {
+                const u64 x = a[j] + r; // operands change every round so that nothing is hoisted
+                if (LIMB)
+                {
+                    const u64 f = fold_solinas(x, P.bits, P.dsol);
+                    const unsigned a0 = static_cast<unsigned>(f) & 0x0FFFFFFFu, a1 = static_cast<unsigned>(f >> 28);
+                    mac_limb28(s[j], a0, a1, a0 + a1, kw[j]);
+                    mac_limb28(s[(j + 1) & 7], a0, a1, a0 + a1, kw[(j + 3) & 7]);
+                }
+                else
+                {
+                    mac128(lo[j], hi[j], x, kw[j]);
+                    mac128(lo[(j + 1) & 7], hi[(j + 1) & 7], x, kw[(j + 3) & 7]);
+                }
+            }
+            if (LIMB && (r & 31) == 31)
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    u64 l, h;
+                    acc3_value(s[j], l, h);
+                    s[j] = Acc3{ barrett128(l, h, P.q, P.ratio_lo, P.ratio_hi), 0, 0 }; // keep the column sums in range
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            u64 l = lo[j], h = hi[j];
+            if (LIMB)
+                acc3_value(s[j], l, h);
+            d[(static_cast<long long>(blockIdx.x) * 8 + j) * 256 + threadIdx.x] = l ^ h;
+        }
+    }
+    double selftest_rate(Context &c, int kind, cudaStream_t st)
+    {
+        int sms = 0;
+        cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device), "device attribute");
+        const int rounds = 512, nmask = static_cast<int>(c.n - 1);
+        const size_t words = static_cast<size_t>(sms) * 3 * 8 * 512;
+        u64 *d = static_cast<u64 *>(c.ensure_scratch(words * sizeof(u64)));
+        cuda_check(cudaMemsetAsync(d, 0x5a, words * sizeof(u64), st), "memset");
+        cudaEvent_t e0 = c.stats.get_event(), e1 = c.stats.get_event();
+        double ops = 0;
+        auto run = [&](auto launch) {
+            launch();
+            cuda_check(cudaEventRecord(e0, st), "record");
+            launch();
+            cuda_check(cudaEventRecord(e1, st), "record");
+            cuda_check(cudaEventSynchronize(e1), "synchronize");
+            cuda_check(cudaGetLastError(), "selftest kernel");
+        };
+        switch (kind)
+        {
+        case 0: // forward butterflies at the column-pass launch shape (512 threads x 3 CTAs per SM)
+            ops = static_cast<double>(sms) * 3 * 16 * rounds * 12.0;
+            if (c.fast_q)
+                run([&] { selftest_bfly_kernel<0, 512, 3><<<sms * 3, 512, 0, st>>>(d, c.d_primes, rounds, nmask); });
+            else
+                run([&] { selftest_bfly_kernel<1, 512, 3><<<sms * 3, 512, 0, st>>>(d, c.d_primes, rounds, nmask); });
+            break;
+        case 1: // forward butterflies at the fused kernel's launch shape (256 threads x 2 CTAs per SM)
+            ops = static_cast<double>(sms) * 2 * 8 * rounds * 12.0;
+            if (c.fast_q)
+                run([&] { selftest_bfly_kernel<0, 256, 2><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds, nmask); });
+            else
+                run([&] { selftest_bfly_kernel<1, 256, 2><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds, nmask); });
+            break;
+        case 2: // inverse butterflies
+            ops = static_cast<double>(sms) * 3 * 16 * rounds * 12.0;
+            run([&] { selftest_bfly_kernel<2, 512, 3><<<sms * 3, 512, 0, st>>>(d, c.d_primes, rounds, nmask); });
+            break;
+        case 3: // key multiply-accumulates of the fused kernel (the form the context uses)
+            ops = static_cast<double>(sms) * 2 * 8 * rounds * 16.0;
+            if (c.limb_mac)
+                run([&] { selftest_mac_kernel<true><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds); });
+            else
+                run([&] { selftest_mac_kernel<false><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds); });
+            break;
+        default: throw std::invalid_argument("unknown selftest");
+        }
+        float ms = 0;
+        cuda_check(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+        c.stats.pool.push_back(e0);
+        c.stats.pool.push_back(e1);
+        return ops / (ms * 1e-3);
+    }
+
     size_t keyswitch_chunk(const Context &c, size_t L, size_t batch, bool fused)
     {
         if (c.scheme == 1)
@@ -1740,8 +2034,9 @@ namespace sb
     }
 
     // ct[b] (= base) += key-switch(target[b]) for a chunk of B ciphertexts; writes out[b][2][L][n].
+    //   out_bs = words between consecutive ciphertexts of out (0: the dense [B][2][L][n] slab)
     static void key_switch_chunk(Context &c, size_t L, size_t B, const KsScratch &s, Src target, const KSwitchKey &key, BaseSrc base,
-                                 u64 *out, cudaStream_t st)
+                                 u64 *out, cudaStream_t st, long long out_bs = 0)
     {
         const int n = static_cast<int>(c.n), Li = static_cast<int>(L), ki = static_cast<int>(c.k);
         const bool ntt_in = (c.scheme != 1), bgv = (c.scheme == 3);
@@ -1753,6 +2048,7 @@ namespace sb
             dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
         }
         const bool fused = c.logn >= 12; // two-pass transforms: fuse the in-block stages with the key multiply-accumulate
+        double active_rows = 0;
         {
             // the transforms accept inputs below 4q: skip the digit re-reduction when no digit prime reaches 4x an output prime
             u64 qmax = 0, qmin = ~0ull;
@@ -1762,17 +2058,19 @@ namespace sb
             const int reduce = (qmax >> 2) >= qmin ? 1 : 0;
             OpKsDigit op{ dsrc, s.E, c.d_primes, c.logn, Li, ki, ntt_in ? 1 : 0, reduce };
             const int active = static_cast<int>(B * (ntt_in ? L * L : (L + 1) * L));
+            active_rows = active;
+            const bool plain_rows = !reduce && dsrc.perm == nullptr && dsrc.ginv == 0;
             if (fused)
             {
-                c.stats.begin("ks_digit_ntt", 1, 16.0 * active * n, st);
+                c.stats.begin("ks_digit_ntt", 1, 16.0 * active * n, st, 0.5 * active * n * (c.logn - kLocalLog));
                 switch (c.logn - kLocalLog)
                 {
-                case 4: launch_ks_digit_col<4>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
-                case 5: launch_ks_digit_col<5>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
-                case 6: launch_ks_digit_col<6>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
-                case 7: launch_ks_digit_col<7>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
-                case 8: launch_ks_digit_col<8>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
-                case 9: launch_ks_digit_col<9>(op, static_cast<int>(B), c.fast_q, c.d_primes, st); break;
+                case 4: launch_ks_digit_col<4>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
+                case 5: launch_ks_digit_col<5>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
+                case 6: launch_ks_digit_col<6>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
+                case 7: launch_ks_digit_col<7>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
+                case 8: launch_ks_digit_col<8>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
+                case 9: launch_ks_digit_col<9>(op, static_cast<int>(B), c.fast_q, plain_rows, c.d_primes, st); break;
                 default: throw std::logic_error("unsupported transform size");
                 }
                 c.stats.end(st);
@@ -1788,17 +2086,23 @@ namespace sb
         {
             const int na = n >> kLocalLog;
             dim3 grid(static_cast<unsigned>(B * (na / 8)), static_cast<unsigned>(L + 1));
-            constexpr size_t smem = 8 * 256 * (sizeof(u64) + sizeof(ulonglong2)) + (8 * 255 + 1) * sizeof(Tw) + 16;
-            cuda_check(cudaFuncSetAttribute(c.fast_q ? ks_local_mac_kernel<true> : ks_local_mac_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
-                       "smem attr");
-            c.stats.begin("ks_local_mac", 0, mac_bytes, st);
-            if (c.fast_q)
-                ks_local_mac_kernel<true><<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
-                                                                static_cast<int>(B));
+            const bool limb = key.limb28; // set together with c.limb_mac (key_finalize)
+            const bool plain_tgt = target.perm == nullptr && target.ginv == 0;
+            auto launch = [&](auto kern, size_t smem) {
+                cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "smem attr");
+                c.stats.begin("ks_local_mac", 0, mac_bytes, st, 0.5 * active_rows * n * kLocalLog, 2.0 * B * (L + 1) * L * n);
+                kern<<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki, static_cast<int>(B));
+            };
+            if (limb && c.fast_q)
+                plain_tgt ? launch(ks_local_mac_kernel<true, true, true>, KsMacSmem<true, true>::total)
+                          : launch(ks_local_mac_kernel<true, true, false>, KsMacSmem<true, true>::total);
+            else if (limb)
+                throw std::logic_error("limb-encoded key without guard-free primes"); // limb_mac implies fast_q (primes below 2^56)
+            else if (c.fast_q)
+                plain_tgt ? launch(ks_local_mac_kernel<true, false, true>, KsMacSmem<true, false>::total)
+                          : launch(ks_local_mac_kernel<true, false, false>, KsMacSmem<true, false>::total);
             else
-                ks_local_mac_kernel<false><<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki,
-                                                                 static_cast<int>(B));
+                launch(ks_local_mac_kernel<false, false, false>, KsMacSmem<false, false>::total);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_local_mac_kernel");
         }
@@ -1806,8 +2110,8 @@ namespace sb
         {
             int threads = std::min(n, 256);
             dim3 grid(static_cast<unsigned>(B), (n + threads - 1) / threads, static_cast<unsigned>(L + 1));
-            c.stats.begin("ks_mac", 0, mac_bytes, st);
-            ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki);
+            c.stats.begin("ks_mac", 0, mac_bytes, st, 0, 2.0 * B * (L + 1) * L * n);
+            ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki, key.limb28 ? 1 : 0);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_mac_kernel");
         }
@@ -1819,7 +2123,7 @@ namespace sb
             cuda_check(launch_ntt_inv(op, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "ks_top_intt"), "ks top intt");
         }
         const Tw *inv_top = c.d_invq + (c.k - 1) * c.k;
-        const long long o_ps = static_cast<long long>(L) * n, o_bs = 2 * o_ps;
+        const long long o_ps = static_cast<long long>(L) * n, o_bs = out_bs ? out_bs : 2 * o_ps;
         if (bgv)
         {
             OpModDownFwdBgv op{ { s.U, s.Pp, pp_bs, pp_ps, s.T, out, o_bs, o_ps, inv_top, base, c.q[c.k - 1], c.logn, Li },
@@ -1859,6 +2163,32 @@ namespace sb
             base.pstride = static_cast<long long>(poly);
             base.present = 1;
             key_switch_chunk(c, L, B, s, target, key, base, out2 + b0 * 2 * poly, st);
+        }
+    }
+
+    // one step of relinearize_internal's loop (evaluator.cpp:1179-1187) on ciphertexts of any size >= 3:
+    // out = in with (c_0, c_1) += key_switch(c_{size-1}); all other polynomials are copied.  out [B][size][L][n], no aliasing.
+    void op_relinearize_sized(Context &c, size_t L, size_t size, size_t batch, const u64 *in, const KSwitchKey &key, u64 *out, cudaStream_t st)
+    {
+        check_ks_args(c, L, key);
+        if (size < 3 || size > 16)
+            throw std::invalid_argument("invalid ciphertext size");
+        const size_t poly = L * c.n, chunk = ks_chunk(c, L, batch, false);
+        // polynomials 2 .. size-1 are carried over unchanged
+        cuda_check(cudaMemcpy2DAsync(out + 2 * poly, size * poly * sizeof(u64), in + 2 * poly, size * poly * sizeof(u64), (size - 2) * poly * sizeof(u64),
+                                     batch, cudaMemcpyDeviceToDevice, st),
+                   "relinearize copy");
+        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        {
+            size_t B = std::min(chunk, batch - b0);
+            KsScratch s = ks_carve(c, L, B, false);
+            const u64 *src = in + b0 * size * poly;
+            Src target{ src + (size - 1) * poly, static_cast<long long>(size * poly), nullptr, 0, c.logn };
+            BaseSrc base;
+            base.s = Src{ src, static_cast<long long>(size * poly), nullptr, 0, c.logn };
+            base.pstride = static_cast<long long>(poly);
+            base.present = 1;
+            key_switch_chunk(c, L, B, s, target, key, base, out + b0 * size * poly, st, static_cast<long long>(size * poly));
         }
     }
 
@@ -1962,7 +2292,10 @@ namespace sb
     }
 
     // ------------------------------------------------------------------------- rescale / modulus switching ----
-    void op_rescale(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st)
+    // `polys` = batch * size polynomials, each [L][n], contiguous: every polynomial of a ciphertext is treated alike
+    // (rns.cpp:830-901 is applied per polynomial, evaluator.cpp:1263-1280), so any ciphertext size works.  The kernels decode a
+    // row as (pair, component) with pair stride = 2 * polynomial stride, i.e. plain polynomial index * stride.
+    void op_rescale(Context &c, size_t L, size_t polys, const u64 *in, u64 *out, cudaStream_t st)
     {
         if (c.scheme != 2)
             throw std::invalid_argument("unsupported operation for scheme type"); // evaluator.cpp:1533
@@ -1970,27 +2303,27 @@ namespace sb
             throw std::invalid_argument("end of modulus switching chain reached"); // evaluator.cpp:1521
         const int n = static_cast<int>(c.n);
         const size_t Lout = L - 1;
-        const size_t per = (2 + 2 * Lout) * c.n * sizeof(u64);
-        size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
-        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (2 * L * c.n)));
-        for (size_t b0 = 0; b0 < batch; b0 += chunk)
+        const size_t per = (1 + Lout) * c.n * sizeof(u64);
+        size_t chunk = std::min(polys, std::max<size_t>(1, c.scratch_budget / per));
+        chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (L * c.n)));
+        for (size_t p0 = 0; p0 < polys; p0 += chunk)
         {
-            size_t B = std::min(chunk, batch - b0);
-            u64 *U = static_cast<u64 *>(c.ensure_scratch(per * B));
-            u64 *T = U + B * 2 * c.n;
-            const u64 *in = in2 + b0 * 2 * L * c.n;
+            size_t P = std::min(chunk, polys - p0);
+            u64 *U = static_cast<u64 *>(c.ensure_scratch(per * P));
+            u64 *T = U + P * c.n;
+            const u64 *src = in + p0 * L * c.n;
             const long long i_ps = static_cast<long long>(L) * n, i_bs = 2 * i_ps;
-            OpTopIntt top{ in + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
-            cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "rescale_top_intt"), "rescale intt");
+            OpTopIntt top{ src + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
+            cuda_check(launch_ntt_inv(top, static_cast<int>(P), c.logn, c.d_primes, st, c.stats, "rescale_top_intt"), "rescale intt");
             BaseSrc none;
             const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
-            OpModDownFwd op{ U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
+            OpModDownFwd op{ U, src, i_bs, i_ps, T, out + p0 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
                              c.logn, static_cast<int>(Lout) };
-            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "rescale_ntt", -1, c.fast_q), "rescale ntt");
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(P * Lout), c.logn, c.d_primes, st, c.stats, "rescale_ntt", -1, c.fast_q), "rescale ntt");
         }
     }
 
-    void op_mod_switch(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st)
+    void op_mod_switch(Context &c, size_t L, size_t polys, const u64 *in, u64 *out, cudaStream_t st)
     {
         if (L < 2 || L > c.k)
             throw std::invalid_argument("end of modulus switching chain reached");
@@ -1998,7 +2331,7 @@ namespace sb
         if (c.scheme == 2)
         {
             // CKKS mod_switch_drop_to_next: drop the last RNS component (evaluator.cpp:1296-1358)
-            cuda_check(cudaMemcpy2DAsync(out2, Lout * c.n * sizeof(u64), in2, L * c.n * sizeof(u64), Lout * c.n * sizeof(u64), batch * 2,
+            cuda_check(cudaMemcpy2DAsync(out, Lout * c.n * sizeof(u64), in, L * c.n * sizeof(u64), Lout * c.n * sizeof(u64), polys,
                                          cudaMemcpyDeviceToDevice, st),
                        "mod_switch copy");
             return;
@@ -2006,41 +2339,41 @@ namespace sb
         const int n = static_cast<int>(c.n);
         if (c.scheme == 3)
         {
-            // BGV: mod_t_and_divide_q_last_ntt_inplace on both polynomials (evaluator.cpp:1263-1267, rns.cpp:1193-1236)
-            const size_t per = (4 + 2 * Lout) * c.n * sizeof(u64);
-            size_t chunk = std::min(batch, std::max<size_t>(1, c.scratch_budget / per));
-            chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (2 * L * c.n)));
-            for (size_t b0 = 0; b0 < batch; b0 += chunk)
+            // BGV: mod_t_and_divide_q_last_ntt_inplace on every polynomial (evaluator.cpp:1263-1267, rns.cpp:1193-1236)
+            const size_t per = (2 + Lout) * c.n * sizeof(u64);
+            size_t chunk = std::min(polys, std::max<size_t>(1, c.scratch_budget / per));
+            chunk = std::min<size_t>(chunk, std::max<size_t>(1, (size_t(1) << 30) / (L * c.n)));
+            for (size_t p0 = 0; p0 < polys; p0 += chunk)
             {
-                size_t B = std::min(chunk, batch - b0);
-                u64 *U = static_cast<u64 *>(c.ensure_scratch(per * B));
-                u64 *K = U + B * 2 * c.n, *T = K + B * 2 * c.n;
-                const u64 *in = in2 + b0 * 2 * L * c.n;
+                size_t P = std::min(chunk, polys - p0);
+                u64 *U = static_cast<u64 *>(c.ensure_scratch(per * P));
+                u64 *K = U + P * c.n, *T = K + P * c.n;
+                const u64 *src = in + p0 * L * c.n;
                 const long long i_ps = static_cast<long long>(L) * n, i_bs = 2 * i_ps;
-                OpTopIntt top{ in + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
+                OpTopIntt top{ src + (L - 1) * c.n, i_bs, i_ps, U, c.logn, static_cast<int>(L - 1) };
                 bgv_top(c, top, K, L - 1);
-                cuda_check(launch_ntt_inv(top, static_cast<int>(B * 2), c.logn, c.d_primes, st, c.stats, "modswitch_top_intt"), "mod switch intt");
+                cuda_check(launch_ntt_inv(top, static_cast<int>(P), c.logn, c.d_primes, st, c.stats, "modswitch_top_intt"), "mod switch intt");
                 BaseSrc none;
                 const long long o_ps = static_cast<long long>(Lout) * n, o_bs = 2 * o_ps;
-                OpModDownFwdBgv op{ { U, in, i_bs, i_ps, T, out2 + b0 * 2 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
+                OpModDownFwdBgv op{ { U, src, i_bs, i_ps, T, out + p0 * Lout * c.n, o_bs, o_ps, c.d_invq + (L - 1) * c.k, none, c.q[L - 1],
                                       c.logn, static_cast<int>(Lout) },
                                     K, c.d_qmod + (L - 1) * c.k, c.t };
-                cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * Lout), c.logn, c.d_primes, st, c.stats, "modswitch_ntt", -1, c.fast_q),
+                cuda_check(launch_ntt_fwd(op, static_cast<int>(P * Lout), c.logn, c.d_primes, st, c.stats, "modswitch_ntt", -1, c.fast_q),
                            "mod switch ntt");
             }
             return;
         }
         const long long i_ps = static_cast<long long>(L) * n, o_ps = static_cast<long long>(Lout) * n;
-        const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (2 * L * c.n));
+        const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (L * c.n));
         BaseSrc none;
-        for (size_t b0 = 0; b0 < batch; b0 += step)
+        for (size_t p0 = 0; p0 < polys; p0 += step)
         {
-            size_t B = std::min(step, batch - b0);
-            const u64 *in = in2 + b0 * 2 * L * c.n;
-            long long total = static_cast<long long>(B) * 2 * Lout * n;
+            size_t P = std::min(step, polys - p0);
+            const u64 *src = in + p0 * L * c.n;
+            long long total = static_cast<long long>(P) * Lout * n;
             c.stats.begin("moddown_coeff", 0, 24.0 * total, st);
             moddown_coeff_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-                in + (L - 1) * c.n, 2 * i_ps, i_ps, in, 2 * i_ps, i_ps, out2 + b0 * 2 * Lout * c.n, 2 * o_ps, o_ps,
+                src + (L - 1) * c.n, 2 * i_ps, i_ps, src, 2 * i_ps, i_ps, out + p0 * Lout * c.n, 2 * o_ps, o_ps,
                 c.d_invq + (L - 1) * c.k, none, c.q[L - 1], c.d_primes, c.logn, static_cast<int>(Lout), total);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "moddown_coeff_kernel");

@@ -34,6 +34,7 @@ namespace sb
         struct Context *ctx = nullptr;
         u64 *d_key = nullptr; // [digits][2][k][n]
         size_t digits = 0;
+        bool limb28 = false;  // words are stored as two 28-bit limbs (sb_device.cuh: limb28_encode) for the fused key-switch kernel
     };
 
     // staging for the host-buffer entry points (sb_api.cu: HostPipe)
@@ -44,12 +45,17 @@ namespace sb
         cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
         u64 *buf[2][3] = {};
         size_t cap[2][3] = {};
+        // page-locked staging of sb200_upload_rows / sb200_download_rows
+        void *pin[2] = {};
+        size_t pin_cap = 0;
+        cudaEvent_t pin_ev[2] = {};
     };
 
     struct Context
     {
         int scheme = 0, device = 0, logn = 0;
         bool fast_q = true;                  // every q prime < 2^57: guard-free forward butterflies (sb_device.cuh)
+        bool limb_mac = false;               // key multiply-accumulate on 28-bit limbs (primes 2^b - d below 2^56, <= 60 digits)
         size_t n = 0, k = 0;
         u64 t = 0;
         std::vector<u64> q;                  // key-level primes
@@ -137,11 +143,17 @@ namespace sb
     void op_relinearize(Context &c, size_t L, size_t batch, const u64 *in3, const KSwitchKey &key, u64 *out2, cudaStream_t st);
     void op_multiply_relinearize(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, const KSwitchKey &key,
                                  u64 *out2, cudaStream_t st);
-    void op_rescale(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st);
-    void op_mod_switch(Context &c, size_t L, size_t batch, const u64 *in2, u64 *out2, cudaStream_t st);
+    // polys = batch * size polynomials of L components each (any ciphertext size)
+    void op_rescale(Context &c, size_t L, size_t polys, const u64 *in, u64 *out, cudaStream_t st);
+    void op_mod_switch(Context &c, size_t L, size_t polys, const u64 *in, u64 *out, cudaStream_t st);
+    void op_relinearize_sized(Context &c, size_t L, size_t size, size_t batch, const u64 *in, const KSwitchKey &key, u64 *out, cudaStream_t st);
     void op_apply_galois(Context &c, size_t L, size_t batch, const u64 *in2, uint32_t elt, const KSwitchKey &key, u64 *out2,
                          cudaStream_t st);
     size_t keyswitch_chunk(const Context &c, size_t L, size_t batch, bool fused);
+    // arithmetic ceilings measured in process: warp-level butterflies (kind 0-2) / multiply-accumulates (kind 3) per second
+    double selftest_rate(Context &c, int kind, cudaStream_t st);
+    // after upload + validation: re-encode the key words for the context's multiply-accumulate (no-op unless c.limb_mac)
+    void key_finalize(Context &c, KSwitchKey &key, cudaStream_t st);
     const sbh::BehzLevel &behz_host(Context &c, size_t L);
     // wire format support (sb_api.cu): 1 if any residue of data [rows][n] (prime of a row = row % L) is >= its modulus
     bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st);

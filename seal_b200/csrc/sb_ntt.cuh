@@ -491,6 +491,7 @@ namespace sb
             const char *name;
             int pass; // 0 = whole kernel, 1 = column pass of a transform, 2 = local pass
             double bytes;
+            double bflys, macs; // modular butterflies / 64x64-bit multiply-accumulates the launch executes (second ceiling)
             cudaEvent_t e0, e1;
         };
         std::vector<Rec> recs;
@@ -507,12 +508,12 @@ namespace sb
             cudaEventCreate(&e);
             return e;
         }
-        void begin(const char *name, int pass, double bytes, cudaStream_t st)
+        void begin(const char *name, int pass, double bytes, cudaStream_t st, double bflys = 0, double macs = 0)
         {
             launches++;
             if (!profiling)
                 return;
-            Rec r{ name, pass, bytes, get_event(), get_event() };
+            Rec r{ name, pass, bytes, bflys, macs, get_event(), get_event() };
             cudaEventRecord(r.e0, st);
             recs.push_back(r);
         }
@@ -544,18 +545,19 @@ namespace sb
     {
         if (nrows <= 0)
             return cudaSuccess;
-        const double bytes = 16.0 * (active_rows < 0 ? nrows : active_rows) * (1 << logn);
+        const double arows = active_rows < 0 ? nrows : active_rows, bytes = 16.0 * arows * (1 << logn);
+        const double bf_stage = arows * (1 << logn) / 2.0; // butterflies per stage
         if (logn < 12)
         {
             int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
-            ls.begin(name, 0, bytes, st);
+            ls.begin(name, 0, bytes, st, bf_stage * logn);
             ntt_fwd_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
             ls.end(st);
             return cudaGetLastError();
         }
         const int logna = logn - kLocalLog, na = 1 << logna;
         dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
-        ls.begin(name, 1, bytes, st); // column pass
+        ls.begin(name, 1, bytes, st, bf_stage * logna); // column pass
         switch (logna)
         {
         case 4: fast ? ntt_fwd_col<4, true, Op><<<gc, kColThreads, 0, st>>>(op, primes) : ntt_fwd_col<4, false, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;
@@ -569,7 +571,7 @@ namespace sb
         ls.end(st);
         if (col_only)
             return cudaGetLastError(); // the caller runs its own fused local pass on op.mid()
-        ls.begin(name, 2, bytes, st); // local pass
+        ls.begin(name, 2, bytes, st, bf_stage * kLocalLog); // local pass
         if (fast)
             ntt_fwd_local<true, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
         else
@@ -584,21 +586,22 @@ namespace sb
     {
         if (nrows <= 0)
             return cudaSuccess;
-        const double bytes = 16.0 * (active_rows < 0 ? nrows : active_rows) * (1 << logn);
+        const double arows = active_rows < 0 ? nrows : active_rows, bytes = 16.0 * arows * (1 << logn);
+        const double bf_stage = arows * (1 << logn) / 2.0;
         if (logn < 12)
         {
             int n = 1 << logn, threads = n / 2 < 32 ? 32 : (n / 2 > 256 ? 256 : n / 2);
-            ls.begin(name, 0, bytes, st);
+            ls.begin(name, 0, bytes, st, bf_stage * logn);
             ntt_inv_small<Op><<<nrows, threads, n * sizeof(u64), st>>>(op, primes, logn);
             ls.end(st);
             return cudaGetLastError();
         }
         const int logna = logn - kLocalLog, na = 1 << logna;
-        ls.begin(name, 2, bytes, st); // local pass
+        ls.begin(name, 2, bytes, st, bf_stage * kLocalLog); // local pass
         ntt_inv_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
         ls.end(st);
         dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
-        ls.begin(name, 1, bytes, st); // column pass
+        ls.begin(name, 1, bytes, st, bf_stage * logna); // column pass
         switch (logna)
         {
         case 4: ntt_inv_col<4, Op><<<gc, kColThreads, 0, st>>>(op, primes); break;

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <random>
 #include <typeinfo>
 
@@ -752,6 +753,188 @@ static void test_bgv()
     }
 }
 
+// Device-resident batches (seal_b200::CiphertextBatch): a chain of operations that leaves the GPU once, checked against the
+// reference evaluator ciphertext by ciphertext (words and metadata); the reference's usage pattern is the chain
+// multiply -> relinearize -> rescale of native/tests/seal/evaluator.cpp:3513-3780.
+static void test_batches_and_keys()
+{
+    EncryptionParameters parms(scheme_type::ckks);
+    const size_t n = 8192;
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::Create(n, { 50, 40, 40, 40, 50 }));
+    SEALContext context(parms, true, sec_level_type::none);
+    KeyGenerator keygen(context);
+    PublicKey pk;
+    keygen.create_public_key(pk);
+    RelinKeys rlk;
+    keygen.create_relin_keys(rlk);
+    GaloisKeys glk;
+    keygen.create_galois_keys(std::vector<int>{ 1, 2, 4, -1 }, glk); // 3 = 4 - 1 goes through the NAF fallback
+    Encryptor encryptor(context, pk);
+    CKKSEncoder encoder(context);
+    seal::Evaluator ref(context);
+    seal_b200::Evaluator gpu(context);
+    const double scale = std::pow(2.0, 40);
+    const size_t B = 5;
+    std::mt19937_64 rng(11);
+    std::vector<Ciphertext> a(B), b(B);
+    for (size_t i = 0; i < B; i++)
+    {
+        std::vector<double> x(n / 2), y(n / 2);
+        for (auto &v : x)
+            v = double(rng() % 1000) / 100.0;
+        for (auto &v : y)
+            v = double(rng() % 1000) / 100.0;
+        Plaintext px, py;
+        encoder.encode(x, scale, px);
+        encoder.encode(y, scale, py);
+        encryptor.encrypt(px, a[i]);
+        encryptor.encrypt(py, b[i]);
+    }
+    // depth-2 chain on the device: a <- rescale(relin(a*b)); b <- mod_switch_to_next(b)   (SURVEY 8d, cfg3's chain)
+    seal_b200::CiphertextBatch da, db;
+    gpu.upload(a, da);
+    gpu.upload(b, db);
+    std::vector<Ciphertext> ra = a, rb = b;
+    for (int depth = 0; depth < 2; depth++)
+    {
+        gpu.multiply_relinearize_inplace(da, db, rlk);
+        gpu.rescale_to_next_inplace(da);
+        gpu.mod_switch_to_next_inplace(db);
+        // keep the scales aligned the way a user would (the reference does the same below)
+        db.scale() = da.scale();
+        for (size_t i = 0; i < B; i++)
+        {
+            ref.multiply_inplace(ra[i], rb[i]);
+            ref.relinearize_inplace(ra[i], rlk);
+            ref.rescale_to_next_inplace(ra[i]);
+            ref.mod_switch_to_next_inplace(rb[i]);
+            rb[i].scale() = ra[i].scale();
+        }
+    }
+    gpu.rotate_vector_inplace(da, 3, glk); // NAF fallback: -1, then 4
+    gpu.add_inplace(da, db);
+    gpu.negate_inplace(da);
+    std::vector<Ciphertext> ga, gb;
+    gpu.download(da, ga);
+    gpu.download(db, gb);
+    CHECK(ga.size() == B && gb.size() == B);
+    for (size_t i = 0; i < B; i++)
+    {
+        ref.rotate_vector_inplace(ra[i], 3, glk);
+        ref.add_inplace(ra[i], rb[i]);
+        ref.negate_inplace(ra[i]);
+        CHECK(same_ct(ra[i], ga[i]));
+        CHECK(same_ct(rb[i], gb[i]));
+    }
+    {
+        // unfused on the device: multiply (size 3), square of it (size 5), mod switch of a size-3 batch, transforms
+        seal_b200::CiphertextBatch dx, dy;
+        gpu.upload(a, dx);
+        gpu.upload(b, dy);
+        gpu.multiply_inplace(dx, dy);
+        CHECK(dx.size() == 3);
+        gpu.mod_switch_to_next_inplace(dx); // size 3: the reference switches every polynomial (evaluator.cpp:1263-1280)
+        gpu.transform_from_ntt_inplace(dx);
+        gpu.transform_to_ntt_inplace(dx);
+        gpu.relinearize_inplace(dx, rlk);
+        std::vector<Ciphertext> gx;
+        gpu.download(dx, gx);
+        for (size_t i = 0; i < B; i++)
+        {
+            Ciphertext r;
+            ref.multiply(a[i], b[i], r);
+            ref.mod_switch_to_next_inplace(r);
+            ref.relinearize_inplace(r, rlk);
+            CHECK(same_ct(r, gx[i]));
+        }
+        // single-ciphertext members on sizes other than 2 (ADVICE: the shim used to reject them)
+        Ciphertext r3, g3;
+        ref.multiply(a[0], b[0], r3);
+        g3 = r3;
+        ref.rescale_to_next_inplace(r3);
+        gpu.rescale_to_next_inplace(g3);
+        CHECK(r3.size() == 3 && same_ct(r3, g3));
+        // identical exception for mismatching batches
+        auto o = outcome([&] { gpu.add_inplace(dx, dy); });
+        CHECK(o == "invalid_argument");
+    }
+    {
+        // batch overload on std::vector with destination aliasing an operand (ADVICE: metadata was read after the overwrite)
+        std::vector<Ciphertext> u = a, v = b;
+        v[2].scale() = a[2].scale();
+        gpu.multiply_relinearize(u, v, rlk, v);
+        for (size_t i = 0; i < B; i++)
+        {
+            Ciphertext r;
+            ref.multiply(a[i], b[i], r);
+            ref.relinearize_inplace(r, rlk);
+            CHECK(same_ct(r, v[i]));
+        }
+    }
+    {
+        // the key cache is keyed by content, never by address: destroy and regenerate Galois keys between two rotations
+        // (SEAL's pool hands the freed block straight back, so the new key lands where the old one was)
+        Ciphertext r, g;
+        auto gk1 = std::make_unique<GaloisKeys>();
+        keygen.create_galois_keys(std::vector<int>{ 1 }, *gk1);
+        ref.rotate_vector(a[0], 1, *gk1, r);
+        gpu.rotate_vector(a[0], 1, *gk1, g);
+        CHECK(same_ct(r, g));
+        const void *old_addr = gk1->data()[GaloisKeys::get_index(context.key_context_data()->galois_tool()->get_elt_from_step(1))][0].data().data();
+        gk1.reset();
+        KeyGenerator keygen2(context); // another secret key: a different tenant
+        auto gk2 = std::make_unique<GaloisKeys>();
+        keygen2.create_galois_keys(std::vector<int>{ 1 }, *gk2);
+        const void *new_addr = gk2->data()[GaloisKeys::get_index(context.key_context_data()->galois_tool()->get_elt_from_step(1))][0].data().data();
+        std::printf("galois key regenerated at %s address\n", old_addr == new_addr ? "the SAME" : "a different");
+        ref.rotate_vector(a[0], 1, *gk2, r);
+        gpu.rotate_vector(a[0], 1, *gk2, g);
+        CHECK(same_ct(r, g));
+        // eviction: a budget of one key keeps the cache at one entry and results stay right
+        gpu.set_key_cache_limit(1);
+        for (int step : { 1, 2, -1, 1 })
+        {
+            ref.rotate_vector(a[1], step, glk, r);
+            gpu.rotate_vector(a[1], step, glk, g);
+            CHECK(same_ct(r, g));
+            CHECK(gpu.key_cache_entries() == 1);
+        }
+        gpu.clear_key_cache();
+        CHECK(gpu.key_cache_entries() == 0);
+        gpu.set_key_cache_limit(std::size_t(24) << 30);
+    }
+    {
+        // relinearize of a size-4 ciphertext.  KeyGenerator only makes one relinearization key, so the second key slot is
+        // filled with a copy (any valid key-switching key will do for a word-for-word comparison): both evaluators must
+        // agree on the reference's loop (evaluator.cpp:1176-1187)
+        RelinKeys two = rlk;
+        two.data().resize(2);
+        two.data()[1] = two.data()[0];
+        Ciphertext c3, lo = a[0], r4, g4;
+        ref.multiply(a[0], b[0], c3);
+        lo.scale() = 4.0, c3.scale() = 4.0;
+        ref.multiply(c3, lo, r4);
+        g4 = r4;
+        CHECK(r4.size() == 4);
+        ref.relinearize_inplace(r4, two);
+        gpu.relinearize_inplace(g4, two);
+        CHECK(r4.size() == 2 && same_ct(r4, g4));
+        auto x = outcome([&] { Ciphertext t4; ref.multiply(c3, lo, t4); ref.relinearize_inplace(t4, rlk); });
+        auto y = outcome([&] { Ciphertext t4; ref.multiply(c3, lo, t4); gpu.relinearize_inplace(t4, rlk); });
+        CHECK(x == y && x == "invalid_argument"); // not enough relinearization keys
+        seal_b200::CiphertextBatch d4;
+        std::vector<Ciphertext> v4(3), out4;
+        for (auto &c : v4)
+            ref.multiply(c3, lo, c);
+        gpu.upload(v4, d4);
+        gpu.relinearize_inplace(d4, two);
+        gpu.download(d4, out4);
+        for (auto &c : out4)
+            CHECK(same_ct(r4, c));
+    }
+}
+
 int main()
 {
     try
@@ -759,6 +942,7 @@ int main()
         test_ckks();
         test_bfv();
         test_bgv();
+        test_batches_and_keys();
     }
     catch (const std::exception &e)
     {

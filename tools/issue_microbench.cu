@@ -113,10 +113,23 @@ __global__ void __launch_bounds__(256) k(u32 *out, const u32 *in, long long *clk
                 x[i] = (u32)w[(i + 1) & 7];
         }
     }
+    // only the arrays a stream touches stay live across the loop (register pressure decides the resident warps)
+    constexpr bool USES_W = KIND == 0 || (KIND >= 8 && KIND <= 10) || (KIND >= 13 && KIND <= 15) || KIND == 18 || KIND == 20 || KIND == 22 ||
+                            (KIND >= 25 && KIND <= 31) || (KIND >= 34 && KIND <= 45) || KIND == 47;
+    constexpr bool USES_F = (KIND >= 16 && KIND <= 20) || KIND == 24 || KIND == 25 || KIND == 32 || KIND == 43 || KIND == 45 || KIND == 46;
+    constexpr bool USES_G = (KIND >= 21 && KIND <= 23) || KIND == 44;
     u32 s = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++)
-        s += x[i] + y[i] + z[i] + v[i] + (u32)w[i] + (u32)(w[i] >> 32) + (u32)w2[i] + (u32)__double2uint_rz(f[i]) + (u32)__float2uint_rz(g[i]);
+    {
+        s += x[i] + y[i] + z[i] + v[i];
+        if (USES_W)
+            s += (u32)w[i] + (u32)(w[i] >> 32) + (u32)w2[i];
+        if (USES_F)
+            s += (u32)__double2uint_rz(f[i]);
+        if (USES_G)
+            s += (u32)__float2uint_rz(g[i]);
+    }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0)
         clk[blockIdx.x] = clock64() - t0;
@@ -149,8 +162,18 @@ void run(const char *name, int ops_per_iter)
         cycles += (double)hclk[i] / blocks;
     cudaFree(dclk);
     double warp_instr = (double)blocks * 8 /*warps*/ * ITER * 8.0 * ops_per_iter;
-    printf("%-40s %8.3f ms  %6.2f warp-instr/clk/SM  (%.3f per SMSP, %.2f clk per group per SMSP)\n", name, ms, warp_instr / cycles / 148.0,
-           warp_instr / cycles / 148.0 / 4, ops_per_iter / (warp_instr / cycles / 148.0 / 4));
+    // event time x SM clock = cycles the whole grid took; per SMSP one "group" = one warp executing the stream once
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double groups_per_smsp = (double)blocks * 8 * ITER * 8.0 / (148.0 * 4);
+    int regs = 0;
+    {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k<KIND>);
+        regs = fa.numRegs;
+    }
+    (void)cycles, (void)warp_instr;
+    printf("%-40s %8.3f ms  %6.2f clk per group per SMSP (nominal %d instr)  regs %d\n", name, ms, ms * 1e-3 * khz * 1e3 / groups_per_smsp, ops_per_iter, regs);
     cudaFree(d);
     cudaFree(in);
 }
