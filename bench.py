@@ -318,17 +318,49 @@ def run_cfg3(S, R, torch, np):
     sec = timed(torch, lambda: chain(a0, b0), 3, 1)
     ra, rb = chain(a0, b0)
     torch.cuda.synchronize()
-    # end to end: operands start in pinned host memory, the two results end there; the chain stays on the device in between
+    ra, rb = ra.clone(), rb.clone()
+    # end to end: operands start in pinned host memory, the two results end there; the chain stays on the device in between.
+    # The batch flows in 4 slices: the H2D copy of slice k+1 and the D2H copy of slice k-1 run on their own streams while the
+    # device works on slice k (every slice has its own level buffers).
     ha, hb = a0.cpu().pin_memory(), b0.cpu().pin_memory()
     hra, hrb = torch.empty_like(ra, device="cpu").pin_memory(), torch.empty_like(rb, device="cpu").pin_memory()
-    da, db = torch.empty_like(a0), torch.empty_like(b0)
+    nsl = 4
+    per = batch // nsl
+    s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    sl_in = [(torch.empty((per, 2, L0, n), dtype=torch.int64, device="cuda"), torch.empty((per, 2, L0, n), dtype=torch.int64, device="cuda"))
+             for _ in range(nsl)]
+    sl_bufs = [[[torch.empty((per, 2, L0 - d, n), dtype=torch.int64, device="cuda") for d in range(depth + 1)] for _ in range(2)] for _ in range(nsl)]
+    sl_prod = torch.empty((per, 2, L0, n), dtype=torch.int64, device="cuda")
+
+    def chain_slice(k):
+        a, b, L = sl_in[k][0], sl_in[k][1], L0
+        for d in range(depth):
+            p = sl_prod.view(-1)[: per * 2 * L * n].view(per, 2, L, n)
+            ctx.d_multiply_relinearize(a, b, rk, p, L, per)
+            na_, nb_ = sl_bufs[k][0][d + 1], sl_bufs[k][1][d + 1]
+            ctx.d_rescale_to_next(p, na_, L, per)
+            ctx.d_mod_switch_to_next(b, nb_, L, per)
+            a, b, L = na_, nb_, L - 1
+        return a, b
 
     def e2e():
-        da.copy_(ha, non_blocking=True)
-        db.copy_(hb, non_blocking=True)
-        xa, xb = chain(da, db)
-        hra.copy_(xa, non_blocking=True)
-        hrb.copy_(xb, non_blocking=True)
+        ups, dones = [], []
+        for k in range(nsl):
+            with torch.cuda.stream(s_in):
+                sl_in[k][0].copy_(ha[k * per:(k + 1) * per], non_blocking=True)
+                sl_in[k][1].copy_(hb[k * per:(k + 1) * per], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                ups.append(ev)
+        for k in range(nsl):
+            s_cmp.wait_event(ups[k])
+            xa, xb = chain_slice(k)
+            ev = torch.cuda.Event()
+            ev.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev)
+                hra[k * per:(k + 1) * per].copy_(xa, non_blocking=True)
+                hrb[k * per:(k + 1) * per].copy_(xb, non_blocking=True)
         torch.cuda.synchronize()
 
     e2e()
@@ -348,7 +380,8 @@ def run_cfg3(S, R, torch, np):
     return {"config": "CKKS n=32768, 16 primes, batch 256, depth-8 chain of multiply+relinearize+rescale (+ mod_switch_to_next of b)",
             "value": batch * depth / sec, "unit": "chain steps (multiply+relinearize+rescale)/s", "chains_per_s": batch / sec,
             "e2e": {"value": batch * depth / e2e_sec, "unit": "chain steps/s", "h2d_bytes_per_step": int(ha.nbytes + hb.nbytes),
-                    "d2h_bytes_per_step": int(hra.nbytes + hrb.nbytes), "e2e_over_device": sec / e2e_sec},
+                    "d2h_bytes_per_step": int(hra.nbytes + hrb.nbytes), "e2e_over_device": sec / e2e_sec, "slices": nsl,
+                    "note": "host operands in, host results out; copies of neighbouring slices overlap the chain of the current one"},
             "verified": {"indices": idx, "ok": True, "against": "oracle/_ref: the same 8-level chain on the reference Evaluator"}}
 
 
@@ -422,6 +455,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE.json cfg2-cfg4 lines and the C++ harness")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the reference (profiling runs only)")
+    ap.add_argument("--scratch-gib", type=float, default=0.0, help="key-switching scratch budget (0: what the device has left, at most 64 GiB)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -473,6 +507,11 @@ def main():
     a, b = device_rand(torch, mods, n, (B, 2), L, g), device_rand(torch, mods, n, (B, 2), L, g)
     out = torch.empty((B, 2, L, n), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
+    # key-switching scratch: what the device has left after the batch is resident (180 GB HBM3e), so that one pass over the 1 GB key
+    # serves as many ciphertexts as possible (B_reuse of SURVEY 8d); the library default is 8 GiB
+    free_b, _ = torch.cuda.mem_get_info()
+    scratch_budget = int(args.scratch_gib * 2**30) if args.scratch_gib > 0 else int(max(8 << 30, min(free_b - (6 << 30), 64 << 30)))
+    ctx.set_limit(ctx.LIMIT_SCRATCH_BYTES, scratch_budget)
 
     def step():
         ctx.d_multiply_relinearize(a, b, rk, out, L, B)
@@ -692,6 +731,7 @@ def main():
         "config": {"workload": args.workload, "scheme": "CKKS", "n": n, "coeff_modulus_primes": k, "L": L, "prime_bits": wl["bits"][0],
                    "batch_per_gpu": B, "global_batch": B * world, "ops": "Evaluator::multiply + relinearize_inplace (fused call)",
                    "l2": f"inputs {2 * B * 2 * L * n * 8 / 2**30:.1f} GiB per GPU >> 126 MB L2 (no flush needed)",
+                   "scratch_budget_GiB": round(scratch_budget / 2**30, 1), "ciphertexts_per_key_pass": chunk,
                    "parallelism": f"batch sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "verified": verified, "roofline": roofline,
         "ntt": {"metric": "negacyclic NTT GB/s (2*n*8 B per row per transform)", "rows_per_transform_call": ntt_rows, "n": n,

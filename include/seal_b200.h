@@ -237,9 +237,11 @@ int sb200_relinearize_sized_host(sb200_context *ctx, size_t L, size_t size, size
                                  uint64_t *h_out);
 
 /* ---- wire format: Ciphertext::save / load with compr_mode_type::none, straight between a byte
- * stream and a device slab (ciphertext.cpp:190-359, serialization.h:76-91, dynarray.h:662-690).  Compressed streams
- * (zlib / zstd) and seed-compressed ciphertexts (Ciphertext::save of a symmetric encryption) stay with the reference:
- * inspect reports them, load rejects them. */
+ * stream and a device slab (ciphertext.cpp:190-359, serialization.h:76-91, dynarray.h:662-690).  Seed-compressed ciphertexts
+ * (Serializable<Ciphertext> of a symmetric-key encryption: c_1 replaced by the seed of the PRNG that made it) are expanded on
+ * the device -- Ciphertext::expand_seed -> sample_poly_uniform on a Blake2xbPRNG (ciphertext.cpp:118-150, util/rlwe.cpp:104-132,
+ * randomgen.cpp:204-214), bit for bit -- so a fresh ciphertext crosses PCIe with half its bytes.  Compressed streams (zlib / zstd)
+ * and the shake256 PRNG stay with the reference: inspect reports them, load rejects them. */
 typedef struct sb200_ct_info
 {
     uint64_t parms_id[4];         /* Ciphertext::parms_id() */
@@ -249,10 +251,12 @@ typedef struct sb200_ct_info
     uint64_t correction_factor;   /* BGV */
     double scale;                 /* CKKS */
     int32_t is_ntt_form;
-    int32_t seeded;               /* 1: only c_0 is stored, c_1 is a PRNG seed */
+    int32_t seeded;               /* 0: both polynomials are stored; otherwise only c_0 is, and c_1 is the output of the PRNG of this
+                                     prng_type (randomgen.h:29-36: 1 = blake2xb, 2 = shake256) on the 64-byte seed at seed_offset */
     uint64_t data_offset;         /* byte offset of the first coefficient word in the stream */
     uint64_t data_words;          /* 64-bit words stored */
     uint64_t stream_bytes;        /* length of the serialized object (SEALHeader::size) */
+    uint64_t seed_offset;         /* seeded streams: byte offset of the prng_seed_type (64 bytes); 0 otherwise */
 } sb200_ct_info;
 
 /* EncryptionParameters::parms_id() of the level with L primes (L = k: the key level); encryptionparams.cpp:124-158 */
@@ -263,7 +267,8 @@ int sb200_ciphertext_inspect(const uint8_t *stream, size_t len, sb200_ct_info *i
 size_t sb200_ciphertext_save_size(const sb200_context *ctx, size_t L, size_t size);
 /* Ciphertext::load (validate != 0; also checks every residue < q_i like is_data_valid_for, valcheck.cpp) or unsafe_load
  * (validate == 0) of `batch` serialized ciphertexts of one shape into d_out [batch][size][L][n]; infos may be NULL.
- * The coefficient words are copied from the streams to the device directly. */
+ * The coefficient words are copied from the streams to the device directly; seeded streams (size 2) upload c_0 and expand
+ * c_1 on the device. */
 int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const *streams, const size_t *lens, size_t L, size_t size,
                           int validate, uint64_t *d_out, sb200_ct_info *infos, void *stream);
 /* Ciphertext::save(compr_mode_type::none) of d_in [batch][size][L][n] into outs[b] (capacity >= sb200_ciphertext_save_size);

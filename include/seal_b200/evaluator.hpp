@@ -717,8 +717,8 @@ namespace seal_b200
                                  : a[i].correction_factor();
             }
             CiphertextBatch da, db;
-            upload_rows(a, da);
-            upload_rows(b, db);
+            upload_rows(a.data(), B, da);
+            upload_rows(b.data(), B, db);
             da.scale_ = db.scale_ = 1.0; // per-ciphertext metadata is applied below
             multiply_relinearize_inplace(da, db, relin_keys);
             download(da, destination);
@@ -733,23 +733,36 @@ namespace seal_b200
         // Same members, same checks and metadata updates as the seal::Ciphertext overloads above; the data never leaves the GPU.
         void upload(const std::vector<seal::Ciphertext> &cts, CiphertextBatch &destination) const
         {
-            if (cts.empty())
+            upload(cts.data(), cts.size(), destination);
+        }
+        // a contiguous range of ciphertext objects (e.g. one slice of a larger vector: slices of a batch can be uploaded, processed and
+        // downloaded by different host threads so that the copies of one slice overlap the kernels of another)
+        void upload(const seal::Ciphertext *first, std::size_t count, CiphertextBatch &destination) const
+        {
+            if (!first || !count)
                 throw std::invalid_argument("batch cannot be empty");
-            const seal::Ciphertext &f = cts[0];
-            for (auto &c : cts)
+            const seal::Ciphertext &f = first[0];
+            for (std::size_t i = 0; i < count; i++)
             {
+                const seal::Ciphertext &c = first[i];
                 validate(c, "encrypted is not valid for encryption parameters");
                 const double s1 = c.scale(), s2 = f.scale();
                 if (c.parms_id() != f.parms_id() || c.size() != f.size() || c.is_ntt_form() != f.is_ntt_form() ||
                     c.correction_factor() != f.correction_factor() || std::memcmp(&s1, &s2, sizeof(double)) != 0)
                     throw std::invalid_argument("batch members must share parms_id, size, NTT form, scale and correction factor");
             }
-            upload_rows(cts, destination);
+            upload_rows(first, count, destination);
         }
         void download(const CiphertextBatch &source, std::vector<seal::Ciphertext> &cts) const
         {
-            owned(source);
             cts.resize(source.batch_);
+            download(source, cts.data());
+        }
+        void download(const CiphertextBatch &source, seal::Ciphertext *cts) const
+        {
+            owned(source);
+            if (!cts)
+                throw std::invalid_argument("destination cannot be null");
             std::vector<std::uint64_t *> rows(source.batch_);
             for (std::size_t i = 0; i < source.batch_; i++)
             {
@@ -759,10 +772,9 @@ namespace seal_b200
                 cts[i].correction_factor() = source.cf_;
                 rows[i] = cts[i].data();
             }
-            std::lock_guard<std::mutex> lock(mu_);
             check(sb200_download_rows(ctx_, rows.data(), source.d_, source.words_per_ciphertext() * sizeof(std::uint64_t), source.batch_));
-            for (auto &c : cts)
-                throw_if_transparent(c);
+            for (std::size_t i = 0; i < source.batch_; i++)
+                throw_if_transparent(cts[i]);
         }
         void copy(const CiphertextBatch &source, CiphertextBatch &destination) const
         {
@@ -791,7 +803,7 @@ namespace seal_b200
             if (ckks && !scale_within_bounds(new_scale, *cd))
                 throw std::invalid_argument("scale out of bounds");
             std::lock_guard<std::mutex> lock(mu_);
-            std::uint64_t *out = out_slab(encrypted1.batch_ * so * encrypted1.L_ * encrypted1.n_);
+            std::uint64_t *out = out_slab(encrypted1.batch_ * so * encrypted1.L_ * encrypted1.n_, encrypted1);
             check(sb200_multiply_sized(ctx_, encrypted1.L_, s1, s2, encrypted1.batch_, encrypted1.d_, encrypted2.d_, out, nullptr));
             adopt(encrypted1);
             encrypted1.size_ = so;
@@ -819,7 +831,7 @@ namespace seal_b200
             if (size == 3)
             {
                 sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(2), encrypted.L_);
-                std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly);
+                std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly, encrypted);
                 check(sb200_relinearize(ctx_, encrypted.L_, encrypted.batch_, encrypted.d_, key, out, nullptr));
                 adopt(encrypted);
                 encrypted.size_ = 2;
@@ -830,11 +842,11 @@ namespace seal_b200
             for (std::size_t I = 0; I < size - 2; I++)
             {
                 sb200_kswitch_key *key = key_for(relin_keys, seal::RelinKeys::get_index(size - 1 - I), encrypted.L_);
-                std::uint64_t *out = out_slab(encrypted.batch_ * size * poly);
+                std::uint64_t *out = out_slab(encrypted.batch_ * size * poly, encrypted);
                 check(sb200_relinearize_sized(ctx_, encrypted.L_, size, encrypted.batch_, encrypted.d_, key, out, nullptr));
                 adopt(encrypted);
             }
-            std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly);
+            std::uint64_t *out = out_slab(encrypted.batch_ * 2 * poly, encrypted);
             check(sb200_memcpy_d2d_2d(ctx_, out, 2 * poly * sizeof(std::uint64_t), encrypted.d_, size * poly * sizeof(std::uint64_t),
                                       2 * poly * sizeof(std::uint64_t), encrypted.batch_, nullptr));
             adopt(encrypted);
@@ -912,7 +924,7 @@ namespace seal_b200
             check_keyswitch_form(encrypted.ntt_);
             std::lock_guard<std::mutex> lock(mu_);
             sb200_kswitch_key *key = key_for(galois_keys, seal::GaloisKeys::get_index(galois_elt), encrypted.L_);
-            std::uint64_t *out = out_slab(encrypted.batch_ * encrypted.words_per_ciphertext());
+            std::uint64_t *out = out_slab(encrypted.batch_ * encrypted.words_per_ciphertext(), encrypted);
             check(sb200_apply_galois(ctx_, encrypted.L_, encrypted.batch_, encrypted.d_, galois_elt, key, out, nullptr));
             adopt(encrypted);
         }
@@ -1282,17 +1294,21 @@ namespace seal_b200
         }
         // ---- helpers of the CiphertextBatch members ----
         // data of already validated ciphertexts of one shape -> one device slab; metadata of the first member
-        void upload_rows(const std::vector<seal::Ciphertext> &cts, CiphertextBatch &destination) const
+        void upload_rows(const seal::Ciphertext *cts, std::size_t count, CiphertextBatch &destination) const
         {
             const seal::Ciphertext &f = cts[0];
-            std::lock_guard<std::mutex> lock(mu_);
-            shape(destination, cts.size(), f.size(), f.coeff_modulus_size(), f.poly_modulus_degree());
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                shape(destination, count, f.size(), f.coeff_modulus_size(), f.poly_modulus_degree());
+            }
             destination.parms_id_ = f.parms_id(), destination.ntt_ = f.is_ntt_form(), destination.scale_ = f.scale();
             destination.cf_ = f.correction_factor();
-            std::vector<const std::uint64_t *> rows(cts.size());
-            for (std::size_t i = 0; i < cts.size(); i++)
+            // the transfer itself runs outside the lock (its own staging lane and stream in the library): uploads of one batch
+            // overlap the operations another thread enqueues on other batches
+            std::vector<const std::uint64_t *> rows(count);
+            for (std::size_t i = 0; i < count; i++)
                 rows[i] = cts[i].data();
-            check(sb200_upload_rows(ctx_, destination.d_, rows.data(), destination.words_per_ciphertext() * sizeof(std::uint64_t), cts.size()));
+            check(sb200_upload_rows(ctx_, destination.d_, rows.data(), destination.words_per_ciphertext() * sizeof(std::uint64_t), count));
         }
         void owned(const CiphertextBatch &b) const
         {
@@ -1326,9 +1342,11 @@ namespace seal_b200
         }
         // result slab of a layout-changing operation; adopt() swaps it with the operand's storage, so a chain of operations
         // allocates nothing once the largest shape has been seen.  Caller holds mu_.
-        std::uint64_t *out_slab(std::size_t words) const
+        // (never smaller than the slab it will be swapped with: every buffer in circulation then fits every level of a chain,
+        // and a later upload into the same batch object finds room without reallocating)
+        std::uint64_t *out_slab(std::size_t words, const CiphertextBatch &operand) const
         {
-            reserve(tmp_, words);
+            reserve(tmp_, std::max(words, operand.cap_));
             return tmp_.d_;
         }
         void adopt(CiphertextBatch &b) const
@@ -1368,7 +1386,7 @@ namespace seal_b200
             if ((rescale || ckks) && !scale_within_bounds(scale, *next))
                 throw std::invalid_argument("scale out of bounds"); // :1236-1241, mod_switch_drop_to_next :1318-1322
             std::lock_guard<std::mutex> lock(mu_);
-            std::uint64_t *out = out_slab(e.batch_ * e.size_ * (e.L_ - 1) * e.n_);
+            std::uint64_t *out = out_slab(e.batch_ * e.size_ * (e.L_ - 1) * e.n_, e);
             check(rescale ? sb200_rescale_to_next_sized(ctx_, e.L_, e.size_, e.batch_, e.d_, out, nullptr)
                           : sb200_mod_switch_to_next_sized(ctx_, e.L_, e.size_, e.batch_, e.d_, out, nullptr));
             adopt(e);

@@ -1083,3 +1083,113 @@ int orc_bgv_decrypt(const orc_ctx *c, size_t L, size_t size, u64 correction_fact
     free(phase);
     return 0;
 }
+
+
+/* ---- seed-compressed ciphertexts --------------------------------------------------------------------------------------
+ * BLAKE2b / BLAKE2Xb restated from RFC 7693 and the BLAKE2X specification (the reference vendors the BLAKE2 team's
+ * reference code as util/blake2b.c, util/blake2xb.c); parameter block layout: digest_length, key_length, fanout, depth,
+ * leaf_length (4), node_offset (4), xof_length (4), node_depth, inner_length, reserved (14), salt (16), personal (16). */
+static const uint64_t b2_iv[8] = { 0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                                   0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL };
+static const unsigned char b2_sigma[10][16] = {
+    { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15 }, { 14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3 },
+    { 11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4 }, { 7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8 },
+    { 9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13 }, { 2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9 },
+    { 12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11 }, { 13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10 },
+    { 6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5 }, { 10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0 }
+};
+static uint64_t b2_rotr(uint64_t v, int s)
+{
+    return (v >> s) | (v << (64 - s));
+}
+static void b2_compress(uint64_t h[8], const uint64_t m[16], uint64_t t, int last)
+{
+    uint64_t v[16];
+    for (int i = 0; i < 8; i++)
+        v[i] = h[i], v[i + 8] = b2_iv[i];
+    v[12] ^= t;
+    if (last)
+        v[14] = ~v[14];
+    for (int r = 0; r < 12; r++)
+    {
+        const unsigned char *s = b2_sigma[r % 10];
+        static const int idx[8][4] = { { 0, 4, 8, 12 }, { 1, 5, 9, 13 }, { 2, 6, 10, 14 }, { 3, 7, 11, 15 },
+                                       { 0, 5, 10, 15 }, { 1, 6, 11, 12 }, { 2, 7, 8, 13 }, { 3, 4, 9, 14 } };
+        for (int g = 0; g < 8; g++)
+        {
+            const int a = idx[g][0], b = idx[g][1], c = idx[g][2], d = idx[g][3];
+            v[a] += v[b] + m[s[2 * g]], v[d] = b2_rotr(v[d] ^ v[a], 32);
+            v[c] += v[d], v[b] = b2_rotr(v[b] ^ v[c], 24);
+            v[a] += v[b] + m[s[2 * g + 1]], v[d] = b2_rotr(v[d] ^ v[a], 16);
+            v[c] += v[d], v[b] = b2_rotr(v[b] ^ v[c], 63);
+        }
+    }
+    for (int i = 0; i < 8; i++)
+        h[i] ^= v[i] ^ v[i + 8];
+}
+/* one PRNG buffer: 4096 bytes = BLAKE2Xb(in = counter, key = seed) (randomgen.cpp:204-214, util/blake2xb.c) */
+static void b2x_buffer(const uint64_t seed[8], uint64_t counter, uint64_t out[512])
+{
+    uint64_t h[8], m[16];
+    for (int i = 0; i < 8; i++)
+        h[i] = b2_iv[i];
+    h[0] ^= 64ULL | (64ULL << 8) | (1ULL << 16) | (1ULL << 24); /* digest 64, key 64, fanout 1, depth 1 */
+    h[1] ^= 4096ULL << 32;                                       /* node_offset 0, xof_length 4096 */
+    for (int i = 0; i < 8; i++)
+        m[i] = seed[i], m[i + 8] = 0;
+    b2_compress(h, m, 128, 0); /* the key block */
+    memset(m, 0, sizeof(m));
+    m[0] = counter;
+    b2_compress(h, m, 136, 1); /* the 8-byte message */
+    for (uint64_t node = 0; node < 64; node++)
+    {
+        uint64_t o[8];
+        for (int i = 0; i < 8; i++)
+            o[i] = b2_iv[i], m[i] = h[i], m[i + 8] = 0;
+        o[0] ^= 64ULL | (64ULL << 32);   /* digest 64, key 0, fanout 0, depth 0, leaf_length 64 */
+        o[1] ^= node | (4096ULL << 32);  /* node_offset, xof_length */
+        o[2] ^= 64ULL << 8;              /* node_depth 0, inner_length 64 */
+        b2_compress(o, m, 64, 1);
+        memcpy(out + 8 * node, o, 64);
+    }
+}
+void orc_blake2xb_stream(const uint64_t seed[8], size_t words, uint64_t *out)
+{
+    uint64_t buf[512];
+    for (size_t w = 0, counter = 0; w < words; counter++)
+    {
+        b2x_buffer(seed, counter, buf);
+        const size_t take = words - w < 512 ? words - w : 512;
+        memcpy(out + w, buf, take * 8);
+        w += take;
+    }
+}
+void orc_expand_seed(const orc_ctx *c, size_t L, const uint64_t seed[8], uint64_t *out)
+{
+    /* util/rlwe.cpp:104-132: fill all L*n words from the stream, then replace every word >= max_multiple of its prime, in
+       coefficient order, by further words of the same stream; reduce modulo the prime */
+    const size_t n = c->n, need = L * n;
+    uint64_t buf[512];
+    size_t counter = 0, head = 512;
+    for (size_t i = 0; i < need; i++)
+    {
+        if (head == 512)
+            b2x_buffer(seed, counter++, buf), head = 0;
+        out[i] = buf[head++];
+    }
+    for (size_t j = 0; j < L; j++)
+    {
+        const uint64_t q = c->q[j], max_random = ~0ULL, max_multiple = max_random - max_random % q - 1;
+        for (size_t i = 0; i < n; i++)
+        {
+            uint64_t r = out[j * n + i];
+            while (r >= max_multiple)
+            {
+                if (head == 512)
+                    b2x_buffer(seed, counter++, buf), head = 0;
+                r = buf[head++];
+            }
+            out[j * n + i] = r % q;
+        }
+    }
+}

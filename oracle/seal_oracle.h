@@ -92,6 +92,12 @@ void orc_decrypt_phase(const orc_ctx *c, size_t L, size_t size, int ct_is_ntt, c
 int orc_bfv_decrypt(const orc_ctx *c, size_t L, size_t size, const uint64_t *ct, const uint64_t *sk, uint64_t *plain);                 /* :111-135, rns.cpp:1133-1191 */
 int orc_bgv_decrypt(const orc_ctx *c, size_t L, size_t size, uint64_t correction_factor, const uint64_t *ct, const uint64_t *sk, uint64_t *plain); /* :159-197, rns.cpp:466-539 */
 
+/* seed-compressed ciphertexts: Ciphertext::expand_seed (ciphertext.cpp:118-150) = sample_poly_uniform (util/rlwe.cpp:104-132) on a
+ * Blake2xbPRNG (randomgen.cpp:204-214: buffer b = BLAKE2Xb(4096 bytes, in = counter b, key = the 64-byte seed), util/blake2xb.c).
+ * seed = prng_seed_type (8 words); out = the polynomial [L][n] the seed expands into at the level with L primes */
+void orc_blake2xb_stream(const uint64_t seed[8], size_t words, uint64_t *out); /* the first `words` 64-bit words of the PRNG's output */
+void orc_expand_seed(const orc_ctx *c, size_t L, const uint64_t seed[8], uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

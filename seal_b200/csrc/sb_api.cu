@@ -340,33 +340,45 @@ namespace
         for (auto &x : th)
             x.join();
     }
-    void ensure_pin(Context &c, size_t bytes)
+    void ensure_lane(Context &c, IoArena::Lane &ln, size_t bytes)
     {
-        IoArena &io = c.io;
-        if (io.pin_cap >= bytes)
+        if (!ln.st)
+        {
+            cuda_check(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_check(cudaEventCreateWithFlags(&ln.order, cudaEventDisableTiming), "cudaEventCreate");
+            for (int i = 0; i < 2; i++)
+                cuda_check(cudaEventCreateWithFlags(&ln.ev[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        if (ln.cap >= bytes)
             return;
         for (int i = 0; i < 2; i++)
         {
-            cudaFreeHost(io.pin[i]);
-            io.pin[i] = nullptr;
+            cudaFreeHost(ln.pin[i]);
+            ln.pin[i] = nullptr;
         }
-        io.pin_cap = 0;
+        ln.cap = 0;
         for (int i = 0; i < 2; i++)
-        {
-            cuda_check(cudaHostAlloc(&io.pin[i], bytes, cudaHostAllocDefault), "cudaHostAlloc(staging)");
-            if (!io.pin_ev[i])
-                cuda_check(cudaEventCreateWithFlags(&io.pin_ev[i], cudaEventDisableTiming), "cudaEventCreate");
-        }
-        io.pin_cap = bytes;
+            cuda_check(cudaHostAlloc(&ln.pin[i], bytes, cudaHostAllocDefault), "cudaHostAlloc(staging)");
+        ln.cap = bytes;
     }
+    // The copies run on the lane's own non-blocking stream: they overlap kernels of other batches.  Ordering with the caller's
+    // work: a download first waits for everything the legacy default stream has been given so far (the batch operations of the
+    // C++ shim enqueue there); an upload returns when the data has arrived, so whatever the caller enqueues next sees it.
     void rows_transfer(Context &c, bool upload, uint64_t *dev, const uint64_t *const *rows, size_t row_bytes, size_t count)
     {
         if (!count || !row_bytes)
             return;
+        IoArena::Lane &ln = c.io.lane[upload ? 0 : 1];
+        std::lock_guard<std::mutex> lock(ln.mu);
+        cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
         const size_t per = std::max<size_t>(1, (size_t(128) << 20) / row_bytes), stage_bytes = std::min(per, count) * row_bytes;
-        ensure_pin(c, stage_bytes);
-        IoArena &io = c.io;
-        cudaStream_t st = nullptr; // legacy default stream: ordered with the caller's default-stream work
+        ensure_lane(c, ln, stage_bytes);
+        cudaStream_t st = ln.st;
+        if (!upload)
+        {
+            cuda_check(cudaEventRecord(ln.order, nullptr), "record");
+            cuda_check(cudaStreamWaitEvent(st, ln.order, 0), "wait");
+        }
         uint8_t *d = reinterpret_cast<uint8_t *>(dev);
         size_t i = 0, pend[2] = { 0, 0 }, pend_n[2] = { 0, 0 };
         bool used[2] = { false, false };
@@ -374,10 +386,10 @@ namespace
         {
             const size_t r1 = std::min(count, r0 + per);
             const int slot = static_cast<int>(i & 1);
-            uint8_t *stage = static_cast<uint8_t *>(io.pin[slot]);
+            uint8_t *stage = static_cast<uint8_t *>(ln.pin[slot]);
             if (used[slot])
             {
-                cuda_check(cudaEventSynchronize(io.pin_ev[slot]), "cudaEventSynchronize");
+                cuda_check(cudaEventSynchronize(ln.ev[slot]), "cudaEventSynchronize");
                 if (!upload)
                     rows_copy(false, stage, rows, row_bytes, pend[slot], pend[slot] + pend_n[slot]);
             }
@@ -388,16 +400,16 @@ namespace
             }
             else
                 cuda_check(cudaMemcpyAsync(stage, d + r0 * row_bytes, (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, st), "D2H");
-            cuda_check(cudaEventRecord(io.pin_ev[slot], st), "record");
+            cuda_check(cudaEventRecord(ln.ev[slot], st), "record");
             used[slot] = true, pend[slot] = r0, pend_n[slot] = r1 - r0;
         }
         // drain in submission order
         for (size_t j = (i >= 2 ? i - 2 : 0); j < i; j++)
         {
             const int slot = static_cast<int>(j & 1);
-            cuda_check(cudaEventSynchronize(io.pin_ev[slot]), "cudaEventSynchronize");
+            cuda_check(cudaEventSynchronize(ln.ev[slot]), "cudaEventSynchronize");
             if (!upload)
-                rows_copy(false, static_cast<uint8_t *>(io.pin[slot]), rows, row_bytes, pend[slot], pend[slot] + pend_n[slot]);
+                rows_copy(false, static_cast<uint8_t *>(ln.pin[slot]), rows, row_bytes, pend[slot], pend[slot] + pend_n[slot]);
         }
     }
 } // namespace
@@ -408,10 +420,7 @@ int sb200_upload_rows(sb200_context *ctx, uint64_t *d_dst, const uint64_t *const
     SB_NEED(h_rows);
     SB_TRY
     SB_NEED(ctx);
-    Context &c = *ctx->c;
-    std::lock_guard<std::mutex> lock(c.mu);
-    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-    rows_transfer(c, true, d_dst, h_rows, row_bytes, count);
+    rows_transfer(*ctx->c, true, d_dst, h_rows, row_bytes, count);
     return SB200_OK;
     SB_CATCH
 }
@@ -421,10 +430,7 @@ int sb200_download_rows(sb200_context *ctx, uint64_t *const *h_rows, const uint6
     SB_NEED(h_rows);
     SB_TRY
     SB_NEED(ctx);
-    Context &c = *ctx->c;
-    std::lock_guard<std::mutex> lock(c.mu);
-    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-    rows_transfer(c, false, const_cast<uint64_t *>(d_src), h_rows, row_bytes, count);
+    rows_transfer(*ctx->c, false, const_cast<uint64_t *>(d_src), h_rows, row_bytes, count);
     return SB200_OK;
     SB_CATCH
 }
@@ -565,7 +571,6 @@ int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t d
     // keep its 128-bit sums in range
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr))
         throw std::invalid_argument("kswitch key data is not valid for encryption parameters");
-    key_finalize(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -600,7 +605,6 @@ int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len
     h->k.digits = digits;
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr)) // KSwitchKeys::load ends in is_valid_for (kswitchkeys.cpp:149-153)
         throw std::logic_error("KSwitchKeys data is invalid");
-    key_finalize(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -1345,20 +1349,31 @@ int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const
     check_level(c, L, batch);
     auto st = static_cast<cudaStream_t>(stream);
     const size_t words = size * L * c.n;
+    std::vector<u64> seeds;            // seeded members: 8 words each
+    std::vector<long long> seed_dst;   // word offset of their second polynomial in d_out
     for (size_t b = 0; b < batch; b++)
     {
         sb200_ct_info info;
         sbw::inspect(streams[b], lens[b], info);
-        if (info.seeded)
-            throw std::logic_error("seeded ciphertexts must be expanded by the reference (Ciphertext::load) first");
+        if (info.seeded == 2)
+            throw std::logic_error("unsupported prng_type"); // shake256 streams stay with the reference (ciphertext.cpp:124-128)
         // is_metadata_valid_for (ciphertext.cpp:299-302): the stream must belong to this context at the level asked for
         if (info.poly_modulus_degree != c.n || info.coeff_modulus_size != L || info.size != size ||
             std::memcmp(info.parms_id, c.parms_ids[L - 1].data(), sizeof(info.parms_id)) != 0)
             throw std::logic_error("ciphertext data is invalid");
         if (infos)
             infos[b] = info;
-        cuda_check(cudaMemcpyAsync(d_out + b * words, streams[b] + info.data_offset, words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+        cuda_check(cudaMemcpyAsync(d_out + b * words, streams[b] + info.data_offset, info.data_words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+        if (info.seeded)
+        {
+            u64 sd[8];
+            std::memcpy(sd, streams[b] + info.seed_offset, sizeof(sd));
+            seeds.insert(seeds.end(), sd, sd + 8);
+            seed_dst.push_back(static_cast<long long>(b * words + L * c.n));
+        }
     }
+    if (!seed_dst.empty())
+        op_expand_seeded(c, L, seed_dst.size(), seeds.data(), seed_dst.data(), reinterpret_cast<u64 *>(d_out), st); // Ciphertext::expand_seed
     if (validate && !op_residues_in_range(c, L, batch * size * L, reinterpret_cast<const u64 *>(d_out), st))
         throw std::logic_error("ciphertext data is invalid"); // Ciphertext::load -> is_valid_for (ciphertext.h:640-655)
     return SB200_OK;

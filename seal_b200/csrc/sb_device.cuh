@@ -30,9 +30,6 @@ struct PrimeDev
     Tw inv_n_w;     // n^-1 * (last inverse-stage twiddle) mod q
     const Tw *fwd;  // fwd[m + i]: forward stage with m groups, group i  (psi powers, bit-reversed order)
     const Tw *inv;  // inv[m + i]: inverse stage with m groups, group i  (psi^-1 powers)
-    // q = 2^bits - dsol: every prime CoeffModulus::Create / get_primes makes has this shape with a small dsol
-    // (util/numth.cpp:278-311: 2^bits - c * 2n + 1); dsol == 0 marks a prime without it (no Solinas folding)
-    unsigned bits, dsol;
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 q)
@@ -57,11 +54,12 @@ __device__ __forceinline__ void unpack64(u64 v, unsigned &lo, unsigned &hi)
 {
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
 }
-// written so that ptxas keeps the sum of the two 32-bit high halves in ONE three-input 64-bit add (IADD3 with two carry outputs +
-// IADD3.X) on the integer ALU instead of materialising the carry (SEL) and adding it on the multiply pipe (IMAD.X)
+// written so that the two 32-bit high halves are added to the low word of y1*wq1 in ONE three-input add with two carry outputs and
+// the carries enter the high word in one IADD3.X: no zero-extended register pair, no carry materialised with SEL, nothing on
+// the multiply pipe besides the three wide products (tools/bfly2.cu, tools/sass_cost.py)
 __device__ __forceinline__ u64 approx_mulhi(u64 y, u64 wq)
 {
-    unsigned y0, y1, wq0, wq1, alo, ahi, blo, bhi;
+    unsigned y0, y1, wq0, wq1, alo, ahi, blo, bhi, tl, th;
     unpack64(y, y0, y1);
     unpack64(wq, wq0, wq1);
     u64 a, b, T;
@@ -71,7 +69,9 @@ __device__ __forceinline__ u64 approx_mulhi(u64 y, u64 wq)
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(T) : "r"(y1), "r"(wq1));
     unpack64(a, alo, ahi);
     unpack64(b, blo, bhi);
-    return T + static_cast<u64>(ahi) + static_cast<u64>(bhi);
+    unpack64(T, tl, th);
+    const u64 s = static_cast<u64>(tl) + ahi + bhi; // < 3 * 2^32
+    return pack64(static_cast<unsigned>(s), th + static_cast<unsigned>(s >> 32));
 }
 // lo64(y*w + T*nq)
 __device__ __forceinline__ u64 mullo_combine(u64 y, u64 w, u64 T, u64 nq)
@@ -151,50 +151,34 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b)
     asm("mad.lo.cc.u64 %0, %2, %3, %0;\n\tmadc.hi.u64 %1, %2, %3, %1;" : "+l"(lo), "+l"(hi) : "l"(a), "l"(b));
 }
 
-// ---- key multiply-accumulate on 28-bit limbs (fused key-switch kernel) ------------------------------------------------
-// A carry-chained 128-bit multiply-accumulate costs ~7 wide multiplies + ~10 adds as ptxas expands it.  For primes
-// q = 2^bits - dsol below 2^56 the transformed digit is first folded below 2^56 (Solinas: x = (x mod 2^bits) + (x >> bits) * dsol,
-// one wide multiply), split into 28-bit limbs a = a1*2^28 + a0, and multiplied with the key word kept in the same limb form
-// k = k1*2^28 + k0 (encoded once at key upload) Karatsuba-style into three plain 64-bit column sums without any carry:
-//     S0 += a0*k0      S2 += a1*k1      S1 += (a0+a1)*(k0+k1)          (each product < 2^58; up to 60 digits per sum)
-// and the 128-bit value S0 + (S1 - S0 - S2)*2^28 + S2*2^56 is formed once at the end: 3 wide multiplies per product.
-__device__ __forceinline__ u64 fold_solinas(u64 a, unsigned bits, unsigned dsol)
+// (hi:lo) += a*b for bounded operands (a < 2^63.25, b < 2^62: lazily grown transform outputs times canonical key words): four
+// wide multiplies -- p0 = a0*b0, mid = a0*b1 + a1*b0 (fits 64 bits under the bounds), p3 = a1*b1 -- and two carry chains over the
+// four 32-bit words of the sum.  ptxas expands the generic mac128 into 5-7 wide multiplies and ~10 adds per product.
+__device__ __forceinline__ void mac128_4(u64 &lo, u64 &hi, u64 a, u64 b)
 {
-    const u64 low = a & ((1ull << bits) - 1ull);
-    return low + static_cast<u64>(static_cast<unsigned>(a >> bits)) * dsol;
-}
-__device__ __forceinline__ u64 limb28_encode(u64 k)
-{
-    return (k & 0x0FFFFFFFull) | ((k >> 28) << 32);
-}
-__device__ __forceinline__ u64 limb28_decode(u64 e)
-{
-    return (e & 0xFFFFFFFFull) | ((e >> 32) << 28);
-}
-struct Acc3
-{
-    u64 s0, s1, s2;
-};
-// a0, a1, as = a0 + a1 of the folded digit; ke = limb-encoded key word
-__device__ __forceinline__ void mac_limb28(Acc3 &s, unsigned a0, unsigned a1, unsigned as, u64 ke)
-{
-    unsigned k0, k1;
-    unpack64(ke, k0, k1);
-    const unsigned ks = k0 + k1;
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s0) : "r"(a0), "r"(k0));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s2) : "r"(a1), "r"(k1));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s1) : "r"(as), "r"(ks));
-}
-__device__ __forceinline__ void acc3_value(const Acc3 &s, u64 &lo, u64 &hi)
-{
-    const u64 mid = s.s1 - s.s0 - s.s2; // sum of a0*k1 + a1*k0, < 2^63
-    // s0 + mid * 2^28 + s2 * 2^56
-    u64 l = s.s0, h = 0, t;
-    t = mid << 28;
-    l += t, h += (mid >> 36) + (l < t);
-    t = s.s2 << 56;
-    l += t, h += (s.s2 >> 8) + (l < t);
-    lo = l, hi = h;
+    unsigned a0, a1, b0, b1, w0, w1, w2, w3, p00, p01, m0, m1, p30, p31;
+    unpack64(a, a0, a1);
+    unpack64(b, b0, b1);
+    unpack64(lo, w0, w1);
+    unpack64(hi, w2, w3);
+    u64 p0, mid, p3;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(a0), "r"(b0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(mid) : "r"(a0), "r"(b1));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(mid) : "r"(a1), "r"(b0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p3) : "r"(a1), "r"(b1));
+    unpack64(p0, p00, p01);
+    unpack64(mid, m0, m1);
+    unpack64(p3, p30, p31);
+    asm("add.cc.u32 %0, %0, %4;\n\t"
+        "addc.cc.u32 %1, %1, %5;\n\t"
+        "addc.cc.u32 %2, %2, %6;\n\t"
+        "addc.u32 %3, %3, %7;\n\t"
+        "add.cc.u32 %1, %1, %8;\n\t"
+        "addc.cc.u32 %2, %2, %9;\n\t"
+        "addc.u32 %3, %3, 0;"
+        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3)
+        : "r"(p00), "r"(p01), "r"(p30), "r"(p31), "r"(m0), "r"(m1));
+    lo = pack64(w0, w1), hi = pack64(w2, w3);
 }
 
 // Harvey-style butterflies on lazily reduced values.

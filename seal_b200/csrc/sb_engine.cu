@@ -51,11 +51,18 @@ namespace sb
         for (auto &slot : io.buf)
             for (auto p : slot)
                 cudaFree(p);
-        for (int i = 0; i < 2; i++)
+        for (auto &ln : io.lane)
         {
-            cudaFreeHost(io.pin[i]);
-            if (io.pin_ev[i])
-                cudaEventDestroy(io.pin_ev[i]);
+            for (int i = 0; i < 2; i++)
+            {
+                cudaFreeHost(ln.pin[i]);
+                if (ln.ev[i])
+                    cudaEventDestroy(ln.ev[i]);
+            }
+            if (ln.order)
+                cudaEventDestroy(ln.order);
+            if (ln.st)
+                cudaStreamDestroy(ln.st);
         }
         if (io.ready)
         {
@@ -141,9 +148,6 @@ namespace sb
         d.inv_n_w = to_tw(pt.inv_n_w);
         d.fwd = f;
         d.inv = i;
-        d.bits = 64u - static_cast<unsigned>(__builtin_clzll(pt.q));
-        const u64 dsol = (d.bits < 64 ? (1ull << d.bits) : 0ull) - pt.q;
-        d.dsol = dsol < (1ull << 31) ? static_cast<unsigned>(dsol) : 0u;
         hp.push_back(d);
     }
 
@@ -230,16 +234,6 @@ namespace sb
             upload_prime(*c, c->tabs[i], hp);
         }
         c->nprimes = hp.size();
-        // 28-bit-limb key multiply-accumulate (sb_device.cuh): every key-level prime must fold below 2^56 and the three column
-        // sums must hold all digits
-        c->limb_mac = k >= 2 && k - 1 <= 60 && !std::getenv("SB200_NO_LIMB_MAC"); // the env switch exists for A/B runs and the parity test
-        for (size_t i = 0; i < k && c->limb_mac; i++)
-        {
-            const PrimeDev &d = hp[i];
-            const unsigned __int128 folded = (static_cast<unsigned __int128>(1) << d.bits) + ((static_cast<unsigned __int128>(d.dsol) << (64 - d.bits)));
-            if (!d.dsol || d.bits < 32 || d.bits > 56 || folded >= (static_cast<unsigned __int128>(1) << 56))
-                c->limb_mac = false;
-        }
         cuda_check(cudaMalloc(&c->d_primes, hp.size() * sizeof(PrimeDev)), "cudaMalloc(primes)");
         cuda_check(cudaMemcpy(c->d_primes, hp.data(), hp.size() * sizeof(PrimeDev), cudaMemcpyHostToDevice), "upload primes");
         // q_j^-1 mod q_i (rns.cpp:767-776 for every level at once)
@@ -1282,8 +1276,7 @@ namespace sb
     // (3) multiply-accumulate with the key, 128-bit lazy sums, one Barrett at the end; evaluator.cpp:2705-2755
     //     grid = (B, n/256, L+1): consecutive CTAs share the key tile of (I, coefficient range) through L2.
     __global__ void __launch_bounds__(256) ks_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
-                                                          u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
-                                                          int limb28)
+                                                          u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k)
     {
         const int n = 1 << logn;
         const int b = blockIdx.x, I = blockIdx.z;
@@ -1298,11 +1291,8 @@ namespace sb
         {
             u64 x = (ntt_in && I == J) ? tgt.get(b, J, idx, P.q) : e[static_cast<long long>(J) << logn];
             const u64 *kr = key + ((static_cast<long long>(J) * 2 * k + ki) << logn) + idx;
-            u64 w0 = __ldg(kr), w1 = __ldg(kr + (static_cast<long long>(k) << logn));
-            if (limb28)
-                w0 = limb28_decode(w0), w1 = limb28_decode(w1);
-            mac128(lo0, hi0, x, w0);
-            mac128(lo1, hi1, x, w1);
+            mac128(lo0, hi0, x, __ldg(kr));
+            mac128(lo1, hi1, x, __ldg(kr + (static_cast<long long>(k) << logn)));
         }
         u64 *o = Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + idx;
         o[0] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
@@ -1403,29 +1393,27 @@ namespace sb
     //     over the digits J inside the kernel so the transformed digits never reach memory and the 128-bit sums live in
     //     registers.  One warp owns one 256-coefficient block of one (ciphertext b, output prime I); a CTA = 8 adjacent
     //     blocks.  blockIdx.x = b + B * block_group: consecutive CTAs share the key tile of (I, block group) through L2.
-    // LIMB: the key words are limb-encoded and the sums are the three Karatsuba columns of sb_device.cuh (mac_limb28); otherwise
-    // plain 128-bit carry-chain sums.  Component 0 accumulates in registers, component 1 in shared memory.
-    template <bool FAST, bool LIMB>
+    // Component 0 accumulates in registers, component 1 in shared memory (128-bit carry-chain sums).
     struct KsMacSmem
     {
         static constexpr size_t xs = 8 * 256 * sizeof(u64);
-        static constexpr size_t acc = LIMB ? 8 * 3 * 256 * sizeof(u64) : 8 * 256 * sizeof(ulonglong2);
+        static constexpr size_t acc = 8 * 256 * sizeof(ulonglong2);
         static constexpr size_t tw = (8 * 255 + 1) * sizeof(Tw);
         static constexpr size_t total = xs + acc + tw + 16;
     };
     // PLAIN: the target is a plain slab (relinearize / multiply_relinearize); rotations read it through a Galois view.
-    template <bool FAST, bool LIMB, bool PLAIN>
+    template <bool FAST, bool PLAIN>
     __global__ void __launch_bounds__(256, SB_MAC_MIN_BLOCKS) ks_local_mac_kernel(const u64 *__restrict__ E, Src tgt, int ntt_in, const u64 *__restrict__ key,
                                                                    u64 *__restrict__ Pp, const PrimeDev *__restrict__ primes, int logn, int L, int k,
                                                                    int B)
     {
-        // dynamic shared memory: [xs 8x256 u64 | component-1 sums | twiddles 8*255 x 16 B | mbarrier]
+        // dynamic shared memory: [xs 8x256 u64 | component-1 sums 8x256 x 16 B | twiddles 8*255 x 16 B | mbarrier]
         extern __shared__ __align__(16) unsigned char ks_smem[];
-        using SM = KsMacSmem<FAST, LIMB>;
+        using SM = KsMacSmem;
         u64(*xs)[256] = reinterpret_cast<u64(*)[256]>(ks_smem);
-        // sums of key component 1 live in shared memory ([j][..][thread], conflict-free accesses); component 0 stays in registers
+        // 128-bit sums of key component 1 live in shared memory ([j][thread], conflict-free 16-byte accesses); component 0
+        // stays in registers
         ulonglong2(*acc1)[256] = reinterpret_cast<ulonglong2(*)[256]>(ks_smem + SM::xs);
-        u64(*acc3)[3][256] = reinterpret_cast<u64(*)[3][256]>(ks_smem + SM::xs);
         // the twiddles of this CTA's 8 blocks are the same for every digit J: staged once with 8 TMA bulk copies
         // (stage s of 8 adjacent blocks is one contiguous run of 8*2^s table entries)
         Tw *tws = reinterpret_cast<Tw *>(ks_smem + SM::xs + SM::acc);
@@ -1447,20 +1435,11 @@ namespace sb
                 tma_load_1d(tws + 8 * ((1 << st) - 1), P.fwd + ((na + bg * 8) << st), (8u << st) * sizeof(Tw), bar);
         }
         u64 s0l[8], s0h[8];
-        Acc3 c0[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
         {
-            if (LIMB)
-            {
-                c0[j] = Acc3{ 0, 0, 0 };
-                acc3[j][0][threadIdx.x] = acc3[j][1][threadIdx.x] = acc3[j][2][threadIdx.x] = 0;
-            }
-            else
-            {
-                s0l[j] = s0h[j] = 0;
-                acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
-            }
+            s0l[j] = s0h[j] = 0;
+            acc1[j][threadIdx.x] = make_ulonglong2(0, 0);
         }
         mbar_wait(bar, 0);
         auto twf = [&](int st, int i) { return tws[8 * ((1 << st) - 1) + (warp << st) + i]; };
@@ -1504,7 +1483,7 @@ namespace sb
                     for (int j = 0; j < 8; j++)
                         a[j] = csub(csub(csub(a[j], P.q4), P.q2), P.q); // keeps 256 summands below 2^128 for 60-bit primes
                 }
-                else if (!LIMB && L > 200)
+                else if (L > 200)
                 {
                     // guard-free values reach 72q < 2^63.2: more than 227 products with a 57-bit key word would overflow 128 bits
 #pragma unroll
@@ -1514,57 +1493,22 @@ namespace sb
             }
             const ulonglong2 *k0 = reinterpret_cast<const ulonglong2 *>(krow);
             const ulonglong2 *k1 = reinterpret_cast<const ulonglong2 *>(krow + kcomp);
-            if (LIMB)
+#pragma unroll
+            for (int h = 0; h < 4; h++)
             {
-                unsigned a0[8], a1[8], as[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    const u64 f = fold_solinas(a[j], P.bits, P.dsol); // < 2^56 whatever the lazy growth was
-                    a0[j] = static_cast<unsigned>(f) & 0x0FFFFFFFu;
-                    a1[j] = static_cast<unsigned>(f >> 28);
-                    as[j] = a0[j] + a1[j];
-                }
-#pragma unroll
-                for (int h = 0; h < 4; h++)
-                {
-                    ulonglong2 v = __ldg(k0 + h);
-                    mac_limb28(c0[2 * h], a0[2 * h], a1[2 * h], as[2 * h], v.x);
-                    mac_limb28(c0[2 * h + 1], a0[2 * h + 1], a1[2 * h + 1], as[2 * h + 1], v.y);
-                }
-#pragma unroll
-                for (int h = 0; h < 4; h++)
-                {
-                    ulonglong2 v = __ldg(k1 + h);
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-                    {
-                        const int j = 2 * h + e;
-                        Acc3 t{ acc3[j][0][threadIdx.x], acc3[j][1][threadIdx.x], acc3[j][2][threadIdx.x] };
-                        mac_limb28(t, a0[j], a1[j], as[j], e ? v.y : v.x);
-                        acc3[j][0][threadIdx.x] = t.s0, acc3[j][1][threadIdx.x] = t.s1, acc3[j][2][threadIdx.x] = t.s2;
-                    }
-                }
+                ulonglong2 v = __ldg(k0 + h);
+                mac128_4(s0l[2 * h], s0h[2 * h], a[2 * h], v.x);
+                mac128_4(s0l[2 * h + 1], s0h[2 * h + 1], a[2 * h + 1], v.y);
             }
-            else
+#pragma unroll
+            for (int h = 0; h < 4; h++)
             {
-#pragma unroll
-                for (int h = 0; h < 4; h++)
-                {
-                    ulonglong2 v = __ldg(k0 + h);
-                    mac128(s0l[2 * h], s0h[2 * h], a[2 * h], v.x);
-                    mac128(s0l[2 * h + 1], s0h[2 * h + 1], a[2 * h + 1], v.y);
-                }
-#pragma unroll
-                for (int h = 0; h < 4; h++)
-                {
-                    ulonglong2 v = __ldg(k1 + h);
-                    ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
-                    mac128(t0.x, t0.y, a[2 * h], v.x);
-                    mac128(t1.x, t1.y, a[2 * h + 1], v.y);
-                    acc1[2 * h][threadIdx.x] = t0;
-                    acc1[2 * h + 1][threadIdx.x] = t1;
-                }
+                ulonglong2 v = __ldg(k1 + h);
+                ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
+                mac128_4(t0.x, t0.y, a[2 * h], v.x);
+                mac128_4(t1.x, t1.y, a[2 * h + 1], v.y);
+                acc1[2 * h][threadIdx.x] = t0;
+                acc1[2 * h + 1][threadIdx.x] = t1;
             }
         }
         ulonglong2 *o0 = reinterpret_cast<ulonglong2 *>(Pp + (((static_cast<long long>(b) * 2) * (L + 1) + I) << logn) + e0);
@@ -1572,52 +1516,11 @@ namespace sb
 #pragma unroll
         for (int h = 0; h < 4; h++)
         {
-            u64 r0[2], r1[2];
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-            {
-                const int j = 2 * h + e;
-                u64 lo0, hi0, lo1, hi1;
-                if (LIMB)
-                {
-                    acc3_value(c0[j], lo0, hi0);
-                    acc3_value(Acc3{ acc3[j][0][threadIdx.x], acc3[j][1][threadIdx.x], acc3[j][2][threadIdx.x] }, lo1, hi1);
-                }
-                else
-                {
-                    lo0 = s0l[j], hi0 = s0h[j];
-                    const ulonglong2 t = acc1[j][threadIdx.x];
-                    lo1 = t.x, hi1 = t.y;
-                }
-                r0[e] = barrett128(lo0, hi0, P.q, P.ratio_lo, P.ratio_hi);
-                r1[e] = barrett128(lo1, hi1, P.q, P.ratio_lo, P.ratio_hi);
-            }
-            o0[h] = make_ulonglong2(r0[0], r0[1]);
-            o1[h] = make_ulonglong2(r1[0], r1[1]);
+            o0[h] = make_ulonglong2(barrett128(s0l[2 * h], s0h[2 * h], P.q, P.ratio_lo, P.ratio_hi),
+                                    barrett128(s0l[2 * h + 1], s0h[2 * h + 1], P.q, P.ratio_lo, P.ratio_hi));
+            ulonglong2 t0 = acc1[2 * h][threadIdx.x], t1 = acc1[2 * h + 1][threadIdx.x];
+            o1[h] = make_ulonglong2(barrett128(t0.x, t0.y, P.q, P.ratio_lo, P.ratio_hi), barrett128(t1.x, t1.y, P.q, P.ratio_lo, P.ratio_hi));
         }
-    }
-
-    // re-encodes uploaded key words as two 28-bit limbs (sb_device.cuh: limb28_encode)
-    __global__ void __launch_bounds__(256) key_limb_encode_kernel(u64 *__restrict__ d, long long total)
-    {
-        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-        if (e < total)
-            d[e] = limb28_encode(d[e]);
-    }
-    void key_finalize(Context &c, KSwitchKey &key, cudaStream_t st)
-    {
-        if (!c.limb_mac || key.limb28)
-            return;
-        const long long total = static_cast<long long>(key.digits) * 2 * c.k * c.n;
-        const long long step = 1LL << 30;
-        for (long long e0 = 0; e0 < total; e0 += step)
-        {
-            const long long cnt = std::min(step, total - e0);
-            key_limb_encode_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(key.d_key + e0, cnt);
-            cuda_check(cudaGetLastError(), "key_limb_encode_kernel");
-        }
-        cuda_check(cudaStreamSynchronize(st), "synchronize");
-        key.limb28 = true;
     }
 
     // (4a) special-prime component back to coefficients, + floor(q_sp/2) for rounding; evaluator.cpp:2809-2817.
@@ -1854,8 +1757,8 @@ namespace sb
     {
         size_t per = ks_words_per_ct(c, L, need_c2) * sizeof(u64);
         size_t chunk = std::max<size_t>(1, c.scratch_budget / per);
-        // keep row counts of a launch inside int range
-        chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 30) / ((L + 1) * L * c.n)));
+        // keep the row counts of a launch (B * (L+1) * L digit rows) far inside int range; element offsets are 64-bit everywhere
+        chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 22) / ((L + 1) * L)));
         chunk = std::min<size_t>(chunk, 32768);
         chunk = std::min<size_t>(chunk, 65535 / (L + 1)); // (b, I) pairs ride in gridDim.y of the key-switch kernels
         if (c.ks_chunk_max)
@@ -1900,19 +1803,16 @@ namespace sb
         for (int j = 0; j < 8; j++)
             d[(static_cast<long long>(blockIdx.x) * 8 + j) * THREADS + threadIdx.x] = a[j];
     }
-    template <bool LIMB>
     __global__ void __launch_bounds__(256, 2) selftest_mac_kernel(u64 *d, const PrimeDev *__restrict__ primes, int rounds)
     {
         const PrimeDev P = primes[0];
         u64 a[8], kw[8], lo[8], hi[8];
-        Acc3 s[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
         {
             a[j] = d[(static_cast<long long>(blockIdx.x) * 8 + j) * 256 + threadIdx.x];
-            kw[j] = LIMB ? limb28_encode(a[j] % P.q) : a[j] % P.q;
+            kw[j] = a[j] % P.q;
             lo[j] = hi[j] = 0;
-            s[j] = Acc3{ 0, 0, 0 };
         }
         for (int r = 0; r < rounds; r++)
         {
@@ -1920,38 +1820,13 @@ namespace sb
             for (int j = 0; j < 8; j++)
             {
                 const u64 x = a[j] + r; // operands change every round so that nothing is hoisted
-                if (LIMB)
-                {
-                    const u64 f = fold_solinas(x, P.bits, P.dsol);
-                    const unsigned a0 = static_cast<unsigned>(f) & 0x0FFFFFFFu, a1 = static_cast<unsigned>(f >> 28);
-                    mac_limb28(s[j], a0, a1, a0 + a1, kw[j]);
-                    mac_limb28(s[(j + 1) & 7], a0, a1, a0 + a1, kw[(j + 3) & 7]);
-                }
-                else
-                {
-                    mac128(lo[j], hi[j], x, kw[j]);
-                    mac128(lo[(j + 1) & 7], hi[(j + 1) & 7], x, kw[(j + 3) & 7]);
-                }
-            }
-            if (LIMB && (r & 31) == 31)
-            {
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    u64 l, h;
-                    acc3_value(s[j], l, h);
-                    s[j] = Acc3{ barrett128(l, h, P.q, P.ratio_lo, P.ratio_hi), 0, 0 }; // keep the column sums in range
-                }
+                mac128_4(lo[j], hi[j], x >> 1, kw[j]); // the kernel's bound: transform outputs below 2^63.25
+                mac128_4(lo[(j + 1) & 7], hi[(j + 1) & 7], x >> 1, kw[(j + 3) & 7]);
             }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++)
-        {
-            u64 l = lo[j], h = hi[j];
-            if (LIMB)
-                acc3_value(s[j], l, h);
-            d[(static_cast<long long>(blockIdx.x) * 8 + j) * 256 + threadIdx.x] = l ^ h;
-        }
+            d[(static_cast<long long>(blockIdx.x) * 8 + j) * 256 + threadIdx.x] = lo[j] ^ hi[j];
     }
     double selftest_rate(Context &c, int kind, cudaStream_t st)
     {
@@ -1991,12 +1866,9 @@ namespace sb
             ops = static_cast<double>(sms) * 3 * 16 * rounds * 12.0;
             run([&] { selftest_bfly_kernel<2, 512, 3><<<sms * 3, 512, 0, st>>>(d, c.d_primes, rounds, nmask); });
             break;
-        case 3: // key multiply-accumulates of the fused kernel (the form the context uses)
+        case 3: // key multiply-accumulates of the fused kernel
             ops = static_cast<double>(sms) * 2 * 8 * rounds * 16.0;
-            if (c.limb_mac)
-                run([&] { selftest_mac_kernel<true><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds); });
-            else
-                run([&] { selftest_mac_kernel<false><<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds); });
+            run([&] { selftest_mac_kernel<<<sms * 2, 256, 0, st>>>(d, c.d_primes, rounds); });
             break;
         default: throw std::invalid_argument("unknown selftest");
         }
@@ -2086,23 +1958,17 @@ namespace sb
         {
             const int na = n >> kLocalLog;
             dim3 grid(static_cast<unsigned>(B * (na / 8)), static_cast<unsigned>(L + 1));
-            const bool limb = key.limb28; // set together with c.limb_mac (key_finalize)
             const bool plain_tgt = target.perm == nullptr && target.ginv == 0;
-            auto launch = [&](auto kern, size_t smem) {
+            auto launch = [&](auto kern) {
+                constexpr size_t smem = KsMacSmem::total;
                 cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "smem attr");
                 c.stats.begin("ks_local_mac", 0, mac_bytes, st, 0.5 * active_rows * n * kLocalLog, 2.0 * B * (L + 1) * L * n);
                 kern<<<grid, 256, smem, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki, static_cast<int>(B));
             };
-            if (limb && c.fast_q)
-                plain_tgt ? launch(ks_local_mac_kernel<true, true, true>, KsMacSmem<true, true>::total)
-                          : launch(ks_local_mac_kernel<true, true, false>, KsMacSmem<true, true>::total);
-            else if (limb)
-                throw std::logic_error("limb-encoded key without guard-free primes"); // limb_mac implies fast_q (primes below 2^56)
-            else if (c.fast_q)
-                plain_tgt ? launch(ks_local_mac_kernel<true, false, true>, KsMacSmem<true, false>::total)
-                          : launch(ks_local_mac_kernel<true, false, false>, KsMacSmem<true, false>::total);
+            if (c.fast_q)
+                plain_tgt ? launch(ks_local_mac_kernel<true, true>) : launch(ks_local_mac_kernel<true, false>);
             else
-                launch(ks_local_mac_kernel<false, false, false>, KsMacSmem<false, false>::total);
+                plain_tgt ? launch(ks_local_mac_kernel<false, true>) : launch(ks_local_mac_kernel<false, false>);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_local_mac_kernel");
         }
@@ -2111,7 +1977,7 @@ namespace sb
             int threads = std::min(n, 256);
             dim3 grid(static_cast<unsigned>(B), (n + threads - 1) / threads, static_cast<unsigned>(L + 1));
             c.stats.begin("ks_mac", 0, mac_bytes, st, 0, 2.0 * B * (L + 1) * L * n);
-            ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki, key.limb28 ? 1 : 0);
+            ks_mac_kernel<<<grid, threads, 0, st>>>(s.E, target, ntt_in ? 1 : 0, key.d_key, s.Pp, c.d_primes, c.logn, Li, ki);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks_mac_kernel");
         }

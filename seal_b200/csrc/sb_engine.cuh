@@ -34,7 +34,6 @@ namespace sb
         struct Context *ctx = nullptr;
         u64 *d_key = nullptr; // [digits][2][k][n]
         size_t digits = 0;
-        bool limb28 = false;  // words are stored as two 28-bit limbs (sb_device.cuh: limb28_encode) for the fused key-switch kernel
     };
 
     // staging for the host-buffer entry points (sb_api.cu: HostPipe)
@@ -45,17 +44,22 @@ namespace sb
         cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
         u64 *buf[2][3] = {};
         size_t cap[2][3] = {};
-        // page-locked staging of sb200_upload_rows / sb200_download_rows
-        void *pin[2] = {};
-        size_t pin_cap = 0;
-        cudaEvent_t pin_ev[2] = {};
+        // page-locked staging of sb200_upload_rows ([0]) / sb200_download_rows ([1]): separate double buffers, streams and locks,
+        // so that an upload, a download and the kernels of a third batch overlap (three host threads, or one thread per direction)
+        struct Lane
+        {
+            void *pin[2] = {};
+            size_t cap = 0;
+            cudaEvent_t ev[2] = {}, order = nullptr;
+            cudaStream_t st = nullptr;
+            std::mutex mu;
+        } lane[2];
     };
 
     struct Context
     {
         int scheme = 0, device = 0, logn = 0;
         bool fast_q = true;                  // every q prime < 2^57: guard-free forward butterflies (sb_device.cuh)
-        bool limb_mac = false;               // key multiply-accumulate on 28-bit limbs (primes 2^b - d below 2^56, <= 60 digits)
         size_t n = 0, k = 0;
         u64 t = 0;
         std::vector<u64> q;                  // key-level primes
@@ -152,8 +156,9 @@ namespace sb
     size_t keyswitch_chunk(const Context &c, size_t L, size_t batch, bool fused);
     // arithmetic ceilings measured in process: warp-level butterflies (kind 0-2) / multiply-accumulates (kind 3) per second
     double selftest_rate(Context &c, int kind, cudaStream_t st);
-    // after upload + validation: re-encode the key words for the context's multiply-accumulate (no-op unless c.limb_mac)
-    void key_finalize(Context &c, KSwitchKey &key, cudaStream_t st);
+    // Ciphertext::expand_seed on the device (sb_prng.cu): seeds [B][8] host words, dst_off [B] host word offsets into d_out of the
+    // polynomial ([L][n]) each seed expands into; returns after the expansion has been enqueued and the host arrays are free
+    void op_expand_seeded(Context &c, size_t L, size_t B, const u64 *h_seeds, const long long *h_dst_off, u64 *d_out, cudaStream_t st);
     const sbh::BehzLevel &behz_host(Context &c, size_t L);
     // wire format support (sb_api.cu): 1 if any residue of data [rows][n] (prime of a row = row % L) is >= its modulus
     bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st);

@@ -171,6 +171,22 @@ namespace sbw
             throw std::logic_error("ciphertext data is invalid");
         if (!info.seeded && kHeaderBytes + kMemberBytes + inner.size != outer.size)
             throw std::logic_error("loaded data is invalid");
+        if (info.seeded)
+        {
+            // UniformRandomGeneratorInfo::save behind its own SEALHeader: prng_type (1 byte) + prng_seed_type (64 bytes)
+            // (randomgen.cpp:95-118, ciphertext.cpp:334-338)
+            const uint8_t *g = r + 8 * count;
+            if (kHeaderBytes + kMemberBytes + inner.size + kHeaderBytes + 1 + 64 != outer.size)
+                throw std::logic_error("loaded data is invalid");
+            const Header ph = read_header(g);
+            if (ph.size != kHeaderBytes + 1 + 64)
+                throw std::logic_error("loaded data is invalid");
+            const uint8_t type = g[kHeaderBytes];
+            if (type != 1 && type != 2)
+                throw std::logic_error("prng_type is invalid"); // randomgen.cpp:132-136
+            info.seeded = type;
+            info.seed_offset = static_cast<uint64_t>(g + kHeaderBytes + 1 - p);
+        }
         info.data_offset = kDataOffset;
         info.data_words = count;
         info.stream_bytes = outer.size;

@@ -3,6 +3,8 @@
 // (CoeffModulus::BFVDefault(32768)), batch 256, chain  a <- rescale(relin(a*b)); b <- mod_switch_to_next(b)  of depth 8 -- the usage
 // pattern of native/tests/seal/evaluator.cpp:3513-3780.
 //   chain_e2e      upload(std::vector<Ciphertext>) -> 8 levels on the device -> download: wall clock, host objects in and out
+//   chain_e2e_pipelined  the same work cut into 4 slices: one host thread uploads slice k+1 and another downloads slice k-1 while the
+//                  device runs the chain of slice k (upload / download run on their own streams inside the library)
 //   chain_device   the same 8 levels with the batch already resident (upload / download outside the timed region)
 //   single_calls   the reference-signature members on one seal::Ciphertext at a time (every call moves its operands both ways)
 // One ciphertext of the batch is checked against the reference's own seal::Evaluator (linked from oracle/_ref/libseal.so).
@@ -11,7 +13,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <random>
+#include <thread>
 
 using namespace seal;
 using clk = std::chrono::steady_clock;
@@ -97,6 +101,45 @@ int main(int argc, char **argv)
         gpu.download(da, out);
         const double e2e_s = secs(t0, clk::now());
 
+        // pipelined end to end: slices of the batch flow upload -> chain -> download on three host threads
+        const size_t slices = std::min<size_t>(4, batch), per = (batch + slices - 1) / slices;
+        std::vector<seal_b200::CiphertextBatch> sa(slices), sb(slices);
+        std::vector<Ciphertext> pout(batch);
+        double pipe_s = 0;
+        for (int rep = 0; rep < 2; rep++) // the first repetition sizes the slabs of every slice
+        {
+            std::vector<std::promise<void>> up(slices), enq(slices);
+            t0 = clk::now();
+            std::thread uploader([&] {
+                for (size_t k = 0; k < slices; k++)
+                {
+                    const size_t f = k * per, c = std::min(per, batch - f);
+                    gpu.upload(a.data() + f, c, sa[k]);
+                    gpu.upload(b.data() + f, c, sb[k]);
+                    up[k].set_value();
+                }
+            });
+            std::thread downloader([&] {
+                for (size_t k = 0; k < slices; k++)
+                {
+                    enq[k].get_future().wait();
+                    gpu.download(sa[k], pout.data() + k * per);
+                }
+            });
+            for (size_t k = 0; k < slices; k++)
+            {
+                up[k].get_future().wait();
+                run_chain(sa[k], sb[k]);
+                enq[k].set_value();
+            }
+            uploader.join();
+            downloader.join();
+            pipe_s = secs(t0, clk::now());
+        }
+        bool pipe_ok = true;
+        for (size_t i = 0; i < batch; i += std::max<size_t>(1, batch / 8))
+            pipe_ok = pipe_ok && same_ct(out[i], pout[i]);
+
         // check one ciphertext of the batch against the reference evaluator (same chain)
         const size_t pick = batch - 1;
         Ciphertext ra = a[pick], rb = b[pick];
@@ -110,7 +153,7 @@ int main(int argc, char **argv)
             ra.scale() = scale, rb.scale() = scale;
         }
         const double ref_chain_s = secs(t0, clk::now());
-        const bool ok = same_ct(ra, out[pick]);
+        const bool ok = same_ct(ra, out[pick]) && same_ct(ra, pout[pick]) && pipe_ok;
 
         // the reference-signature members, one seal::Ciphertext per call (first level only): what a user gets without batches
         const size_t singles = std::min<size_t>(batch, 16);
@@ -128,12 +171,14 @@ int main(int argc, char **argv)
         std::printf("{\"harness\": \"tests/cpp/chain_bench.cpp (seal_b200::Evaluator + CiphertextBatch, C++)\", "
                     "\"config\": \"CKKS n=32768, 16 primes, batch %zu, depth-%zu chain\", "
                     "\"chain_e2e\": {\"value\": %.1f, \"unit\": \"chain steps/s\", \"seconds\": %.4f, \"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f}, "
+                    "\"chain_e2e_pipelined\": {\"value\": %.1f, \"unit\": \"chain steps/s\", \"seconds\": %.4f, \"slices\": %zu}, "
                     "\"chain_device\": {\"value\": %.1f, \"unit\": \"chain steps/s\", \"seconds\": %.4f}, "
-                    "\"e2e_over_device\": %.3f, "
+                    "\"e2e_over_device\": %.3f, \"pipelined_e2e_over_device\": %.3f, "
                     "\"single_ciphertext_calls\": {\"value\": %.1f, \"unit\": \"multiply+relinearize+rescale/s, one seal::Ciphertext per call\"}, "
                     "\"reference_cpu_one_thread\": {\"value\": %.2f, \"unit\": \"chain steps/s\"}, "
                     "\"verified\": {\"index\": %zu, \"ok\": %s, \"against\": \"seal::Evaluator of the reference, same chain\"}}\n",
-                    batch, depth, batch * depth / e2e_s, e2e_s, h2d, d2h, batch * depth / dev_s, dev_s, dev_s / e2e_s, 1.0 / single_s,
+                    batch, depth, batch * depth / e2e_s, e2e_s, h2d, d2h, batch * depth / pipe_s, pipe_s, slices, batch * depth / dev_s, dev_s,
+                    dev_s / e2e_s, dev_s / pipe_s, 1.0 / single_s,
                     depth / ref_chain_s, pick, ok ? "true" : "false");
         return ok ? 0 : 1;
     }

@@ -21,6 +21,8 @@ def lib():
             subprocess.check_call(["make", "-C", _DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
         L = C.CDLL(_LIB_PATH)
         L.orc_create.restype = C.c_void_p
+        L.orc_blake2xb_stream.argtypes = [_u64p, C.c_size_t, _u64p]
+        L.orc_expand_seed.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
         L.orc_create.argtypes = [C.c_int, C.c_size_t, _u64p, C.c_size_t, C.c_uint64]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_is_prime.argtypes = [C.c_uint64]
@@ -100,6 +102,14 @@ class Oracle:
         self.h = lib().orc_create(scheme, n, _p(m), self.k, plain_modulus)
         if not self.h:
             raise RuntimeError("orc_create failed")
+
+    def expand_seed(self, L, seed):
+        """Ciphertext::expand_seed: the polynomial [L][n] a 64-byte PRNG seed (8 words) expands into (Blake2xbPRNG)"""
+        seed = np.ascontiguousarray(seed, dtype=np.uint64)
+        assert seed.shape == (8,)
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        lib().orc_expand_seed(self.h, L, _p(seed), _p(out))
+        return out
 
     def __del__(self):
         try:

@@ -151,11 +151,9 @@ def test_multichunk_keyswitch_scratch_budget_vs_oracle():
         assert (to_np(out[i]) == oc.multiply_relin(L, to_np(a[i]), to_np(b[i]), key)).all()
 
 
-def test_limb_mac_equals_carry_chain_mac_and_selftests():
-    """the 28-bit-limb key multiply-accumulate (sb_device.cuh: mac_limb28) and the 128-bit carry-chain one give identical words;
-    the in-process ceilings (sb200_selftest_rate) and the work counters of the profile are sane"""
-    import os
-
+def test_selftest_rates_and_profile_work_counters():
+    """the in-process ceilings (sb200_selftest_rate) and the work counters of the profile (butterflies, multiply-accumulates per
+    launch: the second ceiling of SURVEY 8d) are sane"""
     import torch
 
     S = sb()
@@ -164,27 +162,17 @@ def test_limb_mac_equals_carry_chain_mac_and_selftests():
     k, L = len(mods), len(mods) - 1
     key = to_np(device_rand(mods, n, (L, 2), k, 31))
     a, b = device_rand(mods, n, (batch, 2), L, 32), device_rand(mods, n, (batch, 2), L, 33)
-    outs = []
-    for no_limb in (False, True):
-        if no_limb:
-            os.environ["SB200_NO_LIMB_MAC"] = "1"
-        try:
-            ctx = S.Context(S.CKKS, n, mods)
-        finally:
-            os.environ.pop("SB200_NO_LIMB_MAC", None)
-        rk = ctx.load_key(key)
-        out = torch.empty_like(a)
-        ctx.profile(True)
-        ctx.d_multiply_relinearize(a, b, rk, out, L, batch)
-        torch.cuda.synchronize()
-        work = {r[0]: r for r in ctx.profile_read_work()}
-        ctx.profile(False)
-        assert work["ks_local_mac"][4] == 0.5 * batch * L * L * n * 8 and work["ks_local_mac"][5] == 2.0 * batch * (L + 1) * L * n
-        assert work["ks_digit_ntt:col"][4] == 0.5 * batch * L * L * n * (13 - 8)
-        outs.append(out)
-        if not no_limb:
-            rates = [ctx.selftest_rate(kind) for kind in range(4)]
-            assert all(r > 1e9 for r in rates), rates
-    assert torch.equal(outs[0], outs[1])
+    ctx = S.Context(S.CKKS, n, mods)
+    rk = ctx.load_key(key)
+    out = torch.empty_like(a)
+    ctx.profile(True)
+    ctx.d_multiply_relinearize(a, b, rk, out, L, batch)
+    torch.cuda.synchronize()
+    work = {r[0]: r for r in ctx.profile_read_work()}
+    ctx.profile(False)
+    assert work["ks_local_mac"][4] == 0.5 * batch * L * L * n * 8 and work["ks_local_mac"][5] == 2.0 * batch * (L + 1) * L * n
+    assert work["ks_digit_ntt:col"][4] == 0.5 * batch * L * L * n * (13 - 8)
+    rates = [ctx.selftest_rate(kind) for kind in range(4)]
+    assert all(r > 1e9 for r in rates), rates
     oc = O.Oracle(O.CKKS, n, mods)
-    assert (to_np(outs[0][batch - 1]) == oc.multiply_relin(L, to_np(a[batch - 1]), to_np(b[batch - 1]), key)).all()
+    assert (to_np(out[batch - 1]) == oc.multiply_relin(L, to_np(a[batch - 1]), to_np(b[batch - 1]), key)).all()

@@ -435,7 +435,41 @@ def test_wire_format_vs_reference(scheme):
     with pytest.raises(RuntimeError):
         ctx.d_load_ciphertexts([rc.ct_save(1, data[0][:, :1], ntt, scale)], dev, L, size)
     with pytest.raises(RuntimeError):
-        ctx.d_load_ciphertexts([rc.seeded_ct_stream()], dev, 2, 2)
+        ctx.d_load_ciphertexts([rc.seeded_ct_stream()], dev, 2, 2)  # a fresh ciphertext lives at the top level, not at level 2
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 8192, [55, 55, 55, 55]), ("ckks", 4096, [60, 60, 60]), ("bfv", 4096, [36, 36, 37]),
+                                          ("ckks", 32768, [55] * 4)])
+def test_seeded_ciphertext_expansion_vs_reference(scheme, n, bits):
+    """Ciphertext::load of seed-compressed streams (symmetric-key encryptions saved with their second polynomial as a PRNG seed):
+    c_0 is uploaded, c_1 is re-created on the device (BLAKE2Xb stream + sample_poly_uniform's rejection sampling, sb_prng.cu) and
+    must equal what the reference's own load produces, word for word; 60-bit primes make rejections frequent (~2^-4 per word)"""
+    import torch
+
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme == "bfv" else 0
+    sid = R.BFV if scheme == "bfv" else R.CKKS
+    rc = R.RefContext(sid, n, mods, t)
+    ctx = sb().Context(sid, n, mods, t)
+    oc = O.Oracle(O.BFV if scheme == "bfv" else O.CKKS, n, mods, t)
+    L = len(mods) - 1 if len(mods) > 1 else 1
+    seeded = [rc.seeded_ct_stream() for _ in range(3)]
+    full = [rc.ct_load(s)[0] for s in seeded]
+    assert full[0].shape == (2, L, n)
+    # a mixed batch: seeded, plain (re-saved by the reference), seeded, seeded
+    plain_stream = rc.ct_save(L, full[1], scheme != "bfv", 1.0)
+    streams = [seeded[0], plain_stream, seeded[1], seeded[2]]
+    want = [full[0], full[1], full[1], full[2]]
+    dev = torch.zeros((4, 2, L, n), dtype=torch.int64, device="cuda")
+    infos = ctx.d_load_ciphertexts(streams, dev, L, 2)
+    torch.cuda.synchronize()
+    got = dev.cpu().numpy().view(np.uint64)
+    assert [i.seeded for i in infos] == [1, 0, 1, 1]
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    seed = np.frombuffer(seeded[0], dtype=np.uint64, count=8, offset=infos[0].seed_offset)
+    assert (oc.expand_seed(L, seed) == got[0][1]).all()  # and the oracle's restatement agrees
 
 
 @needs_ref

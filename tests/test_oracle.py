@@ -271,3 +271,26 @@ def test_oracle_decrypt_vs_live_reference(scheme):
         p = oc.decrypt(3, ct, sk)
         assert (p == rc.decrypt(3, ct, False)).all()
         assert (oc.batch_codec(p, True) == slots).all()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not present")
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 4096, [40, 40, 40]), ("ckks", 8192, [60, 60, 60]), ("bfv", 4096, [36, 36, 37])])
+def test_expand_seed_matches_reference_load(scheme, n, bits):
+    """the oracle's restatement of Ciphertext::expand_seed (BLAKE2Xb stream + sample_poly_uniform with its rejection sampling,
+    ciphertext.cpp:118-150, util/rlwe.cpp:104-132, randomgen.cpp:204-214) against the reference loading its own seeded stream"""
+    import seal_b200 as S  # host-only use: the stream parser (no device needed)
+
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme == "bfv" else 0
+    rc = R.RefContext(R.BFV if scheme == "bfv" else R.CKKS, n, mods, t)
+    oc = O.Oracle(O.BFV if scheme == "bfv" else O.CKKS, n, mods, t)
+    for _ in range(2):
+        stream = rc.seeded_ct_stream()
+        info = S.ciphertext_inspect(stream)
+        assert info.seeded == 1 and info.size == 2 and info.seed_offset + 64 == len(stream)
+        L = info.coeff_modulus_size
+        full, _, _, _ = rc.ct_load(stream)  # the reference expands the seed itself
+        c0 = np.frombuffer(stream, dtype=np.uint64, count=L * n, offset=info.data_offset).reshape(L, n)
+        seed = np.frombuffer(stream, dtype=np.uint64, count=8, offset=info.seed_offset)
+        assert (full[0] == c0).all()
+        assert (oc.expand_seed(L, seed) == full[1]).all()

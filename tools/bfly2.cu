@@ -60,7 +60,40 @@ __device__ __forceinline__ void ct_bfly_hi(u64 &x, u64 &y, Tw w, const PrimeDev 
     y = u - v + P.q4;
 }
 
-// ---- multiply-accumulate candidates (the shipped ones are mac128 and mac_limb28 of sb_device.cuh) ----
+// ---- multiply-accumulate candidates (the shipped one is mac128 of sb_device.cuh) ----
+// 28-bit limbs: for primes q = 2^bits - dsol below 2^56 the transformed digit is folded below 2^56 (Solinas: x = (x mod 2^bits) +
+// (x >> bits) * dsol), split into limbs a = a1*2^28 + a0 and multiplied with the key word kept in the same limb form into three
+// plain 64-bit column sums without carries (Karatsuba: 3 wide multiplies per product; schoolbook: 4).  Measured (this file, and the
+// fused key-switch kernel built both ways, profiles/r02_experiments.md): fewer multiply-pipe clocks, but three 64-bit sums per
+// accumulator instead of two -- with half of the sums in shared memory the real kernel got 6 % slower, so mac128 stayed.
+__device__ __forceinline__ u64 fold_solinas(u64 a, unsigned bits, unsigned dsol)
+{
+    const u64 low = a & ((1ull << bits) - 1ull);
+    return low + static_cast<u64>(static_cast<unsigned>(a >> bits)) * dsol;
+}
+struct Acc3
+{
+    u64 s0, s1, s2;
+};
+__device__ __forceinline__ void mac_limb28(Acc3 &s, unsigned a0, unsigned a1, unsigned as, u64 ke)
+{
+    unsigned k0, k1;
+    unpack64(ke, k0, k1);
+    const unsigned ks = k0 + k1;
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s0) : "r"(a0), "r"(k0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s2) : "r"(a1), "r"(k1));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s.s1) : "r"(as), "r"(ks));
+}
+__device__ __forceinline__ void acc3_value(const Acc3 &s, u64 &lo, u64 &hi)
+{
+    const u64 mid = s.s1 - s.s0 - s.s2; // sum of a0*k1 + a1*k0
+    u64 l = s.s0, h = 0, t;
+    t = mid << 28;
+    l += t, h += (mid >> 36) + (l < t);
+    t = s.s2 << 56;
+    l += t, h += (s.s2 >> 8) + (l < t);
+    lo = l, hi = h;
+}
 // schoolbook on 28-bit limbs: four wide multiplies, three column sums
 __device__ __forceinline__ void mac_limb28_school(Acc3 &s, unsigned a0, unsigned a1, u64 klimbs)
 {
