@@ -240,8 +240,9 @@ int sb200_relinearize_sized_host(sb200_context *ctx, size_t L, size_t size, size
  * stream and a device slab (ciphertext.cpp:190-359, serialization.h:76-91, dynarray.h:662-690).  Seed-compressed ciphertexts
  * (Serializable<Ciphertext> of a symmetric-key encryption: c_1 replaced by the seed of the PRNG that made it) are expanded on
  * the device -- Ciphertext::expand_seed -> sample_poly_uniform on a Blake2xbPRNG (ciphertext.cpp:118-150, util/rlwe.cpp:104-132,
- * randomgen.cpp:204-214), bit for bit -- so a fresh ciphertext crosses PCIe with half its bytes.  Compressed streams (zlib / zstd)
- * and the shake256 PRNG stay with the reference: inspect reports them, load rejects them. */
+ * randomgen.cpp:204-214), bit for bit -- so a fresh ciphertext crosses PCIe with half its bytes.  zlib-compressed objects
+ * (compr_mode_type::zlib, serialization.cpp:236-300, util/ztools.cpp) are inflated on the host with the system's zlib before
+ * they are parsed; zstd streams and the shake256 PRNG stay with the reference: load rejects them. */
 typedef struct sb200_ct_info
 {
     uint64_t parms_id[4];         /* Ciphertext::parms_id() */
@@ -257,6 +258,8 @@ typedef struct sb200_ct_info
     uint64_t data_words;          /* 64-bit words stored */
     uint64_t stream_bytes;        /* length of the serialized object (SEALHeader::size) */
     uint64_t seed_offset;         /* seeded streams: byte offset of the prng_seed_type (64 bytes); 0 otherwise */
+    uint64_t compr_mode;          /* compr_mode_type of the stream (serialization.h:33-47): 0 none, 1 zlib; for a compressed stream the
+                                     offsets above refer to the decompressed object and stream_bytes to the stream as given */
 } sb200_ct_info;
 
 /* EncryptionParameters::parms_id() of the level with L primes (L = k: the key level); encryptionparams.cpp:124-158 */

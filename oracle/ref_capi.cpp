@@ -521,6 +521,46 @@ extern "C" long sealref_ct_save(
     REF_CATCH(-1)
 }
 
+// the same three writers with an explicit compression mode (0 none, 1 zlib; serialization.h:33-47)
+static compr_mode_type mode_of(int mode)
+{
+    if (mode == 0)
+        return compr_mode_type::none;
+#ifdef SEAL_USE_ZLIB
+    if (mode == 1)
+        return compr_mode_type::zlib;
+#endif
+    throw std::invalid_argument("unsupported compression mode");
+}
+extern "C" long sealref_ct_save_mode(
+    sealref_ctx *c, size_t L, size_t size, const uint64_t *data, int is_ntt_form, double scale, uint64_t correction_factor, int mode,
+    uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    Ciphertext ct = make_ct(c, L, size, data);
+    ct.is_ntt_form() = is_ntt_form != 0;
+    ct.scale() = scale;
+    ct.correction_factor() = correction_factor;
+    return static_cast<long>(ct.save(reinterpret_cast<seal_byte *>(out), capacity, mode_of(mode)));
+    REF_CATCH(-1)
+}
+extern "C" long sealref_kswitch_keys_stream_mode(sealref_ctx *c, uint32_t galois_elt, int mode, uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    if (galois_elt == 0)
+        return static_cast<long>(relin_keys(c).save(reinterpret_cast<seal_byte *>(out), capacity, mode_of(mode)));
+    return static_cast<long>(galois_for(c, galois_elt).save(reinterpret_cast<seal_byte *>(out), capacity, mode_of(mode)));
+    REF_CATCH(-1)
+}
+extern "C" long sealref_seeded_ct_stream_mode(sealref_ctx *c, int mode, uint8_t *out, size_t capacity)
+{
+    REF_TRY
+    Encryptor encryptor(*c->context, c->keygen->secret_key());
+    auto ser = encryptor.encrypt_zero_symmetric();
+    return static_cast<long>(ser.save(reinterpret_cast<seal_byte *>(out), capacity, mode_of(mode)));
+    REF_CATCH(-1)
+}
+
 extern "C" int sealref_ct_load(
     sealref_ctx *c, const uint8_t *in, size_t len, uint64_t *data, size_t capacity_words, uint64_t *size, uint64_t *L,
     int *is_ntt_form, double *scale, uint64_t *correction_factor)

@@ -68,6 +68,10 @@ long sealref_ct_save(sealref_ctx *c, size_t L, size_t size, const uint64_t *data
 int sealref_ct_load(sealref_ctx *c, const uint8_t *in, size_t len, uint64_t *data, size_t capacity_words, uint64_t *size, uint64_t *L, int *is_ntt_form, double *scale, uint64_t *correction_factor);
 long sealref_kswitch_keys_stream(sealref_ctx *c, uint32_t galois_elt, uint8_t *out, size_t capacity); /* 0: RelinKeys, else GaloisKeys of that element */
 long sealref_seeded_ct_stream(sealref_ctx *c, uint8_t *out, size_t capacity);
+/* the writers above with an explicit compr_mode (0 = none, 1 = zlib) */
+long sealref_ct_save_mode(sealref_ctx *c, size_t L, size_t size, const uint64_t *data, int is_ntt_form, double scale, uint64_t correction_factor, int mode, uint8_t *out, size_t capacity);
+long sealref_kswitch_keys_stream_mode(sealref_ctx *c, uint32_t galois_elt, int mode, uint8_t *out, size_t capacity);
+long sealref_seeded_ct_stream_mode(sealref_ctx *c, int mode, uint8_t *out, size_t capacity);
 int sealref_bfv_encrypt(sealref_ctx *c, const uint64_t *slots, uint64_t *out2);
 int sealref_bfv_decrypt(sealref_ctx *c, size_t L, size_t size, const uint64_t *ct, uint64_t *slots, int *noise_budget);
 

@@ -46,7 +46,7 @@ class CtInfo(C.Structure):
     _fields_ = [("parms_id", C.c_uint64 * 4), ("size", C.c_uint64), ("poly_modulus_degree", C.c_uint64),
                 ("coeff_modulus_size", C.c_uint64), ("correction_factor", C.c_uint64), ("scale", C.c_double),
                 ("is_ntt_form", C.c_int32), ("seeded", C.c_int32), ("data_offset", C.c_uint64), ("data_words", C.c_uint64),
-                ("stream_bytes", C.c_uint64), ("seed_offset", C.c_uint64)]
+                ("stream_bytes", C.c_uint64), ("seed_offset", C.c_uint64), ("compr_mode", C.c_uint64)]
 
 
 def lib():

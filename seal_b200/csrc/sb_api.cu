@@ -586,6 +586,10 @@ int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len
     if (c.k < 2)
         throw std::logic_error("keyswitching is not supported by the context");
     sbw::KSwitchEntry e;
+    std::vector<uint8_t> plain; // KSwitchKeys saved with compr_mode_type::zlib: inflate the object, then parse as usual
+    // bound: a GaloisKeys object holds at most 2 log2(n) + 1 < 64 keys of k-1 digits, plus one size word per slot
+    if (sbw::inflate_stream(stream, len, 64 * (c.k - 1) * sbw::save_size(2 * c.k * c.n) + 16 * c.n + 4096, plain))
+        stream = plain.data(), len = plain.size();
     sbw::inspect_kswitch(stream, len, index, e);
     // is_valid_for(KSwitchKeys): keys live at the key level of this context (valcheck.cpp, kswitchkeys.cpp:149-153)
     if (e.n != c.n || e.L != c.k || std::memcmp(e.parms_id, c.parms_ids[c.k - 1].data(), sizeof(e.parms_id)) != 0)
@@ -1326,9 +1330,21 @@ int sb200_get_parms_id(const sb200_context *ctx, size_t L, uint64_t out[4])
 
 int sb200_ciphertext_inspect(const uint8_t *stream, size_t len, sb200_ct_info *info)
 {
+    SB_NEED(stream);
     SB_NEED(info);
     SB_TRY
-    sbw::inspect(stream, len, *info);
+    std::vector<uint8_t> plain;
+    // a compressed object is inflated first (bounded by the largest ciphertext the format allows: 16 x 256 x 131072 words)
+    if (sbw::inflate_stream(stream, len, sbw::save_size(size_t(16) * 256 * 131072) + 128, plain))
+    {
+        sbw::inspect(plain.data(), plain.size(), *info);
+        uint64_t total = 0;
+        std::memcpy(&total, stream + 8, sizeof(total)); // SEALHeader::size of the stream as given
+        info->stream_bytes = total;
+        info->compr_mode = 1;
+    }
+    else
+        sbw::inspect(stream, len, *info);
     return SB200_OK;
     SB_CATCH
 }
@@ -1354,7 +1370,18 @@ int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const
     for (size_t b = 0; b < batch; b++)
     {
         sb200_ct_info info;
-        sbw::inspect(streams[b], lens[b], info);
+        std::vector<uint8_t> plain; // a zlib-compressed member is inflated on the host (bounded by the shape asked for)
+        const uint8_t *src = streams[b];
+        if (!src)
+            throw std::invalid_argument("in cannot be null");
+        if (sbw::inflate_stream(src, lens[b], sbw::save_size(words) + 128, plain))
+        {
+            sbw::inspect(plain.data(), plain.size(), info);
+            src = plain.data();
+            info.compr_mode = 1;
+        }
+        else
+            sbw::inspect(src, lens[b], info);
         if (info.seeded == 2)
             throw std::logic_error("unsupported prng_type"); // shake256 streams stay with the reference (ciphertext.cpp:124-128)
         // is_metadata_valid_for (ciphertext.cpp:299-302): the stream must belong to this context at the level asked for
@@ -1363,11 +1390,12 @@ int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const
             throw std::logic_error("ciphertext data is invalid");
         if (infos)
             infos[b] = info;
-        cuda_check(cudaMemcpyAsync(d_out + b * words, streams[b] + info.data_offset, info.data_words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+        // (pageable source: the call returns once the bytes have left the buffer, so `plain` may go out of scope)
+        cuda_check(cudaMemcpyAsync(d_out + b * words, src + info.data_offset, info.data_words * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
         if (info.seeded)
         {
             u64 sd[8];
-            std::memcpy(sd, streams[b] + info.seed_offset, sizeof(sd));
+            std::memcpy(sd, src + info.seed_offset, sizeof(sd));
             seeds.insert(seeds.end(), sd, sd + 8);
             seed_dst.push_back(static_cast<long long>(b * words + L * c.n));
         }

@@ -1,8 +1,10 @@
 // seal_b200/csrc/sb_wire.cpp -- see sb_wire.hpp
 #include "sb_wire.hpp"
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
+#include <zlib.h>
 
 namespace sbw
 {
@@ -114,7 +116,7 @@ namespace sbw
             if (h.magic != kMagic || h.header_size != kHeaderBytes)
                 throw std::logic_error("loaded SEALHeader is invalid");
             if (h.compr != 0)
-                throw std::logic_error("unsupported compression mode"); // zlib / zstd streams stay with the reference
+                throw std::logic_error("unsupported compression mode"); // compressed objects go through inflate_stream first
             if (h.size < kHeaderBytes)
                 throw std::logic_error("loaded SEALHeader is invalid");
             return h;
@@ -134,6 +136,57 @@ namespace sbw
             p += sizeof(T);
         }
     } // namespace
+
+    bool inflate_stream(const uint8_t *p, size_t len, size_t limit, std::vector<uint8_t> &plain)
+    {
+        if (!p)
+            throw std::invalid_argument("in cannot be null");
+        if (len < kHeaderBytes)
+            throw std::invalid_argument("insufficient size");
+        Header h;
+        std::memcpy(&h, p, sizeof(h));
+        if (h.major != kMajor || h.minor > kMinor)
+            throw std::logic_error("incompatible version");
+        if (h.magic != kMagic || h.header_size != kHeaderBytes || h.size < kHeaderBytes || h.size > len)
+            throw std::logic_error("loaded SEALHeader is invalid");
+        if (h.compr == 0)
+            return false;
+        if (h.compr != 1)
+            throw std::logic_error("unsupported compression mode"); // compr_mode_type::zstd: not part of this build
+        z_stream z;
+        std::memset(&z, 0, sizeof(z));
+        if (inflateInit(&z) != Z_OK)
+            throw std::logic_error("ZLIB decompression failed");
+        plain.assign(kHeaderBytes, 0);
+        z.next_in = const_cast<Bytef *>(p + kHeaderBytes);
+        size_t in_left = static_cast<size_t>(h.size) - kHeaderBytes;
+        std::vector<uint8_t> chunk(size_t(1) << 20);
+        int rc = Z_OK;
+        while (rc != Z_STREAM_END)
+        {
+            if (z.avail_in == 0 && in_left)
+            {
+                const size_t take = std::min<size_t>(in_left, size_t(1) << 30); // uInt is 32 bits wide
+                z.avail_in = static_cast<uInt>(take);
+                in_left -= take;
+            }
+            z.next_out = chunk.data();
+            z.avail_out = static_cast<uInt>(chunk.size());
+            rc = inflate(&z, Z_NO_FLUSH);
+            const size_t got = chunk.size() - z.avail_out;
+            if ((rc != Z_OK && rc != Z_STREAM_END) || plain.size() - kHeaderBytes + got > limit || (rc == Z_OK && got == 0 && z.avail_in == 0 && !in_left))
+            {
+                inflateEnd(&z);
+                throw std::logic_error("ZLIB decompression failed"); // serialization.cpp:283-289
+            }
+            plain.insert(plain.end(), chunk.data(), chunk.data() + got);
+        }
+        inflateEnd(&z);
+        h.compr = 0;
+        h.size = plain.size();
+        std::memcpy(plain.data(), &h, sizeof(h));
+        return true;
+    }
 
     void inspect(const uint8_t *p, size_t len, sb200_ct_info &info)
     {

@@ -23,6 +23,12 @@ namespace sbw
     constexpr size_t kMemberBytes = 32 + 1 + 8 + 8 + 8 + 8 + 8;      // parms_id .. correction_factor
     constexpr size_t kDataOffset = kHeaderBytes + kMemberBytes + kHeaderBytes + 8; // first coefficient word
 
+    // Serialization::Load of a zlib-compressed object (serialization.cpp:236-300, util/ztools.cpp): SEALHeader{compr_mode = zlib,
+    // size} followed by ONE zlib stream of the object's body.  Returns false for an uncompressed stream; otherwise fills `plain`
+    // with the equivalent uncompressed stream (header with compr_mode none + body) and returns true.  `limit` bounds the
+    // decompressed body (the reference bounds loads by the expected in-memory size for the same reason: a malformed stream must
+    // not cause arbitrarily large allocations).  zstd streams throw (std::logic_error): the library is not part of this build.
+    bool inflate_stream(const uint8_t *p, size_t len, size_t limit, std::vector<uint8_t> &plain);
     // parses and validates one serialized ciphertext (throws std::invalid_argument / std::logic_error like Serialization::Load)
     void inspect(const uint8_t *p, size_t len, sb200_ct_info &info);
     inline size_t save_size(size_t words) { return kDataOffset + 8 * words; }

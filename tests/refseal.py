@@ -72,6 +72,12 @@ def lib():
         L.sealref_kswitch_keys_stream.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]
         L.sealref_seeded_ct_stream.restype = C.c_long
         L.sealref_seeded_ct_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.sealref_ct_save_mode.restype = C.c_long
+        L.sealref_ct_save_mode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_char_p, C.c_size_t]
+        L.sealref_kswitch_keys_stream_mode.restype = C.c_long
+        L.sealref_kswitch_keys_stream_mode.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_char_p, C.c_size_t]
+        L.sealref_seeded_ct_stream_mode.restype = C.c_long
+        L.sealref_seeded_ct_stream_mode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -276,11 +282,11 @@ class RefContext:
         self._chk(lib().sealref_parms_id(self.h, L, _p(out)))
         return tuple(int(x) for x in out)
 
-    def ct_save(self, L, data, is_ntt_form, scale=1.0, correction_factor=1):
-        """Ciphertext::save(compr_mode_type::none) of [size][L][n] words"""
+    def ct_save(self, L, data, is_ntt_form, scale=1.0, correction_factor=1, compr=0):
+        """Ciphertext::save of [size][L][n] words with compr_mode none (0) or zlib (1)"""
         data = np.ascontiguousarray(data)
-        buf = C.create_string_buffer(data.nbytes + 4096)
-        ln = lib().sealref_ct_save(self.h, L, data.shape[0], _p(data), int(is_ntt_form), scale, correction_factor, buf, len(buf))
+        buf = C.create_string_buffer(data.nbytes + data.nbytes // 8 + 4096)
+        ln = lib().sealref_ct_save_mode(self.h, L, data.shape[0], _p(data), int(is_ntt_form), scale, correction_factor, compr, buf, len(buf))
         if ln < 0:
             raise RuntimeError(lib().sealref_last_error().decode())
         return buf.raw[:ln]
@@ -294,17 +300,18 @@ class RefContext:
                                         C.byref(scale), C.byref(cf)))
         return out[: size.value * L.value * self.n].reshape(size.value, L.value, self.n).copy(), bool(ntt.value), scale.value, cf.value
 
-    def kswitch_keys_stream(self, galois_elt=0):
-        """RelinKeys::save (galois_elt == 0) or GaloisKeys::save of the keys holding that element, compr_mode none"""
-        buf = C.create_string_buffer((self.k - 1) * 2 * self.k * self.n * 8 + 8 * self.n + (1 << 16))
-        ln = lib().sealref_kswitch_keys_stream(self.h, galois_elt, buf, len(buf))
+    def kswitch_keys_stream(self, galois_elt=0, compr=0):
+        """RelinKeys::save (galois_elt == 0) or GaloisKeys::save of the keys holding that element, compr_mode none (0) / zlib (1)"""
+        raw = (self.k - 1) * 2 * self.k * self.n * 8
+        buf = C.create_string_buffer(raw + raw // 8 + 8 * self.n + (1 << 16))
+        ln = lib().sealref_kswitch_keys_stream_mode(self.h, galois_elt, compr, buf, len(buf))
         if ln < 0:
             raise RuntimeError(lib().sealref_last_error().decode())
         return buf.raw[:ln]
 
-    def seeded_ct_stream(self):
-        buf = C.create_string_buffer(2 * self.k * self.n * 8 + 4096)
-        ln = lib().sealref_seeded_ct_stream(self.h, buf, len(buf))
+    def seeded_ct_stream(self, compr=0):
+        buf = C.create_string_buffer(2 * self.k * self.n * 8 + self.k * self.n + 4096)
+        ln = lib().sealref_seeded_ct_stream_mode(self.h, compr, buf, len(buf))
         if ln < 0:
             raise RuntimeError(lib().sealref_last_error().decode())
         return buf.raw[:ln]

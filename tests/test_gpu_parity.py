@@ -470,6 +470,20 @@ def test_seeded_ciphertext_expansion_vs_reference(scheme, n, bits):
         assert (g == w).all()
     seed = np.frombuffer(seeded[0], dtype=np.uint64, count=8, offset=infos[0].seed_offset)
     assert (oc.expand_seed(L, seed) == got[0][1]).all()  # and the oracle's restatement agrees
+    # the same objects saved with compr_mode_type::zlib (the reference's default when it is built with zlib): inflated on the host,
+    # then the same path; a key-switching key object too
+    zstreams = [rc.seeded_ct_stream(compr=1), rc.ct_save(L, full[1], scheme != "bfv", 1.0, compr=1)]
+    zwant = [rc.ct_load(zstreams[0])[0], full[1]]
+    zdev = torch.zeros((2, 2, L, n), dtype=torch.int64, device="cuda")
+    zinfos = ctx.d_load_ciphertexts(zstreams, zdev, L, 2)
+    torch.cuda.synchronize()
+    assert [(i.compr_mode, i.seeded) for i in zinfos] == [(1, 1), (1, 0)]
+    for g, w in zip(zdev.cpu().numpy().view(np.uint64), zwant):
+        assert (g == w).all()
+    if scheme == "ckks" and n == 8192:
+        m = ctx.multiply(full[:1], full[:1])
+        rk_z = ctx.load_key_stream(rc.kswitch_keys_stream(0, compr=1), 0)
+        assert (ctx.relinearize(m, rk_z) == ctx.relinearize(m, ctx.load_key(rc.relin_key()))).all()
 
 
 @needs_ref

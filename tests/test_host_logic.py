@@ -236,8 +236,18 @@ def test_ciphertext_inspect_vs_reference_stream():
         assert info.stream_bytes == len(stream) and info.data_words == data.size
         words = np.frombuffer(stream, dtype=np.uint64, count=data.size, offset=info.data_offset)
         assert (words == data.reshape(-1)).all()
-    # seed-compressed ciphertexts are recognised (and left to the reference)
-    assert S.ciphertext_inspect(rc.seeded_ct_stream()).seeded == 1
+    # seed-compressed ciphertexts: the PRNG type and where the seed sits
+    sinfo = S.ciphertext_inspect(rc.seeded_ct_stream())
+    assert sinfo.seeded == 1 and sinfo.seed_offset + 64 == sinfo.stream_bytes and sinfo.compr_mode == 0
+    # zlib-compressed objects (compr_mode_type::zlib) are inflated on the host and parse to the same metadata and words
+    z = rc.ct_save(L, data, True, scale=2.0 ** 30, correction_factor=1, compr=1)
+    assert z[5] == 1 and len(z) != len(stream)
+    zinfo = S.ciphertext_inspect(z)
+    assert zinfo.compr_mode == 1 and zinfo.stream_bytes == len(z) and zinfo.data_words == data.size and tuple(zinfo.parms_id) == rc.parms_id(L)
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(z[:40] + bytes([z[40] ^ 0xFF]) + z[41:])   # corrupted deflate data
+    with pytest.raises(RuntimeError):
+        S.ciphertext_inspect(z[:len(z) // 2] + b"\x00" * (len(z) - len(z) // 2))  # truncated deflate data
     # malformed streams: Serialization::Load's error ladder
     with pytest.raises(ValueError):
         S.ciphertext_inspect(stream[:8])                       # insufficient size
