@@ -38,6 +38,7 @@ extern "C" {
 #define SB200_SCHEME_BGV 3  /* seal::scheme_type::bgv: NTT-form ciphertexts like CKKS, plain-modulus-aware mod-down */
 
 typedef struct sb200_context sb200_context;   /* mirrors SEALContext + Evaluator state (context.h:277-439) */
+typedef struct sb200_public_key sb200_public_key;   /* Encryptor state: the public key on the device (publickey.h) */
 typedef struct sb200_secret_key sb200_secret_key;   /* Decryptor state: the secret key and its powers on the device (decryptor.h) */
 typedef struct sb200_kswitch_key sb200_kswitch_key; /* one KSwitchKeys::data()[index] entry on the device (kswitchkeys.h) */
 
@@ -280,11 +281,53 @@ int sb200_ciphertext_load(sb200_context *ctx, size_t batch, const uint8_t *const
 int sb200_ciphertext_save(sb200_context *ctx, size_t batch, size_t L, size_t size, const uint64_t *d_in, const sb200_ct_info *meta,
                           uint8_t *const *outs, size_t capacity, void *stream);
 
+/* ---- public-key encryption: Encryptor(context, public_key) and Encryptor::encrypt_zero(parms_id, destination)
+ * (encryptor.cpp:88-174 -> util::encrypt_zero_asymmetric, util/rlwe.cpp:184-276) for a batch.
+ * h_public_key = PublicKey::data().data(): [2][k][n] words, NTT form at the key level (range-checked).
+ * d_out = [batch][2][L][n] at the level with L primes (L == k: the key level): NTT form for CKKS / BGV, coefficient form for BFV,
+ * scale 1, correction factor 1.  As in the reference the sample is drawn one level above (L + 1 primes) and divided down by that
+ * level's last prime.  Per ciphertext ONE PRNG (Blake2xb of a 64-byte seed) yields the ternary polynomial u and the two noise
+ * polynomials exactly as the reference draws them (u through std::uniform_int_distribution as libstdc++ >= 11 implements it),
+ * so the same seed gives the reference's ciphertext bit for bit.  h_seeds = [batch][8] words or NULL = fresh seeds from the OS
+ * entropy source.  Synchronises the stream.  Add the plaintext as for the symmetric variant to obtain Encryptor::encrypt. */
+int sb200_public_key_create(sb200_context *ctx, const uint64_t *h_public_key, sb200_public_key **out);
+int sb200_public_key_destroy(sb200_public_key *key);
+int sb200_encrypt_zero_asymmetric(sb200_context *ctx, sb200_public_key *key, size_t L, size_t batch, const uint64_t *h_seeds,
+                                  uint64_t *d_out, void *stream);
+
+/* ---- CKKSEncoder (the data format either side of the path): CKKSEncoder::encode(values, parms_id, scale, plain) and
+ * CKKSEncoder::decode(plain, values) (ckks.h:455-807) for a batch.  values = doubles: [batch][count] complex numbers as (re, im)
+ * pairs when is_complex, else [batch][count] reals; count <= n/2, missing slots are zero.  plain = [batch][L][n] NTT form at the
+ * level with L primes (Plaintext::data() of each plaintext; its parms_id is sb200_get_parms_id(L), its scale the scale given).
+ * Bit-exact with the reference: the double-precision transform performs the reference's operations in the reference's order.
+ * Errors as the reference throws them (SB200_E_INVALID_ARG): "scale out of bounds", "values must be finite", "encoded values are
+ * too large" (the plaintext buffer is left unspecified), "unsupported scheme" for a non-CKKS context.
+ * decode writes [batch][n/2] complex numbers as (re, im) pairs; `scale` is Plaintext::scale().  The encode entry points
+ * synchronise the stream once (the magnitude check precedes the reduction). */
+int sb200_ckks_encode(sb200_context *ctx, size_t L, size_t batch, const double *d_values, size_t count, int is_complex, double scale,
+                      uint64_t *d_plain, void *stream);
+int sb200_ckks_decode(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_plain, double scale, double *d_values, void *stream);
+int sb200_ckks_encode_host(sb200_context *ctx, size_t L, size_t batch, const double *h_values, size_t count, int is_complex, double scale,
+                           uint64_t *h_plain);
+int sb200_ckks_decode_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_plain, double scale, double *h_values);
+
 /* ---- decryption: Decryptor(context, secret_key) and Decryptor::decrypt (decryptor.cpp:62-197) ------
  * h_secret_key = SecretKey::data().data(): [k][n] words, NTT form at the key level.  Powers of the key for ciphertexts
  * of size > 2 are built on the device on first use (compute_secret_key_array, :199-310). */
 int sb200_secret_key_create(sb200_context *ctx, const uint64_t *h_secret_key, sb200_secret_key **out);
 int sb200_secret_key_destroy(sb200_secret_key *key);
+/* Encryptor::encrypt_zero_symmetric(parms_id, destination) for a batch (encryptor.cpp:168-173 -> util/rlwe.cpp:264-408): fresh
+ * encryptions of zero under the secret key at the level with L primes, d_out = [batch][2][L][n] (NTT form for CKKS / BGV,
+ * coefficient form for BFV; scale 1, correction factor 1).  Per ciphertext ONE bootstrap PRNG (Blake2xb of a 64-byte seed) yields
+ * the public seed c_1 is sampled from and the centred binomial noise, exactly as the reference draws them, so that the same
+ * bootstrap seed gives the reference's ciphertext bit for bit.  h_bootstrap_seeds = [batch][8] words, or NULL = fresh seeds from
+ * the OS entropy source (what the reference's default UniformRandomGeneratorFactory does, randomgen.cpp:34-50).
+ * save_seed != 0 selects the Serializable<Ciphertext> variant (differs for BFV only: which domain c_1 is sampled in);
+ * h_public_seeds = NULL or [batch][8]: the seed each c_1 expands from (what a seeded stream carries instead of c_1: send
+ * (c_0, seed) over the wire and let the receiver expand, sb200_ciphertext_load).  Add the plaintext (sb200_add for NTT-form CKKS plaintexts, sb200_add_plain_coeff for BFV / BGV)
+ * to obtain Encryptor::encrypt_symmetric (encryptor.cpp:199-262). */
+int sb200_encrypt_zero_symmetric(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t batch, const uint64_t *h_bootstrap_seeds,
+                                 int save_seed, uint64_t *d_out, uint64_t *h_public_seeds, void *stream);
 /* d_ct [batch][size][L][n] in the scheme's own form -> d_plain: CKKS [batch][L][n] (NTT form, same level; the caller keeps
  * scale and parms_id); BFV [batch][n] coefficients mod t (dot product + decrypt_scale_and_round, rns.cpp:1133-1191);
  * BGV [batch][n] (dot product, INTT, exact base conversion rns.cpp:466-539, times the inverse of the ciphertext's

@@ -4,6 +4,7 @@
 #include "ref_capi.h"
 #include "seal/seal.h"
 #include <chrono>
+#include <complex>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -595,6 +596,100 @@ extern "C" long sealref_seeded_ct_stream(sealref_ctx *c, uint8_t *out, size_t ca
     Encryptor encryptor(*c->context, c->keygen->secret_key());
     auto ser = encryptor.encrypt_zero_symmetric();
     return static_cast<long>(ser.save(reinterpret_cast<seal_byte *>(out), capacity, compr_mode_type::none));
+    REF_CATCH(-1)
+}
+
+// the public key (KeyGenerator::create_public_key: [2][k][n], NTT form at the key level) and Encryptor::encrypt_zero(parms_id, ct)
+// with it; L == k: the key level itself.  Deterministic: every PRNG the seeded factory creates starts from {seed, 0, ..., 0}
+extern "C" int sealref_public_key(sealref_ctx *c, uint64_t *out)
+{
+    REF_TRY
+    PublicKey pk;
+    c->keygen->create_public_key(pk);
+    std::memcpy(out, pk.data().data(), 2 * c->k * c->n * sizeof(uint64_t));
+    return 0;
+    REF_CATCH(-1)
+}
+
+extern "C" int sealref_encrypt_zero_asymmetric(sealref_ctx *c, size_t L, uint64_t *out2)
+{
+    REF_TRY
+    PublicKey pk;
+    c->keygen->create_public_key(pk);
+    Encryptor encryptor(*c->context, pk);
+    Ciphertext ct;
+    encryptor.encrypt_zero(L == c->k ? c->context->key_parms_id() : level(c, L)->parms_id(), ct);
+    std::memcpy(out2, ct.data(), 2 * L * c->n * sizeof(uint64_t));
+    return 0;
+    REF_CATCH(-1)
+}
+
+// CKKSEncoder::encode(vector<complex<double>>, parms_id, scale, plain) / decode; values = [count][2] doubles.
+// Returns 1 when the reference throws invalid_argument (values too large, scale out of bounds, non-finite input).
+extern "C" int sealref_ckks_encode(sealref_ctx *c, size_t L, const double *values, size_t count, double scale, uint64_t *out)
+{
+    try
+    {
+        CKKSEncoder encoder(*c->context);
+        std::vector<std::complex<double>> v(count);
+        for (size_t i = 0; i < count; i++)
+            v[i] = { values[2 * i], values[2 * i + 1] };
+        Plaintext p;
+        encoder.encode(v, level(c, L)->parms_id(), scale, p);
+        std::memcpy(out, p.data(), L * c->n * sizeof(uint64_t));
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+    catch (const std::exception &e)
+    {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+extern "C" int sealref_ckks_decode(sealref_ctx *c, size_t L, const uint64_t *plain, double scale, double *out)
+{
+    try
+    {
+        CKKSEncoder encoder(*c->context);
+        auto cd = level(c, L);
+        Plaintext p;
+        p.resize(L * c->n);
+        std::memcpy(p.data(), plain, L * c->n * sizeof(uint64_t));
+        p.parms_id() = cd->parms_id();
+        p.scale() = scale;
+        std::vector<std::complex<double>> v;
+        encoder.decode(p, v);
+        for (size_t i = 0; i < v.size(); i++)
+            out[2 * i] = v[i].real(), out[2 * i + 1] = v[i].imag();
+        return 0;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        g_err = e.what();
+        return 1;
+    }
+    catch (const std::exception &e)
+    {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// Encryptor::encrypt_zero_symmetric(destination): the plain (not seed-compressed) variant.  Deterministic here: the context's random
+// generator factory is seeded (sealref_create), so every bootstrap PRNG starts from {seed, 0, ..., 0}
+extern "C" int sealref_encrypt_zero_symmetric(sealref_ctx *c, size_t L, uint64_t *out2)
+{
+    REF_TRY
+    Encryptor encryptor(*c->context, c->keygen->secret_key());
+    Ciphertext ct;
+    encryptor.encrypt_zero_symmetric(level(c, L)->parms_id(), ct);
+    store_ct(c, ct, out2);
+    return 0;
     REF_CATCH(-1)
 }
 

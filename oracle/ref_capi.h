@@ -72,6 +72,12 @@ long sealref_seeded_ct_stream(sealref_ctx *c, uint8_t *out, size_t capacity);
 long sealref_ct_save_mode(sealref_ctx *c, size_t L, size_t size, const uint64_t *data, int is_ntt_form, double scale, uint64_t correction_factor, int mode, uint8_t *out, size_t capacity);
 long sealref_kswitch_keys_stream_mode(sealref_ctx *c, uint32_t galois_elt, int mode, uint8_t *out, size_t capacity);
 long sealref_seeded_ct_stream_mode(sealref_ctx *c, int mode, uint8_t *out, size_t capacity);
+/* CKKSEncoder::encode / decode (complex vectors, [count][2] doubles); 1 = the reference threw invalid_argument */
+int sealref_ckks_encode(sealref_ctx *c, size_t L, const double *values, size_t count, double scale, uint64_t *out);
+int sealref_ckks_decode(sealref_ctx *c, size_t L, const uint64_t *plain, double scale, double *out);
+int sealref_public_key(sealref_ctx *c, uint64_t *out);                        /* [2][k][n] */
+int sealref_encrypt_zero_asymmetric(sealref_ctx *c, size_t L, uint64_t *out2); /* Encryptor(pk)::encrypt_zero(parms_id of level L): [2][L][n] */
+int sealref_encrypt_zero_symmetric(sealref_ctx *c, size_t L, uint64_t *out2); /* Encryptor::encrypt_zero_symmetric(parms_id of level L, ct): [2][L][n] */
 int sealref_bfv_encrypt(sealref_ctx *c, const uint64_t *slots, uint64_t *out2);
 int sealref_bfv_decrypt(sealref_ctx *c, size_t L, size_t size, const uint64_t *ct, uint64_t *slots, int *noise_budget);
 

@@ -4,6 +4,7 @@
  * to /root/reference/native/src/seal/.  Nothing here is tuned; clarity over speed.
  */
 #include "seal_oracle.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1192,4 +1193,452 @@ void orc_expand_seed(const orc_ctx *c, size_t L, const uint64_t seed[8], uint64_
             out[j * n + i] = r % q;
         }
     }
+}
+
+
+/* ---- symmetric-key encryption of zero (util/rlwe.cpp:264-408, encrypt_zero_symmetric) -----------------------------------
+ * bootstrap PRNG = Blake2xbPRNG(seed): its first 64 bytes are the public seed of the PRNG that samples c_1 (sample_poly_uniform),
+ * the following 6 bytes per coefficient feed the centred binomial noise (sample_poly_cbd, rlwe.cpp:73-102).
+ * (c_0, c_1) = (-(c_1 s + e), c_1) [BFV, CKKS], (-(c_1 s + t e), c_1) [BGV].  BFV ciphertexts are in coefficient form: with
+ * save_seed the sampled polynomial IS c_1 (coefficient form, re-created from the seed at load time), without it the sampled
+ * polynomial is taken to be NTT(c_1).  sk = secret key, NTT form, [k][n]; out = [2][L][n] at the level with L primes (symmetric
+ * encryption at a lower level samples at that level directly: Encryptor::encrypt_zero_internal, encryptor.cpp:168-173). */
+static int cbd_noise(const unsigned char x[6])
+{
+    static const unsigned char pop[16] = { 0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4 };
+#define HW(b) (pop[(b) & 15] + pop[(b) >> 4])
+    return HW(x[0]) + HW(x[1]) + HW(x[2] & 0x1F) - HW(x[3]) - HW(x[4]) - HW(x[5] & 0x1F);
+#undef HW
+}
+void orc_encrypt_zero_symmetric(const orc_ctx *c, size_t L, const uint64_t *sk, const uint64_t seed[8], int save_seed, uint64_t *out2)
+{
+    const size_t n = c->n;
+    const int ntt_form = c->scheme != ORC_BFV;
+    /* bootstrap stream: 64 bytes of public seed, then 6 bytes per coefficient */
+    const size_t bwords = (64 + 6 * n + 7) / 8;
+    u64 *boot = (u64 *)malloc(bwords * sizeof(u64));
+    orc_blake2xb_stream(seed, bwords, boot);
+    u64 *c0 = out2, *c1 = out2 + L * n;
+    orc_expand_seed(c, L, boot, c1); /* the first 8 words are the public seed */
+    u64 *c1n = (u64 *)malloc(L * n * sizeof(u64));
+    memcpy(c1n, c1, L * n * sizeof(u64));
+    if (!ntt_form)
+    {
+        if (save_seed)
+            for (size_t j = 0; j < L; j++)
+                ntt_fwd(&c->tab[j], n, c1n + j * n); /* the sample is c_1 itself: transform a copy for the product */
+        else
+            for (size_t j = 0; j < L; j++)
+                ntt_inv(&c->tab[j], n, c1 + j * n);  /* the sample is NTT(c_1): c_1 is its inverse transform */
+    }
+    const unsigned char *bytes = (const unsigned char *)boot + 64;
+    u64 *e = (u64 *)malloc(n * sizeof(u64));
+    for (size_t j = 0; j < L; j++)
+    {
+        const u64 q = c->q[j];
+        for (size_t i = 0; i < n; i++)
+        {
+            const int noise = cbd_noise(bytes + 6 * i);
+            e[i] = noise >= 0 ? (u64)noise : q - (u64)(-noise);
+            c0[j * n + i] = mulmod(sk[j * n + i], c1n[j * n + i], q);
+        }
+        if (ntt_form)
+            ntt_fwd(&c->tab[j], n, e);
+        else
+            ntt_inv(&c->tab[j], n, c0 + j * n);
+        for (size_t i = 0; i < n; i++)
+        {
+            u64 en = e[i];
+            if (c->scheme == ORC_BGV)
+                en = mulmod(en, c->t % q, q);
+            const u64 v = addmod(c0[j * n + i], en, q);
+            c0[j * n + i] = v ? q - v : 0;
+        }
+    }
+    free(e);
+    free(c1n);
+    free(boot);
+}
+
+
+/* ---- CKKSEncoder (ckks.h:455-807, ckks.cpp:20-76; util/croots.cpp; util/dwthandler.h) ----------------------------------------
+ * Floating point: every operation below is one IEEE double operation in the order the reference performs it (std::complex
+ * products expand to (ac - bd, ad + bc)); compiled without FMA contraction the results are bit-identical. */
+typedef struct
+{
+    double re, im;
+} cplx;
+static cplx c_mul(cplx a, cplx b)
+{
+    cplx r = { a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re };
+    return r;
+}
+/* util/croots.cpp:16-70: one eighth of the m-th roots from polar(), the rest through the 8-fold symmetry */
+static cplx croot(const cplx *eighth, size_t m, size_t index)
+{
+    index &= m - 1;
+    cplx r;
+    if (index <= m / 8)
+        return eighth[index];
+    if (index <= m / 4)
+    {
+        cplx a = eighth[m / 4 - index];
+        r.re = a.im, r.im = a.re;
+        return r;
+    }
+    if (index <= m / 2)
+    {
+        cplx a = croot(eighth, m, m / 2 - index);
+        r.re = -a.re, r.im = -(-a.im); /* -conj(a) */
+        return r;
+    }
+    if (index <= 3 * m / 4)
+    {
+        cplx a = croot(eighth, m, index - m / 2);
+        r.re = -a.re, r.im = -a.im;
+        return r;
+    }
+    cplx a = croot(eighth, m, m - index);
+    r.re = a.re, r.im = -a.im;
+    return r;
+}
+/* ckks.cpp:33-73: the slot -> coefficient index map and the (inverse) root powers in the order the transforms consume them */
+static void ckks_tables(size_t n, size_t *map, cplx *roots, cplx *inv_roots)
+{
+    const int logn = ilog2(n);
+    const size_t slots = n >> 1;
+    const u64 m = (u64)n << 1;
+    u64 pos = 1;
+    for (size_t i = 0; i < slots; i++)
+    {
+        const u64 index1 = (pos - 1) >> 1, index2 = (m - pos - 1) >> 1;
+        map[i] = (size_t)reverse_bits(index1, logn);
+        map[slots | i] = (size_t)reverse_bits(index2, logn);
+        pos = (pos * 3) & (m - 1);
+    }
+    roots[0].re = roots[0].im = inv_roots[0].re = inv_roots[0].im = 0;
+    if (m >= 8)
+    {
+        const double PI = 3.1415926535897932384626433832795028842;
+        cplx *eighth = (cplx *)malloc((m / 8 + 1) * sizeof(cplx));
+        for (size_t i = 0; i <= m / 8; i++)
+        {
+            const double theta = 2 * PI * (double)i / (double)m;
+            eighth[i].re = 1.0 * cos(theta), eighth[i].im = 1.0 * sin(theta);
+        }
+        for (size_t i = 1; i < n; i++)
+        {
+            roots[i] = croot(eighth, m, reverse_bits(i, logn));
+            inv_roots[i] = croot(eighth, m, reverse_bits(i - 1, logn) + 1);
+            inv_roots[i].im = -inv_roots[i].im;
+        }
+        free(eighth);
+    }
+    else if (m == 4)
+    {
+        roots[1].re = 0, roots[1].im = 1;
+        inv_roots[1].re = 0, inv_roots[1].im = -1;
+    }
+}
+/* DWTHandler::transform_from_rev with a scalar (dwthandler.h:207-311): Gentleman-Sande butterflies, the scaling merged into the
+ * last stage */
+static void fft_from_rev(cplx *v, size_t n, const cplx *roots, double scalar)
+{
+    size_t gap = 1, m = n >> 1;
+    for (; m > 1; m >>= 1, gap <<= 1)
+        for (size_t i = 0, offset = 0; i < m; i++, offset += gap << 1)
+        {
+            const cplx r = *++roots;
+            for (size_t j = 0; j < gap; j++)
+            {
+                cplx *x = v + offset + j, *y = x + gap, u = *x, w = *y, d = { u.re - w.re, u.im - w.im };
+                x->re = u.re + w.re, x->im = u.im + w.im;
+                *y = c_mul(d, r);
+            }
+        }
+    const cplx r = *++roots, sr = { r.re * scalar, r.im * scalar };
+    for (size_t j = 0; j < gap; j++)
+    {
+        cplx *x = v + j, *y = x + gap, u = *x, w = *y, d = { u.re - w.re, u.im - w.im };
+        x->re = (u.re + w.re) * scalar, x->im = (u.im + w.im) * scalar;
+        *y = c_mul(d, sr);
+    }
+}
+/* DWTHandler::transform_to_rev without a scalar (dwthandler.h:94-205): Cooley-Tukey butterflies */
+static void fft_to_rev(cplx *v, size_t n, const cplx *roots)
+{
+    size_t gap = n >> 1, m = 1;
+    for (; m <= (n >> 1); m <<= 1, gap >>= 1)
+        for (size_t i = 0, offset = 0; i < m; i++, offset += gap << 1)
+        {
+            const cplx r = *++roots;
+            for (size_t j = 0; j < gap; j++)
+            {
+                cplx *x = v + offset + j, *y = x + gap, u = *x, w = c_mul(*y, r);
+                x->re = u.re + w.re, x->im = u.im + w.im;
+                y->re = u.re - w.re, y->im = u.im - w.im;
+            }
+        }
+}
+/* CKKSEncoder::encode (vector of complex values, ckks.h:455-690): values = [count][2] doubles (re, im), count <= n/2;
+ * out = [L][n] NTT form at the level with L primes.  Returns 0, or 1 = "encoded values are too large" / "scale out of bounds" /
+ * "values must be finite". */
+int orc_ckks_encode(const orc_ctx *c, size_t L, const double *values, size_t count, double scale, uint64_t *out)
+{
+    const size_t n = c->n, slots = n >> 1;
+    const int total_bits = prod_bit_count(c->q, L);
+    if (!isnormal(scale) || scale <= 0 || ((int)log2(scale) + 1 >= total_bits) || count > slots)
+        return 1;
+    for (size_t i = 0; i < 2 * count; i++)
+        if (!isfinite(values[i]))
+            return 1;
+    size_t *map = (size_t *)malloc(n * sizeof(size_t));
+    cplx *roots = (cplx *)malloc(n * sizeof(cplx)), *inv_roots = (cplx *)malloc(n * sizeof(cplx));
+    cplx *v = (cplx *)calloc(n, sizeof(cplx));
+    ckks_tables(n, map, roots, inv_roots);
+    for (size_t i = 0; i < count; i++)
+    {
+        v[map[i]].re = values[2 * i], v[map[i]].im = values[2 * i + 1];
+        v[map[i + slots]].re = values[2 * i], v[map[i + slots]].im = -values[2 * i + 1];
+    }
+    const double fix = scale / (double)n;
+    fft_from_rev(v, n, inv_roots, fix);
+    int rc = 0;
+    double max_coeff = 0;
+    for (size_t i = 0; i < n; i++)
+    {
+        const double a = fabs(v[i].re);
+        if (isnan(a))
+            rc = 1;
+        max_coeff = a > max_coeff ? a : max_coeff;
+    }
+    if (!rc && !isfinite(max_coeff))
+        rc = 1;
+    if (!rc && (int)ceil(log2(max_coeff > 1.0 ? max_coeff : 1.0)) + 1 >= total_bits)
+        rc = 1;
+    for (size_t i = 0; !rc && i < n; i++)
+    {
+        /* the three decomposition branches of the reference (<= 64 bits, <= 128 bits, multi-precision) all reduce the exact
+         * integer |round(coefficient)|: mantissa * 2^exponent here */
+        double d = round(v[i].re);
+        const int negative = signbit(d);
+        d = fabs(d);
+        int e = 0;
+        u64 mant = 0;
+        if (d >= 1)
+        {
+            const double f = frexp(d, &e); /* d = f 2^e, f in [0.5, 1) */
+            mant = (u64)ldexp(f, 53);      /* exact: 53-bit integer */
+            e -= 53;
+            while (e < 0)                  /* d is an integer: the shifted-out bits are zero */
+                mant >>= 1, e++;
+        }
+        for (size_t j = 0; j < L; j++)
+        {
+            const u64 q = c->q[j];
+            u64 r = mulmod(mant % q, powmod(2, (u64)e, q), q);
+            out[j * n + i] = negative && r ? q - r : r;
+        }
+    }
+    for (size_t j = 0; !rc && j < L; j++)
+        ntt_fwd(&c->tab[j], n, out + j * n);
+    free(v), free(roots), free(inv_roots), free(map);
+    return rc;
+}
+/* CKKSEncoder::decode (ckks.h:692-790): plain = [L][n] NTT form, scale = Plaintext::scale(); out = [n/2][2] doubles (re, im) */
+int orc_ckks_decode(const orc_ctx *c, size_t L, const uint64_t *plain, double scale, double *out)
+{
+    const size_t n = c->n, slots = n >> 1;
+    const int total_bits = prod_bit_count(c->q, L);
+    if (!isnormal(scale) || scale <= 0 || ((int)log2(scale) >= total_bits))
+        return 1;
+    const double inv_scale = 1.0 / scale, two_pow_64 = 18446744073709551616.0;
+    /* big integers of L words: Q = prod q_j, the punctured products Q / q_j, the threshold (Q + 1) / 2 (context.cpp:406-412) */
+    u64 *Q = (u64 *)calloc(L + 1, sizeof(u64)), *punct = (u64 *)calloc(L * (L + 1), sizeof(u64)), *thr = (u64 *)calloc(L + 1, sizeof(u64));
+    u64 *invp = (u64 *)calloc(L, sizeof(u64));
+    for (size_t j = 0; j <= L; j++)
+    {
+        u64 *dst = j < L ? punct + j * (L + 1) : Q;
+        dst[0] = 1;
+        for (size_t i = 0; i < L; i++)
+        {
+            if (i == j)
+                continue;
+            u64 carry = 0;
+            for (size_t w = 0; w < L; w++)
+            {
+                const u128 t = (u128)dst[w] * c->q[i] + carry;
+                dst[w] = (u64)t, carry = (u64)(t >> 64);
+            }
+        }
+        if (j < L)
+        {
+            u64 pm = 1;
+            for (size_t i = 0; i < L; i++)
+                if (i != j)
+                    pm = mulmod(pm, c->q[i] % c->q[j], c->q[j]);
+            invp[j] = powmod(pm, c->q[j] - 2, c->q[j]);
+        }
+    }
+    {
+        u64 carry = 1; /* (Q + 1) >> 1 */
+        for (size_t w = 0; w < L; w++)
+        {
+            const u64 t = Q[w] + carry;
+            carry = t < carry;
+            thr[w] = t;
+        }
+        for (size_t w = 0; w < L; w++)
+            thr[w] = (thr[w] >> 1) | (w + 1 < L ? thr[w + 1] << 63 : carry << 63);
+    }
+    u64 *coef = (u64 *)malloc(L * n * sizeof(u64));
+    memcpy(coef, plain, L * n * sizeof(u64));
+    for (size_t j = 0; j < L; j++)
+        ntt_inv(&c->tab[j], n, coef + j * n);
+    size_t *map = (size_t *)malloc(n * sizeof(size_t));
+    cplx *roots = (cplx *)malloc(n * sizeof(cplx)), *inv_roots = (cplx *)malloc(n * sizeof(cplx));
+    cplx *res = (cplx *)calloc(n, sizeof(cplx));
+    ckks_tables(n, map, roots, inv_roots);
+    u64 *val = (u64 *)malloc((L + 1) * sizeof(u64)), *tmp = (u64 *)malloc((L + 1) * sizeof(u64));
+    for (size_t i = 0; i < n; i++)
+    {
+        /* RNSBase::compose (rns.cpp:321-352): sum_j [x_j (Q/q_j)^-1 mod q_j] (Q/q_j) mod Q */
+        memset(val, 0, (L + 1) * sizeof(u64));
+        for (size_t j = 0; j < L; j++)
+        {
+            const u64 t = mulmod(coef[j * n + i], invp[j], c->q[j]);
+            u64 carry = 0;
+            for (size_t w = 0; w < L; w++)
+            {
+                const u128 p = (u128)punct[j * (L + 1) + w] * t + carry;
+                tmp[w] = (u64)p, carry = (u64)(p >> 64);
+            }
+            u64 cy = 0;
+            for (size_t w = 0; w < L; w++)
+            {
+                const u128 a = (u128)val[w] + tmp[w] + cy;
+                val[w] = (u64)a, cy = (u64)(a >> 64);
+            }
+            int ge = cy != 0;
+            if (!ge)
+            {
+                ge = 1;
+                for (size_t w = L; w-- > 0;)
+                    if (val[w] != Q[w])
+                    {
+                        ge = val[w] > Q[w];
+                        break;
+                    }
+            }
+            if (ge)
+            {
+                u64 bw = 0;
+                for (size_t w = 0; w < L; w++)
+                {
+                    const u128 a = (u128)val[w] - Q[w] - bw;
+                    val[w] = (u64)a, bw = (u64)(a >> 64) & 1;
+                }
+            }
+        }
+        int upper = 1;
+        for (size_t w = L; w-- > 0;)
+            if (val[w] != thr[w])
+            {
+                upper = val[w] > thr[w];
+                break;
+            }
+        double acc = 0.0, s64 = inv_scale;
+        for (size_t w = 0; w < L; w++, s64 *= two_pow_64)
+        {
+            if (upper)
+            {
+                if (val[w] > Q[w])
+                {
+                    const u64 diff = val[w] - Q[w];
+                    acc += diff ? (double)diff * s64 : 0.0;
+                }
+                else
+                {
+                    const u64 diff = Q[w] - val[w];
+                    acc -= diff ? (double)diff * s64 : 0.0;
+                }
+            }
+            else
+                acc += val[w] ? (double)val[w] * s64 : 0.0;
+        }
+        res[i].re = acc, res[i].im = 0.0;
+    }
+    fft_to_rev(res, n, roots);
+    for (size_t i = 0; i < slots; i++)
+        out[2 * i] = res[map[i]].re, out[2 * i + 1] = res[map[i]].im;
+    free(val), free(tmp), free(res), free(roots), free(inv_roots), free(map), free(coef), free(Q), free(punct), free(thr), free(invp);
+    return 0;
+}
+
+
+/* ---- public-key encryption of zero (Encryptor::encrypt_zero_internal, encryptor.cpp:88-174 -> util::encrypt_zero_asymmetric,
+ * util/rlwe.cpp:184-276) --------------------------------------------------------------------------------------------------
+ * One PRNG (Blake2xb of `seed`) yields, in this order: the ternary polynomial u (sample_poly_ternary, rlwe.cpp:21-39: one 32-bit
+ * word per coefficient through std::uniform_int_distribution<uint64_t>(0, 2) -- libstdc++ >= 11 maps a 32-bit generator word r to
+ * (r * 3) >> 32 and redraws when the low half of r * 3 is below 2^32 mod 3 = 1, i.e. for r == 0 only, bits/uniform_int_dist.h
+ * _S_nd), then the noise polynomials e_0, e_1 (sample_poly_cbd, 6 bytes per coefficient).  c_j = pk_j u + e_j (BGV: t e_j) at
+ * the level ABOVE the requested one (one more prime: the level's prev_context_data), followed by the scheme's
+ * divide-and-round by that prime; at the key level (L == k) there is no level above and the sample is returned as is.
+ * pk = [2][k][n] NTT form (PublicKey::data()); out = [2][L][n]. */
+void orc_encrypt_zero_asymmetric(const orc_ctx *c, size_t L, const uint64_t *pk, const uint64_t seed[8], uint64_t *out2)
+{
+    const size_t n = c->n, k = c->k, Lp = L < k ? L + 1 : L;
+    const int ntt_form = c->scheme != ORC_BFV;
+    const size_t words = (4 * n + 12 * n + 7) / 8 + 64; /* spare words for (astronomically rare) ternary redraws */
+    u64 *stream = (u64 *)malloc(words * sizeof(u64));
+    orc_blake2xb_stream(seed, words, stream);
+    const uint32_t *w32 = (const uint32_t *)stream;
+    size_t pos = 0; /* in 32-bit words */
+    u64 *u = (u64 *)malloc(Lp * n * sizeof(u64)), *t2 = (u64 *)malloc(2 * Lp * n * sizeof(u64)), *e = (u64 *)malloc(n * sizeof(u64));
+    for (size_t i = 0; i < n; i++)
+    {
+        uint64_t product = (uint64_t)w32[pos++] * 3u;
+        while ((uint32_t)product < 1u)
+            product = (uint64_t)w32[pos++] * 3u;
+        const u64 r = product >> 32;
+        for (size_t j = 0; j < Lp; j++)
+            u[j * n + i] = r + (r == 0 ? c->q[j] : 0) - 1;
+    }
+    for (size_t j = 0; j < Lp; j++)
+        ntt_fwd(&c->tab[j], n, u + j * n);
+    const unsigned char *bytes = (const unsigned char *)stream + 4 * pos;
+    for (size_t p = 0; p < 2; p++)
+        for (size_t j = 0; j < Lp; j++)
+        {
+            const u64 q = c->q[j];
+            u64 *dst = t2 + (p * Lp + j) * n;
+            const u64 *key = pk + (p * k + j) * n;
+            for (size_t i = 0; i < n; i++)
+                dst[i] = mulmod(u[j * n + i], key[i], q);
+            if (!ntt_form)
+                ntt_inv(&c->tab[j], n, dst);
+            for (size_t i = 0; i < n; i++)
+            {
+                const int noise = cbd_noise(bytes + 6 * (p * n + i));
+                e[i] = noise >= 0 ? (u64)noise : q - (u64)(-noise);
+            }
+            if (ntt_form)
+                ntt_fwd(&c->tab[j], n, e);
+            for (size_t i = 0; i < n; i++)
+            {
+                u64 en = e[i];
+                if (c->scheme == ORC_BGV)
+                    en = mulmod(en, c->t % q, q);
+                dst[i] = addmod(dst[i], en, q);
+            }
+        }
+    if (Lp == L)
+        memcpy(out2, t2, 2 * L * n * sizeof(u64));
+    else if (c->scheme == ORC_CKKS)
+        orc_rescale(c, Lp, t2, out2);
+    else if (c->scheme == ORC_BFV)
+        orc_bfv_mod_switch(c, Lp, t2, out2);
+    else
+        orc_bgv_mod_switch(c, Lp, t2, out2);
+    free(stream), free(u), free(t2), free(e);
 }

@@ -97,6 +97,16 @@ int orc_bgv_decrypt(const orc_ctx *c, size_t L, size_t size, uint64_t correction
  * seed = prng_seed_type (8 words); out = the polynomial [L][n] the seed expands into at the level with L primes */
 void orc_blake2xb_stream(const uint64_t seed[8], size_t words, uint64_t *out); /* the first `words` 64-bit words of the PRNG's output */
 void orc_expand_seed(const orc_ctx *c, size_t L, const uint64_t seed[8], uint64_t *out);
+/* Encryptor::encrypt_zero (public key; encryptor.cpp:88-174, util/rlwe.cpp:184-276) with the PRNG seeded by `seed`; pk = [2][k][n]
+ * NTT form; out = [2][L][n] at the level with L primes (sampled one level above and divided down, L == k: sampled directly) */
+void orc_encrypt_zero_asymmetric(const orc_ctx *c, size_t L, const uint64_t *pk, const uint64_t seed[8], uint64_t *out2);
+/* CKKSEncoder::encode / decode of complex vectors (ckks.h:455-807): values = [count][2] doubles, plaintext = [L][n] NTT form;
+ * return 0, or 1 for the reference's invalid_argument cases (values too large, scale out of bounds, non-finite input) */
+int orc_ckks_encode(const orc_ctx *c, size_t L, const double *values, size_t count, double scale, uint64_t *out);
+int orc_ckks_decode(const orc_ctx *c, size_t L, const uint64_t *plain, double scale, double *out);
+/* encrypt_zero_symmetric (util/rlwe.cpp:264-408) with the bootstrap PRNG seeded by `seed`; sk = [k][n] NTT form; out = [2][L][n] at
+ * the first data level; save_seed selects which BFV variant (the Serializable one or the plain one) */
+void orc_encrypt_zero_symmetric(const orc_ctx *c, size_t L, const uint64_t *sk, const uint64_t seed[8], int save_seed, uint64_t *out2);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ SYMBOLS = [
     "sb200_relinearize_host", "sb200_multiply_relinearize_host", "sb200_rescale_to_next_host",
     "sb200_mod_switch_to_next_host", "sb200_apply_galois_host", "sb200_get_parms_id", "sb200_ciphertext_inspect",
     "sb200_ciphertext_save_size", "sb200_ciphertext_load", "sb200_ciphertext_save", "sb200_secret_key_create",
-    "sb200_secret_key_destroy", "sb200_decrypt", "sb200_decrypt_host",
+    "sb200_secret_key_destroy", "sb200_decrypt", "sb200_decrypt_host", "sb200_encrypt_zero_symmetric", "sb200_public_key_create", "sb200_public_key_destroy", "sb200_encrypt_zero_asymmetric", "sb200_ckks_encode", "sb200_ckks_decode", "sb200_ckks_encode_host", "sb200_ckks_decode_host",
     "sb200_group_create", "sb200_group_destroy", "sb200_group_size", "sb200_group_context", "sb200_group_slice",
     "sb200_group_kswitch_key_create", "sb200_group_kswitch_key_destroy", "sb200_group_multiply_relinearize_host",
     "sb200_group_relinearize_host", "sb200_group_apply_galois_host", "sb200_group_multiply_host", "sb200_group_rescale_to_next_host",
@@ -136,6 +136,14 @@ def lib():
         L.sb200_secret_key_create.argtypes = [vp, _u64p, C.POINTER(vp)]
         L.sb200_secret_key_destroy.argtypes = [vp]
         L.sb200_decrypt.argtypes = [vp, vp, sz, sz, sz, vp, _u64p, vp, vp]
+        L.sb200_ckks_encode.argtypes = [vp, sz, sz, vp, sz, i32, C.c_double, vp, vp]
+        L.sb200_ckks_decode.argtypes = [vp, sz, sz, vp, C.c_double, vp, vp]
+        L.sb200_ckks_encode_host.argtypes = [vp, sz, sz, vp, sz, i32, C.c_double, _u64p]
+        L.sb200_ckks_decode_host.argtypes = [vp, sz, sz, _u64p, C.c_double, vp]
+        L.sb200_public_key_create.argtypes = [vp, _u64p, C.POINTER(vp)]
+        L.sb200_public_key_destroy.argtypes = [vp]
+        L.sb200_encrypt_zero_asymmetric.argtypes = [vp, vp, sz, sz, _u64p, vp, vp]
+        L.sb200_encrypt_zero_symmetric.argtypes = [vp, vp, sz, sz, _u64p, i32, vp, _u64p, vp]
         L.sb200_decrypt_host.argtypes = [vp, vp, sz, sz, sz, _u64p, _u64p, _u64p]
         _lib = L
     return _lib
@@ -196,6 +204,26 @@ class KSwitchKey:
         try:
             if getattr(self, "h", None):
                 lib().sb200_kswitch_key_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class PublicKey:
+    """Encryptor state: the public key ([2][k][n], NTT form at the key level) on the device."""
+
+    def __init__(self, ctx, host_key):
+        host_key = np.ascontiguousarray(host_key, dtype=np.uint64)
+        assert host_key.shape == (2, ctx.k, ctx.n)
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(lib().sb200_public_key_create(ctx.h, _hp(host_key), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().sb200_public_key_destroy(self.h)
                 self.h = None
         except Exception:
             pass
@@ -405,6 +433,34 @@ class Context:
         _check(lib().sb200_batch_decode_host(self.h, p.shape[0], _hp(p), _hp(out)))
         return out[0] if single else out
 
+    def ckks_encode(self, values, L, scale):
+        """CKKSEncoder.encode: values [B][count] (or [count]) complex128 / float64 -> plaintexts [B][L][n] (NTT form)"""
+        v = np.asarray(values)
+        is_complex = np.iscomplexobj(v)
+        v = np.ascontiguousarray(v, dtype=np.complex128 if is_complex else np.float64)
+        single = v.ndim == 1
+        v2 = v[None] if single else v
+        B, count = v2.shape
+        out = np.zeros((B, L, self.n), dtype=np.uint64)
+        _check(lib().sb200_ckks_encode_host(self.h, L, B, v2.ctypes.data if count else None, count, int(is_complex), float(scale), _hp(out)))
+        return out[0] if single else out
+
+    def ckks_decode(self, plain, scale):
+        """CKKSEncoder.decode: plaintexts [B][L][n] (or [L][n]) -> [B][n/2] complex128"""
+        p = np.ascontiguousarray(plain, dtype=np.uint64)
+        single = p.ndim == 2
+        p2 = p[None] if single else p
+        B, L, n = p2.shape
+        out = np.zeros((B, n // 2), dtype=np.complex128)
+        _check(lib().sb200_ckks_decode_host(self.h, L, B, _hp(p2), float(scale), out.ctypes.data))
+        return out[0] if single else out
+
+    def d_ckks_encode(self, values, plain, L, batch, count, is_complex, scale):
+        _check(lib().sb200_ckks_encode(self.h, L, batch, _dp(values), count, int(is_complex), float(scale), _dp(plain), self._stream()))
+
+    def d_ckks_decode(self, plain, values, L, batch, scale):
+        _check(lib().sb200_ckks_decode(self.h, L, batch, _dp(plain), float(scale), _dp(values), self._stream()))
+
     def load_secret_key(self, host_key):
         return SecretKey(self, host_key)
 
@@ -540,6 +596,24 @@ class Context:
             m.is_ntt_form, m.scale, m.correction_factor = int(is_ntt_form), scale, correction_factor
         _check(lib().sb200_ciphertext_save(self.h, batch, L, size, _dp(t), meta, outs, cap, self._stream()))
         return [b.raw for b in bufs]
+
+    def load_public_key(self, host_key):
+        return PublicKey(self, host_key)
+
+    def d_encrypt_zero_asymmetric(self, pk, out2, L, batch, seeds=None):
+        """Encryptor(public key).encrypt_zero for a batch into the device slab out2 [batch][2][L][n]; seeds [batch][8] words (None =
+        fresh from the OS entropy source)"""
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64).reshape(batch, 8)
+        _check(lib().sb200_encrypt_zero_asymmetric(self.h, pk.h, L, batch, None if seeds is None else _hp(seeds), _dp(out2), self._stream()))
+
+    def d_encrypt_zero_symmetric(self, sk, out2, L, batch, bootstrap_seeds=None, save_seed=False, want_public_seeds=False):
+        """Encryptor.encrypt_zero_symmetric for a batch into the device slab out2 [batch][2][L][n]; bootstrap_seeds [batch][8] words
+        (None = fresh from the OS entropy source); returns the public seeds [batch][8] when asked for (the seeded wire form)"""
+        seeds = None if bootstrap_seeds is None else np.ascontiguousarray(bootstrap_seeds, dtype=np.uint64).reshape(batch, 8)
+        pub = np.zeros((batch, 8), dtype=np.uint64) if want_public_seeds else None
+        _check(lib().sb200_encrypt_zero_symmetric(self.h, sk.h, L, batch, None if seeds is None else _hp(seeds), int(save_seed), _dp(out2),
+                                                  None if pub is None else _hp(pub), self._stream()))
+        return pub
 
     def d_relinearize(self, in3, key, out2, L, batch):
         _check(lib().sb200_relinearize(self.h, L, batch, _dp(in3), key.h, _dp(out2), self._stream()))

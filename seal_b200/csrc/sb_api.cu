@@ -3,6 +3,7 @@
 // (native/src/seal/c/defines.h:72-96) and the message is kept in a thread-local string.
 #include "../../include/seal_b200.h"
 #include "sb_engine.cuh"
+#include <random>
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -17,6 +18,18 @@ static thread_local std::string g_last_error;
 struct sb200_context
 {
     std::unique_ptr<Context> c;
+};
+struct sb200_public_key
+{
+    PublicKey k;
+    ~sb200_public_key()
+    {
+        if (k.d_key && k.ctx)
+        {
+            cudaSetDevice(k.ctx->device);
+            cudaFree(k.d_key);
+        }
+    }
 };
 struct sb200_secret_key
 {
@@ -1459,6 +1472,169 @@ int sb200_secret_key_destroy(sb200_secret_key *key)
     return SB200_OK;
 }
 
+// ---- Encryptor(context, public_key)::encrypt_zero (sb_prng.cu) ----
+int sb200_public_key_create(sb200_context *ctx, const uint64_t *h_public_key, sb200_public_key **out)
+{
+    SB_NEED(h_public_key);
+    SB_NEED(out);
+    SB_TRY
+    SB_ENTER(ctx)
+    auto h = std::make_unique<sb200_public_key>();
+    public_key_create(c, (const u64 *)h_public_key, h->k);
+    *out = h.release();
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_public_key_destroy(sb200_public_key *key)
+{
+    SB_NEED(key);
+    delete key;
+    return SB200_OK;
+}
+
+namespace
+{
+    // fresh PRNG seeds from the OS entropy source, as UniformRandomGeneratorFactory::create does (randomgen.cpp:34-50); wiped on scope exit
+    struct FreshSeeds
+    {
+        std::vector<u64> words;
+        explicit FreshSeeds(size_t batch) : words(batch * 8)
+        {
+            std::random_device rd("/dev/urandom");
+            for (auto &w : words)
+                w = (static_cast<u64>(rd()) << 32) | static_cast<u64>(rd());
+        }
+        ~FreshSeeds()
+        {
+            volatile u64 *w = words.data(); // the seeds determine the noise: do not leave them on the heap
+            for (size_t i = 0; i < words.size(); i++)
+                w[i] = 0;
+        }
+    };
+} // namespace
+
+int sb200_encrypt_zero_asymmetric(sb200_context *ctx, sb200_public_key *key, size_t L, size_t batch, const uint64_t *h_seeds, uint64_t *d_out,
+                                  void *stream)
+{
+    SB_NEED(key);
+    SB_NEED(d_out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    std::unique_ptr<FreshSeeds> fresh;
+    if (!h_seeds)
+    {
+        fresh = std::make_unique<FreshSeeds>(batch);
+        h_seeds = reinterpret_cast<const uint64_t *>(fresh->words.data());
+    }
+    // returns after a stream synchronisation: the seeds may be wiped
+    op_encrypt_zero_asymmetric(c, key->k, L, batch, (const u64 *)h_seeds, (u64 *)d_out, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+// ---- CKKSEncoder::encode / decode (sb_ckks.cu) ----
+int sb200_ckks_encode(sb200_context *ctx, size_t L, size_t batch, const double *d_values, size_t count, int is_complex, double scale,
+                      uint64_t *d_plain, void *stream)
+{
+    SB_NEED(d_plain);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_ckks_encode(c, L, batch, d_values, count, is_complex != 0, scale, (u64 *)d_plain, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_ckks_decode(sb200_context *ctx, size_t L, size_t batch, const uint64_t *d_plain, double scale, double *d_values, void *stream)
+{
+    SB_NEED(d_plain);
+    SB_NEED(d_values);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    op_ckks_decode(c, L, batch, (const u64 *)d_plain, scale, d_values, static_cast<cudaStream_t>(stream));
+    return SB200_OK;
+    SB_CATCH
+}
+
+namespace
+{
+    struct DevBuf // scoped device allocation of the (not hot) host-buffer encoder entry points
+    {
+        void *p = nullptr;
+        explicit DevBuf(size_t bytes)
+        {
+            cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc");
+        }
+        ~DevBuf()
+        {
+            cudaFree(p);
+        }
+        DevBuf(const DevBuf &) = delete;
+        DevBuf &operator=(const DevBuf &) = delete;
+    };
+} // namespace
+
+int sb200_ckks_encode_host(sb200_context *ctx, size_t L, size_t batch, const double *h_values, size_t count, int is_complex, double scale,
+                           uint64_t *h_plain)
+{
+    SB_NEED(h_plain);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, nullptr)
+    check_level(c, L, batch);
+    if (count && !h_values)
+        throw std::invalid_argument("values cannot be null");
+    const size_t vbytes = batch * count * (is_complex ? 16 : 8), pbytes = batch * L * c.n * sizeof(u64);
+    DevBuf v(vbytes), p(pbytes);
+    if (vbytes)
+        cuda_check(cudaMemcpy(v.p, h_values, vbytes, cudaMemcpyHostToDevice), "values H2D");
+    op_ckks_encode(c, L, batch, static_cast<const double *>(v.p), count, is_complex != 0, scale, static_cast<u64 *>(p.p), nullptr);
+    cuda_check(cudaMemcpy(h_plain, p.p, pbytes, cudaMemcpyDeviceToHost), "plain D2H");
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_ckks_decode_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *h_plain, double scale, double *h_values)
+{
+    SB_NEED(h_plain);
+    SB_NEED(h_values);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, nullptr)
+    check_level(c, L, batch);
+    const size_t vbytes = batch * (c.n / 2) * 16, pbytes = batch * L * c.n * sizeof(u64);
+    DevBuf v(vbytes), p(pbytes);
+    cuda_check(cudaMemcpy(p.p, h_plain, pbytes, cudaMemcpyHostToDevice), "plain H2D");
+    op_ckks_decode(c, L, batch, static_cast<const u64 *>(p.p), scale, static_cast<double *>(v.p), nullptr);
+    cuda_check(cudaMemcpy(h_values, v.p, vbytes, cudaMemcpyDeviceToHost), "values D2H");
+    return SB200_OK;
+    SB_CATCH
+}
+
+// Encryptor::encrypt_zero_symmetric for a batch (sb_prng.cu); h_bootstrap_seeds == nullptr: fresh seeds from the OS entropy source,
+// as UniformRandomGeneratorFactory::create does through random_uint64 (randomgen.cpp:34-50)
+int sb200_encrypt_zero_symmetric(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t batch, const uint64_t *h_bootstrap_seeds,
+                                 int save_seed, uint64_t *d_out, uint64_t *h_public_seeds, void *stream)
+{
+    SB_NEED(key);
+    SB_NEED(d_out);
+    SB_TRY
+    SB_ENTER_STREAM(ctx, stream)
+    check_level(c, L, batch);
+    std::unique_ptr<FreshSeeds> fresh;
+    if (!h_bootstrap_seeds)
+    {
+        fresh = std::make_unique<FreshSeeds>(batch);
+        h_bootstrap_seeds = reinterpret_cast<const uint64_t *>(fresh->words.data());
+    }
+    op_encrypt_zero_symmetric(c, key->k, L, batch, (const u64 *)h_bootstrap_seeds, save_seed != 0, (u64 *)d_out, (u64 *)h_public_seeds,
+                              static_cast<cudaStream_t>(stream));
+    // op_encrypt_zero_symmetric synchronised the stream while expanding c_1: the seeds have been consumed and may be wiped
+    return SB200_OK;
+    SB_CATCH
+}
+
 int sb200_decrypt(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t size, size_t batch, const uint64_t *ct,
                   const uint64_t *h_correction_factors, uint64_t *plain, void *stream)
 {
@@ -1469,6 +1645,7 @@ int sb200_decrypt(sb200_context *ctx, sb200_secret_key *key, size_t L, size_t si
     SB_ENTER_STREAM(ctx, stream)
     check_level(c, L, batch);
     op_decrypt(c, key->k, L, size, batch, (const u64 *)ct, (const u64 *)h_correction_factors, (u64 *)plain, static_cast<cudaStream_t>(stream));
+    c.wipe_scratch(static_cast<cudaStream_t>(stream)); // the decryption phases (decryptor.cpp:106-109 keeps them in a clearing pool)
     return SB200_OK;
     SB_CATCH
 }
@@ -1488,6 +1665,12 @@ int sb200_decrypt_host(sb200_context *ctx, sb200_secret_key *key, size_t L, size
         op_decrypt(c, key->k, L, size, B, da, h_correction_factors ? (const u64 *)h_correction_factors + done : nullptr, dout, st);
         done += B;
     });
+    // phases and plaintexts do not stay behind in the arenas (the reference decrypts inside a clear-on-destruction pool)
+    c.wipe_scratch(c.io.s_comp);
+    for (int slot = 0; slot < 2; slot++)
+        if (c.io.buf[slot][2])
+            cuda_check(cudaMemsetAsync(c.io.buf[slot][2], 0, c.io.cap[slot][2] * sizeof(u64), c.io.s_comp), "wipe staging");
+    cuda_check(cudaStreamSynchronize(c.io.s_comp), "synchronize");
     return SB200_OK;
     SB_CATCH
 }

@@ -43,6 +43,15 @@ namespace sb
             cudaFree(kv.second.d_consts);
         for (auto &kv : plain_levels)
             cudaFree(kv.second.d_delta);
+        cudaFree(ckks.d_roots);
+        cudaFree(ckks.d_inv_roots);
+        cudaFree(ckks.d_map);
+        cudaFree(ckks.d_stat);
+        for (auto &kv : ckks_levels)
+        {
+            cudaFree(kv.second.d_big);
+            cudaFree(kv.second.d_invp);
+        }
         cudaFree(scratch);
         cudaFree(aux_buf);
         cudaFree(d_flag);
@@ -85,7 +94,20 @@ namespace sb
             cuda_check(cudaMalloc(&scratch, bytes), "cudaMalloc(scratch)");
             scratch_bytes = bytes;
         }
+        scratch_used = bytes;
         return scratch;
+    }
+
+    void Context::wipe_scratch(cudaStream_t st)
+    {
+        if (scratch && scratch_used)
+            cuda_check(cudaMemsetAsync(scratch, 0, std::min(scratch_used, scratch_bytes), st), "wipe scratch");
+    }
+
+    void Context::wipe_aux(cudaStream_t st)
+    {
+        if (aux_buf && aux_used)
+            cuda_check(cudaMemsetAsync(aux_buf, 0, std::min(aux_used, aux_bytes), st), "wipe aux");
     }
 
     void *Context::ensure_aux(size_t bytes)
@@ -99,6 +121,7 @@ namespace sb
             cuda_check(cudaMalloc(&aux_buf, bytes), "cudaMalloc(aux)");
             aux_bytes = bytes;
         }
+        aux_used = bytes;
         return aux_buf;
     }
 

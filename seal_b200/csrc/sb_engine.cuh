@@ -29,6 +29,13 @@ namespace sb
         size_t powers = 0;
     };
 
+    // PublicKey::data() on the device: [2][k][n], NTT form at the key level
+    struct PublicKey
+    {
+        struct Context *ctx = nullptr;
+        u64 *d_key = nullptr;
+    };
+
     struct KSwitchKey
     {
         struct Context *ctx = nullptr;
@@ -89,6 +96,21 @@ namespace sb
             u64 q_mod_t = 0;        // ContextData::coeff_modulus_mod_plain_modulus
         };
         std::map<size_t, PlainLevel> plain_levels;
+        // CKKSEncoder on the device (sb_ckks.cu): complex root tables + slot map, built on first use; per-level big integers for decode
+        struct CkksEncoder
+        {
+            bool ready = false;
+            void *d_roots = nullptr, *d_inv_roots = nullptr; // double2 [n]
+            uint32_t *d_map = nullptr;                       // matrix_reps_index_map_
+            void *d_stat = nullptr;                          // { max |coefficient| bits, flags }
+        } ckks;
+        struct CkksLevel
+        {
+            int total_bits = 0;
+            u64 *d_big = nullptr; // [Q | (Q+1)/2 | Q/q_j ...] words
+            Tw *d_invp = nullptr; // (Q/q_j)^-1 mod q_j
+        };
+        std::map<size_t, CkksLevel> ckks_levels;
         u64 *d_t_mod_q = nullptr;   // [k]: t mod q_i
         u64 t_ratio_lo = 0, t_ratio_hi = 0; // floor(2^128 / t)
         std::vector<std::array<u64, 4>> parms_ids; // parms_ids[L-1] = parms_id of the level with L primes (sb_wire.hpp)
@@ -98,6 +120,7 @@ namespace sb
         int *d_flag = nullptr;               // result word of the range check (op_residues_in_range)
         void *aux_buf = nullptr;             // second grow-only arena (size-3 intermediate of BFV multiply+relinearize)
         size_t aux_bytes = 0;
+        size_t scratch_used = 0, aux_used = 0; // bytes of the latest ensure_scratch / ensure_aux request (what wipe_* clears)
         size_t scratch_bytes = 0, table_bytes = 0, scratch_budget = size_t(8) << 30;
         size_t ks_chunk_max = 0;                       // 0 = derived from scratch_budget (sb200_context_set_limit)
         size_t host_stage_bytes = size_t(640) << 20;   // per pipeline slot of the *_host entry points
@@ -112,6 +135,10 @@ namespace sb
         ~Context();
         void *ensure_scratch(size_t bytes);
         void *ensure_aux(size_t bytes);
+        // secret-dependent intermediates (decryption phases, encryption noise) do not stay in the arenas: the reference keeps them in
+        // clear-on-destruction pools (decryptor.cpp:106-109, util/rlwe.cpp:195, 292)
+        void wipe_scratch(cudaStream_t st);
+        void wipe_aux(cudaStream_t st);
         const uint32_t *galois_table(uint32_t elt);
         size_t prime_id_aux(size_t aux_index) const { return k + aux_index; }
     };
@@ -159,6 +186,16 @@ namespace sb
     // Ciphertext::expand_seed on the device (sb_prng.cu): seeds [B][8] host words, dst_off [B] host word offsets into d_out of the
     // polynomial ([L][n]) each seed expands into; returns after the expansion has been enqueued and the host arrays are free
     void op_expand_seeded(Context &c, size_t L, size_t B, const u64 *h_seeds, const long long *h_dst_off, u64 *d_out, cudaStream_t st);
+    // Encryptor::encrypt_zero_symmetric on the device (sb_prng.cu): bootstrap seeds [B][8] on the host, out [B][2][L][n]
+    void op_encrypt_zero_symmetric(Context &c, const SecretKey &sk, size_t L, size_t B, const u64 *h_boot_seeds, bool save_seed, u64 *d_out,
+                                   u64 *h_public_seeds, cudaStream_t st);
+    // Encryptor(public key)::encrypt_zero on the device (sb_prng.cu): seeds [B][8] on the host, out [B][2][L][n]
+    void public_key_create(Context &c, const u64 *h_pk, PublicKey &out);
+    void op_encrypt_zero_asymmetric(Context &c, const PublicKey &pk, size_t L, size_t B, const u64 *h_seeds, u64 *d_out, cudaStream_t st);
+    // CKKSEncoder::encode / decode (sb_ckks.cu): values = device doubles, [B][count] complex pairs (or reals); plain = [B][L][n] NTT form
+    void op_ckks_encode(Context &c, size_t L, size_t B, const double *values, size_t count, bool is_complex, double scale, u64 *plain,
+                        cudaStream_t st);
+    void op_ckks_decode(Context &c, size_t L, size_t B, const u64 *plain, double scale, double *values, cudaStream_t st);
     const sbh::BehzLevel &behz_host(Context &c, size_t L);
     // wire format support (sb_api.cu): 1 if any residue of data [rows][n] (prime of a row = row % L) is >= its modulus
     bool op_residues_in_range(Context &c, size_t L, size_t rows, const u64 *d, cudaStream_t st);

@@ -1,4 +1,5 @@
 // seal_b200/csrc/sb_host.cpp -- host-side precomputation; see sb_host.hpp.
+#include <complex>
 #include "sb_host.hpp"
 #include <algorithm>
 #include <map>
@@ -320,5 +321,103 @@ namespace sbh
             t[i] = static_cast<std::uint32_t>(reverse_bits(raw, logn));
         }
         return t;
+    }
+
+    // ---- CKKSEncoder tables ----
+    namespace
+    {
+        using cd = std::complex<double>;
+        // ComplexRoots::get_root (util/croots.cpp:41-70)
+        cd complex_root(const std::vector<cd> &eighth, std::size_t m, std::size_t index)
+        {
+            index &= m - 1;
+            if (index <= m / 8)
+                return eighth[index];
+            if (index <= m / 4)
+            {
+                const cd a = eighth[m / 4 - index];
+                return cd(a.imag(), a.real());
+            }
+            if (index <= m / 2)
+                return -std::conj(complex_root(eighth, m, m / 2 - index));
+            if (index <= 3 * m / 4)
+                return -complex_root(eighth, m, index - m / 2);
+            return std::conj(complex_root(eighth, m, m - index));
+        }
+    } // namespace
+
+    CkksTables ckks_tables(std::size_t n)
+    {
+        const int logn = ilog2(n);
+        const std::size_t m = n << 1;
+        CkksTables t;
+        t.roots.assign(2 * n, 0.0);
+        t.inv_roots.assign(2 * n, 0.0);
+        if (m >= 8)
+        {
+            constexpr double PI = 3.1415926535897932384626433832795028842; // ComplexRoots::PI_ (util/croots.h)
+            std::vector<cd> eighth(m / 8 + 1);
+            for (std::size_t i = 0; i <= m / 8; i++)
+                eighth[i] = std::polar<double>(1.0, 2 * PI * static_cast<double>(i) / static_cast<double>(m));
+            for (std::size_t i = 1; i < n; i++)
+            {
+                const cd r = complex_root(eighth, m, reverse_bits(i, logn));
+                const cd ir = std::conj(complex_root(eighth, m, reverse_bits(i - 1, logn) + 1));
+                t.roots[2 * i] = r.real(), t.roots[2 * i + 1] = r.imag();
+                t.inv_roots[2 * i] = ir.real(), t.inv_roots[2 * i + 1] = ir.imag();
+            }
+        }
+        else if (m == 4)
+        {
+            t.roots[3] = 1.0;
+            t.inv_roots[3] = -1.0;
+        }
+        return t;
+    }
+
+    CkksLevelHost ckks_level(const u64 *q, std::size_t L)
+    {
+        CkksLevelHost h;
+        h.total_bits = product_bit_count(q, L);
+        auto product_without = [&](std::size_t skip, u64 *dst) {
+            std::vector<u64> acc(L + 1, 0);
+            acc[0] = 1;
+            for (std::size_t i = 0; i < L; i++)
+            {
+                if (i == skip)
+                    continue;
+                u64 carry = 0;
+                for (std::size_t w = 0; w <= L; w++)
+                {
+                    const u128 v = static_cast<u128>(acc[w]) * q[i] + carry;
+                    acc[w] = static_cast<u64>(v), carry = static_cast<u64>(v >> 64);
+                }
+            }
+            for (std::size_t w = 0; w < L; w++)
+                dst[w] = acc[w];
+        };
+        h.Q.resize(L), h.threshold.resize(L), h.punctured.resize(L * L), h.inv_punctured.resize(L);
+        product_without(L, h.Q.data());
+        for (std::size_t j = 0; j < L; j++)
+        {
+            product_without(j, h.punctured.data() + j * L);
+            u64 pm = 1;
+            for (std::size_t i = 0; i < L; i++)
+                if (i != j)
+                    pm = mulmod(pm, q[i] % q[j], q[j]);
+            u64 inv = 0;
+            invmod(pm, q[j], inv);
+            h.inv_punctured[j] = pair(inv, q[j]);
+        }
+        // (Q + 1) >> 1
+        u64 carry = 1;
+        for (std::size_t w = 0; w < L; w++)
+        {
+            h.threshold[w] = h.Q[w] + carry;
+            carry = h.threshold[w] < carry ? 1 : 0;
+        }
+        for (std::size_t w = 0; w < L; w++)
+            h.threshold[w] = (h.threshold[w] >> 1) | ((w + 1 < L ? h.threshold[w + 1] : carry) << 63);
+        return h;
     }
 } // namespace sbh

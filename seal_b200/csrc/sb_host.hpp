@@ -42,10 +42,29 @@ namespace sbh
     }
     int product_bit_count(const u64 *q, std::size_t count);
 
+    // CKKSEncoder tables (ckks.cpp:33-73 + util/croots.cpp:16-70): the powers of the primitive 2n-th complex root in the order
+    // the transforms consume them, as (re, im) pairs; computed exactly as the reference does (std::polar on one eighth of the
+    // circle, the rest by symmetry) so that the device transforms reproduce its doubles bit for bit
+    struct CkksTables
+    {
+        std::vector<double> roots, inv_roots; // [n][2]; entry 0 unused
+    };
+    CkksTables ckks_tables(std::size_t n);
+    // what CKKSEncoder::decode needs of a level with L primes: Q = prod q_j, (Q + 1) / 2 (ContextData::upper_half_threshold,
+    // context.cpp:406-412), the punctured products Q / q_j and their inverses mod q_j (RNSBase::initialize, rns.cpp:149-193)
+
     struct TwPair
     {
         u64 w, wq;
     };
+
+    struct CkksLevelHost
+    {
+        int total_bits = 0;
+        std::vector<u64> Q, threshold, punctured; // L, L, L * L words (little endian)
+        std::vector<TwPair> inv_punctured;        // L
+    };
+    CkksLevelHost ckks_level(const u64 *q, std::size_t L);
 
     struct PrimeTables
     {

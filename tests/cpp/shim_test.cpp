@@ -5,6 +5,8 @@
 // :4326 (CKKSEncryptRotateDecrypt), :5670 (BFVEncryptRotateMatrixDecrypt), :2505/:2532 (negative relinearize tests).
 // TEST INFRASTRUCTURE: links the reference; built only where /root/reference exists; the binary travels to the GPU box.
 #include "seal_b200/batchencoder.hpp"
+#include "seal_b200/ckks.hpp"
+#include "seal_b200/encryptor.hpp"
 #include "seal_b200/decryptor.hpp"
 #include "seal_b200/evaluator.hpp"
 #include <complex>
@@ -935,6 +937,195 @@ static void test_batches_and_keys()
     }
 }
 
+// seal_b200::CKKSEncoder and seal_b200::Encryptor (symmetric) against the reference's classes: identical plaintexts, decoded
+// values and -- with a seeded random generator factory on the context, so that both sides draw the same bootstrap seed --
+// identical fresh ciphertexts; cf. native/tests/seal/ckks.cpp (CKKSEncoderEncodeVectorDecodeTest), encryptor.cpp
+// (BFVEncryptDecrypt / CKKSEncryptDecrypt, the symmetric halves)
+static void test_encoder_and_encryptor()
+{
+    prng_seed_type seed{};
+    seed[0] = 0xABCDEF;
+    {
+        EncryptionParameters parms(scheme_type::ckks);
+        parms.set_poly_modulus_degree(8192);
+        parms.set_coeff_modulus(CoeffModulus::Create(8192, { 60, 40, 40, 60 }));
+        parms.set_random_generator(std::make_shared<Blake2xbPRNGFactory>(seed));
+        SEALContext context(parms, true, sec_level_type::none);
+        KeyGenerator keygen(context);
+        seal::CKKSEncoder renc(context);
+        seal::Encryptor rcrypt(context, keygen.secret_key());
+        seal::Decryptor rdec(context, keygen.secret_key());
+        seal_b200::Evaluator gev(context);
+        seal_b200::CKKSEncoder genc(context, gev);
+        seal_b200::Encryptor gcrypt(context, keygen.secret_key(), gev);
+        CHECK(genc.slot_count() == renc.slot_count());
+        std::mt19937_64 rng(3);
+        std::uniform_real_distribution<double> dist(-10.0, 10.0);
+        std::vector<std::complex<double>> cv(renc.slot_count());
+        for (auto &v : cv)
+            v = { dist(rng), dist(rng) };
+        std::vector<double> rv(100);
+        for (auto &v : rv)
+            v = dist(rng);
+        const double scale = std::pow(2.0, 40);
+        Plaintext pr, pg;
+        renc.encode(cv, scale, pr);
+        genc.encode(cv, scale, pg);
+        CHECK(same_plain(pr, pg));
+        CHECK(pg.is_ntt_form());
+        renc.encode(rv, scale, pr);
+        genc.encode(rv, scale, pg);
+        CHECK(same_plain(pr, pg));
+        auto low = context.last_parms_id();
+        renc.encode(cv, low, std::pow(2.0, 20), pr);
+        genc.encode(cv, low, std::pow(2.0, 20), pg);
+        CHECK(same_plain(pr, pg));
+        std::vector<std::complex<double>> dr, dg;
+        renc.decode(pr, dr);
+        genc.decode(pg, dg);
+        CHECK(dr.size() == dg.size() && std::memcmp(dr.data(), dg.data(), dr.size() * 16) == 0);
+        std::vector<double> ddr, ddg;
+        renc.decode(pr, ddr);
+        genc.decode(pg, ddg);
+        CHECK(ddr.size() == ddg.size() && std::memcmp(ddr.data(), ddg.data(), ddr.size() * 8) == 0);
+        // batch encode = the single-vector results
+        std::vector<std::vector<std::complex<double>>> many{ cv, std::vector<std::complex<double>>(cv.begin(), cv.begin() + 7), cv };
+        std::vector<Plaintext> pb;
+        genc.encode(many, context.first_parms_id(), scale, pb);
+        for (size_t i = 0; i < many.size(); i++)
+        {
+            renc.encode(many[i], scale, pr);
+            CHECK(same_plain(pr, pb[i]));
+        }
+        // the reference's exception types
+        CHECK(outcome([&] { renc.encode(cv, std::pow(2.0, 300), pr); }) == outcome([&] { genc.encode(cv, std::pow(2.0, 300), pg); }));
+        std::vector<std::complex<double>> big(4, { 1e200, 0 });
+        CHECK(outcome([&] { renc.encode(big, scale, pr); }) == outcome([&] { genc.encode(big, scale, pg); }));
+        std::vector<std::complex<double>> toolong(renc.slot_count() + 1);
+        CHECK(outcome([&] { renc.encode(toolong, scale, pr); }) == outcome([&] { genc.encode(toolong, scale, pg); }));
+        // symmetric encryption: the same bootstrap seed on both sides -> the same ciphertext
+        renc.encode(cv, scale, pr);
+        Ciphertext cr, cg;
+        rcrypt.encrypt_symmetric(pr, cr);
+        gcrypt.encrypt_symmetric(pr, cg);
+        CHECK(same_ct(cr, cg));
+        rcrypt.encrypt_zero_symmetric(cr);
+        gcrypt.encrypt_zero_symmetric(cg);
+        CHECK(same_ct(cr, cg));
+        rcrypt.encrypt_zero_symmetric(low, cr);
+        gcrypt.encrypt_zero_symmetric(low, cg);
+        CHECK(same_ct(cr, cg));
+        renc.encode(cv, low, std::pow(2.0, 20), pr);
+        rcrypt.encrypt_symmetric(pr, cr);
+        gcrypt.encrypt_symmetric(pr, cg);
+        CHECK(same_ct(cr, cg));
+        // public-key encryption: first level, a lower level (sampled one level up, divided down)
+        {
+            PublicKey pk;
+            keygen.create_public_key(pk);
+            seal::Encryptor rpub(context, pk);
+            seal_b200::Encryptor gpub(context, pk, gev);
+            renc.encode(cv, scale, pr);
+            rpub.encrypt(pr, cr);
+            gpub.encrypt(pr, cg);
+            CHECK(same_ct(cr, cg));
+            rpub.encrypt_zero(low, cr);
+            gpub.encrypt_zero(low, cg);
+            CHECK(same_ct(cr, cg));
+            renc.encode(cv, low, std::pow(2.0, 20), pr);
+            rpub.encrypt(pr, cr);
+            gpub.encrypt(pr, cg);
+            CHECK(same_ct(cr, cg));
+            CHECK(outcome([&] { rpub.encrypt_symmetric(pr, cr); }) == outcome([&] { gpub.encrypt_symmetric(pr, cg); })); // secret key is not set
+            CHECK(outcome([&] { rcrypt.encrypt(pr, cr); }) == outcome([&] { gcrypt.encrypt(pr, cg); }));                 // public key is not set
+        }
+        // round trip through the device classes only: encode -> encrypt -> (reference) decrypt -> decode
+        genc.encode(cv, scale, pg);
+        gcrypt.encrypt_symmetric(pg, cg);
+        Plaintext back;
+        rdec.decrypt(cg, back);
+        genc.decode(back, dg);
+        double err = 0;
+        for (size_t i = 0; i < cv.size(); i++)
+            err = std::max(err, std::abs(dg[i] - cv[i]));
+        CHECK(err < 1e-6);
+        // batch encryption: every member equals the single call (seeded factory: the same seed each time)
+        std::vector<Plaintext> plains{ pg, pg, pg };
+        std::vector<Ciphertext> cts;
+        gcrypt.encrypt_symmetric(plains, cts);
+        rcrypt.encrypt_symmetric(pg, cr);
+        for (auto &c : cts)
+            CHECK(same_ct(cr, c));
+        CHECK(outcome([&] { Plaintext bad; rcrypt.encrypt_symmetric(bad, cr); }) == outcome([&] { Plaintext bad; gcrypt.encrypt_symmetric(bad, cg); }));
+    }
+    for (auto scheme : { scheme_type::bfv, scheme_type::bgv })
+    {
+        EncryptionParameters parms(scheme);
+        parms.set_poly_modulus_degree(4096);
+        parms.set_coeff_modulus(CoeffModulus::Create(4096, { 36, 36, 37 }));
+        parms.set_plain_modulus(PlainModulus::Batching(4096, 20));
+        parms.set_random_generator(std::make_shared<Blake2xbPRNGFactory>(seed));
+        SEALContext context(parms, true, sec_level_type::none);
+        KeyGenerator keygen(context);
+        seal::BatchEncoder benc(context);
+        seal::Encryptor rcrypt(context, keygen.secret_key());
+        seal::Decryptor rdec(context, keygen.secret_key());
+        seal_b200::Evaluator gev(context);
+        seal_b200::Encryptor gcrypt(context, keygen.secret_key(), gev);
+        std::vector<uint64_t> slots(benc.slot_count());
+        for (size_t i = 0; i < slots.size(); i++)
+            slots[i] = (i * 7919 + 13) % parms.plain_modulus().value();
+        Plaintext p;
+        benc.encode(slots, p);
+        Ciphertext cr, cg;
+        rcrypt.encrypt_symmetric(p, cr);
+        gcrypt.encrypt_symmetric(p, cg);
+        CHECK(same_ct(cr, cg));
+        rcrypt.encrypt_zero_symmetric(cr);
+        gcrypt.encrypt_zero_symmetric(cg);
+        CHECK(same_ct(cr, cg));
+        Plaintext back;
+        rdec.decrypt(cg, back);
+        CHECK(back.is_zero());
+        Plaintext small("1x^3 + 2");
+        rcrypt.encrypt_symmetric(small, cr);
+        gcrypt.encrypt_symmetric(small, cg);
+        CHECK(same_ct(cr, cg));
+        PublicKey pk;
+        keygen.create_public_key(pk);
+        seal::Encryptor rpub(context, pk);
+        seal_b200::Encryptor gpub(context, pk, keygen.secret_key(), gev);
+        rpub.encrypt(p, cr);
+        gpub.encrypt(p, cg);
+        CHECK(same_ct(cr, cg));
+        rdec.decrypt(cg, back);
+        CHECK(back == p);
+        rpub.encrypt_zero(context.last_parms_id(), cr);
+        gpub.encrypt_zero(context.last_parms_id(), cg);
+        CHECK(same_ct(cr, cg));
+    }
+    // default factory: fresh seeds, two encryptions differ and decrypt correctly
+    {
+        EncryptionParameters parms(scheme_type::bfv);
+        parms.set_poly_modulus_degree(4096);
+        parms.set_coeff_modulus(CoeffModulus::BFVDefault(4096));
+        parms.set_plain_modulus(PlainModulus::Batching(4096, 20));
+        SEALContext context(parms);
+        KeyGenerator keygen(context);
+        seal::Decryptor rdec(context, keygen.secret_key());
+        seal_b200::Evaluator gev(context);
+        seal_b200::Encryptor gcrypt(context, keygen.secret_key(), gev);
+        Plaintext p("5x^2 + 1"), back;
+        Ciphertext a, b;
+        gcrypt.encrypt_symmetric(p, a);
+        gcrypt.encrypt_symmetric(p, b);
+        CHECK(!same_ct(a, b));
+        rdec.decrypt(a, back);
+        CHECK(back == p);
+        CHECK(rdec.invariant_noise_budget(a) > 20);
+    }
+}
+
 int main()
 {
     try
@@ -943,6 +1134,7 @@ int main()
         test_bfv();
         test_bgv();
         test_batches_and_keys();
+        test_encoder_and_encryptor();
     }
     catch (const std::exception &e)
     {

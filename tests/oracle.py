@@ -23,6 +23,10 @@ def lib():
         L.orc_create.restype = C.c_void_p
         L.orc_blake2xb_stream.argtypes = [_u64p, C.c_size_t, _u64p]
         L.orc_expand_seed.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p]
+        L.orc_ckks_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, _u64p]
+        L.orc_ckks_decode.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_double, C.c_void_p]
+        L.orc_encrypt_zero_asymmetric.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p]
+        L.orc_encrypt_zero_symmetric.argtypes = [C.c_void_p, C.c_size_t, _u64p, _u64p, C.c_int, _u64p]
         L.orc_create.argtypes = [C.c_int, C.c_size_t, _u64p, C.c_size_t, C.c_uint64]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_is_prime.argtypes = [C.c_uint64]
@@ -102,6 +106,43 @@ class Oracle:
         self.h = lib().orc_create(scheme, n, _p(m), self.k, plain_modulus)
         if not self.h:
             raise RuntimeError("orc_create failed")
+
+    def ckks_encode(self, L, values, scale):
+        """CKKSEncoder::encode of a complex vector -> [L][n] NTT form, or None for the reference's invalid_argument cases"""
+        v = np.ascontiguousarray(values, dtype=np.complex128)
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        return None if lib().orc_ckks_encode(self.h, L, v.ctypes.data, v.size, float(scale), _p(out)) else out
+
+    def ckks_decode(self, L, plain, scale):
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros(self.n // 2, dtype=np.complex128)
+        return None if lib().orc_ckks_decode(self.h, L, _p(plain), float(scale), out.ctypes.data) else out
+
+    def encrypt_zero_asymmetric(self, pk, seed, L=None):
+        """public-key encryption of zero with the PRNG seeded by `seed` (8 words): [2][L][n]"""
+        pk = np.ascontiguousarray(pk, dtype=np.uint64)
+        seed = np.ascontiguousarray(seed, dtype=np.uint64)
+        L = L or (self.k - 1 if self.k > 1 else 1)
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        lib().orc_encrypt_zero_asymmetric(self.h, L, _p(pk), _p(seed), _p(out))
+        return out
+
+    def encrypt_zero_symmetric(self, sk, seed, save_seed, L=None):
+        """encrypt_zero_symmetric with the bootstrap PRNG seeded by `seed` (8 words): [2][L][n] (default: the first data level)"""
+        sk = np.ascontiguousarray(sk, dtype=np.uint64)
+        seed = np.ascontiguousarray(seed, dtype=np.uint64)
+        L = L or (self.k - 1 if self.k > 1 else 1)
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        lib().orc_encrypt_zero_symmetric(self.h, L, _p(sk), _p(seed), int(save_seed), _p(out))
+        return out
+
+    @staticmethod
+    def blake2xb_stream(seed, words):
+        """the first `words` 64-bit words of Blake2xbPRNG(seed)"""
+        seed = np.ascontiguousarray(seed, dtype=np.uint64)
+        out = np.zeros(words, dtype=np.uint64)
+        lib().orc_blake2xb_stream(_p(seed), words, _p(out))
+        return out
 
     def expand_seed(self, L, seed):
         """Ciphertext::expand_seed: the polynomial [L][n] a 64-byte PRNG seed (8 words) expands into (Blake2xbPRNG)"""

@@ -72,6 +72,11 @@ def lib():
         L.sealref_kswitch_keys_stream.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t]
         L.sealref_seeded_ct_stream.restype = C.c_long
         L.sealref_seeded_ct_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.sealref_ckks_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_double, _u64p]
+        L.sealref_ckks_decode.argtypes = [C.c_void_p, C.c_size_t, _u64p, C.c_double, C.c_void_p]
+        L.sealref_public_key.argtypes = [C.c_void_p, _u64p]
+        L.sealref_encrypt_zero_asymmetric.argtypes = [C.c_void_p, C.c_size_t, _u64p]
+        L.sealref_encrypt_zero_symmetric.argtypes = [C.c_void_p, C.c_size_t, _u64p]
         L.sealref_ct_save_mode.restype = C.c_long
         L.sealref_ct_save_mode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, _u64p, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_char_p, C.c_size_t]
         L.sealref_kswitch_keys_stream_mode.restype = C.c_long
@@ -308,6 +313,48 @@ class RefContext:
         if ln < 0:
             raise RuntimeError(lib().sealref_last_error().decode())
         return buf.raw[:ln]
+
+    def ckks_encode(self, L, values, scale):
+        """CKKSEncoder::encode(vector<complex<double>>, parms_id of level L, scale) -> [L][n] (NTT form), or None when the
+        reference throws invalid_argument"""
+        v = np.ascontiguousarray(values, dtype=np.complex128)
+        out = np.zeros((L, self.n), dtype=np.uint64)
+        rc = lib().sealref_ckks_encode(self.h, L, v.ctypes.data, v.size, float(scale), _p(out))
+        if rc == 1:
+            return None
+        self._chk(rc)
+        return out
+
+    def ckks_decode(self, L, plain, scale):
+        """CKKSEncoder::decode -> n/2 complex values, or None when the reference throws invalid_argument"""
+        plain = np.ascontiguousarray(plain, dtype=np.uint64)
+        out = np.zeros(self.n // 2, dtype=np.complex128)
+        rc = lib().sealref_ckks_decode(self.h, L, _p(plain), float(scale), out.ctypes.data)
+        if rc == 1:
+            return None
+        self._chk(rc)
+        return out
+
+    def public_key(self):
+        """KeyGenerator::create_public_key -> [2][k][n] (NTT form, key level)"""
+        out = np.zeros((2, self.k, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_public_key(self.h, _p(out)))
+        return out
+
+    def encrypt_zero_asymmetric(self, L=None):
+        """Encryptor(public key)::encrypt_zero(parms_id of the level with L primes; L == k: the key level) -> [2][L][n]"""
+        L = L or (self.k - 1 if self.k > 1 else 1)
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_encrypt_zero_asymmetric(self.h, L, _p(out)))
+        return out
+
+    def encrypt_zero_symmetric(self, L=None):
+        """Encryptor::encrypt_zero_symmetric(parms_id, ct) (not seed-compressed) -> [2][L][n]; the bootstrap PRNG is seeded with
+        {seed, 0, ...} (deterministic)"""
+        L = L or (self.k - 1 if self.k > 1 else 1)
+        out = np.zeros((2, L, self.n), dtype=np.uint64)
+        self._chk(lib().sealref_encrypt_zero_symmetric(self.h, L, _p(out)))
+        return out
 
     def seeded_ct_stream(self, compr=0):
         buf = C.create_string_buffer(2 * self.k * self.n * 8 + self.k * self.n + 4096)

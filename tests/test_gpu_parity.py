@@ -434,8 +434,13 @@ def test_wire_format_vs_reference(scheme):
     # a stream of another level / another context
     with pytest.raises(RuntimeError):
         ctx.d_load_ciphertexts([rc.ct_save(1, data[0][:, :1], ntt, scale)], dev, L, size)
+    # a seed-compressed fresh ciphertext lives at the first data level (2 primes here): loads there, not at level 1
+    one = torch.zeros((1, 2, 2, n), dtype=torch.int64, device="cuda")
+    ctx.d_load_ciphertexts([rc.seeded_ct_stream()], one, 2, 2)
+    torch.cuda.synchronize()
+    assert (one.cpu().numpy().view(np.uint64)[0] == rc.ct_load(rc.seeded_ct_stream())[0]).all()
     with pytest.raises(RuntimeError):
-        ctx.d_load_ciphertexts([rc.seeded_ct_stream()], dev, 2, 2)  # a fresh ciphertext lives at the top level, not at level 2
+        ctx.d_load_ciphertexts([rc.seeded_ct_stream()], torch.zeros((1, 2, 1, n), dtype=torch.int64, device="cuda"), 1, 2)
 
 
 @needs_ref
@@ -619,3 +624,172 @@ def test_keyswitch_extreme_sizes_vs_oracle(logn, scheme):
         assert (ctx.rescale_to_next(a)[1] == oc.rescale(L, a[1])).all()
     else:
         assert (ctx.mod_switch_to_next(a)[1] == oc.bfv_mod_switch(L, a[1])).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 8192, [50, 50, 50, 51]), ("bfv", 4096, [36, 36, 37]), ("bgv", 4096, [40, 40, 40]),
+                                          ("ckks", 2048, [54])])
+def test_encrypt_zero_symmetric_vs_reference(scheme, n, bits):
+    """sb200_encrypt_zero_symmetric against Encryptor::encrypt_zero_symmetric of the reference with the same bootstrap seed (the
+    reference context's generator factory is seeded): the plain variant, the seed-keeping variant (the reference's seeded stream,
+    loaded by the reference), a lower level, and other seeds of the batch against the oracle; the ciphertexts decrypt to the noise"""
+    import torch
+
+    def to_np(x):
+        return x.cpu().numpy().view(np.uint64)
+
+    S = sb()
+    sid = {"ckks": (R.CKKS, S.CKKS, O.CKKS), "bfv": (R.BFV, S.BFV, O.BFV), "bgv": (R.BGV, S.BGV, O.BGV)}[scheme]
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme != "ckks" else 0
+    seed0 = 0xC0FFEE
+    rc = R.RefContext(sid[0], n, mods, t, seed=seed0)
+    oc = O.Oracle(sid[2], n, mods, t)
+    ctx = S.Context(sid[1], n, mods, t)
+    sk_host = rc.secret_key()
+    sk = ctx.load_secret_key(sk_host)
+    k = len(mods)
+    L = k - 1 if k > 1 else 1
+    batch = 3
+    seeds = np.zeros((batch, 8), dtype=np.uint64)
+    seeds[0, 0] = seed0
+    seeds[1] = np.arange(1, 9, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    seeds[2, 7] = 5
+    for save_seed in (False, True):
+        out = torch.zeros((batch, 2, L, n), dtype=torch.int64, device="cuda")
+        pub = ctx.d_encrypt_zero_symmetric(sk, out, L, batch, seeds, save_seed=save_seed, want_public_seeds=True)
+        torch.cuda.synchronize()
+        got = to_np(out)
+        if save_seed:
+            want0, _, _, _ = rc.ct_load(rc.seeded_ct_stream())
+        else:
+            want0 = rc.encrypt_zero_symmetric()
+        assert (got[0] == want0).all(), f"ciphertext 0 vs the reference, save_seed={save_seed}"
+        for b in range(batch):
+            assert (got[b] == oc.encrypt_zero_symmetric(sk_host, seeds[b], save_seed)).all(), f"ciphertext {b} vs the oracle"
+            assert (pub[b] == oc.blake2xb_stream(seeds[b], 8)).all()
+    if k > 2:
+        out = torch.zeros((1, 2, 1, n), dtype=torch.int64, device="cuda")
+        ctx.d_encrypt_zero_symmetric(sk, out, 1, 1, seeds[:1])
+        torch.cuda.synchronize()
+        assert (to_np(out)[0] == rc.encrypt_zero_symmetric(L=1)).all()
+    # fresh seeds: two calls differ, and c_0 + c_1 s is small (the noise) -- checked through the library's own decryption
+    a = torch.zeros((2, 2, L, n), dtype=torch.int64, device="cuda")
+    ctx.d_encrypt_zero_symmetric(sk, a, L, 2)
+    torch.cuda.synchronize()
+    ha = to_np(a)
+    assert not (ha[0] == ha[1]).all()
+    if scheme == "bfv":
+        assert (ctx.decrypt(ha, sk) == 0).all()
+
+
+@pytest.mark.parametrize("n,bits", [(8192, [60, 60, 60, 60]), (4096, [40, 40, 40]), (1024, [27]), (65536, [55] * 5)])
+def test_ckks_encoder_vs_reference(n, bits):
+    """sb200_ckks_encode / sb200_ckks_decode BIT-exact against CKKSEncoder of the reference (or the oracle pinned to it, where the
+    reference library is absent): batches, partial vectors, real input, every decomposition branch (coefficients below 2^64, below
+    2^128, multi-precision), a lower level, the reference's error cases, and decode of encoded and of arbitrary plaintexts"""
+    S = sb()
+    mods = O.coeff_modulus_create(n, bits)
+    oc = O.Oracle(O.CKKS, n, mods)
+    rc = R.RefContext(R.CKKS, n, mods) if R.available() else oc
+    ctx = S.Context(S.CKKS, n, mods)
+    k = len(mods)
+    Lmax = k - 1 if k > 1 else 1
+    rng = np.random.default_rng(11)
+    slots = n // 2
+    total = sum(bits[:Lmax])
+    cases = [(Lmax, slots, 2.0 ** 20, 1.0), (Lmax, slots // 3, 2.0 ** 30, 100.0), (1, slots, 2.0 ** 10, 1e-3), (Lmax, 1, 3.7e5, 1.0)]
+    if total > 70:
+        cases.append((Lmax, slots, 2.0 ** 62, 50.0))
+    if total > 140:
+        cases.append((Lmax, slots, 2.0 ** 120, 1000.0))
+    B = 3
+    for L, count, scale, mag in cases:
+        v = (rng.standard_normal((B, count)) + 1j * rng.standard_normal((B, count))) * mag
+        got = ctx.ckks_encode(v, L, scale)
+        for b in range(B):
+            want = rc.ckks_encode(L, v[b], scale)
+            assert want is not None
+            assert (got[b] == want).all(), ("encode", L, count, scale, b)
+        dec = ctx.ckks_decode(got, scale)
+        for b in (0, B - 1):
+            want = rc.ckks_decode(L, got[b], scale)
+            assert (dec[b].view(np.uint64) == want.view(np.uint64)).all(), ("decode", L, count, scale, b)
+    # real input = complex input with zero imaginary parts
+    r = rng.standard_normal(slots)
+    assert (ctx.ckks_encode(r, Lmax, 2.0 ** 20) == rc.ckks_encode(Lmax, r + 0j, 2.0 ** 20)).all()
+    # empty vector: the zero plaintext
+    assert (ctx.ckks_encode(np.zeros((1, 0), dtype=np.complex128), Lmax, 2.0 ** 20) == 0).all()
+    # decode of arbitrary plaintexts (uniform residues: coefficients in both halves of [0, Q))
+    for L in sorted({1, Lmax}):
+        p = np.stack([rng.integers(0, mods[j], n, dtype=np.uint64) for j in range(L)])
+        for scale in (2.0 ** 12, 2.0 ** 30):
+            want = rc.ckks_decode(L, p, scale)
+            if want is None:
+                with pytest.raises(ValueError, match="scale out of bounds"):
+                    ctx.ckks_decode(p, scale)
+            else:
+                assert (ctx.ckks_decode(p, scale).view(np.uint64) == want.view(np.uint64)).all(), ("decode random", L, scale)
+    # the reference's invalid_argument cases
+    with pytest.raises(ValueError, match="encoded values are too large"):
+        ctx.ckks_encode(np.full(slots, 1e30 + 0j), 1, 2.0 ** 20)
+    with pytest.raises(ValueError, match="values must be finite"):
+        ctx.ckks_encode(np.array([np.inf + 0j]), 1, 2.0 ** 20)
+    with pytest.raises(ValueError, match="scale out of bounds"):
+        ctx.ckks_encode(np.ones(4) + 0j, 1, 2.0 ** 200)
+    with pytest.raises(ValueError, match="values_size is too large"):
+        ctx.ckks_encode(np.ones(slots + 1) + 0j, 1, 2.0 ** 20)
+    bfv = S.Context(S.BFV, 4096, O.coeff_modulus_create(4096, [36, 36, 37]), 65537)
+    with pytest.raises(ValueError, match="unsupported scheme"):
+        bfv.ckks_encode(np.ones(4) + 0j, 1, 2.0 ** 20)
+
+
+@needs_ref
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 8192, [50, 50, 50, 51]), ("bfv", 4096, [36, 36, 37]), ("bgv", 4096, [40, 40, 40]),
+                                          ("ckks", 2048, [54])])
+def test_encrypt_zero_asymmetric_vs_reference(scheme, n, bits):
+    """sb200_encrypt_zero_asymmetric against Encryptor(public key)::encrypt_zero of the reference with the same PRNG seed: first data
+    level, the lowest level, the key level; other seeds of the batch against the oracle (incl. a stream whose ternary words contain
+    a zero word is covered by the oracle-level restatement only: probability 2^-32 per coefficient); decrypts to zero"""
+    import torch
+
+    def to_np(x):
+        return x.cpu().numpy().view(np.uint64)
+
+    S = sb()
+    sid = {"ckks": (R.CKKS, S.CKKS, O.CKKS), "bfv": (R.BFV, S.BFV, O.BFV), "bgv": (R.BGV, S.BGV, O.BGV)}[scheme]
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme != "ckks" else 0
+    seed0 = 0xC0FFEE
+    rc = R.RefContext(sid[0], n, mods, t, seed=seed0)
+    oc = O.Oracle(sid[2], n, mods, t)
+    ctx = S.Context(sid[1], n, mods, t)
+    pk_host = rc.public_key()
+    pk = ctx.load_public_key(pk_host)
+    k = len(mods)
+    batch = 3
+    seeds = np.zeros((batch, 8), dtype=np.uint64)
+    seeds[0, 0] = seed0
+    seeds[1] = np.arange(1, 9, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    seeds[2, 3] = 77
+    for L in sorted({k - 1 if k > 1 else 1, 1, k}):
+        out = torch.zeros((batch, 2, L, n), dtype=torch.int64, device="cuda")
+        ctx.d_encrypt_zero_asymmetric(pk, out, L, batch, seeds)
+        torch.cuda.synchronize()
+        got = to_np(out)
+        assert (got[0] == rc.encrypt_zero_asymmetric(L=L)).all(), f"level {L} vs the reference"
+        for b in range(1, batch):
+            assert (got[b] == oc.encrypt_zero_asymmetric(pk_host, seeds[b], L=L)).all(), f"level {L}, ciphertext {b} vs the oracle"
+    L = k - 1 if k > 1 else 1
+    a = torch.zeros((2, 2, L, n), dtype=torch.int64, device="cuda")
+    ctx.d_encrypt_zero_asymmetric(pk, a, L, 2)
+    torch.cuda.synchronize()
+    ha = to_np(a)
+    assert not (ha[0] == ha[1]).all()
+    if scheme == "bfv":
+        sk = ctx.load_secret_key(rc.secret_key())
+        assert (ctx.decrypt(ha, sk) == 0).all()
+    bad = pk_host.copy()
+    bad[1, 0, 5] = mods[0]
+    with pytest.raises(ValueError, match="public key is not valid"):
+        ctx.load_public_key(bad)

@@ -294,3 +294,94 @@ def test_expand_seed_matches_reference_load(scheme, n, bits):
         seed = np.frombuffer(stream, dtype=np.uint64, count=8, offset=info.seed_offset)
         assert (full[0] == c0).all()
         assert (oc.expand_seed(L, seed) == full[1]).all()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not present")
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 4096, [40, 40, 40]), ("bfv", 4096, [36, 36, 37]), ("bgv", 4096, [40, 40, 40]),
+                                          ("ckks", 2048, [54])])
+def test_encrypt_zero_symmetric_matches_reference(scheme, n, bits):
+    """the oracle's restatement of encrypt_zero_symmetric (util/rlwe.cpp:264-408: public seed + uniform c_1 from one PRNG, centred
+    binomial noise from the bootstrap PRNG, c_0 = -(c_1 s + e)) against the reference's Encryptor with the same bootstrap seed,
+    both the plain and the seed-compressed variant (they differ for BFV)"""
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme != "ckks" else 0
+    seed0 = 0x5EA1
+    rc = R.RefContext(sid, n, mods, t, seed=seed0)
+    oc = O.Oracle({"ckks": O.CKKS, "bfv": O.BFV, "bgv": O.BGV}[scheme], n, mods, t)
+    sk = rc.secret_key()
+    seed = np.zeros(8, dtype=np.uint64)
+    seed[0] = seed0
+    assert (oc.encrypt_zero_symmetric(sk, seed, False) == rc.encrypt_zero_symmetric()).all()
+    seeded, _, _, _ = rc.ct_load(rc.seeded_ct_stream())
+    assert (oc.encrypt_zero_symmetric(sk, seed, True) == seeded).all()
+    if len(mods) > 2:  # a lower level: sampled at that level directly (no modulus switching for symmetric encryption)
+        assert (oc.encrypt_zero_symmetric(sk, seed, False, L=1) == rc.encrypt_zero_symmetric(L=1)).all()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not present")
+@pytest.mark.parametrize("n,bits", [(4096, [40, 40, 40]), (1024, [27]), (8192, [60, 60, 60, 60]), (2048, [54])])
+def test_ckks_encoder_matches_reference(n, bits):
+    """the oracle's CKKSEncoder restatement (ckks.h:455-807; double-precision FFT in the reference's operation order) is BIT-exact
+    against the reference: full and partial vectors, scales that reach the 64-bit, 128-bit and multi-precision decomposition
+    branches, lower levels, the error cases, and decode of encoded and of arbitrary plaintexts"""
+    mods = R.coeff_modulus_create(n, bits)
+    rc = R.RefContext(R.CKKS, n, mods)
+    oc = O.Oracle(O.CKKS, n, mods)
+    k = len(mods)
+    Lmax = k - 1 if k > 1 else 1
+    rng = np.random.default_rng(7)
+    slots = n // 2
+    total = sum(bits[:Lmax])
+    cases = [(Lmax, slots, 2.0 ** 20, 1.0), (Lmax, slots // 3, 2.0 ** 30, 100.0), (1, slots, 2.0 ** 10, 1e-3), (Lmax, 0, 2.0 ** 20, 1.0),
+             (Lmax, 1, 3.7e5, 1.0)]
+    if total > 70:
+        cases.append((Lmax, slots, 2.0 ** 62, 50.0))     # coefficients beyond 64 bits
+    if total > 140:
+        cases.append((Lmax, slots, 2.0 ** 120, 1000.0))  # beyond 128 bits: the multi-precision branch
+    for L, count, scale, mag in cases:
+        v = (rng.standard_normal(count) + 1j * rng.standard_normal(count)) * mag
+        want = rc.ckks_encode(L, v, scale)
+        got = oc.ckks_encode(L, v, scale)
+        assert (want is None) == (got is None), (L, count, scale)
+        if want is None:
+            continue
+        assert (got == want).all(), (L, count, scale)
+        dw, dg = rc.ckks_decode(L, want, scale), oc.ckks_decode(L, want, scale)
+        assert dw is not None and dg is not None
+        assert (dw.view(np.uint64) == dg.view(np.uint64)).all(), ("decode", L, count, scale)
+        if count and scale >= 2.0 ** 20:
+            assert np.abs(dw[:count] - v).max() < mag * 1e-3 + 1e-3
+    # error cases: values too large for the modulus, non-finite input, scale out of bounds
+    assert rc.ckks_encode(1, np.full(slots, 1e30 + 0j), 2.0 ** 20) is None and oc.ckks_encode(1, np.full(slots, 1e30 + 0j), 2.0 ** 20) is None
+    assert oc.ckks_encode(1, np.array([np.inf + 0j]), 2.0 ** 20) is None and rc.ckks_encode(1, np.array([np.inf + 0j]), 2.0 ** 20) is None
+    assert oc.ckks_encode(1, np.ones(4) + 0j, 2.0 ** 200) is None and rc.ckks_encode(1, np.ones(4) + 0j, 2.0 ** 200) is None
+    # decode of an arbitrary plaintext (uniform residues: large "negative" and positive coefficients)
+    for L in sorted({1, Lmax}):
+        p = np.stack([rng.integers(0, mods[j], n, dtype=np.uint64) for j in range(L)])
+        for scale in (2.0 ** 12, 2.0 ** 30):
+            dw, dg = rc.ckks_decode(L, p, scale), oc.ckks_decode(L, p, scale)
+            assert (dw is None) == (dg is None), ("decode random: scale bound", L, scale)
+            assert dw is None or (dw.view(np.uint64) == dg.view(np.uint64)).all(), ("decode random", L, scale)
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libsealref.so not present")
+@pytest.mark.parametrize("scheme,n,bits", [("ckks", 4096, [40, 40, 40, 40]), ("bfv", 4096, [36, 36, 37]), ("bgv", 4096, [40, 40, 40]),
+                                          ("ckks", 2048, [54])])
+def test_encrypt_zero_asymmetric_matches_reference(scheme, n, bits):
+    """the oracle's restatement of public-key encryption of zero (ternary u through libstdc++'s uniform_int_distribution, two noise
+    polynomials, c_j = pk_j u + e_j one level up, divide-and-round down) against Encryptor(public key)::encrypt_zero with the same
+    PRNG seed: first data level, a lower level, the key level"""
+    sid = {"ckks": R.CKKS, "bfv": R.BFV, "bgv": R.BGV}[scheme]
+    mods = R.coeff_modulus_create(n, bits)
+    t = R.plain_modulus_batching(n, 20) if scheme != "ckks" else 0
+    seed0 = 0x5EA1
+    rc = R.RefContext(sid, n, mods, t, seed=seed0)
+    oc = O.Oracle({"ckks": O.CKKS, "bfv": O.BFV, "bgv": O.BGV}[scheme], n, mods, t)
+    pk = rc.public_key()
+    seed = np.zeros(8, dtype=np.uint64)
+    seed[0] = seed0
+    k = len(mods)
+    levels = sorted({k - 1 if k > 1 else 1, 1, k})
+    for L in levels:
+        assert (oc.encrypt_zero_asymmetric(pk, seed, L=L) == rc.encrypt_zero_asymmetric(L=L)).all(), L
