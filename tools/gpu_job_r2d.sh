@@ -21,3 +21,7 @@ except Exception as e:
     print("bench_r2d failed", e)
 PY
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_r2d.json 2> $O/bench_ref_r2d.err; tail -c 400 $O/bench_ref_r2d.json
+# DRAM traffic of the two dominant kernels at the chunk size the benchmark runs (110 ciphertexts per key pass)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ks_local_mac|ks_digit_col' -s 2 -c 2 -o $O/r02_chunk110 python bench.py --batch 110 --steps 1 --warmup 1 --scratch-gib 64 --no-cpu-baseline --no-e2e --no-configs --no-verify > $O/ncu_chunk110.log 2>&1
+ls -la $O/r02_chunk110.ncu-rep
+ncu -i $O/r02_chunk110.ncu-rep --page raw --csv > $O/r02_chunk110_raw.csv 2>/dev/null; wc -c $O/r02_chunk110_raw.csv
