@@ -72,10 +72,13 @@ size_t sb200_device_bytes(const sb200_context *ctx);
  * to force the multi-chunk paths (ragged last chunk) at small batch sizes.
  *   SB200_LIMIT_SCRATCH_BYTES     budget of the per-context scratch arena (default 8 GiB, env SB200_SCRATCH_MB)
  *   SB200_LIMIT_KS_CHUNK          max ciphertexts per key-switching chunk (0 = derived from the scratch budget)
- *   SB200_LIMIT_HOST_STAGE_BYTES  device staging per pipeline slot of the *_host entry points (default 640 MiB) */
+ *   SB200_LIMIT_HOST_STAGE_BYTES  device staging per pipeline slot of the *_host entry points (default 640 MiB)
+ *   SB200_LIMIT_KS_ALGORITHM      key switching: 1 = exact integer convolution on 29-bit auxiliary primes (default where
+ *                                 available: n >= 4096; env SB200_KS_ALGO), 0 = 64-bit digit transforms per output prime */
 #define SB200_LIMIT_SCRATCH_BYTES 0
 #define SB200_LIMIT_KS_CHUNK 1
 #define SB200_LIMIT_HOST_STAGE_BYTES 2
+#define SB200_LIMIT_KS_ALGORITHM 3
 int sb200_context_set_limit(sb200_context *ctx, int which, size_t value);
 
 /* ---- device-resident slabs (the storage behind seal_b200::CiphertextBatch, include/seal_b200/batch.hpp) ------------
@@ -125,6 +128,18 @@ int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t
  * butterflies (fused kernel's shape), 2: inverse butterflies, 3: key multiply-accumulates.  Result: warp-level operations per
  * second of the whole device (one warp-level operation = 32 coefficient-level ones). */
 int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_second);
+/* the integer key-switching path (SB200_LIMIT_KS_ALGORITHM 1): its work is counted in 32-bit butterflies and 32x32->64-bit
+ * multiply-accumulates (sb200_profile_read_work32 = sb200_profile_read_work + those two counters); sb200_selftest_rate kinds
+ * 10, 11, 12 measure their ceilings (forward butterflies, inverse butterflies, multiply-accumulates).  The transforms modulo the
+ * auxiliary primes are exposed for the parity tests: _info returns the primes (capacity 8), _forward maps rows of n 64-bit
+ * words to h_out[prime][row][n] (canonical residues, transformed), _inverse transforms h_data[row][prime][n] in place (values
+ * in [0, 2p), not scaled by n^-1). */
+int sb200_profile_read_work32(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                              unsigned long long *launches, double *algorithmic_bytes, double *butterflies, double *macs,
+                              double *butterflies32, double *macs32);
+int sb200_selftest_ksint_info(sb200_context *ctx, int *count, uint32_t *primes);
+int sb200_selftest_ksint_forward(sb200_context *ctx, const uint64_t *h_rows, size_t rows, uint32_t *h_out);
+int sb200_selftest_ksint_inverse(sb200_context *ctx, uint32_t *h_data, size_t rows);
 
 /* ---- key-switching keys --------------------------------------------------------------------------------------
  * h_key = the flattened KSwitchKeys::data()[index]: [digit j < digits][component 2][key prime k][coeff n], i.e. for

@@ -25,7 +25,7 @@ _STATUS = {-1: ValueError, -2: RuntimeError, -3: IndexError, -4: RuntimeError, -
 SYMBOLS = [
     "sb200_last_error", "sb200_context_create", "sb200_context_destroy", "sb200_coeff_modulus_create",
     "sb200_get_ntt_tables", "sb200_get_base_bsk", "sb200_galois_elt_from_step", "sb200_launch_count",
-    "sb200_device_bytes", "sb200_context_set_limit", "sb200_device_malloc", "sb200_device_free", "sb200_host_malloc", "sb200_host_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d", "sb200_memcpy_d2d_2d", "sb200_stream_synchronize", "sb200_upload_rows", "sb200_download_rows", "sb200_rescale_to_next_sized", "sb200_mod_switch_to_next_sized", "sb200_relinearize_sized", "sb200_rescale_to_next_sized_host", "sb200_mod_switch_to_next_sized_host", "sb200_relinearize_sized_host", "sb200_device_numa_node", "sb200_device_index", "sb200_keyswitch_chunk", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read", "sb200_profile_read_work", "sb200_selftest_rate",
+    "sb200_device_bytes", "sb200_context_set_limit", "sb200_device_malloc", "sb200_device_free", "sb200_host_malloc", "sb200_host_free", "sb200_memcpy_h2d", "sb200_memcpy_d2h", "sb200_memcpy_d2d", "sb200_memcpy_d2d_2d", "sb200_stream_synchronize", "sb200_upload_rows", "sb200_download_rows", "sb200_rescale_to_next_sized", "sb200_mod_switch_to_next_sized", "sb200_relinearize_sized", "sb200_rescale_to_next_sized_host", "sb200_mod_switch_to_next_sized_host", "sb200_relinearize_sized_host", "sb200_device_numa_node", "sb200_device_index", "sb200_keyswitch_chunk", "sb200_profile_enable", "sb200_profile_reset", "sb200_profile_read", "sb200_profile_read_work", "sb200_selftest_rate", "sb200_profile_read_work32", "sb200_selftest_ksint_info", "sb200_selftest_ksint_forward", "sb200_selftest_ksint_inverse",
     "sb200_kswitch_key_create", "sb200_kswitch_key_load", "sb200_kswitch_key_destroy", "sb200_ntt_forward",
     "sb200_ntt_inverse", "sb200_multiply", "sb200_multiply_sized", "sb200_square", "sb200_add", "sb200_sub", "sb200_negate", "sb200_multiply_plain", "sb200_batch_encode", "sb200_batch_decode", "sb200_plain_to_ntt", "sb200_multiply_plain_coeff", "sb200_add_plain_coeff", "sb200_relinearize", "sb200_multiply_relinearize", "sb200_rescale_to_next",
     "sb200_mod_switch_to_next", "sb200_apply_galois", "sb200_ntt_forward_host", "sb200_ntt_inverse_host",
@@ -83,6 +83,12 @@ def lib():
         L.sb200_profile_read_work.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
                                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.sb200_selftest_rate.argtypes = [vp, i32, C.POINTER(C.c_double)]
+        L.sb200_profile_read_work32.argtypes = [vp, sz, C.c_char_p, sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong),
+                                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.sb200_selftest_ksint_info.argtypes = [vp, C.POINTER(i32), C.POINTER(u32)]
+        L.sb200_selftest_ksint_forward.argtypes = [vp, _u64p, sz, C.POINTER(u32)]
+        L.sb200_selftest_ksint_inverse.argtypes = [vp, C.POINTER(u32), sz]
         L.sb200_kswitch_key_create.argtypes = [vp, _u64p, sz, C.POINTER(vp)]
         L.sb200_kswitch_key_destroy.argtypes = [vp]
         L.sb200_kswitch_key_load.argtypes = [vp, C.c_char_p, sz, sz, C.POINTER(vp)]
@@ -300,7 +306,7 @@ class Context:
     def device_bytes(self):
         return int(lib().sb200_device_bytes(self.h))
 
-    LIMIT_SCRATCH_BYTES, LIMIT_KS_CHUNK, LIMIT_HOST_STAGE_BYTES = 0, 1, 2
+    LIMIT_SCRATCH_BYTES, LIMIT_KS_CHUNK, LIMIT_HOST_STAGE_BYTES, LIMIT_KS_ALGORITHM = 0, 1, 2, 3
 
     def set_limit(self, which, value):
         """sb200_context_set_limit: how a batch is cut into device chunks (results never depend on it)"""
@@ -332,6 +338,38 @@ class Context:
             out.append((name.value.decode(), ms.value, n.value, by.value, bf.value, mc.value))
             i += 1
         return out
+
+    def profile_read_work32(self):
+        """profile_read_work + (32-bit butterflies, 32x32->64 multiply-accumulates) of the integer key-switching path"""
+        out, i = [], 0
+        name = C.create_string_buffer(128)
+        ms, n, by, bf, mc, b32, m32 = C.c_double(0), C.c_ulonglong(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
+        while lib().sb200_profile_read_work32(self.h, i, name, 128, C.byref(ms), C.byref(n), C.byref(by), C.byref(bf), C.byref(mc),
+                                              C.byref(b32), C.byref(m32)) == 0:
+            out.append((name.value.decode(), ms.value, n.value, by.value, bf.value, mc.value, b32.value, m32.value))
+            i += 1
+        return out
+
+    def ksint_primes(self):
+        """auxiliary primes of the integer key-switching path ([] when it is not available: n < 4096)"""
+        cnt, pr = C.c_int(0), (C.c_uint32 * 8)()
+        _check(lib().sb200_selftest_ksint_info(self.h, C.byref(cnt), pr))
+        return [int(pr[i]) for i in range(cnt.value)]
+
+    def ksint_forward(self, rows64):
+        """rows [R][n] uint64 -> [S][R][n] uint32: residues modulo the auxiliary primes, transformed (bit-reversed order)"""
+        rows64 = np.ascontiguousarray(rows64, dtype=np.uint64)
+        S = len(self.ksint_primes())
+        out = np.empty((S,) + rows64.shape, dtype=np.uint32)
+        _check(lib().sb200_selftest_ksint_forward(self.h, rows64.ctypes.data_as(C.POINTER(C.c_uint64)), rows64.shape[0],
+                                                  out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def ksint_inverse(self, data32):
+        """[R][S][n] uint32 (values < 2p) -> inverse transforms, not scaled by n^-1, values in [0, 2p)"""
+        data32 = np.ascontiguousarray(data32, dtype=np.uint32).copy()
+        _check(lib().sb200_selftest_ksint_inverse(self.h, data32.ctypes.data_as(C.POINTER(C.c_uint32)), data32.shape[0]))
+        return data32
 
     def selftest_rate(self, kind):
         """warp-level butterflies (kind 0, 1, 2) / key multiply-accumulates (kind 3) per second, registers only"""

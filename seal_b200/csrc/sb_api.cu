@@ -50,7 +50,13 @@ struct sb200_secret_key
 struct sb200_kswitch_key
 {
     KSwitchKey k;
-    ~sb200_kswitch_key() { cudaFree(k.d_key); }
+    ~sb200_kswitch_key()
+    {
+        if (k.ctx)
+            cudaSetDevice(k.ctx->device);
+        cudaFree(k.d_key);
+        cudaFree(k.d_key32);
+    }
 };
 
 #define SB_TRY try {
@@ -214,6 +220,7 @@ int sb200_context_set_limit(sb200_context *ctx, int which, size_t value)
     case SB200_LIMIT_SCRATCH_BYTES: c.scratch_budget = std::max<size_t>(value, size_t(1) << 20); break;
     case SB200_LIMIT_KS_CHUNK: c.ks_chunk_max = value; break;
     case SB200_LIMIT_HOST_STAGE_BYTES: c.host_stage_bytes = std::max<size_t>(value, size_t(1) << 16); break;
+    case SB200_LIMIT_KS_ALGORITHM: c.ks_algo = value ? 1 : 0; break;
     default: throw std::invalid_argument("unknown limit");
     }
     return SB200_OK;
@@ -499,6 +506,45 @@ int sb200_profile_read(sb200_context *ctx, size_t index, char *name, size_t name
     return sb200_profile_read_work(ctx, index, name, name_capacity, total_ms, launches, algorithmic_bytes, nullptr, nullptr);
 }
 
+int sb200_selftest_ksint_info(sb200_context *ctx, int *count, uint32_t *primes)
+{
+    SB_NEED(ctx);
+    SB_NEED(count);
+    SB_NEED(primes);
+    const KsInt &d = ctx->c->ksint;
+    *count = d.ready ? d.prm.S : 0;
+    for (int t = 0; t < *count; t++)
+        primes[t] = d.prm.p[t];
+    return SB200_OK;
+}
+
+int sb200_selftest_ksint_forward(sb200_context *ctx, const uint64_t *h_rows, size_t rows, uint32_t *h_out)
+{
+    SB_NEED(ctx);
+    SB_NEED(h_rows);
+    SB_NEED(h_out);
+    SB_TRY
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    ksint_selftest_transform(c, false, reinterpret_cast<const u64 *>(h_rows), rows, h_out);
+    return SB200_OK;
+    SB_CATCH
+}
+
+int sb200_selftest_ksint_inverse(sb200_context *ctx, uint32_t *h_data, size_t rows)
+{
+    SB_NEED(ctx);
+    SB_NEED(h_data);
+    SB_TRY
+    Context &c = *ctx->c;
+    std::lock_guard<std::mutex> lock(c.mu);
+    cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
+    ksint_selftest_transform(c, true, nullptr, rows, h_data);
+    return SB200_OK;
+    SB_CATCH
+}
+
 int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_second)
 {
     SB_NEED(warp_ops_per_second);
@@ -507,13 +553,20 @@ int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_secon
     Context &c = *ctx->c;
     std::lock_guard<std::mutex> lock(c.mu);
     cuda_check(cudaSetDevice(c.device), "cudaSetDevice");
-    *warp_ops_per_second = selftest_rate(c, kind, nullptr);
+    *warp_ops_per_second = kind >= 10 ? ksint_selftest_rate(c, kind - 10, nullptr) : selftest_rate(c, kind, nullptr);
     return SB200_OK;
     SB_CATCH
 }
 
 int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
                             unsigned long long *launches, double *algorithmic_bytes, double *butterflies, double *macs)
+{
+    return sb200_profile_read_work32(ctx, index, name, name_capacity, total_ms, launches, algorithmic_bytes, butterflies, macs, nullptr, nullptr);
+}
+
+int sb200_profile_read_work32(sb200_context *ctx, size_t index, char *name, size_t name_capacity, double *total_ms,
+                              unsigned long long *launches, double *algorithmic_bytes, double *butterflies, double *macs,
+                              double *butterflies32, double *macs32)
 {
     SB_NEED(ctx);
     SB_NEED(name);
@@ -529,7 +582,7 @@ int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t
     struct Agg
     {
         std::string name;
-        double ms = 0, bytes = 0, bflys = 0, macs = 0;
+        double ms = 0, bytes = 0, bflys = 0, macs = 0, bflys32 = 0, macs32 = 0;
         unsigned long long n = 0;
     };
     std::vector<Agg> aggs;
@@ -545,7 +598,7 @@ int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t
             aggs.push_back(Agg{ nm });
             it = aggs.end() - 1;
         }
-        it->ms += ms, it->bytes += r.bytes, it->bflys += r.bflys, it->macs += r.macs, it->n++;
+        it->ms += ms, it->bytes += r.bytes, it->bflys += r.bflys, it->macs += r.macs, it->bflys32 += r.bflys32, it->macs32 += r.macs32, it->n++;
     }
     if (index >= aggs.size())
         throw std::out_of_range("profile index");
@@ -557,6 +610,10 @@ int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t
         *butterflies = aggs[index].bflys;
     if (macs)
         *macs = aggs[index].macs;
+    if (butterflies32)
+        *butterflies32 = aggs[index].bflys32;
+    if (macs32)
+        *macs32 = aggs[index].macs32;
     return SB200_OK;
     SB_CATCH
 }
@@ -584,6 +641,7 @@ int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t d
     // keep its 128-bit sums in range
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr))
         throw std::invalid_argument("kswitch key data is not valid for encryption parameters");
+    ksint_prepare_key(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH
@@ -622,6 +680,7 @@ int sb200_kswitch_key_load(sb200_context *ctx, const uint8_t *stream, size_t len
     h->k.digits = digits;
     if (!op_residues_in_range(c, c.k, digits * 2 * c.k, h->k.d_key, nullptr)) // KSwitchKeys::load ends in is_valid_for (kswitchkeys.cpp:149-153)
         throw std::logic_error("KSwitchKeys data is invalid");
+    ksint_prepare_key(c, h->k, nullptr);
     *out = h.release();
     return SB200_OK;
     SB_CATCH

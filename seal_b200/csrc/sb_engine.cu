@@ -8,6 +8,7 @@
 //   evaluator.cpp:2384-2502 apply_galois_inplace     -> op_apply_galois (permutation fused into the loads)
 //   evaluator.cpp:1201-1294 + rns.cpp:789-901        -> op_rescale / op_mod_switch
 #include "sb_engine.cuh"
+#include "sb_src.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,7 @@ namespace sb
             cudaFree(kv.second.d_big);
             cudaFree(kv.second.d_invp);
         }
+        ksint_free(*this);
         cudaFree(scratch);
         cudaFree(aux_buf);
         cudaFree(d_flag);
@@ -308,37 +310,11 @@ namespace sb
             cuda_check(cudaMemcpy(c->d_qmod, qmod.data(), qmod.size() * sizeof(Tw), cudaMemcpyHostToDevice), "upload qmod");
             c->table_bytes += qmod.size() * sizeof(Tw);
         }
+        if (const char *e = std::getenv("SB200_KS_ALGO"))
+            c->ks_algo = std::atoi(e);
+        ksint_init(*c);
         return c;
     }
-
-    // --------------------------------------------------------------------------------- source accessors ----
-    // A batch of [L][n] polynomials, optionally seen through a Galois automorphism (galois.cpp:148-218).
-    struct Src
-    {
-        const u64 *p = nullptr;
-        long long bstride = 0; // words between consecutive batch items
-        const uint32_t *perm = nullptr; // NTT-form: out[i] = in[perm[i]]
-        uint32_t ginv = 0;              // coefficient form: inverse Galois element mod 2n (0 = identity)
-        int logn = 0;
-
-        __device__ __forceinline__ bool plain() const { return perm == nullptr && ginv == 0; }
-        __device__ __forceinline__ const u64 *row(int b, int J) const { return p + b * bstride + (static_cast<long long>(J) << logn); }
-        __device__ __forceinline__ u64 get(int b, int J, int idx, u64 qJ) const
-        {
-            const u64 *r = p + b * bstride + (static_cast<long long>(J) << logn);
-            if (perm)
-                return r[perm[idx]];
-            if (ginv)
-            {
-                uint32_t ip = (static_cast<uint32_t>(idx) * ginv) & ((2u << logn) - 1u);
-                u64 v = r[ip & ((1u << logn) - 1u)];
-                if (ip >> logn)
-                    v = v ? qJ - v : 0;
-                return v;
-            }
-            return r[idx];
-        }
-    };
 
     // -------------------------------------------------------------------------------------- NTT functors ----
     struct OpBase
@@ -1622,23 +1598,6 @@ namespace sb
         }
     };
 
-    // what the mod-down result is added to (the ciphertext being updated)
-    struct BaseSrc
-    {
-        Src s;            // polys 0,1 of the base ciphertext: poly c of item b at s.p + b*s.bstride + c*pstride
-        long long pstride = 0;
-        int c1_zero = 0;  // apply_galois: component 1 starts from zero (evaluator.cpp:2487)
-        int present = 0;
-        __device__ __forceinline__ u64 get(int b, int c, int i, int idx, u64 q) const
-        {
-            if (!present || (c == 1 && c1_zero))
-                return 0;
-            Src t = s;
-            t.p += c * pstride;
-            return t.get(b, i, idx, q);
-        }
-    };
-
     // (4b) per data prime: NTT((u mod q_i) - (half mod q_i)), subtract from the accumulated component, scale by
     //      q_top^-1 and add into the ciphertext; evaluator.cpp:2819-2864 (CKKS branch), rns.cpp:863-900 (rescale).
     //      rows = (b, c, i), i < Lout
@@ -1758,16 +1717,26 @@ namespace sb
     struct KsScratch
     {
         u64 *D, *E, *Pp, *U, *K, *T, *C2;
+        KsIntScratch I;
     };
     static size_t ks_words_per_ct(const Context &c, size_t L, bool need_c2)
     {
+        if (c.ksint_on()) // digits + (the key-multiplied tensor component) + the integer path's own buffers
+            return c.n * (L + (need_c2 ? L : 0)) + ksint_bytes_per_ct(c, L) / sizeof(u64);
         return c.n * (L + (L + 1) * L + 2 * (L + 1) + 4 + 2 * L + (need_c2 ? L : 0));
     }
     static KsScratch ks_carve(Context &c, size_t L, size_t B, bool need_c2)
     {
         u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64)));
-        KsScratch s;
+        KsScratch s{};
         s.D = p, p += B * L * c.n;
+        if (c.ksint_on())
+        {
+            s.C2 = need_c2 ? p : nullptr;
+            p += need_c2 ? B * L * c.n : 0;
+            s.I = ksint_carve(c, L, B, p);
+            return s;
+        }
         s.E = p, p += B * (L + 1) * L * c.n;
         s.Pp = p, p += B * 2 * (L + 1) * c.n;
         s.U = p, p += B * 2 * c.n;
@@ -1784,6 +1753,8 @@ namespace sb
         chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 22) / ((L + 1) * L)));
         chunk = std::min<size_t>(chunk, 32768);
         chunk = std::min<size_t>(chunk, 65535 / (L + 1)); // (b, I) pairs ride in gridDim.y of the key-switch kernels
+        if (c.ksint_on()) // 32-bit element offsets of the digit rows inside one auxiliary prime's slab
+            chunk = std::min<size_t>(chunk, std::max<size_t>(1, ((size_t(1) << 32) - 1) / (L * c.n)));
         if (c.ks_chunk_max)
             chunk = std::min(chunk, c.ks_chunk_max);
         return std::min(chunk, batch);
@@ -1941,6 +1912,11 @@ namespace sb
             OpKsIntt op{ target, s.D, c.logn, Li };
             cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats, "ks_target_intt"), "ks intt");
             dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
+        }
+        if (c.ksint_on())
+        {
+            ksint_core(c, L, B, s.I, dsrc, key, base, out, out_bs, st);
+            return;
         }
         const bool fused = c.logn >= 12; // two-pass transforms: fuse the in-block stages with the key multiply-accumulate
         double active_rows = 0;

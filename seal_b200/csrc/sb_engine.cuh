@@ -2,6 +2,7 @@
 #pragma once
 #include "sb_host.hpp"
 #include "sb_ntt.cuh"
+#include "sb_ksint.cuh"
 #include "sb_wire.hpp"
 #include <array>
 #include <map>
@@ -40,6 +41,7 @@ namespace sb
     {
         struct Context *ctx = nullptr;
         u64 *d_key = nullptr; // [digits][2][k][n]
+        uint32_t *d_key32 = nullptr; // [S][digits][2][k][n]: the key modulo the auxiliary primes, transformed (sb_ksint.cuh)
         size_t digits = 0;
     };
 
@@ -125,6 +127,9 @@ namespace sb
         size_t ks_chunk_max = 0;                       // 0 = derived from scratch_budget (sb200_context_set_limit)
         size_t host_stage_bytes = size_t(640) << 20;   // per pipeline slot of the *_host entry points
         LaunchStats stats;
+        KsInt ksint;                         // integer key-switching path (sb_ksint.cuh); ready = tables built
+        int ks_algo = 1;                     // 1 = integer path when available (n >= 4096), 0 = 64-bit digit transforms
+        bool ksint_on() const { return ks_algo == 1 && ksint.ready; }
         IoArena io;
         std::mutex mu;
         // cross-stream ordering of calls that share the scratch arenas (sb_api.cu: StreamOrder)

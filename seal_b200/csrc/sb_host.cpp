@@ -421,3 +421,118 @@ namespace sbh
         return h;
     }
 } // namespace sbh
+
+// ---- key switching through an exact integer convolution: auxiliary 29-bit primes, their transforms' tables, CRT constants ----
+#include <cmath>
+namespace sbh
+{
+    KsIntHost build_ksint(std::size_t n, const u64 *q, std::size_t k)
+    {
+        KsIntHost h;
+        const int logn = ilog2(n);
+        if (logn < 12 || logn > 17 || k < 2)
+            return h; // S = 0: not available
+        h.r = logn - 12;
+        // |sum_J d_J * k_JI| < L n max(q_J) max(q_I); the reconstruction needs P > 4 x that (fraction of P within (1/4, 3/4))
+        u64 qmax = 0;
+        for (std::size_t i = 0; i < k; i++)
+            qmax = std::max(qmax, q[i]);
+        const long double need = 2.0L + std::log2(static_cast<long double>(k - 1)) + logn + 2.0L * std::log2(static_cast<long double>(qmax)) + 0.01L;
+        long double have = 0;
+        u64 cand = ((u64(1) << 29) / (2 * n)) * (2 * n) + 1;
+        while (have < need)
+        {
+            do
+                cand -= 2 * n;
+            while (cand > (u64(1) << 28) && !is_prime(cand));
+            if (cand <= (u64(1) << 28) || h.p.size() >= 8)
+                throw std::logic_error("not enough auxiliary primes");
+            h.p.push_back(static_cast<std::uint32_t>(cand));
+            have += std::log2(static_cast<long double>(cand));
+        }
+        const int S = h.S = static_cast<int>(h.p.size());
+        const std::size_t nb = std::size_t(1) << h.r;
+        auto pair32 = [](u64 w, u64 p, std::uint32_t *dst) {
+            dst[0] = static_cast<std::uint32_t>(w);
+            dst[1] = static_cast<std::uint32_t>((w << 32) / p);
+        };
+        h.red.resize(2 * S), h.mu.resize(S), h.c1.resize(2 * S), h.c2.resize(S), h.inv_p.resize(S);
+        h.fwd_outer.assign(S * nb * 2, 0), h.inv_outer.assign(S * nb * 2, 0);
+        h.fwd_local.assign(S * n * 2, 0), h.inv_local.assign(S * n * 2, 0);
+        std::vector<u64> rp(n), irp(n);
+        for (int t = 0; t < S; t++)
+        {
+            const u64 p = h.p[t];
+            u64 psi = 0, ipsi = 0;
+            if (!minimal_primitive_root(2 * n, p, psi) || !invmod(psi, p, ipsi))
+                throw std::logic_error("auxiliary prime without a 2n-th root");
+            u64 pw = 1, ipw = 1;
+            for (std::size_t e = 0; e < n; e++)
+            {
+                const std::size_t idx = reverse_bits(e, logn);
+                rp[idx] = pw, irp[idx] = ipw;
+                pw = mulmod(pw, psi, p), ipw = mulmod(ipw, ipsi, p);
+            }
+            pair32((u64(1) << 32) % p, p, &h.red[2 * t]);
+            h.mu[t] = static_cast<std::uint32_t>((u64(1) << 32) / p);
+            h.inv_p[t] = 1.0f / static_cast<float>(p);
+            for (std::size_t e = 1; e < nb; e++)
+            {
+                pair32(rp[e], p, &h.fwd_outer[(t * nb + e) * 2]);
+                pair32(irp[e], p, &h.inv_outer[(t * nb + e) * 2]);
+            }
+            for (std::size_t g = 0; g < nb; g++)
+            {
+                std::uint32_t *f = &h.fwd_local[(t * nb + g) * 4096 * 2], *v = &h.inv_local[(t * nb + g) * 4096 * 2];
+                for (int s = 0; s < 12; s++)
+                    for (std::size_t i = 0; i < (std::size_t(1) << s); i++)
+                    {
+                        const std::size_t src = (std::size_t(1) << (h.r + s)) + (g << s) + i;
+                        std::size_t e = (std::size_t(1) << s) + i;
+                        if (s >= 8)
+                        {
+                            const std::size_t per = std::size_t(1) << (s - 8), th = i / per, u = i % per;
+                            e = 256 + (per - 1 + u) * 256 + th;
+                        }
+                        pair32(rp[src], p, f + 2 * e);
+                        pair32(irp[src], p, v + 2 * e);
+                    }
+            }
+            // CRT: (P/p_t)^-1 mod p_t
+            u64 punct = 1;
+            for (int u = 0; u < S; u++)
+                if (u != t)
+                    punct = mulmod(punct, h.p[u] % p, p);
+            u64 inv_punct = 0, inv_n = 0;
+            if (!invmod(punct, p, inv_punct) || !invmod(n % p, p, inv_n))
+                throw std::logic_error("auxiliary primes are not coprime");
+            pair32(mulmod(inv_n, inv_punct, p), p, &h.c1[2 * t]);
+            h.c2[t] = static_cast<std::uint32_t>(mulmod((p - 1) / 2, inv_punct, p)); // H = (P-1)/2 = -1/2 mod p_t
+        }
+        h.punct_mod_q.resize(k * S), h.neg_mod_q.resize(k * S);
+        for (std::size_t i = 0; i < k; i++)
+        {
+            const u64 qi = q[i];
+            u64 Pq = 1;
+            for (int t = 0; t < S; t++)
+            {
+                Pq = mulmod(Pq, h.p[t] % qi, qi);
+                u64 v = 1;
+                for (int u = 0; u < S; u++)
+                    if (u != t)
+                        v = mulmod(v, h.p[u] % qi, qi);
+                h.punct_mod_q[i * S + t] = v;
+            }
+            u64 inv2 = 0;
+            if (!invmod(2 % qi, qi, inv2))
+                throw std::logic_error("even coefficient modulus");
+            const u64 Hq = mulmod((Pq + qi - 1) % qi, inv2, qi);
+            for (int a = 0; a < S; a++)
+            {
+                const u64 aP = mulmod(static_cast<u64>(a), Pq, qi);
+                h.neg_mod_q[i * S + a] = (2 * qi - aP - Hq) % qi;
+            }
+        }
+        return h;
+    }
+} // namespace sbh

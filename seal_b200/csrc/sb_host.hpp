@@ -101,6 +101,35 @@ namespace sbh
     };
     BehzLevel build_behz(std::size_t n, const std::vector<u64> &q, std::size_t L, u64 t);
 
+
+    // ---- key switching through an exact integer convolution (sb_ksint.cu) ------------------------------------------------
+    // The sum over digits of switch_key_inplace (evaluator.cpp:2664-2755), sum_J NTT_I(d_J) (.) K_JI mod q_I, is the NTT_I image
+    // of the integer polynomial c = sum_J d_J * k_JI (negacyclic, d_J in [0,q_J), k_JI = INTT_I(K_JI) in [0,q_I)) reduced mod
+    // q_I.  |c| < L n q_J q_I, so c is computed exactly modulo S auxiliary 29-bit NTT primes (32-bit butterflies, 4x cheaper on
+    // 32-bit multipliers than 64-bit ones; the digit transforms are shared by all output primes) and reduced mod q_I afterwards.
+    // Tables: {w, floor(w 2^32 / p)} pairs.
+    struct KsIntHost
+    {
+        int S = 0;     // auxiliary primes
+        int r = 0;     // stages of the outer pass: logn - 12 (the local pass transforms 4096-element blocks in shared memory)
+        std::vector<std::uint32_t> p;          // [S]
+        std::vector<std::uint32_t> red;        // [S][2]: 2^32 mod p with its quotient (reduction of 64-bit words)
+        std::vector<std::uint32_t> mu;         // [S]: floor(2^32 / p)
+        // outer-pass twiddles [S][2^r][2]: entry m + i of the stage with m groups (entry 0 unused); forward and inverse
+        std::vector<std::uint32_t> fwd_outer, inv_outer;
+        // local-pass twiddles [S][2^r blocks][4096][2]: entries 1..255 = stages with 1..128 groups per block in natural order
+        // (2^s + i), entries 256.. = the last four stages transposed per thread: [256 + j * 256 + thread], j < 15
+        std::vector<std::uint32_t> fwd_local, inv_local;
+        // CRT reconstruction (P = prod p_t, H = (P - 1) / 2): y_t = x_t * c1_t + c2_t mod p_t with c1 = n^-1 (P/p_t)^-1,
+        // c2 = H (P/p_t)^-1; value = sum y_t (P/p_t) - alpha P - H, alpha = floor(sum y_t / p_t)
+        std::vector<std::uint32_t> c1;         // [S][2]
+        std::vector<std::uint32_t> c2;         // [S]
+        std::vector<float> inv_p;              // [S]
+        std::vector<u64> punct_mod_q;          // [k][S]: (P/p_t) mod q_i
+        std::vector<u64> neg_mod_q;            // [k][S]: (-(alpha P) - H) mod q_i, alpha < S
+    };
+    KsIntHost build_ksint(std::size_t n, const u64 *q, std::size_t k);
+
     std::uint32_t galois_elt_from_step(std::size_t n, int step);                 // galois.cpp:53-95
     std::vector<std::uint32_t> galois_table_ntt(std::size_t n, std::uint32_t elt); // galois.cpp:18-51
     // BatchEncoder::populate_matrix_reps_index_map (batchencoder.cpp:54-76): slot i of the 2 x n/2 matrix -> coefficient index

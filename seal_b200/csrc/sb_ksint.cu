@@ -1,0 +1,829 @@
+// seal_b200/csrc/sb_ksint.cu -- key switching through an exact integer convolution on 29-bit auxiliary primes (sm_100a).
+// Design and the reference lines it replaces: sb_ksint.cuh.  All kernels are integer-only; every word that leaves the path is
+// a canonical residue mod q_i, identical to the reference's.
+#include "sb_engine.cuh"
+#include "sb_ksint.cuh"
+#include <algorithm>
+
+namespace sb
+{
+    // ---------------------------------------------------------------------------------- 32-bit lazy arithmetic ----
+    struct P32
+    {
+        uint32_t p, p2, np; // p, 2p, 2^32 - p
+    };
+    __device__ __forceinline__ P32 make_p32(uint32_t p) { return P32{ p, 2 * p, 0u - p }; }
+    // x in [0, 2m) -> [0, m)
+    __device__ __forceinline__ uint32_t minsub(uint32_t x, uint32_t m) { return min(x, x - m); }
+    // y * w mod p in [0, 2p) for ANY 32-bit y  (w < p, w.y = floor(w 2^32 / p)): one high + two low multiplies
+    __device__ __forceinline__ uint32_t mul32_lazy(uint32_t y, uint2 w, uint32_t np) { return y * w.x + __umulhi(y, w.y) * np; }
+    // forward (Cooley-Tukey), values in [0, 4p)
+    __device__ __forceinline__ void ct32(uint32_t &x, uint32_t &y, uint2 w, const P32 &P)
+    {
+        const uint32_t u = minsub(x, P.p2), t = mul32_lazy(y, w, P.np);
+        x = u + t;
+        y = u - t + P.p2;
+    }
+    // inverse (Gentleman-Sande), values in [0, 2p)
+    __device__ __forceinline__ void gs32(uint32_t &x, uint32_t &y, uint2 w, const P32 &P)
+    {
+        const uint32_t u = x + y, v = x - y + P.p2;
+        x = minsub(u, P.p2);
+        y = mul32_lazy(v, w, P.np);
+    }
+    // any 64-bit word -> [0, 4p)
+    __device__ __forceinline__ uint32_t reduce64(u64 v, uint2 red, uint32_t mu, const P32 &P)
+    {
+        const uint32_t hi = static_cast<uint32_t>(v >> 32), lo = static_cast<uint32_t>(v);
+        return mul32_lazy(hi, red, P.np) + (lo + __umulhi(lo, mu) * P.np);
+    }
+
+    // LOG stages on 2^LOG registers; tw(lvl, g): twiddle of group g (< 2^lvl) of level lvl
+    template <int LOG, class TwF>
+    __device__ __forceinline__ void radix_fwd(uint32_t *a, TwF tw, const P32 &P)
+    {
+#pragma unroll
+        for (int lvl = 0; lvl < LOG; lvl++)
+        {
+            const int gap = (1 << (LOG - 1)) >> lvl;
+#pragma unroll
+            for (int g = 0; g < (1 << lvl); g++)
+            {
+                const uint2 w = tw(lvl, g);
+#pragma unroll
+                for (int e = 0; e < gap; e++)
+                    ct32(a[2 * g * gap + e], a[2 * g * gap + e + gap], w, P);
+            }
+        }
+    }
+    template <int LOG, class TwF>
+    __device__ __forceinline__ void radix_inv(uint32_t *a, TwF tw, const P32 &P)
+    {
+#pragma unroll
+        for (int lvl = LOG - 1; lvl >= 0; lvl--)
+        {
+            const int gap = (1 << (LOG - 1)) >> lvl;
+#pragma unroll
+            for (int g = 0; g < (1 << lvl); g++)
+            {
+                const uint2 w = tw(lvl, g);
+#pragma unroll
+                for (int e = 0; e < gap; e++)
+                    gs32(a[2 * g * gap + e], a[2 * g * gap + e + gap], w, P);
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------ (1a) forward, outer pass ----
+    // thread = coefficients j + 4096 e (e < 2^R) of one digit row: reduce the 64-bit words modulo every auxiliary prime and run the
+    // R stages whose butterflies span more than a 4096-block.  grid.x = rows * 16.  Dh[t][row][n].
+    template <int R, bool PLAIN>
+    __global__ void __launch_bounds__(256) ks32_fwd_outer(Src dsrc, int L, const PrimeDev *__restrict__ primes, KsIntParams prm,
+                                                           const uint2 *__restrict__ tw_outer, uint32_t *__restrict__ Dh, int rows)
+    {
+        constexpr int E = 1 << R;
+        const int row = blockIdx.x >> 4, j = ((blockIdx.x & 15) << 8) + threadIdx.x;
+        const int b = row / L, J = row - b * L;
+        u64 v[E];
+        if (PLAIN)
+        {
+            const u64 *p = dsrc.row(b, J) + j;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                v[e] = p[e << 12];
+        }
+        else
+        {
+            const u64 qJ = primes[J].q;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                v[e] = dsrc.get(b, J, j + (e << 12), qJ);
+        }
+        for (int t = 0; t < prm.S; t++)
+        {
+            const P32 P = make_p32(prm.p[t]);
+            const uint2 red = prm.red[t];
+            const uint32_t mu = prm.mu[t];
+            uint32_t a[E];
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                a[e] = reduce64(v[e], red, mu, P);
+            const uint2 *tw = tw_outer + (t << R);
+            radix_fwd<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
+            uint32_t *o = Dh + ((static_cast<size_t>(t) * rows + row) << prm.logn) + j;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                o[e << 12] = a[e];
+        }
+    }
+
+    // -------------------------------------------------------------------------------- local passes (12 stages) ----
+    // One CTA (256 threads) transforms 4096-element blocks in shared memory: three radix-16 register passes.  The block's 4095
+    // twiddles are the same for every row: staged once per CTA with one TMA bulk copy (32 KB), reused for kRowsPerCta rows.
+    // Shared-memory layout of the data: idx ^ (bit 8 -> bit 4) ^ (bits 5,6 -> bits 2,3): every access pattern below is
+    // conflict-free (pass 1: lanes consecutive; pass 2: half-warps 256 apart; pass 3: 16 consecutive words per lane as 4 x 16 B).
+    constexpr int kKsLocalSmem = 4096 * 8 + 4096 * 4 + 16;
+    constexpr int kRowsPerCta = 8;
+    __device__ __forceinline__ int swz32(int idx) { return idx ^ (((idx >> 8) & 1) << 4) ^ (((idx >> 5) & 3) << 2); }
+
+    // rows: row rr of this launch lives at data + ((rr * rstride + t) << logn); grid = (row groups, S * 2^r)
+    __global__ void __launch_bounds__(256, 4) ks32_fwd_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
+                                                              KsIntParams prm, const uint2 *__restrict__ tw_local)
+    {
+        extern __shared__ __align__(16) unsigned char ks32_smem[];
+        uint2 *tws = reinterpret_cast<uint2 *>(ks32_smem);
+        uint32_t *xs = reinterpret_cast<uint32_t *>(ks32_smem + 4096 * 8);
+        u64 *bar = reinterpret_cast<u64 *>(ks32_smem + 4096 * 12);
+        const int nb = 1 << prm.r, t = blockIdx.y / nb, g = blockIdx.y - t * nb, tid = threadIdx.x;
+        if (tid == 0)
+            mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(bar, 4096 * 8);
+            tma_load_1d(tws, tw_local + (static_cast<size_t>(blockIdx.y) << 12), 4096 * 8, bar);
+        }
+        const P32 P = make_p32(prm.p[t]);
+        const int row0 = blockIdx.x * kRowsPerCta, row1 = min(rows, row0 + kRowsPerCta);
+        const int blk = tid >> 4, l16 = tid & 15;
+        const int p3 = ((16 * tid) ^ (((tid >> 4) & 1) << 4)), hx = (tid >> 1) & 3;
+        bool first = true;
+        for (int row = row0; row < row1; row++)
+        {
+            uint32_t *base = data + ((row * rstride + t * tstride) << prm.logn) + (g << 12);
+            uint32_t a[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                a[e] = base[tid + 256 * e];
+            if (first)
+                mbar_wait(bar, 0), first = false;
+            radix_fwd<4>(a, [&](int lvl, int gg) { return tws[(1 << lvl) + gg]; }, P);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                xs[swz32(tid + 256 * e)] = a[e];
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                a[e] = xs[swz32((blk << 8) + l16 + 16 * e)];
+            radix_fwd<4>(a, [&](int lvl, int gg) { return tws[(16 << lvl) + (blk << lvl) + gg]; }, P);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                xs[swz32((blk << 8) + l16 + 16 * e)] = a[e];
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+            {
+                const uint4 q = *reinterpret_cast<const uint4 *>(xs + p3 + 4 * (h ^ hx));
+                a[4 * h] = q.x, a[4 * h + 1] = q.y, a[4 * h + 2] = q.z, a[4 * h + 3] = q.w;
+            }
+            radix_fwd<4>(a, [&](int lvl, int gg) { return tws[256 + (((1 << lvl) - 1 + gg) << 8) + tid]; }, P);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                a[e] = minsub(minsub(a[e], P.p2), P.p); // canonical: the multiply-accumulate sums L products in 64 bits
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                *reinterpret_cast<uint4 *>(base + 16 * tid + 4 * h) = make_uint4(a[4 * h], a[4 * h + 1], a[4 * h + 2], a[4 * h + 3]);
+            __syncthreads();
+        }
+    }
+
+    // inverse: inputs in [0, 2p), outputs in [0, 2p) (the scaling by n^-1 is folded into the CRT constants)
+    __global__ void __launch_bounds__(256, 4) ks32_inv_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
+                                                              KsIntParams prm, const uint2 *__restrict__ tw_local)
+    {
+        extern __shared__ __align__(16) unsigned char ks32_smem[];
+        uint2 *tws = reinterpret_cast<uint2 *>(ks32_smem);
+        uint32_t *xs = reinterpret_cast<uint32_t *>(ks32_smem + 4096 * 8);
+        u64 *bar = reinterpret_cast<u64 *>(ks32_smem + 4096 * 12);
+        const int nb = 1 << prm.r, t = blockIdx.y / nb, g = blockIdx.y - t * nb, tid = threadIdx.x;
+        if (tid == 0)
+            mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0)
+        {
+            mbar_expect_tx(bar, 4096 * 8);
+            tma_load_1d(tws, tw_local + (static_cast<size_t>(blockIdx.y) << 12), 4096 * 8, bar);
+        }
+        const P32 P = make_p32(prm.p[t]);
+        const int row0 = blockIdx.x * kRowsPerCta, row1 = min(rows, row0 + kRowsPerCta);
+        const int blk = tid >> 4, l16 = tid & 15;
+        const int p3 = ((16 * tid) ^ (((tid >> 4) & 1) << 4)), hx = (tid >> 1) & 3;
+        bool first = true;
+        for (int row = row0; row < row1; row++)
+        {
+            uint32_t *base = data + ((row * rstride + t * tstride) << prm.logn) + (g << 12);
+            uint32_t a[16];
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+            {
+                const uint4 q = *reinterpret_cast<const uint4 *>(base + 16 * tid + 4 * h);
+                a[4 * h] = q.x, a[4 * h + 1] = q.y, a[4 * h + 2] = q.z, a[4 * h + 3] = q.w;
+            }
+            if (first)
+                mbar_wait(bar, 0), first = false;
+            radix_inv<4>(a, [&](int lvl, int gg) { return tws[256 + (((1 << lvl) - 1 + gg) << 8) + tid]; }, P);
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                *reinterpret_cast<uint4 *>(xs + p3 + 4 * (h ^ hx)) = make_uint4(a[4 * h], a[4 * h + 1], a[4 * h + 2], a[4 * h + 3]);
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                a[e] = xs[swz32((blk << 8) + l16 + 16 * e)];
+            radix_inv<4>(a, [&](int lvl, int gg) { return tws[(16 << lvl) + (blk << lvl) + gg]; }, P);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                xs[swz32((blk << 8) + l16 + 16 * e)] = a[e];
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                a[e] = xs[swz32(tid + 256 * e)];
+            radix_inv<4>(a, [&](int lvl, int gg) { return tws[(1 << lvl) + gg]; }, P);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                base[tid + 256 * e] = a[e];
+            __syncthreads();
+        }
+    }
+
+    // ------------------------------------------------------------------------------ (3b) inverse, outer pass ----
+    // rows (b, c, I, t): row % S = auxiliary prime.  In place.  grid.x = rows * 16
+    template <int R>
+    __global__ void __launch_bounds__(256) ks32_inv_outer(uint32_t *__restrict__ data, KsIntParams prm, const uint2 *__restrict__ tw_outer)
+    {
+        constexpr int E = 1 << R;
+        const int row = blockIdx.x >> 4, j = ((blockIdx.x & 15) << 8) + threadIdx.x;
+        const int t = row % prm.S;
+        const P32 P = make_p32(prm.p[t]);
+        uint32_t *o = data + (static_cast<size_t>(row) << prm.logn) + j;
+        uint32_t a[E];
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            a[e] = o[e << 12];
+        const uint2 *tw = tw_outer + (t << R);
+        radix_inv<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            o[e << 12] = a[e];
+    }
+
+    // ----------------------------------------------------------------------------- (2) multiply-accumulate ----
+    // Acc[b][ic][t][x] = sum_J Dh[t][b*L + J][x] * key32[t][J][c][ki][x]  mod p_t  (-> [0, 2p)),  ic = c (L+1) + I.
+    // lane = coefficient; a warp owns a register tile of TB ciphertexts x TC outputs; the 4 warps of a CTA = 4 such tiles over the
+    // same 32 coefficients and ciphertexts, so digit words are shared by the 4 warps through L1, and consecutive CTAs (other
+    // ciphertexts, same key tile) share the key through L2.  No reduction inside the loop: L p^2 < 2^64.
+    template <int TB, int TC>
+    __global__ void __launch_bounds__(128, 3) ks32_mac(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
+                                                        KsIntParams prm, int L, int k, int digits, int B, int nbt)
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int bt = blockIdx.x % nbt, xt = blockIdx.x / nbt, t = blockIdx.z;
+        const int b0 = bt * TB, ic0 = (blockIdx.y * 4 + warp) * TC;
+        const int nic = 2 * (L + 1), logn = prm.logn;
+        if (ic0 >= nic)
+            return;
+        const int x = (xt << 5) + lane;
+        const uint32_t *dp = Dh + ((static_cast<size_t>(t) * B * L) << logn) + x;
+        const uint32_t *kp = key32 + ((static_cast<size_t>(t) * digits * 2 * k) << logn) + x;
+        uint32_t doff[TB], koff[TC];
+#pragma unroll
+        for (int i = 0; i < TB; i++)
+            doff[i] = static_cast<uint32_t>(min(b0 + i, B - 1) * L) << logn;
+#pragma unroll
+        for (int r = 0; r < TC; r++)
+        {
+            const int ic = min(ic0 + r, nic - 1), c = ic / (L + 1), I = ic - c * (L + 1);
+            koff[r] = static_cast<uint32_t>(c * k + (I == L ? k - 1 : I)) << logn;
+        }
+        u64 acc[TB][TC];
+#pragma unroll
+        for (int i = 0; i < TB; i++)
+#pragma unroll
+            for (int r = 0; r < TC; r++)
+                acc[i][r] = 0;
+        const uint32_t dstep = 1u << logn, kstep = static_cast<uint32_t>(2 * k) << logn;
+        uint32_t dv[TB], kv[TC];
+#pragma unroll
+        for (int i = 0; i < TB; i++)
+            dv[i] = dp[doff[i]];
+#pragma unroll
+        for (int r = 0; r < TC; r++)
+            kv[r] = __ldg(kp + koff[r]);
+        for (int J = 0; J < L; J++)
+        {
+            uint32_t dn[TB], kn[TC];
+            const bool more = J + 1 < L;
+            dp += dstep, kp += kstep;
+#pragma unroll
+            for (int i = 0; i < TB; i++)
+                dn[i] = more ? dp[doff[i]] : 0;
+#pragma unroll
+            for (int r = 0; r < TC; r++)
+                kn[r] = more ? __ldg(kp + koff[r]) : 0;
+#pragma unroll
+            for (int i = 0; i < TB; i++)
+#pragma unroll
+                for (int r = 0; r < TC; r++)
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(dv[i]), "r"(kv[r]));
+#pragma unroll
+            for (int i = 0; i < TB; i++)
+                dv[i] = dn[i];
+#pragma unroll
+            for (int r = 0; r < TC; r++)
+                kv[r] = kn[r];
+        }
+        const P32 P = make_p32(prm.p[t]);
+        const uint2 red = prm.red[t];
+        const uint32_t mu = prm.mu[t];
+#pragma unroll
+        for (int i = 0; i < TB; i++)
+        {
+            if (b0 + i < B)
+            {
+                uint32_t *o = Acc + (((static_cast<size_t>(b0 + i) * nic + ic0) * prm.S + t) << logn) + x;
+#pragma unroll
+                for (int r = 0; r < TC; r++)
+                    if (ic0 + r < nic)
+                        o[(static_cast<size_t>(r) * prm.S) << logn] = minsub(reduce64(acc[i][r], red, mu, P), P.p2);
+            }
+        }
+    }
+
+    // -------------------------------------------------------------- (4) reconstruction + mod-down, per coefficient ----
+    struct CrtArgs
+    {
+        const uint32_t *Acc;
+        const u64 *punct, *neg; // [k][S]
+        const PrimeDev *primes;
+        const Tw *inv_top;       // q_sp^-1 mod q_i
+        const Tw *qtop_mod;      // BGV: q_sp mod q_i
+        u64 t = 0, t_ratio = 0;  // BGV plain modulus
+        Tw inv_top_mod_t = { 0, 0 };
+        u64 *R;                  // MODE 0 / 3: [B][2][L][n]
+        u64 *out;                // MODE 1: out + b*o_bs + c*o_ps + i*n
+        long long o_bs, o_ps;
+        BaseSrc base;
+        int L, k;
+        long long total;         // B * 2 * n
+    };
+    // exact value of (sum_J d_J * k_JI)[x] mod q, from its residues modulo the auxiliary primes
+    __device__ __forceinline__ u64 crt_reconstruct(const uint32_t *__restrict__ a, const KsIntParams &prm, const u64 *__restrict__ punct,
+                                                   const u64 *__restrict__ neg, const PrimeDev &Q)
+    {
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        float f = 0.0f;
+        for (int t = 0; t < prm.S; t++)
+        {
+            const P32 P = make_p32(prm.p[t]);
+            // y = (x n^-1 + H) (P/p_t)^-1 mod p_t, canonical
+            uint32_t y = mul32_lazy(a[static_cast<size_t>(t) << prm.logn], prm.c1[t], P.np) + prm.c2[t]; // < 3p
+            y = minsub(y, P.p2);
+            y = minsub(y, P.p);
+            f += static_cast<float>(y) * prm.inv_p[t];
+            const u64 C = __ldg(punct + t);
+            const u64 p0 = static_cast<u64>(y) * static_cast<uint32_t>(C), p1 = static_cast<u64>(y) * static_cast<uint32_t>(C >> 32);
+            asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t"
+                "add.cc.u32 %1, %1, %5;\n\taddc.u32 %2, %2, %6;"
+                : "+r"(w0), "+r"(w1), "+r"(w2)
+                : "r"(static_cast<uint32_t>(p0)), "r"(static_cast<uint32_t>(p0 >> 32)), "r"(static_cast<uint32_t>(p1)),
+                  "r"(static_cast<uint32_t>(p1 >> 32)));
+        }
+        // the value is sum y_t (P/p_t) - alpha P - H with alpha = floor(sum y_t / p_t); (value + H) / P lies in (1/4, 3/4)
+        const int alpha = static_cast<int>(f);
+        const u64 ng = __ldg(neg + alpha);
+        u64 lo = (static_cast<u64>(w1) << 32) | w0, hi = w2;
+        lo += ng;
+        hi += (lo < ng);
+        return barrett128(lo, hi, Q.q, Q.ratio_lo, Q.ratio_hi);
+    }
+    // MODE 0: CKKS (coefficient-form result to R), 1: BFV (result + base to out), 3: BGV (R)
+    template <int MODE>
+    __global__ void __launch_bounds__(256) ks32_crt_kernel(CrtArgs A, KsIntParams prm)
+    {
+        const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (e >= A.total)
+            return;
+        const int logn = prm.logn, S = prm.S, L = A.L, k = A.k;
+        const int x = static_cast<int>(e & ((1 << logn) - 1)), bc = static_cast<int>(e >> logn), b = bc >> 1, c = bc & 1;
+        const uint32_t *arow = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << logn) + x;
+        const PrimeDev T = A.primes[k - 1];
+        const u64 a_top = crt_reconstruct(arow + ((static_cast<size_t>(L) * S) << logn), prm, A.punct + (k - 1) * S, A.neg + (k - 1) * S, T);
+        u64 U, K = 0;
+        if (MODE == 3)
+        {
+            // evaluator.cpp:2770-2779, rns.cpp:1202-1213: k = -u q_top^-1 mod t
+            U = a_top;
+            const u64 r = barrett64(U, A.t, A.t_ratio);
+            K = mul_shoup(r ? A.t - r : 0, A.inv_top_mod_t, A.t);
+        }
+        else
+            U = csub(a_top + (T.q >> 1), T.q); // evaluator.cpp:2809-2817
+        for (int i = 0; i < L; i++)
+        {
+            const PrimeDev Q = A.primes[i];
+            const u64 a = crt_reconstruct(arow + ((static_cast<size_t>(i) * S) << logn), prm, A.punct + i * S, A.neg + i * S, Q);
+            u64 u = (T.q > Q.q) ? barrett64(U, Q.q, Q.ratio_hi) : csub(U, Q.q), d;
+            if (MODE == 3)
+            {
+                const u64 kk = (A.t > Q.q) ? barrett64(K, Q.q, Q.ratio_hi) : K;
+                d = csub(u + mul_shoup(kk, A.qtop_mod[i], Q.q), Q.q); // rns.cpp:1216-1235
+            }
+            else
+                d = csub(u + Q.q - barrett64(T.q >> 1, Q.q, Q.ratio_hi), Q.q); // evaluator.cpp:2819-2864
+            const u64 r = mul_shoup(a + Q.q - d, A.inv_top[i], Q.q);
+            if (MODE == 1)
+                A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << logn) + x] = csub(r + A.base.get(b, c, i, x, Q.q), Q.q);
+            else
+                A.R[((static_cast<size_t>(bc) * L + i) << logn) + x] = r;
+        }
+    }
+
+    // ------------------------------------------------- (5) the result back to NTT form, added into the ciphertext ----
+    struct OpAddBaseFwd
+    {
+        u64 *R;   // [B][2][L][n], transformed in place
+        u64 *out; // out + b*o_bs + c*o_ps + i*n
+        long long o_bs, o_ps;
+        BaseSrc base;
+        int logn, L;
+        __device__ __forceinline__ bool skip(int) const { return false; }
+        __device__ __forceinline__ int pid(int row) const { return row % L; }
+        __device__ __forceinline__ u64 *rowp(int row) const { return R + (static_cast<long long>(row) << logn); }
+        __device__ __forceinline__ const u64 *direct(int row, const PrimeDev &) const { return rowp(row); }
+        __device__ __forceinline__ u64 load1(int row, int idx, const PrimeDev &) const { return rowp(row)[idx]; }
+        __device__ __forceinline__ void load8(int row, int idx0, u64 (&a)[8], const PrimeDev &) const
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                a[j] = rowp(row)[idx0 + j];
+        }
+        __device__ __forceinline__ u64 *mid(int row) const { return rowp(row); }
+        __device__ __forceinline__ void store1(int row, int idx, u64 v, const PrimeDev &P) const
+        {
+            const int i = row % L, bc = row / L, b = bc >> 1, c = bc & 1;
+            const u64 t = csub(csub(v, P.q2), P.q);
+            out[b * o_bs + c * o_ps + (static_cast<long long>(i) << logn) + idx] = csub(t + base.get(b, c, i, idx, P.q), P.q);
+        }
+        __device__ __forceinline__ void store8(int row, int idx0, u64 (&a)[8], const PrimeDev &P) const
+        {
+            const int i = row % L, bc = row / L, b = bc >> 1, c = bc & 1;
+            ulonglong2 *op_ = reinterpret_cast<ulonglong2 *>(out + b * o_bs + c * o_ps + (static_cast<long long>(i) << logn) + idx0);
+            const bool has_base = base.present && !(c == 1 && base.c1_zero);
+            const bool base_plain = has_base && base.s.plain();
+            const ulonglong2 *bp = base_plain ? reinterpret_cast<const ulonglong2 *>(base.s.row(b, i) + c * base.pstride + idx0) : nullptr;
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+            {
+                u64 r0 = csub(csub(a[2 * h], P.q2), P.q), r1 = csub(csub(a[2 * h + 1], P.q2), P.q);
+                if (base_plain)
+                {
+                    const ulonglong2 bv = bp[h];
+                    r0 = csub(r0 + bv.x, P.q), r1 = csub(r1 + bv.y, P.q);
+                }
+                else if (has_base)
+                {
+                    r0 = csub(r0 + base.get(b, c, i, idx0 + 2 * h, P.q), P.q);
+                    r1 = csub(r1 + base.get(b, c, i, idx0 + 2 * h + 1, P.q), P.q);
+                }
+                op_[h] = make_ulonglong2(r0, r1);
+            }
+        }
+    };
+
+    // ------------------------------------------------------------------------------------------------ host side ----
+    template <class T>
+    static T *upload(const std::vector<T> &v, size_t &bytes)
+    {
+        T *d = nullptr;
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&d), std::max<size_t>(1, v.size()) * sizeof(T)), "cudaMalloc(ksint table)");
+        cuda_check(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice), "upload ksint table");
+        bytes += v.size() * sizeof(T);
+        return d;
+    }
+
+    void ksint_init(Context &c)
+    {
+        c.ksint.ready = false;
+        if (c.logn < 12 || c.k < 2)
+            return;
+        const sbh::KsIntHost h = sbh::build_ksint(c.n, c.q.data(), c.k);
+        if (h.S == 0 || h.S > kKsMaxS)
+            return;
+        KsInt &d = c.ksint;
+        d.prm.S = h.S, d.prm.r = h.r, d.prm.logn = c.logn;
+        for (int t = 0; t < h.S; t++)
+        {
+            d.prm.p[t] = h.p[t], d.prm.mu[t] = h.mu[t], d.prm.c2[t] = h.c2[t], d.prm.inv_p[t] = h.inv_p[t];
+            d.prm.red[t] = make_uint2(h.red[2 * t], h.red[2 * t + 1]);
+            d.prm.c1[t] = make_uint2(h.c1[2 * t], h.c1[2 * t + 1]);
+        }
+        d.d_fwd_outer = reinterpret_cast<uint2 *>(upload(h.fwd_outer, c.table_bytes));
+        d.d_inv_outer = reinterpret_cast<uint2 *>(upload(h.inv_outer, c.table_bytes));
+        d.d_fwd_local = reinterpret_cast<uint2 *>(upload(h.fwd_local, c.table_bytes));
+        d.d_inv_local = reinterpret_cast<uint2 *>(upload(h.inv_local, c.table_bytes));
+        d.d_punct = upload(h.punct_mod_q, c.table_bytes);
+        d.d_neg = upload(h.neg_mod_q, c.table_bytes);
+        cuda_check(cudaFuncSetAttribute(ks32_fwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
+        cuda_check(cudaFuncSetAttribute(ks32_inv_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
+        d.ready = true;
+    }
+    void ksint_free(Context &c)
+    {
+        KsInt &d = c.ksint;
+        cudaFree(d.d_fwd_outer), cudaFree(d.d_inv_outer), cudaFree(d.d_fwd_local), cudaFree(d.d_inv_local), cudaFree(d.d_punct), cudaFree(d.d_neg);
+        d = KsInt{};
+    }
+
+    size_t ksint_bytes_per_ct(const Context &c, size_t L)
+    {
+        const size_t S = c.ksint.prm.S;
+        return c.n * (std::max(S * L * 4, 2 * L * 8) + 2 * (L + 1) * S * 4);
+    }
+    KsIntScratch ksint_carve(const Context &c, size_t L, size_t B, void *base)
+    {
+        const size_t S = c.ksint.prm.S;
+        KsIntScratch s;
+        unsigned char *p = static_cast<unsigned char *>(base);
+        s.Dh = reinterpret_cast<uint32_t *>(p);
+        s.R = reinterpret_cast<u64 *>(p);
+        p += B * c.n * std::max(S * L * 4, 2 * L * 8);
+        s.Acc = reinterpret_cast<uint32_t *>(p);
+        return s;
+    }
+
+    template <bool PLAIN>
+    static void launch_fwd_outer(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, cudaStream_t st)
+    {
+        const KsInt &d = c.ksint;
+        const unsigned grid = static_cast<unsigned>(rows) * 16u;
+        switch (d.prm.r)
+        {
+        case 0: ks32_fwd_outer<0, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 1: ks32_fwd_outer<1, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 2: ks32_fwd_outer<2, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 3: ks32_fwd_outer<3, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 4: ks32_fwd_outer<4, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 5: ks32_fwd_outer<5, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        default: throw std::logic_error("unsupported transform size");
+        }
+    }
+
+    // rows of 64-bit words (dsrc rows (b, J), J < L) -> Dh[t][rows][n], transformed modulo every auxiliary prime
+    static void ksint_forward(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, cudaStream_t st)
+    {
+        const KsInt &d = c.ksint;
+        const double n = static_cast<double>(c.n), S = d.prm.S;
+        const bool plain = dsrc.perm == nullptr && dsrc.ginv == 0;
+        c.stats.begin("ks32_fwd_outer", 0, rows * n * (8.0 + 4.0 * S), st, 0, 0);
+        c.stats.work32(0.5 * rows * n * S * d.prm.r, 0);
+        plain ? launch_fwd_outer<true>(c, dsrc, L, rows, Dh, st) : launch_fwd_outer<false>(c, dsrc, L, rows, Dh, st);
+        c.stats.end(st);
+        cuda_check(cudaGetLastError(), "ks32_fwd_outer");
+        dim3 grid(static_cast<unsigned>((rows + kRowsPerCta - 1) / kRowsPerCta), static_cast<unsigned>(d.prm.S << d.prm.r));
+        c.stats.begin("ks32_fwd_local", 0, rows * n * 8.0 * S, st, 0, 0);
+        c.stats.work32(0.5 * rows * n * S * 12, 0);
+        ks32_fwd_local<<<grid, 256, kKsLocalSmem, st>>>(Dh, rows, 1, rows, d.prm, d.d_fwd_local);
+        c.stats.end(st);
+        cuda_check(cudaGetLastError(), "ks32_fwd_local");
+    }
+
+    void ksint_prepare_key(Context &c, KSwitchKey &key, cudaStream_t st)
+    {
+        if (!c.ksint.ready || key.d_key32)
+            return;
+        const size_t rows = key.digits * 2 * c.k, words = rows * c.n, S = c.ksint.prm.S;
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&key.d_key32), S * words * sizeof(uint32_t)), "cudaMalloc(key, auxiliary primes)");
+        // coefficient form of every key row (row % k = its prime), then the digit path's forward transforms: khat[t][row][n]
+        u64 *tmp = nullptr;
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&tmp), words * sizeof(u64)), "cudaMalloc(key staging)");
+        cuda_check(cudaMemcpyAsync(tmp, key.d_key, words * sizeof(u64), cudaMemcpyDeviceToDevice, st), "key copy");
+        op_ntt(c, true, c.k, 2, key.digits, tmp, st);
+        const bool prof = c.stats.profiling; // a one-time conversion: not part of any timed operation
+        c.stats.profiling = false;
+        ksint_forward(c, Src{ tmp, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), key.d_key32, st);
+        c.stats.profiling = prof;
+        cuda_check(cudaStreamSynchronize(st), "synchronize");
+        cuda_check(cudaFree(tmp), "cudaFree(key staging)");
+    }
+
+    template <int R>
+    static void launch_inv_outer_r(uint32_t *data, unsigned grid, const KsInt &d, cudaStream_t st)
+    {
+        ks32_inv_outer<R><<<grid, 256, 0, st>>>(data, d.prm, d.d_inv_outer);
+    }
+
+    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st);
+
+    void ksint_core(Context &c, size_t L, size_t B, const KsIntScratch &s, Src dsrc, const KSwitchKey &key, BaseSrc base, u64 *out,
+                    long long o_bs, cudaStream_t st)
+    {
+        const KsInt &d = c.ksint;
+        if (!d.ready || !key.d_key32)
+            throw std::logic_error("integer key-switching path is not initialised");
+        const int Li = static_cast<int>(L), ki = static_cast<int>(c.k), Bi = static_cast<int>(B), S = d.prm.S;
+        const double n = static_cast<double>(c.n);
+        const int rows = Bi * Li, nic = 2 * (Li + 1), arows = Bi * nic;
+        // (1) digits -> auxiliary primes, forward transforms
+        ksint_forward(c, dsrc, Li, rows, s.Dh, st);
+        // (2) products with the key, summed over the digits
+        {
+            constexpr int TB = 4, TC = 8;
+            const int nbt = (Bi + TB - 1) / TB;
+            dim3 grid(static_cast<unsigned>(nbt) * static_cast<unsigned>(c.n / 32), static_cast<unsigned>((nic + 4 * TC - 1) / (4 * TC)),
+                      static_cast<unsigned>(S));
+            // one pass over the key + the transformed digits in, the sums out
+            c.stats.begin("ks32_mac", 0, 4.0 * n * S * (static_cast<double>(key.digits) * 2 * ki + rows + arows), st);
+            c.stats.work32(0, static_cast<double>(arows) * Li * S * n);
+            ks32_mac<TB, TC><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, static_cast<int>(key.digits), Bi, nbt);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "ks32_mac");
+        }
+        // (3) inverse transforms of the sums
+        launch_inverse(c, s.Acc, arows, st);
+        // (4) exact integers -> residues mod q_I, mod-down by the special prime in coefficient form
+        const long long o_ps = static_cast<long long>(L) * c.n;
+        if (!o_bs)
+            o_bs = 2 * o_ps;
+        {
+            CrtArgs A{};
+            A.Acc = s.Acc, A.punct = d.d_punct, A.neg = d.d_neg, A.primes = c.d_primes;
+            A.inv_top = c.d_invq + (c.k - 1) * c.k;
+            A.R = s.R, A.out = out, A.o_bs = o_bs, A.o_ps = o_ps, A.base = base, A.L = Li, A.k = ki;
+            A.total = static_cast<long long>(B) * 2 * c.n;
+            const unsigned grid = static_cast<unsigned>((A.total + 255) / 256);
+            c.stats.begin("ks32_crt", 0, n * B * 2 * (4.0 * S * (L + 1) + 8.0 * L), st);
+            if (c.scheme == 3)
+            {
+                A.qtop_mod = c.d_qmod + (c.k - 1) * c.k;
+                A.t = c.t, A.t_ratio = c.t_ratio;
+                A.inv_top_mod_t = Tw{ c.inv_q_mod_t[c.k - 1], sbh::shoup(c.inv_q_mod_t[c.k - 1], c.t) };
+                ks32_crt_kernel<3><<<grid, 256, 0, st>>>(A, d.prm);
+            }
+            else if (c.scheme == 1)
+                ks32_crt_kernel<1><<<grid, 256, 0, st>>>(A, d.prm);
+            else
+                ks32_crt_kernel<0><<<grid, 256, 0, st>>>(A, d.prm);
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "ks32_crt_kernel");
+        }
+        // (5) CKKS / BGV: back to NTT form, added into the ciphertext
+        if (c.scheme != 1)
+        {
+            OpAddBaseFwd op{ s.R, out, o_bs, o_ps, base, c.logn, Li };
+            cuda_check(launch_ntt_fwd(op, static_cast<int>(B * 2 * L), c.logn, c.d_primes, st, c.stats, "ks_result_ntt", -1, c.fast_q), "ks result ntt");
+        }
+    }
+
+    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st)
+    {
+        const KsInt &d = c.ksint;
+        const int S = d.prm.S;
+        const double n = static_cast<double>(c.n);
+        dim3 grid(static_cast<unsigned>((arows + kRowsPerCta - 1) / kRowsPerCta), static_cast<unsigned>(S << d.prm.r));
+        c.stats.begin("ks32_inv_local", 0, 8.0 * arows * S * n, st);
+        c.stats.work32(0.5 * arows * S * n * 12, 0);
+        ks32_inv_local<<<grid, 256, kKsLocalSmem, st>>>(data, arows, S, 1, d.prm, d.d_inv_local);
+        c.stats.end(st);
+        cuda_check(cudaGetLastError(), "ks32_inv_local");
+        if (d.prm.r > 0)
+        {
+            const unsigned g1 = static_cast<unsigned>(arows) * S * 16u;
+            c.stats.begin("ks32_inv_outer", 0, 8.0 * arows * S * n, st);
+            c.stats.work32(0.5 * arows * S * n * d.prm.r, 0);
+            switch (d.prm.r)
+            {
+            case 1: launch_inv_outer_r<1>(data, g1, d, st); break;
+            case 2: launch_inv_outer_r<2>(data, g1, d, st); break;
+            case 3: launch_inv_outer_r<3>(data, g1, d, st); break;
+            case 4: launch_inv_outer_r<4>(data, g1, d, st); break;
+            case 5: launch_inv_outer_r<5>(data, g1, d, st); break;
+            default: throw std::logic_error("unsupported transform size");
+            }
+            c.stats.end(st);
+            cuda_check(cudaGetLastError(), "ks32_inv_outer");
+        }
+    }
+
+    void ksint_selftest_transform(Context &c, bool inverse, const u64 *h_rows, size_t rows, uint32_t *h_io)
+    {
+        if (!c.ksint.ready)
+            throw std::logic_error("integer key-switching path is not available for this context");
+        const size_t S = c.ksint.prm.S, out_bytes = S * rows * c.n * sizeof(uint32_t), in_bytes = rows * c.n * sizeof(u64);
+        unsigned char *base = static_cast<unsigned char *>(c.ensure_scratch(out_bytes + in_bytes));
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(base);
+        if (inverse)
+        {
+            cuda_check(cudaMemcpy(d32, h_io, out_bytes, cudaMemcpyHostToDevice), "upload");
+            launch_inverse(c, d32, static_cast<int>(rows), nullptr);
+        }
+        else
+        {
+            u64 *d64 = reinterpret_cast<u64 *>(base + out_bytes);
+            cuda_check(cudaMemcpy(d64, h_rows, in_bytes, cudaMemcpyHostToDevice), "upload");
+            ksint_forward(c, Src{ d64, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), d32, nullptr);
+        }
+        cuda_check(cudaMemcpy(h_io, d32, out_bytes, cudaMemcpyDeviceToHost), "download");
+    }
+
+    // ---- arithmetic ceilings of this path, measured in process: the butterflies / multiply-accumulates on registers only ----
+    template <int KIND>
+    __global__ void __launch_bounds__(256, 4) ks32_selftest_bfly(uint32_t *d, uint32_t p, int rounds)
+    {
+        __shared__ uint2 ts[256];
+        const P32 P = make_p32(p);
+        {
+            const uint32_t w = (threadIdx.x * 2654435761u + 12345u) % p;
+            ts[threadIdx.x] = make_uint2(w, static_cast<uint32_t>((static_cast<u64>(w) << 32) / p));
+        }
+        __syncthreads();
+        uint32_t a[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            a[j] = d[(static_cast<size_t>(blockIdx.x) * 16 + j) * 256 + threadIdx.x] % p;
+        const int lane = threadIdx.x & 31;
+        for (int r = 0; r < rounds; r++)
+        {
+            const uint2 *t = ts + ((r * 7 + lane) & 127); // per-lane twiddles from shared memory, as the local passes read them
+            auto tw = [&](int lvl, int g) { return t[(1 << lvl) - 1 + g]; };
+            if (KIND == 0)
+                radix_fwd<4>(a, tw, P);
+            else
+                radix_inv<4>(a, tw, P);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            d[(static_cast<size_t>(blockIdx.x) * 16 + j) * 256 + threadIdx.x] = a[j];
+    }
+    __global__ void __launch_bounds__(128, 3) ks32_selftest_mac(uint32_t *d, int rounds)
+    {
+        uint32_t dv[4], kv[8];
+        u64 acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            dv[i] = d[(static_cast<size_t>(blockIdx.x) * 12 + i) * 128 + threadIdx.x] >> 3;
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            kv[r] = d[(static_cast<size_t>(blockIdx.x) * 12 + 4 + r) * 128 + threadIdx.x] >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                acc[i][r] = 0;
+        for (int q = 0; q < rounds; q++)
+        {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(dv[i] + q), "r"(kv[r] ^ q)); // operands change every round
+        }
+        u64 x = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                x ^= acc[i][r];
+        d[static_cast<size_t>(blockIdx.x) * 12 * 128 + threadIdx.x] = static_cast<uint32_t>(x) ^ static_cast<uint32_t>(x >> 32);
+    }
+    double ksint_selftest_rate(Context &c, int kind, cudaStream_t st)
+    {
+        if (!c.ksint.ready)
+            throw std::logic_error("integer key-switching path is not available for this context");
+        int sms = 0;
+        cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device), "device attribute");
+        const int rounds = 512;
+        const size_t words = static_cast<size_t>(sms) * 4 * 16 * 256;
+        uint32_t *d = static_cast<uint32_t *>(c.ensure_scratch(words * sizeof(uint32_t)));
+        cuda_check(cudaMemsetAsync(d, 0x5a, words * sizeof(uint32_t), st), "memset");
+        cudaEvent_t e0 = c.stats.get_event(), e1 = c.stats.get_event();
+        double ops = 0;
+        auto run = [&](auto launch) {
+            launch();
+            cuda_check(cudaEventRecord(e0, st), "record");
+            launch();
+            cuda_check(cudaEventRecord(e1, st), "record");
+            cuda_check(cudaEventSynchronize(e1), "synchronize");
+            cuda_check(cudaGetLastError(), "selftest kernel");
+        };
+        switch (kind)
+        {
+        case 0: // forward butterflies at the local passes' launch shape (256 threads x 4 CTAs per SM): 32 per thread and round
+            ops = static_cast<double>(sms) * 4 * 8 * rounds * 32.0;
+            run([&] { ks32_selftest_bfly<0><<<sms * 4, 256, 0, st>>>(d, c.ksint.prm.p[0], rounds); });
+            break;
+        case 1:
+            ops = static_cast<double>(sms) * 4 * 8 * rounds * 32.0;
+            run([&] { ks32_selftest_bfly<1><<<sms * 4, 256, 0, st>>>(d, c.ksint.prm.p[0], rounds); });
+            break;
+        case 2: // multiply-accumulates at the product kernel's launch shape (128 threads x 3 CTAs per SM): 32 per thread and round
+            ops = static_cast<double>(sms) * 3 * 4 * rounds * 32.0;
+            run([&] { ks32_selftest_mac<<<sms * 3, 128, 0, st>>>(d, rounds); });
+            break;
+        default: throw std::invalid_argument("unknown selftest");
+        }
+        float ms = 0;
+        cuda_check(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+        c.stats.pool.push_back(e0);
+        c.stats.pool.push_back(e1);
+        return ops / (ms * 1e-3);
+    }
+} // namespace sb

@@ -493,6 +493,7 @@ namespace sb
             double bytes;
             double bflys, macs; // modular butterflies / 64x64-bit multiply-accumulates the launch executes (second ceiling)
             cudaEvent_t e0, e1;
+            double bflys32 = 0, macs32 = 0; // 32-bit butterflies / 32x32->64 multiply-accumulates (integer key-switching path)
         };
         std::vector<Rec> recs;
         std::vector<cudaEvent_t> pool;
@@ -516,6 +517,11 @@ namespace sb
             Rec r{ name, pass, bytes, bflys, macs, get_event(), get_event() };
             cudaEventRecord(r.e0, st);
             recs.push_back(r);
+        }
+        void work32(double bflys32, double macs32)
+        {
+            if (profiling)
+                recs.back().bflys32 = bflys32, recs.back().macs32 = macs32;
         }
         void end(cudaStream_t st)
         {

@@ -1,0 +1,103 @@
+"""The integer key-switching path (-m gpu; seal_b200/csrc/sb_ksint.cu): its 32-bit transforms modulo the auxiliary primes are
+checked by what a negacyclic NTT must satisfy (round trip, convolution theorem against a direct O(n^2) product), and the whole
+path is compared with the 64-bit digit-transform path of the same library and with the oracle / the reference on the same
+inputs (switch_key_inplace, evaluator.cpp:2561-2867) -- both must give the reference's words."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sb():
+    import seal_b200
+
+    return seal_b200
+
+
+def negacyclic(a, b, p):
+    """direct product in Z_p[x]/(x^n + 1); a, b < p < 2^29"""
+    n = len(a)
+    a, b = a.astype(np.uint64), b.astype(np.uint64)
+    acc = np.zeros(n, dtype=np.uint64)
+    for i in range(n):
+        # x^i * b: coefficients wrap with a sign
+        rot = np.concatenate([(p - b[n - i:]) % p, b[:n - i]]) if i else b
+        acc = (acc + a[i] * rot) % p
+    return acc
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 65536])
+def test_small_transforms_roundtrip_and_convolution(n):
+    S = sb()
+    mods = O.coeff_modulus_create(n, [50, 50, 51])
+    ctx = S.Context(S.CKKS, n, mods)
+    primes = ctx.ksint_primes()
+    assert len(primes) >= 4 and all(p < 2 ** 29 and p % (2 * n) == 1 for p in primes)
+    rng = np.random.default_rng(n)
+    rows = 11  # not a multiple of the rows a CTA loops over
+    x = rng.integers(0, 2 ** 61, (rows, n), dtype=np.uint64)
+    x[0, :] = 0
+    x[0, 1] = 1  # the monomial x: its transform is the table of odd psi powers, all nonzero
+    f = ctx.ksint_forward(x)  # [S][rows][n]
+    assert f.shape == (len(primes), rows, n)
+    for t, p in enumerate(primes):
+        assert (f[t] < p).all(), "forward outputs must be canonical"
+    back = ctx.ksint_inverse(np.ascontiguousarray(f.transpose(1, 0, 2)))  # [rows][S][n]
+    for t, p in enumerate(primes):
+        assert (back[:, t, :] < 2 * p).all()
+        assert ((back[:, t, :].astype(np.uint64) % p) == ((x % p) * n) % p).all(), f"round trip, prime {p}"
+    if n <= 8192:
+        a, b = x[1], x[2]
+        fa, fb = f[:, 1, :].astype(np.uint64), f[:, 2, :].astype(np.uint64)
+        prod = np.stack([(fa[t] * fb[t]) % p for t, p in enumerate(primes)])[None].astype(np.uint32)  # [1][S][n]
+        conv = ctx.ksint_inverse(prod)[0]
+        for t, p in enumerate(primes):
+            want = negacyclic(a % p, b % p, p)
+            assert ((conv[t].astype(np.uint64) % p) == (want * n) % p).all(), f"convolution theorem, prime {p}"
+
+
+def _keyswitch_case(scheme_name, n, bits, batch, t=0):
+    S = sb()
+    scheme = getattr(S, scheme_name)
+    mods = O.coeff_modulus_create(n, bits)
+    k, L = len(mods), len(mods) - 1
+    ctx = S.Context(scheme, n, mods, t) if t else S.Context(scheme, n, mods)
+    oc = O.Oracle(getattr(O, scheme_name), n, mods, t) if t else O.Oracle(getattr(O, scheme_name), n, mods)
+    rng = np.random.default_rng(7 * n + k)
+    key = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k)]) for _ in range(2)])
+                    for _ in range(L)])
+    c3 = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(L)]) for _ in range(3)])
+                   for _ in range(batch)])
+    rk = ctx.load_key(key)
+    assert ctx.ksint_primes(), "the integer path must be available at n >= 4096"
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
+    got_int = ctx.relinearize(c3, rk)
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 0)
+    got_64 = ctx.relinearize(c3, rk)
+    for b in range(batch):
+        want = oc.relinearize(L, c3[b], key)
+        assert (got_64[b] == want).all(), "64-bit digit-transform path vs oracle"
+        assert (got_int[b] == want).all(), "integer path vs oracle"
+    # a lower level uses a subset of the digits and of the output primes (evaluator.cpp:2617-2640)
+    if L >= 2:
+        ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
+        low = np.ascontiguousarray(c3[:, :, :L - 1, :])
+        got = ctx.relinearize(low, rk)
+        for b in range(batch):
+            assert (got[b] == oc.relinearize(L - 1, low[b], key)).all(), "integer path, lower level"
+
+
+@pytest.mark.parametrize("n,bits,batch", [(4096, [36, 36, 37], 3), (8192, [50, 50, 50, 51], 5), (16384, [60, 60, 60], 2),
+                                          (32768, [55] * 5, 9)])
+def test_relinearize_integer_path_vs_oracle_ckks(n, bits, batch):
+    _keyswitch_case("CKKS", n, bits, batch)
+
+
+def test_relinearize_integer_path_vs_oracle_bfv():
+    _keyswitch_case("BFV", 4096, [36, 36, 37], 3, t=65537)
+
+
+def test_relinearize_integer_path_vs_oracle_bgv():
+    _keyswitch_case("BGV", 8192, [50, 50, 50, 51], 3, t=65537)

@@ -311,3 +311,36 @@ def test_batch_index_map_matches_oracle():
         assert (oc.batch_codec(oc.batch_codec(v, False), True) == v).all()
         tt = O.Oracle(O.CKKS, n, [t])  # a context whose only prime is t gives the plain transform
         assert (tt.ntt_row(0, oc.batch_codec(v, False)) == scattered).all()
+
+
+@pytest.mark.parametrize("args", [["4096", "36", "36", "37"], ["8192", "55", "55", "55", "56"], ["16384", "60", "60", "60"],
+                                  ["32768"] + ["55"] * 16])
+def test_ksint_host_tables_transforms_and_crt(args):
+    """integer key-switching path (seal_b200/csrc/sb_ksint.cu): the tables sbh::build_ksint produces, driven on the CPU with
+    the kernels' own index scheme, give transforms that invert each other and satisfy the convolution theorem, and CRT
+    constants that reconstruct signed integers inside the bound L n q^2 exactly (tests/cpp/ksint_host_check.cpp)"""
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-C", cpp, "ksint"], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(cpp, "_bin", "ksint_host_check")] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_ksint_swizzle_conflict_free():
+    """shared-memory layout of the 4096-word blocks of the 32-bit local passes (swz32 in sb_ksint.cu): every access pattern of
+    the three radix-16 passes touches 32 distinct banks per warp-wide 4-byte access and 8 distinct 16-byte bank groups per
+    quarter-warp for the 16-byte accesses of the last pass"""
+    def swz(i):
+        return i ^ (((i >> 8) & 1) << 4) ^ (((i >> 5) & 3) << 2)
+
+    assert sorted(swz(i) for i in range(4096)) == list(range(4096))
+    for warp in range(8):
+        tids = [warp * 32 + l for l in range(32)]
+        for e in range(16):
+            assert len({swz(t + 256 * e) % 32 for t in tids}) == 32                              # pass 1
+            assert len({swz(((t >> 4) << 8) + (t & 15) + 16 * e) % 32 for t in tids}) == 32      # pass 2
+        for h in range(4):                                                                        # pass 3: 16-byte accesses
+            for q in range(4):
+                grp = tids[8 * q: 8 * q + 8]
+                phys = [((16 * t) ^ (((t >> 4) & 1) << 4)) + 4 * (h ^ ((t >> 1) & 3)) for t in grp]
+                assert all(p == swz(16 * t + 4 * h) for p, t in zip(phys, grp))
+                assert len({(p // 4) % 8 for p in phys}) == 8
