@@ -455,6 +455,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE.json cfg2-cfg4 lines and the C++ harness")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the reference (profiling runs only)")
+    ap.add_argument("--ks-algo", type=int, default=None, choices=[0, 1],
+                    help="key switching: 1 = integer convolution on auxiliary primes (library default), 0 = 64-bit digit transforms")
     ap.add_argument("--scratch-gib", type=float, default=0.0, help="key-switching scratch budget (0: what the device has left, at most 64 GiB)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -483,6 +485,9 @@ def main():
     mods = S.coeff_modulus_create(n, wl["bits"])
     k, L = len(mods), len(mods) - 1
     ctx = S.Context(wl["scheme"], n, mods, device=local)
+    if args.ks_algo is not None:
+        ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, args.ks_algo)
+    aux_primes = ctx.ksint_primes() if args.ks_algo != 0 else []
     g = torch.Generator(device="cuda")
     g.manual_seed(0x5EA1 + rank)
 
@@ -540,7 +545,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = ctx.launch_count - launches0
-    prof = ctx.profile_read_work()
+    prof = ctx.profile_read_work32()
     ctx.profile(False)
 
     # ---- verification of the timed run's outputs against the reference Evaluator (rank 0's shard; the other ranks run the
@@ -597,6 +602,8 @@ def main():
     if rank == 0:
         ceil = {"fwd_col_shape": ctx.selftest_rate(0), "fwd_fused_shape": ctx.selftest_rate(1), "inverse": ctx.selftest_rate(2),
                 "mac": ctx.selftest_rate(3)}
+        if aux_primes:  # the integer key-switching path: 32-bit butterflies and 32x32->64 multiply-accumulates
+            ceil.update({"bfly32_fwd": ctx.selftest_rate(10), "bfly32_inv": ctx.selftest_rate(11), "mac32": ctx.selftest_rate(12)})
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
@@ -671,16 +678,26 @@ def main():
 
     def alu_entry(r):
         """second ceiling for one kernel: time the measured butterfly / multiply-accumulate rates would need vs the time it took"""
-        name, kms, launches_, _, bf, mc = r
-        if bf <= 0 and mc <= 0:
+        name, kms, launches_, _, bf, mc, b32, m32 = r
+        if bf <= 0 and mc <= 0 and b32 <= 0 and m32 <= 0:
             return None
         inv = name.startswith(("ks_target_intt", "ks_top_intt", "rescale_top", "ntt_inv", "ks_prod_intt", "modswitch_top"))
         rate_b = ceil["inverse"] if inv else (ceil["fwd_fused_shape"] if name == "ks_local_mac" else ceil["fwd_col_shape"])
         floor_s = bf / 32 / rate_b + mc / 32 / ceil["mac"]
+        rate32 = None
+        if b32 > 0 or m32 > 0:
+            rate32 = ceil["bfly32_inv"] if name.startswith("ks32_inv") else ceil["bfly32_fwd"]
+            floor_s += b32 / 32 / rate32 + m32 / 32 / ceil["mac32"]
         e = {"kernel": name, "frac_of_alu_ceiling": floor_s / (kms * 1e-3), "floor_ms": floor_s * 1e3}
         if bf > 0:
             e["achieved_clk_per_warp_bfly"] = kms * 1e-3 * sm_hz * smsp / (bf / 32)
             e["floor_clk_per_warp_bfly"] = sm_hz * smsp / rate_b
+        if b32 > 0:
+            e["achieved_clk_per_warp_bfly32"] = kms * 1e-3 * sm_hz * smsp / (b32 / 32)
+            e["floor_clk_per_warp_bfly32"] = sm_hz * smsp / rate32
+        if m32 > 0:
+            e["achieved_clk_per_warp_mac32"] = kms * 1e-3 * sm_hz * smsp / (m32 / 32)
+            e["floor_clk_per_warp_mac32"] = sm_hz * smsp / ceil["mac32"]
         return e
 
     alu = [e for e in (alu_entry(r) for r in prof) if e]
@@ -697,11 +714,14 @@ def main():
         "bytes_basis": "SURVEY 8(d): the whole operation's compulsory bytes (6*L*n*8 per ciphertext + key per B_reuse) are attributed to "
                        "the dominant kernel's launches; intermediates (digits, accumulated products) are not counted",
         "alg_bytes_per_ciphertext": ct_bytes, "key_bytes": key_bytes, "B_reuse": b_reuse, "key_passes_per_step": nchunks,
+        "key_bytes_device_format": (len(aux_primes) * 4 * 2 * L * k * n) if aux_primes else key_bytes,
         "alu": {"unit": "clocks per warp-butterfly per SM sub-partition (32 butterflies, one sub-partition)",
                 "ceiling_source": "sb200_selftest_rate in this process, same clocks: the path's butterfly / multiply-accumulate code on registers only",
                 "ceilings_warp_ops_per_s": ceil, "sm_hz_used": sm_hz, "kernels": alu,
                 "step_frac_of_alu_ceiling": whole_floor / (tot_prof_ms * 1e-3)},
-        "note": "integer-multiply-issue bound path (64-bit modular butterflies on 32-bit multipliers); both ceilings of SURVEY 8(d) are reported",
+        "note": ("key switching = exact integer convolution modulo %d auxiliary 29-bit primes (32-bit butterflies, 32x32->64 multiply-accumulates), "
+                 "CRT back to the q_i; both ceilings of SURVEY 8(d) are reported" % len(aux_primes)) if aux_primes else
+                "integer-multiply-issue bound path (64-bit modular butterflies on 32-bit multipliers); both ceilings of SURVEY 8(d) are reported",
         "kernels": [{"name": r[0], "ms": round(r[1], 3), "launches": r[2], "share": round(r[1] / tot_prof_ms, 4)} for r in prof]}
     op_gbps = step_bytes * args.steps / (ms_total * 1e-3) / 1e9 / 1.0  # per GPU: every rank runs the same step
     cpu = None
@@ -732,6 +752,7 @@ def main():
                    "batch_per_gpu": B, "global_batch": B * world, "ops": "Evaluator::multiply + relinearize_inplace (fused call)",
                    "l2": f"inputs {2 * B * 2 * L * n * 8 / 2**30:.1f} GiB per GPU >> 126 MB L2 (no flush needed)",
                    "scratch_budget_GiB": round(scratch_budget / 2**30, 1), "ciphertexts_per_key_pass": chunk,
+                   "key_switching": ("integer convolution, auxiliary primes %s" % aux_primes) if aux_primes else "64-bit digit transforms",
                    "parallelism": f"batch sharded x{world}, no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "verified": verified, "roofline": roofline,
         "ntt": {"metric": "negacyclic NTT GB/s (2*n*8 B per row per transform)", "rows_per_transform_call": ntt_rows, "n": n,

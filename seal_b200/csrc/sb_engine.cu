@@ -1727,7 +1727,7 @@ namespace sb
     }
     static KsScratch ks_carve(Context &c, size_t L, size_t B, bool need_c2)
     {
-        u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64)));
+        u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64) + (c.ksint_on() ? ksint_bytes_fixed(c, L) : 0)));
         KsScratch s{};
         s.D = p, p += B * L * c.n;
         if (c.ksint_on())
@@ -1749,12 +1749,12 @@ namespace sb
     {
         size_t per = ks_words_per_ct(c, L, need_c2) * sizeof(u64);
         size_t chunk = std::max<size_t>(1, c.scratch_budget / per);
+        if (c.ksint_on() && c.scratch_budget > 2 * ksint_bytes_fixed(c, L))
+            chunk = std::max<size_t>(1, (c.scratch_budget - ksint_bytes_fixed(c, L)) / per);
         // keep the row counts of a launch (B * (L+1) * L digit rows) far inside int range; element offsets are 64-bit everywhere
         chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 22) / ((L + 1) * L)));
         chunk = std::min<size_t>(chunk, 32768);
         chunk = std::min<size_t>(chunk, 65535 / (L + 1)); // (b, I) pairs ride in gridDim.y of the key-switch kernels
-        if (c.ksint_on()) // 32-bit element offsets of the digit rows inside one auxiliary prime's slab
-            chunk = std::min<size_t>(chunk, std::max<size_t>(1, ((size_t(1) << 32) - 1) / (L * c.n)));
         if (c.ks_chunk_max)
             chunk = std::min(chunk, c.ks_chunk_max);
         return std::min(chunk, batch);

@@ -4,6 +4,7 @@
 #include "sb_engine.cuh"
 #include "sb_ksint.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace sb
 {
@@ -76,10 +77,28 @@ namespace sb
 
     // ------------------------------------------------------------------------------ (1a) forward, outer pass ----
     // thread = coefficients j + 4096 e (e < 2^R) of one digit row: reduce the 64-bit words modulo every auxiliary prime and run the
-    // R stages whose butterflies span more than a 4096-block.  grid.x = rows * 16.  Dh[t][row][n].
+    // R stages whose butterflies span more than a 4096-block.  grid.x = rows * 16.  Dh[t][out row][n], out rows per RowMap.
+    struct RowMap
+    {
+        int mode, a, rows_out;
+        // 0: identity; 1: digit rows (b, J) -> J * a + b (a = padded ciphertext count: the product kernel reads the ciphertexts of one
+        // digit at constant strides); 2: key rows (J, c, ki) -> (J, c, (ki + 1) mod k), a = k: the special prime first, so that the
+        // output primes of every level are consecutive rows
+        __device__ __forceinline__ int out(int row, int b, int J) const
+        {
+            if (mode == 1)
+                return J * a + b;
+            if (mode == 2)
+            {
+                const int hi = row / a, ki = row - hi * a;
+                return hi * a + (ki + 1 == a ? 0 : ki + 1);
+            }
+            return row;
+        }
+    };
     template <int R, bool PLAIN>
     __global__ void __launch_bounds__(256) ks32_fwd_outer(Src dsrc, int L, const PrimeDev *__restrict__ primes, KsIntParams prm,
-                                                           const uint2 *__restrict__ tw_outer, uint32_t *__restrict__ Dh, int rows)
+                                                           const uint2 *__restrict__ tw_outer, uint32_t *__restrict__ Dh, RowMap map)
     {
         constexpr int E = 1 << R;
         const int row = blockIdx.x >> 4, j = ((blockIdx.x & 15) << 8) + threadIdx.x;
@@ -99,6 +118,7 @@ namespace sb
             for (int e = 0; e < E; e++)
                 v[e] = dsrc.get(b, J, j + (e << 12), qJ);
         }
+        const int orow = map.out(row, b, J);
         for (int t = 0; t < prm.S; t++)
         {
             const P32 P = make_p32(prm.p[t]);
@@ -110,7 +130,7 @@ namespace sb
                 a[e] = reduce64(v[e], red, mu, P);
             const uint2 *tw = tw_outer + (t << R);
             radix_fwd<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
-            uint32_t *o = Dh + ((static_cast<size_t>(t) * rows + row) << prm.logn) + j;
+            uint32_t *o = Dh + ((static_cast<size_t>(t) * map.rows_out + orow) << prm.logn) + j;
 #pragma unroll
             for (int e = 0; e < E; e++)
                 o[e << 12] = a[e];
@@ -267,70 +287,69 @@ namespace sb
     }
 
     // ----------------------------------------------------------------------------- (2) multiply-accumulate ----
-    // Acc[b][ic][t][x] = sum_J Dh[t][b*L + J][x] * key32[t][J][c][ki][x]  mod p_t  (-> [0, 2p)),  ic = c (L+1) + I.
-    // lane = coefficient; a warp owns a register tile of TB ciphertexts x TC outputs; the 4 warps of a CTA = 4 such tiles over the
-    // same 32 coefficients and ciphertexts, so digit words are shared by the 4 warps through L1, and consecutive CTAs (other
-    // ciphertexts, same key tile) share the key through L2.  No reduction inside the loop: L p^2 < 2^64.
-    template <int TB, int TC>
-    __global__ void __launch_bounds__(128, 3) ks32_mac(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
+    // Acc[b][c][I'][t][x] = sum_J Dh[t][J][b][x] * key32[t][J][c][I'][x]  mod p_t  (-> [0, 2p));  I' = 0: the special prime,
+    // I' = i + 1: data prime i (so the L + 1 outputs of every level are consecutive key rows).
+    // lane = coefficient; a warp owns a register tile of TB ciphertexts x TC outputs (one component c); the 4 warps of a CTA take 4
+    // output tiles over the same 32 coefficients and ciphertexts, so digit words are shared through L1, and consecutive CTAs (other
+    // ciphertexts, same key tile) share the key through L2.  LOGN is a template parameter: every load of the loop has an immediate
+    // offset from one of two pointers that advance once per digit.  No reduction inside the loop: L p^2 < 2^64.
+    constexpr int kMacTB = 4, kMacTC = 8;
+    template <int LOGN>
+    __global__ void __launch_bounds__(128, 4) ks32_mac(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
                                                         KsIntParams prm, int L, int k, int digits, int B, int nbt)
     {
+        constexpr int TB = kMacTB, TC = kMacTC;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int bt = blockIdx.x % nbt, xt = blockIdx.x / nbt, t = blockIdx.z;
-        const int b0 = bt * TB, ic0 = (blockIdx.y * 4 + warp) * TC;
-        const int nic = 2 * (L + 1), logn = prm.logn;
-        if (ic0 >= nic)
+        // CTA order: ciphertext tile fastest (same key tile: L2), then the output-tile group (same digit words: L2), then coefficients
+        const int ntile = (L + TC) / TC; // tiles per component: ceil((L + 1) / TC)
+        const int ny = (2 * ntile + 3) / 4;
+        const int bt = blockIdx.x % nbt, yg = (blockIdx.x / nbt) % ny, xt = blockIdx.x / (nbt * ny), t = blockIdx.z;
+        const int task = yg * 4 + warp;
+        if (task >= 2 * ntile)
             return;
+        const int c = task / ntile, i0 = (task - c * ntile) * TC, b0 = bt * TB, Bpad = nbt * TB;
         const int x = (xt << 5) + lane;
-        const uint32_t *dp = Dh + ((static_cast<size_t>(t) * B * L) << logn) + x;
-        const uint32_t *kp = key32 + ((static_cast<size_t>(t) * digits * 2 * k) << logn) + x;
-        uint32_t doff[TB], koff[TC];
-#pragma unroll
-        for (int i = 0; i < TB; i++)
-            doff[i] = static_cast<uint32_t>(min(b0 + i, B - 1) * L) << logn;
-#pragma unroll
-        for (int r = 0; r < TC; r++)
-        {
-            const int ic = min(ic0 + r, nic - 1), c = ic / (L + 1), I = ic - c * (L + 1);
-            koff[r] = static_cast<uint32_t>(c * k + (I == L ? k - 1 : I)) << logn;
-        }
+        const uint32_t *dp = Dh + ((static_cast<size_t>(t) * L * Bpad + b0) << LOGN) + x;
+        const uint32_t *kp = key32 + (((static_cast<size_t>(t) * digits * 2 + c) * k + i0) << LOGN) + x;
+        const size_t dstep = static_cast<size_t>(Bpad) << LOGN, kstep = static_cast<size_t>(2 * k) << LOGN;
         u64 acc[TB][TC];
 #pragma unroll
         for (int i = 0; i < TB; i++)
 #pragma unroll
             for (int r = 0; r < TC; r++)
                 acc[i][r] = 0;
-        const uint32_t dstep = 1u << logn, kstep = static_cast<uint32_t>(2 * k) << logn;
-        uint32_t dv[TB], kv[TC];
-#pragma unroll
-        for (int i = 0; i < TB; i++)
-            dv[i] = dp[doff[i]];
-#pragma unroll
-        for (int r = 0; r < TC; r++)
-            kv[r] = __ldg(kp + koff[r]);
-        for (int J = 0; J < L; J++)
-        {
-            uint32_t dn[TB], kn[TC];
-            const bool more = J + 1 < L;
-            dp += dstep, kp += kstep;
+        // two operand sets in flight: the loads of digit J+1 are issued before the products of digit J
+        uint32_t dA[TB], kA[TC], dB[TB], kB[TC];
+        auto load = [&](uint32_t(&d_)[TB], uint32_t(&k_)[TC]) {
 #pragma unroll
             for (int i = 0; i < TB; i++)
-                dn[i] = more ? dp[doff[i]] : 0;
+                d_[i] = dp[i << LOGN];
 #pragma unroll
             for (int r = 0; r < TC; r++)
-                kn[r] = more ? __ldg(kp + koff[r]) : 0;
+                k_[r] = __ldg(kp + (r << LOGN));
+        };
+        auto macs = [&](const uint32_t(&d_)[TB], const uint32_t(&k_)[TC]) {
 #pragma unroll
             for (int i = 0; i < TB; i++)
 #pragma unroll
                 for (int r = 0; r < TC; r++)
-                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(dv[i]), "r"(kv[r]));
-#pragma unroll
-            for (int i = 0; i < TB; i++)
-                dv[i] = dn[i];
-#pragma unroll
-            for (int r = 0; r < TC; r++)
-                kv[r] = kn[r];
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d_[i]), "r"(k_[r]));
+        };
+        load(dA, kA);
+        int J = 0;
+#pragma unroll 1
+        for (; J + 2 <= L; J += 2)
+        {
+            dp += dstep, kp += kstep;
+            load(dB, kB);
+            macs(dA, kA);
+            if (J + 2 < L)
+                dp += dstep, kp += kstep;
+            load(dA, kA);
+            macs(dB, kB);
         }
+        if (J < L)
+            macs(dA, kA);
         const P32 P = make_p32(prm.p[t]);
         const uint2 red = prm.red[t];
         const uint32_t mu = prm.mu[t];
@@ -339,11 +358,11 @@ namespace sb
         {
             if (b0 + i < B)
             {
-                uint32_t *o = Acc + (((static_cast<size_t>(b0 + i) * nic + ic0) * prm.S + t) << logn) + x;
+                uint32_t *o = Acc + ((((static_cast<size_t>(b0 + i) * 2 + c) * (L + 1) + i0) * prm.S + t) << LOGN) + x;
 #pragma unroll
                 for (int r = 0; r < TC; r++)
-                    if (ic0 + r < nic)
-                        o[(static_cast<size_t>(r) * prm.S) << logn] = minsub(reduce64(acc[i][r], red, mu, P), P.p2);
+                    if (i0 + r <= L)
+                        o[(static_cast<size_t>(r) * prm.S) << LOGN] = minsub(reduce64(acc[i][r], red, mu, P), P.p2);
             }
         }
     }
@@ -406,7 +425,7 @@ namespace sb
         const int x = static_cast<int>(e & ((1 << logn) - 1)), bc = static_cast<int>(e >> logn), b = bc >> 1, c = bc & 1;
         const uint32_t *arow = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << logn) + x;
         const PrimeDev T = A.primes[k - 1];
-        const u64 a_top = crt_reconstruct(arow + ((static_cast<size_t>(L) * S) << logn), prm, A.punct + (k - 1) * S, A.neg + (k - 1) * S, T);
+        const u64 a_top = crt_reconstruct(arow, prm, A.punct + (k - 1) * S, A.neg + (k - 1) * S, T); // I' = 0: the special prime
         u64 U, K = 0;
         if (MODE == 3)
         {
@@ -420,7 +439,7 @@ namespace sb
         for (int i = 0; i < L; i++)
         {
             const PrimeDev Q = A.primes[i];
-            const u64 a = crt_reconstruct(arow + ((static_cast<size_t>(i) * S) << logn), prm, A.punct + i * S, A.neg + i * S, Q);
+            const u64 a = crt_reconstruct(arow + ((static_cast<size_t>(i + 1) * S) << logn), prm, A.punct + i * S, A.neg + i * S, Q);
             u64 u = (T.q > Q.q) ? barrett64(U, Q.q, Q.ratio_hi) : csub(U, Q.q), d;
             if (MODE == 3)
             {
@@ -434,6 +453,119 @@ namespace sb
                 A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << logn) + x] = csub(r + A.base.get(b, c, i, x, Q.q), Q.q);
             else
                 A.R[((static_cast<size_t>(bc) * L + i) << logn) + x] = r;
+        }
+    }
+
+    // (3b)+(4) fused: the thread that reconstructs coefficients j + 4096 e (e < 2^R) first runs the R outer inverse stages on them
+    // (they are exactly the 2^R words those butterflies couple), so the inverse transforms' outer pass never goes through memory.
+    // grid.x = B * 2 * 32 CTAs of 128 threads.
+    template <int MODE, int R>
+    __global__ void __launch_bounds__(128) ks32_crt_fused(CrtArgs A, KsIntParams prm, const uint2 *__restrict__ tw_outer)
+    {
+        constexpr int E = 1 << R;
+        const int logn = prm.logn, S = prm.S, L = A.L, k = A.k;
+        const int bc = blockIdx.x >> 5, j = ((blockIdx.x & 31) << 7) + threadIdx.x, b = bc >> 1, c = bc & 1;
+        const uint32_t *arow = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << logn) + j;
+        auto reconstruct = [&](int Ip, int ki, const PrimeDev &Q, u64(&val)[E]) {
+            uint32_t w0[E], w1[E], w2[E];
+            float f[E];
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                w0[e] = w1[e] = w2[e] = 0, f[e] = 0.0f;
+            const u64 *punct = A.punct + ki * S;
+            for (int t = 0; t < S; t++)
+            {
+                const P32 P = make_p32(prm.p[t]);
+                const uint32_t *src = arow + ((static_cast<size_t>(Ip) * S + t) << logn);
+                uint32_t a[E];
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                    a[e] = src[e << 12];
+                const uint2 *tw = tw_outer + (t << R);
+                radix_inv<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
+                const uint2 c1 = prm.c1[t];
+                const uint32_t c2 = prm.c2[t];
+                const float ip = prm.inv_p[t];
+                const u64 C = __ldg(punct + t);
+                const uint32_t C0 = static_cast<uint32_t>(C), C1 = static_cast<uint32_t>(C >> 32);
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                {
+                    uint32_t y = mul32_lazy(a[e], c1, P.np) + c2; // < 3p
+                    y = minsub(minsub(y, P.p2), P.p);
+                    f[e] += static_cast<float>(y) * ip;
+                    const u64 p0 = static_cast<u64>(y) * C0, p1 = static_cast<u64>(y) * C1;
+                    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t"
+                        "add.cc.u32 %1, %1, %5;\n\taddc.u32 %2, %2, %6;"
+                        : "+r"(w0[e]), "+r"(w1[e]), "+r"(w2[e])
+                        : "r"(static_cast<uint32_t>(p0)), "r"(static_cast<uint32_t>(p0 >> 32)), "r"(static_cast<uint32_t>(p1)),
+                          "r"(static_cast<uint32_t>(p1 >> 32)));
+                }
+            }
+            const u64 *neg = A.neg + ki * S;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+            {
+                const u64 ng = __ldg(neg + static_cast<int>(f[e]));
+                u64 lo = (static_cast<u64>(w1[e]) << 32) | w0[e], hi = w2[e];
+                lo += ng;
+                hi += (lo < ng);
+                val[e] = barrett128(lo, hi, Q.q, Q.ratio_lo, Q.ratio_hi);
+            }
+        };
+        const PrimeDev T = A.primes[k - 1];
+        u64 U[E], K[MODE == 3 ? E : 1];
+        reconstruct(0, k - 1, T, U);
+#pragma unroll
+        for (int e = 0; e < E; e++)
+        {
+            if (MODE == 3)
+            {
+                const u64 r = barrett64(U[e], A.t, A.t_ratio);
+                K[e] = mul_shoup(r ? A.t - r : 0, A.inv_top_mod_t, A.t);
+            }
+            else
+                U[e] = csub(U[e] + (T.q >> 1), T.q);
+        }
+        for (int i = 0; i < L; i++)
+        {
+            const PrimeDev Q = A.primes[i];
+            u64 a[E];
+            reconstruct(i + 1, i, Q, a);
+            const Tw inv = A.inv_top[i];
+            const u64 half_mod = barrett64(T.q >> 1, Q.q, Q.ratio_hi);
+#pragma unroll
+            for (int e = 0; e < E; e++)
+            {
+                const u64 u = (T.q > Q.q) ? barrett64(U[e], Q.q, Q.ratio_hi) : csub(U[e], Q.q);
+                u64 d;
+                if (MODE == 3)
+                {
+                    const u64 kk = (A.t > Q.q) ? barrett64(K[e], Q.q, Q.ratio_hi) : K[e];
+                    d = csub(u + mul_shoup(kk, A.qtop_mod[i], Q.q), Q.q);
+                }
+                else
+                    d = csub(u + Q.q - half_mod, Q.q);
+                const u64 r = mul_shoup(a[e] + Q.q - d, inv, Q.q);
+                const int x = j + (e << 12);
+                if (MODE == 1)
+                    A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << logn) + x] = csub(r + A.base.get(b, c, i, x, Q.q), Q.q);
+                else
+                    A.R[((static_cast<size_t>(bc) * L + i) << logn) + x] = r;
+            }
+        }
+    }
+    template <int MODE>
+    static void launch_crt_fused(const CrtArgs &A, const KsInt &d, unsigned grid, cudaStream_t st)
+    {
+        switch (d.prm.r)
+        {
+        case 0: ks32_crt_fused<MODE, 0><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        case 1: ks32_crt_fused<MODE, 1><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        case 2: ks32_crt_fused<MODE, 2><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        case 3: ks32_crt_fused<MODE, 3><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        case 4: ks32_crt_fused<MODE, 4><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        default: throw std::logic_error("unsupported transform size");
         }
     }
 
@@ -524,6 +656,8 @@ namespace sb
         d.d_neg = upload(h.neg_mod_q, c.table_bytes);
         cuda_check(cudaFuncSetAttribute(ks32_fwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
         cuda_check(cudaFuncSetAttribute(ks32_inv_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
+        if (const char *e = std::getenv("SB200_KS_FUSE_CRT"))
+            d.fuse_crt = std::atoi(e) != 0;
         d.ready = true;
     }
     void ksint_free(Context &c)
@@ -533,55 +667,59 @@ namespace sb
         d = KsInt{};
     }
 
+    // the digit slab holds ceil(B / TB) * TB ciphertexts (register tiles of the product kernel); the per-ciphertext figure counts one
+    // ciphertext of padding per real one only through ksint_bytes_fixed (at most TB - 1 rows per digit and prime)
     size_t ksint_bytes_per_ct(const Context &c, size_t L)
     {
         const size_t S = c.ksint.prm.S;
         return c.n * (std::max(S * L * 4, 2 * L * 8) + 2 * (L + 1) * S * 4);
     }
+    size_t ksint_bytes_fixed(const Context &c, size_t L) { return c.n * c.ksint.prm.S * L * 4 * (kMacTB - 1); }
     KsIntScratch ksint_carve(const Context &c, size_t L, size_t B, void *base)
     {
-        const size_t S = c.ksint.prm.S;
+        const size_t S = c.ksint.prm.S, Bpad = (B + kMacTB - 1) / kMacTB * kMacTB;
         KsIntScratch s;
         unsigned char *p = static_cast<unsigned char *>(base);
         s.Dh = reinterpret_cast<uint32_t *>(p);
         s.R = reinterpret_cast<u64 *>(p);
-        p += B * c.n * std::max(S * L * 4, 2 * L * 8);
+        p += c.n * std::max(S * L * 4 * Bpad, 2 * L * 8 * B);
         s.Acc = reinterpret_cast<uint32_t *>(p);
         return s;
     }
 
     template <bool PLAIN>
-    static void launch_fwd_outer(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, cudaStream_t st)
+    static void launch_fwd_outer(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, RowMap map, cudaStream_t st)
     {
         const KsInt &d = c.ksint;
         const unsigned grid = static_cast<unsigned>(rows) * 16u;
         switch (d.prm.r)
         {
-        case 0: ks32_fwd_outer<0, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
-        case 1: ks32_fwd_outer<1, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
-        case 2: ks32_fwd_outer<2, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
-        case 3: ks32_fwd_outer<3, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
-        case 4: ks32_fwd_outer<4, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
-        case 5: ks32_fwd_outer<5, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, rows); break;
+        case 0: ks32_fwd_outer<0, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
+        case 1: ks32_fwd_outer<1, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
+        case 2: ks32_fwd_outer<2, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
+        case 3: ks32_fwd_outer<3, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
+        case 4: ks32_fwd_outer<4, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
+        case 5: ks32_fwd_outer<5, PLAIN><<<grid, 256, 0, st>>>(dsrc, L, c.d_primes, d.prm, d.d_fwd_outer, Dh, map); break;
         default: throw std::logic_error("unsupported transform size");
         }
     }
 
-    // rows of 64-bit words (dsrc rows (b, J), J < L) -> Dh[t][rows][n], transformed modulo every auxiliary prime
-    static void ksint_forward(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, cudaStream_t st)
+    // rows of 64-bit words (dsrc rows (b, J), J < L) -> Dh[t][map.rows_out][n], transformed modulo every auxiliary prime
+    static void ksint_forward(Context &c, Src dsrc, int L, int rows, uint32_t *Dh, RowMap map, cudaStream_t st)
     {
         const KsInt &d = c.ksint;
         const double n = static_cast<double>(c.n), S = d.prm.S;
         const bool plain = dsrc.perm == nullptr && dsrc.ginv == 0;
         c.stats.begin("ks32_fwd_outer", 0, rows * n * (8.0 + 4.0 * S), st, 0, 0);
         c.stats.work32(0.5 * rows * n * S * d.prm.r, 0);
-        plain ? launch_fwd_outer<true>(c, dsrc, L, rows, Dh, st) : launch_fwd_outer<false>(c, dsrc, L, rows, Dh, st);
+        plain ? launch_fwd_outer<true>(c, dsrc, L, rows, Dh, map, st) : launch_fwd_outer<false>(c, dsrc, L, rows, Dh, map, st);
         c.stats.end(st);
         cuda_check(cudaGetLastError(), "ks32_fwd_outer");
-        dim3 grid(static_cast<unsigned>((rows + kRowsPerCta - 1) / kRowsPerCta), static_cast<unsigned>(d.prm.S << d.prm.r));
+        // (padding rows of the digit layout are transformed too: a few uninitialised rows whose products are never stored)
+        dim3 grid(static_cast<unsigned>((map.rows_out + kRowsPerCta - 1) / kRowsPerCta), static_cast<unsigned>(d.prm.S << d.prm.r));
         c.stats.begin("ks32_fwd_local", 0, rows * n * 8.0 * S, st, 0, 0);
         c.stats.work32(0.5 * rows * n * S * 12, 0);
-        ks32_fwd_local<<<grid, 256, kKsLocalSmem, st>>>(Dh, rows, 1, rows, d.prm, d.d_fwd_local);
+        ks32_fwd_local<<<grid, 256, kKsLocalSmem, st>>>(Dh, map.rows_out, 1, map.rows_out, d.prm, d.d_fwd_local);
         c.stats.end(st);
         cuda_check(cudaGetLastError(), "ks32_fwd_local");
     }
@@ -591,7 +729,9 @@ namespace sb
         if (!c.ksint.ready || key.d_key32)
             return;
         const size_t rows = key.digits * 2 * c.k, words = rows * c.n, S = c.ksint.prm.S;
-        cuda_check(cudaMalloc(reinterpret_cast<void **>(&key.d_key32), S * words * sizeof(uint32_t)), "cudaMalloc(key, auxiliary primes)");
+        // + 8 rows: the last register tile of the product kernel may read (and discard) up to 7 rows past the end
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&key.d_key32), (S * words + 8 * c.n) * sizeof(uint32_t)), "cudaMalloc(key, auxiliary primes)");
+        cuda_check(cudaMemsetAsync(key.d_key32 + S * words, 0, 8 * c.n * sizeof(uint32_t), st), "memset");
         // coefficient form of every key row (row % k = its prime), then the digit path's forward transforms: khat[t][row][n]
         u64 *tmp = nullptr;
         cuda_check(cudaMalloc(reinterpret_cast<void **>(&tmp), words * sizeof(u64)), "cudaMalloc(key staging)");
@@ -599,7 +739,8 @@ namespace sb
         op_ntt(c, true, c.k, 2, key.digits, tmp, st);
         const bool prof = c.stats.profiling; // a one-time conversion: not part of any timed operation
         c.stats.profiling = false;
-        ksint_forward(c, Src{ tmp, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), key.d_key32, st);
+        ksint_forward(c, Src{ tmp, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), key.d_key32,
+                      RowMap{ 2, static_cast<int>(c.k), static_cast<int>(rows) }, st);
         c.stats.profiling = prof;
         cuda_check(cudaStreamSynchronize(st), "synchronize");
         cuda_check(cudaFree(tmp), "cudaFree(key staging)");
@@ -611,7 +752,7 @@ namespace sb
         ks32_inv_outer<R><<<grid, 256, 0, st>>>(data, d.prm, d.d_inv_outer);
     }
 
-    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st);
+    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st, bool outer = true);
 
     void ksint_core(Context &c, size_t L, size_t B, const KsIntScratch &s, Src dsrc, const KSwitchKey &key, BaseSrc base, u64 *out,
                     long long o_bs, cudaStream_t st)
@@ -623,22 +764,32 @@ namespace sb
         const double n = static_cast<double>(c.n);
         const int rows = Bi * Li, nic = 2 * (Li + 1), arows = Bi * nic;
         // (1) digits -> auxiliary primes, forward transforms
-        ksint_forward(c, dsrc, Li, rows, s.Dh, st);
+        const int nbt = (Bi + kMacTB - 1) / kMacTB, Bpad = nbt * kMacTB;
+        ksint_forward(c, dsrc, Li, rows, s.Dh, RowMap{ 1, Bpad, Li * Bpad }, st);
         // (2) products with the key, summed over the digits
         {
-            constexpr int TB = 4, TC = 8;
-            const int nbt = (Bi + TB - 1) / TB;
-            dim3 grid(static_cast<unsigned>(nbt) * static_cast<unsigned>(c.n / 32), static_cast<unsigned>((nic + 4 * TC - 1) / (4 * TC)),
-                      static_cast<unsigned>(S));
+            const int ntile = (Li + kMacTC) / kMacTC;
+            dim3 grid(static_cast<unsigned>(nbt) * static_cast<unsigned>((2 * ntile + 3) / 4) * static_cast<unsigned>(c.n / 32), 1, static_cast<unsigned>(S));
             // one pass over the key + the transformed digits in, the sums out
-            c.stats.begin("ks32_mac", 0, 4.0 * n * S * (static_cast<double>(key.digits) * 2 * ki + rows + arows), st);
+            c.stats.begin("ks32_mac", 0, 4.0 * n * S * (static_cast<double>(Li) * 2 * (Li + 1) + rows + arows), st);
             c.stats.work32(0, static_cast<double>(arows) * Li * S * n);
-            ks32_mac<TB, TC><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, static_cast<int>(key.digits), Bi, nbt);
+            const int dg = static_cast<int>(key.digits);
+            switch (c.logn)
+            {
+            case 12: ks32_mac<12><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 13: ks32_mac<13><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 14: ks32_mac<14><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 15: ks32_mac<15><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 16: ks32_mac<16><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 17: ks32_mac<17><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            default: throw std::logic_error("unsupported transform size");
+            }
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks32_mac");
         }
-        // (3) inverse transforms of the sums
-        launch_inverse(c, s.Acc, arows, st);
+        // (3) inverse transforms of the sums; the outer stages ride in the reconstruction kernel (fuse_crt) or run as their own pass
+        const bool fuse_crt = d.fuse_crt && d.prm.r <= 4;
+        launch_inverse(c, s.Acc, arows, st, !fuse_crt);
         // (4) exact integers -> residues mod q_I, mod-down by the special prime in coefficient form
         const long long o_ps = static_cast<long long>(L) * c.n;
         if (!o_bs)
@@ -649,17 +800,29 @@ namespace sb
             A.inv_top = c.d_invq + (c.k - 1) * c.k;
             A.R = s.R, A.out = out, A.o_bs = o_bs, A.o_ps = o_ps, A.base = base, A.L = Li, A.k = ki;
             A.total = static_cast<long long>(B) * 2 * c.n;
-            const unsigned grid = static_cast<unsigned>((A.total + 255) / 256);
+            const unsigned grid = static_cast<unsigned>((A.total + 255) / 256), gridf = static_cast<unsigned>(B * 2 * 32);
             c.stats.begin("ks32_crt", 0, n * B * 2 * (4.0 * S * (L + 1) + 8.0 * L), st);
+            if (fuse_crt)
+                c.stats.work32(0.5 * arows * S * n * d.prm.r, 0);
             if (c.scheme == 3)
             {
                 A.qtop_mod = c.d_qmod + (c.k - 1) * c.k;
                 A.t = c.t, A.t_ratio = c.t_ratio;
                 A.inv_top_mod_t = Tw{ c.inv_q_mod_t[c.k - 1], sbh::shoup(c.inv_q_mod_t[c.k - 1], c.t) };
-                ks32_crt_kernel<3><<<grid, 256, 0, st>>>(A, d.prm);
+                if (fuse_crt)
+                    launch_crt_fused<3>(A, d, gridf, st);
+                else
+                    ks32_crt_kernel<3><<<grid, 256, 0, st>>>(A, d.prm);
             }
             else if (c.scheme == 1)
-                ks32_crt_kernel<1><<<grid, 256, 0, st>>>(A, d.prm);
+            {
+                if (fuse_crt)
+                    launch_crt_fused<1>(A, d, gridf, st);
+                else
+                    ks32_crt_kernel<1><<<grid, 256, 0, st>>>(A, d.prm);
+            }
+            else if (fuse_crt)
+                launch_crt_fused<0>(A, d, gridf, st);
             else
                 ks32_crt_kernel<0><<<grid, 256, 0, st>>>(A, d.prm);
             c.stats.end(st);
@@ -673,7 +836,7 @@ namespace sb
         }
     }
 
-    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st)
+    static void launch_inverse(Context &c, uint32_t *data, int arows, cudaStream_t st, bool outer)
     {
         const KsInt &d = c.ksint;
         const int S = d.prm.S;
@@ -684,7 +847,7 @@ namespace sb
         ks32_inv_local<<<grid, 256, kKsLocalSmem, st>>>(data, arows, S, 1, d.prm, d.d_inv_local);
         c.stats.end(st);
         cuda_check(cudaGetLastError(), "ks32_inv_local");
-        if (d.prm.r > 0)
+        if (d.prm.r > 0 && outer)
         {
             const unsigned g1 = static_cast<unsigned>(arows) * S * 16u;
             c.stats.begin("ks32_inv_outer", 0, 8.0 * arows * S * n, st);
@@ -719,7 +882,8 @@ namespace sb
         {
             u64 *d64 = reinterpret_cast<u64 *>(base + out_bytes);
             cuda_check(cudaMemcpy(d64, h_rows, in_bytes, cudaMemcpyHostToDevice), "upload");
-            ksint_forward(c, Src{ d64, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), d32, nullptr);
+            ksint_forward(c, Src{ d64, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), d32,
+                          RowMap{ 0, 0, static_cast<int>(rows) }, nullptr);
         }
         cuda_check(cudaMemcpy(h_io, d32, out_bytes, cudaMemcpyDeviceToHost), "download");
     }
@@ -753,7 +917,7 @@ namespace sb
         for (int j = 0; j < 16; j++)
             d[(static_cast<size_t>(blockIdx.x) * 16 + j) * 256 + threadIdx.x] = a[j];
     }
-    __global__ void __launch_bounds__(128, 3) ks32_selftest_mac(uint32_t *d, int rounds)
+    __global__ void __launch_bounds__(128, 4) ks32_selftest_mac(uint32_t *d, int rounds)
     {
         uint32_t dv[4], kv[8];
         u64 acc[4][8];
@@ -814,9 +978,9 @@ namespace sb
             ops = static_cast<double>(sms) * 4 * 8 * rounds * 32.0;
             run([&] { ks32_selftest_bfly<1><<<sms * 4, 256, 0, st>>>(d, c.ksint.prm.p[0], rounds); });
             break;
-        case 2: // multiply-accumulates at the product kernel's launch shape (128 threads x 3 CTAs per SM): 32 per thread and round
-            ops = static_cast<double>(sms) * 3 * 4 * rounds * 32.0;
-            run([&] { ks32_selftest_mac<<<sms * 3, 128, 0, st>>>(d, rounds); });
+        case 2: // multiply-accumulates at the product kernel's launch shape (128 threads x 4 CTAs per SM): 32 per thread and round
+            ops = static_cast<double>(sms) * 4 * 4 * rounds * 32.0;
+            run([&] { ks32_selftest_mac<<<sms * 4, 128, 0, st>>>(d, rounds); });
             break;
         default: throw std::invalid_argument("unknown selftest");
         }

@@ -36,6 +36,7 @@ namespace sb
     struct KsInt
     {
         bool ready = false;
+        bool fuse_crt = false; // outer inverse stages inside the reconstruction kernel (env SB200_KS_FUSE_CRT)
         KsIntParams prm;
         uint2 *d_fwd_outer = nullptr, *d_inv_outer = nullptr; // [S][2^r]
         uint2 *d_fwd_local = nullptr, *d_inv_local = nullptr; // [S][2^r][4096]
@@ -45,11 +46,12 @@ namespace sb
     // per-ciphertext scratch of the integer path (bytes): digits' transforms, accumulated products, coefficient-form result
     struct KsIntScratch
     {
-        uint32_t *Dh = nullptr;  // [S][B*L][n]
-        uint32_t *Acc = nullptr; // [B][2][L+1][S][n]
+        uint32_t *Dh = nullptr;  // [S][L][Bpad][n]
+        uint32_t *Acc = nullptr; // [B][2][L+1][S][n], output prime index 0 = the special prime, i + 1 = data prime i
         u64 *R = nullptr;        // [B][2][L][n] (aliases Dh: the transformed digits are dead once the products exist)
     };
     size_t ksint_bytes_per_ct(const Context &c, size_t L);
+    size_t ksint_bytes_fixed(const Context &c, size_t L); // padding of the digit slab, once per chunk
     KsIntScratch ksint_carve(const Context &c, size_t L, size_t B, void *base);
 
     void ksint_init(Context &c);
