@@ -30,6 +30,9 @@ struct PrimeDev
     Tw inv_n_w;     // n^-1 * (last inverse-stage twiddle) mod q
     const Tw *fwd;  // fwd[m + i]: forward stage with m groups, group i  (psi powers, bit-reversed order)
     const Tw *inv;  // inv[m + i]: inverse stage with m groups, group i  (psi^-1 powers)
+    u64 mu;         // floor(2^(b+62) / q), b = bit length of q: one-word Barrett constant of barrett_wide
+    int sh;         // b - 2
+    int pad_;
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 q)
@@ -136,6 +139,27 @@ __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, u64 q, u64 ratio_lo, u
     carry += (s2 < s);
     u64 t = hi * ratio_hi + a_hi + b_hi + carry;
     return csub(lo - t * q, q);
+}
+
+// (hi:lo) mod q for values below 2^(b+62), b = bit length of q (a product of two residues, a sum of two such products, the CRT sums
+// of sb_ksint.cu): the quotient is estimated from the top 64 bits of the value with ONE high multiply -- floor(z / 2^(b-2)) * mu
+// / 2^64 is at most 2 below floor(z / q) -- instead of the three high + three low multiplies of the full 128-bit Barrett step.
+__device__ __forceinline__ u64 barrett_wide(u64 lo, u64 hi, const PrimeDev &P)
+{
+    unsigned w0, w1, w2, w3;
+    unpack64(lo, w0, w1);
+    unpack64(hi, w2, w3);
+    const bool up = P.sh >= 32;
+    const unsigned a0 = up ? w1 : w0, a1 = up ? w2 : w1, a2 = up ? w3 : w2;
+    const u64 zh = pack64(__funnelshift_r(a0, a1, P.sh), __funnelshift_r(a1, a2, P.sh)); // z >> sh, fits 64 bits
+    const u64 t = __umul64hi(zh, P.mu);
+    const u64 r = lo - t * P.q; // in [0, 3q)
+    return csub(csub(r, P.q2), P.q);
+}
+// a * b mod q, canonical, for a * b < 2^(b+62) (e.g. both operands below q)
+__device__ __forceinline__ u64 mulmod_wide(u64 a, u64 b, const PrimeDev &P)
+{
+    return barrett_wide(a * b, __umul64hi(a, b), P);
 }
 
 // a * b mod q, canonical, a and b arbitrary 64-bit with a*b < 2^128 trivially.

@@ -173,6 +173,14 @@ namespace sb
         d.inv_n_w = to_tw(pt.inv_n_w);
         d.fwd = f;
         d.inv = i;
+        {
+            int bits = 0;
+            while (bits < 64 && (pt.q >> bits))
+                bits++;
+            d.sh = bits - 2;
+            d.mu = static_cast<u64>((static_cast<unsigned __int128>(1) << (bits + 62)) / pt.q);
+            d.pad_ = 0;
+        }
         hp.push_back(d);
     }
 
@@ -395,11 +403,13 @@ namespace sb
     // ------------------------------------------------------------------------------------ CKKS multiply ----
     // (x0 y0, x0 y1 + x1 y0, x1 y1) per prime per coefficient; evaluator.cpp:634-662.
     // FUSED: poly 0,1 go to out (stride 2 polys) and poly 2 to c2 ([b][L][n]) -- the key-switch target.
+    // two consecutive coefficients per thread (16-byte accesses); residues are below their modulus (valid ciphertexts), so every
+    // 128-bit value reduced here is below 2 q^2 and barrett_wide applies
     template <bool FUSED>
     __global__ void __launch_bounds__(256) ckks_tensor_kernel(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *out, u64 *c2,
                                                                const PrimeDev *__restrict__ primes, int logn, int L, long long total)
     {
-        long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; // over batch*L*n
+        long long e = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; // over batch*L*n
         if (e >= total)
             return;
         const long long poly = static_cast<long long>(L) << logn;
@@ -407,23 +417,28 @@ namespace sb
         const int i = static_cast<int>(r >> logn);
         const PrimeDev P = primes[i];
         const u64 *pa = a + bidx * 2 * poly + r, *pb = b + bidx * 2 * poly + r;
-        u64 x0 = pa[0], x1 = pa[poly], y0 = pb[0], y1 = pb[poly];
-        u64 d0 = mulmod_barrett(x0, y0, P);
-        u64 lo = 0, hi = 0;
-        mac128(lo, hi, x0, y1);
-        mac128(lo, hi, x1, y0);
-        u64 d1 = barrett128(lo, hi, P.q, P.ratio_lo, P.ratio_hi);
-        u64 d2 = mulmod_barrett(x1, y1, P);
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
+        const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(pb), y1 = *reinterpret_cast<const ulonglong2 *>(pb + poly);
+        auto mid = [&](u64 p0, u64 p1, u64 q0, u64 q1) {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, p0, q1);
+            mac128(lo, hi, p1, q0);
+            return barrett_wide(lo, hi, P);
+        };
+        const ulonglong2 d0 = make_ulonglong2(mulmod_wide(x0.x, y0.x, P), mulmod_wide(x0.y, y0.y, P));
+        const ulonglong2 d1 = make_ulonglong2(mid(x0.x, x1.x, y0.x, y1.x), mid(x0.y, x1.y, y0.y, y1.y));
+        const ulonglong2 d2 = make_ulonglong2(mulmod_wide(x1.x, y1.x, P), mulmod_wide(x1.y, y1.y, P));
         if (FUSED)
         {
             u64 *po = out + bidx * 2 * poly + r;
-            po[0] = d0, po[poly] = d1;
-            c2[bidx * poly + r] = d2;
+            *reinterpret_cast<ulonglong2 *>(po) = d0, *reinterpret_cast<ulonglong2 *>(po + poly) = d1;
+            *reinterpret_cast<ulonglong2 *>(c2 + bidx * poly + r) = d2;
         }
         else
         {
             u64 *po = out + bidx * 3 * poly + r;
-            po[0] = d0, po[poly] = d1, po[2 * poly] = d2;
+            *reinterpret_cast<ulonglong2 *>(po) = d0, *reinterpret_cast<ulonglong2 *>(po + poly) = d1;
+            *reinterpret_cast<ulonglong2 *>(po + 2 * poly) = d2;
         }
     }
 
@@ -431,7 +446,7 @@ namespace sb
                               cudaStream_t st)
     {
         long long total = static_cast<long long>(batch) * L * c.n;
-        unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        unsigned blocks = static_cast<unsigned>((total / 2 + 255) / 256);
         c.stats.begin("ckks_tensor", 0, 7.0 * 8.0 * total, st); // 4 reads + 3 writes per coefficient
         if (fused)
             ckks_tensor_kernel<true><<<blocks, 256, 0, st>>>(a, b, out, c2, c.d_primes, c.logn, static_cast<int>(L), total);

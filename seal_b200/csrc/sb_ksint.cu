@@ -412,7 +412,7 @@ namespace sb
         u64 lo = (static_cast<u64>(w1) << 32) | w0, hi = w2;
         lo += ng;
         hi += (lo < ng);
-        return barrett128(lo, hi, Q.q, Q.ratio_lo, Q.ratio_hi);
+        return barrett_wide(lo, hi, Q); // < S 2^29 q + q
     }
     // MODE 0: CKKS (coefficient-form result to R), 1: BFV (result + base to out), 3: BGV (R)
     template <int MODE>
@@ -510,7 +510,7 @@ namespace sb
                 u64 lo = (static_cast<u64>(w1[e]) << 32) | w0[e], hi = w2[e];
                 lo += ng;
                 hi += (lo < ng);
-                val[e] = barrett128(lo, hi, Q.q, Q.ratio_lo, Q.ratio_hi);
+                val[e] = barrett_wide(lo, hi, Q); // < S 2^29 q + q
             }
         };
         const PrimeDev T = A.primes[k - 1];

@@ -165,6 +165,8 @@ def test_selftest_rates_and_profile_work_counters():
     ctx = S.Context(S.CKKS, n, mods)
     rk = ctx.load_key(key)
     out = torch.empty_like(a)
+    # (a) the 64-bit digit-transform path
+    ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, 0)
     ctx.profile(True)
     ctx.d_multiply_relinearize(a, b, rk, out, L, batch)
     torch.cuda.synchronize()
@@ -173,6 +175,22 @@ def test_selftest_rates_and_profile_work_counters():
     assert work["ks_local_mac"][4] == 0.5 * batch * L * L * n * 8 and work["ks_local_mac"][5] == 2.0 * batch * (L + 1) * L * n
     assert work["ks_digit_ntt:col"][4] == 0.5 * batch * L * L * n * (13 - 8)
     rates = [ctx.selftest_rate(kind) for kind in range(4)]
+    assert all(r > 1e9 for r in rates), rates
+    # (b) the integer path (default): 32-bit butterflies and multiply-accumulates are counted separately
+    ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, 1)
+    S5 = len(ctx.ksint_primes())
+    out64 = out.clone()
+    out.zero_()
+    ctx.profile(True)
+    ctx.d_multiply_relinearize(a, b, rk, out, L, batch)
+    torch.cuda.synchronize()
+    work = {r[0]: r for r in ctx.profile_read_work32()}
+    ctx.profile(False)
+    assert torch.equal(out, out64)
+    assert work["ks32_mac"][7] == 2.0 * batch * (L + 1) * L * S5 * n and work["ks32_mac"][5] == 0
+    assert work["ks32_fwd_local"][6] == 0.5 * batch * L * S5 * n * 12
+    assert work["ks32_inv_local"][6] == 0.5 * batch * 2 * (L + 1) * S5 * n * 12
+    rates = [ctx.selftest_rate(kind) for kind in (10, 11, 12)]
     assert all(r > 1e9 for r in rates), rates
     oc = O.Oracle(O.CKKS, n, mods)
     assert (to_np(out[batch - 1]) == oc.multiply_relin(L, to_np(a[batch - 1]), to_np(b[batch - 1]), key)).all()
