@@ -40,6 +40,8 @@ WORKLOADS = {
     "ckks_n8192_k4": dict(scheme=2, n=8192, bits=[54] * 4, batch=1024, e2e_batch=256, cpu_reps=200),
     # metric text "n=2^16, L=16 primes"
     "ckks_n65536_k16": dict(scheme=2, n=65536, bits=[55] * 16, batch=1024, e2e_batch=32, cpu_reps=2),
+    # diagnostic shape: the headline's prime count at a degree whose rows are 8x shorter (same bytes per step at 8x the batch)
+    "ckks_n8192_k32": dict(scheme=2, n=8192, bits=[55] * 32, batch=2048, e2e_batch=64, cpu_reps=8),
     "ckks_n32768_k16": dict(scheme=2, n=32768, bits=[55] * 15 + [56], batch=256, e2e_batch=64, cpu_reps=4),
     # tiny shape for the CPU contract test of the reference arm (tests/test_bench_contract.py); not a bench line
     "smoke": dict(scheme=2, n=4096, bits=[40, 40, 40], batch=8, e2e_batch=4, cpu_reps=4),

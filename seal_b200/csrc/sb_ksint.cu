@@ -147,7 +147,7 @@ namespace sb
     __device__ __forceinline__ int swz32(int idx) { return idx ^ (((idx >> 8) & 1) << 4) ^ (((idx >> 5) & 3) << 2); }
 
     // rows: row rr of this launch lives at data + ((rr * rstride + t) << logn); grid = (row groups, S * 2^r)
-    __global__ void __launch_bounds__(256, 4) ks32_fwd_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
+    __global__ void __launch_bounds__(256, 3) ks32_fwd_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
                                                               KsIntParams prm, const uint2 *__restrict__ tw_local)
     {
         extern __shared__ __align__(16) unsigned char ks32_smem[];
@@ -168,13 +168,29 @@ namespace sb
         const int blk = tid >> 4, l16 = tid & 15;
         const int p3 = ((16 * tid) ^ (((tid >> 4) & 1) << 4)), hx = (tid >> 1) & 3;
         bool first = true;
+        // the words of row r+1 are requested before the three passes of row r: their latency hides behind a whole row of arithmetic
+        uint32_t nxt[16];
+        if (row0 < row1)
+        {
+            const uint32_t *b0 = data + ((row0 * rstride + t * tstride) << prm.logn) + (g << 12);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                nxt[e] = b0[tid + 256 * e];
+        }
         for (int row = row0; row < row1; row++)
         {
             uint32_t *base = data + ((row * rstride + t * tstride) << prm.logn) + (g << 12);
             uint32_t a[16];
 #pragma unroll
             for (int e = 0; e < 16; e++)
-                a[e] = base[tid + 256 * e];
+                a[e] = nxt[e];
+            if (row + 1 < row1)
+            {
+                const uint32_t *bn = data + (((row + 1) * rstride + t * tstride) << prm.logn) + (g << 12);
+#pragma unroll
+                for (int e = 0; e < 16; e++)
+                    nxt[e] = bn[tid + 256 * e];
+            }
             if (first)
                 mbar_wait(bar, 0), first = false;
             radix_fwd<4>(a, [&](int lvl, int gg) { return tws[(1 << lvl) + gg]; }, P);
@@ -208,7 +224,7 @@ namespace sb
     }
 
     // inverse: inputs in [0, 2p), outputs in [0, 2p) (the scaling by n^-1 is folded into the CRT constants)
-    __global__ void __launch_bounds__(256, 4) ks32_inv_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
+    __global__ void __launch_bounds__(256, 3) ks32_inv_local(uint32_t *__restrict__ data, int rows, long long rstride, long long tstride,
                                                               KsIntParams prm, const uint2 *__restrict__ tw_local)
     {
         extern __shared__ __align__(16) unsigned char ks32_smem[];
@@ -229,15 +245,27 @@ namespace sb
         const int blk = tid >> 4, l16 = tid & 15;
         const int p3 = ((16 * tid) ^ (((tid >> 4) & 1) << 4)), hx = (tid >> 1) & 3;
         bool first = true;
+        uint4 nxt[4]; // row r+1 is requested before the three passes of row r
+        if (row0 < row1)
+        {
+            const uint32_t *b0 = data + ((row0 * rstride + t * tstride) << prm.logn) + (g << 12);
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                nxt[h] = *reinterpret_cast<const uint4 *>(b0 + 16 * tid + 4 * h);
+        }
         for (int row = row0; row < row1; row++)
         {
             uint32_t *base = data + ((row * rstride + t * tstride) << prm.logn) + (g << 12);
             uint32_t a[16];
 #pragma unroll
             for (int h = 0; h < 4; h++)
+                a[4 * h] = nxt[h].x, a[4 * h + 1] = nxt[h].y, a[4 * h + 2] = nxt[h].z, a[4 * h + 3] = nxt[h].w;
+            if (row + 1 < row1)
             {
-                const uint4 q = *reinterpret_cast<const uint4 *>(base + 16 * tid + 4 * h);
-                a[4 * h] = q.x, a[4 * h + 1] = q.y, a[4 * h + 2] = q.z, a[4 * h + 3] = q.w;
+                const uint32_t *bn = data + (((row + 1) * rstride + t * tstride) << prm.logn) + (g << 12);
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                    nxt[h] = *reinterpret_cast<const uint4 *>(bn + 16 * tid + 4 * h);
             }
             if (first)
                 mbar_wait(bar, 0), first = false;
@@ -290,15 +318,24 @@ namespace sb
     // Acc[b][c][I'][t][x] = sum_J Dh[t][J][b][x] * key32[t][J][c][I'][x]  mod p_t  (-> [0, 2p));  I' = 0: the special prime,
     // I' = i + 1: data prime i (so the L + 1 outputs of every level are consecutive key rows).
     // lane = coefficient; a warp owns a register tile of TB ciphertexts x TC outputs (one component c); the 4 warps of a CTA take 4
-    // output tiles over the same 32 coefficients and ciphertexts, so digit words are shared through L1, and consecutive CTAs (other
-    // ciphertexts, same key tile) share the key through L2.  LOGN is a template parameter: every load of the loop has an immediate
-    // offset from one of two pointers that advance once per digit.  No reduction inside the loop: L p^2 < 2^64.
-    constexpr int kMacTB = 4, kMacTC = 8;
+    // output tiles over the same 32 coefficients and ciphertexts, and consecutive CTAs (other ciphertexts, same key tile) share the
+    // key through L2.  Every operand word is a 128-byte line of its own row (rows are 4 n bytes apart): the loads are latency-bound
+    // (ncu: long-scoreboard stalls), so the operands of the next kStages - 1 digits are kept in flight with cp.async into a
+    // per-thread ring in shared memory -- each lane copies and later reads only its own words, no barrier is involved -- and the
+    // products read them from there.  LOGN is a template parameter: every copy has an immediate offset from one of two pointers that
+    // advance once per digit.  No reduction inside the loop: L p^2 < 2^64.
+    constexpr int kMacTB = 4, kMacTC = 8, kMacStages = 8;
+    constexpr int kMacSmem = kMacStages * (kMacTB + kMacTC) * 128 * 4;
+    __device__ __forceinline__ void cp_async4(uint32_t *dst_smem, const uint32_t *src)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+    }
     template <int LOGN>
-    __global__ void __launch_bounds__(128, 4) ks32_mac(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
+    __global__ void __launch_bounds__(128, 3) ks32_mac(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
                                                         KsIntParams prm, int L, int k, int digits, int B, int nbt)
     {
-        constexpr int TB = kMacTB, TC = kMacTC;
+        constexpr int TB = kMacTB, TC = kMacTC, D = kMacStages, W = TB + TC;
+        extern __shared__ __align__(16) uint32_t ks_ring[]; // [stage][word W][thread 128]
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         // CTA order: ciphertext tile fastest (same key tile: L2), then the output-tile group (same digit words: L2), then coefficients
         const int ntile = (L + TC) / TC; // tiles per component: ceil((L + 1) / TC)
@@ -312,21 +349,38 @@ namespace sb
         const uint32_t *dp = Dh + ((static_cast<size_t>(t) * L * Bpad + b0) << LOGN) + x;
         const uint32_t *kp = key32 + (((static_cast<size_t>(t) * digits * 2 + c) * k + i0) << LOGN) + x;
         const size_t dstep = static_cast<size_t>(Bpad) << LOGN, kstep = static_cast<size_t>(2 * k) << LOGN;
+        uint32_t *ring = ks_ring + threadIdx.x;
         u64 acc[TB][TC];
 #pragma unroll
         for (int i = 0; i < TB; i++)
 #pragma unroll
             for (int r = 0; r < TC; r++)
                 acc[i][r] = 0;
-        // two operand sets in flight: the loads of digit J+1 are issued before the products of digit J
+        int Jissue = 0;
+        auto issue = [&]() { // operands of digit Jissue -> stage Jissue % D (an empty group once the digits are exhausted)
+            if (Jissue < L)
+            {
+                uint32_t *dst = ring + (Jissue & (D - 1)) * (W * 128);
+#pragma unroll
+                for (int i = 0; i < TB; i++)
+                    cp_async4(dst + i * 128, dp + (i << LOGN));
+#pragma unroll
+                for (int r = 0; r < TC; r++)
+                    cp_async4(dst + (TB + r) * 128, kp + (r << LOGN));
+                dp += dstep, kp += kstep;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            Jissue++;
+        };
         uint32_t dA[TB], kA[TC], dB[TB], kB[TC];
-        auto load = [&](uint32_t(&d_)[TB], uint32_t(&k_)[TC]) {
+        auto fetch = [&](uint32_t(&d_)[TB], uint32_t(&k_)[TC], int J) {
+            const uint32_t *src = ring + (J & (D - 1)) * (W * 128);
 #pragma unroll
             for (int i = 0; i < TB; i++)
-                d_[i] = dp[i << LOGN];
+                d_[i] = src[i * 128];
 #pragma unroll
             for (int r = 0; r < TC; r++)
-                k_[r] = __ldg(kp + (r << LOGN));
+                k_[r] = src[(TB + r) * 128];
         };
         auto macs = [&](const uint32_t(&d_)[TB], const uint32_t(&k_)[TC]) {
 #pragma unroll
@@ -335,21 +389,28 @@ namespace sb
                 for (int r = 0; r < TC; r++)
                     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d_[i]), "r"(k_[r]));
         };
-        load(dA, kA);
+#pragma unroll
+        for (int j = 0; j < D - 1; j++)
+            issue();
+        // invariant at the top of an iteration: groups 0 .. J + D - 2 committed; "wait_group D - 2" leaves digit J complete
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+        fetch(dA, kA, 0);
         int J = 0;
 #pragma unroll 1
         for (; J + 2 <= L; J += 2)
         {
-            dp += dstep, kp += kstep;
-            load(dB, kB);
+            issue();
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+            fetch(dB, kB, J + 1);
             macs(dA, kA);
-            if (J + 2 < L)
-                dp += dstep, kp += kstep;
-            load(dA, kA);
+            issue();
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+            fetch(dA, kA, J + 2); // digit L (one past the end) reads a stale stage; its products are never formed
             macs(dB, kB);
         }
         if (J < L)
             macs(dA, kA);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         const P32 P = make_p32(prm.p[t]);
         const uint2 red = prm.red[t];
         const uint32_t mu = prm.mu[t];
@@ -366,6 +427,138 @@ namespace sb
             }
         }
     }
+    // The same product with the key tile in shared memory: a CTA (16 warps = 4 ciphertext tiles x 4 output tiles) owns 32
+    // coefficients x 32 outputs of one auxiliary prime, copies the L x 32 key rows of that tile (L x 4 KB) into shared memory once and
+    // then walks over ALL ciphertexts of the chunk, 16 per iteration.  Key words come from shared memory (conflict-free: lanes =
+    // consecutive words); only the digit words (4 per digit and thread) travel through the cp.async ring, so the number of global
+    // requests in flight per multiply-accumulate is a third of the register-tile kernel's -- that kernel is bound by request
+    // latency x requests in flight (ncu: the first product after each operand fetch holds half of the stall samples).
+    // grid = (output groups * n/32, 1, S); dynamic shared memory L * 4096 + ring bytes.
+    constexpr int kMacRingBytes = kMacStages * kMacTB * 512 * 4;
+    template <int LOGN>
+    __global__ void __launch_bounds__(512, 1) ks32_mac_tile(const uint32_t *__restrict__ Dh, const uint32_t *__restrict__ key32, uint32_t *__restrict__ Acc,
+                                                             KsIntParams prm, int L, int k, int digits, int B, int Bpad)
+    {
+        constexpr int TB = kMacTB, TC = kMacTC, D = kMacStages;
+        extern __shared__ __align__(16) uint32_t ks_tile[]; // [J][32 rows][32 lanes] | ring [stage][TB][512 threads]
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int ntile = (L + TC) / TC, ny = (2 * ntile + 3) / 4;
+        const int yg = blockIdx.x % ny, xt = blockIdx.x / ny, t = blockIdx.z;
+        const int x = (xt << 5) + lane;
+        const uint32_t *kbase = key32 + ((static_cast<size_t>(t) * digits * 2 * k) << LOGN) + x;
+        const size_t kstep = static_cast<size_t>(2 * k) << LOGN;
+        // tile rows: row tr (< 32) = output r = tr % 8 of task yg * 4 + tr / 8; unused tasks of a ragged last group re-read valid rows
+        for (int rho = warp; rho < L * 32; rho += 16)
+        {
+            const int J = rho >> 5, tr = rho & 31;
+            const int task = min(yg * 4 + (tr >> 3), 2 * ntile - 1), c = task / ntile, i0 = (task - c * ntile) * TC;
+            ks_tile[(rho << 5) + lane] = __ldg(kbase + J * kstep + (static_cast<size_t>(c * k + i0 + (tr & 7)) << LOGN));
+        }
+        __syncthreads();
+        const int bsub = warp & 3, icsub = warp >> 2;
+        const int task = yg * 4 + icsub;
+        if (task >= 2 * ntile)
+            return;
+        const int c = task / ntile, i0 = (task - c * ntile) * TC;
+        const uint32_t *ktile = ks_tile + ((icsub * TC) << 5) + lane;
+        uint32_t *ring = ks_tile + L * 1024 + threadIdx.x;
+        const P32 P = make_p32(prm.p[t]);
+        const uint2 red = prm.red[t];
+        const uint32_t mu = prm.mu[t];
+        const size_t dstep = static_cast<size_t>(Bpad) << LOGN;
+        for (int b0 = bsub * TB; b0 < B; b0 += 4 * TB)
+        {
+            const uint32_t *dp = Dh + ((static_cast<size_t>(t) * L * Bpad + b0) << LOGN) + x;
+            u64 acc[TB][TC];
+#pragma unroll
+            for (int i = 0; i < TB; i++)
+#pragma unroll
+                for (int r = 0; r < TC; r++)
+                    acc[i][r] = 0;
+            int Jissue = 0;
+            auto issue = [&]() { // digit words of digit Jissue -> stage Jissue % D (an empty group once the digits are exhausted)
+                if (Jissue < L)
+                {
+                    uint32_t *dst = ring + (Jissue & (D - 1)) * (TB * 512);
+#pragma unroll
+                    for (int i = 0; i < TB; i++)
+                        cp_async4(dst + i * 512, dp + (i << LOGN));
+                    dp += dstep;
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                Jissue++;
+            };
+            uint32_t dA[TB], kA[TC], dB[TB], kB[TC];
+            auto fetch = [&](uint32_t(&d_)[TB], uint32_t(&k_)[TC], int J) {
+                const uint32_t *src = ring + (J & (D - 1)) * (TB * 512);
+                const uint32_t *kt = ktile + (min(J, L - 1) << 10);
+#pragma unroll
+                for (int i = 0; i < TB; i++)
+                    d_[i] = src[i * 512];
+#pragma unroll
+                for (int r = 0; r < TC; r++)
+                    k_[r] = kt[r << 5];
+            };
+            auto macs = [&](const uint32_t(&d_)[TB], const uint32_t(&k_)[TC]) {
+#pragma unroll
+                for (int i = 0; i < TB; i++)
+#pragma unroll
+                    for (int r = 0; r < TC; r++)
+                        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d_[i]), "r"(k_[r]));
+            };
+#pragma unroll
+            for (int j = 0; j < D - 1; j++)
+                issue();
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+            fetch(dA, kA, 0);
+            int J = 0;
+#pragma unroll 1
+            for (; J + 2 <= L; J += 2)
+            {
+                issue();
+                asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+                fetch(dB, kB, J + 1);
+                macs(dA, kA);
+                issue();
+                asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+                fetch(dA, kA, J + 2); // one past the end reads a stale stage; its products are never formed
+                macs(dB, kB);
+            }
+            if (J < L)
+                macs(dA, kA);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < TB; i++)
+            {
+                if (b0 + i < B)
+                {
+                    uint32_t *o = Acc + ((((static_cast<size_t>(b0 + i) * 2 + c) * (L + 1) + i0) * prm.S + t) << LOGN) + x;
+#pragma unroll
+                    for (int r = 0; r < TC; r++)
+                        if (i0 + r <= L)
+                            o[(static_cast<size_t>(r) * prm.S) << LOGN] = minsub(reduce64(acc[i][r], red, mu, P), P.p2);
+                }
+            }
+        }
+    }
+    template <int LOGN>
+    static void launch_mac(const KsIntScratch &s, const uint32_t *key32, const KsInt &d, int L, int k, int digits, int B, int nbt, int n,
+                           cudaStream_t st)
+    {
+        const int ntile = (L + kMacTC) / kMacTC, ny = (2 * ntile + 3) / 4;
+        const size_t tile_smem = static_cast<size_t>(L) * 4096 + kMacRingBytes;
+        // the tile kernel walks over all ciphertexts with one CTA per (coefficient tile, output group): worth it from a few tiles on
+        if (d.mac_tile && tile_smem <= 227 * 1024 && B >= 16)
+        {
+            cuda_check(cudaFuncSetAttribute(ks32_mac_tile<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)), "smem attr");
+            dim3 grid(static_cast<unsigned>(ny) * static_cast<unsigned>(n / 32), 1, static_cast<unsigned>(d.prm.S));
+            ks32_mac_tile<LOGN><<<grid, 512, tile_smem, st>>>(s.Dh, key32, s.Acc, d.prm, L, k, digits, B, nbt * kMacTB);
+            return;
+        }
+        cuda_check(cudaFuncSetAttribute(ks32_mac<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMacSmem), "smem attr");
+        dim3 grid(static_cast<unsigned>(nbt) * static_cast<unsigned>(ny) * static_cast<unsigned>(n / 32), 1, static_cast<unsigned>(d.prm.S));
+        ks32_mac<LOGN><<<grid, 128, kMacSmem, st>>>(s.Dh, key32, s.Acc, d.prm, L, k, digits, B, nbt);
+    }
 
     // -------------------------------------------------------------- (4) reconstruction + mod-down, per coefficient ----
     struct CrtArgs
@@ -374,6 +567,7 @@ namespace sb
         const u64 *punct, *neg; // [k][S]
         const PrimeDev *primes;
         const Tw *inv_top;       // q_sp^-1 mod q_i
+        const u64 *half_mod;     // floor(q_sp / 2) mod q_i
         const Tw *qtop_mod;      // BGV: q_sp mod q_i
         u64 t = 0, t_ratio = 0;  // BGV plain modulus
         Tw inv_top_mod_t = { 0, 0 };
@@ -384,187 +578,172 @@ namespace sb
         int L, k;
         long long total;         // B * 2 * n
     };
-    // exact value of (sum_J d_J * k_JI)[x] mod q, from its residues modulo the auxiliary primes
-    __device__ __forceinline__ u64 crt_reconstruct(const uint32_t *__restrict__ a, const KsIntParams &prm, const u64 *__restrict__ punct,
-                                                   const u64 *__restrict__ neg, const PrimeDev &Q)
-    {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        float f = 0.0f;
-        for (int t = 0; t < prm.S; t++)
-        {
-            const P32 P = make_p32(prm.p[t]);
-            // y = (x n^-1 + H) (P/p_t)^-1 mod p_t, canonical
-            uint32_t y = mul32_lazy(a[static_cast<size_t>(t) << prm.logn], prm.c1[t], P.np) + prm.c2[t]; // < 3p
-            y = minsub(y, P.p2);
-            y = minsub(y, P.p);
-            f += static_cast<float>(y) * prm.inv_p[t];
-            const u64 C = __ldg(punct + t);
-            const u64 p0 = static_cast<u64>(y) * static_cast<uint32_t>(C), p1 = static_cast<u64>(y) * static_cast<uint32_t>(C >> 32);
-            asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t"
-                "add.cc.u32 %1, %1, %5;\n\taddc.u32 %2, %2, %6;"
-                : "+r"(w0), "+r"(w1), "+r"(w2)
-                : "r"(static_cast<uint32_t>(p0)), "r"(static_cast<uint32_t>(p0 >> 32)), "r"(static_cast<uint32_t>(p1)),
-                  "r"(static_cast<uint32_t>(p1 >> 32)));
-        }
-        // the value is sum y_t (P/p_t) - alpha P - H with alpha = floor(sum y_t / p_t); (value + H) / P lies in (1/4, 3/4)
-        const int alpha = static_cast<int>(f);
-        const u64 ng = __ldg(neg + alpha);
-        u64 lo = (static_cast<u64>(w1) << 32) | w0, hi = w2;
-        lo += ng;
-        hi += (lo < ng);
-        return barrett_wide(lo, hi, Q); // < S 2^29 q + q
-    }
+    // One kernel, two shapes.  FUSE = false: a thread reconstructs one coefficient of one (ciphertext, component) for every output
+    // prime.  FUSE = true: a thread owns the 2^(LOGN-12) coefficients j + 4096 e and first runs the outer inverse stages on them (they
+    // are exactly the words those butterflies couple), so the outer pass of the inverse transforms never goes through memory.
+    // Per output prime and coefficient: y_t = x_t c1_t + c2_t mod p_t (canonical), three 64-bit sums sum y_t C_t.lo, sum y_t C_t.hi,
+    // sum y_t floor(2^60 / p_t) (the last one's top bits are alpha: the true fraction lies in (1/4, 3/4), the estimate is 2^-28 below
+    // it), one barrett_wide of sum y_t (P/p_t) + (-(alpha P) - H) mod q, then the mod-down (evaluator.cpp:2762-2864) with lazy operands:
+    // (a_i - ((u mod q_i) - half)) q_sp^-1 is formed from a_i + (2 q_i + half mod q_i) - u without reducing u when q_sp < 2 q_i.
+    // The instruction count per reconstruction (it is what bounds this kernel: ncu, issue slots 75 % busy in the first version) is
+    // ~2.5x lower than with a 96-bit carry chain, a 128-bit Barrett step and canonical intermediates.
     // MODE 0: CKKS (coefficient-form result to R), 1: BFV (result + base to out), 3: BGV (R)
-    template <int MODE>
-    __global__ void __launch_bounds__(256) ks32_crt_kernel(CrtArgs A, KsIntParams prm)
+    template <int MODE, int LOGN, bool FUSE>
+    __global__ void __launch_bounds__(FUSE ? 128 : 256) ks32_crt_kernel(CrtArgs A, KsIntParams prm, const uint2 *__restrict__ tw_outer)
     {
-        const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-        if (e >= A.total)
-            return;
-        const int logn = prm.logn, S = prm.S, L = A.L, k = A.k;
-        const int x = static_cast<int>(e & ((1 << logn) - 1)), bc = static_cast<int>(e >> logn), b = bc >> 1, c = bc & 1;
-        const uint32_t *arow = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << logn) + x;
-        const PrimeDev T = A.primes[k - 1];
-        const u64 a_top = crt_reconstruct(arow, prm, A.punct + (k - 1) * S, A.neg + (k - 1) * S, T); // I' = 0: the special prime
-        u64 U, K = 0;
-        if (MODE == 3)
-        {
-            // evaluator.cpp:2770-2779, rns.cpp:1202-1213: k = -u q_top^-1 mod t
-            U = a_top;
-            const u64 r = barrett64(U, A.t, A.t_ratio);
-            K = mul_shoup(r ? A.t - r : 0, A.inv_top_mod_t, A.t);
-        }
+        constexpr int R = LOGN - 12, E = FUSE ? (1 << R) : 1;
+        const int S = prm.S, L = A.L, k = A.k;
+        int bc, j;
+        if (FUSE)
+            bc = blockIdx.x >> 5, j = ((blockIdx.x & 31) << 7) + threadIdx.x;
         else
-            U = csub(a_top + (T.q >> 1), T.q); // evaluator.cpp:2809-2817
-        for (int i = 0; i < L; i++)
         {
-            const PrimeDev Q = A.primes[i];
-            const u64 a = crt_reconstruct(arow + ((static_cast<size_t>(i + 1) * S) << logn), prm, A.punct + i * S, A.neg + i * S, Q);
-            u64 u = (T.q > Q.q) ? barrett64(U, Q.q, Q.ratio_hi) : csub(U, Q.q), d;
-            if (MODE == 3)
-            {
-                const u64 kk = (A.t > Q.q) ? barrett64(K, Q.q, Q.ratio_hi) : K;
-                d = csub(u + mul_shoup(kk, A.qtop_mod[i], Q.q), Q.q); // rns.cpp:1216-1235
-            }
-            else
-                d = csub(u + Q.q - barrett64(T.q >> 1, Q.q, Q.ratio_hi), Q.q); // evaluator.cpp:2819-2864
-            const u64 r = mul_shoup(a + Q.q - d, A.inv_top[i], Q.q);
-            if (MODE == 1)
-                A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << logn) + x] = csub(r + A.base.get(b, c, i, x, Q.q), Q.q);
-            else
-                A.R[((static_cast<size_t>(bc) * L + i) << logn) + x] = r;
+            const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+            if (e >= A.total)
+                return;
+            bc = static_cast<int>(e >> LOGN), j = static_cast<int>(e & ((1 << LOGN) - 1));
         }
-    }
-
-    // (3b)+(4) fused: the thread that reconstructs coefficients j + 4096 e (e < 2^R) first runs the R outer inverse stages on them
-    // (they are exactly the 2^R words those butterflies couple), so the inverse transforms' outer pass never goes through memory.
-    // grid.x = B * 2 * 32 CTAs of 128 threads.
-    template <int MODE, int R>
-    __global__ void __launch_bounds__(128) ks32_crt_fused(CrtArgs A, KsIntParams prm, const uint2 *__restrict__ tw_outer)
-    {
-        constexpr int E = 1 << R;
-        const int logn = prm.logn, S = prm.S, L = A.L, k = A.k;
-        const int bc = blockIdx.x >> 5, j = ((blockIdx.x & 31) << 7) + threadIdx.x, b = bc >> 1, c = bc & 1;
-        const uint32_t *arow = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << logn) + j;
-        auto reconstruct = [&](int Ip, int ki, const PrimeDev &Q, u64(&val)[E]) {
-            uint32_t w0[E], w1[E], w2[E];
-            float f[E];
+        const int b = bc >> 1, c = bc & 1;
+        const uint32_t *src = A.Acc + ((static_cast<size_t>(bc) * (L + 1) * S) << LOGN) + j; // output prime I' = 0; += S << LOGN per prime
+        // the residues of the NEXT output prime are requested before the arithmetic of the current one (ncu of the first version: the
+        // first multiply after each load held the stall samples); the fused shape has 2^R words per residue and loads them in place
+        constexpr int PF = FUSE ? 1 : kKsMaxS;
+        uint32_t nxt[PF];
+        auto prefetch = [&]() {
+            if (!FUSE)
+            {
+#pragma unroll
+                for (int t = 0; t < kKsMaxS; t++)
+                    if (t < S)
+                        nxt[t] = src[static_cast<size_t>(t) << LOGN];
+            }
+        };
+        prefetch();
+        auto reconstruct = [&](int ki, const PrimeDev &Q, u64(&val)[E], bool more) {
+            u64 a0[E], a1[E], f[E];
 #pragma unroll
             for (int e = 0; e < E; e++)
-                w0[e] = w1[e] = w2[e] = 0, f[e] = 0.0f;
+                a0[e] = a1[e] = f[e] = 0;
             const u64 *punct = A.punct + ki * S;
-            for (int t = 0; t < S; t++)
+            uint32_t cur[PF];
+            if (!FUSE)
             {
-                const P32 P = make_p32(prm.p[t]);
-                const uint32_t *src = arow + ((static_cast<size_t>(Ip) * S + t) << logn);
-                uint32_t a[E];
 #pragma unroll
-                for (int e = 0; e < E; e++)
-                    a[e] = src[e << 12];
-                const uint2 *tw = tw_outer + (t << R);
-                radix_inv<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
+                for (int t = 0; t < kKsMaxS; t++)
+                    cur[t] = nxt[t];
+                src += static_cast<size_t>(S) << LOGN;
+                if (more)
+                    prefetch();
+            }
+            // fully unrolled with an early exit: the per-prime constants become constant-bank operands of the instructions
+#pragma unroll
+            for (int t = 0; t < kKsMaxS; t++)
+            {
+                if (t >= S)
+                    break;
+                const P32 P = make_p32(prm.p[t]);
+                uint32_t a[E];
+                if (FUSE)
+                {
+                    const uint32_t *st = src + (static_cast<size_t>(t) << LOGN);
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        a[e] = st[e << 12];
+                    const uint2 *tw = tw_outer + (t << R);
+                    radix_inv<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
+                }
+                else
+                    a[0] = cur[t];
                 const uint2 c1 = prm.c1[t];
-                const uint32_t c2 = prm.c2[t];
-                const float ip = prm.inv_p[t];
+                const uint32_t c2 = prm.c2[t], ip = prm.inv60[t];
                 const u64 C = __ldg(punct + t);
                 const uint32_t C0 = static_cast<uint32_t>(C), C1 = static_cast<uint32_t>(C >> 32);
 #pragma unroll
                 for (int e = 0; e < E; e++)
                 {
-                    uint32_t y = mul32_lazy(a[e], c1, P.np) + c2; // < 3p
-                    y = minsub(minsub(y, P.p2), P.p);
-                    f[e] += static_cast<float>(y) * ip;
-                    const u64 p0 = static_cast<u64>(y) * C0, p1 = static_cast<u64>(y) * C1;
-                    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t"
-                        "add.cc.u32 %1, %1, %5;\n\taddc.u32 %2, %2, %6;"
-                        : "+r"(w0[e]), "+r"(w1[e]), "+r"(w2[e])
-                        : "r"(static_cast<uint32_t>(p0)), "r"(static_cast<uint32_t>(p0 >> 32)), "r"(static_cast<uint32_t>(p1)),
-                          "r"(static_cast<uint32_t>(p1 >> 32)));
+                    // (x n^-1 + H) (P/p_t)^-1 mod p_t, canonical: the three sums below then stay inside 64 bits (S 2^29 2^32 < 2^64)
+                    const uint32_t y = minsub(minsub(a[e] * c1.x + c2 + __umulhi(a[e], c1.y) * P.np, P.p2), P.p);
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0[e]) : "r"(y), "r"(C0));
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1[e]) : "r"(y), "r"(C1));
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(f[e]) : "r"(y), "r"(ip));
                 }
             }
             const u64 *neg = A.neg + ki * S;
 #pragma unroll
             for (int e = 0; e < E; e++)
             {
-                const u64 ng = __ldg(neg + static_cast<int>(f[e]));
-                u64 lo = (static_cast<u64>(w1[e]) << 32) | w0[e], hi = w2[e];
+                const u64 ng = __ldg(neg + static_cast<int>(f[e] >> 60));
+                u64 lo = a0[e] + (a1[e] << 32), hi = (a1[e] >> 32) + (lo < a0[e]);
                 lo += ng;
                 hi += (lo < ng);
                 val[e] = barrett_wide(lo, hi, Q); // < S 2^29 q + q
             }
+            if (FUSE)
+                src += static_cast<size_t>(S) << LOGN;
         };
         const PrimeDev T = A.primes[k - 1];
         u64 U[E], K[MODE == 3 ? E : 1];
-        reconstruct(0, k - 1, T, U);
+        reconstruct(k - 1, T, U, L > 0);
 #pragma unroll
         for (int e = 0; e < E; e++)
         {
             if (MODE == 3)
             {
+                // evaluator.cpp:2770-2779, rns.cpp:1202-1213: k = -u q_top^-1 mod t
                 const u64 r = barrett64(U[e], A.t, A.t_ratio);
                 K[e] = mul_shoup(r ? A.t - r : 0, A.inv_top_mod_t, A.t);
             }
             else
-                U[e] = csub(U[e] + (T.q >> 1), T.q);
+                U[e] = csub(U[e] + (T.q >> 1), T.q); // evaluator.cpp:2809-2817
         }
         for (int i = 0; i < L; i++)
         {
             const PrimeDev Q = A.primes[i];
             u64 a[E];
-            reconstruct(i + 1, i, Q, a);
+            reconstruct(i, Q, a, i + 1 < L);
             const Tw inv = A.inv_top[i];
-            const u64 half_mod = barrett64(T.q >> 1, Q.q, Q.ratio_hi);
+            const bool same_size = T.q < Q.q2; // u < q_top < 2 q_i: no reduction of u needed
+            const u64 half_mod = __ldg(A.half_mod + i);
 #pragma unroll
             for (int e = 0; e < E; e++)
             {
-                const u64 u = (T.q > Q.q) ? barrett64(U[e], Q.q, Q.ratio_hi) : csub(U[e], Q.q);
-                u64 d;
+                u64 x; // a_i - delta_i + (multiple of q_i), in (0, 4 q_i)
+                const u64 u = same_size ? U[e] : barrett64(U[e], Q.q, Q.ratio_hi);
                 if (MODE == 3)
                 {
                     const u64 kk = (A.t > Q.q) ? barrett64(K[e], Q.q, Q.ratio_hi) : K[e];
-                    d = csub(u + mul_shoup(kk, A.qtop_mod[i], Q.q), Q.q);
+                    x = a[e] + (Q.q2 + Q.q) - u - mul_shoup(kk, A.qtop_mod[i], Q.q); // rns.cpp:1216-1235
                 }
                 else
-                    d = csub(u + Q.q - half_mod, Q.q);
-                const u64 r = mul_shoup(a[e] + Q.q - d, inv, Q.q);
-                const int x = j + (e << 12);
+                    x = a[e] + (Q.q2 + half_mod) - u; // evaluator.cpp:2819-2864
+                const u64 r = mul_shoup(x, inv, Q.q);
+                const int xi = j + (e << 12);
                 if (MODE == 1)
-                    A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << logn) + x] = csub(r + A.base.get(b, c, i, x, Q.q), Q.q);
+                    A.out[b * A.o_bs + c * A.o_ps + (static_cast<long long>(i) << LOGN) + xi] = csub(r + A.base.get(b, c, i, xi, Q.q), Q.q);
                 else
-                    A.R[((static_cast<size_t>(bc) * L + i) << logn) + x] = r;
+                    A.R[((static_cast<size_t>(bc) * L + i) << LOGN) + xi] = r;
             }
         }
     }
-    template <int MODE>
-    static void launch_crt_fused(const CrtArgs &A, const KsInt &d, unsigned grid, cudaStream_t st)
+    template <int MODE, int LOGN>
+    static void launch_crt_logn(const CrtArgs &A, const KsInt &d, bool fuse, size_t B, cudaStream_t st)
     {
-        switch (d.prm.r)
+        if (fuse)
+            ks32_crt_kernel<MODE, LOGN, true><<<static_cast<unsigned>(B * 2 * 32), 128, 0, st>>>(A, d.prm, d.d_inv_outer);
+        else
+            ks32_crt_kernel<MODE, LOGN, false><<<static_cast<unsigned>((A.total + 255) / 256), 256, 0, st>>>(A, d.prm, d.d_inv_outer);
+    }
+    template <int MODE>
+    static void launch_crt(const CrtArgs &A, const KsInt &d, bool fuse, size_t B, int logn, cudaStream_t st)
+    {
+        switch (logn)
         {
-        case 0: ks32_crt_fused<MODE, 0><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
-        case 1: ks32_crt_fused<MODE, 1><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
-        case 2: ks32_crt_fused<MODE, 2><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
-        case 3: ks32_crt_fused<MODE, 3><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
-        case 4: ks32_crt_fused<MODE, 4><<<grid, 128, 0, st>>>(A, d.prm, d.d_inv_outer); break;
+        case 12: launch_crt_logn<MODE, 12>(A, d, false, B, st); break; // no outer stages at n = 4096
+        case 13: launch_crt_logn<MODE, 13>(A, d, fuse, B, st); break;
+        case 14: launch_crt_logn<MODE, 14>(A, d, fuse, B, st); break;
+        case 15: launch_crt_logn<MODE, 15>(A, d, fuse, B, st); break;
+        case 16: launch_crt_logn<MODE, 16>(A, d, fuse, B, st); break;
+        case 17: launch_crt_logn<MODE, 17>(A, d, false, B, st); break; // 32 coefficients per thread do not fit the register file
         default: throw std::logic_error("unsupported transform size");
         }
     }
@@ -645,6 +824,7 @@ namespace sb
         for (int t = 0; t < h.S; t++)
         {
             d.prm.p[t] = h.p[t], d.prm.mu[t] = h.mu[t], d.prm.c2[t] = h.c2[t], d.prm.inv_p[t] = h.inv_p[t];
+            d.prm.inv60[t] = static_cast<uint32_t>((u64(1) << 60) / h.p[t]);
             d.prm.red[t] = make_uint2(h.red[2 * t], h.red[2 * t + 1]);
             d.prm.c1[t] = make_uint2(h.c1[2 * t], h.c1[2 * t + 1]);
         }
@@ -654,16 +834,24 @@ namespace sb
         d.d_inv_local = reinterpret_cast<uint2 *>(upload(h.inv_local, c.table_bytes));
         d.d_punct = upload(h.punct_mod_q, c.table_bytes);
         d.d_neg = upload(h.neg_mod_q, c.table_bytes);
+        {
+            std::vector<u64> hm(c.k);
+            for (size_t i = 0; i < c.k; i++)
+                hm[i] = (c.q[c.k - 1] >> 1) % c.q[i];
+            d.d_half_mod = upload(hm, c.table_bytes);
+        }
         cuda_check(cudaFuncSetAttribute(ks32_fwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
         cuda_check(cudaFuncSetAttribute(ks32_inv_local, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsLocalSmem), "smem attr");
         if (const char *e = std::getenv("SB200_KS_FUSE_CRT"))
             d.fuse_crt = std::atoi(e) != 0;
+        if (const char *e = std::getenv("SB200_KS_MAC_TILE"))
+            d.mac_tile = std::atoi(e) != 0;
         d.ready = true;
     }
     void ksint_free(Context &c)
     {
         KsInt &d = c.ksint;
-        cudaFree(d.d_fwd_outer), cudaFree(d.d_inv_outer), cudaFree(d.d_fwd_local), cudaFree(d.d_inv_local), cudaFree(d.d_punct), cudaFree(d.d_neg);
+        cudaFree(d.d_fwd_outer), cudaFree(d.d_inv_outer), cudaFree(d.d_fwd_local), cudaFree(d.d_inv_local), cudaFree(d.d_punct), cudaFree(d.d_neg), cudaFree(d.d_half_mod);
         d = KsInt{};
     }
 
@@ -768,27 +956,25 @@ namespace sb
         ksint_forward(c, dsrc, Li, rows, s.Dh, RowMap{ 1, Bpad, Li * Bpad }, st);
         // (2) products with the key, summed over the digits
         {
-            const int ntile = (Li + kMacTC) / kMacTC;
-            dim3 grid(static_cast<unsigned>(nbt) * static_cast<unsigned>((2 * ntile + 3) / 4) * static_cast<unsigned>(c.n / 32), 1, static_cast<unsigned>(S));
             // one pass over the key + the transformed digits in, the sums out
             c.stats.begin("ks32_mac", 0, 4.0 * n * S * (static_cast<double>(Li) * 2 * (Li + 1) + rows + arows), st);
             c.stats.work32(0, static_cast<double>(arows) * Li * S * n);
-            const int dg = static_cast<int>(key.digits);
+            const int dg = static_cast<int>(key.digits), ni = static_cast<int>(c.n);
             switch (c.logn)
             {
-            case 12: ks32_mac<12><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
-            case 13: ks32_mac<13><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
-            case 14: ks32_mac<14><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
-            case 15: ks32_mac<15><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
-            case 16: ks32_mac<16><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
-            case 17: ks32_mac<17><<<grid, 128, 0, st>>>(s.Dh, key.d_key32, s.Acc, d.prm, Li, ki, dg, Bi, nbt); break;
+            case 12: launch_mac<12>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
+            case 13: launch_mac<13>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
+            case 14: launch_mac<14>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
+            case 15: launch_mac<15>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
+            case 16: launch_mac<16>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
+            case 17: launch_mac<17>(s, key.d_key32, d, Li, ki, dg, Bi, nbt, ni, st); break;
             default: throw std::logic_error("unsupported transform size");
             }
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks32_mac");
         }
         // (3) inverse transforms of the sums; the outer stages ride in the reconstruction kernel (fuse_crt) or run as their own pass
-        const bool fuse_crt = d.fuse_crt && d.prm.r <= 4;
+        const bool fuse_crt = d.fuse_crt && d.prm.r >= 1 && d.prm.r <= 4;
         launch_inverse(c, s.Acc, arows, st, !fuse_crt);
         // (4) exact integers -> residues mod q_I, mod-down by the special prime in coefficient form
         const long long o_ps = static_cast<long long>(L) * c.n;
@@ -798,9 +984,9 @@ namespace sb
             CrtArgs A{};
             A.Acc = s.Acc, A.punct = d.d_punct, A.neg = d.d_neg, A.primes = c.d_primes;
             A.inv_top = c.d_invq + (c.k - 1) * c.k;
+            A.half_mod = d.d_half_mod;
             A.R = s.R, A.out = out, A.o_bs = o_bs, A.o_ps = o_ps, A.base = base, A.L = Li, A.k = ki;
             A.total = static_cast<long long>(B) * 2 * c.n;
-            const unsigned grid = static_cast<unsigned>((A.total + 255) / 256), gridf = static_cast<unsigned>(B * 2 * 32);
             c.stats.begin("ks32_crt", 0, n * B * 2 * (4.0 * S * (L + 1) + 8.0 * L), st);
             if (fuse_crt)
                 c.stats.work32(0.5 * arows * S * n * d.prm.r, 0);
@@ -809,22 +995,12 @@ namespace sb
                 A.qtop_mod = c.d_qmod + (c.k - 1) * c.k;
                 A.t = c.t, A.t_ratio = c.t_ratio;
                 A.inv_top_mod_t = Tw{ c.inv_q_mod_t[c.k - 1], sbh::shoup(c.inv_q_mod_t[c.k - 1], c.t) };
-                if (fuse_crt)
-                    launch_crt_fused<3>(A, d, gridf, st);
-                else
-                    ks32_crt_kernel<3><<<grid, 256, 0, st>>>(A, d.prm);
+                launch_crt<3>(A, d, fuse_crt, B, c.logn, st);
             }
             else if (c.scheme == 1)
-            {
-                if (fuse_crt)
-                    launch_crt_fused<1>(A, d, gridf, st);
-                else
-                    ks32_crt_kernel<1><<<grid, 256, 0, st>>>(A, d.prm);
-            }
-            else if (fuse_crt)
-                launch_crt_fused<0>(A, d, gridf, st);
+                launch_crt<1>(A, d, fuse_crt, B, c.logn, st);
             else
-                ks32_crt_kernel<0><<<grid, 256, 0, st>>>(A, d.prm);
+                launch_crt<0>(A, d, fuse_crt, B, c.logn, st);
             c.stats.end(st);
             cuda_check(cudaGetLastError(), "ks32_crt_kernel");
         }

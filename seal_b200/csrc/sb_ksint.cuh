@@ -28,7 +28,7 @@ namespace sb
     struct KsIntParams
     {
         int S = 0, r = 0, logn = 0;
-        uint32_t p[kKsMaxS] = {}, mu[kKsMaxS] = {}, c2[kKsMaxS] = {};
+        uint32_t p[kKsMaxS] = {}, mu[kKsMaxS] = {}, c2[kKsMaxS] = {}, inv60[kKsMaxS] = {}; // inv60 = floor(2^60 / p)
         uint2 red[kKsMaxS] = {}, c1[kKsMaxS] = {};
         float inv_p[kKsMaxS] = {};
     };
@@ -36,11 +36,13 @@ namespace sb
     struct KsInt
     {
         bool ready = false;
+        bool mac_tile = true;  // product kernel with the key tile in shared memory (env SB200_KS_MAC_TILE)
         bool fuse_crt = false; // outer inverse stages inside the reconstruction kernel (env SB200_KS_FUSE_CRT)
         KsIntParams prm;
         uint2 *d_fwd_outer = nullptr, *d_inv_outer = nullptr; // [S][2^r]
         uint2 *d_fwd_local = nullptr, *d_inv_local = nullptr; // [S][2^r][4096]
         u64 *d_punct = nullptr, *d_neg = nullptr;              // [k][S]
+        u64 *d_half_mod = nullptr;                             // [k]: floor(q_special / 2) mod q_i
     };
 
     // per-ciphertext scratch of the integer path (bytes): digits' transforms, accumulated products, coefficient-form result

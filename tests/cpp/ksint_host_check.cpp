@@ -191,7 +191,7 @@ int main(int argc, char **argv)
         const u64 qi = q[i];
         u64 vq = mulmod(mulmod(m1 % qi, m2 % qi, qi), mult % qi, qi);
         if (neg) vq = (qi - vq) % qi;
-        float f = 0;
+        u64 f = 0; // the kernels' estimate of alpha: sum y_t floor(2^60 / p_t) >> 60
         u128 acc = 0; // 96 bits suffice
         for (int t = 0; t < h.S; t++)
         {
@@ -200,10 +200,10 @@ int main(int argc, char **argv)
             if (neg) r = (p - r) % p;
             const u64 x = mulmod(r, n % p, p);              // what the unscaled inverse transform returns
             u64 y = (mulmod(x, h.c1[2 * t], p) + h.c2[t]) % p;
-            f += static_cast<float>(static_cast<u32>(y)) * h.inv_p[t];
+            f += y * ((u64(1) << 60) / p);
             acc += static_cast<u128>(y) * h.punct_mod_q[i * h.S + t];
         }
-        const int alpha = static_cast<int>(f);
+        const int alpha = static_cast<int>(f >> 60);
         if (alpha < 0 || alpha >= h.S) { bad++; std::printf("alpha out of range\n"); break; }
         acc += h.neg_mod_q[i * h.S + alpha];
         if (static_cast<u64>(acc % qi) != vq) { bad++; std::printf("CRT reconstruction fails (trial %d)\n", trial); break; }
