@@ -457,8 +457,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE.json cfg2-cfg4 lines and the C++ harness")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the reference (profiling runs only)")
-    ap.add_argument("--ks-algo", type=int, default=None, choices=[0, 1],
-                    help="key switching: 1 = integer convolution on auxiliary primes (library default), 0 = 64-bit digit transforms")
+    ap.add_argument("--ks-algo", type=int, default=None, choices=[0, 1, 2],
+                    help="key switching: 0 = 64-bit digit transforms, 1 = automatic (library default: the integer convolution on auxiliary "
+                         "primes from 6 digits on), 2 = the integer path at every level")
     ap.add_argument("--scratch-gib", type=float, default=0.0, help="key-switching scratch budget (0: what the device has left, at most 64 GiB)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -489,7 +490,7 @@ def main():
     ctx = S.Context(wl["scheme"], n, mods, device=local)
     if args.ks_algo is not None:
         ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, args.ks_algo)
-    aux_primes = ctx.ksint_primes() if args.ks_algo != 0 else []
+    aux_primes = ctx.ksint_primes() if (args.ks_algo != 0 and (L >= 6 or args.ks_algo == 2)) else []
     g = torch.Generator(device="cuda")
     g.manual_seed(0x5EA1 + rank)
 

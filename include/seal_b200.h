@@ -73,8 +73,10 @@ size_t sb200_device_bytes(const sb200_context *ctx);
  *   SB200_LIMIT_SCRATCH_BYTES     budget of the per-context scratch arena (default 8 GiB, env SB200_SCRATCH_MB)
  *   SB200_LIMIT_KS_CHUNK          max ciphertexts per key-switching chunk (0 = derived from the scratch budget)
  *   SB200_LIMIT_HOST_STAGE_BYTES  device staging per pipeline slot of the *_host entry points (default 640 MiB)
- *   SB200_LIMIT_KS_ALGORITHM      key switching: 1 = exact integer convolution on 29-bit auxiliary primes (default where
- *                                 available: n >= 4096; env SB200_KS_ALGO), 0 = 64-bit digit transforms per output prime */
+ *   SB200_LIMIT_KS_ALGORITHM      key switching: 0 = 64-bit digit transforms per output prime; 1 (default, env SB200_KS_ALGO) =
+ *                                 automatic: the exact integer convolution on 29-bit auxiliary primes where it is available
+ *                                 (n >= 4096) and pays (levels with >= 6 digits, env SB200_KS_MIN_DIGITS); 2 = that path at every
+ *                                 level.  Results are identical words in every mode. */
 #define SB200_LIMIT_SCRATCH_BYTES 0
 #define SB200_LIMIT_KS_CHUNK 1
 #define SB200_LIMIT_HOST_STAGE_BYTES 2

@@ -220,7 +220,11 @@ int sb200_context_set_limit(sb200_context *ctx, int which, size_t value)
     case SB200_LIMIT_SCRATCH_BYTES: c.scratch_budget = std::max<size_t>(value, size_t(1) << 20); break;
     case SB200_LIMIT_KS_CHUNK: c.ks_chunk_max = value; break;
     case SB200_LIMIT_HOST_STAGE_BYTES: c.host_stage_bytes = std::max<size_t>(value, size_t(1) << 16); break;
-    case SB200_LIMIT_KS_ALGORITHM: c.ks_algo = value ? 1 : 0; break;
+    case SB200_LIMIT_KS_ALGORITHM:
+        if (value > 2)
+            throw std::invalid_argument("unknown key-switching algorithm");
+        c.ks_algo = static_cast<int>(value);
+        break;
     default: throw std::invalid_argument("unknown limit");
     }
     return SB200_OK;

@@ -320,6 +320,8 @@ namespace sb
         }
         if (const char *e = std::getenv("SB200_KS_ALGO"))
             c->ks_algo = std::atoi(e);
+        if (const char *e = std::getenv("SB200_KS_MIN_DIGITS"))
+            c->ks_min_digits = static_cast<size_t>(std::atoi(e));
         ksint_init(*c);
         return c;
     }
@@ -1736,16 +1738,16 @@ namespace sb
     };
     static size_t ks_words_per_ct(const Context &c, size_t L, bool need_c2)
     {
-        if (c.ksint_on()) // digits + (the key-multiplied tensor component) + the integer path's own buffers
+        if (c.ksint_on(L)) // digits + (the key-multiplied tensor component) + the integer path's own buffers
             return c.n * (L + (need_c2 ? L : 0)) + ksint_bytes_per_ct(c, L) / sizeof(u64);
         return c.n * (L + (L + 1) * L + 2 * (L + 1) + 4 + 2 * L + (need_c2 ? L : 0));
     }
     static KsScratch ks_carve(Context &c, size_t L, size_t B, bool need_c2)
     {
-        u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64) + (c.ksint_on() ? ksint_bytes_fixed(c, L) : 0)));
+        u64 *p = static_cast<u64 *>(c.ensure_scratch(ks_words_per_ct(c, L, need_c2) * B * sizeof(u64) + (c.ksint_on(L) ? ksint_bytes_fixed(c, L) : 0)));
         KsScratch s{};
         s.D = p, p += B * L * c.n;
-        if (c.ksint_on())
+        if (c.ksint_on(L))
         {
             s.C2 = need_c2 ? p : nullptr;
             p += need_c2 ? B * L * c.n : 0;
@@ -1764,7 +1766,7 @@ namespace sb
     {
         size_t per = ks_words_per_ct(c, L, need_c2) * sizeof(u64);
         size_t chunk = std::max<size_t>(1, c.scratch_budget / per);
-        if (c.ksint_on() && c.scratch_budget > 2 * ksint_bytes_fixed(c, L))
+        if (c.ksint_on(L) && c.scratch_budget > 2 * ksint_bytes_fixed(c, L))
             chunk = std::max<size_t>(1, (c.scratch_budget - ksint_bytes_fixed(c, L)) / per);
         // keep the row counts of a launch (B * (L+1) * L digit rows) far inside int range; element offsets are 64-bit everywhere
         chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 22) / ((L + 1) * L)));
@@ -1928,7 +1930,7 @@ namespace sb
             cuda_check(launch_ntt_inv(op, static_cast<int>(B * L), c.logn, c.d_primes, st, c.stats, "ks_target_intt"), "ks intt");
             dsrc = Src{ s.D, static_cast<long long>(L) * n, nullptr, 0, c.logn };
         }
-        if (c.ksint_on())
+        if (c.ksint_on(L))
         {
             ksint_core(c, L, B, s.I, dsrc, key, base, out, out_bs, st);
             return;

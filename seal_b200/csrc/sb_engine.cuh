@@ -128,8 +128,11 @@ namespace sb
         size_t host_stage_bytes = size_t(640) << 20;   // per pipeline slot of the *_host entry points
         LaunchStats stats;
         KsInt ksint;                         // integer key-switching path (sb_ksint.cuh); ready = tables built
-        int ks_algo = 1;                     // 1 = integer path when available (n >= 4096), 0 = 64-bit digit transforms
-        bool ksint_on() const { return ks_algo == 1 && ksint.ready; }
+        // key switching: 0 = 64-bit digit transforms, 1 = automatic (the integer path from ks_min_digits digits on: below that the
+        // L (L+1) large transforms are cheaper than S L + 2 S (L+1) small ones plus the reconstruction), 2 = integer path always
+        int ks_algo = 1;
+        size_t ks_min_digits = 6;
+        bool ksint_on(size_t L) const { return ksint.ready && (ks_algo == 2 || (ks_algo == 1 && L >= ks_min_digits)); }
         IoArena io;
         std::mutex mu;
         // cross-stream ordering of calls that share the scratch arenas (sb_api.cu: StreamOrder)

@@ -448,12 +448,14 @@ namespace sb
         const uint32_t *kbase = key32 + ((static_cast<size_t>(t) * digits * 2 * k) << LOGN) + x;
         const size_t kstep = static_cast<size_t>(2 * k) << LOGN;
         // tile rows: row tr (< 32) = output r = tr % 8 of task yg * 4 + tr / 8; unused tasks of a ragged last group re-read valid rows
+        // (asynchronous copies: all of a warp's rows are in flight together instead of one load-store round trip per row)
         for (int rho = warp; rho < L * 32; rho += 16)
         {
             const int J = rho >> 5, tr = rho & 31;
             const int task = min(yg * 4 + (tr >> 3), 2 * ntile - 1), c = task / ntile, i0 = (task - c * ntile) * TC;
-            ks_tile[(rho << 5) + lane] = __ldg(kbase + J * kstep + (static_cast<size_t>(c * k + i0 + (tr & 7)) << LOGN));
+            cp_async4(ks_tile + (rho << 5) + lane, kbase + J * kstep + (static_cast<size_t>(c * k + i0 + (tr & 7)) << LOGN));
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int bsub = warp & 3, icsub = warp >> 2;
         const int task = yg * 4 + icsub;

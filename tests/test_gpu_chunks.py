@@ -177,7 +177,7 @@ def test_selftest_rates_and_profile_work_counters():
     rates = [ctx.selftest_rate(kind) for kind in range(4)]
     assert all(r > 1e9 for r in rates), rates
     # (b) the integer path (default): 32-bit butterflies and multiply-accumulates are counted separately
-    ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, 1)
+    ctx.set_limit(ctx.LIMIT_KS_ALGORITHM, 2)
     S5 = len(ctx.ksint_primes())
     out64 = out.clone()
     out.zero_()

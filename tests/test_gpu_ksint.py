@@ -72,7 +72,7 @@ def _keyswitch_case(scheme_name, n, bits, batch, t=0):
                    for _ in range(batch)])
     rk = ctx.load_key(key)
     assert ctx.ksint_primes(), "the integer path must be available at n >= 4096"
-    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 2)
     got_int = ctx.relinearize(c3, rk)
     ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 0)
     got_64 = ctx.relinearize(c3, rk)
@@ -82,7 +82,7 @@ def _keyswitch_case(scheme_name, n, bits, batch, t=0):
         assert (got_int[b] == want).all(), "integer path vs oracle"
     # a lower level uses a subset of the digits and of the output primes (evaluator.cpp:2617-2640)
     if L >= 2:
-        ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
+        ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 2)
         low = np.ascontiguousarray(c3[:, :, :L - 1, :])
         got = ctx.relinearize(low, rk)
         for b in range(batch):
@@ -101,3 +101,38 @@ def test_relinearize_integer_path_vs_oracle_bfv():
 
 def test_relinearize_integer_path_vs_oracle_bgv():
     _keyswitch_case("BGV", 8192, [50, 50, 50, 51], 3, t=65537)
+
+
+@pytest.mark.parametrize("scheme_name,n,bits,t", [("CKKS", 8192, [50, 50, 50, 51], 0), ("BFV", 4096, [36, 36, 37], 65537),
+                                                 ("BGV", 4096, [40, 40, 40], 65537), ("CKKS", 4096, [30] * 9, 0)])
+def test_rotation_and_fused_multiply_integer_path_vs_oracle(scheme_name, n, bits, t):
+    """apply_galois (Galois views of the target: NTT-form permutation for CKKS / BGV, coefficient-form automorphism with sign flips
+    for BFV, evaluator.cpp:2384-2502) and multiply + relinearize through the integer path, every word against the oracle; the last
+    case has 8 digits (the automatic mode's territory) of 30-bit primes (4 auxiliary primes)"""
+    S = sb()
+    scheme = getattr(S, scheme_name)
+    mods = O.coeff_modulus_create(n, bits)
+    k, L = len(mods), len(mods) - 1
+    ctx = S.Context(scheme, n, mods, t) if t else S.Context(scheme, n, mods)
+    oc = O.Oracle(getattr(O, scheme_name), n, mods, t) if t else O.Oracle(getattr(O, scheme_name), n, mods)
+    rng = np.random.default_rng(3 * n + k)
+    key = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k)]) for _ in range(2)])
+                    for _ in range(L)])
+    rk = ctx.load_key(key)
+    batch = 3
+    c2 = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(L)]) for _ in range(2)])
+                   for _ in range(batch)])
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 2)
+    for elt in (3, 2 * n - 1, O.galois_elt_from_step(n, 1)):
+        got = ctx.apply_galois(c2, elt, rk)
+        for b in range(batch):
+            assert (got[b] == oc.apply_galois(L, c2[b], elt, key)).all(), ("apply_galois", elt, b)
+    if scheme_name == "CKKS":
+        d2 = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(L)]) for _ in range(2)])
+                       for _ in range(batch)])
+        got = ctx.multiply_relinearize(c2, d2, rk)
+        for b in range(batch):
+            assert (got[b] == oc.multiply_relin(L, c2[b], d2[b], key)).all(), ("multiply_relinearize", b)
+        # automatic mode picks the same words whatever path a level runs
+        ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
+        assert (ctx.multiply_relinearize(c2, d2, rk) == got).all()

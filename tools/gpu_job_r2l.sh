@@ -1,17 +1,17 @@
 #!/bin/bash
-# round-2 GPU job K: key-tile product kernel with the digit ring, reconstruction kernel with next-prime prefetch
+# round-2 GPU job L: key-tile product kernel with the digit ring, reconstruction kernel with next-prime prefetch
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
-python -m pytest tests/test_gpu_ksint.py tests/test_gpu_chunks.py -q -x > $O/r2k_ksint.log 2>&1; tail -3 $O/r2k_ksint.log
-SB200_KS_MAC_TILE=0 python -m pytest tests/test_gpu_ksint.py -q -x > $O/r2k_ksint_notile.log 2>&1; tail -3 $O/r2k_ksint_notile.log
+python -m pytest tests/test_gpu_ksint.py tests/test_gpu_chunks.py -q -x > $O/r2l_ksint.log 2>&1; tail -3 $O/r2l_ksint.log
+SB200_KS_MAC_TILE=0 python -m pytest tests/test_gpu_ksint.py -q -x > $O/r2l_ksint_notile.log 2>&1; tail -3 $O/r2l_ksint_notile.log
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 900 python bench.py --batch 256 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --no-configs > $O/bench_r2k_$name.json 2> $O/bench_r2k_$name.err
-  tail -c 300 $O/bench_r2k_$name.err
+  env "$@" timeout 900 python bench.py --batch 256 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --no-configs > $O/bench_r2l_$name.json 2> $O/bench_r2l_$name.err
+  tail -c 300 $O/bench_r2l_$name.err
   python - $name <<'PY'
 import json, sys
 try:
-    l = json.loads(open("gpurun_out/bench_r2k_%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
+    l = json.loads(open("gpurun_out/bench_r2l_%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
     print(sys.argv[1], "value", round(l["value"], 1), "verified", l["verified"] and l["verified"]["ok"], "chunk", l["config"]["ciphertexts_per_key_pass"])
     alu = {e["kernel"]: e for e in l["roofline"]["alu"]["kernels"]}
     for kk in l["roofline"]["kernels"]:
