@@ -477,57 +477,66 @@ namespace sb
 #pragma unroll
                 for (int r = 0; r < TC; r++)
                     acc[i][r] = 0;
-            int Jissue = 0;
-            auto issue = [&]() { // digit words of digit Jissue -> stage Jissue % D (an empty group once the digits are exhausted)
-                if (Jissue < L)
+            // The digits are consumed in pairs: the two products that go to one accumulator sit next to each other, so ptxas forms them
+            // with zero addends and adds both with ONE three-input 64-bit add (2.0 instructions per multiply-accumulate; one digit at a
+            // time costs 3.0, and this kernel is bound by instruction issue: ncu).  The loop is unrolled by the ring depth, so stage
+            // offsets are compile-time constants.  One cp.async group = one pair of digits; three pairs are in flight.
+            auto issue_pair = [&](int stage, int J) { // digits J, J + 1 -> stages `stage`, `stage + 1`
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (J + h < L)
+                    {
+                        uint32_t *dst = ring + (stage + h) * (TB * 512);
+#pragma unroll
+                        for (int i = 0; i < TB; i++)
+                            cp_async4(dst + i * 512, dp + (i << LOGN));
+                        dp += dstep;
+                    }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            issue_pair(0, 0), issue_pair(2, 2), issue_pair(4, 4);
+            const uint32_t *kt = ktile;
+#pragma unroll 1
+            for (int J0 = 0; J0 < L; J0 += D)
+            {
+#pragma unroll
+                for (int u = 0; u < D; u += 2)
                 {
-                    uint32_t *dst = ring + (Jissue & (D - 1)) * (TB * 512);
+                    const int J = J0 + u;
+                    if (J >= L)
+                        break;
+                    issue_pair((u + 6) & (D - 1), J + 6);
+                    asm volatile("cp.async.wait_group 3;" ::: "memory"); // pairs up to this one have landed
+                    uint32_t d0[TB], k0[TC], d1[TB], k1[TC];
+                    const uint32_t *src = ring + u * (TB * 512);
 #pragma unroll
                     for (int i = 0; i < TB; i++)
-                        cp_async4(dst + i * 512, dp + (i << LOGN));
-                    dp += dstep;
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                Jissue++;
-            };
-            uint32_t dA[TB], kA[TC], dB[TB], kB[TC];
-            auto fetch = [&](uint32_t(&d_)[TB], uint32_t(&k_)[TC], int J) {
-                const uint32_t *src = ring + (J & (D - 1)) * (TB * 512);
-                const uint32_t *kt = ktile + (min(J, L - 1) << 10);
-#pragma unroll
-                for (int i = 0; i < TB; i++)
-                    d_[i] = src[i * 512];
-#pragma unroll
-                for (int r = 0; r < TC; r++)
-                    k_[r] = kt[r << 5];
-            };
-            auto macs = [&](const uint32_t(&d_)[TB], const uint32_t(&k_)[TC]) {
-#pragma unroll
-                for (int i = 0; i < TB; i++)
+                        d0[i] = src[i * 512], d1[i] = src[TB * 512 + i * 512];
 #pragma unroll
                     for (int r = 0; r < TC; r++)
-                        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d_[i]), "r"(k_[r]));
-            };
+                        k0[r] = kt[r << 5], k1[r] = kt[1024 + (r << 5)];
+                    kt += 2048;
+                    if (J + 1 < L)
+                    {
 #pragma unroll
-            for (int j = 0; j < D - 1; j++)
-                issue();
-            asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
-            fetch(dA, kA, 0);
-            int J = 0;
-#pragma unroll 1
-            for (; J + 2 <= L; J += 2)
-            {
-                issue();
-                asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
-                fetch(dB, kB, J + 1);
-                macs(dA, kA);
-                issue();
-                asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
-                fetch(dA, kA, J + 2); // one past the end reads a stale stage; its products are never formed
-                macs(dB, kB);
+                        for (int i = 0; i < TB; i++)
+#pragma unroll
+                            for (int r = 0; r < TC; r++)
+                            {
+                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
+                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d1[i]), "r"(k1[r]));
+                            }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i = 0; i < TB; i++)
+#pragma unroll
+                            for (int r = 0; r < TC; r++)
+                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
+                    }
+                }
             }
-            if (J < L)
-                macs(dA, kA);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < TB; i++)
