@@ -630,6 +630,24 @@ namespace sb
             }
         };
         prefetch();
+        // fused shape: the rows (output prime, auxiliary prime) are consecutive in memory; the 2^R words of the NEXT row are requested
+        // before the butterflies of the current one (two warps per scheduler cannot hide a DRAM round trip per row otherwise)
+        uint32_t nrow[FUSE ? E : 1];
+        int rows_left = FUSE ? (L + 1) * S : 0;
+        auto fetch_row = [&]() {
+            if (FUSE)
+            {
+                if (rows_left > 0)
+                {
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+                        nrow[e] = src[e << 12];
+                }
+                src += size_t(1) << LOGN;
+                rows_left--;
+            }
+        };
+        fetch_row();
         auto reconstruct = [&](int ki, const PrimeDev &Q, u64(&val)[E], bool more) {
             u64 a0[E], a1[E], f[E];
 #pragma unroll
@@ -656,10 +674,10 @@ namespace sb
                 uint32_t a[E];
                 if (FUSE)
                 {
-                    const uint32_t *st = src + (static_cast<size_t>(t) << LOGN);
 #pragma unroll
                     for (int e = 0; e < E; e++)
-                        a[e] = st[e << 12];
+                        a[e] = nrow[e];
+                    fetch_row();
                     const uint2 *tw = tw_outer + (t << R);
                     radix_inv<R>(a, [&](int lvl, int g) { return __ldg(tw + (1 << lvl) + g); }, P);
                 }
@@ -689,8 +707,6 @@ namespace sb
                 hi += (lo < ng);
                 val[e] = barrett_wide(lo, hi, Q); // < S 2^29 q + q
             }
-            if (FUSE)
-                src += static_cast<size_t>(S) << LOGN;
         };
         const PrimeDev T = A.primes[k - 1];
         u64 U[E], K[MODE == 3 ? E : 1];
