@@ -136,3 +136,27 @@ def test_rotation_and_fused_multiply_integer_path_vs_oracle(scheme_name, n, bits
         # automatic mode picks the same words whatever path a level runs
         ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 1)
         assert (ctx.multiply_relinearize(c2, d2, rk) == got).all()
+
+
+@pytest.mark.parametrize("n,bits,batch", [(4096, [30] * 9, 37), (4096, [30] * 42, 18)])
+def test_product_kernel_shapes_vs_oracle(n, bits, batch):
+    """the two product kernels of the integer path: the key-tile kernel walks over 16 ciphertexts per iteration (batch 37: two full
+    iterations and a ragged one), and falls back to the register-tile kernel when the key tile of a level does not fit shared memory
+    (41 digits); sampled ciphertexts against the oracle, all of them against the 64-bit path"""
+    S = sb()
+    mods = O.coeff_modulus_create(n, bits)
+    k, L = len(mods), len(mods) - 1
+    ctx = S.Context(S.CKKS, n, mods)
+    oc = O.Oracle(O.CKKS, n, mods)
+    rng = np.random.default_rng(n + k + batch)
+    key = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k)]) for _ in range(2)])
+                    for _ in range(L)])
+    c3 = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(L)]) for _ in range(3)])
+                   for _ in range(batch)])
+    rk = ctx.load_key(key)
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 2)
+    got = ctx.relinearize(c3, rk)
+    ctx.set_limit(S.Context.LIMIT_KS_ALGORITHM, 0)
+    assert (ctx.relinearize(c3, rk) == got).all()
+    for b in (0, 15, 16, batch - 1):
+        assert (got[b] == oc.relinearize(L, c3[b], key)).all(), b
