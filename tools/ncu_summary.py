@@ -38,7 +38,10 @@ def main():
             while args and not args[0].startswith("--"):
                 k, v = args.pop(0).split("=")
                 names[k] = v
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # the raw page exported on the GPU box (ncu -i REPORT --page raw --csv) when the report itself is too large to keep
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
