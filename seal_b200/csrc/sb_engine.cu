@@ -587,7 +587,7 @@ namespace sb
         const long long pe = (((b * L + i) << logn) >> 1) + (e & ((1ll << (logn - 1)) - 1));
         const PrimeDev &P = primes[i];
         const ulonglong2 x = a[e], y = plain[pe];
-        out[e] = make_ulonglong2(mulmod_barrett(x.x, y.x, P), mulmod_barrett(x.y, y.y, P));
+        out[e] = make_ulonglong2(mulmod_wide(x.x, y.x, P), mulmod_wide(x.y, y.y, P)); // residues below q: one-word Barrett applies
     }
 
     void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st)
