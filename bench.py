@@ -706,13 +706,23 @@ def main():
     alu = [e for e in (alu_entry(r) for r in prof) if e]
     whole_floor = sum(e["floor_ms"] for e in alu) * 1e-3
     traffic = ncu_traffic(top[0])
+    # DRAM traffic of ALL kernels of one key-switching chunk (committed ncu capture, one launch each) against the compulsory bytes of
+    # that chunk: what the intermediates of the path cost in HBM traffic
+    step_traffic = None
+    per_kernel = [ncu_traffic(r[0]) for r in prof]
+    if all(per_kernel) and len({t_["batch"] for t_ in per_kernel}) == 1:
+        cb = per_kernel[0]["batch"]
+        tot_b = sum(t_["dram_bytes_per_launch"] for t_ in per_kernel)
+        step_traffic = {"ciphertexts_per_chunk": cb, "dram_bytes_per_chunk": tot_b, "dram_bytes_per_ciphertext": tot_b / cb,
+                        "ratio_to_compulsory": tot_b / (cb * ct_bytes + key_bytes),
+                        "avg_dram_GBps_at_measured_speed": tot_b / cb * value / 1e9, "frac_of_hbm_peak": tot_b / cb * value / 1e9 / peak}
     alg_per_launch = step_bytes * args.steps / max(top[2], 1)  # the operation's compulsory bytes behind one launch of the dominant kernel
     achieved = alg_per_launch / (top_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
         "traffic_ratio": (traffic["dram_bytes_per_launch"] / (traffic.get("batch", chunk) * ct_bytes + key_bytes)) if traffic else None,
-        "traffic_source": traffic.get("source") if traffic else None,
+        "traffic_source": traffic.get("source") if traffic else None, "step_traffic": step_traffic,
         "peak_source": peak_src, "share_of_step": top[1] / tot_prof_ms, "launches": top[2], "avg_launch_ms": top_launch_ms,
         "bytes_basis": "SURVEY 8(d): the whole operation's compulsory bytes (6*L*n*8 per ciphertext + key per B_reuse) are attributed to "
                        "the dominant kernel's launches; intermediates (digits, accumulated products) are not counted",
