@@ -260,21 +260,44 @@ namespace sb
         fwd_local_block_tw<FAST>(a, x, twf, l, P);
     }
 
+    // dynamic shared memory of the local passes: [xs 8 x 256 u64 | twiddles of the CTA's 8 adjacent blocks 8 * 255 x 16 B | mbarrier].
+    // Stage s of 8 adjacent blocks is one contiguous run of 8 * 2^s table entries: 8 TMA bulk copies stage all 2040 twiddles while
+    // the data loads are in flight (fetching them with one dependent global load per stage left the warps waiting on memory 8 times
+    // per block: ncu long-scoreboard 6.5 per issue in round 2's capture of the result transform).
+    constexpr int kLocalSmem = 8 * 256 * 8 + 8 * 255 * 16 + 16;
+    __device__ __forceinline__ void stage_local_twiddles(Tw *tws, u64 *bar, const Tw *table, int na)
+    {
+        if (threadIdx.x == 0)
+            mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            mbar_expect_tx(bar, 8 * 255 * sizeof(Tw));
+#pragma unroll
+            for (int st = 0; st < 8; st++)
+                tma_load_1d(tws + 8 * ((1 << st) - 1), table + ((na + blockIdx.y * 8) << st), (8u << st) * sizeof(Tw), bar);
+        }
+    }
     template <bool FAST, class Op>
     __global__ void __launch_bounds__(256) ntt_fwd_local(Op op, const PrimeDev *__restrict__ primes, int na)
     {
-        __shared__ __align__(16) u64 xs[8][256];
+        extern __shared__ __align__(16) unsigned char nl_smem[];
+        u64(*xs)[256] = reinterpret_cast<u64(*)[256]>(nl_smem);
+        Tw *tws = reinterpret_cast<Tw *>(nl_smem + 8 * 256 * 8);
+        u64 *bar = reinterpret_cast<u64 *>(tws + 8 * 255);
         const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         if (op.skip(row))
             return;
         const int b = blockIdx.y * 8 + warp;
         const PrimeDev P = primes[op.pid(row)];
+        stage_local_twiddles(tws, bar, P.fwd, na);
         const u64 *src = op.mid(row) + (b << kLocalLog);
         u64 a[8];
 #pragma unroll
         for (int j = 0; j < 8; j++)
             a[j] = src[l + 32 * j];
-        fwd_local_block<FAST>(a, xs[warp], P.fwd, na + b, l, P);
+        mbar_wait(bar, 0);
+        fwd_local_block_tw<FAST>(a, xs[warp], [&](int s_, int i) { return tws[8 * ((1 << s_) - 1) + (warp << s_) + i]; }, l, P);
 #pragma unroll
         for (int j = 0; j < 8; j++)
             a[j] = fwd_finish<FAST>(a[j], P);
@@ -285,21 +308,26 @@ namespace sb
     template <class Op>
     __global__ void __launch_bounds__(256) ntt_inv_local(Op op, const PrimeDev *__restrict__ primes, int na)
     {
-        __shared__ __align__(16) u64 xs[8][256];
+        extern __shared__ __align__(16) unsigned char nl_smem[];
+        u64(*xs)[256] = reinterpret_cast<u64(*)[256]>(nl_smem);
+        Tw *tws = reinterpret_cast<Tw *>(nl_smem + 8 * 256 * 8);
+        u64 *bar = reinterpret_cast<u64 *>(tws + 8 * 255);
         const int row = blockIdx.x, warp = threadIdx.x >> 5, l = threadIdx.x & 31;
         if (op.skip(row))
             return;
         const int b = blockIdx.y * 8 + warp;
         const PrimeDev P = primes[op.pid(row)];
         u64 *x = xs[warp];
-        const Tw *__restrict__ tw = P.inv;
-        const int t0 = na + b;
+        stage_local_twiddles(tws, bar, P.inv, na);
+        // in-block stage s (2^s groups per block), group i of this warp's block
+        auto tws_at = [&](int s_, int i) { return tws[8 * ((1 << s_) - 1) + (warp << s_) + i]; };
 
         u64 a[8];
         op.load8(row, (b << kLocalLog) + 8 * l, a, P);
+        mbar_wait(bar, 0);
         {
             // strides 1,2,4
-            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (7 - lvl)) + (l << (2 - lvl)) + k); };
+            auto twf = [&](int lvl, int k) { return tws_at(7 - lvl, (l << (2 - lvl)) + k); };
             inv_regs<0, false>(a, twf, P);
         }
 #pragma unroll
@@ -312,7 +340,7 @@ namespace sb
             for (int j = 0; j < 8; j++)
                 a[j] = x[swz(64 * hi + lo + 8 * j)];
             // strides 8,16,32
-            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (4 - lvl)) + (hi << (2 - lvl)) + k); };
+            auto twf = [&](int lvl, int k) { return tws_at(4 - lvl, (hi << (2 - lvl)) + k); };
             inv_regs<0, false>(a, twf, P);
             __syncwarp();
 #pragma unroll
@@ -325,7 +353,7 @@ namespace sb
             a[j] = x[swz(l + 32 * j)];
         {
             // strides 64 (pairs j,j+2) and 128 (pairs j,j+4)
-            auto twf = [&](int lvl, int k) { return ldg_tw(tw + (t0 << (2 - lvl)) + k); };
+            auto twf = [&](int lvl, int k) { return tws_at(2 - lvl, k); };
             inv_regs<1, false>(a, twf, P);
         }
         u64 *mid = op.mid(row) + (b << kLocalLog);
@@ -579,9 +607,15 @@ namespace sb
             return cudaGetLastError(); // the caller runs its own fused local pass on op.mid()
         ls.begin(name, 2, bytes, st, bf_stage * kLocalLog); // local pass
         if (fast)
-            ntt_fwd_local<true, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        {
+            cudaFuncSetAttribute(ntt_fwd_local<true, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLocalSmem);
+            ntt_fwd_local<true, Op><<<dim3(nrows, na / 8), 256, kLocalSmem, st>>>(op, primes, na);
+        }
         else
-            ntt_fwd_local<false, Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        {
+            cudaFuncSetAttribute(ntt_fwd_local<false, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLocalSmem);
+            ntt_fwd_local<false, Op><<<dim3(nrows, na / 8), 256, kLocalSmem, st>>>(op, primes, na);
+        }
         ls.end(st);
         return cudaGetLastError();
     }
@@ -604,7 +638,8 @@ namespace sb
         }
         const int logna = logn - kLocalLog, na = 1 << logna;
         ls.begin(name, 2, bytes, st, bf_stage * kLocalLog); // local pass
-        ntt_inv_local<Op><<<dim3(nrows, na / 8), 256, 0, st>>>(op, primes, na);
+        cudaFuncSetAttribute(ntt_inv_local<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLocalSmem);
+        ntt_inv_local<Op><<<dim3(nrows, na / 8), 256, kLocalSmem, st>>>(op, primes, na);
         ls.end(st);
         dim3 gc(nrows, (1 << kLocalLog) / (kTile / na));
         ls.begin(name, 1, bytes, st, bf_stage * logna); // column pass
