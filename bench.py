@@ -291,6 +291,30 @@ def run_cfg2(S, R, torch, np):
             "verified": {"indices": idx, "ok": True, "against": "oracle/_ref (reference Evaluator), device-resident and host-buffer results"}}
 
 
+def run_k16(S, R, torch, np):
+    """the shape BASELINE.json's metric text names ("n=2^16, L=16 primes"): CKKS n=65536, 16 primes, batch 512: multiply + relinearize"""
+    n, batch = 65536, 512
+    mods = R.coeff_modulus_create(n, [55] * 16)
+    L = len(mods) - 1
+    rc = R.RefContext(R.CKKS, n, mods)
+    ctx = S.Context(S.CKKS, n, mods)
+    free_b, _ = torch.cuda.mem_get_info()
+    ctx.set_limit(ctx.LIMIT_SCRATCH_BYTES, int(max(8 << 30, min(free_b - (40 << 30), 64 << 30))))
+    rk = ctx.load_key(rc.relin_key())
+    g = torch.Generator(device="cuda")
+    g.manual_seed(16)
+    a, b = device_rand(torch, mods, n, (batch, 2), L, g), device_rand(torch, mods, n, (batch, 2), L, g)
+    out = torch.empty_like(a)
+    sec = timed(torch, lambda: ctx.d_multiply_relinearize(a, b, rk, out, L, batch), 3, 2)
+    idx = [0, batch - 1]
+    for i in idx:
+        if not (to_np(out[i]) == rc.multiply_relin(L, to_np(a[i]), to_np(b[i]))).all():
+            fail(f"k16 ciphertext {i}")
+    return {"config": "CKKS n=65536, 16 primes, batch 512, multiply+relinearize (device-resident)", "value": batch / sec, "unit": UNIT,
+            "ciphertexts_per_key_pass": ctx.keyswitch_chunk(L, batch, True),
+            "verified": {"indices": idx, "ok": True, "against": "oracle/_ref (reference Evaluator)"}}
+
+
 def run_cfg3(S, R, torch, np):
     """CKKS n=32768, 16 primes, batch 256: a <- rescale(relin(a*b)); b <- mod_switch_to_next(b), depth 8"""
     n, batch, depth = 32768, 256, 8
@@ -751,7 +775,7 @@ def main():
         del a, b, out
         torch.cuda.empty_cache()
         configs = {}
-        for name, fn in (("cfg2", run_cfg2), ("cfg3", run_cfg3), ("cfg4", run_cfg4)):
+        for name, fn in (("cfg2", run_cfg2), ("cfg3", run_cfg3), ("cfg4", run_cfg4), ("n65536_k16", run_k16)):
             t0 = time.time()
             configs[name] = fn(S, R, torch, np)
             configs[name]["wall_s"] = round(time.time() - t0, 1)

@@ -453,7 +453,9 @@ namespace sb
         {
             const int J = rho >> 5, tr = rho & 31;
             const int task = min(yg * 4 + (tr >> 3), 2 * ntile - 1), c = task / ntile, i0 = (task - c * ntile) * TC;
-            cp_async4(ks_tile + (rho << 5) + lane, kbase + J * kstep + (static_cast<size_t>(c * k + i0 + (tr & 7)) << LOGN));
+            // tile layout [J][output tile][half][lane][4 words]: a lane's 8 key words of a digit are two 16-byte reads
+            cp_async4(ks_tile + ((((J << 3) + (tr >> 2)) << 5) + lane) * 4 + (tr & 3),
+                      kbase + J * kstep + (static_cast<size_t>(c * k + i0 + (tr & 7)) << LOGN));
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -462,8 +464,8 @@ namespace sb
         if (task >= 2 * ntile)
             return;
         const int c = task / ntile, i0 = (task - c * ntile) * TC;
-        const uint32_t *ktile = ks_tile + ((icsub * TC) << 5) + lane;
-        uint32_t *ring = ks_tile + L * 1024 + threadIdx.x;
+        const uint32_t *ktile = ks_tile + (((icsub * 2) << 5) + lane) * 4; // + J * 1024 words per digit, + 128 words for the second half
+        uint32_t *ring = ks_tile + L * 1024 + threadIdx.x * 4;           // [stage][thread][TB words]
         const P32 P = make_p32(prm.p[t]);
         const uint2 red = prm.red[t];
         const uint32_t mu = prm.mu[t];
@@ -489,7 +491,7 @@ namespace sb
                         uint32_t *dst = ring + (stage + h) * (TB * 512);
 #pragma unroll
                         for (int i = 0; i < TB; i++)
-                            cp_async4(dst + i * 512, dp + (i << LOGN));
+                            cp_async4(dst + i, dp + (i << LOGN));
                         dp += dstep;
                     }
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -507,14 +509,17 @@ namespace sb
                         break;
                     issue_pair((u + 6) & (D - 1), J + 6);
                     asm volatile("cp.async.wait_group 3;" ::: "memory"); // pairs up to this one have landed
+                    static_assert(TB == 4 && TC == 8, "the operand fetches below are 16-byte reads of 4 digit words / 2 x 4 key words");
                     uint32_t d0[TB], k0[TC], d1[TB], k1[TC];
-                    const uint32_t *src = ring + u * (TB * 512);
-#pragma unroll
-                    for (int i = 0; i < TB; i++)
-                        d0[i] = src[i * 512], d1[i] = src[TB * 512 + i * 512];
-#pragma unroll
-                    for (int r = 0; r < TC; r++)
-                        k0[r] = kt[r << 5], k1[r] = kt[1024 + (r << 5)];
+                    {
+                        const uint32_t *src = ring + u * (TB * 512);
+                        const uint4 da = *reinterpret_cast<const uint4 *>(src), db = *reinterpret_cast<const uint4 *>(src + TB * 512);
+                        const uint4 ka = *reinterpret_cast<const uint4 *>(kt), kb = *reinterpret_cast<const uint4 *>(kt + 128);
+                        const uint4 kc = *reinterpret_cast<const uint4 *>(kt + 1024), kd = *reinterpret_cast<const uint4 *>(kt + 1024 + 128);
+                        d0[0] = da.x, d0[1] = da.y, d0[2] = da.z, d0[3] = da.w, d1[0] = db.x, d1[1] = db.y, d1[2] = db.z, d1[3] = db.w;
+                        k0[0] = ka.x, k0[1] = ka.y, k0[2] = ka.z, k0[3] = ka.w, k0[4] = kb.x, k0[5] = kb.y, k0[6] = kb.z, k0[7] = kb.w;
+                        k1[0] = kc.x, k1[1] = kc.y, k1[2] = kc.z, k1[3] = kc.w, k1[4] = kd.x, k1[5] = kd.y, k1[6] = kd.z, k1[7] = kd.w;
+                    }
                     kt += 2048;
                     if (J + 1 < L)
                     {
