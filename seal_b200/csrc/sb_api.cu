@@ -1285,7 +1285,21 @@ int sb200_batch_decode_host(sb200_context *ctx, size_t batch, const uint64_t *pl
 
 int sb200_square_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *a, uint64_t *out3)
 {
-    return sb200_multiply_host(ctx, L, batch, a, a, out3);
+    SB_NEED(a);
+    SB_NEED(out3);
+    SB_TRY
+    SB_ENTER(ctx)
+    check_level(c, L, batch);
+    const size_t w = L * c.n;
+    // one operand crosses the bus; the NTT-form schemes square with their own kernel (op_ckks_multiply sees a == b)
+    HostPipe(c).run(batch, 2 * w, 0, 3 * w, a, nullptr, out3, [&](size_t B, u64 *da, u64 *, u64 *dout, cudaStream_t st) {
+        if (c.scheme != SB200_SCHEME_BFV)
+            op_ckks_multiply(c, L, B, da, da, dout, st);
+        else
+            op_bfv_multiply(c, L, B, da, da, dout, st);
+    });
+    return SB200_OK;
+    SB_CATCH
 }
 
 int sb200_relinearize_host(sb200_context *ctx, size_t L, size_t batch, const uint64_t *in3, const sb200_kswitch_key *key, uint64_t *out2)

@@ -517,9 +517,46 @@ namespace sb
         }
     }
 
+    // squaring (ckks_square / bgv_square, evaluator.cpp:1022-1142): (x0^2, 2 x0 x1, x1^2) -- three products and two input rows per
+    // coefficient instead of four and four; the kernel is bound by HBM (5 rows moved instead of 7)
+    __global__ void __launch_bounds__(256) ckks_square_kernel(const u64 *__restrict__ a, u64 *out, const PrimeDev *__restrict__ primes, int logn,
+                                                               int L, long long total)
+    {
+        long long e = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; // over batch*L*n
+        if (e >= total)
+            return;
+        const long long poly = static_cast<long long>(L) << logn;
+        const long long bidx = e / poly, r = e % poly;
+        const PrimeDev P = primes[static_cast<int>(r >> logn)];
+        const u64 *pa = a + bidx * 2 * poly + r;
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
+        auto twice = [&](u64 p0, u64 p1) {
+            const u64 m = mulmod_wide(p0, p1, P);
+            return csub(m + m, P.q);
+        };
+        u64 *po = out + bidx * 3 * poly + r;
+        *reinterpret_cast<ulonglong2 *>(po) = make_ulonglong2(mulmod_wide(x0.x, x0.x, P), mulmod_wide(x0.y, x0.y, P));
+        *reinterpret_cast<ulonglong2 *>(po + poly) = make_ulonglong2(twice(x0.x, x1.x), twice(x0.y, x1.y));
+        *reinterpret_cast<ulonglong2 *>(po + 2 * poly) = make_ulonglong2(mulmod_wide(x1.x, x1.x, P), mulmod_wide(x1.y, x1.y, P));
+    }
+
     void op_ckks_multiply(Context &c, size_t L, size_t batch, const u64 *a, const u64 *b, u64 *out3, cudaStream_t st)
     {
         const size_t step = std::max<size_t>(1, (size_t(1) << 31) / (L * c.n));
+        if (a == b)
+        {
+            for (size_t b0 = 0; b0 < batch; b0 += step)
+            {
+                const size_t nb = std::min(step, batch - b0);
+                const long long total = static_cast<long long>(nb) * L * c.n;
+                c.stats.begin("ckks_square", 0, 5.0 * 8.0 * total, st); // 2 reads + 3 writes per coefficient
+                ckks_square_kernel<<<static_cast<unsigned>((total / 2 + 255) / 256), 256, 0, st>>>(a + b0 * 2 * L * c.n, out3 + b0 * 3 * L * c.n,
+                                                                                                     c.d_primes, c.logn, static_cast<int>(L), total);
+                c.stats.end(st);
+                cuda_check(cudaGetLastError(), "ckks_square_kernel");
+            }
+            return;
+        }
         for (size_t b0 = 0; b0 < batch; b0 += step)
         {
             size_t nb = std::min(step, batch - b0);
