@@ -456,7 +456,7 @@ namespace sbh
             dst[0] = static_cast<std::uint32_t>(w);
             dst[1] = static_cast<std::uint32_t>((w << 32) / p);
         };
-        h.red.resize(2 * S), h.mu.resize(S), h.c1.resize(2 * S), h.c2.resize(S), h.inv_p.resize(S);
+        h.red.resize(2 * S), h.mu.resize(S), h.c1.resize(2 * S), h.c2.resize(S);
         h.fwd_outer.assign(S * nb * 2, 0), h.inv_outer.assign(S * nb * 2, 0);
         h.fwd_local.assign(S * n * 2, 0), h.inv_local.assign(S * n * 2, 0);
         std::vector<u64> rp(n), irp(n);
@@ -475,7 +475,6 @@ namespace sbh
             }
             pair32((u64(1) << 32) % p, p, &h.red[2 * t]);
             h.mu[t] = static_cast<std::uint32_t>((u64(1) << 32) / p);
-            h.inv_p[t] = 1.0f / static_cast<float>(p);
             for (std::size_t e = 1; e < nb; e++)
             {
                 pair32(rp[e], p, &h.fwd_outer[(t * nb + e) * 2]);

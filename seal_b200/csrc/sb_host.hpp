@@ -121,10 +121,10 @@ namespace sbh
         // (2^s + i), entries 256.. = the last four stages transposed per thread: [256 + j * 256 + thread], j < 15
         std::vector<std::uint32_t> fwd_local, inv_local;
         // CRT reconstruction (P = prod p_t, H = (P - 1) / 2): y_t = x_t * c1_t + c2_t mod p_t with c1 = n^-1 (P/p_t)^-1,
-        // c2 = H (P/p_t)^-1; value = sum y_t (P/p_t) - alpha P - H, alpha = floor(sum y_t / p_t)
+        // c2 = H (P/p_t)^-1; value = sum y_t (P/p_t) - alpha P - H, alpha = floor(sum y_t / p_t) (the kernels estimate it from
+        // sum y_t floor(2^60 / p_t): the true fraction lies in (1/4, 3/4))
         std::vector<std::uint32_t> c1;         // [S][2]
         std::vector<std::uint32_t> c2;         // [S]
-        std::vector<float> inv_p;              // [S]
         std::vector<u64> punct_mod_q;          // [k][S]: (P/p_t) mod q_i
         std::vector<u64> neg_mod_q;            // [k][S]: (-(alpha P) - H) mod q_i, alpha < S
     };

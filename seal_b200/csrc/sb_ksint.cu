@@ -46,7 +46,7 @@ namespace sb
 #pragma unroll
         for (int lvl = 0; lvl < LOG; lvl++)
         {
-            const int gap = (1 << (LOG - 1)) >> lvl;
+            const int gap = (1 << (LOG > 0 ? LOG - 1 : 0)) >> lvl;
 #pragma unroll
             for (int g = 0; g < (1 << lvl); g++)
             {
@@ -63,7 +63,7 @@ namespace sb
 #pragma unroll
         for (int lvl = LOG - 1; lvl >= 0; lvl--)
         {
-            const int gap = (1 << (LOG - 1)) >> lvl;
+            const int gap = (1 << (LOG > 0 ? LOG - 1 : 0)) >> lvl;
 #pragma unroll
             for (int g = 0; g < (1 << lvl); g++)
             {
@@ -855,7 +855,7 @@ namespace sb
         d.prm.S = h.S, d.prm.r = h.r, d.prm.logn = c.logn;
         for (int t = 0; t < h.S; t++)
         {
-            d.prm.p[t] = h.p[t], d.prm.mu[t] = h.mu[t], d.prm.c2[t] = h.c2[t], d.prm.inv_p[t] = h.inv_p[t];
+            d.prm.p[t] = h.p[t], d.prm.mu[t] = h.mu[t], d.prm.c2[t] = h.c2[t];
             d.prm.inv60[t] = static_cast<uint32_t>((u64(1) << 60) / h.p[t]);
             d.prm.red[t] = make_uint2(h.red[2 * t], h.red[2 * t + 1]);
             d.prm.c1[t] = make_uint2(h.c1[2 * t], h.c1[2 * t + 1]);
@@ -955,14 +955,23 @@ namespace sb
         // coefficient form of every key row (row % k = its prime), then the digit path's forward transforms: khat[t][row][n]
         u64 *tmp = nullptr;
         cuda_check(cudaMalloc(reinterpret_cast<void **>(&tmp), words * sizeof(u64)), "cudaMalloc(key staging)");
-        cuda_check(cudaMemcpyAsync(tmp, key.d_key, words * sizeof(u64), cudaMemcpyDeviceToDevice, st), "key copy");
-        op_ntt(c, true, c.k, 2, key.digits, tmp, st);
         const bool prof = c.stats.profiling; // a one-time conversion: not part of any timed operation
         c.stats.profiling = false;
-        ksint_forward(c, Src{ tmp, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), key.d_key32,
-                      RowMap{ 2, static_cast<int>(c.k), static_cast<int>(rows) }, st);
+        try
+        {
+            cuda_check(cudaMemcpyAsync(tmp, key.d_key, words * sizeof(u64), cudaMemcpyDeviceToDevice, st), "key copy");
+            op_ntt(c, true, c.k, 2, key.digits, tmp, st);
+            ksint_forward(c, Src{ tmp, 0, nullptr, 0, c.logn }, static_cast<int>(rows), static_cast<int>(rows), key.d_key32,
+                          RowMap{ 2, static_cast<int>(c.k), static_cast<int>(rows) }, st);
+            cuda_check(cudaStreamSynchronize(st), "synchronize");
+        }
+        catch (...)
+        {
+            c.stats.profiling = prof;
+            cudaFree(tmp); // the key's own buffers belong to the handle and go with it
+            throw;
+        }
         c.stats.profiling = prof;
-        cuda_check(cudaStreamSynchronize(st), "synchronize");
         cuda_check(cudaFree(tmp), "cudaFree(key staging)");
     }
 

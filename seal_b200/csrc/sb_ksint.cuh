@@ -30,7 +30,6 @@ namespace sb
         int S = 0, r = 0, logn = 0;
         uint32_t p[kKsMaxS] = {}, mu[kKsMaxS] = {}, c2[kKsMaxS] = {}, inv60[kKsMaxS] = {}; // inv60 = floor(2^60 / p)
         uint2 red[kKsMaxS] = {}, c1[kKsMaxS] = {};
-        float inv_p[kKsMaxS] = {};
     };
 
     struct KsInt
