@@ -13,9 +13,11 @@ the relinearization key once at setup and gathers per-ciphertext digests at the 
   verified  sampled outputs of the TIMED run (both sides of a key-switching chunk boundary, first and last ciphertext) compared
             word for word with the reference's own Evaluator (oracle/_ref); a mismatch aborts the run with a non-zero status
   roofline  SURVEY 8(d) accounting: compulsory bytes of the fused operation (6*L*n*8 per ciphertext + one pass over the key per
-            B_reuse ciphertexts) over the measured time, plus the second ceiling (integer-multiply issue rate) measured in process
-  configs   BASELINE.json configs[1..3] (cfg2 batch multiply+relinearize, cfg3 depth-8 chain, cfg4 rotate sweep): device-resident
-            and end-to-end rates, each with its own verification (N=1 only)
+            B_reuse ciphertexts) over the measured time, the DRAM traffic of the whole step from the committed ncu capture
+            (step_traffic), plus the second ceiling (integer-multiply issue rate: 64-bit and 32-bit butterflies / multiply-accumulates)
+            measured in process
+  configs   BASELINE.json configs[1..3] (cfg2 batch multiply+relinearize, cfg3 depth-8 chain, cfg4 rotate sweep) and the shape the
+            metric text names (n=65536, 16 primes): device-resident and end-to-end rates, each with its own verification (N=1 only)
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, i.e. SEAL 4.4.3 compiled from its sources, HEXL off)
                 on this box's host cores, bounded sample, best of {physical cores, all hardware threads}
 

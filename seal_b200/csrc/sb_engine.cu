@@ -3,7 +3,7 @@
 //
 // Reference behaviour being reproduced (paths under /root/reference/native/src/seal/):
 //   evaluator.cpp:569-708   ckks_multiply            -> ckks_tensor_kernel
-//   evaluator.cpp:2561-2867 switch_key_inplace       -> key_switch(): INTT(target) | digit NTTs | MAC | mod-down
+//   evaluator.cpp:2561-2867 switch_key_inplace       -> key_switch_chunk(): INTT(target) | integer path (sb_ksint.cu) or digit NTTs | MAC | mod-down
 //   evaluator.cpp:1144-1199 relinearize_internal     -> op_relinearize / op_multiply_relinearize
 //   evaluator.cpp:2384-2502 apply_galois_inplace     -> op_apply_galois (permutation fused into the loads)
 //   evaluator.cpp:1201-1294 + rns.cpp:789-901        -> op_rescale / op_mod_switch
