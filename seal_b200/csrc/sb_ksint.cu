@@ -482,10 +482,10 @@ namespace sb
             // The digits are consumed in pairs: the two products that go to one accumulator sit next to each other, so ptxas forms them
             // with zero addends and adds both with ONE three-input 64-bit add (2.0 instructions per multiply-accumulate; one digit at a
             // time costs 3.0, and this kernel is bound by instruction issue: ncu).  The loop is unrolled by the ring depth, so stage
-            // offsets are compile-time constants.  One cp.async group = one pair of digits; three pairs are in flight.
-            auto issue_pair = [&](int stage, int J) { // digits J, J + 1 -> stages `stage`, `stage + 1`
+            // offsets are compile-time constants.  One cp.async group = four digits (two pairs); the next group is in flight.
+            auto issue_quad = [&](int stage, int J) { // digits J .. J + 3 -> stages `stage` .. `stage + 3`: one cp.async group
 #pragma unroll
-                for (int h = 0; h < 2; h++)
+                for (int h = 0; h < 4; h++)
                     if (J + h < L)
                     {
                         uint32_t *dst = ring + (stage + h) * (TB * 512);
@@ -496,50 +496,53 @@ namespace sb
                     }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            issue_pair(0, 0), issue_pair(2, 2), issue_pair(4, 4);
+            static_assert(TB == 4 && TC == 8 && D == 8, "operand fetches are 16-byte reads; the ring holds two groups of four digits");
+            auto pair_step = [&](int stage, const uint32_t *kt, bool both) {
+                uint32_t d0[TB], k0[TC], d1[TB], k1[TC];
+                const uint32_t *src = ring + stage * (TB * 512);
+                const uint4 da = *reinterpret_cast<const uint4 *>(src), db = *reinterpret_cast<const uint4 *>(src + TB * 512);
+                const uint4 ka = *reinterpret_cast<const uint4 *>(kt), kb = *reinterpret_cast<const uint4 *>(kt + 128);
+                const uint4 kc = *reinterpret_cast<const uint4 *>(kt + 1024), kd = *reinterpret_cast<const uint4 *>(kt + 1024 + 128);
+                d0[0] = da.x, d0[1] = da.y, d0[2] = da.z, d0[3] = da.w, d1[0] = db.x, d1[1] = db.y, d1[2] = db.z, d1[3] = db.w;
+                k0[0] = ka.x, k0[1] = ka.y, k0[2] = ka.z, k0[3] = ka.w, k0[4] = kb.x, k0[5] = kb.y, k0[6] = kb.z, k0[7] = kb.w;
+                k1[0] = kc.x, k1[1] = kc.y, k1[2] = kc.z, k1[3] = kc.w, k1[4] = kd.x, k1[5] = kd.y, k1[6] = kd.z, k1[7] = kd.w;
+                if (both)
+                {
+#pragma unroll
+                    for (int i = 0; i < TB; i++)
+#pragma unroll
+                        for (int r = 0; r < TC; r++)
+                        {
+                            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
+                            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d1[i]), "r"(k1[r]));
+                        }
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < TB; i++)
+#pragma unroll
+                        for (int r = 0; r < TC; r++)
+                            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
+                }
+            };
+            issue_quad(0, 0);
             const uint32_t *kt = ktile;
 #pragma unroll 1
             for (int J0 = 0; J0 < L; J0 += D)
             {
 #pragma unroll
-                for (int u = 0; u < D; u += 2)
+                for (int u = 0; u < D; u += 4)
                 {
                     const int J = J0 + u;
                     if (J >= L)
                         break;
-                    issue_pair((u + 6) & (D - 1), J + 6);
-                    asm volatile("cp.async.wait_group 3;" ::: "memory"); // pairs up to this one have landed
-                    static_assert(TB == 4 && TC == 8, "the operand fetches below are 16-byte reads of 4 digit words / 2 x 4 key words");
-                    uint32_t d0[TB], k0[TC], d1[TB], k1[TC];
-                    {
-                        const uint32_t *src = ring + u * (TB * 512);
-                        const uint4 da = *reinterpret_cast<const uint4 *>(src), db = *reinterpret_cast<const uint4 *>(src + TB * 512);
-                        const uint4 ka = *reinterpret_cast<const uint4 *>(kt), kb = *reinterpret_cast<const uint4 *>(kt + 128);
-                        const uint4 kc = *reinterpret_cast<const uint4 *>(kt + 1024), kd = *reinterpret_cast<const uint4 *>(kt + 1024 + 128);
-                        d0[0] = da.x, d0[1] = da.y, d0[2] = da.z, d0[3] = da.w, d1[0] = db.x, d1[1] = db.y, d1[2] = db.z, d1[3] = db.w;
-                        k0[0] = ka.x, k0[1] = ka.y, k0[2] = ka.z, k0[3] = ka.w, k0[4] = kb.x, k0[5] = kb.y, k0[6] = kb.z, k0[7] = kb.w;
-                        k1[0] = kc.x, k1[1] = kc.y, k1[2] = kc.z, k1[3] = kc.w, k1[4] = kd.x, k1[5] = kd.y, k1[6] = kd.z, k1[7] = kd.w;
-                    }
-                    kt += 2048;
-                    if (J + 1 < L)
-                    {
-#pragma unroll
-                        for (int i = 0; i < TB; i++)
-#pragma unroll
-                            for (int r = 0; r < TC; r++)
-                            {
-                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
-                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d1[i]), "r"(k1[r]));
-                            }
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int i = 0; i < TB; i++)
-#pragma unroll
-                            for (int r = 0; r < TC; r++)
-                                asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
-                    }
+                    issue_quad((u + 4) & (D - 1), J + 4);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory"); // the four digits of this step have landed
+                    pair_step(u, kt, J + 1 < L);
+                    if (J + 2 < L)
+                        pair_step(u + 2, kt + 2048, J + 3 < L);
+                    kt += 4096;
                 }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1134,16 +1137,19 @@ namespace sb
         for (int j = 0; j < 16; j++)
             d[(static_cast<size_t>(blockIdx.x) * 16 + j) * 256 + threadIdx.x] = a[j];
     }
-    __global__ void __launch_bounds__(128, 4) ks32_selftest_mac(uint32_t *d, int rounds)
+    // PAIRED: two products per accumulator and round, as the product kernel consumes its digits (ptxas adds both with one three-input
+    // 64-bit add); THREADS x MINB: the launch shape (128 x 4: the register-tile kernel's; 512 x 1: the key-tile kernel's)
+    template <int THREADS, int MINB, bool PAIRED>
+    __global__ void __launch_bounds__(THREADS, MINB) ks32_selftest_mac(uint32_t *d, int rounds)
     {
         uint32_t dv[4], kv[8];
         u64 acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            dv[i] = d[(static_cast<size_t>(blockIdx.x) * 12 + i) * 128 + threadIdx.x] >> 3;
+            dv[i] = d[(static_cast<size_t>(blockIdx.x) * 12 + i) * THREADS + threadIdx.x] >> 3;
 #pragma unroll
         for (int r = 0; r < 8; r++)
-            kv[r] = d[(static_cast<size_t>(blockIdx.x) * 12 + 4 + r) * 128 + threadIdx.x] >> 3;
+            kv[r] = d[(static_cast<size_t>(blockIdx.x) * 12 + 4 + r) * THREADS + threadIdx.x] >> 3;
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -1151,11 +1157,22 @@ namespace sb
                 acc[i][r] = 0;
         for (int q = 0; q < rounds; q++)
         {
+            uint32_t d0[4], k0[8], d1[4], k1[8]; // operands change every round
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                d0[i] = dv[i] + q, d1[i] = dv[i] ^ q;
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                k0[r] = kv[r] ^ q, k1[r] = kv[r] + q;
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int r = 0; r < 8; r++)
-                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(dv[i] + q), "r"(kv[r] ^ q)); // operands change every round
+                {
+                    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d0[i]), "r"(k0[r]));
+                    if (PAIRED)
+                        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][r]) : "r"(d1[i]), "r"(k1[r]));
+                }
         }
         u64 x = 0;
 #pragma unroll
@@ -1163,7 +1180,7 @@ namespace sb
 #pragma unroll
             for (int r = 0; r < 8; r++)
                 x ^= acc[i][r];
-        d[static_cast<size_t>(blockIdx.x) * 12 * 128 + threadIdx.x] = static_cast<uint32_t>(x) ^ static_cast<uint32_t>(x >> 32);
+        d[static_cast<size_t>(blockIdx.x) * 12 * THREADS + threadIdx.x] = static_cast<uint32_t>(x) ^ static_cast<uint32_t>(x >> 32);
     }
     double ksint_selftest_rate(Context &c, int kind, cudaStream_t st)
     {
@@ -1195,9 +1212,21 @@ namespace sb
             ops = static_cast<double>(sms) * 4 * 8 * rounds * 32.0;
             run([&] { ks32_selftest_bfly<1><<<sms * 4, 256, 0, st>>>(d, c.ksint.prm.p[0], rounds); });
             break;
-        case 2: // multiply-accumulates at the product kernel's launch shape (128 threads x 4 CTAs per SM): 32 per thread and round
+        case 2: // multiply-accumulates, one product per accumulator and round, 128 threads x 4 CTAs per SM: 32 per thread and round
             ops = static_cast<double>(sms) * 4 * 4 * rounds * 32.0;
-            run([&] { ks32_selftest_mac<<<sms * 4, 128, 0, st>>>(d, rounds); });
+            run([&] { ks32_selftest_mac<128, 4, false><<<sms * 4, 128, 0, st>>>(d, rounds); });
+            break;
+        case 3: // the same at the key-tile kernel's launch shape (512 threads x 1 CTA per SM)
+            ops = static_cast<double>(sms) * 16 * rounds * 32.0;
+            run([&] { ks32_selftest_mac<512, 1, false><<<sms, 512, 0, st>>>(d, rounds); });
+            break;
+        case 4: // two products per accumulator and round (the product kernel's form), 128 x 4
+            ops = static_cast<double>(sms) * 4 * 4 * rounds * 64.0;
+            run([&] { ks32_selftest_mac<128, 4, true><<<sms * 4, 128, 0, st>>>(d, rounds); });
+            break;
+        case 5: // two products per accumulator and round, 512 x 1
+            ops = static_cast<double>(sms) * 16 * rounds * 64.0;
+            run([&] { ks32_selftest_mac<512, 1, true><<<sms, 512, 0, st>>>(d, rounds); });
             break;
         default: throw std::invalid_argument("unknown selftest");
         }
