@@ -632,7 +632,9 @@ def main():
         ceil = {"fwd_col_shape": ctx.selftest_rate(0), "fwd_fused_shape": ctx.selftest_rate(1), "inverse": ctx.selftest_rate(2),
                 "mac": ctx.selftest_rate(3)}
         if aux_primes:  # the integer key-switching path: 32-bit butterflies and 32x32->64 multiply-accumulates
-            ceil.update({"bfly32_fwd": ctx.selftest_rate(10), "bfly32_inv": ctx.selftest_rate(11), "mac32": ctx.selftest_rate(12)})
+            # mac32: the product kernel's own form and launch shape (two products per accumulator and digit pair, 512 threads x 1 CTA)
+            ceil.update({"bfly32_fwd": ctx.selftest_rate(10), "bfly32_inv": ctx.selftest_rate(11), "mac32": ctx.selftest_rate(15),
+                         "mac32_unpaired_128x4": ctx.selftest_rate(12)})
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, H2D + D2H inside the timed region)
     e2e = None

@@ -132,7 +132,9 @@ int sb200_profile_read_work(sb200_context *ctx, size_t index, char *name, size_t
 int sb200_selftest_rate(sb200_context *ctx, int kind, double *warp_ops_per_second);
 /* the integer key-switching path (SB200_LIMIT_KS_ALGORITHM 1): its work is counted in 32-bit butterflies and 32x32->64-bit
  * multiply-accumulates (sb200_profile_read_work32 = sb200_profile_read_work + those two counters); sb200_selftest_rate kinds
- * 10, 11, 12 measure their ceilings (forward butterflies, inverse butterflies, multiply-accumulates).  The transforms modulo the
+ * 10, 11, 12 measure their ceilings (forward butterflies, inverse butterflies, multiply-accumulates); 13, 14, 15 repeat the
+ * multiply-accumulate loop at the key-tile kernel's launch shape (512 threads, one CTA per SM), with two products per accumulator and
+ * round (the product kernel's form: one three-input 64-bit add per pair), and with both.  The transforms modulo the
  * auxiliary primes are exposed for the parity tests: _info returns the primes (capacity 8), _forward maps rows of n 64-bit
  * words to h_out[prime][row][n] (canonical residues, transformed), _inverse transforms h_data[row][prime][n] in place (values
  * in [0, 2p), not scaled by n^-1). */

@@ -190,7 +190,7 @@ def test_selftest_rates_and_profile_work_counters():
     assert work["ks32_mac"][7] == 2.0 * batch * (L + 1) * L * S5 * n and work["ks32_mac"][5] == 0
     assert work["ks32_fwd_local"][6] == 0.5 * batch * L * S5 * n * 12
     assert work["ks32_inv_local"][6] == 0.5 * batch * 2 * (L + 1) * S5 * n * 12
-    rates = [ctx.selftest_rate(kind) for kind in (10, 11, 12)]
+    rates = [ctx.selftest_rate(kind) for kind in (10, 11, 12, 13, 14, 15)]
     assert all(r > 1e9 for r in rates), rates
     oc = O.Oracle(O.CKKS, n, mods)
     assert (to_np(out[batch - 1]) == oc.multiply_relin(L, to_np(a[batch - 1]), to_np(b[batch - 1]), key)).all()
