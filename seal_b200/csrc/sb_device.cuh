@@ -156,6 +156,12 @@ __device__ __forceinline__ u64 barrett_wide(u64 lo, u64 hi, const PrimeDev &P)
     const u64 r = lo - t * P.q; // in [0, 3q)
     return csub(csub(r, P.q2), P.q);
 }
+// a word of a ciphertext / plaintext the caller handed in: below q for valid objects; anything else is reduced first, so that the
+// dyadic kernels give the reference's result (its Barrett step accepts any 64-bit operands) instead of relying on the range
+__device__ __forceinline__ u64 canon_in(u64 x, const PrimeDev &P)
+{
+    return x < P.q ? x : barrett64(x, P.q, P.ratio_hi);
+}
 // a * b mod q, canonical, for a * b < 2^(b+62) (e.g. both operands below q)
 __device__ __forceinline__ u64 mulmod_wide(u64 a, u64 b, const PrimeDev &P)
 {

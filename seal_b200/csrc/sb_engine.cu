@@ -419,8 +419,10 @@ namespace sb
         const int i = static_cast<int>(r >> logn);
         const PrimeDev P = primes[i];
         const u64 *pa = a + bidx * 2 * poly + r, *pb = b + bidx * 2 * poly + r;
-        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
-        const ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(pb), y1 = *reinterpret_cast<const ulonglong2 *>(pb + poly);
+        ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
+        ulonglong2 y0 = *reinterpret_cast<const ulonglong2 *>(pb), y1 = *reinterpret_cast<const ulonglong2 *>(pb + poly);
+        x0 = make_ulonglong2(canon_in(x0.x, P), canon_in(x0.y, P)), x1 = make_ulonglong2(canon_in(x1.x, P), canon_in(x1.y, P));
+        y0 = make_ulonglong2(canon_in(y0.x, P), canon_in(y0.y, P)), y1 = make_ulonglong2(canon_in(y1.x, P), canon_in(y1.y, P));
         auto mid = [&](u64 p0, u64 p1, u64 q0, u64 q1) {
             u64 lo = 0, hi = 0;
             mac128(lo, hi, p0, q1);
@@ -529,7 +531,8 @@ namespace sb
         const long long bidx = e / poly, r = e % poly;
         const PrimeDev P = primes[static_cast<int>(r >> logn)];
         const u64 *pa = a + bidx * 2 * poly + r;
-        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
+        ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(pa), x1 = *reinterpret_cast<const ulonglong2 *>(pa + poly);
+        x0 = make_ulonglong2(canon_in(x0.x, P), canon_in(x0.y, P)), x1 = make_ulonglong2(canon_in(x1.x, P), canon_in(x1.y, P));
         auto twice = [&](u64 p0, u64 p1) {
             const u64 m = mulmod_wide(p0, p1, P);
             return csub(m + m, P.q);
@@ -624,7 +627,7 @@ namespace sb
         const long long pe = (((b * L + i) << logn) >> 1) + (e & ((1ll << (logn - 1)) - 1));
         const PrimeDev &P = primes[i];
         const ulonglong2 x = a[e], y = plain[pe];
-        out[e] = make_ulonglong2(mulmod_wide(x.x, y.x, P), mulmod_wide(x.y, y.y, P)); // residues below q: one-word Barrett applies
+        out[e] = make_ulonglong2(mulmod_wide(canon_in(x.x, P), canon_in(y.x, P), P), mulmod_wide(canon_in(x.y, P), canon_in(y.y, P), P));
     }
 
     void op_multiply_plain(Context &c, size_t L, size_t size, size_t batch, const u64 *a, const u64 *plain, u64 *out, cudaStream_t st)

@@ -311,6 +311,33 @@ def test_multiply_plain_vs_reference(scheme):
 
 
 @needs_ref
+def test_dyadic_kernels_accept_unreduced_words_like_the_reference():
+    """the reference's dyadic products (multiply_uint64 + barrett_reduce_128, util/uintarithsmallmod.h) accept any 64-bit operand
+    words; a ciphertext or plaintext whose words are congruent but not reduced must give the reference's words here too (the
+    kernels use a one-word Barrett step that presumes reduced operands, and reduce anything else on the way in)"""
+    n, batch, L = 4096, 3, 2
+    mods = R.coeff_modulus_create(n, [50, 45, 60])
+    rc = R.RefContext(sb().CKKS, n, mods)
+    ctx = sb().Context(sb().CKKS, n, mods)
+    rng = np.random.default_rng(41)
+    a, b = rand_ct(rng, mods, n, 2, L, batch), rand_ct(rng, mods, n, 2, L, batch)
+    plain = rand_ct(rng, mods, n, 1, L, batch)[:, 0]
+    ua, ub, up = a.copy(), b.copy(), plain.copy()
+    for i in range(L):  # add multiples of the prime (still below 2^64) to a third of the words
+        q = np.uint64(mods[i])
+        for arr in (ua[:, :, i, :], ub[:, :, i, :], up[:, i, :]):
+            mask = rng.integers(0, 3, arr.shape) == 0
+            arr[mask] += q * np.uint64((2 ** 63 // mods[i]) - 1)
+    assert (ua >= a).all() and (ua != a).any()
+    got_m, got_s, got_p = ctx.multiply(ua, ub), ctx.square(ua), ctx.multiply_plain(ua, up)
+    for i in range(batch):
+        assert (got_m[i] == rc.multiply(L, a[i], b[i])).all()
+        assert (got_m[i] == rc.multiply(L, ua[i], ub[i])).all(), "the reference itself is insensitive to the representative"
+        assert (got_s[i] == rc.square(L, a[i])).all()
+        assert (got_p[i] == rc.multiply_plain(L, a[i], plain[i])).all()
+
+
+@needs_ref
 @pytest.mark.parametrize("n,bits,t_bits,batch", [(4096, [50, 36, 45, 60], 20, 3), (4096, [50, 36, 45, 60], 38, 2),
                                                   (256, [40, 36, 42, 43], 17, 3), (16384, [54, 54, 54, 54, 54], 20, 2)])
 def test_bgv_ops_vs_reference(n, bits, t_bits, batch):
