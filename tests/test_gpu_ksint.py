@@ -90,7 +90,7 @@ def _keyswitch_case(scheme_name, n, bits, batch, t=0):
 
 
 @pytest.mark.parametrize("n,bits,batch", [(4096, [36, 36, 37], 3), (8192, [50, 50, 50, 51], 5), (16384, [60, 60, 60], 2),
-                                          (32768, [55] * 5, 9)])
+                                          (32768, [55] * 5, 9), (131072, [58, 58, 59], 1)])
 def test_relinearize_integer_path_vs_oracle_ckks(n, bits, batch):
     _keyswitch_case("CKKS", n, bits, batch)
 
