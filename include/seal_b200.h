@@ -148,7 +148,9 @@ int sb200_selftest_ksint_inverse(sb200_context *ctx, uint32_t *h_data, size_t ro
 /* ---- key-switching keys --------------------------------------------------------------------------------------
  * h_key = the flattened KSwitchKeys::data()[index]: [digit j < digits][component 2][key prime k][coeff n], i.e. for
  * each j the PublicKey's ciphertext data (kswitchkeys.h, keygenerator.cpp:327-360).  digits must be >= L of every
- * ciphertext it is used with (evaluator.cpp:2635). */
+ * ciphertext it is used with (evaluator.cpp:2635).  For n >= 4096 the handle also holds the key modulo the context's 29-bit
+ * auxiliary primes in transformed form (2.5x the bytes above, prepared once at creation: INTT of every key row + the small
+ * forward transforms), which is what key switching at levels with >= 6 digits multiplies with (SB200_LIMIT_KS_ALGORITHM). */
 int sb200_kswitch_key_create(sb200_context *ctx, const uint64_t *h_key, size_t digits, sb200_kswitch_key **out);
 int sb200_kswitch_key_destroy(sb200_kswitch_key *key);
 /* KSwitchKeys::load of the single entry data()[index] out of a RelinKeys / GaloisKeys stream saved with
