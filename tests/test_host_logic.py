@@ -344,3 +344,72 @@ def test_ksint_swizzle_conflict_free():
                 phys = [((16 * t) ^ (((t >> 4) & 1) << 4)) + 4 * (h ^ ((t >> 1) & 3)) for t in grp]
                 assert all(p == swz(16 * t + 4 * h) for p, t in zip(phys, grp))
                 assert len({(p // 4) % 8 for p in phys}) == 8
+
+
+@pytest.mark.parametrize("scheme", ["ckks", "bfv"])
+def test_integer_key_switching_identity_vs_oracle(scheme):
+    """the identity the integer key-switching path rests on (seal_b200/csrc/sb_ksint.cuh), checked with Python integers against the
+    oracle's switch_key_inplace restatement at n = 16: the digit sum sum_J NTT_I(d_J) (.) K_JI is the NTT_I image of the INTEGER
+    polynomial sum_J d_J * INTT_I(K_JI) reduced mod q_I; reconstructing that integer from its residues modulo 29-bit primes (with the
+    offset P/2 and alpha = floor(sum y_t / p_t)) and doing the mod-down in coefficient form gives the reference's words"""
+    n, bits = 16, [40, 40, 40, 41]
+    mods = O.coeff_modulus_create(n, bits)
+    k, L = len(mods), len(mods) - 1
+    sid = O.CKKS if scheme == "ckks" else O.BFV
+    oc = O.Oracle(sid, n, mods, 0 if scheme == "ckks" else 65537)
+    rng = np.random.default_rng(5)
+    c3 = np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(L)]) for _ in range(3)])
+    key = np.stack([np.stack([np.stack([rng.integers(0, mods[i], n, dtype=np.uint64) for i in range(k)]) for _ in range(2)])
+                    for _ in range(L)])
+    want = oc.relinearize(L, c3, key)
+
+    def negconv(a, b):
+        r = [0] * n
+        for i in range(n):
+            for j in range(n):
+                if i + j < n:
+                    r[i + j] += a[i] * b[j]
+                else:
+                    r[i + j - n] -= a[i] * b[j]
+        return r
+
+    # digits: coefficient form of the target (CKKS: INTT per prime; BFV: already coefficients)
+    D = [[int(v) for v in (oc.intt_row(J, c3[2][J]) if scheme == "ckks" else c3[2][J])] for J in range(L)]
+    aux, cand = [], ((1 << 29) // (2 * n)) * (2 * n) + 1
+    while len(aux) < 5:  # the largest 29-bit primes = 1 mod 2n, as sbh::build_ksint picks them
+        cand -= 2 * n
+        if all(cand % d for d in range(3, 23171, 2)):
+            aux.append(cand)
+    P = 1
+    for p in aux:
+        P *= p
+    H = (P - 1) // 2
+    assert P > 4 * L * n * max(mods) ** 2
+    qsp, half = int(mods[k - 1]), int(mods[k - 1]) >> 1
+    out = np.zeros((2, L, n), dtype=np.uint64)
+    for comp in range(2):
+        A = {}
+        for I in list(range(L)) + [k - 1]:
+            q = int(mods[I])
+            acc = [0] * n
+            for J in range(L):
+                kI = [int(v) for v in oc.intt_row(I, key[J][comp][I])]
+                acc = [x + y for x, y in zip(acc, negconv(D[J], kI))]
+            res = []
+            for x in range(n):
+                assert abs(acc[x]) < P // 4
+                y = [((acc[x] + H) % p) * pow(P // p, -1, p) % p for p in aux]
+                alpha = sum(yt * ((1 << 60) // p) for yt, p in zip(y, aux)) >> 60  # the kernels' estimate of floor(sum y_t / p_t)
+                assert alpha == sum(yt * (P // p) for yt, p in zip(y, aux)) // P
+                v = (sum(yt * ((P // p) % q) for yt, p in zip(y, aux)) - alpha * (P % q) - H % q) % q
+                assert v == acc[x] % q
+                res.append(v)
+            A[I] = res
+        for i in range(L):
+            q = int(mods[i])
+            inv = pow(qsp, -1, q)
+            r = [((A[i][x] - ((A[k - 1][x] + half) % qsp % q - half % q)) * inv) % q for x in range(n)]
+            if scheme == "ckks":
+                r = [int(v) for v in oc.ntt_row(i, np.array(r, dtype=np.uint64))]
+            out[comp][i] = [(r[x] + int(c3[comp][i][x])) % q for x in range(n)]
+    assert (out == want).all()
