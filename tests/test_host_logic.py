@@ -413,3 +413,27 @@ def test_integer_key_switching_identity_vs_oracle(scheme):
                 r = [int(v) for v in oc.ntt_row(i, np.array(r, dtype=np.uint64))]
             out[comp][i] = [(r[x] + int(c3[comp][i][x])) % q for x in range(n)]
     assert (out == want).all()
+
+
+def test_one_word_barrett_bound():
+    """barrett_wide (seal_b200/csrc/sb_device.cuh): for z < 2^(b+62), b = bit length of q, the quotient estimate
+    floor(floor(z / 2^(b-2)) * floor(2^(b+62) / q) / 2^64) is at most 2 below floor(z / q), so z - t q lies in [0, 3q) and its low
+    64 bits are the whole value: the two conditional subtractions of the kernel canonicalise it.  Python-integer re-enactment."""
+    rng = np.random.default_rng(62)
+    for _ in range(4000):
+        b = int(rng.integers(2, 62))
+        q = int(rng.integers(1 << (b - 1), 1 << b)) | 1
+        if q.bit_length() != b:
+            continue
+        mu, sh = (1 << (b + 62)) // q, b - 2
+        assert mu < 1 << 63
+        for z in (int(rng.integers(0, 1 << 62)) * (1 << b) // (1 << int(rng.integers(0, 62))), (1 << (b + 62)) - 1, q * q - 1 if b <= 61 else 0,
+                  2 * (q - 1) ** 2):
+            if z >= 1 << (b + 62):
+                continue
+            zh = z >> sh
+            assert zh < 1 << 64
+            t = (zh * mu) >> 64
+            r = z - t * q
+            assert 0 <= r < 3 * q and r < 1 << 64, (b, q, z)
+            assert (z & ((1 << 64) - 1)) - ((t * q) & ((1 << 64) - 1)) in (r, r - (1 << 64))  # what the 64-bit subtraction yields
